@@ -1,0 +1,119 @@
+"""ctypes binding of the C-ABI library (include/dualvar_b200.h).
+
+The product path has no CPU or eager fallback: if the shared library is missing, importing any
+compute entry point raises. Build it with ``make`` (or ``python -c "import __graft_entry__ as g;
+g.build()"``) at the repo root; the built ``dualvar_b200/lib/libdualvar_b200.so`` stays in-tree.
+"""
+import ctypes
+import os
+
+import torch
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libdualvar_b200.so")
+_lib = None
+
+
+class DualVarNativeError(RuntimeError):
+    pass
+
+
+class ConvGeom(ctypes.Structure):
+    """Mirror of ``dv_conv_geom``."""
+
+    _fields_ = [(n, ctypes.c_int32) for n in (
+        "N", "T", "H", "W", "Cin", "Cout", "Cin_p", "Cout_p",
+        "kt", "kh", "kw", "st", "sh", "sw", "pt", "ph", "pw", "To", "Ho", "Wo")]
+
+    @property
+    def taps(self):
+        return self.kt * self.kh * self.kw
+
+    def out_positions(self):
+        return self.N * self.To * self.Ho * self.Wo
+
+    def in_positions(self):
+        return self.N * self.T * self.H * self.W
+
+
+def pad8(c):
+    return (int(c) + 7) // 8 * 8
+
+
+def make_geom(N, T, H, W, Cin, Cout, kernel, stride, padding):
+    kt, kh, kw = kernel
+    st, sh, sw = stride
+    pt, ph, pw = padding
+    g = ConvGeom()
+    g.N, g.T, g.H, g.W = N, T, H, W
+    g.Cin, g.Cout, g.Cin_p, g.Cout_p = Cin, Cout, pad8(Cin), pad8(Cout)
+    g.kt, g.kh, g.kw = kt, kh, kw
+    g.st, g.sh, g.sw = st, sh, sw
+    g.pt, g.ph, g.pw = pt, ph, pw
+    g.To = (T + 2 * pt - kt) // st + 1
+    g.Ho = (H + 2 * ph - kh) // sh + 1
+    g.Wo = (W + 2 * pw - kw) // sw + 1
+    return g
+
+
+_P = ctypes.c_void_p
+_SIGNATURES = {
+    "dv_last_error": (ctypes.c_char_p, []),
+    "dv_version": (ctypes.c_int, []),
+    "dv_device_ok": (ctypes.c_int, []),
+    "dv_pack_conv_weight": (ctypes.c_int, [_P, _P, _P, ctypes.POINTER(ConvGeom), _P]),
+    "dv_unpack_conv_wgrad": (ctypes.c_int, [_P, _P, ctypes.POINTER(ConvGeom), ctypes.c_float, _P]),
+    "dv_ncdhw_to_ndhwc_bf16": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, _P]),
+    "dv_ndhwc_bf16_to_ncdhw": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, _P]),
+    "dv_conv3d_fprop_bf16": (ctypes.c_int, [_P, _P, _P, _P, _P, ctypes.POINTER(ConvGeom), _P]),
+    "dv_conv3d_dgrad_bf16": (ctypes.c_int, [_P, _P, _P, ctypes.POINTER(ConvGeom), _P]),
+    "dv_conv3d_wgrad_bf16": (ctypes.c_int, [_P, _P, _P, ctypes.POINTER(ConvGeom), _P]),
+}
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def load():
+    """Load the shared library once; raise loudly if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise DualVarNativeError(
+            f"{_LIB_PATH} is missing: the CUDA extension is not built (run `make` at the repo "
+            "root). dualvar_b200 has no CPU/eager fallback.")
+    lib = ctypes.CDLL(_LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().dv_last_error()
+        raise DualVarNativeError(f"{what} failed (status {rc}): {msg.decode() if msg else ''}")
+
+
+def call(name, *args):
+    """Invoke a C-ABI function that returns a status code; raise on failure."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    check(rc, name)

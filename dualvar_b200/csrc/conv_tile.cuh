@@ -1,0 +1,63 @@
+// Shared definitions for the tcgen05 implicit-GEMM convolution kernels (conv_fprop.cu, conv_wgrad.cu).
+//
+// Data layout in HBM (bf16 mode): activations are NDHWC with the channel count padded to a multiple
+// of 8 (16 bytes) so every TMA stride is 16-byte aligned; pad channels always hold zeros.
+// An im2col row-block is never materialised: an output tile is a (tn x tt x th x tw) = 128-position
+// box of the output tensor, and for filter tap (kt,kh,kw) its A operand is the same box of the
+// input tensor shifted by the tap offset, fetched by ONE 5-D TMA box copy (out-of-bounds = zero
+// padding). Strided convolutions use one tensor map per input parity class so that the box is
+// dense in map coordinates.
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+
+namespace dv {
+
+constexpr int kTileM = 128;        // output positions per tile (= TMEM lanes)
+constexpr int kChunkK = 64;        // bf16 channels per TMA box row (= 128 B, one swizzle span)
+constexpr int kMaxTaps = 152;      // (3,7,7) stem = 147 taps
+constexpr int kMaxAMaps = 8;       // 2 x 2 x 2 stride parities
+constexpr int kMaxBlockN = 256;
+
+struct Tap {
+  int8_t map;    // which a_map (stride parity class)
+  int8_t dt, dh, dw;  // box origin offset in map coordinates
+  int16_t widx;  // tap index in the packed weight tensor
+  int16_t pad_;
+};
+
+struct TileGeom {
+  // tile box (powers of two, product 128) as log2
+  int lw, lh, lt, ln;
+  // number of tiles along each dim and output extents (for row validity)
+  int tiles_w, tiles_h, tiles_t, tiles_n;
+  int ext_w, ext_h, ext_t, ext_n;
+};
+
+struct alignas(64) ConvTileParams {
+  CUtensorMap a_map[kMaxAMaps];
+  CUtensorMap b_map;     // weights [rows=Cout_p][taps][Cin_p], box (64, 1, block_n)
+  CUtensorMap out_map;   // output NDHWC, box (64, tw, th, tt, tn), 128B swizzle
+  Tap taps[kMaxTaps];
+  TileGeom g;
+  int num_taps;
+  int k_chunks;       // ceil(Cin_p / 64)
+  int k_steps_last;   // UMMA K=16 steps in the last chunk (1..4)
+  int n_tiles;        // channel tiles
+  int block_n;        // columns per full channel tile (multiple of 16, <= 256; multiple of 64 if n_tiles > 1)
+  int last_n;         // MMA N of the last channel tile (multiple of 16)
+  int stages;         // smem ring depth
+  int total_tiles;
+  double* stats;      // nullable: [2][stats_ld] per-channel sum and sum of squares (of the stored bf16)
+  int stats_ld;
+  const float* bias;  // nullable: per output channel, added before rounding
+};
+
+// Convolution geometry shared by fprop / dgrad / wgrad host code (padded channel counts).
+struct ConvGeom {
+  int N, T, H, W, Cin_p;   // input
+  int To, Ho, Wo, Cout_p;  // output
+  int kt, kh, kw, st, sh, sw, pt, ph, pw;
+};
+
+}  // namespace dv

@@ -1,0 +1,312 @@
+// tcgen05 / TMEM / TMA implicit-GEMM 3-D convolution weight gradient (wgrad).
+//
+// Replaces cuDNN's wgrad behind autograd of nn.Conv3d on the reference path.
+//   dW[co][tap][ci] = sum over output positions m of  dY[m][co] * X[m shifted by tap][ci]
+// The contraction runs over output positions, which are the slow dimension of both NDHWC operands,
+// so both are fed to tcgen05.mma as MN-major SWIZZLE_128B tiles: a 64-position x 64-channel TMA box
+// is exactly one such tile (row = position = K index, 128 B of channels = M/N index).
+//   A (M side) = X boxes: "units" (tap, 64-channel chunk of Cin); two units form one M=128 MMA
+//   B (N side) = dY boxes: N = up to 256 output channels
+//   D          = fp32 accumulators in TMEM, one per unit pair, all sharing the same dY tile
+// Split-K over position tiles across gridDim.y; partial results are reduced with fp32 red.global
+// into a zero-initialised [Cout_p][taps][Cin_p] buffer.
+#include "conv_tile.cuh"
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace dv {
+
+constexpr int kWgThreads = 192;
+constexpr int kBoxBytes = 64 * 128;  // one 64-position x 64-channel box
+constexpr int kWgMaxUnits = 8;
+constexpr int kWgSmemBudget = 232448 - 2048;
+
+struct alignas(64) WgradParams {
+  CUtensorMap a_map[kMaxAMaps];
+  CUtensorMap dy_map;
+  Tap taps[kMaxTaps];
+  TileGeom g;  // 64-position tiles
+  int num_taps;
+  int k_chunks;     // ceil(Cin_p / 64)
+  int total_units;  // num_taps * k_chunks
+  int units_per_group;
+  int n_tiles, block_n, last_n, acc_stride;
+  int pos_tiles, tiles_per_split;
+  int stages;
+  float* dw;  // [Cout_p][taps_total][Cin_p]
+  int cin_p, cout_p, taps_total;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[8];
+  __shared__ __align__(8) uint64_t empty_bar[8];
+  __shared__ __align__(8) uint64_t acc_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int group = blockIdx.x / p.n_tiles;
+  const int n_tile = blockIdx.x % p.n_tiles;
+  const int unit0 = group * p.units_per_group;
+  const int nu = min(p.units_per_group, p.total_units - unit0);
+  const int npairs = (nu + 1) >> 1;
+  const int bn = (n_tile == p.n_tiles - 1) ? p.last_n : p.block_n;
+  const int nbx = (bn + 63) >> 6;  // dY boxes
+  const int tile_begin = blockIdx.y * p.tiles_per_split;
+  const int tile_end = min(p.pos_tiles, tile_begin + p.tiles_per_split);
+  if (tile_begin >= tile_end) return;  // uniform per CTA
+
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const int a_bytes = p.units_per_group * kBoxBytes;
+  const int b_bytes = ((p.block_n + 63) >> 6) * kBoxBytes;
+  const int stage_bytes = a_bytes + b_bytes;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(&acc_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_slot;
+  const TileGeom& g = p.g;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx = (nu + nbx) * kBoxBytes;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        int m_id = tile;
+        const int wb = m_id % g.tiles_w; m_id /= g.tiles_w;
+        const int hb = m_id % g.tiles_h; m_id /= g.tiles_h;
+        const int tb = m_id % g.tiles_t; m_id /= g.tiles_t;
+        const int nb = m_id;
+        const int w0 = wb << g.lw, h0 = hb << g.lh, t0 = tb << g.lt, n0 = nb << g.ln;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], tx);
+        uint8_t* a_s = smem + stage * stage_bytes;
+        uint8_t* b_s = a_s + a_bytes;
+        for (int j = 0; j < nbx; ++j)
+          tma_load_5d(b_s + j * kBoxBytes, &p.dy_map, &full_bar[stage],
+                      n_tile * p.block_n + j * 64, w0, h0, t0, n0);
+        for (int i = 0; i < nu; ++i) {
+          const int u = unit0 + i;
+          const int tap = u / p.k_chunks;
+          const int kc = u - tap * p.k_chunks;
+          const Tap tp = p.taps[tap];
+          tma_load_5d(a_s + i * kBoxBytes, &p.a_map[tp.map], &full_bar[stage], kc * 64,
+                      w0 + tp.dw, h0 + tp.dh, t0 + tp.dt, n0);
+        }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, bn, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after_sync();
+        const uint32_t a_s = smem_u32(smem + stage * stage_bytes);
+        const uint32_t b_s = a_s + a_bytes;
+        for (int pr = 0; pr < npairs; ++pr) {
+          for (int k = 0; k < 4; ++k) {
+            // MN-major: 8-position groups 1024 B apart (SBO), 64-channel groups one box apart (LBO)
+            const uint64_t adesc = make_smem_desc(a_s + pr * 2 * kBoxBytes + k * 2048, kBoxBytes, 1024);
+            const uint64_t bdesc = make_smem_desc(b_s + k * 2048, kBoxBytes, 1024);
+            umma_bf16(tmem_base + pr * p.acc_stride, adesc, bdesc, idesc,
+                      (tile != tile_begin) || (k != 0));
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&acc_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    mbar_wait(&acc_bar, 0);
+    tc_fence_after_sync();
+    const int co0 = n_tile * p.block_n;
+    for (int pr = 0; pr < npairs; ++pr) {
+      const int i = pr * 2 + (row >> 6);
+      const bool unit_ok = i < nu;
+      int tapw = 0, ci = 0;
+      if (unit_ok) {
+        const int u = unit0 + i;
+        const int tap = u / p.k_chunks;
+        const int kc = u - tap * p.k_chunks;
+        tapw = p.taps[tap].widx;
+        ci = kc * 64 + (row & 63);
+      }
+      const bool row_ok = unit_ok && ci < p.cin_p;
+      float* dst = p.dw + (size_t)tapw * p.cin_p + ci;
+      const size_t co_stride = (size_t)p.taps_total * p.cin_p;
+      const uint32_t t_addr = tmem_base + pr * p.acc_stride + (static_cast<uint32_t>(q * 32) << 16);
+      for (int gi = 0; gi < (bn >> 4); ++gi) {
+        uint32_t v[16];
+        tmem_ld16(t_addr + gi * 16, v);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int co = co0 + gi * 16 + j;
+            if (co < p.cout_p) atomicAdd(dst + (size_t)co * co_stride, __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------ host
+void choose_tile_log2(int total_log2, int N, int T, int H, int W, int* ln, int* lt, int* lh, int* lw) {
+  double best = 1e30;
+  for (int a = 0; a <= total_log2; ++a)
+    for (int b = 0; a + b <= total_log2; ++b)
+      for (int c = 0; a + b + c <= total_log2; ++c) {
+        const int d = total_log2 - a - b - c;
+        const int tw = 1 << a, th = 1 << b, tt = 1 << c, tn = 1 << d;
+        const double vol = (double)round_up(W, tw) * round_up(H, th) * round_up(T, tt) * round_up(N, tn);
+        const double cost = vol * (1.0 + 0.02 * (total_log2 - a) + 0.004 * (total_log2 - a - b));
+        if (cost < best) { best = cost; *lw = a; *lh = b; *lt = c; *ln = d; }
+      }
+}
+
+static int floordiv_w(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+static int posmod_w(int a, int b) { int m = a % b; return m < 0 ? m + b : m; }
+
+int conv_wgrad_bf16(const void* x, const void* dy, float* dw, const ConvGeom& c,
+                    cudaStream_t stream) {
+  static thread_local WgradParams P;
+  const int taps_total = c.kt * c.kh * c.kw;
+  DV_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)c.Cout_p * taps_total * c.Cin_p, stream));
+
+  TileGeom& g = P.g;
+  choose_tile_log2(6, c.N, c.To, c.Ho, c.Wo, &g.ln, &g.lt, &g.lh, &g.lw);
+  g.ext_w = c.Wo; g.ext_h = c.Ho; g.ext_t = c.To; g.ext_n = c.N;
+  g.tiles_w = ceil_div(c.Wo, 1 << g.lw);
+  g.tiles_h = ceil_div(c.Ho, 1 << g.lh);
+  g.tiles_t = ceil_div(c.To, 1 << g.lt);
+  g.tiles_n = ceil_div(c.N, 1 << g.ln);
+  const uint32_t box[5] = {64, 1u << g.lw, 1u << g.lh, 1u << g.lt, 1u << g.ln};
+
+  auto encode5 = [&](CUtensorMap* m, const void* base, const long long dim[5], const long long str[5]) {
+    uint64_t dims[5], strides[5];
+    for (int i = 0; i < 5; ++i) { dims[i] = (uint64_t)dim[i]; strides[i] = (uint64_t)str[i] * 2; }
+    return encode_tmap(m, base, 2, 5, dims, strides, box, true);
+  };
+  const long long xdim[5] = {c.Cin_p, c.W, c.H, c.T, c.N};
+  const long long xstr[5] = {1, c.Cin_p, (long long)c.W * c.Cin_p, (long long)c.H * c.W * c.Cin_p,
+                             (long long)c.T * c.H * c.W * c.Cin_p};
+  const long long ydim[5] = {c.Cout_p, c.Wo, c.Ho, c.To, c.N};
+  const long long ystr[5] = {1, c.Cout_p, (long long)c.Wo * c.Cout_p, (long long)c.Ho * c.Wo * c.Cout_p,
+                             (long long)c.To * c.Ho * c.Wo * c.Cout_p};
+  int rc = encode5(&P.dy_map, dy, ydim, ystr);
+  if (rc) return rc;
+
+  int map_of_parity[8];
+  for (int i = 0; i < 8; ++i) map_of_parity[i] = -1;
+  int nmaps = 0, ntaps = 0;
+  for (int a = 0; a < c.kt; ++a)
+    for (int b = 0; b < c.kh; ++b)
+      for (int d = 0; d < c.kw; ++d) {
+        const int ot = a - c.pt, oh = b - c.ph, ow = d - c.pw;
+        const int rt = posmod_w(ot, c.st), rh = posmod_w(oh, c.sh), rw = posmod_w(ow, c.sw);
+        if (rt > 1 || rh > 1 || rw > 1) return fail(kUnsupported, "conv stride > 2 not supported");
+        if (rt >= c.T || rh >= c.H || rw >= c.W) continue;
+        const int key = (rt * 2 + rh) * 2 + rw;
+        if (map_of_parity[key] < 0) {
+          long long dim[5], str[5];
+          for (int i = 0; i < 5; ++i) { dim[i] = xdim[i]; str[i] = xstr[i]; }
+          const uint8_t* bp = static_cast<const uint8_t*>(x);
+          const int rr[3] = {rw, rh, rt};
+          const int ss[3] = {c.sw, c.sh, c.st};
+          for (int i = 0; i < 3; ++i) {
+            bp += (long long)rr[i] * str[1 + i] * 2;
+            dim[1 + i] = (dim[1 + i] - rr[i] + ss[i] - 1) / ss[i];
+            str[1 + i] *= ss[i];
+          }
+          rc = encode5(&P.a_map[nmaps], bp, dim, str);
+          if (rc) return rc;
+          map_of_parity[key] = nmaps++;
+        }
+        Tap& tp = P.taps[ntaps++];
+        tp.map = (int8_t)map_of_parity[key];
+        tp.dt = (int8_t)floordiv_w(ot, c.st);
+        tp.dh = (int8_t)floordiv_w(oh, c.sh);
+        tp.dw = (int8_t)floordiv_w(ow, c.sw);
+        tp.widx = (int16_t)((a * c.kh + b) * c.kw + d);
+        tp.pad_ = 0;
+      }
+  if (ntaps == 0) return kOk;
+  for (int i = nmaps; i < kMaxAMaps; ++i) P.a_map[i] = P.a_map[0];
+  P.num_taps = ntaps;
+  P.k_chunks = ceil_div(c.Cin_p, 64);
+  P.total_units = ntaps * P.k_chunks;
+  // N side (Cout)
+  if (c.Cout_p <= 256) {
+    P.n_tiles = 1; P.block_n = round_up(c.Cout_p, 16); P.last_n = P.block_n;
+  } else {
+    P.block_n = 256; P.n_tiles = ceil_div(c.Cout_p, 256);
+    P.last_n = round_up(c.Cout_p - (P.n_tiles - 1) * 256, 16);
+  }
+  P.acc_stride = round_up(P.block_n, 32);
+  const int nbx = ceil_div(P.block_n, 64);
+  int max_pairs = 512 / P.acc_stride;
+  int upg = max_pairs * 2;
+  if (upg > kWgMaxUnits) upg = kWgMaxUnits;
+  // keep at least 3 stages in shared memory
+  while (upg > 2 && (kWgSmemBudget - 1024) / ((upg + nbx) * kBoxBytes) < 3) upg -= 2;
+  if (upg > P.total_units) upg = P.total_units;
+  P.units_per_group = upg;
+  const int groups = ceil_div(P.total_units, upg);
+  const int stage_bytes = (upg + nbx) * kBoxBytes;
+  P.stages = (kWgSmemBudget - 1024) / stage_bytes;
+  if (P.stages > 8) P.stages = 8;
+  if (P.stages < 2) return fail(kUnsupported, "wgrad: stage too large for shared memory");
+  P.pos_tiles = g.tiles_w * g.tiles_h * g.tiles_t * g.tiles_n;
+  const int items = groups * P.n_tiles;
+  int ksplit = (2 * sm_count()) / items;
+  if (ksplit < 1) ksplit = 1;
+  if (ksplit > P.pos_tiles) ksplit = P.pos_tiles;
+  P.tiles_per_split = ceil_div(P.pos_tiles, ksplit);
+  ksplit = ceil_div(P.pos_tiles, P.tiles_per_split);
+  P.dw = dw;
+  P.cin_p = c.Cin_p; P.cout_p = c.Cout_p; P.taps_total = taps_total;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    DV_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kWgSmemBudget));
+    attr_set = true;
+  }
+  const int smem_bytes = 1024 + P.stages * stage_bytes;
+  dim3 grid(items, ksplit);
+  conv_wgrad_kernel<<<grid, kWgThreads, smem_bytes, stream>>>(P);
+  DV_LAUNCH_OK();
+  return kOk;
+}
+
+}  // namespace dv
