@@ -6,6 +6,7 @@ g.build()"``) at the repo root; the built ``dualvar_b200/lib/libdualvar_b200.so`
 """
 import ctypes
 import os
+import re
 
 import torch
 
@@ -56,18 +57,32 @@ def make_geom(N, T, H, W, Cin, Cout, kernel, stride, padding):
 
 
 _P = ctypes.c_void_p
-_SIGNATURES = {
-    "dv_last_error": (ctypes.c_char_p, []),
-    "dv_version": (ctypes.c_int, []),
-    "dv_device_ok": (ctypes.c_int, []),
-    "dv_pack_conv_weight": (ctypes.c_int, [_P, _P, _P, ctypes.POINTER(ConvGeom), _P]),
-    "dv_unpack_conv_wgrad": (ctypes.c_int, [_P, _P, ctypes.POINTER(ConvGeom), ctypes.c_float, _P]),
-    "dv_ncdhw_to_ndhwc_bf16": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, _P]),
-    "dv_ndhwc_bf16_to_ncdhw": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, _P]),
-    "dv_conv3d_fprop_bf16": (ctypes.c_int, [_P, _P, _P, _P, _P, ctypes.POINTER(ConvGeom), _P]),
-    "dv_conv3d_dgrad_bf16": (ctypes.c_int, [_P, _P, _P, ctypes.POINTER(ConvGeom), _P]),
-    "dv_conv3d_wgrad_bf16": (ctypes.c_int, [_P, _P, _P, ctypes.POINTER(ConvGeom), _P]),
-}
+_HEADER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "dualvar_b200.h")
+_SCALARS = {"int": ctypes.c_int, "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64,
+            "float": ctypes.c_float, "double": ctypes.c_double}
+
+
+def _parse_header(path=_HEADER):
+    """Derive the ctypes signatures from the public header so the binding cannot drift from it."""
+    text = open(path).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    sigs = {}
+    for m in re.finditer(r"\b(int|const char\*)\s+(dv_\w+)\s*\(([^)]*)\)\s*;", text):
+        ret, name, args = m.group(1), m.group(2), m.group(3).strip()
+        argtypes = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = " ".join(a.split())
+                if "*" in a:
+                    argtypes.append(_P)
+                else:
+                    base = a.replace("const ", "").split(" ")[0]
+                    argtypes.append(_SCALARS[base])
+        sigs[name] = (ctypes.c_char_p if "char" in ret else ctypes.c_int, argtypes)
+    return sigs
+
+
+_SIGNATURES = _parse_header()
 
 
 def lib_path():

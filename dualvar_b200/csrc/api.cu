@@ -19,6 +19,51 @@ int unpack_wgrad(const float* dwp, float* dw, int Cout, int Cin, int taps, int C
                  cudaStream_t stream);
 int ncdhw_to_ndhwc(const float* x, void* y, int N, int C, int Cp, long long S, cudaStream_t stream);
 int ndhwc_to_ncdhw(const void* y, float* x, int N, int C, int Cp, long long S, cudaStream_t stream);
+
+int bn_finalize(const double* stats, const float* gamma, const float* beta, float* running_mean,
+                float* running_var, float* ss, float* saved, int C, int Cp, double count, float eps,
+                float momentum, int training, cudaStream_t stream);
+int bn_apply(const void* y1, const float* ss1, const void* y2, const float* ss2, const void* res,
+             void* out, long long rows, int Cp, int out_ld, int out_coff, int relu, cudaStream_t stream);
+int bn_bwd_reduce(const void* dout, const void* out, const void* y, double* sums, long long rows,
+                  int Cp, int o_ld, int o_coff, int relu, cudaStream_t stream);
+int bn_bwd_finalize(const double* sums_local, const double* sums_global, const float* gamma,
+                    const float* saved, float* dgamma, float* dbeta, float* coef, int C, int Cp,
+                    double count_global, float grad_beta, cudaStream_t stream);
+int bn_bwd_apply(const void* dout, const void* out, const void* y, const float* coef, void* dy,
+                 void* g_out, long long rows, int Cp, int o_ld, int o_coff, int relu, cudaStream_t stream);
+int add_bf16(const void* a, const void* b, void* out, long long n, cudaStream_t stream);
+struct PoolGeom {
+  int N, T, H, W, To, Ho, Wo, Cp;
+  int kt, kh, kw, st, sh, sw, pt, ph, pw;
+};
+int avgpool_fwd(const void* x, float* out, int N, int S, int C, int Cp, int ld_out, cudaStream_t stream);
+int avgpool_bwd(const float* dout, void* dx, int N, int S, int C, int Cp, int ld_out, cudaStream_t stream);
+int maxpool_fwd(const void* x, void* y, const PoolGeom& g, cudaStream_t stream);
+int maxpool_bwd(const void* x, const void* y, const void* dy, void* dx, const PoolGeom& g, cudaStream_t stream);
+int ingest(const float* src, void* dst, const int* perm, long long sb, long long sv, long long sc,
+           long long st, int B, int C, int T, int H, int W, int view, int n_series, const float* mean,
+           const float* stdv, cudaStream_t stream);
+int sgemm(int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
+          int ldb, float beta, float* C, int ldc, const float* bias, int relu, cudaStream_t stream);
+int colsum(const float* X, float* out, int M, int N, int ld, float beta, cudaStream_t stream);
+int relu_bwd(const float* dy, const float* y, float* dx, long long n, cudaStream_t stream);
+int l2norm_fwd(const float* x, float* y, float* inv_norm, long long rows, int d, float eps, cudaStream_t stream);
+int l2norm_bwd(const float* dy, const float* y, const float* inv_norm, float* dx, long long rows, int d,
+               cudaStream_t stream);
+int contrast_rows(float* S, float* logits, const int* self_col, const int* pos_col, int R, int C,
+                  int ld_s, int ld_logits, float inv_T, float grad_scale, float* loss_sum, int* hits,
+                  cudaStream_t stream);
+int rank_loss(const float* a, const float* b, float* da, float* db, float* logits, float* loss_sum,
+              int* hits, int B, int s, int e, float theta, float clip_max, float weight, cudaStream_t stream);
+int permute_segments(const float* in, float* out, const int* perm, int B, int s, int e, int inverse,
+                     cudaStream_t stream);
+int segment_sum(const float* in, float* out, long long rows, int s, int e, float scale, cudaStream_t stream);
+int segment_bcast(const float* in, float* out, long long rows, int s, int e, float scale, float beta,
+                  cudaStream_t stream);
+int rowdot(const float* a, const float* b, float* out, int rows, int d, int ld_out, cudaStream_t stream);
+int row_axpy(const float* alpha, int ld_alpha, const float* x, float* y, int rows, int d, float beta,
+             cudaStream_t stream);
 }  // namespace dv
 
 using namespace dv;
@@ -106,6 +151,134 @@ int dv_conv3d_wgrad_bf16(const void* x, const void* dy, float* dw_packed, const 
   if (int rc = check_geom(g)) return rc;
   DV_REQUIRE(x && dy && dw_packed, "NULL tensor pointer");
   return conv_wgrad_bf16(x, dy, dw_packed, to_geom<ConvGeom>(g), (cudaStream_t)stream);
+}
+
+#define ST ((cudaStream_t)stream)
+int dv_bn_finalize(const double* stats, const float* gamma, const float* beta, float* running_mean,
+                   float* running_var, float* scale_shift, float* saved, int C, int Cp, double count,
+                   float eps, float momentum, int training, void* stream) {
+  DV_REQUIRE(gamma && beta && scale_shift && C > 0 && Cp >= C && Cp % 8 == 0, "bad bn_finalize arguments");
+  DV_REQUIRE(training ? (stats != nullptr && count > 0) : (running_mean && running_var),
+             "bn_finalize: training needs stats, eval needs running statistics");
+  return bn_finalize(stats, gamma, beta, running_mean, running_var, scale_shift, saved, C, Cp, count, eps,
+                     momentum, training, ST);
+}
+int dv_bn_apply(const void* y1, const float* ss1, const void* y2, const float* ss2, const void* res,
+                void* out, int64_t rows, int Cp, int out_ld, int out_coff, int relu, void* stream) {
+  DV_REQUIRE(y1 && ss1 && out && rows > 0 && Cp % 8 == 0 && out_ld % 8 == 0 && out_coff % 8 == 0,
+             "bad bn_apply arguments");
+  DV_REQUIRE((y2 == nullptr) == (ss2 == nullptr), "bn_apply: y2 and ss2 go together");
+  return bn_apply(y1, ss1, y2, ss2, res, out, rows, Cp, out_ld, out_coff, relu, ST);
+}
+int dv_bn_bwd_reduce(const void* dout, const void* out, const void* y, double* sums, int64_t rows,
+                     int Cp, int o_ld, int o_coff, int relu, void* stream) {
+  DV_REQUIRE(dout && y && sums && (!relu || out) && rows > 0 && Cp % 8 == 0, "bad bn_bwd_reduce arguments");
+  return bn_bwd_reduce(dout, out, y, sums, rows, Cp, o_ld, o_coff, relu, ST);
+}
+int dv_bn_bwd_finalize(const double* sums_local, const double* sums_global, const float* gamma,
+                       const float* saved, float* dgamma, float* dbeta, float* coef, int C, int Cp,
+                       double count_global, float grad_beta, void* stream) {
+  DV_REQUIRE(sums_local && sums_global && gamma && saved && coef && count_global > 0, "bad bn_bwd_finalize arguments");
+  return bn_bwd_finalize(sums_local, sums_global, gamma, saved, dgamma, dbeta, coef, C, Cp, count_global,
+                         grad_beta, ST);
+}
+int dv_bn_bwd_apply(const void* dout, const void* out, const void* y, const float* coef, void* dy,
+                    void* g_out, int64_t rows, int Cp, int o_ld, int o_coff, int relu, void* stream) {
+  DV_REQUIRE(dout && y && coef && dy && (!relu || out) && rows > 0 && Cp % 8 == 0, "bad bn_bwd_apply arguments");
+  return bn_bwd_apply(dout, out, y, coef, dy, g_out, rows, Cp, o_ld, o_coff, relu, ST);
+}
+int dv_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream) {
+  DV_REQUIRE(a && b && out && n > 0 && n % 8 == 0, "bad add_bf16 arguments");
+  return add_bf16(a, b, out, n, ST);
+}
+int dv_avgpool_fwd(const void* x, float* out, int N, int S, int C, int Cp, int ld_out, void* stream) {
+  DV_REQUIRE(x && out && N > 0 && S > 0 && C > 0 && Cp >= C && ld_out >= C, "bad avgpool arguments");
+  return avgpool_fwd(x, out, N, S, C, Cp, ld_out, ST);
+}
+int dv_avgpool_bwd(const float* dout, void* dx, int N, int S, int C, int Cp, int ld_out, void* stream) {
+  DV_REQUIRE(dout && dx && N > 0 && S > 0 && C > 0 && Cp >= C && ld_out >= C, "bad avgpool arguments");
+  return avgpool_bwd(dout, dx, N, S, C, Cp, ld_out, ST);
+}
+static PoolGeom to_pool(const dv_pool_geom* g) {
+  PoolGeom p;
+  p.N = g->N; p.T = g->T; p.H = g->H; p.W = g->W; p.To = g->To; p.Ho = g->Ho; p.Wo = g->Wo; p.Cp = g->Cp;
+  p.kt = g->kt; p.kh = g->kh; p.kw = g->kw; p.st = g->st; p.sh = g->sh; p.sw = g->sw;
+  p.pt = g->pt; p.ph = g->ph; p.pw = g->pw;
+  return p;
+}
+int dv_maxpool3d_fwd(const void* x, void* y, const dv_pool_geom* g, void* stream) {
+  DV_REQUIRE(x && y && g && g->Cp % 8 == 0, "bad maxpool arguments");
+  return maxpool_fwd(x, y, to_pool(g), ST);
+}
+int dv_maxpool3d_bwd(const void* x, const void* y, const void* dy, void* dx, const dv_pool_geom* g,
+                     void* stream) {
+  DV_REQUIRE(x && y && dy && dx && g && g->Cp % 8 == 0, "bad maxpool arguments");
+  return maxpool_bwd(x, y, dy, dx, to_pool(g), ST);
+}
+int dv_ingest_clips(const float* src, void* dst, const int32_t* perm, int64_t sb, int64_t sv, int64_t sc,
+                    int64_t st, int B, int C, int T, int H, int W, int view, int n_series,
+                    const float* mean_host, const float* std_host, void* stream) {
+  DV_REQUIRE(src && dst && B > 0 && C > 0 && C <= 4 && T > 0 && H > 0 && W > 0, "bad ingest arguments");
+  DV_REQUIRE(perm == nullptr || (n_series > 0 && T % n_series == 0), "ingest: T must divide into n_series segments");
+  return ingest(src, dst, perm, sb, sv, sc, st, B, C, T, H, W, view, n_series, mean_host, std_host, ST);
+}
+int dv_sgemm(int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
+             int ldb, float beta, float* C, int ldc, const float* bias, int relu, void* stream) {
+  DV_REQUIRE(A && B && C && K > 0, "bad sgemm arguments");
+  return sgemm(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, relu, ST);
+}
+int dv_colsum(const float* X, float* out, int M, int N, int ld, float beta, void* stream) {
+  DV_REQUIRE(X && out && M > 0 && N > 0, "bad colsum arguments");
+  return colsum(X, out, M, N, ld, beta, ST);
+}
+int dv_relu_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream) {
+  DV_REQUIRE(dy && y && dx && n > 0, "bad relu_bwd arguments");
+  return relu_bwd(dy, y, dx, n, ST);
+}
+int dv_l2norm_fwd(const float* x, float* y, float* inv_norm, int64_t rows, int d, float eps, void* stream) {
+  DV_REQUIRE(x && y && rows > 0 && d > 0, "bad l2norm arguments");
+  return l2norm_fwd(x, y, inv_norm, rows, d, eps, ST);
+}
+int dv_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, float* dx, int64_t rows, int d,
+                  void* stream) {
+  DV_REQUIRE(dy && y && inv_norm && dx && rows > 0 && d > 0, "bad l2norm arguments");
+  return l2norm_bwd(dy, y, inv_norm, dx, rows, d, ST);
+}
+int dv_contrast_rows(float* S, float* logits, const int32_t* self_col, const int32_t* pos_col, int R,
+                     int C, int ld_s, int ld_logits, float inv_T, float grad_scale, float* loss_sum,
+                     int32_t* hits, void* stream) {
+  DV_REQUIRE(S && pos_col && loss_sum && R > 0 && C > 1, "bad contrast_rows arguments");
+  return contrast_rows(S, logits, self_col, pos_col, R, C, ld_s, ld_logits, inv_T, grad_scale, loss_sum,
+                       hits, ST);
+}
+int dv_rank_loss(const float* a, const float* b, float* da, float* db, float* logits, float* loss_sum,
+                 int32_t* hits, int B, int s, int e, float theta, float clip_max, float weight,
+                 void* stream) {
+  DV_REQUIRE(a && b && da && db && loss_sum && B > 0 && s > 1 && e > 0 && theta > 0, "bad rank_loss arguments");
+  return rank_loss(a, b, da, db, logits, loss_sum, hits, B, s, e, theta, clip_max, weight, ST);
+}
+int dv_permute_segments(const float* in, float* out, const int32_t* perm, int B, int s, int e,
+                        int inverse, void* stream) {
+  DV_REQUIRE(in && out && perm && in != out, "bad permute_segments arguments");
+  return permute_segments(in, out, perm, B, s, e, inverse, ST);
+}
+int dv_segment_sum(const float* in, float* out, int64_t rows, int s, int e, float scale, void* stream) {
+  DV_REQUIRE(in && out && rows > 0, "bad segment_sum arguments");
+  return segment_sum(in, out, rows, s, e, scale, ST);
+}
+int dv_segment_bcast(const float* in, float* out, int64_t rows, int s, int e, float scale, float beta,
+                     void* stream) {
+  DV_REQUIRE(in && out && rows > 0, "bad segment_bcast arguments");
+  return segment_bcast(in, out, rows, s, e, scale, beta, ST);
+}
+int dv_rowdot(const float* a, const float* b, float* out, int rows, int d, int ld_out, void* stream) {
+  DV_REQUIRE(a && b && out && rows > 0, "bad rowdot arguments");
+  return rowdot(a, b, out, rows, d, ld_out, ST);
+}
+int dv_row_axpy(const float* alpha, int ld_alpha, const float* x, float* y, int rows, int d, float beta,
+                void* stream) {
+  DV_REQUIRE(alpha && x && y && rows > 0, "bad row_axpy arguments");
+  return row_axpy(alpha, ld_alpha, x, y, rows, d, beta, ST);
 }
 
 }  // extern "C"

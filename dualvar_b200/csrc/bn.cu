@@ -1,0 +1,350 @@
+// BatchNorm3d (training and eval mode) around the convolutions, on bf16 NDHWC activations.
+//
+// Replaces ATen native_batch_norm / SyncBatchNorm + ReLU + residual add on the reference path
+// (reference: nn.BatchNorm3d / nn.ReLU / `x + res` in backbone/r21d.py:56-57,106-122,
+//  backbone/r3d.py:74-89, backbone/c3d.py:16-46, backbone/s3dg.py:16-27,44-64).
+//
+// Forward : the conv epilogue already produced per-channel sum / sum-of-squares (double).
+//           bn_finalize turns them into (scale, shift) + saved (mean, invstd) and updates the
+//           running statistics; bn_apply computes  out = relu?(s1*y1+b1 [+ s2*y2+b2] [+ res]).
+// Backward: bn_bwd_reduce  -> per-channel  sum(g), sum(g*y)   with g = dout * (out > 0)
+//           bn_bwd_finalize-> dgamma, dbeta and the coefficients of dy = A*g + B*y + C
+//           bn_bwd_apply   -> dy (bf16) and optionally g itself (gradient of the residual branch).
+// All passes are HBM-bound: 16-byte vector accesses, one thread owns 8 consecutive channels so the
+// per-channel coefficients sit in registers; a CTA covers (channel groups) x (rows) so that a warp
+// reads contiguous memory.
+#include <cuda_bf16.h>
+
+#include "host_common.h"
+
+namespace dv {
+
+struct Vec8 {
+  float v[8];
+};
+
+__device__ __forceinline__ Vec8 load8(const __nv_bfloat16* p) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+  Vec8 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    r.v[2 * i] = f.x;
+    r.v[2 * i + 1] = f.y;
+  }
+  return r;
+}
+
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const Vec8& r) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(r.v[2 * i], r.v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+__device__ __forceinline__ Vec8 loadf8(const float* p) {
+  Vec8 r;
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+
+// ------------------------------------------------------------------------------ finalize
+// stats: [2][Cp] double (sum, sumsq) over `count` elements per channel.
+// ss: [2][Cp] float (scale, shift) for bn_apply; saved: [2][Cp] float (mean, invstd).
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float* __restrict__ ss,
+                                   float* __restrict__ saved, int C, int Cp, double count, float eps,
+                                   float momentum, int training) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cp) return;
+  if (c >= C) {
+    ss[c] = 0.f; ss[Cp + c] = 0.f;
+    if (saved) { saved[c] = 0.f; saved[Cp + c] = 0.f; }
+    return;
+  }
+  float mean, invstd;
+  if (training) {
+    const double m = stats[c] / count;
+    double var = stats[Cp + c] / count - m * m;
+    if (var < 0.0) var = 0.0;
+    mean = (float)m;
+    invstd = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+      const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+  } else {
+    mean = running_mean[c];
+    invstd = rsqrtf(running_var[c] + eps);
+  }
+  const float sc = gamma[c] * invstd;
+  ss[c] = sc;
+  ss[Cp + c] = beta[c] - mean * sc;
+  if (saved) { saved[c] = mean; saved[Cp + c] = invstd; }
+}
+
+// ------------------------------------------------------------------------------ apply
+struct ApplyArgs {
+  const __nv_bfloat16* y1; const float* ss1;
+  const __nv_bfloat16* y2; const float* ss2;   // optional second normalised input
+  const __nv_bfloat16* res;                    // optional plain residual
+  __nv_bfloat16* out;
+  long long rows;
+  int Cp;       // channels (padded) of y1/y2/res rows
+  int out_ld;   // channel stride of out rows (>= Cp; concat destination)
+  int out_coff; // channel offset inside out rows
+  int relu;
+};
+
+__global__ void __launch_bounds__(256) bn_apply_kernel(const ApplyArgs a) {
+  const int G = a.Cp >> 3;
+  for (int cg = threadIdx.x; cg < G; cg += blockDim.x) {
+    const Vec8 s1 = loadf8(a.ss1 + cg * 8), b1 = loadf8(a.ss1 + a.Cp + cg * 8);
+    Vec8 s2, b2;
+    if (a.y2) { s2 = loadf8(a.ss2 + cg * 8); b2 = loadf8(a.ss2 + a.Cp + cg * 8); }
+    for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < a.rows;
+         r += (long long)gridDim.x * blockDim.y) {
+      const long long off = r * a.Cp + cg * 8;
+      Vec8 x = load8(a.y1 + off);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x.v[i] = fmaf(x.v[i], s1.v[i], b1.v[i]);
+      if (a.y2) {
+        const Vec8 t = load8(a.y2 + off);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x.v[i] += fmaf(t.v[i], s2.v[i], b2.v[i]);
+      }
+      if (a.res) {
+        const Vec8 t = load8(a.res + off);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x.v[i] += t.v[i];
+      }
+      if (a.relu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x.v[i] = fmaxf(x.v[i], 0.f);
+      }
+      store8(a.out + r * a.out_ld + a.out_coff + cg * 8, x);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ backward reduce
+// sums: [2][Cp] double: sum(g), sum(g*y);  g = dout * (out > 0) if relu else dout.
+// dout/out rows may live inside a wider (concat) tensor: ld / channel offset given.
+struct BwdArgs {
+  const __nv_bfloat16* dout; const __nv_bfloat16* out; const __nv_bfloat16* y;
+  long long rows;
+  int Cp;
+  int o_ld, o_coff;   // layout of dout / out rows
+  int relu;
+  double* sums;       // reduce
+  const float* coef;  // apply: [3][Cp] A, B, C
+  __nv_bfloat16* dy;  // apply
+  __nv_bfloat16* g_out;  // apply: optional masked gradient (residual branch), dense [rows][Cp]
+};
+
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BwdArgs a) {
+  extern __shared__ float red[];  // [blockDim.y][2][8*blockDim.x]
+  const int G = a.Cp >> 3;
+  const int GT = blockDim.x;
+  for (int cg0 = 0; cg0 < G; cg0 += GT) {
+    const int cg = cg0 + threadIdx.x;
+    float sg[8], sgy[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sg[i] = 0.f; sgy[i] = 0.f; }
+    if (cg < G) {
+      for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < a.rows;
+           r += (long long)gridDim.x * blockDim.y) {
+        const long long ooff = r * a.o_ld + a.o_coff + cg * 8;
+        Vec8 d = load8(a.dout + ooff);
+        if (a.relu) {
+          const Vec8 o = load8(a.out + ooff);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d.v[i] = o.v[i] > 0.f ? d.v[i] : 0.f;
+        }
+        const Vec8 yv = load8(a.y + r * a.Cp + cg * 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { sg[i] += d.v[i]; sgy[i] = fmaf(d.v[i], yv.v[i], sgy[i]); }
+      }
+    }
+    float* mine = red + (size_t)threadIdx.y * 16 * GT;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      mine[threadIdx.x * 8 + i] = sg[i];
+      mine[8 * GT + threadIdx.x * 8 + i] = sgy[i];
+    }
+    __syncthreads();
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    for (int j = tid; j < 16 * GT; j += blockDim.x * blockDim.y) {
+      float s = 0.f;
+      for (int ry = 0; ry < (int)blockDim.y; ++ry) s += red[(size_t)ry * 16 * GT + j];
+      const int which = j / (8 * GT);
+      const int c = cg0 * 8 + (j - which * 8 * GT);
+      if (c < a.Cp) atomicAdd(&a.sums[which * a.Cp + c], (double)s);
+    }
+    __syncthreads();
+  }
+}
+
+// sums_local: this rank's sums (parameter gradients); sums_global + count_global: over the whole
+// (cross-replica) batch, used for the dy coefficients. saved: mean/invstd from forward.
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums_local,
+                                       const double* __restrict__ sums_global,
+                                       const float* __restrict__ gamma, const float* __restrict__ saved,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                       float* __restrict__ coef, int C, int Cp, double count_global,
+                                       float grad_beta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cp) return;
+  if (c >= C) {
+    coef[c] = 0.f; coef[Cp + c] = 0.f; coef[2 * Cp + c] = 0.f;
+    return;
+  }
+  const double mean = saved[c], invstd = saved[Cp + c];
+  const double sg_l = sums_local[c], sgy_l = sums_local[Cp + c];
+  const double dg_l = (sgy_l - mean * sg_l) * invstd;
+  if (dgamma) dgamma[c] = (grad_beta != 0.f ? grad_beta * dgamma[c] : 0.f) + (float)dg_l;
+  if (dbeta) dbeta[c] = (grad_beta != 0.f ? grad_beta * dbeta[c] : 0.f) + (float)sg_l;
+  const double sg = sums_global[c], sgy = sums_global[Cp + c];
+  const double dg = (sgy - mean * sg) * invstd;
+  const double A = (double)gamma[c] * invstd;
+  const double B = -A * invstd * dg / count_global;
+  const double Cc = A * (-sg / count_global + mean * invstd * dg / count_global);
+  coef[c] = (float)A;
+  coef[Cp + c] = (float)B;
+  coef[2 * Cp + c] = (float)Cc;
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdArgs a) {
+  const int G = a.Cp >> 3;
+  for (int cg = threadIdx.x; cg < G; cg += blockDim.x) {
+    const Vec8 A = loadf8(a.coef + cg * 8), B = loadf8(a.coef + a.Cp + cg * 8),
+               C = loadf8(a.coef + 2 * a.Cp + cg * 8);
+    for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < a.rows;
+         r += (long long)gridDim.x * blockDim.y) {
+      const long long ooff = r * a.o_ld + a.o_coff + cg * 8;
+      Vec8 d = load8(a.dout + ooff);
+      if (a.relu) {
+        const Vec8 o = load8(a.out + ooff);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d.v[i] = o.v[i] > 0.f ? d.v[i] : 0.f;
+      }
+      const long long off = r * a.Cp + cg * 8;
+      if (a.g_out) store8(a.g_out + off, d);
+      const Vec8 yv = load8(a.y + off);
+      Vec8 o;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o.v[i] = fmaf(A.v[i], d.v[i], fmaf(B.v[i], yv.v[i], C.v[i]));
+      store8(a.dy + off, o);
+    }
+  }
+}
+
+// out = a + b (bf16), gradient accumulation where two consumers meet (reference: autograd add).
+__global__ void __launch_bounds__(256) add_bf16_kernel(const __nv_bfloat16* __restrict__ a,
+                                                       const __nv_bfloat16* __restrict__ b,
+                                                       __nv_bfloat16* __restrict__ out, long long n8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    Vec8 x = load8(a + i * 8);
+    const Vec8 y = load8(b + i * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x.v[j] += y.v[j];
+    store8(out + i * 8, x);
+  }
+}
+
+// ------------------------------------------------------------------------------ host
+static void row_block(int Cp, long long rows, dim3* block, int* grid) {
+  const int G = Cp / 8;
+  const int gt = G < 256 ? G : 256;
+  int ry = 256 / gt;
+  if (ry < 1) ry = 1;
+  *block = dim3(gt, ry);
+  long long want = ceil_div_ll(rows, ry * 4);  // ~4 rows per thread minimum
+  const long long cap = (long long)sm_count() * 8;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  *grid = (int)want;
+}
+
+int bn_finalize(const double* stats, const float* gamma, const float* beta, float* running_mean,
+                float* running_var, float* ss, float* saved, int C, int Cp, double count, float eps,
+                float momentum, int training, cudaStream_t stream) {
+  bn_finalize_kernel<<<ceil_div(Cp, 128), 128, 0, stream>>>(stats, gamma, beta, running_mean,
+                                                             running_var, ss, saved, C, Cp, count,
+                                                             eps, momentum, training);
+  DV_LAUNCH_OK();
+  return kOk;
+}
+
+int bn_apply(const void* y1, const float* ss1, const void* y2, const float* ss2, const void* res,
+             void* out, long long rows, int Cp, int out_ld, int out_coff, int relu,
+             cudaStream_t stream) {
+  ApplyArgs a;
+  a.y1 = (const __nv_bfloat16*)y1; a.ss1 = ss1;
+  a.y2 = (const __nv_bfloat16*)y2; a.ss2 = ss2;
+  a.res = (const __nv_bfloat16*)res;
+  a.out = (__nv_bfloat16*)out;
+  a.rows = rows; a.Cp = Cp; a.out_ld = out_ld; a.out_coff = out_coff; a.relu = relu;
+  dim3 block; int grid;
+  row_block(Cp, rows, &block, &grid);
+  bn_apply_kernel<<<grid, block, 0, stream>>>(a);
+  DV_LAUNCH_OK();
+  return kOk;
+}
+
+int bn_bwd_reduce(const void* dout, const void* out, const void* y, double* sums, long long rows,
+                  int Cp, int o_ld, int o_coff, int relu, cudaStream_t stream) {
+  BwdArgs a = {};
+  a.dout = (const __nv_bfloat16*)dout; a.out = (const __nv_bfloat16*)out;
+  a.y = (const __nv_bfloat16*)y; a.rows = rows; a.Cp = Cp; a.o_ld = o_ld; a.o_coff = o_coff;
+  a.relu = relu; a.sums = sums;
+  dim3 block; int grid;
+  row_block(Cp, rows, &block, &grid);
+  const size_t smem = (size_t)block.y * 16 * block.x * sizeof(float);
+  bn_bwd_reduce_kernel<<<grid, block, smem, stream>>>(a);
+  DV_LAUNCH_OK();
+  return kOk;
+}
+
+int bn_bwd_finalize(const double* sums_local, const double* sums_global, const float* gamma,
+                    const float* saved, float* dgamma, float* dbeta, float* coef, int C, int Cp,
+                    double count_global, float grad_beta, cudaStream_t stream) {
+  bn_bwd_finalize_kernel<<<ceil_div(Cp, 128), 128, 0, stream>>>(
+      sums_local, sums_global, gamma, saved, dgamma, dbeta, coef, C, Cp, count_global, grad_beta);
+  DV_LAUNCH_OK();
+  return kOk;
+}
+
+int bn_bwd_apply(const void* dout, const void* out, const void* y, const float* coef, void* dy,
+                 void* g_out, long long rows, int Cp, int o_ld, int o_coff, int relu,
+                 cudaStream_t stream) {
+  BwdArgs a = {};
+  a.dout = (const __nv_bfloat16*)dout; a.out = (const __nv_bfloat16*)out;
+  a.y = (const __nv_bfloat16*)y; a.rows = rows; a.Cp = Cp; a.o_ld = o_ld; a.o_coff = o_coff;
+  a.relu = relu; a.coef = coef; a.dy = (__nv_bfloat16*)dy; a.g_out = (__nv_bfloat16*)g_out;
+  dim3 block; int grid;
+  row_block(Cp, rows, &block, &grid);
+  bn_bwd_apply_kernel<<<grid, block, 0, stream>>>(a);
+  DV_LAUNCH_OK();
+  return kOk;
+}
+
+int add_bf16(const void* a, const void* b, void* out, long long n, cudaStream_t stream) {
+  const long long n8 = n / 8;
+  int grid = (int)std::min<long long>(ceil_div_ll(n8, 256), (long long)sm_count() * 8);
+  if (grid < 1) grid = 1;
+  add_bf16_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b,
+                                            (__nv_bfloat16*)out, n8);
+  DV_LAUNCH_OK();
+  return kOk;
+}
+
+}  // namespace dv

@@ -1,0 +1,271 @@
+// Pooling on bf16 NDHWC activations.
+//  - global average pool to fp32 features and its backward
+//    (reference: nn.AdaptiveAvgPool3d((1,1,1)) in model/simclr.py:166, model/moco.py:281,
+//     F.adaptive_avg_pool3d in model/classifier.py:66)
+//  - MaxPool3d forward/backward with arbitrary window/stride/padding
+//    (reference: backbone/c3d.py:18-39, backbone/s3dg.py:105,151,162,173,190)
+//  - ingest: fp32 NCDHW clip views -> bf16 NDHWC (3 -> 8 channels) with the optional per-channel
+//    Normalize and the DualVar segment shuffle folded into the address computation
+//    (reference: pretrain.py:386-389 + utils/transforms.py:57-63; model/simclr.py:378-383; K16, K22)
+#include <cuda_bf16.h>
+
+#include "host_common.h"
+
+namespace dv {
+
+// x: [N][S][Cp] bf16 -> out: [N][ld_out] fp32 (first C entries), mean over S.
+__global__ void avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out,
+                                   int S, int C, int Cp, int ld_out) {
+  const int n = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;  // channel; blockDim.y splits S
+  __shared__ float part[8][128];
+  float s = 0.f;
+  if (c < Cp) {
+    const __nv_bfloat16* p = x + (long long)n * S * Cp + c;
+    for (int i = threadIdx.y; i < S; i += blockDim.y) s += __bfloat162float(p[(long long)i * Cp]);
+  }
+  part[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+    for (int j = 0; j < (int)blockDim.y; ++j) t += part[j][threadIdx.x];
+    out[(long long)n * ld_out + c] = t / (float)S;
+  }
+}
+
+// dx[n][s][c] = dout[n][c] / S (pad channels zero)
+__global__ void avgpool_bwd_kernel(const float* __restrict__ dout, __nv_bfloat16* __restrict__ dx,
+                                   int S, int C, int Cp, int ld_out, long long total) {
+  const float inv = 1.f / (float)S;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cp);
+    const long long n = i / ((long long)S * Cp);
+    const float v = (c < C) ? dout[n * ld_out + c] * inv : 0.f;
+    dx[i] = __float2bfloat16_rn(v);
+  }
+}
+
+struct PoolGeom {
+  int N, T, H, W, To, Ho, Wo, Cp;
+  int kt, kh, kw, st, sh, sw, pt, ph, pw;
+};
+
+// One thread = one output position x 8 channels. Saves nothing: backward recomputes the argmax
+// (first maximum in (t,h,w) scan order, as ATen does).
+__global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                   const PoolGeom g, long long total) {
+  const int G = g.Cp >> 3;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % G);
+    long long r = i / G;
+    const int wo = (int)(r % g.Wo); r /= g.Wo;
+    const int ho = (int)(r % g.Ho); r /= g.Ho;
+    const int to = (int)(r % g.To);
+    const long long n = r / g.To;
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+    for (int a = 0; a < g.kt; ++a) {
+      const int t = to * g.st - g.pt + a;
+      if (t < 0 || t >= g.T) continue;
+      for (int b = 0; b < g.kh; ++b) {
+        const int h = ho * g.sh - g.ph + b;
+        if (h < 0 || h >= g.H) continue;
+        for (int c = 0; c < g.kw; ++c) {
+          const int w = wo * g.sw - g.pw + c;
+          if (w < 0 || w >= g.W) continue;
+          const uint4 u = *reinterpret_cast<const uint4*>(
+              x + ((((n * g.T + t) * g.H + h) * g.W + w) * (long long)g.Cp + cg * 8));
+          const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __bfloat1622float2(hh[j]);
+            m[2 * j] = fmaxf(m[2 * j], f.x);
+            m[2 * j + 1] = fmaxf(m[2 * j + 1], f.y);
+          }
+        }
+      }
+    }
+    uint4 o;
+    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(m[2 * j], m[2 * j + 1]);
+    *reinterpret_cast<uint4*>(y + i * 8) = o;
+  }
+}
+
+// Gather form (no atomics): one thread = one INPUT position x 8 channels; it sums dy of every
+// output window whose first-max element is this position.
+__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y,
+                                   const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx,
+                                   const PoolGeom g, long long total) {
+  const int G = g.Cp >> 3;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % G);
+    long long r = i / G;
+    const int w = (int)(r % g.W); r /= g.W;
+    const int h = (int)(r % g.H); r /= g.H;
+    const int t = (int)(r % g.T);
+    const long long n = r / g.T;
+    const uint4 ux = *reinterpret_cast<const uint4*>(x + i * 8);
+    const __nv_bfloat16* xv = reinterpret_cast<const __nv_bfloat16*>(&ux);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    // output windows containing (t,h,w): to in [ceil((t+pt-kt+1)/st), floor((t+pt)/st)]
+    const int to_lo = max(0, (t + g.pt - g.kt + g.st) / g.st), to_hi = min(g.To - 1, (t + g.pt) / g.st);
+    const int ho_lo = max(0, (h + g.ph - g.kh + g.sh) / g.sh), ho_hi = min(g.Ho - 1, (h + g.ph) / g.sh);
+    const int wo_lo = max(0, (w + g.pw - g.kw + g.sw) / g.sw), wo_hi = min(g.Wo - 1, (w + g.pw) / g.sw);
+    for (int to = to_lo; to <= to_hi; ++to)
+      for (int ho = ho_lo; ho <= ho_hi; ++ho)
+        for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+          const long long oo = ((((n * g.To + to) * g.Ho + ho) * g.Wo + wo) * (long long)g.Cp + cg * 8);
+          const uint4 uy = *reinterpret_cast<const uint4*>(y + oo);
+          const uint4 ud = *reinterpret_cast<const uint4*>(dy + oo);
+          const __nv_bfloat16* yv = reinterpret_cast<const __nv_bfloat16*>(&uy);
+          const __nv_bfloat16* dv_ = reinterpret_cast<const __nv_bfloat16*>(&ud);
+          // is this position the FIRST element equal to the max in the window's scan order?
+          unsigned eq = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (__bfloat162float(xv[j]) == __bfloat162float(yv[j])) eq |= 1u << j;
+          if (eq == 0) continue;
+          // knock out channels where an earlier window element already equals the max
+          for (int a = 0; a < g.kt && eq; ++a) {
+            const int tt = to * g.st - g.pt + a;
+            if (tt < 0 || tt >= g.T) continue;
+            for (int b = 0; b < g.kh && eq; ++b) {
+              const int hh = ho * g.sh - g.ph + b;
+              if (hh < 0 || hh >= g.H) continue;
+              for (int c = 0; c < g.kw && eq; ++c) {
+                const int ww = wo * g.sw - g.pw + c;
+                if (ww < 0 || ww >= g.W) continue;
+                const bool earlier = (tt < t) || (tt == t && (hh < h || (hh == h && ww < w)));
+                if (!earlier) continue;
+                const uint4 ue = *reinterpret_cast<const uint4*>(
+                    x + ((((n * g.T + tt) * g.H + hh) * g.W + ww) * (long long)g.Cp + cg * 8));
+                const __nv_bfloat16* ev = reinterpret_cast<const __nv_bfloat16*>(&ue);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (__bfloat162float(ev[j]) == __bfloat162float(yv[j])) eq &= ~(1u << j);
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (eq & (1u << j)) acc[j] += __bfloat162float(dv_[j]);
+        }
+    uint4 o;
+    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+    *reinterpret_cast<uint4*>(dx + i * 8) = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------- ingest
+// src: fp32, element (b, v, c, t, h, w) at  b*sb + v*sv + c*sc + t*st + h*W + w  (strides in elements)
+// dst: bf16 [B][T][H][W][8]; channel c < C gets (x - mean[c]) * inv_std[c], others 0.
+// perm: optional int32 [B][n_series]; output segment j of sample b reads source segment perm[b][j].
+struct IngestArgs {
+  const float* src;
+  __nv_bfloat16* dst;
+  const int* perm;
+  long long sb, sv, sc, st;
+  int B, C, T, H, W, view, n_series;
+  float mean[4], inv_std[4];
+};
+
+__global__ void __launch_bounds__(256) ingest_kernel(const IngestArgs a) {
+  const long long HW = (long long)a.H * a.W;
+  const long long total = (long long)a.B * a.T * HW;
+  const int seg_len = a.n_series > 0 ? a.T / a.n_series : a.T;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long hw = i % HW;
+    const int t = (int)((i / HW) % a.T);
+    const int b = (int)(i / (HW * a.T));
+    int ts = t;
+    if (a.perm) {
+      const int seg = t / seg_len;
+      ts = a.perm[b * a.n_series + seg] * seg_len + (t - seg * seg_len);
+    }
+    const float* p = a.src + b * a.sb + a.view * a.sv + ts * a.st + hw;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (c < a.C) v[c] = (p[c * a.sc] - a.mean[c]) * a.inv_std[c];
+    uint4 o;
+    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+    oh[0] = __floats2bfloat162_rn(v[0], v[1]);
+    oh[1] = __floats2bfloat162_rn(v[2], v[3]);
+    oh[2] = __floats2bfloat162_rn(0.f, 0.f);
+    oh[3] = oh[2];
+    *reinterpret_cast<uint4*>(a.dst + i * 8) = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------- host
+static int flat_grid(long long total, int threads) {
+  long long g = ceil_div_ll(total, threads);
+  const long long cap = (long long)sm_count() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+int avgpool_fwd(const void* x, float* out, int N, int S, int C, int Cp, int ld_out, cudaStream_t stream) {
+  dim3 block(128, 8);
+  dim3 grid(ceil_div(Cp, 128), N);
+  avgpool_fwd_kernel<<<grid, block, 0, stream>>>((const __nv_bfloat16*)x, out, S, C, Cp, ld_out);
+  DV_LAUNCH_OK();
+  return kOk;
+}
+
+int avgpool_bwd(const float* dout, void* dx, int N, int S, int C, int Cp, int ld_out, cudaStream_t stream) {
+  const long long total = (long long)N * S * Cp;
+  avgpool_bwd_kernel<<<flat_grid(total, 256), 256, 0, stream>>>(dout, (__nv_bfloat16*)dx, S, C, Cp,
+                                                                ld_out, total);
+  DV_LAUNCH_OK();
+  return kOk;
+}
+
+int maxpool_fwd(const void* x, void* y, const PoolGeom& g, cudaStream_t stream) {
+  const long long total = (long long)g.N * g.To * g.Ho * g.Wo * (g.Cp / 8);
+  maxpool_fwd_kernel<<<flat_grid(total, 256), 256, 0, stream>>>((const __nv_bfloat16*)x,
+                                                                (__nv_bfloat16*)y, g, total);
+  DV_LAUNCH_OK();
+  return kOk;
+}
+
+int maxpool_bwd(const void* x, const void* y, const void* dy, void* dx, const PoolGeom& g,
+                cudaStream_t stream) {
+  const long long total = (long long)g.N * g.T * g.H * g.W * (g.Cp / 8);
+  maxpool_bwd_kernel<<<flat_grid(total, 256), 256, 0, stream>>>(
+      (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx,
+      g, total);
+  DV_LAUNCH_OK();
+  return kOk;
+}
+
+int ingest(const float* src, void* dst, const int* perm, long long sb, long long sv, long long sc,
+           long long st, int B, int C, int T, int H, int W, int view, int n_series, const float* mean,
+           const float* stdv, cudaStream_t stream) {
+  IngestArgs a;
+  a.src = src; a.dst = (__nv_bfloat16*)dst; a.perm = perm;
+  a.sb = sb; a.sv = sv; a.sc = sc; a.st = st;
+  a.B = B; a.C = C; a.T = T; a.H = H; a.W = W; a.view = view; a.n_series = n_series;
+  for (int c = 0; c < 4; ++c) {
+    a.mean[c] = (mean && c < C) ? mean[c] : 0.f;
+    a.inv_std[c] = (stdv && c < C) ? 1.f / stdv[c] : 1.f;
+  }
+  const long long total = (long long)B * T * H * W;
+  ingest_kernel<<<flat_grid(total, 256), 256, 0, stream>>>(a);
+  DV_LAUNCH_OK();
+  return kOk;
+}
+
+}  // namespace dv

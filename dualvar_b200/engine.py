@@ -1,0 +1,346 @@
+"""Forward/backward executor for the clip encoders on bf16 NDHWC activations.
+
+The reference runs its backbones op by op through autograd (conv -> BN -> ReLU ..., each an ATen /
+cuDNN call that reads and writes a full fp32 NCDHW tensor). Here a backbone forward is ONE
+``torch.autograd.Function``: the host modules (dualvar_b200/backbones.py) describe their graph with the
+primitives below, every primitive launches kernels through the C ABI and records a closure on a tape;
+the Function's backward replays the tape in reverse. torch only allocates memory and carries the
+fp32 parameters/gradients at the boundary.
+
+Primitive <-> reference op:
+  conv_stats   nn.Conv3d forward + the batch statistics of the nn.BatchNorm3d that follows
+  activate     BatchNorm3d normalise/affine (+ second BN branch) (+ residual) (+ ReLU)
+  max_pool     nn.MaxPool3d
+  global_pool  nn.AdaptiveAvgPool3d((1,1,1))
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import _lib
+from ._lib import make_geom, pad8, ptr, stream_ptr
+
+call = _lib.call
+
+
+class Act:
+    """A bf16 NDHWC activation [N,T,H,W,Cp] with C logical channels and an optional gradient."""
+
+    __slots__ = ("data", "C", "grad", "needs_grad")
+
+    def __init__(self, data, C, needs_grad=True):
+        self.data = data
+        self.C = C
+        self.grad = None
+        self.needs_grad = needs_grad
+
+    @property
+    def shape5(self):
+        return tuple(self.data.shape)
+
+    @property
+    def rows(self):
+        s = self.data.shape
+        return s[0] * s[1] * s[2] * s[3]
+
+    @property
+    def Cp(self):
+        return self.data.shape[4]
+
+
+class RawBN:
+    """Un-normalised conv output + everything BN needs, between conv_stats() and activate()."""
+
+    __slots__ = ("y", "ss", "saved", "geom", "x", "conv", "bn", "packed", "count", "sync")
+
+
+class Context:
+    """Per-forward state: tape of backward closures, parameter-gradient sink, mode flags."""
+
+    def __init__(self, training, record=True):
+        self.training = training
+        self.record = record
+        self.tape = []
+        self.param_grads = {}      # id(param) -> fp32 tensor shaped like the parameter
+        self.launches = 0
+
+    def add_param_grad(self, p, g):
+        k = id(p)
+        if k in self.param_grads:
+            self.param_grads[k].add_(g)
+        else:
+            self.param_grads[k] = g
+
+
+# ----------------------------------------------------------------------------- helpers
+_weight_cache = {}
+
+
+def packed_weights(conv):
+    """bf16 packed copies of a conv weight, refreshed when the fp32 parameter changes
+    (optimizer.step() bumps Tensor._version)."""
+    w = conv.weight
+    key = id(w)
+    ver = (w._version, w.data_ptr())
+    hit = _weight_cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1], hit[2]
+    Cout, Cin, kt, kh, kw = w.shape
+    g = make_geom(1, kt, kh, kw, Cin, Cout, (kt, kh, kw), (1, 1, 1), (0, 0, 0))
+    wf = torch.empty((g.Cout_p, g.taps, g.Cin_p), dtype=torch.bfloat16, device=w.device)
+    wt = torch.empty((g.Cin_p, g.taps, g.Cout_p), dtype=torch.bfloat16, device=w.device)
+    call("dv_pack_conv_weight", ptr(w.detach()), ptr(wf), ptr(wt), ctypes.byref(g), stream_ptr())
+    _weight_cache[key] = (ver, wf, wt)
+    return wf, wt
+
+
+def _bias_padded(conv, Cp):
+    if conv.bias is None:
+        return None
+    b = torch.zeros(Cp, dtype=torch.float32, device=conv.bias.device)
+    b[:conv.bias.shape[0]] = conv.bias.detach()
+    return b
+
+
+def _is_sync(bn):
+    return isinstance(bn, nn.SyncBatchNorm) and dist.is_available() and dist.is_initialized() \
+        and dist.get_world_size() > 1
+
+
+def _acc_grad(act, g):
+    if act.grad is None:
+        act.grad = g
+    else:
+        call("dv_add_bf16", ptr(act.grad), ptr(g), ptr(act.grad), act.grad.numel(), stream_ptr())
+
+
+# ----------------------------------------------------------------------------- primitives
+def ingest(block5, view_stride=0, view=0, perm=None, n_series=0, batch=None, batch_stride=None):
+    """fp32 clips (contiguous, channels-first) -> Act. ``block5`` is addressed as
+    element(b, c, t, h, w) = base + b*batch_stride + view*view_stride + c*T*H*W + t*H*W + h*W + w."""
+    C, T, H, W = block5.shape[-4:]
+    B = batch if batch is not None else block5.numel() // (C * T * H * W)
+    sb = batch_stride if batch_stride is not None else C * T * H * W
+    dst = torch.empty((B, T, H, W, 8), dtype=torch.bfloat16, device=block5.device)
+    call("dv_ingest_clips", ptr(block5), ptr(dst), ptr(perm), sb, view_stride, T * H * W, H * W,
+         B, C, T, H, W, view, n_series, None, None, stream_ptr())
+    return Act(dst, C, needs_grad=False)
+
+
+def conv_stats(ctx, x, conv, bn):
+    """y = conv(x) (raw, bf16) with fused per-channel sum/sumsq, then BN finalize -> scale/shift.
+    Reference: nn.Conv3d + the statistics half of nn.BatchNorm3d (e.g. backbone/r21d.py:68)."""
+    N, T, H, W, Cin_p = x.shape5
+    w = conv.weight
+    Cout, Cin = w.shape[0], w.shape[1]
+    g = make_geom(N, T, H, W, Cin, Cout, tuple(w.shape[2:]), tuple(conv.stride), tuple(conv.padding))
+    assert g.Cin_p == Cin_p, (g.Cin_p, Cin_p)
+    wf, wt = packed_weights(conv)
+    dev = x.data.device
+    y = torch.empty((N, g.To, g.Ho, g.Wo, g.Cout_p), dtype=torch.bfloat16, device=dev)
+    training_stats = ctx.training and bn.training if bn is not None else False
+    stats = torch.zeros(2 * g.Cout_p, dtype=torch.float64, device=dev) if training_stats else None
+    call("dv_conv3d_fprop_bf16", ptr(x.data), ptr(wf), ptr(y), ptr(stats), ptr(_bias_padded(conv, g.Cout_p)),
+         ctypes.byref(g), stream_ptr())
+    r = RawBN()
+    r.y, r.geom, r.x, r.conv, r.bn, r.packed = y, g, x, conv, bn, (wf, wt)
+    r.count = float(N * g.To * g.Ho * g.Wo)
+    r.sync = False
+    if bn is None:
+        r.ss = r.saved = None
+        return r
+    if training_stats and _is_sync(bn):
+        dist.all_reduce(stats)
+        r.count *= dist.get_world_size()
+        r.sync = True
+    r.ss = torch.empty(2 * g.Cout_p, dtype=torch.float32, device=dev)
+    r.saved = torch.empty(2 * g.Cout_p, dtype=torch.float32, device=dev) if training_stats else None
+    momentum = bn.momentum if bn.momentum is not None else 0.1
+    track = bn.track_running_stats and bn.running_mean is not None
+    call("dv_bn_finalize", ptr(stats), ptr(bn.weight.detach()), ptr(bn.bias.detach()),
+         ptr(bn.running_mean) if track else None, ptr(bn.running_var) if track else None,
+         ptr(r.ss), ptr(r.saved), Cout, g.Cout_p, ctypes.c_double(r.count), ctypes.c_float(bn.eps),
+         ctypes.c_float(momentum), 1 if training_stats else 0, stream_ptr())
+    if training_stats and track:
+        bn.num_batches_tracked += 1
+    return r
+
+
+def _conv_backward(ctx, r, dy):
+    """wgrad into the parameter-gradient sink, dgrad into r.x.grad."""
+    g = r.geom
+    dwp = torch.empty((g.Cout_p, g.taps, g.Cin_p), dtype=torch.float32, device=dy.device)
+    call("dv_conv3d_wgrad_bf16", ptr(r.x.data), ptr(dy), ptr(dwp), ctypes.byref(g), stream_ptr())
+    gw = torch.empty_like(r.conv.weight)
+    call("dv_unpack_conv_wgrad", ptr(dwp), ptr(gw), ctypes.byref(g), ctypes.c_float(0.0), stream_ptr())
+    ctx.add_param_grad(r.conv.weight, gw)
+    if r.conv.bias is not None:
+        # a bias in front of training-mode BN has exactly zero gradient (BN removes the mean)
+        ctx.add_param_grad(r.conv.bias, torch.zeros_like(r.conv.bias))
+    if r.x.needs_grad:
+        dx = torch.empty_like(r.x.data)
+        call("dv_conv3d_dgrad_bf16", ptr(dy), ptr(r.packed[1]), ptr(dx), ctypes.byref(g), stream_ptr())
+        _acc_grad(r.x, dx)
+
+
+def activate(ctx, r1, r2=None, res=None, relu=True, out=None, out_coff=0):
+    """out = relu?(BN(r1) [+ BN(r2)] [+ res]). ``out``/``out_coff`` let several branches write
+    channel slices of one tensor (concat-free Inception, backbone/s3dg.py:130).
+    Reference: BatchNorm3d affine + ReLU + residual add (backbone/r21d.py:116-122)."""
+    g = r1.geom
+    Cp = g.Cout_p
+    dev = r1.y.device
+    if out is None:
+        out_t = torch.empty_like(r1.y)
+        out_act = Act(out_t, g.Cout)
+        out_ld = Cp
+    else:
+        out_act = out
+        out_t = out.data
+        out_ld = out.Cp
+    rows = r1.y.numel() // Cp
+    call("dv_bn_apply", ptr(r1.y), ptr(r1.ss), ptr(r2.y) if r2 else None, ptr(r2.ss) if r2 else None,
+         ptr(res.data) if res is not None else None, ptr(out_t), rows, Cp, out_ld, out_coff,
+         1 if relu else 0, stream_ptr())
+    if not ctx.record:
+        return out_act
+
+    def backward():
+        dout = out_act.grad
+        assert dout is not None, "activation has no gradient"
+        need_g = res is not None and res.needs_grad
+        g_buf = None
+        for i, r in enumerate((r1, r2)):
+            if r is None:
+                continue
+            sums = torch.zeros(2 * Cp, dtype=torch.float64, device=dev)
+            call("dv_bn_bwd_reduce", ptr(dout), ptr(out_t), ptr(r.y), ptr(sums), rows, Cp, out_ld, out_coff,
+                 1 if relu else 0, stream_ptr())
+            sums_g = sums
+            if r.sync:
+                sums_g = sums.clone()
+                dist.all_reduce(sums_g)
+            bn = r.bn
+            dgamma = torch.empty_like(bn.weight)
+            dbeta = torch.empty_like(bn.bias)
+            coef = torch.empty(3 * Cp, dtype=torch.float32, device=dev)
+            call("dv_bn_bwd_finalize", ptr(sums), ptr(sums_g), ptr(bn.weight.detach()), ptr(r.saved),
+                 ptr(dgamma), ptr(dbeta), ptr(coef), r.geom.Cout, Cp, ctypes.c_double(r.count),
+                 ctypes.c_float(0.0), stream_ptr())
+            ctx.add_param_grad(bn.weight, dgamma)
+            ctx.add_param_grad(bn.bias, dbeta)
+            dy = torch.empty_like(r.y)
+            want_g = need_g and g_buf is None
+            if want_g:
+                g_buf = torch.empty_like(r.y)
+            call("dv_bn_bwd_apply", ptr(dout), ptr(out_t), ptr(r.y), ptr(coef), ptr(dy),
+                 ptr(g_buf) if want_g else None, rows, Cp, out_ld, out_coff, 1 if relu else 0, stream_ptr())
+            _conv_backward(ctx, r, dy)
+        if need_g:
+            _acc_grad(res, g_buf)
+        if out is None:
+            out_act.grad = None
+
+    ctx.tape.append(backward)
+    return out_act
+
+
+def max_pool(ctx, x, kernel, stride, padding):
+    """nn.MaxPool3d (backbone/c3d.py:18, backbone/s3dg.py:151)."""
+    N, T, H, W, Cp = x.shape5
+    kt, kh, kw = kernel
+    st, sh, sw = stride
+    pt, ph, pw = padding
+    To, Ho, Wo = (T + 2 * pt - kt) // st + 1, (H + 2 * ph - kh) // sh + 1, (W + 2 * pw - kw) // sw + 1
+    geom = (ctypes.c_int32 * 17)(N, T, H, W, To, Ho, Wo, Cp, kt, kh, kw, st, sh, sw, pt, ph, pw)
+    y = torch.empty((N, To, Ho, Wo, Cp), dtype=torch.bfloat16, device=x.data.device)
+    call("dv_maxpool3d_fwd", ptr(x.data), ptr(y), geom, stream_ptr())
+    out = Act(y, x.C)
+    if ctx.record and x.needs_grad:
+        def backward():
+            dx = torch.empty_like(x.data)
+            call("dv_maxpool3d_bwd", ptr(x.data), ptr(y), ptr(out.grad), ptr(dx), geom, stream_ptr())
+            _acc_grad(x, dx)
+            out.grad = None
+        ctx.tape.append(backward)
+    return out
+
+
+def global_pool(ctx, x):
+    """AdaptiveAvgPool3d((1,1,1)) -> fp32 [N, C] (model/simclr.py:166)."""
+    N, T, H, W, Cp = x.shape5
+    S = T * H * W
+    out = torch.empty((N, x.C), dtype=torch.float32, device=x.data.device)
+    call("dv_avgpool_fwd", ptr(x.data), ptr(out), N, S, x.C, Cp, x.C, stream_ptr())
+    return out
+
+
+def global_pool_backward(x, dpooled):
+    N, T, H, W, Cp = x.shape5
+    dx = torch.empty_like(x.data)
+    d = dpooled.contiguous()
+    call("dv_avgpool_bwd", ptr(d), ptr(dx), N, T * H * W, x.C, Cp, x.C, stream_ptr())
+    _acc_grad(x, dx)
+
+
+def to_ncdhw(x):
+    N, T, H, W, Cp = x.shape5
+    out = torch.empty((N, x.C, T, H, W), dtype=torch.float32, device=x.data.device)
+    call("dv_ndhwc_bf16_to_ncdhw", ptr(x.data), ptr(out), N, x.C, Cp, T * H * W, stream_ptr())
+    return out
+
+
+def from_ncdhw_grad(x, d):
+    N, T, H, W, Cp = x.shape5
+    dx = torch.empty_like(x.data)
+    d = d.contiguous()
+    call("dv_ncdhw_to_ndhwc_bf16", ptr(d), ptr(dx), N, x.C, Cp, T * H * W, stream_ptr())
+    _acc_grad(x, dx)
+
+
+def run_backward(ctx):
+    for fn in reversed(ctx.tape):
+        fn()
+    ctx.tape.clear()
+
+
+# ----------------------------------------------------------------------------- autograd bridge
+class BackboneFunction(torch.autograd.Function):
+    """One autograd node for a whole backbone pass. ``program(ctx, x_act) -> Act`` builds the graph with
+    the primitives above; parameters are passed as inputs so that their gradients flow through the
+    normal autograd accumulation (DDP hooks, optimizers and .grad all keep working)."""
+
+    @staticmethod
+    def forward(fctx, program, make_input, pooled, training, record, *params):
+        ectx = Context(training, record=record)
+        x = make_input()
+        feat = program(ectx, x)
+        fctx.ectx, fctx.feat, fctx.pooled, fctx.params = ectx, feat, pooled, params
+        fctx.set_materialize_grads(False)
+        out = global_pool(ectx, feat) if pooled else to_ncdhw(feat)
+        if not record:
+            fctx.feat = None
+        return out
+
+    @staticmethod
+    def backward(fctx, dout):
+        ectx, feat = fctx.ectx, fctx.feat
+        if dout is None or feat is None:
+            return (None,) * (5 + len(fctx.params))
+        if fctx.pooled:
+            global_pool_backward(feat, dout)
+        else:
+            from_ncdhw_grad(feat, dout)
+        run_backward(ectx)
+        grads = tuple(ectx.param_grads.get(id(p)) if p.requires_grad else None for p in fctx.params)
+        ectx.param_grads = {}
+        fctx.feat = None
+        return (None, None, None, None, None) + grads
+
+
+def run_backbone(module, program, make_input, pooled):
+    params = [p for p in module.parameters()]
+    record = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    return BackboneFunction.apply(program, make_input, pooled, module.training, record, *params)

@@ -64,6 +64,87 @@ int dv_conv3d_dgrad_bf16(const void* dy, const void* wt, void* dx, const dv_conv
 int dv_conv3d_wgrad_bf16(const void* x, const void* dy, float* dw_packed, const dv_conv_geom* g,
                          void* stream);
 
+
+/* ---- BatchNorm3d (+ReLU, +residual) on bf16 NDHWC ------------------------------------------
+ * Replaces nn.BatchNorm3d / SyncBatchNorm + nn.ReLU + `x + res` at backbone/r21d.py:56-57,106-122,
+ * backbone/r3d.py:74-89, backbone/c3d.py:16-46, backbone/s3dg.py:16-27,44-64. */
+/* stats [2][Cp] double (sum, sumsq over `count` values per channel, from the conv epilogue, already
+ * all-reduced across replicas when cross-replica BN is on) -> scale_shift [2][Cp], saved [2][Cp]
+ * (mean, invstd); updates running_mean/var (momentum, unbiased var) when training != 0; when
+ * training == 0 uses the running statistics instead of stats. */
+int dv_bn_finalize(const double* stats, const float* gamma, const float* beta, float* running_mean,
+                   float* running_var, float* scale_shift, float* saved, int C, int Cp, double count,
+                   float eps, float momentum, int training, void* stream);
+/* out = relu?( ss1.scale*y1 + ss1.shift  [+ ss2.scale*y2 + ss2.shift]  [+ res] ); out rows may sit
+ * inside a wider tensor (channel stride out_ld, channel offset out_coff) for concat-free Inception. */
+int dv_bn_apply(const void* y1, const float* ss1, const void* y2, const float* ss2, const void* res,
+                void* out, int64_t rows, int Cp, int out_ld, int out_coff, int relu, void* stream);
+/* sums [2][Cp] double += (sum g, sum g*y), g = dout*(out>0) if relu else dout */
+int dv_bn_bwd_reduce(const void* dout, const void* out, const void* y, double* sums, int64_t rows,
+                     int Cp, int o_ld, int o_coff, int relu, void* stream);
+/* dgamma/dbeta (= grad_beta*old + local sums) and coef [3][Cp] of dy = A*g + B*y + C from the global sums */
+int dv_bn_bwd_finalize(const double* sums_local, const double* sums_global, const float* gamma,
+                       const float* saved, float* dgamma, float* dbeta, float* coef, int C, int Cp,
+                       double count_global, float grad_beta, void* stream);
+/* dy = A*g + B*y + C; g_out (optional) = g, the gradient flowing into the residual branch */
+int dv_bn_bwd_apply(const void* dout, const void* out, const void* y, const float* coef, void* dy,
+                    void* g_out, int64_t rows, int Cp, int o_ld, int o_coff, int relu, void* stream);
+/* out = a + b over n bf16 elements (n % 8 == 0): gradient accumulation where two consumers meet */
+int dv_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);
+
+/* ---- pooling / ingest ----------------------------------------------------------------------- */
+/* nn.AdaptiveAvgPool3d((1,1,1)) (model/simclr.py:166): x [N][S][Cp] bf16 -> out [N][ld_out] fp32 */
+int dv_avgpool_fwd(const void* x, float* out, int N, int S, int C, int Cp, int ld_out, void* stream);
+int dv_avgpool_bwd(const float* dout, void* dx, int N, int S, int C, int Cp, int ld_out, void* stream);
+typedef struct dv_pool_geom {
+  int32_t N, T, H, W, To, Ho, Wo, Cp;
+  int32_t kt, kh, kw, st, sh, sw, pt, ph, pw;
+} dv_pool_geom;
+/* nn.MaxPool3d (backbone/c3d.py:18-39, backbone/s3dg.py:105,151,162,173,190) */
+int dv_maxpool3d_fwd(const void* x, void* y, const dv_pool_geom* g, void* stream);
+int dv_maxpool3d_bwd(const void* x, const void* y, const void* dy, void* dx, const dv_pool_geom* g,
+                     void* stream);
+/* fp32 clips -> bf16 NDHWC (C<=4 -> 8 channels): element (b,view,c,t,h,w) of src is at
+ * b*sb + view*sv + c*sc + t*st + h*W + w. Optional Normalize (mean_host/std_host, C floats on the
+ * HOST, NULL = identity; utils/transforms.py:57-63) and optional segment shuffle: perm int32 [B][n_series]
+ * on the device, output segment j reads source segment perm[b][j] (model/simclr.py:378-383). */
+int dv_ingest_clips(const float* src, void* dst, const int32_t* perm, int64_t sb, int64_t sv, int64_t sc,
+                    int64_t st, int B, int C, int T, int H, int W, int view, int n_series,
+                    const float* mean_host, const float* std_host, void* stream);
+
+/* ---- fp32 heads and objectives --------------------------------------------------------------- */
+/* C = alpha*op(A)*op(B) + beta*C (+bias[n]) (relu). Row-major. ta: A stored [K][M]; tb: B stored [N][K].
+ * Heads = 1x1x1 nn.Conv3d (model/simclr.py:168-180); similarity matmuls (model/simclr.py:202,297,
+ * model/moco.py:413-414,429-430). */
+int dv_sgemm(int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
+             int ldb, float beta, float* C, int ldc, const float* bias, int relu, void* stream);
+int dv_colsum(const float* X, float* out, int M, int N, int ld, float beta, void* stream);
+int dv_relu_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream);
+/* F.normalize over the last dim d (model/simclr.py:359,367,393) and its backward */
+int dv_l2norm_fwd(const float* x, float* y, float* inv_norm, int64_t rows, int d, float eps, void* stream);
+int dv_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, float* dx, int64_t rows, int d,
+                  void* stream);
+/* Row-wise softmax cross-entropy on a similarity matrix S [R][C] with the reference's column order
+ * (model/simclr.py:205-221,308-329; model/moco.py:431-432): writes logits (positive first, self dropped,
+ * /T), adds sum_r CE to *loss_sum, counts top-1/top-5 hits (utils/utils.py:75-92) and overwrites S with
+ * dLoss/dS * grad_scale. self_col may be NULL (no column dropped). */
+int dv_contrast_rows(float* S, float* logits, const int32_t* self_col, const int32_t* pos_col, int R,
+                     int C, int ld_s, int ld_logits, float inv_T, float grad_scale, float* loss_sum,
+                     int32_t* hits, void* stream);
+/* Shuffle-rank loss + gradient (model/simclr.py:231-278; clip_max<=0: model/moco.py:440-480) */
+int dv_rank_loss(const float* a, const float* b, float* da, float* db, float* logits, float* loss_sum,
+                 int32_t* hits, int B, int s, int e, float theta, float clip_max, float weight,
+                 void* stream);
+/* out[b][perm[b][j]] = in[b][j] (inverse != 0: out[b][j] = in[b][perm[b][j]]) (model/simclr.py:389-392) */
+int dv_permute_segments(const float* in, float* out, const int32_t* perm, int B, int s, int e,
+                        int inverse, void* stream);
+int dv_segment_sum(const float* in, float* out, int64_t rows, int s, int e, float scale, void* stream);
+int dv_segment_bcast(const float* in, float* out, int64_t rows, int s, int e, float scale, float beta,
+                     void* stream);
+int dv_rowdot(const float* a, const float* b, float* out, int rows, int d, int ld_out, void* stream);
+int dv_row_axpy(const float* alpha, int ld_alpha, const float* x, float* y, int rows, int d, float beta,
+                void* stream);
+
 #ifdef __cplusplus
 }
 #endif
