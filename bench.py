@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""Headline benchmark: R(2+1)D (select_backbone('r21d')) SimCLR+DualVar pretraining step,
+64 samples/GPU (3 views each, 16x112x112), bf16 convs — BASELINE.json configs[1].
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+One "step" = what pretrain.py:400-451 does for one batch: Normalize/transpose ingest, model forward
+(two encoder passes: 3B clips + B segment-shuffled clips), four-loss sum, backward, SGD(momentum).
+Prints ONE JSON line (rank 0). See DESIGN.md "Measurement" for the definition of every field.
+"""
+import argparse
+import json
+import os
+import random
+import subprocess
+import sys
+import threading
+import time
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "pretrain samples/sec (1 sample = 3 views; R(2+1)D SimCLR+DualVar 16x112^2)"
+# conv MACs per clip-pass for r21d (1,1,1,1) at 16x112^2: fwd 42.724 GFLOP,
+# fwd+dgrad+wgrad 126.95 GFLOP; a sample = 4 clip-passes.
+GFLOP_PER_SAMPLE = 507.8
+
+
+def seed_all(s):
+    torch.manual_seed(s)
+    np.random.seed(s)
+    random.seed(s)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"bf16_tflops": d.get("bf16_tflops_sustained", d.get("bf16_tflops")), "hbm_gbs": d.get("hbm_gbs"),
+                "source": "measured (MEASURED_PEAKS.json, sustained bf16)"}
+    return {"bf16_tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# --------------------------------------------------------------------------------------- reference arm
+def oracle_step_fn(batch, threads):
+    """The CPU port of the reference step (oracle/, fp32, oneDNN) — the reference itself is Python +
+    torch and is not shipped to the GPU box; oracle/ restates it and is pinned to it by tests/golden."""
+    from oracle import models as OM
+    torch.set_num_threads(threads)
+    seed_all(0)
+    model = OM.SimCLR_TimeSeriesV4("r21d", 128, 0.07, False, True, 2, 64, 0.07, 0.07, "clip-sr-tc",
+                                   SimpleNamespace(shufflerank_theta=0.05)).train()
+    opt = torch.optim.SGD([{"params": p} for p in model.parameters()], lr=0.003, weight_decay=1e-4, momentum=0.9)
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1, 1)
+    frames = torch.rand(batch, 3, 48, 112, 112, generator=torch.Generator().manual_seed(1234))
+
+    def step():
+        x = ((frames - mean) / std).view(batch, 3, 3, 16, 112, 112).transpose(1, 2).contiguous()
+        ret = model(x)
+        loss = sum(v for k, v in ret.items() if "loss" in k)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    return step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = 2
+    step = oracle_step_fn(sample, cores)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    value = sample / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, sample),
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} samples/step (6 input clips, 8 clip-passes) of the same workload, "
+                                   f"oracle/ port of the reference step on the host CPU"},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, batch):
+    return {"workload": "configs[1]: R(2+1)D (select_backbone('r21d'), 14.4M) SimCLR+DualVar mode clip-sr-tc, "
+                        "3 views x 16x112x112 per sample, n_series=2, T=0.07, SGD lr 0.003 m 0.9 wd 1e-4",
+            "samples_per_gpu": batch, "clips_per_gpu_step": batch * 3, "clip_passes_per_gpu_step": batch * 4,
+            "parallelism": f"dp{args.gpus}", "l2": "inputs (462 MB/step/GPU fp32 at 64 samples) exceed the 126 MB L2"}
+
+
+# --------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    from dualvar_b200 import _lib, models as PM
+    from dualvar_b200.engine import RawClips
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if not _lib.load().dv_device_ok():
+        raise SystemExit("bench.py: sm_100a kernels need a compute-capability 10.x device")
+    B = args.batch
+    seed_all(0)
+    model = PM.SimCLR_TimeSeriesV4("r21d", 128, 0.07, world > 1, True, 2, 64, 0.07, 0.07, "clip-sr-tc",
+                                   SimpleNamespace(shufflerank_theta=0.05))
+    if world > 1:
+        model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)     # pretrain.py:244
+    model = model.to(dev).train()
+    net = model
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank])   # pretrain.py:248
+    opt = torch.optim.SGD(net.parameters(), lr=0.003, weight_decay=1e-4, momentum=0.9)
+    # synthetic decoded+augmented batch as the loader yields it: (B, 3, 3*16, 112, 112) in [0,1], pinned host
+    gen = torch.Generator().manual_seed(1234 + rank)
+    host = [torch.rand(B, 3, 48, 112, 112, generator=gen).pin_memory() for _ in range(2)]
+    h2d_bytes = host[0].numel() * 4
+    dev_in = [torch.empty_like(host[0], device=dev) for _ in range(2)]
+    copy_stream = torch.cuda.Stream()
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i % 2])
+            dev_in[i % 2].copy_(host[i % 2], non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
+    loss_host = torch.zeros(1).pin_memory()
+
+    def step(i, e2e):
+        if e2e:
+            torch.cuda.current_stream().wait_event(ready[i % 2])
+            prefetch(i + 1)
+        frames = dev_in[i % 2]
+        ret = model(RawClips(frames, 3))
+        loss = sum(v for k, v in ret.items() if "loss" in k)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        consumed[i % 2].record()
+        if e2e:
+            loss_host.copy_(loss.detach().view(1), non_blocking=True)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nsteps, e2e, first):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(first, first + nsteps):
+            step(i, e2e)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms / nsteps
+
+    # resident inputs for the kernel-side number
+    dev_in[0].copy_(host[0]); dev_in[1].copy_(host[1])
+    for i in range(args.warmup):
+        step(i, False)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.load().dv_launch_count()
+    timer = _lib.KernelTimer(["dv_conv3d_fprop_bf16", "dv_conv3d_dgrad_bf16", "dv_conv3d_wgrad_bf16"])
+    _lib.set_timer(timer)
+    ms_step = timed(args.steps, False, 0)
+    _lib.set_timer(None)
+    launches = _lib.load().dv_launch_count() - launches0
+    ksum = timer.summary()
+    # end-to-end: host buffers, H2D of every step's input inside the timed region (double-buffered on a
+    # copy stream), D2H of the loss every step
+    for i in range(2):
+        consumed[i].record()
+    torch.cuda.synchronize()
+    prefetch(0)
+    ms_e2e = timed(args.steps, True, 0)
+    sampler.stop_flag = True
+    final_loss = float(loss_host[0])
+
+    if rank == 0:
+        peaks = measured_peaks()
+        value = B * world / (ms_step / 1e3)
+        e2e_value = B * world / (ms_e2e / 1e3)
+        conv_ms = sum(d["ms"] for d in ksum.values())
+        kernels = {}
+        for name, d in ksum.items():
+            kernels[name] = {"calls_per_step": d["calls"] / args.steps, "ms_per_step": d["ms"] / args.steps,
+                             "tflops": d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0}
+        top = max(ksum, key=lambda n: ksum[n]["ms"]) if ksum else None
+        roof = None
+        if top:
+            ach = kernels[top]["tflops"]
+            roof = {"bound": "tensor", "kernel": {"dv_conv3d_fprop_bf16": "conv_tile_kernel (fprop)",
+                                                  "dv_conv3d_dgrad_bf16": "conv_tile_kernel (dgrad)",
+                                                  "dv_conv3d_wgrad_bf16": "conv_wgrad_kernel"}[top],
+                    "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": ach / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
+                    "share_of_step": ksum[top]["ms"] / args.steps / ms_step,
+                    "all_conv_kernels": kernels, "conv_share_of_step": conv_ms / args.steps / ms_step,
+                    "whole_step_tflops": GFLOP_PER_SAMPLE * B / ms_step / 1e3}
+        line = {
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, B),
+            "clips_per_s": value * 3, "clip_passes_per_s": value * 4,
+            "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches), "roofline": roof, "clocks": sampler.summary(),
+            "final_loss": final_loss,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            cstep = oracle_step_fn(2, cores)
+            cstep()
+            t0 = time.perf_counter()
+            n = 2
+            for _ in range(n):
+                cstep()
+            dt = (time.perf_counter() - t0) / n
+            line["cpu_baseline"] = {"value": 2 / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+                                    "sample": "2 samples/step (8 clip-passes) x 2 timed steps of the same workload, "
+                                              "oracle/ port of the reference step, fp32 oneDNN"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="samples per GPU (3 views each)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -67,7 +67,7 @@ def _parse_header(path=_HEADER):
     text = open(path).read()
     text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
     sigs = {}
-    for m in re.finditer(r"\b(int|const char\*)\s+(dv_\w+)\s*\(([^)]*)\)\s*;", text):
+    for m in re.finditer(r"\b(int64_t|int|const char\*)\s+(dv_\w+)\s*\(([^)]*)\)\s*;", text):
         ret, name, args = m.group(1), m.group(2), m.group(3).strip()
         argtypes = []
         if args and args != "void":
@@ -78,7 +78,7 @@ def _parse_header(path=_HEADER):
                 else:
                     base = a.replace("const ", "").split(" ")[0]
                     argtypes.append(_SCALARS[base])
-        sigs[name] = (ctypes.c_char_p if "char" in ret else ctypes.c_int, argtypes)
+        sigs[name] = (ctypes.c_char_p if "char" in ret else (ctypes.c_int64 if ret == "int64_t" else ctypes.c_int), argtypes)
     return sigs
 
 
@@ -127,8 +127,75 @@ def check(rc, what):
         raise DualVarNativeError(f"{what} failed (status {rc}): {msg.decode() if msg else ''}")
 
 
+_TRACE = os.environ.get("DV_TRACE", "") not in ("", "0")
+launch_count = 0
+
+
+def _fmt(a):
+    if isinstance(a, ConvGeom):
+        return "geom(" + ",".join(f"{n}={getattr(a, n)}" for n, _ in ConvGeom._fields_) + ")"
+    if hasattr(a, "_obj"):
+        return _fmt(a._obj)
+    if isinstance(a, ctypes.c_void_p):
+        return hex(a.value or 0)
+    if hasattr(a, "value"):
+        return str(a.value)
+    return str(a)
+
+
+class KernelTimer:
+    """CUDA-event timing of selected C-ABI calls on the launching stream (bench.py roofline leg).
+    For conv calls the algorithmic FLOPs (2 * positions * Cout * Cin * taps, logical channels) are
+    accumulated alongside so that achieved TFLOP/s = flops / device time."""
+
+    def __init__(self, names):
+        self.names = set(names)
+        self.records = []   # (name, start_event, end_event, flops)
+
+    def flops_of(self, args):
+        for a in args:
+            g = getattr(a, "_obj", None)
+            if isinstance(g, ConvGeom):
+                return 2.0 * g.N * g.To * g.Ho * g.Wo * g.Cout * g.Cin * g.taps
+        return 0.0
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1, fl in self.records:
+            d = out.setdefault(name, {"calls": 0, "ms": 0.0, "flops": 0.0})
+            d["calls"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += fl
+        return out
+
+
+_timer = None
+
+
+def set_timer(timer):
+    global _timer
+    _timer = timer
+
+
 def call(name, *args):
     """Invoke a C-ABI function that returns a status code; raise on failure."""
+    global launch_count
     lib = load()
+    launch_count += 1
+    if _timer is not None and name in _timer.names:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        check(rc, name)
+        _timer.records.append((name, e0, e1, _timer.flops_of(args)))
+        return
+    if _TRACE:
+        print(f"[dv] {name}(" + ", ".join(_fmt(a) for a in args) + ")", flush=True)
     rc = getattr(lib, name)(*args)
     check(rc, name)
+    if _TRACE:
+        torch.cuda.synchronize()
+        print(f"[dv] {name} done", flush=True)

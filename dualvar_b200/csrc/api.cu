@@ -42,8 +42,8 @@ int avgpool_bwd(const float* dout, void* dx, int N, int S, int C, int Cp, int ld
 int maxpool_fwd(const void* x, void* y, const PoolGeom& g, cudaStream_t stream);
 int maxpool_bwd(const void* x, const void* y, const void* dy, void* dx, const PoolGeom& g, cudaStream_t stream);
 int ingest(const float* src, void* dst, const int* perm, long long sb, long long sv, long long sc,
-           long long st, int B, int C, int T, int H, int W, int view, int n_series, const float* mean,
-           const float* stdv, cudaStream_t stream);
+           long long st, int B, int C, int T, int H, int W, int view, int nv, int n_series,
+           const float* mean, const float* stdv, cudaStream_t stream);
 int sgemm(int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
           int ldb, float beta, float* C, int ldc, const float* bias, int relu, cudaStream_t stream);
 int colsum(const float* X, float* out, int M, int N, int ld, float beta, cudaStream_t stream);
@@ -99,6 +99,7 @@ extern "C" {
 
 const char* dv_last_error(void) { return last_error_ref().c_str(); }
 int dv_version(void) { return 1; }
+int64_t dv_launch_count(void) { return (int64_t)::dv::launch_counter(); }
 
 int dv_device_ok(void) {
   int dev = 0, major = 0;
@@ -216,11 +217,11 @@ int dv_maxpool3d_bwd(const void* x, const void* y, const void* dy, void* dx, con
   return maxpool_bwd(x, y, dy, dx, to_pool(g), ST);
 }
 int dv_ingest_clips(const float* src, void* dst, const int32_t* perm, int64_t sb, int64_t sv, int64_t sc,
-                    int64_t st, int B, int C, int T, int H, int W, int view, int n_series,
+                    int64_t st, int B, int C, int T, int H, int W, int view, int nv, int n_series,
                     const float* mean_host, const float* std_host, void* stream) {
-  DV_REQUIRE(src && dst && B > 0 && C > 0 && C <= 4 && T > 0 && H > 0 && W > 0, "bad ingest arguments");
+  DV_REQUIRE(src && dst && B > 0 && C > 0 && C <= 4 && T > 0 && H > 0 && W > 0 && nv > 0, "bad ingest arguments");
   DV_REQUIRE(perm == nullptr || (n_series > 0 && T % n_series == 0), "ingest: T must divide into n_series segments");
-  return ingest(src, dst, perm, sb, sv, sc, st, B, C, T, H, W, view, n_series, mean_host, std_host, ST);
+  return ingest(src, dst, perm, sb, sv, sc, st, B, C, T, H, W, view, nv, n_series, mean_host, std_host, ST);
 }
 int dv_sgemm(int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
              int ldb, float beta, float* C, int ldc, const float* bias, int relu, void* stream) {

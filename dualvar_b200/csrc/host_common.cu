@@ -3,6 +3,7 @@
 #include <cudaTypedefs.h>
 #include <stdarg.h>
 
+#include <atomic>
 #include <mutex>
 
 namespace dv {
@@ -21,6 +22,10 @@ int fail(int code, const char* fmt, ...) {
   g_last_error = buf;
   return code;
 }
+
+static std::atomic<long long> g_launches{0};
+long long launch_counter() { return g_launches.load(); }
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int sm_count() {
   static int cached = 0;

@@ -28,7 +28,13 @@ int fail(int code, const char* fmt, ...);
     if (!(cond)) return ::dv::fail(::dv::kBadArg, __VA_ARGS__); \
   } while (0)
 
-#define DV_LAUNCH_OK() DV_CUDA_OK(cudaGetLastError())
+long long launch_counter();
+void count_launch();
+#define DV_LAUNCH_OK()                  \
+  do {                                  \
+    ::dv::count_launch();               \
+    DV_CUDA_OK(cudaGetLastError());     \
+  } while (0)
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 inline int ceil_div(int x, int m) { return (x + m - 1) / m; }

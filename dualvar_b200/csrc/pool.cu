@@ -168,14 +168,14 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __
 
 // ---------------------------------------------------------------------------------- ingest
 // src: fp32, element (b, v, c, t, h, w) at  b*sb + v*sv + c*sc + t*st + h*W + w  (strides in elements)
-// dst: bf16 [B][T][H][W][8]; channel c < C gets (x - mean[c]) * inv_std[c], others 0.
+// dst: bf16 [B*nv][T][H][W][8] (clip n = b*nv + j reads view `view + j` of sample b); channel c < C gets (x - mean[c]) * inv_std[c], others 0.
 // perm: optional int32 [B][n_series]; output segment j of sample b reads source segment perm[b][j].
 struct IngestArgs {
   const float* src;
   __nv_bfloat16* dst;
   const int* perm;
   long long sb, sv, sc, st;
-  int B, C, T, H, W, view, n_series;
+  int B, C, T, H, W, view, n_series, nv;
   float mean[4], inv_std[4];
 };
 
@@ -187,13 +187,15 @@ __global__ void __launch_bounds__(256) ingest_kernel(const IngestArgs a) {
        i += (long long)gridDim.x * blockDim.x) {
     const long long hw = i % HW;
     const int t = (int)((i / HW) % a.T);
-    const int b = (int)(i / (HW * a.T));
+    const int n = (int)(i / (HW * a.T));   // output clip index = b * nv + (view - view0)
+    const int b = n / a.nv;
+    const int vw = a.view + (n - b * a.nv);
     int ts = t;
     if (a.perm) {
       const int seg = t / seg_len;
-      ts = a.perm[b * a.n_series + seg] * seg_len + (t - seg * seg_len);
+      ts = a.perm[n * a.n_series + seg] * seg_len + (t - seg * seg_len);
     }
-    const float* p = a.src + b * a.sb + a.view * a.sv + ts * a.st + hw;
+    const float* p = a.src + b * a.sb + vw * a.sv + ts * a.st + hw;
     float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int c = 0; c < 4; ++c)
@@ -252,17 +254,17 @@ int maxpool_bwd(const void* x, const void* y, const void* dy, void* dx, const Po
 }
 
 int ingest(const float* src, void* dst, const int* perm, long long sb, long long sv, long long sc,
-           long long st, int B, int C, int T, int H, int W, int view, int n_series, const float* mean,
-           const float* stdv, cudaStream_t stream) {
+           long long st, int B, int C, int T, int H, int W, int view, int nv, int n_series,
+           const float* mean, const float* stdv, cudaStream_t stream) {
   IngestArgs a;
   a.src = src; a.dst = (__nv_bfloat16*)dst; a.perm = perm;
   a.sb = sb; a.sv = sv; a.sc = sc; a.st = st;
-  a.B = B; a.C = C; a.T = T; a.H = H; a.W = W; a.view = view; a.n_series = n_series;
+  a.B = B; a.C = C; a.T = T; a.H = H; a.W = W; a.view = view; a.n_series = n_series; a.nv = nv;
   for (int c = 0; c < 4; ++c) {
     a.mean[c] = (mean && c < C) ? mean[c] : 0.f;
     a.inv_std[c] = (stdv && c < C) ? 1.f / stdv[c] : 1.f;
   }
-  const long long total = (long long)B * T * H * W;
+  const long long total = (long long)B * nv * T * H * W;
   ingest_kernel<<<flat_grid(total, 256), 256, 0, stream>>>(a);
   DV_LAUNCH_OK();
   return kOk;

@@ -117,15 +117,51 @@ def _acc_grad(act, g):
 
 
 # ----------------------------------------------------------------------------- primitives
-def ingest(block5, view_stride=0, view=0, perm=None, n_series=0, batch=None, batch_stride=None):
-    """fp32 clips (contiguous, channels-first) -> Act. ``block5`` is addressed as
-    element(b, c, t, h, w) = base + b*batch_stride + view*view_stride + c*T*H*W + t*H*W + h*W + w."""
-    C, T, H, W = block5.shape[-4:]
-    B = batch if batch is not None else block5.numel() // (C * T * H * W)
-    sb = batch_stride if batch_stride is not None else C * T * H * W
-    dst = torch.empty((B, T, H, W, 8), dtype=torch.bfloat16, device=block5.device)
-    call("dv_ingest_clips", ptr(block5), ptr(dst), ptr(perm), sb, view_stride, T * H * W, H * W,
-         B, C, T, H, W, view, n_series, None, None, stream_ptr())
+class RawClips:
+    """Un-normalised loader output (B, C, V*T, H, W) in [0,1] plus the Normalize constants: lets the
+    models fuse pretrain.py:386-389 (Normalize + view + transpose + contiguous) into the ingest kernel
+    instead of three fp32 passes. ``model(RawClips(...))`` == ``model(tr(x))`` of the reference loop."""
+
+    def __init__(self, frames, n_views, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):
+        assert frames.dim() == 5 and frames.shape[2] % n_views == 0
+        self.frames = frames.contiguous().float()
+        self.n_views = n_views
+        self.mean, self.std = tuple(mean), tuple(std)
+
+    @property
+    def device(self):
+        return self.frames.device
+
+    @property
+    def block_shape(self):
+        B, C, VT, H, W = self.frames.shape
+        return (B, self.n_views, C, VT // self.n_views, H, W)
+
+
+def ingest(src, first_view=0, n_views=None, perm=None, n_series=0):
+    """Clips -> bf16 NDHWC Act with 8 channels. ``src`` is the reference block (B, V, C, T, H, W)
+    fp32, a plain clip batch (B, C, T, H, W), or RawClips. Output clip order is (b, view) with views
+    first_view .. first_view+n_views-1, matching block.view(-1, C, T, H, W) (model/simclr.py:352)."""
+    mean = std = None
+    if isinstance(src, RawClips):
+        t = src.frames
+        B, V, C, T, H, W = src.block_shape
+        sb, sv, sc, st = C * V * T * H * W, T * H * W, V * T * H * W, H * W
+        mean = (ctypes.c_float * 4)(*src.mean, 0.0)
+        std = (ctypes.c_float * 4)(*src.std, 1.0)
+    elif src.dim() == 6:
+        t = src
+        B, V, C, T, H, W = src.shape
+        sb, sv, sc, st = V * C * T * H * W, C * T * H * W, T * H * W, H * W
+    else:
+        t = src
+        B, C, T, H, W = src.shape
+        V = 1
+        sb, sv, sc, st = C * T * H * W, 0, T * H * W, H * W
+    nv = V - first_view if n_views is None else n_views
+    dst = torch.empty((B * nv, T, H, W, 8), dtype=torch.bfloat16, device=t.device)
+    call("dv_ingest_clips", ptr(t), ptr(dst), ptr(perm), sb, sv, sc, st, B, C, T, H, W, first_view, nv,
+         n_series, mean, std, stream_ptr())
     return Act(dst, C, needs_grad=False)
 
 

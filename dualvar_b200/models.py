@@ -29,9 +29,15 @@ def _head(mods, x):
 
 
 def _check_input(block):
+    """Accept the reference's fp32 block or engine.RawClips (fused Normalize + transpose ingest)."""
+    if isinstance(block, E.RawClips):
+        if not block.device.type == "cuda":
+            raise E._lib.DualVarNativeError("dualvar_b200 models run on a B200 only (no CPU fallback)")
+        return block, block.block_shape
     if not block.is_cuda:
         raise E._lib.DualVarNativeError("dualvar_b200 models run on a B200 only (no CPU fallback)")
-    return block.contiguous().float()
+    block = block.contiguous().float()
+    return block, tuple(block.shape)
 
 
 def _draw_perms(B, n_series, device):
@@ -60,8 +66,8 @@ class SimCLR_Naked(nn.Module):
         return ret
 
     def forward(self, block):
-        block = _check_input(block)
-        B, n_views = block.shape[:2]
+        block, shape = _check_input(block)
+        B, n_views = shape[:2]
         assert n_views == 2
         pooled = self.encoder_q[0].encode(lambda: E.ingest(block), pooled=True)
         f = _head(self.encoder_q[2:], pooled) if self.nonlinear else pooled
@@ -114,13 +120,12 @@ class SimCLR_TimeSeriesV4(nn.Module):
         return ret
 
     def forward(self, block):
-        block = _check_input(block)
-        B = block.size(0)
-        assert block.size(1) == 3
-        _, _, C, T, H, W = block.shape
+        block, shape = _check_input(block)
+        B, n_views_in, C, T, H, W = shape
+        assert n_views_in == 3
         s, e = self.n_series, self.series_dim
         backbone = self.encoder_q[0]
-        clip_elems = C * T * H * W
+        dev = block.device
         # pass 1: all 3B clips in (b, view) order, one batch -> BN statistics over 3B (model/simclr.py:352-357)
         pooled = backbone.encode(lambda: E.ingest(block), pooled=True)                  # (3B, fs)
         ret = dict()
@@ -134,10 +139,9 @@ class SimCLR_TimeSeriesV4(nn.Module):
         if self.with_sr:
             # pass 2: view 2 with its T/s-frame segments permuted per sample; the permutation is folded
             # into the ingest kernel's addressing (model/simclr.py:378-387)
-            perm = _draw_perms(B, s, block.device)
+            perm = _draw_perms(B, s, dev)
             pooled_s = backbone.encode(
-                lambda: E.ingest(block, view_stride=clip_elems, view=2, perm=perm, n_series=s, batch=B,
-                                 batch_stride=3 * clip_elems), pooled=True)             # (B, fs)
+                lambda: E.ingest(block, first_view=2, n_views=1, perm=perm, n_series=s), pooled=True)  # (B, fs)
             shuf = _head(self.series_proj_head, pooled_s).view(B, s, e)
             shuf = O.l2norm(O.PermuteSegmentsFn.apply(shuf, perm))
             theta = self.args.shufflerank_theta
@@ -173,7 +177,7 @@ class LinearClassifier(nn.Module):
         self._initialize_weights(self.final_fc)
 
     def forward(self, block):
-        block = _check_input(block)
+        block, _ = _check_input(block)
         feat3d = self.backbone.encode(lambda: E.ingest(block), pooled=True)
         if self.use_l2_norm:
             feat3d = O.l2norm(feat3d)

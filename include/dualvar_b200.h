@@ -37,6 +37,8 @@ typedef struct dv_conv_geom {
 
 const char* dv_last_error(void);
 int dv_version(void);
+/* number of kernels this library has launched in the calling process */
+int64_t dv_launch_count(void);
 /* 1 if the current device is compute capability 10.x (sm_100a kernels can run), else 0 */
 int dv_device_ok(void);
 
@@ -105,11 +107,14 @@ int dv_maxpool3d_fwd(const void* x, void* y, const dv_pool_geom* g, void* stream
 int dv_maxpool3d_bwd(const void* x, const void* y, const void* dy, void* dx, const dv_pool_geom* g,
                      void* stream);
 /* fp32 clips -> bf16 NDHWC (C<=4 -> 8 channels): element (b,view,c,t,h,w) of src is at
- * b*sb + view*sv + c*sc + t*st + h*W + w. Optional Normalize (mean_host/std_host, C floats on the
- * HOST, NULL = identity; utils/transforms.py:57-63) and optional segment shuffle: perm int32 [B][n_series]
- * on the device, output segment j reads source segment perm[b][j] (model/simclr.py:378-383). */
+ * b*sb + view*sv + c*sc + t*st + h*W + w. Output clip n = b*nv + j holds view (view + j) of sample b,
+ * i.e. nv consecutive views per sample in the reference's block.view(-1, C, T, H, W) order
+ * (model/simclr.py:352). Optional Normalize (mean_host/std_host, C floats on the HOST, NULL = identity;
+ * utils/transforms.py:57-63 + the view/transpose of pretrain.py:386-389 expressed through the strides)
+ * and optional segment shuffle: perm int32 [B*nv][n_series] on the device, output segment j of clip n
+ * reads source segment perm[n][j] (model/simclr.py:378-383). */
 int dv_ingest_clips(const float* src, void* dst, const int32_t* perm, int64_t sb, int64_t sv, int64_t sc,
-                    int64_t st, int B, int C, int T, int H, int W, int view, int n_series,
+                    int64_t st, int B, int C, int T, int H, int W, int view, int nv, int n_series,
                     const float* mean_host, const float* std_host, void* stream);
 
 /* ---- fp32 heads and objectives --------------------------------------------------------------- */

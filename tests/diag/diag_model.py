@@ -21,7 +21,7 @@ def relerr(a, b):
     return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
 
 
-def cmp_backbone(name, shape=(4, 3, 8, 32, 32)):
+def cmp_backbone(name, shape=(8, 3, 8, 64, 64)):
     seed(0)
     ref, _ = OB.select_backbone(name)
     ref = ref.to(dev).train()
@@ -43,6 +43,19 @@ def cmp_backbone(name, shape=(4, 3, 8, 32, 32)):
         if e > worst[1]:
             worst = (n, e)
     print(f"[{name}] worst param-grad rel err {worst[1]:.3e} at {worst[0]}")
+    # yardstick: the oracle itself under bf16 autocast vs its fp32 self
+    import copy
+    ref2 = copy.deepcopy(ref)
+    for p_ in ref2.parameters(): p_.grad = None
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        ya = ref2(x)
+    ya.float().backward(g)
+    w2 = ("", 0.0); allp = []; alla = []
+    for (n, pr), (_, pa), (_, pp) in zip(ref.named_parameters(), ref2.named_parameters(), prod.named_parameters()):
+        e = relerr(pa.grad, pr.grad); alla.append(e); allp.append(relerr(pp.grad, pr.grad))
+        if e > w2[1]: w2 = (n, e)
+    print(f"[{name}] yardstick autocast-bf16 oracle: fwd rel {relerr(ya, yr):.3e} worst grad rel {w2[1]:.3e} at {w2[0]}; "
+          f"median grad rel: autocast {sorted(alla)[len(alla)//2]:.3e} product {sorted(allp)[len(allp)//2]:.3e}")
     # running stats
     wr = 0.0
     for (n, br), (_, bp) in zip(ref.named_buffers(), prod.named_buffers()):
@@ -53,7 +66,7 @@ def cmp_backbone(name, shape=(4, 3, 8, 32, 32)):
     print(f"[{name}] worst running-stat rel err {wr:.3e}")
 
 
-def cmp_simclr(net, B=4, shape=(8, 32, 32)):
+def cmp_simclr(net, B=8, shape=(8, 64, 64)):
     args = SimpleNamespace(shufflerank_theta=0.05)
     seed(0)
     ref = OM.SimCLR_TimeSeriesV4(net, 128, 0.07, False, True, 2, 64, 0.07, 0.07, "clip-sr-tc", args).to(dev).train()
