@@ -255,7 +255,7 @@ def run_ours(args):
                     "frac": ach / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
                     "share_of_step": ksum[top]["ms"] / args.steps / ms_step,
                     "all_conv_kernels": kernels, "conv_share_of_step": conv_ms / args.steps / ms_step,
-                    "whole_step_tflops": GFLOP_PER_SAMPLE * B / ms_step / 1e3}
+                    "whole_step_tflops": GFLOP_PER_SAMPLE * B / ms_step}
         line = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",

@@ -148,9 +148,21 @@ class KernelTimer:
     For conv calls the algorithmic FLOPs (2 * positions * Cout * Cin * taps, logical channels) are
     accumulated alongside so that achieved TFLOP/s = flops / device time."""
 
-    def __init__(self, names):
+    def __init__(self, names, detail=False):
         self.names = set(names)
+        self.detail = detail
         self.records = []   # (name, start_event, end_event, flops)
+
+    def key_of(self, name, args):
+        if not self.detail:
+            return name
+        for a in args:
+            g = getattr(a, "_obj", None)
+            if isinstance(g, ConvGeom):
+                return (f"{name} N{g.N} {g.T}x{g.H}x{g.W} {g.Cin}->{g.Cout} k{g.kt}{g.kh}{g.kw} "
+                        f"s{g.st}{g.sh}{g.sw}")
+        ints = [str(a) for a in args if isinstance(a, int)][:3]
+        return name + " " + ",".join(ints)
 
     def flops_of(self, args):
         for a in args:
@@ -190,7 +202,7 @@ def call(name, *args):
         rc = getattr(lib, name)(*args)
         e1.record()
         check(rc, name)
-        _timer.records.append((name, e0, e1, _timer.flops_of(args)))
+        _timer.records.append((_timer.key_of(name, args), e0, e1, _timer.flops_of(args)))
         return
     if _TRACE:
         print(f"[dv] {name}(" + ", ".join(_fmt(a) for a in args) + ")", flush=True)

@@ -181,7 +181,7 @@ struct IngestArgs {
 
 __global__ void __launch_bounds__(256) ingest_kernel(const IngestArgs a) {
   const long long HW = (long long)a.H * a.W;
-  const long long total = (long long)a.B * a.T * HW;
+  const long long total = (long long)a.B * a.nv * a.T * HW;
   const int seg_len = a.n_series > 0 ? a.T / a.n_series : a.T;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {

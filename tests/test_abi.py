@@ -1,0 +1,71 @@
+"""CPU: the C-ABI library loads and exports every symbol include/dualvar_b200.h declares; the
+product path refuses to run without a GPU / without the extension (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from dualvar_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "dualvar_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dv_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = _declared()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    assert sorted(_lib.exported_symbols()) == names
+
+
+def test_version_and_error_string():
+    lib = _lib.load()
+    assert lib.dv_version() >= 1
+    g = _lib.make_geom(1, 1, 1, 1, 8, 8, (1, 1, 1), (1, 1, 1), (0, 0, 0))
+    rc = lib.dv_pack_conv_weight(None, None, None, ctypes.byref(g), None)
+    assert rc != 0 and b"NULL" in lib.dv_last_error()
+    bad = _lib.make_geom(1, 4, 4, 4, 8, 8, (3, 3, 3), (3, 1, 1), (1, 1, 1))
+    rc = lib.dv_conv3d_fprop_bf16(ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(16), None, None,
+                                  ctypes.byref(bad), None)
+    assert rc != 0 and b"stride" in lib.dv_last_error()
+
+
+def test_geometry_helper_matches_conv_formula():
+    g = _lib.make_geom(2, 16, 112, 112, 3, 83, (1, 7, 7), (1, 2, 2), (0, 3, 3))
+    assert (g.To, g.Ho, g.Wo) == (16, 56, 56) and g.Cin_p == 8 and g.Cout_p == 88 and g.taps == 49
+
+
+def test_missing_extension_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "_LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.DualVarNativeError):
+        _lib.load()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU error path")
+def test_cpu_tensors_are_rejected_not_silently_computed():
+    from types import SimpleNamespace
+    from dualvar_b200 import models as PM
+    m = PM.SimCLR_TimeSeriesV4("r3d", 128, 0.07, False, True, 2, 64, 0.07, 0.07, "clip-sr-tc",
+                               SimpleNamespace(shufflerank_theta=0.05))
+    with pytest.raises(_lib.DualVarNativeError):
+        m(torch.zeros(2, 3, 3, 8, 32, 32))
+    with pytest.raises(_lib.DualVarNativeError):
+        m.encoder_q[0](torch.zeros(1, 3, 8, 32, 32))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "dualvar_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn

@@ -1,0 +1,84 @@
+"""GPU: tcgen05 implicit-GEMM conv3d fprop / dgrad / wgrad through the C ABI vs torch fp32 conv on
+bf16-rounded operands. Tolerance 1e-2 of the output range (bf16 storage of y/dx; wgrad is fp32)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    ("1x1x1 64->64", 2, 4, 16, 16, 64, 64, (1, 1, 1), (1, 1, 1), (0, 0, 0)),
+    ("spatial 64->144", 2, 4, 14, 14, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    ("temporal 144->64", 2, 4, 14, 14, 144, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0)),
+    ("spatial s2 64->230", 2, 4, 28, 28, 64, 230, (1, 3, 3), (1, 2, 2), (0, 1, 1)),
+    ("temporal s2 230->128", 2, 8, 14, 14, 230, 128, (3, 1, 1), (2, 1, 1), (1, 0, 0)),
+    ("down 1x1 s(1,2,2) 64->42", 2, 4, 28, 28, 64, 42, (1, 1, 1), (1, 2, 2), (0, 0, 0)),
+    ("down 1x1 s(2,1,1) 42->128", 2, 8, 14, 14, 42, 128, (1, 1, 1), (2, 1, 1), (0, 0, 0)),
+    ("stem 3->83 7x7 s2", 2, 4, 32, 32, 3, 83, (1, 7, 7), (1, 2, 2), (0, 3, 3)),
+    ("r3d stem 3->64 3x7x7", 1, 4, 32, 32, 3, 64, (3, 7, 7), (1, 2, 2), (1, 3, 3)),
+    ("3x3x3 64->64", 2, 4, 14, 14, 64, 64, (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    ("3x3x3 s2 64->128", 2, 8, 14, 14, 64, 128, (3, 3, 3), (2, 2, 2), (1, 1, 1)),
+    ("spatial 128->288 (2 n-tiles)", 2, 4, 14, 14, 128, 288, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    ("spatial 256->576 7x7", 3, 2, 7, 7, 256, 576, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    ("temporal 921->512 s2", 3, 4, 7, 7, 921, 512, (3, 1, 1), (2, 1, 1), (1, 0, 0)),
+    ("many tiles per CTA 64->64", 24, 8, 32, 32, 64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    ("odd extents 5x9x11", 3, 5, 9, 11, 40, 72, (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+]
+
+
+def _rel(a, b):
+    return ((a - b).abs().max() / (b.abs().max() + 1e-12)).item()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_conv_trio_matches_torch(case):
+    from dualvar_b200 import kernels as K
+    torch.backends.cudnn.allow_tf32 = False
+    name, N, T, H, W, Cin, Cout, k, s, p = case
+    dev = "cuda:0"
+    g = K.make_geom(N, T, H, W, Cin, Cout, k, s, p)
+    gen = torch.Generator(device=dev).manual_seed(abs(hash(name)) % (2 ** 31))
+    x = torch.randn(N, Cin, T, H, W, device=dev, generator=gen)
+    w = torch.randn(Cout, Cin, *k, device=dev, generator=gen) / (Cin * k[0] * k[1] * k[2]) ** 0.5
+    bias = torch.randn(Cout, device=dev, generator=gen)
+    xr = x.bfloat16().float().requires_grad_(True)
+    wr = w.bfloat16().float().requires_grad_(True)
+    yr = F.conv3d(xr, wr, bias, s, p)
+    dy = torch.randn(yr.shape, device=dev, generator=gen).bfloat16().float()
+    yr.backward(dy)
+
+    x_nd = K.to_ndhwc(x)
+    assert torch.equal(K.from_ndhwc(x_nd, Cin), x.bfloat16().float())
+    wf, wt = K.pack_conv_weight(w, g)
+    stats = torch.zeros(2 * g.Cout_p, dtype=torch.float64, device=dev)
+    bias_p = torch.zeros(g.Cout_p, device=dev)
+    bias_p[:Cout] = bias
+    y_nd = K.conv3d_fprop(x_nd, wf, g, bn_stats=stats, bias=bias_p)
+    y = K.from_ndhwc(y_nd, Cout)
+    assert _rel(y, yr.detach()) < 1e-2
+    if g.Cout_p > Cout:
+        assert bool((y_nd[..., Cout:] == 0).all())
+    ys = y_nd.float()[..., :Cout].reshape(-1, Cout).double()
+    torch.testing.assert_close(stats[:Cout], ys.sum(0), rtol=1e-5, atol=1e-3)
+    torch.testing.assert_close(stats[g.Cout_p:g.Cout_p + Cout], (ys * ys).sum(0), rtol=1e-5, atol=1e-3)
+
+    dy_nd = K.to_ndhwc(dy)
+    dx = K.from_ndhwc(K.conv3d_dgrad(dy_nd, wt, g), Cin)
+    assert _rel(dx, xr.grad) < 1e-2
+    dw = K.unpack_conv_wgrad(K.conv3d_wgrad_packed(x_nd, dy_nd, g), g)
+    assert _rel(dw, wr.grad) < 1e-4          # fp32 accumulate + fp32 output
+
+
+def test_conv_linearity_at_full_size():
+    """BASELINE-size property check (no oracle at this size): conv(a*x1 + x2) with power-of-two a is
+    exactly a*conv(x1) + conv(x2) up to bf16 rounding of the stored outputs; pad channels stay zero."""
+    from dualvar_b200 import kernels as K
+    dev = "cuda:0"
+    g = K.make_geom(16, 16, 56, 56, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1))
+    gen = torch.Generator(device=dev).manual_seed(3)
+    x1 = torch.randn(16, 16, 56, 56, 64, device=dev, generator=gen).bfloat16()
+    w = torch.randn(144, 64, 1, 3, 3, device=dev, generator=gen) / 24.0
+    wf, _ = K.pack_conv_weight(w, g)
+    y1 = K.conv3d_fprop(x1, wf, g).float()
+    y2 = K.conv3d_fprop((x1.float() * 2).bfloat16(), wf, g).float()
+    assert torch.equal(y2, y1 * 2)

@@ -1,0 +1,115 @@
+"""GPU: drop-in SimCLR+DualVar modules vs the oracle on identical weights, inputs and NumPy seeds.
+Tolerance: 1e-2 relative on losses and logits (bf16 mode, BASELINE.json north_star); gradients are
+compared against the oracle's own bf16-autocast noise floor."""
+import copy
+import random
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+dev = "cuda:0"
+ARGS = SimpleNamespace(shufflerank_theta=0.05)
+
+
+def _seed(s):
+    torch.manual_seed(s); np.random.seed(s); random.seed(s)
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
+
+
+def _pair(net, mode="clip-sr-tc"):
+    from dualvar_b200 import models as PM
+    from oracle import models as OM
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    _seed(0)
+    ref = OM.SimCLR_TimeSeriesV4(net, 128, 0.07, False, True, 2, 64, 0.07, 0.07, mode, ARGS).to(dev).train()
+    prod = PM.SimCLR_TimeSeriesV4(net, 128, 0.07, False, True, 2, 64, 0.07, 0.07, mode, ARGS)
+    prod.load_state_dict(ref.state_dict())
+    return ref, prod.to(dev).train()
+
+
+@pytest.mark.parametrize("net", ["r21d", "r3d"])
+def test_simclr_dualvar_step_matches_oracle(net):
+    from dualvar_b200 import _lib
+    ref, prod = _pair(net)
+    x = torch.randn(8, 3, 3, 8, 64, 64, device=dev)
+    n0 = _lib.load().dv_launch_count()
+    np.random.seed(11); rr = ref(x)
+    np.random.seed(11); rp = prod(x)
+    assert list(rr.keys()) == list(rp.keys())
+    for k in rr:
+        assert rr[k].shape == rp[k].shape and rr[k].dtype == rp[k].dtype, k
+        if "labels" in k:
+            assert torch.equal(rr[k], rp[k])
+        elif "loss" in k:
+            assert abs(rp[k].item() - rr[k].item()) <= 1e-2 * abs(rr[k].item()), (k, rp[k].item(), rr[k].item())
+        else:
+            assert _rel(rp[k], rr[k]) < 1e-2, (k, _rel(rp[k], rr[k]))
+    lr = sum(v for k, v in rr.items() if "loss" in k)
+    lp = sum(v for k, v in rp.items() if "loss" in k)
+    lr.backward(); lp.backward()
+    assert _lib.load().dv_launch_count() - n0 > 300          # the native path really ran
+    # yardstick: the oracle itself under bf16 autocast
+    ref2 = copy.deepcopy(ref)
+    for p in ref2.parameters():
+        p.grad = None
+    np.random.seed(11)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        ra = ref2(x)
+    sum(v.float() for k, v in ra.items() if "loss" in k).backward()
+    ours, yard = [], []
+    for (n, pr), (_, pa), (_, pp) in zip(ref.named_parameters(), ref2.named_parameters(), prod.named_parameters()):
+        assert pp.grad is not None and torch.isfinite(pp.grad).all(), n
+        ours.append(_rel(pp.grad, pr.grad)); yard.append(_rel(pa.grad, pr.grad))
+    ours.sort(); yard.sort()
+    assert ours[len(ours) // 2] <= 1.5 * yard[len(yard) // 2] + 0.02, (ours[len(ours) // 2], yard[len(yard) // 2])
+    # BN running statistics were updated twice (3B pass and B pass), like the reference
+    for (n, br), (_, bp) in zip(ref.named_buffers(), prod.named_buffers()):
+        if br.dtype.is_floating_point:
+            assert _rel(bp, br) < 2e-2, n
+        else:
+            assert int(br) == int(bp) == 2, n
+
+
+def test_mode_without_tc_and_backbone_module_contract():
+    ref, prod = _pair("r3d", mode="clip-sr")
+    x = torch.randn(4, 3, 3, 8, 32, 32, device=dev)
+    np.random.seed(3); rr = ref(x)
+    np.random.seed(3); rp = prod(x)
+    assert "tc_contrast_loss" not in rp and list(rr.keys()) == list(rp.keys())
+    # backbone alone: fp32 NCDHW in, (B, 512, T', H', W') post-ReLU out (select_backbone.py:30-31)
+    clip = torch.randn(4, 3, 8, 64, 64, device=dev)
+    with torch.no_grad():
+        yr = ref.encoder_q[0](clip)
+        yp = prod.encoder_q[0](clip)
+    assert yp.shape == yr.shape == (4, 512, 1, 4, 4) and yp.dtype == torch.float32 and bool((yp >= 0).all())
+    assert _rel(yp, yr) < 5e-2
+
+
+def test_eval_mode_uses_running_statistics():
+    ref, prod = _pair("r21d")
+    clip = torch.randn(4, 3, 8, 64, 64, device=dev)
+    ref.eval(); prod.eval()
+    with torch.no_grad():
+        yr = ref.encoder_q[0](clip)
+        yp = prod.encoder_q[0](clip)
+    assert _rel(yp, yr) < 3e-2
+    for (n, br), (_, bp) in zip(ref.named_buffers(), prod.named_buffers()):
+        assert torch.equal(br, bp), n            # eval must not touch the statistics
+
+
+def test_full_size_clip_shapes():
+    """BASELINE shape (16x112x112): output extents of SURVEY.md §4 and finite values."""
+    from dualvar_b200 import backbones as PB
+    for name in ("r21d", "r3d"):
+        net, _ = PB.select_backbone(name)
+        net = net.to(dev).train()
+        with torch.no_grad():
+            y = net(torch.randn(2, 3, 16, 112, 112, device=dev))
+        assert y.shape == (2, 512, 2, 7, 7) and torch.isfinite(y).all()
