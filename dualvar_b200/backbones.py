@@ -28,15 +28,22 @@ class _Encoder(nn.Module):
     def program(self, ctx, x):  # pragma: no cover - abstract
         raise NotImplementedError
 
-    def encode(self, make_input, pooled):
-        """Run the backbone on an ingested input. pooled=True returns the (N, C) global average."""
-        return E.run_backbone(self, self.program, make_input, pooled)
+    def first_conv(self):
+        """The nn.Conv3d applied to the raw frames (decides the ingest layout)."""
+        return None
+
+    def encode(self, src, pooled, **ingest_kw):
+        """Ingest ``src`` (reference block, clip batch or RawClips) and run the backbone.
+        pooled=True returns the (N, C) global average instead of the fp32 NCDHW feature map."""
+        shape = src.block_shape if isinstance(src, E.RawClips) else tuple(src.shape)
+        conv = self.first_conv()
+        s2d = conv is not None and E.stem_eligible(conv, shape[-2], shape[-1])
+        return E.run_backbone(self, self.program, lambda: E.ingest(src, s2d=s2d, **ingest_kw), pooled)
 
     def forward(self, x):
         if not x.is_cuda:
             raise E._lib.DualVarNativeError("dualvar_b200 backbones run on a B200 only (no CPU fallback)")
-        x = x.contiguous().float()
-        return self.encode(lambda: E.ingest(x), pooled=False)
+        return self.encode(x.contiguous().float(), pooled=False)
 
 
 # ------------------------------------------------------------------------------------ R(2+1)D / R3D
@@ -142,6 +149,10 @@ class R2Plus1DNet(_Encoder):
         self.conv3 = SpatioTemporalResLayer(64, 128, 3, layer_sizes[1], block_type=block_type, downsample=True)
         self.conv4 = SpatioTemporalResLayer(128, 256, 3, layer_sizes[2], block_type=block_type, downsample=True)
         self.conv5 = SpatioTemporalResLayer(256, 512, 3, layer_sizes[3], block_type=block_type, downsample=True)
+
+    def first_conv(self):
+        c = self.conv1
+        return c.spatial_conv if hasattr(c, "spatial_conv") else c.temporal_spatial_conv
 
     def program(self, ctx, x):
         x = E.activate(ctx, self.conv1.run(ctx, x, self.bn1))

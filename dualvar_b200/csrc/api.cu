@@ -43,7 +43,13 @@ int maxpool_fwd(const void* x, void* y, const PoolGeom& g, cudaStream_t stream);
 int maxpool_bwd(const void* x, const void* y, const void* dy, void* dx, const PoolGeom& g, cudaStream_t stream);
 int ingest(const float* src, void* dst, const int* perm, long long sb, long long sv, long long sc,
            long long st, int B, int C, int T, int H, int W, int view, int nv, int n_series,
-           const float* mean, const float* stdv, cudaStream_t stream);
+           const float* mean, const float* stdv, int s2d, cudaStream_t stream);
+int conv_stem_fprop_bf16(const void* x_s2d, const void* w_stem, void* y, double* stats, const float* bias,
+                         int N, int T, int H2, int W2, int Cout_p, int kt, int pt, cudaStream_t stream);
+int conv_stem_wgrad_bf16(const void* x_s2d, const void* dy, float* dw, int N, int T, int H2, int W2,
+                         int Cout_p, int kt, int pt, cudaStream_t stream);
+int pack_stem_weights(const float* w, void* ws, int Cout, int Cin, int kt, int Cout_p, cudaStream_t stream);
+int unpack_stem_wgrad(const float* dws, float* dw, int Cout, int Cin, int kt, float beta, cudaStream_t stream);
 int sgemm(int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
           int ldb, float beta, float* C, int ldc, const float* bias, int relu, cudaStream_t stream);
 int colsum(const float* X, float* out, int M, int N, int ld, float beta, cudaStream_t stream);
@@ -64,6 +70,7 @@ int segment_bcast(const float* in, float* out, long long rows, int s, int e, flo
 int rowdot(const float* a, const float* b, float* out, int rows, int d, int ld_out, cudaStream_t stream);
 int row_axpy(const float* alpha, int ld_alpha, const float* x, float* y, int rows, int d, float beta,
              cudaStream_t stream);
+int probe_overlap(const void* src, void* out, int c1, cudaStream_t stream);
 }  // namespace dv
 
 using namespace dv;
@@ -218,10 +225,11 @@ int dv_maxpool3d_bwd(const void* x, const void* y, const void* dy, void* dx, con
 }
 int dv_ingest_clips(const float* src, void* dst, const int32_t* perm, int64_t sb, int64_t sv, int64_t sc,
                     int64_t st, int B, int C, int T, int H, int W, int view, int nv, int n_series,
-                    const float* mean_host, const float* std_host, void* stream) {
+                    const float* mean_host, const float* std_host, int s2d, void* stream) {
+  DV_REQUIRE(!s2d || (H % 2 == 0 && W % 2 == 0), "space-to-depth ingest needs even H and W");
   DV_REQUIRE(src && dst && B > 0 && C > 0 && C <= 4 && T > 0 && H > 0 && W > 0 && nv > 0, "bad ingest arguments");
   DV_REQUIRE(perm == nullptr || (n_series > 0 && T % n_series == 0), "ingest: T must divide into n_series segments");
-  return ingest(src, dst, perm, sb, sv, sc, st, B, C, T, H, W, view, nv, n_series, mean_host, std_host, ST);
+  return ingest(src, dst, perm, sb, sv, sc, st, B, C, T, H, W, view, nv, n_series, mean_host, std_host, s2d, ST);
 }
 int dv_sgemm(int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
              int ldb, float beta, float* C, int ldc, const float* bias, int relu, void* stream) {
@@ -280,6 +288,40 @@ int dv_row_axpy(const float* alpha, int ld_alpha, const float* x, float* y, int 
                 void* stream) {
   DV_REQUIRE(alpha && x && y && rows > 0, "bad row_axpy arguments");
   return row_axpy(alpha, ld_alpha, x, y, rows, d, beta, ST);
+}
+
+static int check_stem(const dv_conv_geom* g) {
+  if (int rc = check_geom(g)) return rc;
+  DV_REQUIRE(g->Cin <= 4 && g->kh == 7 && g->kw == 7 && g->sh == 2 && g->sw == 2 && g->st == 1 && g->ph == 3 &&
+                 g->pw == 3 && g->H % 2 == 0 && g->W % 2 == 0,
+             "stem path needs Cin<=4, 7x7 window, stride (1,2,2), padding (p,3,3), even H and W");
+  return kOk;
+}
+int dv_pack_stem_weight(const float* w, void* ws, const dv_conv_geom* g, void* stream) {
+  if (int rc = check_stem(g)) return rc;
+  DV_REQUIRE(w && ws, "NULL weight pointers");
+  return pack_stem_weights(w, ws, g->Cout, g->Cin, g->kt, g->Cout_p, ST);
+}
+int dv_unpack_stem_wgrad(const float* dws, float* grad, const dv_conv_geom* g, float beta, void* stream) {
+  if (int rc = check_stem(g)) return rc;
+  DV_REQUIRE(dws && grad, "NULL gradient pointers");
+  return unpack_stem_wgrad(dws, grad, g->Cout, g->Cin, g->kt, beta, ST);
+}
+int dv_conv3d_stem_fprop_bf16(const void* x_s2d, const void* ws, void* y, double* bn_stats,
+                              const float* bias_padded, const dv_conv_geom* g, void* stream) {
+  if (int rc = check_stem(g)) return rc;
+  DV_REQUIRE(x_s2d && ws && y, "NULL tensor pointer");
+  return conv_stem_fprop_bf16(x_s2d, ws, y, bn_stats, bias_padded, g->N, g->T, g->H / 2, g->W / 2, g->Cout_p,
+                              g->kt, g->pt, ST);
+}
+int dv_conv3d_stem_wgrad_bf16(const void* x_s2d, const void* dy, float* dws, const dv_conv_geom* g, void* stream) {
+  if (int rc = check_stem(g)) return rc;
+  DV_REQUIRE(x_s2d && dy && dws, "NULL tensor pointer");
+  return conv_stem_wgrad_bf16(x_s2d, dy, dws, g->N, g->T, g->H / 2, g->W / 2, g->Cout_p, g->kt, g->pt, ST);
+}
+
+int dv_debug_probe_overlap_tmap(const void* src, void* out, int c1, void* stream) {
+  return probe_overlap(src, out, c1, ST);
 }
 
 }  // extern "C"

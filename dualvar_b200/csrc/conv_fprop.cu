@@ -498,4 +498,40 @@ int conv_dgrad_bf16(const void* dy, const void* w_packed_t, void* dx, const Conv
   return kOk;
 }
 
+// Stride-2 7x7 stem (Cin <= 4) as a 4-tap (per temporal tap) stride-1 GEMM on the space-to-depth input.
+// x_s2d: bf16 [N][T][H2][W2+3][16], channel = (rh*2+rw)*4 + c, two zero columns left / one right
+// (written by the ingest kernel). For output (ho,wo) and row tap a in {-2..1} the A row is the 128-byte
+// window x_s2d[n][t][ho+a][wo .. wo+3][0..15] — an OVERLAPPING-window tensor map (W stride 32 B, inner
+// extent 128 B), so K = 64 per tap instead of 49 taps of K = 16.
+// w_stem: bf16 [Cout_p][kt*4][64] (pack_stem_weights).
+static int encode_stem_map(CUtensorMap* m, const void* x, int N, int T, int H2, int W2, const uint32_t box[5]) {
+  const long long W2p = W2 + 3;
+  uint64_t dims[5] = {64, (uint64_t)W2, (uint64_t)H2, (uint64_t)T, (uint64_t)N};
+  uint64_t strides[5] = {2, 32, (uint64_t)W2p * 32, (uint64_t)H2 * W2p * 32, (uint64_t)T * H2 * W2p * 32};
+  return encode_tmap(m, x, 2, 5, dims, strides, box, true);
+}
+
+int conv_stem_fprop_bf16(const void* x_s2d, const void* w_stem, void* y, double* stats, const float* bias,
+                         int N, int T, int H2, int W2, int Cout_p, int kt, int pt, cudaStream_t stream) {
+  static thread_local ConvTileParams P;
+  const int To = T + 2 * pt - kt + 1;
+  const View5 outv = make_ndhwc(y, N, To, H2, W2, Cout_p);
+  int ln, lt, lh, lw;
+  choose_tile(N, To, H2, W2, &ln, &lt, &lh, &lw);
+  const uint32_t box[5] = {kChunkK, 1u << lw, 1u << lh, 1u << lt, 1u << ln};
+  int rc = encode_stem_map(&P.a_map[0], x_s2d, N, T, H2, W2, box);
+  if (rc) return rc;
+  for (int i = 1; i < kMaxAMaps; ++i) P.a_map[i] = P.a_map[0];
+  int ntaps = 0;
+  for (int a = 0; a < kt; ++a)
+    for (int r = 0; r < 4; ++r) {
+      Tap& tp = P.taps[ntaps];
+      tp.map = 0; tp.dt = (int8_t)(a - pt); tp.dh = (int8_t)(r - 2); tp.dw = 0;
+      tp.widx = (int16_t)ntaps; tp.pad_ = 0;
+      ++ntaps;
+    }
+  P.num_taps = ntaps;
+  return launch_conv_tiles(P, outv, Cout_p, w_stem, Cout_p, ntaps, 64, stats, bias, stream);
+}
+
 }  // namespace dv

@@ -197,6 +197,56 @@ void choose_tile_log2(int total_log2, int N, int T, int H, int W, int* ln, int* 
 static int floordiv_w(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 static int posmod_w(int a, int b) { int m = a % b; return m < 0 ? m + b : m; }
 
+static int wgrad_launch(WgradParams& P, int ntaps, int cin_p, int cout_p, int taps_total, float* dw,
+                        cudaStream_t stream) {
+  TileGeom& g = P.g;
+  P.num_taps = ntaps;
+  P.k_chunks = ceil_div(cin_p, 64);
+  P.total_units = ntaps * P.k_chunks;
+  // N side (Cout)
+  if (cout_p <= 256) {
+    P.n_tiles = 1; P.block_n = round_up(cout_p, 16); P.last_n = P.block_n;
+  } else {
+    P.block_n = 256; P.n_tiles = ceil_div(cout_p, 256);
+    P.last_n = round_up(cout_p - (P.n_tiles - 1) * 256, 16);
+  }
+  P.acc_stride = round_up(P.block_n, 32);
+  const int nbx = ceil_div(P.block_n, 64);
+  int max_pairs = 512 / P.acc_stride;
+  int upg = max_pairs * 2;
+  if (upg > kWgMaxUnits) upg = kWgMaxUnits;
+  // keep at least 3 stages in shared memory
+  while (upg > 2 && (kWgSmemBudget - 1024) / ((upg + nbx) * kBoxBytes) < 3) upg -= 2;
+  if (upg > P.total_units) upg = P.total_units;
+  P.units_per_group = upg;
+  const int groups = ceil_div(P.total_units, upg);
+  const int stage_bytes = (upg + nbx) * kBoxBytes;
+  P.stages = (kWgSmemBudget - 1024) / stage_bytes;
+  if (P.stages > 8) P.stages = 8;
+  if (P.stages < 2) return fail(kUnsupported, "wgrad: stage too large for shared memory");
+  P.pos_tiles = g.tiles_w * g.tiles_h * g.tiles_t * g.tiles_n;
+  const int items = groups * P.n_tiles;
+  int ksplit = (2 * sm_count()) / items;
+  if (ksplit < 1) ksplit = 1;
+  if (ksplit > P.pos_tiles) ksplit = P.pos_tiles;
+  P.tiles_per_split = ceil_div(P.pos_tiles, ksplit);
+  ksplit = ceil_div(P.pos_tiles, P.tiles_per_split);
+  P.dw = dw;
+  P.cin_p = cin_p; P.cout_p = cout_p; P.taps_total = taps_total;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    DV_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kWgSmemBudget));
+    attr_set = true;
+  }
+  const int smem_bytes = 1024 + P.stages * stage_bytes;
+  dim3 grid(items, ksplit);
+  conv_wgrad_kernel<<<grid, kWgThreads, smem_bytes, stream>>>(P);
+  DV_LAUNCH_OK();
+  return kOk;
+}
+
 int conv_wgrad_bf16(const void* x, const void* dy, float* dw, const ConvGeom& c,
                     cudaStream_t stream) {
   static thread_local WgradParams P;
@@ -262,51 +312,47 @@ int conv_wgrad_bf16(const void* x, const void* dy, float* dw, const ConvGeom& c,
       }
   if (ntaps == 0) return kOk;
   for (int i = nmaps; i < kMaxAMaps; ++i) P.a_map[i] = P.a_map[0];
-  P.num_taps = ntaps;
-  P.k_chunks = ceil_div(c.Cin_p, 64);
-  P.total_units = ntaps * P.k_chunks;
-  // N side (Cout)
-  if (c.Cout_p <= 256) {
-    P.n_tiles = 1; P.block_n = round_up(c.Cout_p, 16); P.last_n = P.block_n;
-  } else {
-    P.block_n = 256; P.n_tiles = ceil_div(c.Cout_p, 256);
-    P.last_n = round_up(c.Cout_p - (P.n_tiles - 1) * 256, 16);
-  }
-  P.acc_stride = round_up(P.block_n, 32);
-  const int nbx = ceil_div(P.block_n, 64);
-  int max_pairs = 512 / P.acc_stride;
-  int upg = max_pairs * 2;
-  if (upg > kWgMaxUnits) upg = kWgMaxUnits;
-  // keep at least 3 stages in shared memory
-  while (upg > 2 && (kWgSmemBudget - 1024) / ((upg + nbx) * kBoxBytes) < 3) upg -= 2;
-  if (upg > P.total_units) upg = P.total_units;
-  P.units_per_group = upg;
-  const int groups = ceil_div(P.total_units, upg);
-  const int stage_bytes = (upg + nbx) * kBoxBytes;
-  P.stages = (kWgSmemBudget - 1024) / stage_bytes;
-  if (P.stages > 8) P.stages = 8;
-  if (P.stages < 2) return fail(kUnsupported, "wgrad: stage too large for shared memory");
-  P.pos_tiles = g.tiles_w * g.tiles_h * g.tiles_t * g.tiles_n;
-  const int items = groups * P.n_tiles;
-  int ksplit = (2 * sm_count()) / items;
-  if (ksplit < 1) ksplit = 1;
-  if (ksplit > P.pos_tiles) ksplit = P.pos_tiles;
-  P.tiles_per_split = ceil_div(P.pos_tiles, ksplit);
-  ksplit = ceil_div(P.pos_tiles, P.tiles_per_split);
-  P.dw = dw;
-  P.cin_p = c.Cin_p; P.cout_p = c.Cout_p; P.taps_total = taps_total;
+  return wgrad_launch(P, ntaps, c.Cin_p, c.Cout_p, taps_total, dw, stream);
+}
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    DV_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    kWgSmemBudget));
-    attr_set = true;
+int conv_stem_wgrad_bf16(const void* x_s2d, const void* dy, float* dw, int N, int T, int H2, int W2,
+                         int Cout_p, int kt, int pt, cudaStream_t stream) {
+  static thread_local WgradParams P;
+  const int To = T + 2 * pt - kt + 1;
+  const int taps_total = kt * 4;
+  DV_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout_p * taps_total * 64, stream));
+  TileGeom& g = P.g;
+  choose_tile_log2(6, N, To, H2, W2, &g.ln, &g.lt, &g.lh, &g.lw);
+  g.ext_w = W2; g.ext_h = H2; g.ext_t = To; g.ext_n = N;
+  g.tiles_w = ceil_div(W2, 1 << g.lw);
+  g.tiles_h = ceil_div(H2, 1 << g.lh);
+  g.tiles_t = ceil_div(To, 1 << g.lt);
+  g.tiles_n = ceil_div(N, 1 << g.ln);
+  const uint32_t box[5] = {64, 1u << g.lw, 1u << g.lh, 1u << g.lt, 1u << g.ln};
+  {
+    uint64_t dims[5] = {(uint64_t)Cout_p, (uint64_t)W2, (uint64_t)H2, (uint64_t)To, (uint64_t)N};
+    uint64_t strides[5] = {2, (uint64_t)Cout_p * 2, (uint64_t)W2 * Cout_p * 2, (uint64_t)H2 * W2 * Cout_p * 2,
+                           (uint64_t)To * H2 * W2 * Cout_p * 2};
+    int rc = encode_tmap(&P.dy_map, dy, 2, 5, dims, strides, box, true);
+    if (rc) return rc;
   }
-  const int smem_bytes = 1024 + P.stages * stage_bytes;
-  dim3 grid(items, ksplit);
-  conv_wgrad_kernel<<<grid, kWgThreads, smem_bytes, stream>>>(P);
-  DV_LAUNCH_OK();
-  return kOk;
+  {
+    const long long W2p = W2 + 3;
+    uint64_t dims[5] = {64, (uint64_t)W2, (uint64_t)H2, (uint64_t)T, (uint64_t)N};
+    uint64_t strides[5] = {2, 32, (uint64_t)W2p * 32, (uint64_t)H2 * W2p * 32, (uint64_t)T * H2 * W2p * 32};
+    int rc = encode_tmap(&P.a_map[0], x_s2d, 2, 5, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  for (int i = 1; i < kMaxAMaps; ++i) P.a_map[i] = P.a_map[0];
+  int ntaps = 0;
+  for (int a = 0; a < kt; ++a)
+    for (int r = 0; r < 4; ++r) {
+      Tap& tp = P.taps[ntaps];
+      tp.map = 0; tp.dt = (int8_t)(a - pt); tp.dh = (int8_t)(r - 2); tp.dw = 0;
+      tp.widx = (int16_t)ntaps; tp.pad_ = 0;
+      ++ntaps;
+    }
+  return wgrad_launch(P, ntaps, 64, Cout_p, taps_total, dw, stream);
 }
 
 }  // namespace dv

@@ -120,4 +120,58 @@ int ndhwc_to_ncdhw(const void* y, float* x, int N, int C, int Cp, long long S, c
   return kOk;
 }
 
+// Stem weights for the space-to-depth formulation (conv_fprop.cu: conv_stem_fprop_bf16).
+// w: fp32 [Cout][Cin<=4][kt][7][7] -> ws: bf16 [Cout_p][kt*4][64],
+// ws[co][kt_i*4 + a][b*16 + (rh*2+rw)*4 + c] = w[co][c][kt_i][2a+rh-1][2b+rw-1] (0 outside the 7x7 window).
+__global__ void pack_stem_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ ws,
+                                         int Cout, int Cin, int kt, int Cout_p) {
+  const long long total = (long long)Cout_p * kt * 4 * 64;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % 64);
+    const int a = (int)((i / 64) % 4);
+    const int kti = (int)((i / 256) % kt);
+    const int co = (int)(i / (256LL * kt));
+    const int b = k >> 4, rh = (k >> 3) & 1, rw = (k >> 2) & 1, c = k & 3;
+    const int kh = 2 * a + rh - 1, kw = 2 * b + rw - 1;
+    float v = 0.f;
+    if (co < Cout && c < Cin && kh >= 0 && kh < 7 && kw >= 0 && kw < 7)
+      v = w[((((long long)co * Cin + c) * kt + kti) * 7 + kh) * 7 + kw];
+    ws[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// dws: fp32 [Cout_p][kt*4][64] -> dw: fp32 [Cout][Cin][kt][7][7]; dw = beta*dw + gathered value
+__global__ void unpack_stem_wgrad_kernel(const float* __restrict__ dws, float* __restrict__ dw, int Cout,
+                                         int Cin, int kt, float beta) {
+  const long long total = (long long)Cout * Cin * kt * 49;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int kw = (int)(i % 7);
+    const int kh = (int)((i / 7) % 7);
+    const int kti = (int)((i / 49) % kt);
+    const int c = (int)((i / (49LL * kt)) % Cin);
+    const int co = (int)(i / (49LL * kt * Cin));
+    const int a = (kh + 1) >> 1, rh = (kh + 1) & 1, b = (kw + 1) >> 1, rw = (kw + 1) & 1;
+    const float g = dws[(((long long)co * kt + kti) * 4 + a) * 64 + b * 16 + (rh * 2 + rw) * 4 + c];
+    dw[i] = (beta != 0.f) ? fmaf(beta, dw[i], g) : g;
+  }
+}
+
+int pack_stem_weights(const float* w, void* ws, int Cout, int Cin, int kt, int Cout_p, cudaStream_t stream) {
+  const long long total = (long long)Cout_p * kt * 256;
+  pack_stem_weights_kernel<<<(int)std::min<long long>(ceil_div_ll(total, 256), 1184), 256, 0, stream>>>(
+      w, (__nv_bfloat16*)ws, Cout, Cin, kt, Cout_p);
+  DV_LAUNCH_OK();
+  return kOk;
+}
+
+int unpack_stem_wgrad(const float* dws, float* dw, int Cout, int Cin, int kt, float beta, cudaStream_t stream) {
+  const long long total = (long long)Cout * Cin * kt * 49;
+  unpack_stem_wgrad_kernel<<<(int)std::min<long long>(ceil_div_ll(total, 256), 1184), 256, 0, stream>>>(
+      dws, dw, Cout, Cin, kt, beta);
+  DV_LAUNCH_OK();
+  return kOk;
+}
+
 }  // namespace dv

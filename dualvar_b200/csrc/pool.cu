@@ -210,6 +210,59 @@ __global__ void __launch_bounds__(256) ingest_kernel(const IngestArgs a) {
   }
 }
 
+
+// Space-to-depth ingest for the stride-2 7x7 stems: dst bf16 [B*nv][T][H/2][W/2+3][16],
+// dst[n][t][hs][ws+2][(rh*2+rw)*4 + c] = norm(src(b, v, c, t, 2*hs+rh, 2*ws+rw)); two zero columns on the
+// left and one on the right so that every 4-position window the stem reads is in bounds.
+__global__ void __launch_bounds__(256) ingest_s2d_kernel(const IngestArgs a) {
+  const int H2 = a.H >> 1, W2 = a.W >> 1, W2p = W2 + 3;
+  const long long per_t = (long long)H2 * W2p;
+  const long long total = (long long)a.B * a.nv * a.T * per_t;
+  const int seg_len = a.n_series > 0 ? a.T / a.n_series : a.T;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int wsp = (int)(i % W2p);
+    const int hs = (int)((i / W2p) % H2);
+    const int t = (int)((i / per_t) % a.T);
+    const int n = (int)(i / (per_t * a.T));
+    uint4 o0 = make_uint4(0, 0, 0, 0), o1 = o0;
+    const int ws = wsp - 2;
+    if (ws >= 0 && ws < W2) {
+      const int b = n / a.nv;
+      const int vw = a.view + (n - b * a.nv);
+      int ts = t;
+      if (a.perm) {
+        const int seg = t / seg_len;
+        ts = a.perm[n * a.n_series + seg] * seg_len + (t - seg * seg_len);
+      }
+      const float* p = a.src + b * a.sb + vw * a.sv + ts * a.st + (long long)(2 * hs) * a.W + 2 * ws;
+      float v[2][2][4];
+#pragma unroll
+      for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float2 f = make_float2(0.f, 0.f);
+          if (c < a.C) {
+            f = *reinterpret_cast<const float2*>(p + c * a.sc + rh * a.W);
+            f.x = (f.x - a.mean[c]) * a.inv_std[c];
+            f.y = (f.y - a.mean[c]) * a.inv_std[c];
+          }
+          v[rh][0][c] = f.x;
+          v[rh][1][c] = f.y;
+        }
+      __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+      __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+      h0[0] = __floats2bfloat162_rn(v[0][0][0], v[0][0][1]); h0[1] = __floats2bfloat162_rn(v[0][0][2], v[0][0][3]);
+      h0[2] = __floats2bfloat162_rn(v[0][1][0], v[0][1][1]); h0[3] = __floats2bfloat162_rn(v[0][1][2], v[0][1][3]);
+      h1[0] = __floats2bfloat162_rn(v[1][0][0], v[1][0][1]); h1[1] = __floats2bfloat162_rn(v[1][0][2], v[1][0][3]);
+      h1[2] = __floats2bfloat162_rn(v[1][1][0], v[1][1][1]); h1[3] = __floats2bfloat162_rn(v[1][1][2], v[1][1][3]);
+    }
+    uint4* d = reinterpret_cast<uint4*>(a.dst + i * 16);
+    d[0] = o0;
+    d[1] = o1;
+  }
+}
+
 // ---------------------------------------------------------------------------------- host
 static int flat_grid(long long total, int threads) {
   long long g = ceil_div_ll(total, threads);
@@ -255,7 +308,7 @@ int maxpool_bwd(const void* x, const void* y, const void* dy, void* dx, const Po
 
 int ingest(const float* src, void* dst, const int* perm, long long sb, long long sv, long long sc,
            long long st, int B, int C, int T, int H, int W, int view, int nv, int n_series,
-           const float* mean, const float* stdv, cudaStream_t stream) {
+           const float* mean, const float* stdv, int s2d, cudaStream_t stream) {
   IngestArgs a;
   a.src = src; a.dst = (__nv_bfloat16*)dst; a.perm = perm;
   a.sb = sb; a.sv = sv; a.sc = sc; a.st = st;
@@ -263,6 +316,12 @@ int ingest(const float* src, void* dst, const int* perm, long long sb, long long
   for (int c = 0; c < 4; ++c) {
     a.mean[c] = (mean && c < C) ? mean[c] : 0.f;
     a.inv_std[c] = (stdv && c < C) ? 1.f / stdv[c] : 1.f;
+  }
+  if (s2d) {
+    const long long total2 = (long long)B * nv * T * (H / 2) * (W / 2 + 3);
+    ingest_s2d_kernel<<<flat_grid(total2, 256), 256, 0, stream>>>(a);
+    DV_LAUNCH_OK();
+    return kOk;
   }
   const long long total = (long long)B * nv * T * H * W;
   ingest_kernel<<<flat_grid(total, 256), 256, 0, stream>>>(a);

@@ -28,13 +28,14 @@ call = _lib.call
 class Act:
     """A bf16 NDHWC activation [N,T,H,W,Cp] with C logical channels and an optional gradient."""
 
-    __slots__ = ("data", "C", "grad", "needs_grad")
+    __slots__ = ("data", "C", "grad", "needs_grad", "s2d")
 
-    def __init__(self, data, C, needs_grad=True):
+    def __init__(self, data, C, needs_grad=True, s2d=None):
         self.data = data
         self.C = C
         self.grad = None
         self.needs_grad = needs_grad
+        self.s2d = s2d          # (N, T, H, W) of the original frames when data is the space-to-depth stem layout
 
     @property
     def shape5(self):
@@ -53,7 +54,7 @@ class Act:
 class RawBN:
     """Un-normalised conv output + everything BN needs, between conv_stats() and activate()."""
 
-    __slots__ = ("y", "ss", "saved", "geom", "x", "conv", "bn", "packed", "count", "sync")
+    __slots__ = ("y", "ss", "saved", "geom", "x", "conv", "bn", "packed", "count", "sync", "stem")
 
 
 class Context:
@@ -94,6 +95,26 @@ def packed_weights(conv):
     call("dv_pack_conv_weight", ptr(w.detach()), ptr(wf), ptr(wt), ctypes.byref(g), stream_ptr())
     _weight_cache[key] = (ver, wf, wt)
     return wf, wt
+
+
+def packed_stem_weights(conv, g):
+    """bf16 [Cout_p][kt*4][64] stem weights for the space-to-depth formulation."""
+    w = conv.weight
+    key = ("stem", id(w))
+    ver = (w._version, w.data_ptr())
+    hit = _weight_cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    ws = torch.empty((g.Cout_p, g.kt * 4, 64), dtype=torch.bfloat16, device=w.device)
+    call("dv_pack_stem_weight", ptr(w.detach()), ptr(ws), ctypes.byref(g), stream_ptr())
+    _weight_cache[key] = (ver, ws)
+    return ws
+
+
+def stem_eligible(conv, H, W):
+    """Stride-2 7x7 first conv on <=4 channels with even frame size -> space-to-depth stem kernels."""
+    return (conv.weight.shape[1] <= 4 and tuple(conv.weight.shape[3:]) == (7, 7) and tuple(conv.stride) == (1, 2, 2)
+            and tuple(conv.padding)[1:] == (3, 3) and H % 2 == 0 and W % 2 == 0)
 
 
 def _bias_padded(conv, Cp):
@@ -138,7 +159,7 @@ class RawClips:
         return (B, self.n_views, C, VT // self.n_views, H, W)
 
 
-def ingest(src, first_view=0, n_views=None, perm=None, n_series=0):
+def ingest(src, first_view=0, n_views=None, perm=None, n_series=0, s2d=False):
     """Clips -> bf16 NDHWC Act with 8 channels. ``src`` is the reference block (B, V, C, T, H, W)
     fp32, a plain clip batch (B, C, T, H, W), or RawClips. Output clip order is (b, view) with views
     first_view .. first_view+n_views-1, matching block.view(-1, C, T, H, W) (model/simclr.py:352)."""
@@ -159,29 +180,42 @@ def ingest(src, first_view=0, n_views=None, perm=None, n_series=0):
         V = 1
         sb, sv, sc, st = C * T * H * W, 0, T * H * W, H * W
     nv = V - first_view if n_views is None else n_views
-    dst = torch.empty((B * nv, T, H, W, 8), dtype=torch.bfloat16, device=t.device)
+    if s2d:
+        dst = torch.empty((B * nv, T, H // 2, W // 2 + 3, 16), dtype=torch.bfloat16, device=t.device)
+    else:
+        dst = torch.empty((B * nv, T, H, W, 8), dtype=torch.bfloat16, device=t.device)
     call("dv_ingest_clips", ptr(t), ptr(dst), ptr(perm), sb, sv, sc, st, B, C, T, H, W, first_view, nv,
-         n_series, mean, std, stream_ptr())
-    return Act(dst, C, needs_grad=False)
+         n_series, mean, std, 1 if s2d else 0, stream_ptr())
+    return Act(dst, C, needs_grad=False, s2d=(B * nv, T, H, W) if s2d else None)
 
 
 def conv_stats(ctx, x, conv, bn):
     """y = conv(x) (raw, bf16) with fused per-channel sum/sumsq, then BN finalize -> scale/shift.
     Reference: nn.Conv3d + the statistics half of nn.BatchNorm3d (e.g. backbone/r21d.py:68)."""
-    N, T, H, W, Cin_p = x.shape5
     w = conv.weight
     Cout, Cin = w.shape[0], w.shape[1]
+    stem = x.s2d is not None
+    if stem:
+        N, T, H, W = x.s2d
+    else:
+        N, T, H, W, Cin_p = x.shape5
     g = make_geom(N, T, H, W, Cin, Cout, tuple(w.shape[2:]), tuple(conv.stride), tuple(conv.padding))
-    assert g.Cin_p == Cin_p, (g.Cin_p, Cin_p)
-    wf, wt = packed_weights(conv)
     dev = x.data.device
     y = torch.empty((N, g.To, g.Ho, g.Wo, g.Cout_p), dtype=torch.bfloat16, device=dev)
     training_stats = ctx.training and bn.training if bn is not None else False
     stats = torch.zeros(2 * g.Cout_p, dtype=torch.float64, device=dev) if training_stats else None
-    call("dv_conv3d_fprop_bf16", ptr(x.data), ptr(wf), ptr(y), ptr(stats), ptr(_bias_padded(conv, g.Cout_p)),
-         ctypes.byref(g), stream_ptr())
+    if stem:
+        assert stem_eligible(conv, H, W), "space-to-depth input needs a stride-2 7x7 first conv"
+        packed = (packed_stem_weights(conv, g), None)
+        call("dv_conv3d_stem_fprop_bf16", ptr(x.data), ptr(packed[0]), ptr(y), ptr(stats),
+             ptr(_bias_padded(conv, g.Cout_p)), ctypes.byref(g), stream_ptr())
+    else:
+        assert g.Cin_p == Cin_p, (g.Cin_p, Cin_p)
+        packed = packed_weights(conv)
+        call("dv_conv3d_fprop_bf16", ptr(x.data), ptr(packed[0]), ptr(y), ptr(stats),
+             ptr(_bias_padded(conv, g.Cout_p)), ctypes.byref(g), stream_ptr())
     r = RawBN()
-    r.y, r.geom, r.x, r.conv, r.bn, r.packed = y, g, x, conv, bn, (wf, wt)
+    r.y, r.geom, r.x, r.conv, r.bn, r.packed, r.stem = y, g, x, conv, bn, packed, stem
     r.count = float(N * g.To * g.Ho * g.Wo)
     r.sync = False
     if bn is None:
@@ -207,10 +241,15 @@ def conv_stats(ctx, x, conv, bn):
 def _conv_backward(ctx, r, dy):
     """wgrad into the parameter-gradient sink, dgrad into r.x.grad."""
     g = r.geom
-    dwp = torch.empty((g.Cout_p, g.taps, g.Cin_p), dtype=torch.float32, device=dy.device)
-    call("dv_conv3d_wgrad_bf16", ptr(r.x.data), ptr(dy), ptr(dwp), ctypes.byref(g), stream_ptr())
     gw = torch.empty_like(r.conv.weight)
-    call("dv_unpack_conv_wgrad", ptr(dwp), ptr(gw), ctypes.byref(g), ctypes.c_float(0.0), stream_ptr())
+    if r.stem:
+        dwp = torch.empty((g.Cout_p, g.kt * 4, 64), dtype=torch.float32, device=dy.device)
+        call("dv_conv3d_stem_wgrad_bf16", ptr(r.x.data), ptr(dy), ptr(dwp), ctypes.byref(g), stream_ptr())
+        call("dv_unpack_stem_wgrad", ptr(dwp), ptr(gw), ctypes.byref(g), ctypes.c_float(0.0), stream_ptr())
+    else:
+        dwp = torch.empty((g.Cout_p, g.taps, g.Cin_p), dtype=torch.float32, device=dy.device)
+        call("dv_conv3d_wgrad_bf16", ptr(r.x.data), ptr(dy), ptr(dwp), ctypes.byref(g), stream_ptr())
+        call("dv_unpack_conv_wgrad", ptr(dwp), ptr(gw), ctypes.byref(g), ctypes.c_float(0.0), stream_ptr())
     ctx.add_param_grad(r.conv.weight, gw)
     if r.conv.bias is not None:
         # a bias in front of training-mode BN has exactly zero gradient (BN removes the mean)

@@ -69,7 +69,7 @@ class SimCLR_Naked(nn.Module):
         block, shape = _check_input(block)
         B, n_views = shape[:2]
         assert n_views == 2
-        pooled = self.encoder_q[0].encode(lambda: E.ingest(block), pooled=True)
+        pooled = self.encoder_q[0].encode(block, pooled=True)
         f = _head(self.encoder_q[2:], pooled) if self.nonlinear else pooled
         f = O.l2norm(f).view(B, n_views, -1)
         return self.calc_contrast_loss(f, n_views, 'clip_')
@@ -127,7 +127,7 @@ class SimCLR_TimeSeriesV4(nn.Module):
         backbone = self.encoder_q[0]
         dev = block.device
         # pass 1: all 3B clips in (b, view) order, one batch -> BN statistics over 3B (model/simclr.py:352-357)
-        pooled = backbone.encode(lambda: E.ingest(block), pooled=True)                  # (3B, fs)
+        pooled = backbone.encode(block, pooled=True)                                    # (3B, fs)
         ret = dict()
         if self.with_clip:
             f = _head(self.encoder_q[2:], pooled) if len(self.encoder_q) > 2 else pooled
@@ -140,8 +140,7 @@ class SimCLR_TimeSeriesV4(nn.Module):
             # pass 2: view 2 with its T/s-frame segments permuted per sample; the permutation is folded
             # into the ingest kernel's addressing (model/simclr.py:378-387)
             perm = _draw_perms(B, s, dev)
-            pooled_s = backbone.encode(
-                lambda: E.ingest(block, first_view=2, n_views=1, perm=perm, n_series=s), pooled=True)  # (B, fs)
+            pooled_s = backbone.encode(block, pooled=True, first_view=2, n_views=1, perm=perm, n_series=s)  # (B, fs)
             shuf = _head(self.series_proj_head, pooled_s).view(B, s, e)
             shuf = O.l2norm(O.PermuteSegmentsFn.apply(shuf, perm))
             theta = self.args.shufflerank_theta
@@ -178,7 +177,7 @@ class LinearClassifier(nn.Module):
 
     def forward(self, block):
         block, _ = _check_input(block)
-        feat3d = self.backbone.encode(lambda: E.ingest(block), pooled=True)
+        feat3d = self.backbone.encode(block, pooled=True)
         if self.use_l2_norm:
             feat3d = O.l2norm(feat3d)
         logit = self.final_fc(self.final_bn(feat3d) if self.use_final_bn else feat3d)

@@ -112,10 +112,12 @@ int dv_maxpool3d_bwd(const void* x, const void* y, const void* dy, void* dx, con
  * (model/simclr.py:352). Optional Normalize (mean_host/std_host, C floats on the HOST, NULL = identity;
  * utils/transforms.py:57-63 + the view/transpose of pretrain.py:386-389 expressed through the strides)
  * and optional segment shuffle: perm int32 [B*nv][n_series] on the device, output segment j of clip n
- * reads source segment perm[n][j] (model/simclr.py:378-383). */
+ * reads source segment perm[n][j] (model/simclr.py:378-383).
+ * s2d != 0 writes the space-to-depth layout [B*nv][T][H/2][W/2+3][16] (channel (rh*2+rw)*4+c, 2 zero
+ * columns left, 1 right) consumed by dv_conv3d_stem_*; otherwise [B*nv][T][H][W][8]. */
 int dv_ingest_clips(const float* src, void* dst, const int32_t* perm, int64_t sb, int64_t sv, int64_t sc,
                     int64_t st, int B, int C, int T, int H, int W, int view, int nv, int n_series,
-                    const float* mean_host, const float* std_host, void* stream);
+                    const float* mean_host, const float* std_host, int s2d, void* stream);
 
 /* ---- fp32 heads and objectives --------------------------------------------------------------- */
 /* C = alpha*op(A)*op(B) + beta*C (+bias[n]) (relu). Row-major. ta: A stored [K][M]; tb: B stored [N][K].
@@ -149,6 +151,20 @@ int dv_segment_bcast(const float* in, float* out, int64_t rows, int s, int e, fl
 int dv_rowdot(const float* a, const float* b, float* out, int rows, int d, int ld_out, void* stream);
 int dv_row_axpy(const float* alpha, int ld_alpha, const float* x, float* y, int rows, int d, float beta,
                 void* stream);
+
+/* ---- stride-2 7x7 stem (Cin <= 4) on the space-to-depth input -------------------------------------
+ * Replaces the first nn.Conv3d of R(2+1)D / R3D / S3D (backbone/r21d.py:227, backbone/r3d.py:139,
+ * backbone/s3dg.py:143): geometry g describes the ORIGINAL conv (H, W = frame size, kernel (kt,7,7),
+ * stride (1,2,2), padding (pt,3,3)). Packed stem weights: bf16 [Cout_p][kt*4][64]; packed gradient fp32
+ * of the same shape. */
+int dv_pack_stem_weight(const float* w, void* ws, const dv_conv_geom* g, void* stream);
+int dv_unpack_stem_wgrad(const float* dws, float* grad, const dv_conv_geom* g, float beta, void* stream);
+int dv_conv3d_stem_fprop_bf16(const void* x_s2d, const void* ws, void* y, double* bn_stats,
+                              const float* bias_padded, const dv_conv_geom* g, void* stream);
+int dv_conv3d_stem_wgrad_bf16(const void* x_s2d, const void* dy, float* dws, const dv_conv_geom* g, void* stream);
+
+/* debug probe (tests only): TMA tensor map with overlapping windows */
+int dv_debug_probe_overlap_tmap(const void* src, void* out, int c1, void* stream);
 
 #ifdef __cplusplus
 }

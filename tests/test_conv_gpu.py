@@ -82,3 +82,41 @@ def test_conv_linearity_at_full_size():
     y1 = K.conv3d_fprop(x1, wf, g).float()
     y2 = K.conv3d_fprop((x1.float() * 2).bfloat16(), wf, g).float()
     assert torch.equal(y2, y1 * 2)
+
+
+@pytest.mark.parametrize("kt,pt,Cout", [(1, 0, 83), (3, 1, 64)])
+def test_space_to_depth_stem_matches_torch(kt, pt, Cout):
+    """Stride-2 7x7 stem on the space-to-depth ingest (overlapping-window TMA map) vs torch conv3d."""
+    import ctypes
+    from dualvar_b200 import _lib, engine as E, kernels as K
+    torch.backends.cudnn.allow_tf32 = False
+    dev = "cuda:0"
+    N, T, H, W = 5, 4, 36, 44
+    gen = torch.Generator(device=dev).manual_seed(kt)
+    x = torch.randn(N, 3, T, H, W, device=dev, generator=gen)
+    w = torch.randn(Cout, 3, kt, 7, 7, device=dev, generator=gen) / (3 * kt * 49) ** 0.5
+    xr = x.bfloat16().float()
+    wr = w.bfloat16().float().requires_grad_(True)
+    yr = F.conv3d(xr, wr, None, (1, 2, 2), (pt, 3, 3))
+    dy = torch.randn(yr.shape, device=dev, generator=gen).bfloat16().float()
+    yr.backward(dy)
+    g = K.make_geom(N, T, H, W, 3, Cout, (kt, 7, 7), (1, 2, 2), (pt, 3, 3))
+    xa = E.ingest(x, s2d=True)
+    assert xa.data.shape == (N, T, H // 2, W // 2 + 3, 16)
+    ws = torch.empty((g.Cout_p, kt * 4, 64), dtype=torch.bfloat16, device=dev)
+    _lib.call("dv_pack_stem_weight", _lib.ptr(w), _lib.ptr(ws), ctypes.byref(g), _lib.stream_ptr())
+    y_nd = torch.empty((N, g.To, g.Ho, g.Wo, g.Cout_p), dtype=torch.bfloat16, device=dev)
+    stats = torch.zeros(2 * g.Cout_p, dtype=torch.float64, device=dev)
+    _lib.call("dv_conv3d_stem_fprop_bf16", _lib.ptr(xa.data), _lib.ptr(ws), _lib.ptr(y_nd), _lib.ptr(stats), None,
+              ctypes.byref(g), _lib.stream_ptr())
+    assert _rel(K.from_ndhwc(y_nd, Cout), yr.detach()) < 1e-2
+    ys = y_nd.float()[..., :Cout].reshape(-1, Cout).double()
+    torch.testing.assert_close(stats[:Cout], ys.sum(0), rtol=1e-5, atol=1e-3)
+    dws = torch.empty((g.Cout_p, kt * 4, 64), dtype=torch.float32, device=dev)
+    dw = torch.empty_like(w)
+    dy_nd = K.to_ndhwc(dy)
+    _lib.call("dv_conv3d_stem_wgrad_bf16", _lib.ptr(xa.data), _lib.ptr(dy_nd), _lib.ptr(dws), ctypes.byref(g),
+              _lib.stream_ptr())
+    _lib.call("dv_unpack_stem_wgrad", _lib.ptr(dws), _lib.ptr(dw), ctypes.byref(g), ctypes.c_float(0.0),
+              _lib.stream_ptr())
+    assert _rel(dw, wr.grad) < 1e-4
