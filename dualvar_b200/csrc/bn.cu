@@ -144,6 +144,7 @@ struct BwdArgs {
   int o_ld, o_coff;   // layout of dout / out rows
   int relu;
   double* sums;       // reduce
+  const float* ss;    // optional [2][Cp] forward scale/shift: ReLU mask = (scale*y + shift > 0), `out` not read
   const float* coef;  // apply: [3][Cp] A, B, C
   __nv_bfloat16* dy;  // apply
   __nv_bfloat16* g_out;  // apply: optional masked gradient (residual branch), dense [rows][Cp]
@@ -159,16 +160,23 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BwdArgs a) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) { sg[i] = 0.f; sgy[i] = 0.f; }
     if (cg < G) {
+      Vec8 fs, fb;
+      if (a.ss) { fs = loadf8(a.ss + cg * 8); fb = loadf8(a.ss + a.Cp + cg * 8); }
       for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < a.rows;
            r += (long long)gridDim.x * blockDim.y) {
         const long long ooff = r * a.o_ld + a.o_coff + cg * 8;
         Vec8 d = load8(a.dout + ooff);
-        if (a.relu) {
-          const Vec8 o = load8(a.out + ooff);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) d.v[i] = o.v[i] > 0.f ? d.v[i] : 0.f;
-        }
         const Vec8 yv = load8(a.y + r * a.Cp + cg * 8);
+        if (a.relu) {
+          if (a.ss) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d.v[i] = fmaf(yv.v[i], fs.v[i], fb.v[i]) > 0.f ? d.v[i] : 0.f;
+          } else {
+            const Vec8 o = load8(a.out + ooff);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d.v[i] = o.v[i] > 0.f ? d.v[i] : 0.f;
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) { sg[i] += d.v[i]; sgy[i] = fmaf(d.v[i], yv.v[i], sgy[i]); }
       }
@@ -226,18 +234,25 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdArgs a) {
   for (int cg = threadIdx.x; cg < G; cg += blockDim.x) {
     const Vec8 A = loadf8(a.coef + cg * 8), B = loadf8(a.coef + a.Cp + cg * 8),
                C = loadf8(a.coef + 2 * a.Cp + cg * 8);
+    Vec8 fs, fb;
+    if (a.ss) { fs = loadf8(a.ss + cg * 8); fb = loadf8(a.ss + a.Cp + cg * 8); }
     for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < a.rows;
          r += (long long)gridDim.x * blockDim.y) {
       const long long ooff = r * a.o_ld + a.o_coff + cg * 8;
       Vec8 d = load8(a.dout + ooff);
-      if (a.relu) {
-        const Vec8 o = load8(a.out + ooff);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) d.v[i] = o.v[i] > 0.f ? d.v[i] : 0.f;
-      }
       const long long off = r * a.Cp + cg * 8;
-      if (a.g_out) store8(a.g_out + off, d);
       const Vec8 yv = load8(a.y + off);
+      if (a.relu) {
+        if (a.ss) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d.v[i] = fmaf(yv.v[i], fs.v[i], fb.v[i]) > 0.f ? d.v[i] : 0.f;
+        } else {
+          const Vec8 o = load8(a.out + ooff);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d.v[i] = o.v[i] > 0.f ? d.v[i] : 0.f;
+        }
+      }
+      if (a.g_out) store8(a.g_out + off, d);
       Vec8 o;
 #pragma unroll
       for (int i = 0; i < 8; ++i) o.v[i] = fmaf(A.v[i], d.v[i], fmaf(B.v[i], yv.v[i], C.v[i]));
@@ -300,9 +315,10 @@ int bn_apply(const void* y1, const float* ss1, const void* y2, const float* ss2,
   return kOk;
 }
 
-int bn_bwd_reduce(const void* dout, const void* out, const void* y, double* sums, long long rows,
-                  int Cp, int o_ld, int o_coff, int relu, cudaStream_t stream) {
+int bn_bwd_reduce(const void* dout, const void* out, const void* y, const float* ss, double* sums,
+                  long long rows, int Cp, int o_ld, int o_coff, int relu, cudaStream_t stream) {
   BwdArgs a = {};
+  a.ss = ss;
   a.dout = (const __nv_bfloat16*)dout; a.out = (const __nv_bfloat16*)out;
   a.y = (const __nv_bfloat16*)y; a.rows = rows; a.Cp = Cp; a.o_ld = o_ld; a.o_coff = o_coff;
   a.relu = relu; a.sums = sums;
@@ -323,10 +339,11 @@ int bn_bwd_finalize(const double* sums_local, const double* sums_global, const f
   return kOk;
 }
 
-int bn_bwd_apply(const void* dout, const void* out, const void* y, const float* coef, void* dy,
-                 void* g_out, long long rows, int Cp, int o_ld, int o_coff, int relu,
+int bn_bwd_apply(const void* dout, const void* out, const void* y, const float* ss, const float* coef,
+                 void* dy, void* g_out, long long rows, int Cp, int o_ld, int o_coff, int relu,
                  cudaStream_t stream) {
   BwdArgs a = {};
+  a.ss = ss;
   a.dout = (const __nv_bfloat16*)dout; a.out = (const __nv_bfloat16*)out;
   a.y = (const __nv_bfloat16*)y; a.rows = rows; a.Cp = Cp; a.o_ld = o_ld; a.o_coff = o_coff;
   a.relu = relu; a.coef = coef; a.dy = (__nv_bfloat16*)dy; a.g_out = (__nv_bfloat16*)g_out;

@@ -287,12 +287,14 @@ def activate(ctx, r1, r2=None, res=None, relu=True, out=None, out_coff=0):
         assert dout is not None, "activation has no gradient"
         need_g = res is not None and res.needs_grad
         g_buf = None
+        # plain relu(BN(y)): the mask is recomputed from y, `out` is not re-read
+        mask_ss = ptr(r1.ss) if (relu and r2 is None and res is None) else None
         for i, r in enumerate((r1, r2)):
             if r is None:
                 continue
             sums = torch.zeros(2 * Cp, dtype=torch.float64, device=dev)
-            call("dv_bn_bwd_reduce", ptr(dout), ptr(out_t), ptr(r.y), ptr(sums), rows, Cp, out_ld, out_coff,
-                 1 if relu else 0, stream_ptr())
+            call("dv_bn_bwd_reduce", ptr(dout), ptr(out_t), ptr(r.y), mask_ss, ptr(sums), rows, Cp, out_ld,
+                 out_coff, 1 if relu else 0, stream_ptr())
             sums_g = sums
             if r.sync:
                 sums_g = sums.clone()
@@ -310,7 +312,7 @@ def activate(ctx, r1, r2=None, res=None, relu=True, out=None, out_coff=0):
             want_g = need_g and g_buf is None
             if want_g:
                 g_buf = torch.empty_like(r.y)
-            call("dv_bn_bwd_apply", ptr(dout), ptr(out_t), ptr(r.y), ptr(coef), ptr(dy),
+            call("dv_bn_bwd_apply", ptr(dout), ptr(out_t), ptr(r.y), mask_ss, ptr(coef), ptr(dy),
                  ptr(g_buf) if want_g else None, rows, Cp, out_ld, out_coff, 1 if relu else 0, stream_ptr())
             _conv_backward(ctx, r, dy)
         if need_g:
