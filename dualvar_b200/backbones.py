@@ -32,13 +32,19 @@ class _Encoder(nn.Module):
         """The nn.Conv3d applied to the raw frames (decides the ingest layout)."""
         return None
 
-    def encode(self, src, pooled, **ingest_kw):
-        """Ingest ``src`` (reference block, clip batch or RawClips) and run the backbone.
-        pooled=True returns the (N, C) global average instead of the fp32 NCDHW feature map."""
+    def wants_s2d(self, src):
         shape = src.block_shape if isinstance(src, E.RawClips) else tuple(src.shape)
         conv = self.first_conv()
-        s2d = conv is not None and E.stem_eligible(conv, shape[-2], shape[-1])
-        return E.run_backbone(self, self.program, lambda: E.ingest(src, s2d=s2d, **ingest_kw), pooled)
+        return conv is not None and E.stem_eligible(conv, shape[-2], shape[-1])
+
+    def encode(self, src, pooled, make_input=None, **ingest_kw):
+        """Ingest ``src`` (reference block, clip batch or RawClips) and run the backbone.
+        pooled=True returns the (N, C) global average instead of the fp32 NCDHW feature map.
+        ``make_input`` (optional) builds the input Act itself (e.g. several ingests into one batch)."""
+        if make_input is None:
+            s2d = self.wants_s2d(src)
+            make_input = lambda: E.ingest(src, s2d=s2d, **ingest_kw)  # noqa: E731
+        return E.run_backbone(self, self.program, make_input, pooled)
 
     def forward(self, x):
         if not x.is_cuda:

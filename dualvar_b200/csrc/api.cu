@@ -72,6 +72,8 @@ int rowdot(const float* a, const float* b, float* out, int rows, int d, int ld_o
 int row_axpy(const float* alpha, int ld_alpha, const float* x, float* y, int rows, int d, float beta,
              cudaStream_t stream);
 int probe_overlap(const void* src, void* out, int c1, cudaStream_t stream);
+int momentum_update(const long long* table, int n_chunks, float m, cudaStream_t stream);
+int enqueue(const float* keys, float* queue, int B, int d, int K, int ptr, cudaStream_t stream);
 }  // namespace dv
 
 using namespace dv;
@@ -321,6 +323,17 @@ int dv_conv3d_stem_wgrad_bf16(const void* x_s2d, const void* dy, float* dws, con
   if (int rc = check_stem(g)) return rc;
   DV_REQUIRE(x_s2d && dy && dws, "NULL tensor pointer");
   return conv_stem_wgrad_bf16(x_s2d, dy, dws, g->N, g->T, g->H / 2, g->W / 2, g->Cout_p, g->kt, g->pt, ST);
+}
+
+int dv_moco_momentum_update(const int64_t* chunk_table, int n_chunks, float m, void* stream) {
+  DV_REQUIRE(chunk_table && n_chunks >= 0 && m >= 0.f && m <= 1.f, "bad momentum_update arguments");
+  return momentum_update(reinterpret_cast<const long long*>(chunk_table), n_chunks, m, ST);
+}
+int dv_moco_enqueue(const float* keys, float* queue, int B, int d, int K, int ptr, void* stream) {
+  DV_REQUIRE(keys && queue && B > 0 && d > 0 && K > 0, "bad enqueue arguments");
+  DV_REQUIRE(K % B == 0, "queue size K=%d must be a multiple of the global batch %d", K, B);
+  DV_REQUIRE(ptr >= 0 && ptr + B <= K, "queue pointer %d out of range", ptr);
+  return enqueue(keys, queue, B, d, K, ptr, ST);
 }
 
 int dv_debug_probe_overlap_tmap(const void* src, void* out, int c1, void* stream) {

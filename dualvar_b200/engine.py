@@ -159,7 +159,7 @@ class RawClips:
         return (B, self.n_views, C, VT // self.n_views, H, W)
 
 
-def ingest(src, first_view=0, n_views=None, perm=None, n_series=0, s2d=False):
+def ingest(src, first_view=0, n_views=None, perm=None, n_series=0, s2d=False, out=None):
     """Clips -> bf16 NDHWC Act with 8 channels. ``src`` is the reference block (B, V, C, T, H, W)
     fp32, a plain clip batch (B, C, T, H, W), or RawClips. Output clip order is (b, view) with views
     first_view .. first_view+n_views-1, matching block.view(-1, C, T, H, W) (model/simclr.py:352)."""
@@ -180,13 +180,21 @@ def ingest(src, first_view=0, n_views=None, perm=None, n_series=0, s2d=False):
         V = 1
         sb, sv, sc, st = C * T * H * W, 0, T * H * W, H * W
     nv = V - first_view if n_views is None else n_views
-    if s2d:
-        dst = torch.empty((B * nv, T, H // 2, W // 2 + 3, 16), dtype=torch.bfloat16, device=t.device)
+    shape = (B * nv, T, H // 2, W // 2 + 3, 16) if s2d else (B * nv, T, H, W, 8)
+    if out is not None:
+        assert tuple(out.shape) == shape and out.is_contiguous() and out.dtype == torch.bfloat16
+        dst = out
     else:
-        dst = torch.empty((B * nv, T, H, W, 8), dtype=torch.bfloat16, device=t.device)
+        dst = torch.empty(shape, dtype=torch.bfloat16, device=t.device)
     call("dv_ingest_clips", ptr(t), ptr(dst), ptr(perm), sb, sv, sc, st, B, C, T, H, W, first_view, nv,
          n_series, mean, std, 1 if s2d else 0, stream_ptr())
     return Act(dst, C, needs_grad=False, s2d=(B * nv, T, H, W) if s2d else None)
+
+
+def ingest_shape(src, n_clips, s2d):
+    """Shape of the ingest buffer for n_clips clips of ``src``'s frame geometry."""
+    T, H, W = (src.block_shape if isinstance(src, RawClips) else tuple(src.shape))[-3:]
+    return (n_clips, T, H // 2, W // 2 + 3, 16) if s2d else (n_clips, T, H, W, 8)
 
 
 def conv_stats(ctx, x, conv, bn):

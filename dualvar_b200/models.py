@@ -189,3 +189,266 @@ class LinearClassifier(nn.Module):
                 nn.init.constant_(param, 0.0)
             elif 'weight' in name:
                 nn.init.normal_(param, mean=0.0, std=0.01)
+
+
+# ------------------------------------------------------------------------------------------- MoCo
+@torch.no_grad()
+def concat_all_gather(tensor):
+    """all_gather without gradient (model/moco.py:14-25)."""
+    import torch.distributed as dist
+    out = torch.empty((dist.get_world_size() * tensor.shape[0],) + tuple(tensor.shape[1:]), dtype=tensor.dtype,
+                      device=tensor.device)
+    dist.all_gather_into_tensor(out, tensor.contiguous())
+    return out
+
+
+class _MoCoBase(nn.Module):
+    """Shared MoCo machinery: momentum update (one multi-tensor kernel), queue enqueue, shuffle-BN."""
+
+    def _pairs(self):  # pragma: no cover - abstract
+        raise NotImplementedError
+
+    def _momentum_table(self):
+        """Device table (k ptr, q ptr, count) in 8192-element chunks; rebuilt if storage moves."""
+        import ctypes
+        pairs = [(pq, pk) for pq, pk in self._pairs()]
+        sig = tuple((pq.data_ptr(), pk.data_ptr(), pq.numel()) for pq, pk in pairs)
+        if getattr(self, "_mom_sig", None) != sig:
+            rows = []
+            for pq, pk in pairs:
+                n = pq.numel()
+                for off in range(0, n, 8192):
+                    rows.append((pk.data_ptr() + 4 * off, pq.data_ptr() + 4 * off, min(8192, n - off)))
+            self._mom_table = torch.tensor(rows, dtype=torch.int64).to(pairs[0][0].device)
+            self._mom_sig = sig
+        return self._mom_table
+
+    @torch.no_grad()
+    def _momentum_update_key_encoder(self):
+        """theta_k = m*theta_k + (1-m)*theta_q (model/moco.py:328-334) — one launch for all tensors."""
+        import ctypes
+        t = self._momentum_table()
+        E.call("dv_moco_momentum_update", E.ptr(t), t.shape[0], ctypes.c_float(self.m), E.stream_ptr())
+
+    def _queue_ptr_host(self):
+        """Host mirror of queue_ptr (the reference does int(self.queue_ptr): a D2H sync every step)."""
+        ver = self.queue_ptr._version
+        if getattr(self, "_ptr_ver", None) != ver:
+            self._ptr_host = int(self.queue_ptr)
+        return self._ptr_host
+
+    def _advance_ptr(self, batch):
+        ptr = (self._queue_ptr_host() + batch) % self.K
+        self.queue_ptr.fill_(ptr)
+        self._ptr_host, self._ptr_ver = ptr, self.queue_ptr._version
+
+    @torch.no_grad()
+    def _enqueue(self, queue, keys, ptr):
+        B, d = keys.shape
+        assert self.K % B == 0  # for simplicity (model/moco.py:347)
+        E.call("dv_moco_enqueue", E.ptr(keys.contiguous()), E.ptr(queue), B, d, self.K, ptr, E.stream_ptr())
+
+    def _distributed_on(self):
+        return O._dist_on(self.distributed)
+
+    @torch.no_grad()
+    def _shuffle_plan(self, n_local):
+        """idx_shuffle from rank 0 + its inverse (model/moco.py:371-381)."""
+        import torch.distributed as dist
+        world = dist.get_world_size()
+        idx = torch.randperm(n_local * world).cuda()
+        dist.broadcast(idx, src=0)
+        return idx, torch.argsort(idx), idx.view(world, -1)[dist.get_rank()]
+
+    @torch.no_grad()
+    def _unshuffle(self, x, idx_unshuffle):
+        import torch.distributed as dist
+        xg = concat_all_gather(x)
+        return xg[idx_unshuffle.view(dist.get_world_size(), -1)[dist.get_rank()]]
+
+    def _key_input(self, backbone, block, view):
+        """Ingest the key clips; with shuffle-BN the bf16 ingested clips (not the fp32 frames) are
+        all-gathered and this rank keeps its shuffled share (model/moco.py:357-383)."""
+        s2d = backbone.wants_s2d(block)
+        if not self._distributed_on():
+            return (lambda: E.ingest(block, first_view=view, n_views=1, s2d=s2d)), None
+        B = (block.block_shape if isinstance(block, E.RawClips) else block.shape)[0]
+        idx, unshuf, mine = self._shuffle_plan(B)
+
+        def make():
+            local = E.ingest(block, first_view=view, n_views=1, s2d=s2d)
+            allx = concat_all_gather(local.data)
+            sel = allx.index_select(0, mine).contiguous()
+            return E.Act(sel, local.C, needs_grad=False, s2d=local.s2d)
+        return make, unshuf
+
+
+class MoCo_Naked(_MoCoBase):
+    """Two-view MoCo (model/moco.py:28-239)."""
+
+    def __init__(self, network='s3d', dim=128, K=2048, m=0.999, T=0.07, distributed=True, nonlinear=True):
+        super().__init__()
+        self.dim, self.K, self.m, self.T = dim, K, m, T
+        self.distributed, self.nonlinear = distributed, nonlinear
+        backbone, self.param = select_backbone(network)
+        feature_size = self.param['feature_size']
+        self.encoder_q = nn.ModuleList([backbone, nn.AdaptiveAvgPool3d((1, 1, 1))])
+        if nonlinear:
+            self.encoder_q.extend(_proj_head(feature_size, dim))
+        backbone, _ = select_backbone(network)
+        self.encoder_k = nn.ModuleList([backbone, nn.AdaptiveAvgPool3d((1, 1, 1))])
+        if nonlinear:
+            self.encoder_k.extend(_proj_head(feature_size, dim))
+        for param_q, param_k in zip(self.encoder_q.parameters(), self.encoder_k.parameters()):
+            param_k.data.copy_(param_q.data)
+            param_k.requires_grad = False
+        self.register_buffer("queue", torch.randn(dim, K))
+        self.queue = nn.functional.normalize(self.queue, dim=0)
+        self.register_buffer("queue_ptr", torch.zeros(1, dtype=torch.long))
+        self.criterion = nn.CrossEntropyLoss()
+
+    def _pairs(self):
+        return zip(self.encoder_q.parameters(), self.encoder_k.parameters())
+
+    def forward(self, block):
+        block, shape = _check_input(block)
+        B, N = shape[:2]
+        assert N == 2
+        bq, bk = self.encoder_q[0], self.encoder_k[0]
+        pooled_q = bq.encode(block, pooled=True, first_view=0, n_views=1)
+        q = O.l2norm(_head(self.encoder_q[2:], pooled_q) if self.nonlinear else pooled_q)
+        in_train_mode = q.requires_grad
+        with torch.no_grad():
+            if in_train_mode:
+                self._momentum_update_key_encoder()
+            make, unshuf = self._key_input(bk, block, 1)
+            pooled_k = bk.encode(None, pooled=True, make_input=make)
+            k = O.l2norm(_head(self.encoder_k[2:], pooled_k) if self.nonlinear else pooled_k)
+            if unshuf is not None:
+                k = self._unshuffle(k, unshuf)
+        ret, self.last_hits = O.queue_contrast(q, k, self.queue, self.T, 'clip_')
+        if in_train_mode:
+            keys = concat_all_gather(k) if self._distributed_on() else k
+            self._enqueue(self.queue, keys, self._queue_ptr_host())
+            self._advance_ptr(keys.shape[0])
+        return ret
+
+
+class MoCo_TimeSeriesV4(_MoCoBase):
+    """MoCo + DualVar (model/moco.py:242-573)."""
+
+    def __init__(self, network='s3d', dim=128, K=2048, m=0.999, T=0.07, distributed=True, nonlinear=True,
+                 n_series=2, series_dim=64, series_T=0.07, aligned_T=0.07, mode="clip-sr-tc", args=None):
+        super().__init__()
+        self.dim, self.K, self.m, self.T = dim, K, m, T
+        self.distributed, self.nonlinear = distributed, nonlinear
+        self.n_series, self.series_dim, self.mode = n_series, series_dim, mode
+        self.series_T, self.aligned_T = series_T, aligned_T
+        self.with_clip = 'clip' in mode
+        self.with_sr = 'sr' in mode
+        self.with_tc = 'tc' in mode
+        backbone, self.param = select_backbone(network)
+        feature_size = self.param['feature_size']
+        self.encoder_q = nn.ModuleList([backbone, nn.AdaptiveAvgPool3d((1, 1, 1))])
+        if nonlinear:
+            self.encoder_q.extend(_proj_head(feature_size, dim))
+        self.series_proj_head_q = nn.Sequential(*_proj_head(feature_size, series_dim * n_series))
+        backbone, _ = select_backbone(network)
+        self.encoder_k = nn.ModuleList([backbone, nn.AdaptiveAvgPool3d((1, 1, 1))])
+        if nonlinear:
+            self.encoder_k.extend(_proj_head(feature_size, dim))
+        self.series_proj_head_k = nn.Sequential(*_proj_head(feature_size, series_dim * n_series))
+        for param_q, param_k in zip(self.encoder_q.parameters(), self.encoder_k.parameters()):
+            param_k.data.copy_(param_q.data)
+            param_k.requires_grad = False
+        for param_q, param_k in zip(self.series_proj_head_q.parameters(), self.series_proj_head_k.parameters()):
+            param_k.data.copy_(param_q.data)
+            param_k.requires_grad = False
+        self.register_buffer("queue_ptr", torch.zeros(1, dtype=torch.long))
+        self.register_buffer("queue", torch.randn(dim, K))
+        self.queue = nn.functional.normalize(self.queue, dim=0)
+        self.register_buffer("series_queue", torch.randn(series_dim * n_series, K))
+        self.series_queue = nn.functional.normalize(
+            self.series_queue.view(n_series, series_dim, K), dim=1).view(n_series * series_dim, K)
+        self.criterion = nn.CrossEntropyLoss()
+        self.last_hits = {}
+
+    def _pairs(self):
+        import itertools
+        return itertools.chain(zip(self.encoder_q.parameters(), self.encoder_k.parameters()),
+                               zip(self.series_proj_head_q.parameters(), self.series_proj_head_k.parameters()))
+
+    # objectives under the reference's method names
+    def calc_clip_contrast_loss(self, q, k, queue, prefix='clip_'):
+        ret, self.last_hits[prefix] = O.queue_contrast(q, k, queue, self.T, prefix)
+        return ret
+
+    calc_contrast_loss = calc_clip_contrast_loss
+
+    def calc_tc_contrast_loss(self, q, k, queue, prefix="tc_"):
+        """mean over s x s segment pairs == dot product of segment means (model/moco.py:404-424)."""
+        B, s, e = q.shape
+        assert s == self.n_series and e == self.series_dim
+        qm = O.SegmentMeanFn.apply(q)
+        with torch.no_grad():
+            km = O.SegmentMeanFn.apply(k.reshape(B, s, e))
+            queue_m = O.SegmentMeanFn.apply(queue.detach().view(1, s, e * self.K)).view(e, self.K)
+        ret, self.last_hits[prefix] = O.queue_contrast(qm, km, queue_m, self.aligned_T, prefix)
+        return ret
+
+    def calc_ranking_loss(self, features, n_views=2, prefix='ranking_', weight=1.):
+        a, b = features[:, :, 0].contiguous(), features[:, :, 1].contiguous()
+        ret, self.last_hits[prefix] = O.rank_loss(a, b, 0.05, weight, None, prefix)
+        return ret
+
+    def forward(self, block):
+        block, shape = _check_input(block)
+        B, N, C, T, H, W = shape
+        assert N == 3
+        s, e = self.n_series, self.series_dim
+        bq, bk = self.encoder_q[0], self.encoder_k[0]
+        dev = block.device
+        ret = {}
+        pooled_q = bq.encode(block, pooled=True, first_view=0, n_views=1)
+        q = O.l2norm(_head(self.encoder_q[2:], pooled_q) if self.nonlinear else pooled_q)
+        series_q = O.l2norm(_head(self.series_proj_head_q, pooled_q).view(B * s, e)).view(B, s, e)
+        in_train_mode = q.requires_grad
+        with torch.no_grad():
+            if in_train_mode:
+                self._momentum_update_key_encoder()
+            make, unshuf = self._key_input(bk, block, 1)
+            pooled_k = bk.encode(None, pooled=True, make_input=make)
+            k = O.l2norm(_head(self.encoder_k[2:], pooled_k) if self.nonlinear else pooled_k)
+            series_k = O.l2norm(_head(self.series_proj_head_k, pooled_k).view(B * s, e)).view(B, s * e)
+            if unshuf is not None:
+                k = self._unshuffle(k, unshuf)
+                series_k = self._unshuffle(series_k, unshuf)
+        ret.update(self.calc_contrast_loss(q, k, self.queue, 'clip_'))
+        if self.with_tc:
+            ret.update(self.calc_tc_contrast_loss(series_q, series_k.view(B, s, e), self.series_queue, 'tc_'))
+        if in_train_mode:
+            keys, skeys = k, series_k
+            if self._distributed_on():
+                keys, skeys = concat_all_gather(keys), concat_all_gather(skeys)
+            ptr = self._queue_ptr_host()
+            self._enqueue(self.queue, keys, ptr)
+            self._enqueue(self.series_queue, skeys, ptr)
+            self._advance_ptr(keys.shape[0])
+        # view 2 twice in one batch: as is, and with its segments shuffled (model/moco.py:543-557)
+        perm = _draw_perms(B, s, dev)
+        s2d = bq.wants_s2d(block)
+
+        def make_dual():
+            buf = torch.empty(E.ingest_shape(block, 2 * B, s2d), dtype=torch.bfloat16, device=dev)
+            a = E.ingest(block, first_view=2, n_views=1, s2d=s2d, out=buf[:B])
+            E.ingest(block, first_view=2, n_views=1, perm=perm, n_series=s, s2d=s2d, out=buf[B:])
+            return E.Act(buf, a.C, needs_grad=False, s2d=(2 * B,) + a.s2d[1:] if a.s2d else None)
+
+        pooled_d = bq.encode(None, pooled=True, make_input=make_dual)
+        series_d = O.l2norm(_head(self.series_proj_head_q, pooled_d).view(2 * B * s, e)).view(2 * B, s, e)
+        aug_series = series_d[:B]
+        shuf = O.PermuteSegmentsFn.apply(series_d[B:], perm)
+        for base, prefix in ((series_q, 'unaug_ranking_'), (aug_series, 'aug_ranking_')):
+            r, self.last_hits[prefix] = O.rank_loss(base, shuf, 0.05, 0.5, None, prefix)
+            ret.update(r)
+        return ret

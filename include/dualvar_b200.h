@@ -165,6 +165,13 @@ int dv_conv3d_stem_fprop_bf16(const void* x_s2d, const void* ws, void* y, double
                               const float* bias_padded, const dv_conv_geom* g, void* stream);
 int dv_conv3d_stem_wgrad_bf16(const void* x_s2d, const void* dy, float* dws, const dv_conv_geom* g, void* stream);
 
+/* ---- MoCo bookkeeping -------------------------------------------------------------------------
+ * theta_k = m*theta_k + (1-m)*theta_q for every parameter tensor in one launch (model/moco.py:328-334).
+ * chunk_table: device int64 [n_chunks][3] = (k pointer, q pointer, element count <= 8192). */
+int dv_moco_momentum_update(const int64_t* chunk_table, int n_chunks, float m, void* stream);
+/* queue[:, ptr:ptr+B] = keys^T; queue fp32 (d, K), keys fp32 (B, d); K % B == 0 (model/moco.py:343-351) */
+int dv_moco_enqueue(const float* keys, float* queue, int B, int d, int K, int ptr, void* stream);
+
 /* debug probe (tests only): TMA tensor map with overlapping windows */
 int dv_debug_probe_overlap_tmap(const void* src, void* out, int c1, void* stream);
 

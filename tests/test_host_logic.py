@@ -45,7 +45,8 @@ def test_true_18_layer_variant_is_available():
     assert sum(p.numel() for p in net.parameters()) == 33178423
 
 
-@pytest.mark.parametrize("cls", ["SimCLR_TimeSeriesV4", "SimCLR_Naked", "LinearClassifier"])
+@pytest.mark.parametrize("cls", ["SimCLR_TimeSeriesV4", "SimCLR_Naked", "LinearClassifier", "MoCo_Naked",
+                                 "MoCo_TimeSeriesV4"])
 def test_model_signatures_match_oracle(cls):
     a = inspect.signature(getattr(PM, cls).__init__)
     b = inspect.signature(getattr(OM, cls).__init__)
@@ -83,3 +84,16 @@ def test_rawclips_layout():
     assert rc.block_shape == (2, 3, 3, 16, 8, 8)
     with pytest.raises(AssertionError):
         RawClips(torch.zeros(2, 3, 47, 8, 8), 3)
+
+
+def test_moco_state_dict_interchanges_with_oracle():
+    args = SimpleNamespace(shufflerank_theta=0.05)
+    _seed(0)
+    ref = OM.MoCo_TimeSeriesV4("r21d", 128, 64, 0.999, 0.07, False, True, 2, 64, 0.07, 0.07, "clip-sr-tc", args)
+    _seed(0)
+    prod = PM.MoCo_TimeSeriesV4("r21d", 128, 64, 0.999, 0.07, False, True, 2, 64, 0.07, 0.07, "clip-sr-tc", args)
+    sr, sp = ref.state_dict(), prod.state_dict()
+    assert list(sr.keys()) == list(sp.keys()) and len(sr) == 307
+    assert all(torch.equal(sr[k], sp[k]) for k in sr)
+    assert not any(p.requires_grad for p in prod.encoder_k.parameters())
+    assert sum(p.numel() for p in prod.parameters() if p.requires_grad) == 15021943

@@ -113,3 +113,67 @@ def test_full_size_clip_shapes():
         with torch.no_grad():
             y = net(torch.randn(2, 3, 16, 112, 112, device=dev))
         assert y.shape == (2, 512, 2, 7, 7) and torch.isfinite(y).all()
+
+
+def test_moco_dualvar_step_matches_oracle():
+    """MoCo+DualVar: losses/logits, queue contents after enqueue, queue pointer and the momentum-updated
+    key encoder vs the oracle (model/moco.py:482-573 semantics)."""
+    from dualvar_b200 import models as PM
+    from oracle import models as OM
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    _seed(0)
+    ref = OM.MoCo_TimeSeriesV4("r21d", 128, 64, 0.9, 0.07, False, True, 2, 64, 0.07, 0.07, "clip-sr-tc", ARGS).to(dev).train()
+    prod = PM.MoCo_TimeSeriesV4("r21d", 128, 64, 0.9, 0.07, False, True, 2, 64, 0.07, 0.07, "clip-sr-tc", ARGS)
+    prod.load_state_dict(ref.state_dict())
+    prod = prod.to(dev).train()
+    # make q and k encoders differ so the momentum update is observable
+    with torch.no_grad():
+        for m in (ref, prod):
+            torch.manual_seed(5)
+            for p in m.encoder_q.parameters():
+                p.add_(0.01 * torch.randn_like(p))
+    x = torch.randn(8, 3, 3, 8, 64, 64, device=dev)
+    for step in range(2):
+        np.random.seed(20 + step); rr = ref(x)
+        np.random.seed(20 + step); rp = prod(x)
+        assert list(rr.keys()) == list(rp.keys())
+        for k in rr:
+            if "labels" in k:
+                assert torch.equal(rr[k], rp[k])
+            elif "loss" in k:
+                assert abs(rp[k].item() - rr[k].item()) <= 1e-2 * abs(rr[k].item()), (step, k, rp[k].item(), rr[k].item())
+            else:
+                assert _rel(rp[k], rr[k]) < 1e-2, (step, k, _rel(rp[k], rr[k]))
+        assert int(prod.queue_ptr) == int(ref.queue_ptr) == 8 * (step + 1)
+        assert _rel(prod.queue, ref.queue) < 1e-2 and _rel(prod.series_queue, ref.series_queue) < 1e-2
+        # untouched queue columns are bit-identical
+        assert torch.equal(prod.queue[:, 8 * (step + 1):], ref.queue[:, 8 * (step + 1):])
+        for (n, pr), (_, pp) in zip(ref.encoder_k.named_parameters(), prod.encoder_k.named_parameters()):
+            torch.testing.assert_close(pp, pr, rtol=1e-6, atol=1e-7, msg=n)
+    lp = sum(v for k, v in rp.items() if "loss" in k)
+    lp.backward()
+    assert all(p.grad is None for p in prod.encoder_k.parameters())
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in prod.encoder_q.parameters())
+
+
+def test_moco_naked_and_simclr_naked_match_oracle():
+    from dualvar_b200 import models as PM
+    from oracle import models as OM
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    x = torch.randn(8, 2, 3, 8, 64, 64, device=dev)
+    _seed(0)
+    ref = OM.MoCo_Naked("r3d", 128, 32, 0.99, 0.07, False).to(dev).train()
+    prod = PM.MoCo_Naked("r3d", 128, 32, 0.99, 0.07, False)
+    prod.load_state_dict(ref.state_dict()); prod = prod.to(dev).train()
+    rr, rp = ref(x), prod(x)
+    assert abs(rp["clip_contrast_loss"].item() - rr["clip_contrast_loss"].item()) <= 1e-2 * rr["clip_contrast_loss"].item()
+    assert _rel(rp["clip_logits"], rr["clip_logits"]) < 1e-2 and int(prod.queue_ptr) == int(ref.queue_ptr) == 8
+    _seed(0)
+    ref = OM.SimCLR_Naked("r3d", 128, 0.07, False).to(dev).train()
+    prod = PM.SimCLR_Naked("r3d", 128, 0.07, False)
+    prod.load_state_dict(ref.state_dict()); prod = prod.to(dev).train()
+    rr, rp = ref(x), prod(x)
+    assert abs(rp["clip_contrast_loss"].item() - rr["clip_contrast_loss"].item()) <= 1e-2 * rr["clip_contrast_loss"].item()
+    assert rp["clip_logits"].shape == rr["clip_logits"].shape == (16, 15)
