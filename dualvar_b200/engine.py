@@ -97,6 +97,14 @@ def packed_weights(conv):
     return wf, wt
 
 
+def invalidate_weights(params):
+    """Drop cached packed copies of parameters that were modified through raw pointers (kernels do not
+    bump Tensor._version)."""
+    for p in params:
+        _weight_cache.pop(id(p), None)
+        _weight_cache.pop(("stem", id(p)), None)
+
+
 def packed_stem_weights(conv, g):
     """bf16 [Cout_p][kt*4][64] stem weights for the space-to-depth formulation."""
     w = conv.weight

@@ -229,6 +229,7 @@ class _MoCoBase(nn.Module):
         import ctypes
         t = self._momentum_table()
         E.call("dv_moco_momentum_update", E.ptr(t), t.shape[0], ctypes.c_float(self.m), E.stream_ptr())
+        E.invalidate_weights(pk for _, pk in self._pairs())
 
     def _queue_ptr_host(self):
         """Host mirror of queue_ptr (the reference does int(self.queue_ptr): a D2H sync every step)."""
