@@ -72,6 +72,14 @@ int rowdot(const float* a, const float* b, float* out, int rows, int d, int ld_o
 int row_axpy(const float* alpha, int ld_alpha, const float* x, float* y, int rows, int d, float beta,
              cudaStream_t stream);
 int probe_overlap(const void* src, void* out, int c1, cudaStream_t stream);
+int slice_mean(const void* x, float* out, int N, int S, int C, int ld, int coff, cudaStream_t st);
+int gate_scale(void* x, const float* w, int N, int S, int C, int ld, int coff, cudaStream_t st);
+int gate_bwd_reduce(const void* dout, const void* y, const float* ss, float* dw, int N, int S, int C, int Cp,
+                    int ld, int coff, cudaStream_t st);
+int gate_bwd_apply(const void* dout, const float* w, const float* dmean, void* dz, int N, int S, int C, int Cp,
+                   int ld, int coff, cudaStream_t st);
+int sigmoid_fwd(const float* x, float* y, long long n, cudaStream_t st);
+int sigmoid_bwd(const float* dy, const float* y, float* dx, long long n, cudaStream_t st);
 int momentum_update(const long long* table, int n_chunks, float m, cudaStream_t stream);
 int enqueue(const float* keys, float* queue, int B, int d, int K, int ptr, cudaStream_t stream);
 }  // namespace dv
@@ -334,6 +342,33 @@ int dv_moco_enqueue(const float* keys, float* queue, int B, int d, int K, int pt
   DV_REQUIRE(K % B == 0, "queue size K=%d must be a multiple of the global batch %d", K, B);
   DV_REQUIRE(ptr >= 0 && ptr + B <= K, "queue pointer %d out of range", ptr);
   return enqueue(keys, queue, B, d, K, ptr, ST);
+}
+
+int dv_slice_mean(const void* x, float* out, int N, int S, int C, int ld, int coff, void* stream) {
+  DV_REQUIRE(x && out && N > 0 && S > 0 && C > 0 && ld >= coff + C, "bad slice_mean arguments");
+  return slice_mean(x, out, N, S, C, ld, coff, ST);
+}
+int dv_gate_scale(void* x, const float* w, int N, int S, int C, int ld, int coff, void* stream) {
+  DV_REQUIRE(x && w && N > 0 && S > 0 && C > 0 && ld >= coff + C, "bad gate_scale arguments");
+  return gate_scale(x, w, N, S, C, ld, coff, ST);
+}
+int dv_gate_bwd_reduce(const void* dout, const void* y, const float* ss, float* dw, int N, int S, int C, int Cp,
+                       int ld, int coff, void* stream) {
+  DV_REQUIRE(dout && y && ss && dw && N > 0 && S > 0 && C > 0 && Cp >= C, "bad gate_bwd_reduce arguments");
+  return gate_bwd_reduce(dout, y, ss, dw, N, S, C, Cp, ld, coff, ST);
+}
+int dv_gate_bwd_apply(const void* dout, const float* w, const float* dmean, void* dz, int N, int S, int C, int Cp,
+                      int ld, int coff, void* stream) {
+  DV_REQUIRE(dout && w && dmean && dz && N > 0 && S > 0 && C > 0 && Cp >= C, "bad gate_bwd_apply arguments");
+  return gate_bwd_apply(dout, w, dmean, dz, N, S, C, Cp, ld, coff, ST);
+}
+int dv_sigmoid_fwd(const float* x, float* y, int64_t n, void* stream) {
+  DV_REQUIRE(x && y && n > 0, "bad sigmoid arguments");
+  return sigmoid_fwd(x, y, n, ST);
+}
+int dv_sigmoid_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream) {
+  DV_REQUIRE(dy && y && dx && n > 0, "bad sigmoid arguments");
+  return sigmoid_bwd(dy, y, dx, n, ST);
 }
 
 int dv_debug_probe_overlap_tmap(const void* src, void* out, int c1, void* stream) {

@@ -65,7 +65,7 @@ class Context:
         self.record = record
         self.tape = []
         self.param_grads = {}      # id(param) -> fp32 tensor shaped like the parameter
-        self.launches = 0
+        self.overrides = {}        # (id(concat Act), channel offset) -> dense gradient replacing the slice's
 
     def add_param_grad(self, p, g):
         k = id(p)
@@ -300,17 +300,22 @@ def activate(ctx, r1, r2=None, res=None, relu=True, out=None, out_coff=0):
 
     def backward():
         dout = out_act.grad
+        o_ld, o_coff = out_ld, out_coff
+        ov = ctx.overrides.pop((id(out_act), out_coff), None)
+        if ov is not None:      # a gate in front of this slice already produced the dense gradient
+            dout, o_ld, o_coff = ov, Cp, 0
         assert dout is not None, "activation has no gradient"
         need_g = res is not None and res.needs_grad
         g_buf = None
         # plain relu(BN(y)): the mask is recomputed from y, `out` is not re-read
         mask_ss = ptr(r1.ss) if (relu and r2 is None and res is None) else None
+        assert ov is None or mask_ss is not None
         for i, r in enumerate((r1, r2)):
             if r is None:
                 continue
             sums = torch.zeros(2 * Cp, dtype=torch.float64, device=dev)
-            call("dv_bn_bwd_reduce", ptr(dout), ptr(out_t), ptr(r.y), mask_ss, ptr(sums), rows, Cp, out_ld,
-                 out_coff, 1 if relu else 0, stream_ptr())
+            call("dv_bn_bwd_reduce", ptr(dout), ptr(out_t), ptr(r.y), mask_ss, ptr(sums), rows, Cp, o_ld,
+                 o_coff, 1 if relu else 0, stream_ptr())
             sums_g = sums
             if r.sync:
                 sums_g = sums.clone()
@@ -329,7 +334,7 @@ def activate(ctx, r1, r2=None, res=None, relu=True, out=None, out_coff=0):
             if want_g:
                 g_buf = torch.empty_like(r.y)
             call("dv_bn_bwd_apply", ptr(dout), ptr(out_t), ptr(r.y), mask_ss, ptr(coef), ptr(dy),
-                 ptr(g_buf) if want_g else None, rows, Cp, out_ld, out_coff, 1 if relu else 0, stream_ptr())
+                 ptr(g_buf) if want_g else None, rows, Cp, o_ld, o_coff, 1 if relu else 0, stream_ptr())
             _conv_backward(ctx, r, dy)
         if need_g:
             _acc_grad(res, g_buf)
@@ -338,6 +343,55 @@ def activate(ctx, r1, r2=None, res=None, relu=True, out=None, out_coff=0):
 
     ctx.tape.append(backward)
     return out_act
+
+
+def new_concat(x, C_total):
+    """Empty activation with x's N,T,H,W that several branches fill slice by slice
+    (torch.cat of the Inception branches, backbone/s3dg.py:130)."""
+    N, T, H, W, _ = x.shape5
+    assert C_total % 8 == 0
+    return Act(torch.empty((N, T, H, W, C_total), dtype=torch.bfloat16, device=x.data.device), C_total)
+
+
+def self_gate(ctx, cat, coff, raw, fc):
+    """S3D-G SelfGating on the slice [coff, coff+C) of ``cat`` that ``raw``'s activation just wrote:
+    w = sigmoid(fc(mean_{T,H,W} z)); slice *= w (backbone/s3dg.py:68-78)."""
+    N, T, H, W, ld = cat.shape5
+    S = T * H * W
+    C, Cp = raw.geom.Cout, raw.geom.Cout_p
+    dev = cat.data.device
+    mean = torch.empty((N, C), dtype=torch.float32, device=dev)
+    call("dv_slice_mean", ptr(cat.data), ptr(mean), N, S, C, ld, coff, stream_ptr())
+    pre = torch.empty((N, C), dtype=torch.float32, device=dev)
+    f = ctypes.c_float
+    call("dv_sgemm", 0, 1, N, C, C, f(1.0), ptr(mean), C, ptr(fc.weight.detach()), C, f(0.0), ptr(pre), C,
+         ptr(fc.bias.detach()), 0, stream_ptr())
+    w = torch.empty_like(pre)
+    call("dv_sigmoid_fwd", ptr(pre), ptr(w), N * C, stream_ptr())
+    call("dv_gate_scale", ptr(cat.data), ptr(w), N, S, C, ld, coff, stream_ptr())
+    if not ctx.record:
+        return
+
+    def backward():
+        dout = cat.grad
+        dw = torch.empty((N, C), dtype=torch.float32, device=dev)
+        call("dv_gate_bwd_reduce", ptr(dout), ptr(raw.y), ptr(raw.ss), ptr(dw), N, S, C, Cp, ld, coff, stream_ptr())
+        dpre = torch.empty_like(dw)
+        call("dv_sigmoid_bwd", ptr(dw), ptr(w), ptr(dpre), N * C, stream_ptr())
+        gW = torch.empty_like(fc.weight)
+        call("dv_sgemm", 1, 0, C, C, N, f(1.0), ptr(dpre), C, ptr(mean), C, f(0.0), ptr(gW), C, None, 0, stream_ptr())
+        gb = torch.empty_like(fc.bias)
+        call("dv_colsum", ptr(dpre), ptr(gb), N, C, C, f(0.0), stream_ptr())
+        ctx.add_param_grad(fc.weight, gW)
+        ctx.add_param_grad(fc.bias, gb)
+        dmean = torch.empty_like(dw)
+        call("dv_sgemm", 0, 0, N, C, C, f(1.0), ptr(dpre), C, ptr(fc.weight.detach()), C, f(0.0), ptr(dmean), C,
+             None, 0, stream_ptr())
+        dz = torch.empty((N, T, H, W, Cp), dtype=torch.bfloat16, device=dev)
+        call("dv_gate_bwd_apply", ptr(dout), ptr(w), ptr(dmean), ptr(dz), N, S, C, Cp, ld, coff, stream_ptr())
+        ctx.overrides[(id(cat), coff)] = dz
+
+    ctx.tape.append(backward)
 
 
 def max_pool(ctx, x, kernel, stride, padding):

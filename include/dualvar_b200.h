@@ -172,6 +172,19 @@ int dv_moco_momentum_update(const int64_t* chunk_table, int n_chunks, float m, v
 /* queue[:, ptr:ptr+B] = keys^T; queue fp32 (d, K), keys fp32 (B, d); K % B == 0 (model/moco.py:343-351) */
 int dv_moco_enqueue(const float* keys, float* queue, int B, int d, int K, int ptr, void* stream);
 
+/* ---- S3D-G self-gating on channel slices of the Inception concat tensor (backbone/s3dg.py:68-78,130) ----
+ * x rows have `ld` channels, the branch occupies [coff, coff+C). */
+int dv_slice_mean(const void* x, float* out, int N, int S, int C, int ld, int coff, void* stream);
+int dv_gate_scale(void* x, const float* w, int N, int S, int C, int ld, int coff, void* stream);
+/* dw[n][c] = sum_s dout * relu(scale*y+shift)  (the un-gated activation is recomputed from y) */
+int dv_gate_bwd_reduce(const void* dout, const void* y, const float* ss, float* dw, int N, int S, int C, int Cp,
+                       int ld, int coff, void* stream);
+/* dz = w*dout + dmean/S, dense [N*S][Cp] */
+int dv_gate_bwd_apply(const void* dout, const float* w, const float* dmean, void* dz, int N, int S, int C, int Cp,
+                      int ld, int coff, void* stream);
+int dv_sigmoid_fwd(const float* x, float* y, int64_t n, void* stream);
+int dv_sigmoid_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream);
+
 /* debug probe (tests only): TMA tensor map with overlapping windows */
 int dv_debug_probe_overlap_tmap(const void* src, void* out, int c1, void* stream);
 

@@ -22,6 +22,8 @@ def relerr(a, b):
 
 
 def cmp_backbone(name, shape=(8, 3, 8, 64, 64)):
+    if name in ("s3d", "s3dg"):
+        shape = (4, 3, 16, 64, 64)
     seed(0)
     ref, _ = OB.select_backbone(name)
     ref = ref.to(dev).train()

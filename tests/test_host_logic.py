@@ -21,7 +21,7 @@ def _seed(s):
     random.seed(s)
 
 
-@pytest.mark.parametrize("name", ["r21d", "r3d", "c3d"])
+@pytest.mark.parametrize("name", ["r21d", "r3d", "c3d", "s3d", "s3dg"])
 def test_backbone_state_dict_and_init_match_reference(golden_dir, name):
     g = np.load(os.path.join(golden_dir, "backbones.npz"))
     _seed(0)
