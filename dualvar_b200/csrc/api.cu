@@ -72,6 +72,9 @@ int rowdot(const float* a, const float* b, float* out, int rows, int d, int ld_o
 int row_axpy(const float* alpha, int ld_alpha, const float* x, float* y, int rows, int d, float beta,
              cudaStream_t stream);
 int probe_overlap(const void* src, void* out, int c1, cudaStream_t stream);
+int retrieval_prepare(const float* x, double* mean, double* y, int n, int d, cudaStream_t st);
+int retrieval_sim_topk(const double* test, const double* train, double* sim, float* sim32, long long* idx,
+                       int nt, int ntr, int d, int k, cudaStream_t st);
 int slice_mean(const void* x, float* out, int N, int S, int C, int ld, int coff, cudaStream_t st);
 int gate_scale(void* x, const float* w, int N, int S, int C, int ld, int coff, cudaStream_t st);
 int gate_bwd_reduce(const void* dout, const void* y, const float* ss, float* dw, int N, int S, int C, int Cp,
@@ -369,6 +372,17 @@ int dv_sigmoid_fwd(const float* x, float* y, int64_t n, void* stream) {
 int dv_sigmoid_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream) {
   DV_REQUIRE(dy && y && dx && n > 0, "bad sigmoid arguments");
   return sigmoid_bwd(dy, y, dx, n, ST);
+}
+
+int dv_retrieval_prepare(const float* feat, double* mean, double* out, int n, int d, void* stream) {
+  DV_REQUIRE(feat && mean && out && n > 0 && d > 0, "bad retrieval_prepare arguments");
+  return retrieval_prepare(feat, mean, out, n, d, ST);
+}
+int dv_retrieval_sim_topk(const double* test, const double* train, double* sim, float* sim32, int64_t* idx,
+                          int n_test, int n_train, int d, int k, void* stream) {
+  DV_REQUIRE(test && train && sim && idx && n_test > 0 && n_train > 0 && d > 0 && k > 0 && k <= n_train,
+             "bad retrieval_sim_topk arguments");
+  return retrieval_sim_topk(test, train, sim, sim32, reinterpret_cast<long long*>(idx), n_test, n_train, d, k, ST);
 }
 
 int dv_debug_probe_overlap_tmap(const void* src, void* out, int c1, void* stream) {

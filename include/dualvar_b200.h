@@ -185,6 +185,14 @@ int dv_gate_bwd_apply(const void* dout, const float* w, const float* dmean, void
 int dv_sigmoid_fwd(const float* x, float* y, int64_t n, void* stream);
 int dv_sigmoid_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream);
 
+/* ---- retrieval (classifier.py:963-983) ----------------------------------------------------------------
+ * out (fp64 [n][d]) = L2-normalised rows of (feat - column mean), everything evaluated in fp64 */
+int dv_retrieval_prepare(const float* feat, double* mean, double* out, int n, int d, void* stream);
+/* sim (fp64 [n_test][n_train], optional fp32 copy) = test @ train^T; idx (int64 [n_test][k]) = indices of the k
+ * largest similarities per row in descending order, exact ties broken towards the lowest index */
+int dv_retrieval_sim_topk(const double* test, const double* train, double* sim, float* sim32, int64_t* idx,
+                          int n_test, int n_train, int d, int k, void* stream);
+
 /* debug probe (tests only): TMA tensor map with overlapping windows */
 int dv_debug_probe_overlap_tmap(const void* src, void* out, int c1, void* stream);
 
