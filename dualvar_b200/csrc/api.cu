@@ -72,6 +72,7 @@ int rowdot(const float* a, const float* b, float* out, int rows, int d, int ld_o
 int row_axpy(const float* alpha, int ld_alpha, const float* x, float* y, int rows, int d, float beta,
              cudaStream_t stream);
 int probe_overlap(const void* src, void* out, int c1, cudaStream_t stream);
+void set_conv_profile(long long* p);
 int retrieval_prepare(const float* x, double* mean, double* y, int n, int d, cudaStream_t st);
 int retrieval_sim_topk(const double* test, const double* train, double* sim, float* sim32, long long* idx,
                        int nt, int ntr, int d, int k, cudaStream_t st);
@@ -383,6 +384,11 @@ int dv_retrieval_sim_topk(const double* test, const double* train, double* sim, 
   DV_REQUIRE(test && train && sim && idx && n_test > 0 && n_train > 0 && d > 0 && k > 0 && k <= n_train,
              "bad retrieval_sim_topk arguments");
   return retrieval_sim_topk(test, train, sim, sim32, reinterpret_cast<long long*>(idx), n_test, n_train, d, k, ST);
+}
+
+int dv_debug_set_conv_profile(int64_t* buf) {
+  set_conv_profile(reinterpret_cast<long long*>(buf));
+  return 0;
 }
 
 int dv_debug_probe_overlap_tmap(const void* src, void* out, int c1, void* stream) {

@@ -20,6 +20,9 @@
 
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
+#include <algorithm>
 #include <vector>
 
 namespace dv {
@@ -29,7 +32,8 @@ constexpr int kAStageBytes = kTileM * 128;  // 16 KB
 constexpr int kOutBufBytes = kTileM * 128;  // one 64-channel chunk of the output tile
 constexpr int kMaxStages = 8;
 constexpr int kTmemCols = 512;
-constexpr int kSmemBudget = 232448 - 4096;  // 227 KB minus static smem / alignment slack
+constexpr int kSmemBudget = 232448 - 12288;  // 227 KB minus static smem (stat partials, tap table, barriers)
+constexpr int kOutBufs = 3;                  // output staging buffers: one named barrier per chunk suffices
 
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
@@ -38,25 +42,28 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ __align__(8) uint64_t bres_bar;
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float s_sum[kMaxBlockN];
-  __shared__ float s_sq[kMaxBlockN];
+  __shared__ __align__(16) float s_part[4][2][kMaxBlockN];   // BN partial sums per epilogue warp: [row quarter][sum|sumsq][channel]
 
-  const int warp = threadIdx.x >> 5;
+  // warp-uniform role index (shfl makes the uniformity visible to the compiler: loop state of the
+  // producer / MMA warps then lives in uniform registers, which is what UTMALDG / UTCHMMA consume)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
 
   // carve dynamic smem (1024-byte aligned for the 128B swizzle atoms)
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
-  const int b_stage_bytes = p.block_n * 128;
-  uint8_t* a_smem = smem;                                   // stages * 16 KB
-  uint8_t* b_smem = a_smem + p.stages * kAStageBytes;       // stages * block_n * 128
-  uint8_t* o_smem = b_smem + p.stages * b_stage_bytes;      // 2 * 16 KB
+  const int b_tap_bytes = p.block_n * 128;                  // one weight tile [block_n][64]
+  const int b_stage_bytes = p.b_resident ? 0 : p.max_group * b_tap_bytes;
+  const int stage_bytes = p.a_stage_bytes + b_stage_bytes;
+  uint8_t* res_b = smem;                                    // resident weights: taps * k_chunks tiles
+  uint8_t* ring = res_b + (p.b_resident ? p.num_taps * p.k_chunks * b_tap_bytes : 0);
+  uint8_t* o_smem = ring + p.stages * stage_bytes;          // 2 * 16 KB output staging
 
   const int n_tile = blockIdx.x % p.n_tiles;  // grid is a multiple of n_tiles
   const int bn_mma = (n_tile == p.n_tiles - 1) ? p.last_n : p.block_n;
-  const int num_k_iters = p.num_taps * p.k_chunks;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) {
@@ -67,12 +74,10 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], 128);
     }
+    mbar_init(&bres_bar, 1);
     fence_barrier_init();
   }
-  for (int c = threadIdx.x; c < kMaxBlockN; c += kNumThreads) {
-    s_sum[c] = 0.f;
-    s_sq[c] = 0.f;
-  }
+  for (int c = threadIdx.x; c < 4 * 2 * kMaxBlockN; c += kNumThreads) (&s_part[0][0][0])[c] = 0.f;
   if (warp == 1) {
     tmem_alloc(&tmem_base_slot, kTmemCols);
     tmem_relinquish();
@@ -86,12 +91,25 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      for (int i = 0; i < kMaxAMaps; ++i) tma_prefetch_desc(&p.a_map[i]);
-      tma_prefetch_desc(&p.b_map);
+    {
+      const bool issuer = elect_one();
+      if (issuer) {
+        for (int i = 0; i < kMaxAMaps; ++i) tma_prefetch_desc(&p.a_map[i]);
+        tma_prefetch_desc(&p.b_map);
+      }
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = kAStageBytes + b_stage_bytes;
+      long long prof_wait_empty = 0;
+      const long long prof_t0 = p.prof ? clock64() : 0;
+      const int bcol = n_tile * p.block_n;
+      if (p.b_resident && issuer) {
+        // weight-stationary: every (tap, k-chunk) weight tile of this channel tile is loaded once
+        mbar_expect_tx(&bres_bar, p.num_taps * p.k_chunks * b_tap_bytes);
+        for (int tap = 0; tap < p.num_taps; ++tap)
+          for (int kc = 0; kc < p.k_chunks; ++kc)
+            tma_load_3d(res_b + (tap * p.k_chunks + kc) * b_tap_bytes, &p.b_map, &bres_bar, kc * kChunkK,
+                        p.taps[tap].widx, bcol);
+      }
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int m_id = tile / p.n_tiles;
         const int wb = m_id % g.tiles_w; m_id /= g.tiles_w;
@@ -99,54 +117,106 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
         const int tb = m_id % g.tiles_t; m_id /= g.tiles_t;
         const int nb = m_id;
         const int w0 = wb << g.lw, h0 = hb << g.lh, t0 = tb << g.lt, n0 = nb << g.ln;
-        const int bcol = n_tile * p.block_n;
-        for (int tap = 0; tap < p.num_taps; ++tap) {
-          const Tap tp = p.taps[tap];
+        int gb = 0;
+        for (int grp = 0; grp < p.num_groups; ++grp) {
+          const int len = p.group_len[grp];
+          const Tap lead = p.taps[gb];
+          const uint32_t tx_bytes = p.a_tx_bytes + (p.b_resident ? 0 : len * b_tap_bytes);
           for (int kc = 0; kc < p.k_chunks; ++kc) {
+            const long long c0 = p.prof ? clock64() : 0;
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_expect_tx(&full_bar[stage], tx_bytes);
-            tma_load_5d(a_smem + stage * kAStageBytes, &p.a_map[tp.map], &full_bar[stage],
-                        kc * kChunkK, w0 + tp.dw, h0 + tp.dh, t0 + tp.dt, n0);
-            tma_load_3d(b_smem + stage * b_stage_bytes, &p.b_map, &full_bar[stage], kc * kChunkK,
-                        tp.widx, bcol);
+            if (p.prof) prof_wait_empty += clock64() - c0;
+            if (issuer) {
+              mbar_expect_tx(&full_bar[stage], tx_bytes);
+              uint8_t* st = ring + stage * stage_bytes;
+              tma_load_5d(st, &p.a_map[lead.map], &full_bar[stage], kc * kChunkK, w0 + lead.dw, h0 + lead.dh,
+                          t0 + lead.dt, n0);
+              if (!p.b_resident)
+                for (int i = 0; i < len; ++i)
+                  tma_load_3d(st + p.a_stage_bytes + i * b_tap_bytes, &p.b_map, &full_bar[stage], kc * kChunkK,
+                              p.taps[gb + i].widx, bcol);
+            }
+            __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
+          gb += len;
         }
+      }
+      if (p.prof && issuer) {
+        p.prof[blockIdx.x * 8 + 0] = clock64() - prof_t0;   // producer total
+        p.prof[blockIdx.x * 8 + 1] = prof_wait_empty;       // producer waiting for a free stage
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    {
+      const bool issuer = elect_one();
       const uint32_t idesc = make_idesc_bf16(kTileM, bn_mma, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      long long prof_wait_full = 0, prof_wait_acc = 0;
+      const long long prof_t0 = p.prof ? clock64() : 0;
+      const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO=1024 B, version 1, SWIZZLE_128B
+      const uint32_t desc_lo_flags = 1u << 16;                           // LBO field (unused for K-major swizzled)
+      const uint32_t ring_enc = smem_u32(ring) >> 4, res_enc = smem_u32(res_b) >> 4;
+      const uint32_t stage_enc = (uint32_t)stage_bytes >> 4, btb_enc = (uint32_t)b_tap_bytes >> 4;
+      const uint32_t a_stage_enc = (uint32_t)p.a_stage_bytes >> 4;
+      if (p.b_resident) {
+        mbar_wait(&bres_bar, 0);
+        tc_fence_after_sync();
+      }
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
+        const long long ca = p.prof ? clock64() : 0;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        if (p.prof) prof_wait_acc += clock64() - ca;
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * kMaxBlockN;
-        int kiter = 0;
-        for (int tap = 0; tap < p.num_taps; ++tap) {
-          for (int kc = 0; kc < p.k_chunks; ++kc, ++kiter) {
+        uint32_t accumulate = 0;
+        int gb = 0;
+        for (int grp = 0; grp < p.num_groups; ++grp) {
+          const int len = p.group_len[grp];
+          for (int kc = 0; kc < p.k_chunks; ++kc) {
+            const long long cf = p.prof ? clock64() : 0;
             mbar_wait(&full_bar[stage], phase);
+            if (p.prof) prof_wait_full += clock64() - cf;
             tc_fence_after_sync();
-            const uint64_t adesc =
-                make_smem_desc(smem_u32(a_smem + stage * kAStageBytes), 16, 1024);
-            const uint64_t bdesc =
-                make_smem_desc(smem_u32(b_smem + stage * b_stage_bytes), 16, 1024);
+            // descriptor low words (start address >> 4 | LBO field); the high word is a constant
+            const uint32_t st_lo = desc_lo_flags | (ring_enc + (uint32_t)stage * stage_enc);
+            const uint32_t b_lo = p.b_resident ? (desc_lo_flags | (res_enc + (uint32_t)kc * btb_enc)) : st_lo;
             const int ksteps = (kc == p.k_chunks - 1) ? p.k_steps_last : 4;
-            for (int k = 0; k < ksteps; ++k) {
-              // +32 bytes along K inside the 128B swizzle span = +2 in (addr >> 4) units
-              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kiter | k) != 0);
+            for (int i = 0; i < len; ++i) {
+              // the tap's 128 rows start shift_rows rows into the shared (halo) A box; shifts are multiples
+              // of 8 rows = 1024 B, so the 128B-swizzle phase of every row is unchanged.
+              // (offsets come from the kernel-parameter constant bank: uniform loads, no smem round trip)
+              const uint32_t aoff = (uint32_t)p.taps[gb + i].shift_rows * 8u;
+              const uint32_t boff = p.b_resident ? (uint32_t)((gb + i) * p.k_chunks) * btb_enc
+                                                 : a_stage_enc + (uint32_t)i * btb_enc;
+              const uint32_t al = st_lo + aoff, bl = b_lo + boff;
+              if (issuer) {
+                // +32 bytes along K inside the 128B swizzle span = +2 in (addr >> 4) units
+                umma_bf16_lohi(d_tmem, al, bl, desc_hi, idesc, accumulate);
+                if (ksteps > 1) umma_bf16_lohi(d_tmem, al + 2, bl + 2, desc_hi, idesc, 1);
+                if (ksteps > 2) umma_bf16_lohi(d_tmem, al + 4, bl + 4, desc_hi, idesc, 1);
+                if (ksteps > 3) umma_bf16_lohi(d_tmem, al + 6, bl + 6, desc_hi, idesc, 1);
+              }
+              accumulate = 1;
             }
-            umma_commit(&empty_bar[stage]);
+            if (issuer) umma_commit(&empty_bar[stage]);
+            __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
+          gb += len;
         }
-        (void)num_k_iters;
-        umma_commit(&tmem_full_bar[acc]);
+        if (issuer) umma_commit(&tmem_full_bar[acc]);
+        __syncwarp();
+      }
+      if (p.prof && issuer) {
+        p.prof[blockIdx.x * 8 + 2] = clock64() - prof_t0;   // MMA issuer total
+        p.prof[blockIdx.x * 8 + 3] = prof_wait_full;        // waiting for TMA data
+        p.prof[blockIdx.x * 8 + 4] = prof_wait_acc;         // waiting for the epilogue to free an accumulator
       }
     }
   } else {
@@ -164,6 +234,8 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
     const bool do_stats = p.stats != nullptr;
     int it = 0;
     uint32_t obuf = 0;
+    long long prof_epi_wait = 0;
+    const long long prof_t0 = (p.prof && et == 0) ? clock64() : 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       int m_id = tile / p.n_tiles;
       const int wb = m_id % g.tiles_w; m_id /= g.tiles_w;
@@ -175,52 +247,63 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
                          (n0 + rn < g.ext_n);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      const long long ce = (p.prof && et == 0) ? clock64() : 0;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
+      if (p.prof && et == 0) prof_epi_wait += clock64() - ce;
       tc_fence_after_sync();
       const uint32_t t_addr = tmem_base + acc * kMaxBlockN + (static_cast<uint32_t>(q * 32) << 16);
-      for (int cc = 0; cc < nchunks; ++cc, obuf ^= 1) {
+      for (int cc = 0; cc < nchunks; ++cc) {
         const int ncols = min(64, bn_mma - cc * 64);
         uint8_t* ob = o_smem + obuf * kOutBufBytes;
-        // the TMA store that last read this buffer was committed two chunks ago
-        if (leader) tma_store_wait_read<1>();
-        named_bar_sync(1, 128);
-        uint8_t* orow = ob + row * 128;
-        for (int gi = 0; gi < (ncols >> 4); ++gi) {
-          uint32_t v[16];
-          tmem_ld16(t_addr + cc * 64 + gi * 16, v);
-          tmem_ld_wait();
-          uint32_t pk[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float f0 = __uint_as_float(v[2 * j]);
-            float f1 = __uint_as_float(v[2 * j + 1]);
-            if (p.bias != nullptr) {
-              const int c = bcol + cc * 64 + gi * 16 + 2 * j;
-              f0 += (c < p.stats_ld) ? p.bias[c] : 0.f;
-              f1 += (c + 1 < p.stats_ld) ? p.bias[c + 1] : 0.f;
-            }
-            if (!valid) { f0 = 0.f; f1 = 0.f; }
-            __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
-            pk[j] = *reinterpret_cast<uint32_t*>(&h);
-          }
-          const int c16a = (2 * gi) ^ (row & 7);
-          const int c16b = (2 * gi + 1) ^ (row & 7);
-          *reinterpret_cast<uint4*>(orow + c16a * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(orow + c16b * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        }
+        obuf = (obuf == kOutBufs - 1) ? 0 : obuf + 1;
+        // all TMEM loads of the chunk in flight together, one wait
+        uint32_t v[64];
+        tmem_ld16(t_addr + cc * 64, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+        if (ncols > 16) tmem_ld16(t_addr + cc * 64 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+        if (ncols > 32) tmem_ld16(t_addr + cc * 64 + 32, *reinterpret_cast<uint32_t(*)[16]>(&v[32]));
+        if (ncols > 48) tmem_ld16(t_addr + cc * 64 + 48, *reinterpret_cast<uint32_t(*)[16]>(&v[48]));
+        tmem_ld_wait();
         if (cc == nchunks - 1) {
-          // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+          // the accumulator now lives in registers: hand the TMEM buffer back to the MMA warp
           tc_fence_before_sync();
           mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        uint8_t* orow = ob + row * 128;
+#pragma unroll
+        for (int gi = 0; gi < 4; ++gi) {
+          if (gi * 16 < ncols) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float f0 = __uint_as_float(v[gi * 16 + 2 * j]);
+              float f1 = __uint_as_float(v[gi * 16 + 2 * j + 1]);
+              if (p.bias != nullptr) {
+                const int c = bcol + cc * 64 + gi * 16 + 2 * j;
+                f0 += (c < p.stats_ld) ? p.bias[c] : 0.f;
+                f1 += (c + 1 < p.stats_ld) ? p.bias[c + 1] : 0.f;
+              }
+              if (!valid) { f0 = 0.f; f1 = 0.f; }
+              __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+              pk[j] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            const int c16a = (2 * gi) ^ (row & 7);
+            const int c16b = (2 * gi + 1) ^ (row & 7);
+            *reinterpret_cast<uint4*>(orow + c16a * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(orow + c16b * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
         }
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
         if (leader) {
           tma_store_5d(&p.out_map, ob, bcol + cc * 64, w0, h0, t0, n0);
           tma_store_commit();
+          // <= 1 store pending from here on: together with the next chunk's barrier this guarantees that
+          // the buffer written two chunks ago has been read before anybody overwrites it (3 buffers)
+          tma_store_wait_read<1>();
         }
         if (do_stats) {
-          // column sums over the stored bf16 tile: thread -> (channel pair, row quarter)
+          // column sums over the stored bf16 tile: thread -> (channel pair, row quarter); every
+          // (row quarter, channel) partial is owned by exactly one thread -> no atomics
           const int word = et & 31;
           const int rq = et >> 5;
           if (word * 2 < ncols) {
@@ -234,11 +317,19 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
               b0 = fmaf(f.x, f.x, b0); b1 = fmaf(f.y, f.y, b1);
             }
             const int c = cc * 64 + word * 2;
-            atomicAdd(&s_sum[c], a0); atomicAdd(&s_sum[c + 1], a1);
-            atomicAdd(&s_sq[c], b0);  atomicAdd(&s_sq[c + 1], b1);
+            float2* ps = reinterpret_cast<float2*>(&s_part[rq][0][c]);
+            float2* pq = reinterpret_cast<float2*>(&s_part[rq][1][c]);
+            float2 s2 = *ps, q2 = *pq;
+            s2.x += a0; s2.y += a1; q2.x += b0; q2.y += b1;
+            *ps = s2; *pq = q2;
           }
         }
       }
+    }
+    if (p.prof && et == 0) {
+      p.prof[blockIdx.x * 8 + 5] = clock64() - prof_t0;     // epilogue total
+      p.prof[blockIdx.x * 8 + 6] = prof_epi_wait;           // epilogue waiting for an accumulator
+      p.prof[blockIdx.x * 8 + 7] = it;                      // tiles processed by this CTA
     }
     if (leader) tma_store_wait_all<0>();
     if (do_stats) {
@@ -246,8 +337,12 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
       for (int c = et; c < bn_mma; c += 128) {
         const int gc = bcol + c;
         if (gc < p.stats_ld) {
-          atomicAdd(&p.stats[gc], static_cast<double>(s_sum[c]));
-          atomicAdd(&p.stats[p.stats_ld + gc], static_cast<double>(s_sq[c]));
+          const double su = (double)s_part[0][0][c] + (double)s_part[1][0][c] + (double)s_part[2][0][c] +
+                            (double)s_part[3][0][c];
+          const double sq = (double)s_part[0][1][c] + (double)s_part[1][1][c] + (double)s_part[2][1][c] +
+                            (double)s_part[3][1][c];
+          atomicAdd(&p.stats[gc], su);
+          atomicAdd(&p.stats[p.stats_ld + gc], sq);
         }
       }
     }
@@ -298,8 +393,6 @@ static int encode_view(CUtensorMap* m, const View5& v, const uint32_t box[5]) {
   return encode_tmap(m, v.base, 2, 5, dims, strides, box, /*swizzle128=*/true);
 }
 
-static int ilog2(int x) { int l = 0; while ((1 << l) < x) ++l; return l; }
-
 // Choose a 128-position tile box (tn,tt,th,tw powers of two) minimising padded volume.
 void choose_tile(int N, int T, int H, int W, int* ln, int* lt, int* lh, int* lw) {
   double best = 1e30;
@@ -336,36 +429,154 @@ static void pick_block_n(int rows_p, int* n_tiles, int* block_n, int* last_n) {
   *last_n = round_up(rows_p - (*n_tiles - 1) * best_bn, 16);
 }
 
-// Launch the multi-tap tile GEMM: out(view) = sum_taps in(view shifted) * w[tap].
-//   in_base : NDHWC view the taps index into (possibly different parity sub-views per tap)
-//   taps    : filled by the caller together with the a_maps
-static int launch_conv_tiles(ConvTileParams& P, const View5& outv, int out_rows_p,
-                             const void* w_packed, int w_rows_p, int w_taps, int kin_p,
-                             double* stats, const float* bias, cudaStream_t stream) {
-  // tile geometry over the output view
+// One filter tap as the host sees it: which input view (stride-parity class) it reads and the offset of
+// its box origin relative to the output tile origin, in that view's coordinates.
+struct TapSpec {
+  int view;
+  int ot, oh, ow;
+  int widx;
+};
+
+using MapEncoder = int (*)(CUtensorMap*, const void* ctx, int view, const uint32_t box[5]);
+
+static long long* g_prof = nullptr;
+void set_conv_profile(long long* p) { g_prof = p; }
+static int g_halo_enabled = 1;      // DV_CONV_HALO=0 disables tap grouping (A/B testing)
+static int g_resident_enabled = 1;  // DV_CONV_RESIDENT=0 disables weight-stationary CTAs
+static void read_env_once() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  if (const char* e = getenv("DV_CONV_HALO")) g_halo_enabled = atoi(e);
+  if (const char* e = getenv("DV_CONV_RESIDENT")) g_resident_enabled = atoi(e);
+}
+
+// out(view) = sum_taps A_view(tap)[box shifted by tap] * W[tap]
+//
+// Tap grouping (halo re-use): taps that differ only by whole rows-of-8 of the tile share ONE TMA box
+// with a halo; each tap's MMA reads its 128 rows through a descriptor shifted by a multiple of 1024 B.
+//   temporal-only filters  : one group, box (tw, th, tt + kt - 1), tile th*tw multiple of 8
+//   filters with kh > 1    : tile (tt=1, th=16, tw=8), one group per kw, box (8, 16 + kh - 1, kt)
+// Everything else (strided layers = several views, small maps) keeps one box per tap.
+static int conv_multi_tap(ConvTileParams& P, MapEncoder enc, const void* enc_ctx, int n_views,
+                          const std::vector<TapSpec>& taps_in, const View5& outv, int out_rows_p,
+                          const void* w_packed, int w_rows_p, int w_taps, int kin_p, double* stats,
+                          const float* bias, cudaStream_t stream, bool allow_group = true) {
+  read_env_once();
+  if (taps_in.empty()) return fail(kBadArg, "convolution has no valid taps");
+  if ((int)taps_in.size() > kMaxTaps) return fail(kUnsupported, "too many filter taps (%d)", (int)taps_in.size());
   TileGeom& g = P.g;
-  choose_tile((int)outv.dim[4], (int)outv.dim[3], (int)outv.dim[2], (int)outv.dim[1], &g.ln, &g.lt,
-              &g.lh, &g.lw);
-  g.ext_w = (int)outv.dim[1]; g.ext_h = (int)outv.dim[2]; g.ext_t = (int)outv.dim[3]; g.ext_n = (int)outv.dim[4];
-  g.tiles_w = ceil_div(g.ext_w, 1 << g.lw);
-  g.tiles_h = ceil_div(g.ext_h, 1 << g.lh);
-  g.tiles_t = ceil_div(g.ext_t, 1 << g.lt);
-  g.tiles_n = ceil_div(g.ext_n, 1 << g.ln);
+  const int eN = (int)outv.dim[4], eT = (int)outv.dim[3], eH = (int)outv.dim[2], eW = (int)outv.dim[1];
+  int min_t = 1 << 20, max_t = -(1 << 20), min_h = min_t, max_h = max_t, min_w = min_t, max_w = max_t;
+  for (const TapSpec& t : taps_in) {
+    min_t = std::min(min_t, t.ot); max_t = std::max(max_t, t.ot);
+    min_h = std::min(min_h, t.oh); max_h = std::max(max_h, t.oh);
+    min_w = std::min(min_w, t.ow); max_w = std::max(max_w, t.ow);
+  }
+  const int span_t = max_t - min_t + 1, span_h = max_h - min_h + 1, span_w = max_w - min_w + 1;
+  enum { kPlain, kTemporal, kRows } mode = kPlain;
+  if (g_halo_enabled && allow_group && n_views == 1 && taps_in.size() > 1) {
+    if (span_h == 1 && span_w == 1 && span_t > 1) {
+      mode = kTemporal;
+    } else if (span_h > 1) {
+      const double waste = (double)round_up(eW, 8) * round_up(eH, 16) / ((double)eW * eH);
+      if (waste <= 1.16 && (16 + span_h - 1) * 8 * span_t * 128 <= 64 * 1024) mode = kRows;
+    }
+  }
+  uint32_t abox[5];  // A box (channels, w, h, t, n)
+  if (mode == kTemporal) {
+    double best = 1e30;
+    int blw = 3, blh = 0, blt = 4;
+    for (int a = 0; a <= 7; ++a)
+      for (int b = 0; a + b <= 7; ++b) {
+        if (a + b < 3) continue;               // th*tw must be a multiple of 8 rows
+        const int c = 7 - a - b;
+        const int tw = 1 << a, th = 1 << b, tt = 1 << c;
+        if (tt + span_t - 1 > 256 || (tt + span_t - 1) * th * tw * 128 > 48 * 1024) continue;
+        const double vol = (double)round_up(eW, tw) * round_up(eH, th) * round_up(eT, tt);
+        const double cost = vol * (double)(tt + span_t - 1) / tt * (1.0 + 0.02 * (7 - a));
+        if (cost < best) { best = cost; blw = a; blh = b; blt = c; }
+      }
+    g.lw = blw; g.lh = blh; g.lt = blt; g.ln = 0;
+    abox[0] = kChunkK; abox[1] = 1u << g.lw; abox[2] = 1u << g.lh; abox[3] = (1u << g.lt) + span_t - 1; abox[4] = 1;
+  } else if (mode == kRows) {
+    g.lw = 3; g.lh = 4; g.lt = 0; g.ln = 0;
+    abox[0] = kChunkK; abox[1] = 8; abox[2] = 16 + span_h - 1; abox[3] = span_t; abox[4] = 1;
+  } else {
+    choose_tile(eN, eT, eH, eW, &g.ln, &g.lt, &g.lh, &g.lw);
+    abox[0] = kChunkK; abox[1] = 1u << g.lw; abox[2] = 1u << g.lh; abox[3] = 1u << g.lt; abox[4] = 1u << g.ln;
+  }
+  g.ext_w = eW; g.ext_h = eH; g.ext_t = eT; g.ext_n = eN;
+  g.tiles_w = ceil_div(eW, 1 << g.lw);
+  g.tiles_h = ceil_div(eH, 1 << g.lh);
+  g.tiles_t = ceil_div(eT, 1 << g.lt);
+  g.tiles_n = ceil_div(eN, 1 << g.ln);
+
+  // ---- taps and groups
+  int ntaps = 0, ngroups = 0, max_group = 1;
+  if (mode == kPlain) {
+    for (const TapSpec& t : taps_in) {
+      Tap& tp = P.taps[ntaps];
+      tp.map = (int8_t)t.view; tp.dt = (int8_t)t.ot; tp.dh = (int8_t)t.oh; tp.dw = (int8_t)t.ow;
+      tp.widx = (int16_t)t.widx; tp.shift_rows = 0;
+      P.group_len[ngroups++] = 1;
+      ++ntaps;
+    }
+  } else {
+    // groups: all taps with the same ow (temporal mode has a single ow); leader origin = (min_t, min_h, ow)
+    const int bh = (int)abox[2], bw = (int)abox[1];
+    for (int ow = min_w; ow <= max_w; ++ow) {
+      int len = 0;
+      for (const TapSpec& t : taps_in) {
+        if (t.ow != ow) continue;
+        Tap& tp = P.taps[ntaps++];
+        tp.map = 0; tp.dt = (int8_t)min_t; tp.dh = (int8_t)min_h; tp.dw = (int8_t)ow;
+        tp.widx = (int16_t)t.widx;
+        tp.shift_rows = (int16_t)(((t.ot - min_t) * bh + (t.oh - min_h)) * bw);
+        ++len;
+      }
+      if (len == 0) continue;
+      if (len > 255) return fail(kUnsupported, "tap group too large");
+      P.group_len[ngroups++] = (uint8_t)len;
+      max_group = std::max(max_group, len);
+    }
+  }
+  P.num_taps = ntaps; P.num_groups = ngroups; P.max_group = max_group;
+  const int a_rows = (int)(abox[1] * abox[2] * abox[3] * abox[4]);
+  P.a_tx_bytes = a_rows * 128;
+  P.a_stage_bytes = round_up(P.a_tx_bytes, 1024);
+
+  for (int v = 0; v < n_views; ++v) {
+    int rc = enc(&P.a_map[v], enc_ctx, v, abox);
+    if (rc) return rc;
+  }
+  for (int i = n_views; i < kMaxAMaps; ++i) P.a_map[i] = P.a_map[0];
+
   pick_block_n(out_rows_p, &P.n_tiles, &P.block_n, &P.last_n);
   P.k_chunks = ceil_div(kin_p, kChunkK);
   P.k_steps_last = ceil_div(kin_p - (P.k_chunks - 1) * kChunkK, 16);
   const long long m_tiles = (long long)g.tiles_w * g.tiles_h * g.tiles_t * g.tiles_n;
   P.total_tiles = (int)(m_tiles * P.n_tiles);
-  const int stage_bytes = kAStageBytes + P.block_n * 128;
-  P.stages = (kSmemBudget - 1024 - 2 * kOutBufBytes) / stage_bytes;
+  const int b_tap_bytes = P.block_n * 128;
+  const int avail = kSmemBudget - 1024 - kOutBufs * kOutBufBytes;
+  const int res_bytes = ntaps * P.k_chunks * b_tap_bytes;
+  // weight-stationary when the whole filter of this channel tile fits next to >= 3 A stages and the CTA
+  // amortises the load over several tiles
+  P.b_resident = (g_resident_enabled && P.n_tiles == 1 && res_bytes <= 112 * 1024 &&
+                  avail - res_bytes >= 3 * P.a_stage_bytes && P.total_tiles >= 3 * sm_count()) ? 1 : 0;
+  const int stage_bytes = P.a_stage_bytes + (P.b_resident ? 0 : max_group * b_tap_bytes);
+  P.stages = (avail - (P.b_resident ? res_bytes : 0)) / stage_bytes;
   if (P.stages > kMaxStages) P.stages = kMaxStages;
+  if (P.stages < 3 && mode != kPlain)   // wide layers: a group's weight tiles do not fit -> one box per tap
+    return conv_multi_tap(P, enc, enc_ctx, n_views, taps_in, outv, out_rows_p, w_packed, w_rows_p, w_taps, kin_p,
+                          stats, bias, stream, false);
   if (P.stages < 2) return fail(kUnsupported, "conv tile: not enough shared memory for 2 stages");
   P.stats = stats;
   P.stats_ld = out_rows_p;
   P.bias = bias;
+  P.prof = g_prof;
 
-  // weights: [rows][taps][kin_p] bf16, box (64, 1, block_n)
-  {
+  {  // weights: [rows][taps][kin_p] bf16, box (64, 1, block_n)
     uint64_t dims[3] = {(uint64_t)kin_p, (uint64_t)w_taps, (uint64_t)w_rows_p};
     uint64_t strides[3] = {2, (uint64_t)kin_p * 2, (uint64_t)kin_p * w_taps * 2};
     uint32_t box[3] = {kChunkK, 1, (uint32_t)P.block_n};
@@ -377,7 +588,7 @@ static int launch_conv_tiles(ConvTileParams& P, const View5& outv, int out_rows_
     int rc = encode_view(&P.out_map, outv, box);
     if (rc) return rc;
   }
-  const int smem_bytes = 1024 + P.stages * stage_bytes + 2 * kOutBufBytes;
+  const int smem_bytes = 1024 + (P.b_resident ? res_bytes : 0) + P.stages * stage_bytes + kOutBufs * kOutBufBytes;
   static bool attr_set = false;
   if (!attr_set) {
     DV_CUDA_OK(cudaFuncSetAttribute(conv_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -394,48 +605,44 @@ static int launch_conv_tiles(ConvTileParams& P, const View5& outv, int out_rows_
 static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 static int posmod(int a, int b) { int m = a % b; return m < 0 ? m + b : m; }
 
+struct ViewSet {
+  View5 v[kMaxAMaps];
+};
+static int encode_from_viewset(CUtensorMap* m, const void* ctx, int view, const uint32_t box[5]) {
+  return encode_view(m, static_cast<const ViewSet*>(ctx)->v[view], box);
+}
+
 int conv_fprop_bf16(const void* x, const void* w_packed, void* y, double* stats, const float* bias,
                     const ConvGeom& c, cudaStream_t stream) {
   static thread_local ConvTileParams P;
   const View5 inv = make_ndhwc(x, c.N, c.T, c.H, c.W, c.Cin_p);
   const View5 outv = make_ndhwc(y, c.N, c.To, c.Ho, c.Wo, c.Cout_p);
-  int ln, lt, lh, lw;
-  choose_tile(c.N, c.To, c.Ho, c.Wo, &ln, &lt, &lh, &lw);
-  const uint32_t box[5] = {kChunkK, 1u << lw, 1u << lh, 1u << lt, 1u << ln};
+  ViewSet vs;
   int map_of_parity[8];
   for (int i = 0; i < 8; ++i) map_of_parity[i] = -1;
-  int nmaps = 0, ntaps = 0;
+  int nviews = 0;
+  std::vector<TapSpec> taps;
   for (int a = 0; a < c.kt; ++a)
     for (int b = 0; b < c.kh; ++b)
       for (int d = 0; d < c.kw; ++d) {
         const int ot = a - c.pt, oh = b - c.ph, ow = d - c.pw;
         const int rt = posmod(ot, c.st), rh = posmod(oh, c.sh), rw = posmod(ow, c.sw);
+        if (rt > 1 || rh > 1 || rw > 1) return fail(kUnsupported, "conv stride > 2 not supported");
         if (rt >= c.T || rh >= c.H || rw >= c.W) continue;  // tap never touches real data
         const int key = (rt * 2 + rh) * 2 + rw;
-        if (rt > 1 || rh > 1 || rw > 1) return fail(kUnsupported, "conv stride > 2 not supported");
         if (map_of_parity[key] < 0) {
           View5 v = inv;
           subsample(v, 3, rt, c.st);
           subsample(v, 2, rh, c.sh);
           subsample(v, 1, rw, c.sw);
-          int rc = encode_view(&P.a_map[nmaps], v, box);
-          if (rc) return rc;
-          map_of_parity[key] = nmaps++;
+          vs.v[nviews] = v;
+          map_of_parity[key] = nviews++;
         }
-        if (ntaps >= kMaxTaps) return fail(kUnsupported, "too many filter taps (%d)", c.kt * c.kh * c.kw);
-        Tap& tp = P.taps[ntaps++];
-        tp.map = (int8_t)map_of_parity[key];
-        tp.dt = (int8_t)floordiv(ot, c.st);
-        tp.dh = (int8_t)floordiv(oh, c.sh);
-        tp.dw = (int8_t)floordiv(ow, c.sw);
-        tp.widx = (int16_t)((a * c.kh + b) * c.kw + d);
-        tp.pad_ = 0;
+        taps.push_back({map_of_parity[key], floordiv(ot, c.st), floordiv(oh, c.sh), floordiv(ow, c.sw),
+                        (a * c.kh + b) * c.kw + d});
       }
-  for (int i = nmaps; i < kMaxAMaps; ++i) P.a_map[i] = P.a_map[0];
-  P.num_taps = ntaps;
-  if (ntaps == 0) return fail(kBadArg, "convolution has no valid taps");
-  return launch_conv_tiles(P, outv, c.Cout_p, w_packed, c.Cout_p, c.kt * c.kh * c.kw, c.Cin_p,
-                           stats, bias, stream);
+  return conv_multi_tap(P, encode_from_viewset, &vs, nviews, taps, outv, c.Cout_p, w_packed, c.Cout_p,
+                        c.kt * c.kh * c.kw, c.Cin_p, stats, bias, stream);
 }
 
 // dX = dgrad(dY, W): one launch per stride-parity class of dX positions; each class is a
@@ -444,7 +651,8 @@ int conv_fprop_bf16(const void* x, const void* w_packed, void* y, double* stats,
 int conv_dgrad_bf16(const void* dy, const void* w_packed_t, void* dx, const ConvGeom& c,
                     cudaStream_t stream) {
   static thread_local ConvTileParams P;
-  const View5 dyv = make_ndhwc(dy, c.N, c.To, c.Ho, c.Wo, c.Cout_p);
+  ViewSet vs;
+  vs.v[0] = make_ndhwc(dy, c.N, c.To, c.Ho, c.Wo, c.Cout_p);
   const View5 dxv = make_ndhwc(dx, c.N, c.T, c.H, c.W, c.Cin_p);
   bool need_zero = false;
   for (int rt = 0; rt < c.st; ++rt)
@@ -466,33 +674,21 @@ int conv_dgrad_bf16(const void* dy, const void* w_packed_t, void* dx, const Conv
         subsample(ov, 3, rt, c.st);
         subsample(ov, 2, rh, c.sh);
         subsample(ov, 1, rw, c.sw);
-        int ln, lt, lh, lw;
-        choose_tile((int)ov.dim[4], (int)ov.dim[3], (int)ov.dim[2], (int)ov.dim[1], &ln, &lt, &lh, &lw);
-        const uint32_t box[5] = {kChunkK, 1u << lw, 1u << lh, 1u << lt, 1u << ln};
-        int ntaps = 0;
+        std::vector<TapSpec> taps;
         for (int a = 0; a < c.kt; ++a) {
           if (posmod(rt + c.pt - a, c.st) != 0) continue;
           for (int b = 0; b < c.kh; ++b) {
             if (posmod(rh + c.ph - b, c.sh) != 0) continue;
             for (int d = 0; d < c.kw; ++d) {
               if (posmod(rw + c.pw - d, c.sw) != 0) continue;
-              Tap& tp = P.taps[ntaps++];
-              tp.map = 0;
-              tp.dt = (int8_t)((rt + c.pt - a) / c.st);
-              tp.dh = (int8_t)((rh + c.ph - b) / c.sh);
-              tp.dw = (int8_t)((rw + c.pw - d) / c.sw);
-              tp.widx = (int16_t)((a * c.kh + b) * c.kw + d);
-              tp.pad_ = 0;
+              taps.push_back({0, (rt + c.pt - a) / c.st, (rh + c.ph - b) / c.sh, (rw + c.pw - d) / c.sw,
+                              (a * c.kh + b) * c.kw + d});
             }
           }
         }
-        if (ntaps == 0) continue;  // class receives no gradient (zero-filled above)
-        int rc = encode_view(&P.a_map[0], dyv, box);
-        if (rc) return rc;
-        for (int i = 1; i < kMaxAMaps; ++i) P.a_map[i] = P.a_map[0];
-        P.num_taps = ntaps;
-        rc = launch_conv_tiles(P, ov, c.Cin_p, w_packed_t, c.Cin_p, c.kt * c.kh * c.kw, c.Cout_p,
-                               nullptr, nullptr, stream);
+        if (taps.empty()) continue;  // class receives no gradient (zero-filled above)
+        int rc = conv_multi_tap(P, encode_from_viewset, &vs, 1, taps, ov, c.Cin_p, w_packed_t, c.Cin_p,
+                                c.kt * c.kh * c.kw, c.Cout_p, nullptr, nullptr, stream);
         if (rc) return rc;
       }
   return kOk;
@@ -502,13 +698,19 @@ int conv_dgrad_bf16(const void* dy, const void* w_packed_t, void* dx, const Conv
 // x_s2d: bf16 [N][T][H2][W2+3][16], channel = (rh*2+rw)*4 + c, two zero columns left / one right
 // (written by the ingest kernel). For output (ho,wo) and row tap a in {-2..1} the A row is the 128-byte
 // window x_s2d[n][t][ho+a][wo .. wo+3][0..15] — an OVERLAPPING-window tensor map (W stride 32 B, inner
-// extent 128 B), so K = 64 per tap instead of 49 taps of K = 16.
+// extent 128 B), so K = 64 per tap instead of 49 taps of K = 16. The 4 row taps form one halo group.
 // w_stem: bf16 [Cout_p][kt*4][64] (pack_stem_weights).
-static int encode_stem_map(CUtensorMap* m, const void* x, int N, int T, int H2, int W2, const uint32_t box[5]) {
-  const long long W2p = W2 + 3;
-  uint64_t dims[5] = {64, (uint64_t)W2, (uint64_t)H2, (uint64_t)T, (uint64_t)N};
-  uint64_t strides[5] = {2, 32, (uint64_t)W2p * 32, (uint64_t)H2 * W2p * 32, (uint64_t)T * H2 * W2p * 32};
-  return encode_tmap(m, x, 2, 5, dims, strides, box, true);
+struct StemCtx {
+  const void* x;
+  int N, T, H2, W2;
+};
+static int encode_stem_map(CUtensorMap* m, const void* ctx, int /*view*/, const uint32_t box[5]) {
+  const StemCtx* s = static_cast<const StemCtx*>(ctx);
+  const long long W2p = s->W2 + 3;
+  uint64_t dims[5] = {64, (uint64_t)s->W2, (uint64_t)s->H2, (uint64_t)s->T, (uint64_t)s->N};
+  uint64_t strides[5] = {2, 32, (uint64_t)W2p * 32, (uint64_t)s->H2 * W2p * 32,
+                         (uint64_t)s->T * s->H2 * W2p * 32};
+  return encode_tmap(m, s->x, 2, 5, dims, strides, box, true);
 }
 
 int conv_stem_fprop_bf16(const void* x_s2d, const void* w_stem, void* y, double* stats, const float* bias,
@@ -516,22 +718,12 @@ int conv_stem_fprop_bf16(const void* x_s2d, const void* w_stem, void* y, double*
   static thread_local ConvTileParams P;
   const int To = T + 2 * pt - kt + 1;
   const View5 outv = make_ndhwc(y, N, To, H2, W2, Cout_p);
-  int ln, lt, lh, lw;
-  choose_tile(N, To, H2, W2, &ln, &lt, &lh, &lw);
-  const uint32_t box[5] = {kChunkK, 1u << lw, 1u << lh, 1u << lt, 1u << ln};
-  int rc = encode_stem_map(&P.a_map[0], x_s2d, N, T, H2, W2, box);
-  if (rc) return rc;
-  for (int i = 1; i < kMaxAMaps; ++i) P.a_map[i] = P.a_map[0];
-  int ntaps = 0;
+  StemCtx sc = {x_s2d, N, T, H2, W2};
+  std::vector<TapSpec> taps;
   for (int a = 0; a < kt; ++a)
-    for (int r = 0; r < 4; ++r) {
-      Tap& tp = P.taps[ntaps];
-      tp.map = 0; tp.dt = (int8_t)(a - pt); tp.dh = (int8_t)(r - 2); tp.dw = 0;
-      tp.widx = (int16_t)ntaps; tp.pad_ = 0;
-      ++ntaps;
-    }
-  P.num_taps = ntaps;
-  return launch_conv_tiles(P, outv, Cout_p, w_stem, Cout_p, ntaps, 64, stats, bias, stream);
+    for (int r = 0; r < 4; ++r) taps.push_back({0, a - pt, r - 2, 0, a * 4 + r});
+  return conv_multi_tap(P, encode_stem_map, &sc, 1, taps, outv, Cout_p, w_stem, Cout_p, kt * 4, 64, stats,
+                        bias, stream);
 }
 
 }  // namespace dv

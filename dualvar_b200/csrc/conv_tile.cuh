@@ -21,9 +21,9 @@ constexpr int kMaxBlockN = 256;
 
 struct Tap {
   int8_t map;    // which a_map (stride parity class)
-  int8_t dt, dh, dw;  // box origin offset in map coordinates
+  int8_t dt, dh, dw;  // A box origin offset in map coordinates (of the group leader = first tap of a group)
   int16_t widx;  // tap index in the packed weight tensor
-  int16_t pad_;
+  int16_t shift_rows;  // row offset of this tap's 128 rows inside its group's (halo) A box, multiple of 8
 };
 
 struct TileGeom {
@@ -39,8 +39,14 @@ struct alignas(64) ConvTileParams {
   CUtensorMap b_map;     // weights [rows=Cout_p][taps][Cin_p], box (64, 1, block_n)
   CUtensorMap out_map;   // output NDHWC, box (64, tw, th, tt, tn), 128B swizzle
   Tap taps[kMaxTaps];
+  uint8_t group_len[kMaxTaps];  // taps are grouped in runs; a group shares ONE A box (halo re-use)
   TileGeom g;
   int num_taps;
+  int num_groups;
+  int max_group;      // largest group
+  int a_stage_bytes;  // smem bytes reserved per stage for the A box (multiple of 1024)
+  int a_tx_bytes;     // bytes one A box transfers (rows * 128)
+  int b_resident;     // 1: all weight tiles of this CTA's channel tile stay in smem for the CTA's life
   int k_chunks;       // ceil(Cin_p / 64)
   int k_steps_last;   // UMMA K=16 steps in the last chunk (1..4)
   int n_tiles;        // channel tiles
@@ -51,6 +57,7 @@ struct alignas(64) ConvTileParams {
   double* stats;      // nullable: [2][stats_ld] per-channel sum and sum of squares (of the stored bf16)
   int stats_ld;
   const float* bias;  // nullable: per output channel, added before rounding
+  long long* prof;    // nullable debug buffer: [grid][8] cycle counters per role (see conv_fprop.cu)
 };
 
 // Convolution geometry shared by fprop / dgrad / wgrad host code (padded channel counts).

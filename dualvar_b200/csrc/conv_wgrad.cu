@@ -308,7 +308,7 @@ int conv_wgrad_bf16(const void* x, const void* dy, float* dw, const ConvGeom& c,
         tp.dh = (int8_t)floordiv_w(oh, c.sh);
         tp.dw = (int8_t)floordiv_w(ow, c.sw);
         tp.widx = (int16_t)((a * c.kh + b) * c.kw + d);
-        tp.pad_ = 0;
+        tp.shift_rows = 0;
       }
   if (ntaps == 0) return kOk;
   for (int i = nmaps; i < kMaxAMaps; ++i) P.a_map[i] = P.a_map[0];
@@ -349,7 +349,7 @@ int conv_stem_wgrad_bf16(const void* x_s2d, const void* dy, float* dw, int N, in
     for (int r = 0; r < 4; ++r) {
       Tap& tp = P.taps[ntaps];
       tp.map = 0; tp.dt = (int8_t)(a - pt); tp.dh = (int8_t)(r - 2); tp.dw = 0;
-      tp.widx = (int16_t)ntaps; tp.pad_ = 0;
+      tp.widx = (int16_t)ntaps; tp.shift_rows = 0;
       ++ntaps;
     }
   return wgrad_launch(P, ntaps, 64, Cout_p, taps_total, dw, stream);

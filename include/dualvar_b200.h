@@ -193,6 +193,9 @@ int dv_retrieval_prepare(const float* feat, double* mean, double* out, int n, in
 int dv_retrieval_sim_topk(const double* test, const double* train, double* sim, float* sim32, int64_t* idx,
                           int n_test, int n_train, int d, int k, void* stream);
 
+/* debug (tests/diag only): per-CTA role cycle counters of the next conv_tile_kernel launches are written to
+ * buf [148][8] (producer total/wait, MMA total/wait-data/wait-accumulator, epilogue total/wait, tiles); NULL = off */
+int dv_debug_set_conv_profile(int64_t* buf);
 /* debug probe (tests only): TMA tensor map with overlapping windows */
 int dv_debug_probe_overlap_tmap(const void* src, void* out, int c1, void* stream);
 

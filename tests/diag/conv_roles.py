@@ -1,0 +1,36 @@
+"""GPU diagnostic: where do the producer / MMA / epilogue roles of conv_tile_kernel spend their cycles?"""
+import os, sys, ctypes
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import torch
+from dualvar_b200 import _lib, kernels as K
+dev = "cuda:0"
+N = int(os.environ.get("NCLIPS", "96"))
+LAYERS = [("fprop temporal 144->64", "f", (N, 16, 56, 56, 144, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0))),
+          ("fprop spatial 64->144", "f", (N, 16, 56, 56, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1))),
+          ("dgrad spatial 64->144", "d", (N, 16, 56, 56, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1))),
+          ("fprop temporal 83->64", "f", (N, 16, 56, 56, 83, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0))),
+          ("fprop spatial 128->288", "f", (N, 8, 28, 28, 128, 288, (1, 3, 3), (1, 1, 1), (0, 1, 1)))]
+prof = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
+for name, kind, (n, t, h, w, ci, co, k, s, p) in LAYERS:
+    g = K.make_geom(n, t, h, w, ci, co, k, s, p)
+    x = torch.randn(n, t, h, w, g.Cin_p, device=dev).bfloat16()
+    wt = torch.randn(co, ci, *k, device=dev) / 20
+    wf, wtt = K.pack_conv_weight(wt, g)
+    dy = torch.randn(n, g.To, g.Ho, g.Wo, g.Cout_p, device=dev).bfloat16()
+    stats = torch.zeros(2 * g.Cout_p, dtype=torch.float64, device=dev)
+    run = (lambda: K.conv3d_fprop(x, wf, g, bn_stats=stats)) if kind == "f" else (lambda: K.conv3d_dgrad(dy, wtt, g))
+    for _ in range(2): run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); run(); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    prof.zero_()
+    _lib.load().dv_debug_set_conv_profile(ctypes.c_void_p(prof.data_ptr()))
+    run(); torch.cuda.synchronize()
+    _lib.load().dv_debug_set_conv_profile(None)
+    P = prof.view(148, 8).double()
+    tiles = P[:, 7].clamp_min(1)
+    per = lambda i: (P[:, i] / tiles).mean().item()
+    fl = 2.0 * n * g.To * g.Ho * g.Wo * co * ci * k[0] * k[1] * k[2]
+    print(f"{name}: {ms:.3f} ms {fl/ms/1e9:.0f} TF/s | cycles/tile: producer {per(0):.0f} (wait-free-stage {per(1):.0f}) | "
+          f"mma {per(2):.0f} (wait-data {per(3):.0f}, wait-acc {per(4):.0f}) | epilogue {per(5):.0f} (wait-acc {per(6):.0f}) | tiles/CTA {tiles.mean().item():.0f}", flush=True)
