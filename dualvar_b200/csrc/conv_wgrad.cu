@@ -45,7 +45,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
   __shared__ __align__(8) uint64_t acc_bar;
   __shared__ uint32_t tmem_base_slot;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform role index
   const int lane = threadIdx.x & 31;
   const int group = blockIdx.x / p.n_tiles;
   const int n_tile = blockIdx.x % p.n_tiles;
@@ -84,59 +84,72 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
   const TileGeom& g = p.g;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t tx = (nu + nbx) * kBoxBytes;
-      for (int tile = tile_begin; tile < tile_end; ++tile) {
-        int m_id = tile;
-        const int wb = m_id % g.tiles_w; m_id /= g.tiles_w;
-        const int hb = m_id % g.tiles_h; m_id /= g.tiles_h;
-        const int tb = m_id % g.tiles_t; m_id /= g.tiles_t;
-        const int nb = m_id;
-        const int w0 = wb << g.lw, h0 = hb << g.lh, t0 = tb << g.lt, n0 = nb << g.ln;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+    // TMA producer: the whole warp runs the loop (uniform registers feed UTMALDG), one elected lane issues
+    const bool issuer = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t tx = (nu + nbx) * kBoxBytes;
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      int m_id = tile;
+      const int wb = m_id % g.tiles_w; m_id /= g.tiles_w;
+      const int hb = m_id % g.tiles_h; m_id /= g.tiles_h;
+      const int tb = m_id % g.tiles_t; m_id /= g.tiles_t;
+      const int nb = m_id;
+      const int w0 = wb << g.lw, h0 = hb << g.lh, t0 = tb << g.lt, n0 = nb << g.ln;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (issuer) {
         mbar_expect_tx(&full_bar[stage], tx);
         uint8_t* a_s = smem + stage * stage_bytes;
         uint8_t* b_s = a_s + a_bytes;
         for (int j = 0; j < nbx; ++j)
-          tma_load_5d(b_s + j * kBoxBytes, &p.dy_map, &full_bar[stage],
-                      n_tile * p.block_n + j * 64, w0, h0, t0, n0);
+          tma_load_5d(b_s + j * kBoxBytes, &p.dy_map, &full_bar[stage], n_tile * p.block_n + j * 64, w0, h0, t0, n0);
         for (int i = 0; i < nu; ++i) {
           const int u = unit0 + i;
           const int tap = u / p.k_chunks;
           const int kc = u - tap * p.k_chunks;
           const Tap tp = p.taps[tap];
-          tma_load_5d(a_s + i * kBoxBytes, &p.a_map[tp.map], &full_bar[stage], kc * 64,
-                      w0 + tp.dw, h0 + tp.dh, t0 + tp.dt, n0);
+          tma_load_5d(a_s + i * kBoxBytes, &p.a_map[tp.map], &full_bar[stage], kc * 64, w0 + tp.dw, h0 + tp.dh,
+                      t0 + tp.dt, n0);
         }
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, bn, 1, 1);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = tile_begin; tile < tile_end; ++tile) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after_sync();
-        const uint32_t a_s = smem_u32(smem + stage * stage_bytes);
-        const uint32_t b_s = a_s + a_bytes;
+    // MMA issuer: uniform loop state (descriptor words in uniform registers), one elected lane issues
+    const bool issuer = elect_one();
+    const uint32_t idesc = make_idesc_bf16(128, bn, 1, 1);
+    // MN-major SWIZZLE_128B: 8-position (K) groups 1024 B apart (SBO), 64-channel (M/N) groups one box apart (LBO)
+    const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t lo_flags = (uint32_t)(kBoxBytes >> 4) << 16;
+    const uint32_t base_enc = smem_u32(smem) >> 4, stage_enc = (uint32_t)stage_bytes >> 4;
+    const uint32_t a_enc = (uint32_t)a_bytes >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t accumulate = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after_sync();
+      const uint32_t a_lo = lo_flags | (base_enc + (uint32_t)stage * stage_enc);
+      const uint32_t b_lo = a_lo + a_enc;
+      if (issuer) {
         for (int pr = 0; pr < npairs; ++pr) {
-          for (int k = 0; k < 4; ++k) {
-            // MN-major: 8-position groups 1024 B apart (SBO), 64-channel groups one box apart (LBO)
-            const uint64_t adesc = make_smem_desc(a_s + pr * 2 * kBoxBytes + k * 2048, kBoxBytes, 1024);
-            const uint64_t bdesc = make_smem_desc(b_s + k * 2048, kBoxBytes, 1024);
-            umma_bf16(tmem_base + pr * p.acc_stride, adesc, bdesc, idesc,
-                      (tile != tile_begin) || (k != 0));
-          }
+          const uint32_t al = a_lo + (uint32_t)pr * (2 * kBoxBytes >> 4);
+          const uint32_t dt = tmem_base + pr * p.acc_stride;
+          // one UMMA K step = 16 positions = 2048 B = +128 in (addr >> 4) units
+          umma_bf16_lohi(dt, al, b_lo, desc_hi, idesc, accumulate);
+          umma_bf16_lohi(dt, al + 128, b_lo + 128, desc_hi, idesc, 1);
+          umma_bf16_lohi(dt, al + 256, b_lo + 256, desc_hi, idesc, 1);
+          umma_bf16_lohi(dt, al + 384, b_lo + 384, desc_hi, idesc, 1);
         }
         umma_commit(&empty_bar[stage]);
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(&acc_bar);
+      accumulate = 1;
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
+    if (issuer) umma_commit(&acc_bar);
+    __syncwarp();
   } else {
     const int q = warp & 3;
     const int row = q * 32 + lane;
