@@ -25,13 +25,13 @@ int bn_finalize(const double* stats, const float* gamma, const float* beta, floa
                 float momentum, int training, cudaStream_t stream);
 int bn_apply(const void* y1, const float* ss1, const void* y2, const float* ss2, const void* res,
              void* out, long long rows, int Cp, int out_ld, int out_coff, int relu, cudaStream_t stream);
-int bn_bwd_reduce(const void* dout, const void* out, const void* y, const float* ss, double* sums,
-                  long long rows, int Cp, int o_ld, int o_coff, int relu, cudaStream_t stream);
+int bn_bwd_reduce(const void* dout, const void* dout2, const void* out, const void* y, const float* ss,
+                  double* sums, long long rows, int Cp, int o_ld, int o_coff, int relu, cudaStream_t stream);
 int bn_bwd_finalize(const double* sums_local, const double* sums_global, const float* gamma,
                     const float* saved, float* dgamma, float* dbeta, float* coef, int C, int Cp,
                     double count_global, float grad_beta, cudaStream_t stream);
-int bn_bwd_apply(const void* dout, const void* out, const void* y, const float* ss, const float* coef,
-                 void* dy, void* g_out, long long rows, int Cp, int o_ld, int o_coff, int relu,
+int bn_bwd_apply(const void* dout, const void* dout2, const void* out, const void* y, const float* ss,
+                 const float* coef, void* dy, void* g_out, long long rows, int Cp, int o_ld, int o_coff, int relu,
                  cudaStream_t stream);
 int add_bf16(const void* a, const void* b, void* out, long long n, cudaStream_t stream);
 struct PoolGeom {
@@ -193,11 +193,11 @@ int dv_bn_apply(const void* y1, const float* ss1, const void* y2, const float* s
   DV_REQUIRE((y2 == nullptr) == (ss2 == nullptr), "bn_apply: y2 and ss2 go together");
   return bn_apply(y1, ss1, y2, ss2, res, out, rows, Cp, out_ld, out_coff, relu, ST);
 }
-int dv_bn_bwd_reduce(const void* dout, const void* out, const void* y, const float* mask_ss, double* sums,
-                     int64_t rows, int Cp, int o_ld, int o_coff, int relu, void* stream) {
+int dv_bn_bwd_reduce(const void* dout, const void* dout2, const void* out, const void* y, const float* mask_ss,
+                     double* sums, int64_t rows, int Cp, int o_ld, int o_coff, int relu, void* stream) {
   DV_REQUIRE(dout && y && sums && (!relu || out || mask_ss) && rows > 0 && Cp % 8 == 0,
              "bad bn_bwd_reduce arguments");
-  return bn_bwd_reduce(dout, out, y, mask_ss, sums, rows, Cp, o_ld, o_coff, relu, ST);
+  return bn_bwd_reduce(dout, dout2, out, y, mask_ss, sums, rows, Cp, o_ld, o_coff, relu, ST);
 }
 int dv_bn_bwd_finalize(const double* sums_local, const double* sums_global, const float* gamma,
                        const float* saved, float* dgamma, float* dbeta, float* coef, int C, int Cp,
@@ -206,11 +206,12 @@ int dv_bn_bwd_finalize(const double* sums_local, const double* sums_global, cons
   return bn_bwd_finalize(sums_local, sums_global, gamma, saved, dgamma, dbeta, coef, C, Cp, count_global,
                          grad_beta, ST);
 }
-int dv_bn_bwd_apply(const void* dout, const void* out, const void* y, const float* mask_ss, const float* coef,
-                    void* dy, void* g_out, int64_t rows, int Cp, int o_ld, int o_coff, int relu, void* stream) {
+int dv_bn_bwd_apply(const void* dout, const void* dout2, const void* out, const void* y, const float* mask_ss,
+                    const float* coef, void* dy, void* g_out, int64_t rows, int Cp, int o_ld, int o_coff, int relu,
+                    void* stream) {
   DV_REQUIRE(dout && y && coef && dy && (!relu || out || mask_ss) && rows > 0 && Cp % 8 == 0,
              "bad bn_bwd_apply arguments");
-  return bn_bwd_apply(dout, out, y, mask_ss, coef, dy, g_out, rows, Cp, o_ld, o_coff, relu, ST);
+  return bn_bwd_apply(dout, dout2, out, y, mask_ss, coef, dy, g_out, rows, Cp, o_ld, o_coff, relu, ST);
 }
 int dv_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream) {
   DV_REQUIRE(a && b && out && n > 0 && n % 8 == 0, "bad add_bf16 arguments");

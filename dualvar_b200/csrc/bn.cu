@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const ApplyArgs a) {
 // dout/out rows may live inside a wider (concat) tensor: ld / channel offset given.
 struct BwdArgs {
   const __nv_bfloat16* dout; const __nv_bfloat16* out; const __nv_bfloat16* y;
+  const __nv_bfloat16* dout2;  // optional second gradient contribution (dense [rows][Cp]); g uses dout + dout2
   long long rows;
   int Cp;
   int o_ld, o_coff;   // layout of dout / out rows
@@ -166,6 +167,11 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BwdArgs a) {
            r += (long long)gridDim.x * blockDim.y) {
         const long long ooff = r * a.o_ld + a.o_coff + cg * 8;
         Vec8 d = load8(a.dout + ooff);
+        if (a.dout2) {
+          const Vec8 d2 = load8(a.dout2 + r * a.Cp + cg * 8);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d.v[i] += d2.v[i];
+        }
         const Vec8 yv = load8(a.y + r * a.Cp + cg * 8);
         if (a.relu) {
           if (a.ss) {
@@ -241,6 +247,11 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdArgs a) {
       const long long ooff = r * a.o_ld + a.o_coff + cg * 8;
       Vec8 d = load8(a.dout + ooff);
       const long long off = r * a.Cp + cg * 8;
+      if (a.dout2) {
+        const Vec8 d2 = load8(a.dout2 + off);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d.v[i] += d2.v[i];
+      }
       const Vec8 yv = load8(a.y + off);
       if (a.relu) {
         if (a.ss) {
@@ -315,10 +326,11 @@ int bn_apply(const void* y1, const float* ss1, const void* y2, const float* ss2,
   return kOk;
 }
 
-int bn_bwd_reduce(const void* dout, const void* out, const void* y, const float* ss, double* sums,
-                  long long rows, int Cp, int o_ld, int o_coff, int relu, cudaStream_t stream) {
+int bn_bwd_reduce(const void* dout, const void* dout2, const void* out, const void* y, const float* ss,
+                  double* sums, long long rows, int Cp, int o_ld, int o_coff, int relu, cudaStream_t stream) {
   BwdArgs a = {};
   a.ss = ss;
+  a.dout2 = (const __nv_bfloat16*)dout2;
   a.dout = (const __nv_bfloat16*)dout; a.out = (const __nv_bfloat16*)out;
   a.y = (const __nv_bfloat16*)y; a.rows = rows; a.Cp = Cp; a.o_ld = o_ld; a.o_coff = o_coff;
   a.relu = relu; a.sums = sums;
@@ -339,11 +351,12 @@ int bn_bwd_finalize(const double* sums_local, const double* sums_global, const f
   return kOk;
 }
 
-int bn_bwd_apply(const void* dout, const void* out, const void* y, const float* ss, const float* coef,
-                 void* dy, void* g_out, long long rows, int Cp, int o_ld, int o_coff, int relu,
+int bn_bwd_apply(const void* dout, const void* dout2, const void* out, const void* y, const float* ss,
+                 const float* coef, void* dy, void* g_out, long long rows, int Cp, int o_ld, int o_coff, int relu,
                  cudaStream_t stream) {
   BwdArgs a = {};
   a.ss = ss;
+  a.dout2 = (const __nv_bfloat16*)dout2;
   a.dout = (const __nv_bfloat16*)dout; a.out = (const __nv_bfloat16*)out;
   a.y = (const __nv_bfloat16*)y; a.rows = rows; a.Cp = Cp; a.o_ld = o_ld; a.o_coff = o_coff;
   a.relu = relu; a.coef = coef; a.dy = (__nv_bfloat16*)dy; a.g_out = (__nv_bfloat16*)g_out;

@@ -12,7 +12,7 @@ namespace dv {
 
 // C[M,N] = alpha * op(A) * op(B) + beta * C (+ bias[n]) (relu). Row-major; op(A) is MxK, op(B) is KxN.
 // ta: A stored [K][M] (lda) else [M][K]; tb: B stored [N][K] (ldb) else [K][N].
-template <int BM, int BN, int BK>
+template <int BM, int BN, int BK, int TM, int TN>
 __global__ void __launch_bounds__(256)
 sgemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, int lda, int ta,
              const float* __restrict__ B, int ldb, int tb, float beta, float* __restrict__ C, int ldc,
@@ -20,13 +20,13 @@ sgemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, int 
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
   const int tid = threadIdx.x;
-  const int tx = tid % 16, ty = tid / 16;  // 16 x 16 threads, each 4 x 4 outputs
+  const int tx = tid % (BN / TN), ty = tid / (BN / TN);  // (BM/TM) x (BN/TN) = 256 threads, each TM x TN outputs
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  float acc[4][4];
+  float acc[TM][TN];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
   for (int k0 = 0; k0 < K; k0 += BK) {
     for (int e = tid; e < BM * BK; e += 256) {
       int m, k;
@@ -47,25 +47,25 @@ sgemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, int 
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
-      float a[4], b[4];
+      float a[TM], b[TN];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+      for (int i = 0; i < TM; ++i) a[i] = As[k][ty * TM + i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+      for (int j = 0; j < TN; ++j) b[j] = Bs[k][tx * TN + j];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int gm = m0 + ty * 4 + i;
+  for (int i = 0; i < TM; ++i) {
+    const int gm = m0 + ty * TM + i;
     if (gm >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int gn = n0 + tx * 4 + j;
+    for (int j = 0; j < TN; ++j) {
+      const int gn = n0 + tx * TN + j;
       if (gn >= N) continue;
       float v = alpha * acc[i][j];
       if (bias) v += bias[gn];
@@ -128,9 +128,16 @@ __global__ void l2norm_bwd_kernel(const float* __restrict__ dy, const float* __r
 int sgemm(int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
           int ldb, float beta, float* C, int ldc, const float* bias, int relu, cudaStream_t stream) {
   if (M <= 0 || N <= 0) return kOk;
-  dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
-  sgemm_kernel<64, 64, 16><<<grid, 256, 0, stream>>>(M, N, K, alpha, A, lda, ta, B, ldb, tb, beta, C,
-                                                      ldc, bias, relu);
+  // small head / loss GEMMs: 32x32 tiles so that a 192x512 output still spreads over ~100 CTAs
+  if ((long long)ceil_div(N, 64) * ceil_div(M, 64) < 2 * sm_count()) {
+    dim3 grid(ceil_div(N, 32), ceil_div(M, 32));
+    sgemm_kernel<32, 32, 16, 2, 2><<<grid, 256, 0, stream>>>(M, N, K, alpha, A, lda, ta, B, ldb, tb, beta, C, ldc,
+                                                            bias, relu);
+  } else {
+    dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
+    sgemm_kernel<64, 64, 16, 4, 4><<<grid, 256, 0, stream>>>(M, N, K, alpha, A, lda, ta, B, ldb, tb, beta, C, ldc,
+                                                            bias, relu);
+  }
   DV_LAUNCH_OK();
   return kOk;
 }

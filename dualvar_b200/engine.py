@@ -28,12 +28,13 @@ call = _lib.call
 class Act:
     """A bf16 NDHWC activation [N,T,H,W,Cp] with C logical channels and an optional gradient."""
 
-    __slots__ = ("data", "C", "grad", "needs_grad", "s2d")
+    __slots__ = ("data", "C", "grad", "grad2", "needs_grad", "s2d")
 
     def __init__(self, data, C, needs_grad=True, s2d=None):
         self.data = data
         self.C = C
         self.grad = None
+        self.grad2 = None       # second pending contribution (summed lazily by the consumer)
         self.needs_grad = needs_grad
         self.s2d = s2d          # (N, T, H, W) of the original frames when data is the space-to-depth stem layout
 
@@ -139,10 +140,23 @@ def _is_sync(bn):
 
 
 def _acc_grad(act, g):
+    """Accumulate a gradient contribution. The second contribution is kept separate: the BN-backward
+    kernels sum two streams on the fly, so the usual "main path + shortcut" meeting needs no add pass."""
     if act.grad is None:
         act.grad = g
+    elif act.grad2 is None and g.shape == act.grad.shape:
+        act.grad2 = g
     else:
+        _materialize_grad(act)
         call("dv_add_bf16", ptr(act.grad), ptr(g), ptr(act.grad), act.grad.numel(), stream_ptr())
+
+
+def _materialize_grad(act):
+    """Fold the pending second contribution into act.grad (consumers that read a single tensor)."""
+    if act.grad2 is not None:
+        call("dv_add_bf16", ptr(act.grad), ptr(act.grad2), ptr(act.grad), act.grad.numel(), stream_ptr())
+        act.grad2 = None
+    return act.grad
 
 
 # ----------------------------------------------------------------------------- primitives
@@ -299,11 +313,15 @@ def activate(ctx, r1, r2=None, res=None, relu=True, out=None, out_coff=0):
         return out_act
 
     def backward():
-        dout = out_act.grad
+        dout2 = None
+        if out is None:
+            dout, dout2 = out_act.grad, out_act.grad2      # two pending contributions are summed in-kernel
+        else:
+            dout = _materialize_grad(out_act)
         o_ld, o_coff = out_ld, out_coff
         ov = ctx.overrides.pop((id(out_act), out_coff), None)
         if ov is not None:      # a gate in front of this slice already produced the dense gradient
-            dout, o_ld, o_coff = ov, Cp, 0
+            dout, dout2, o_ld, o_coff = ov, None, Cp, 0
         assert dout is not None, "activation has no gradient"
         need_g = res is not None and res.needs_grad
         g_buf = None
@@ -314,8 +332,8 @@ def activate(ctx, r1, r2=None, res=None, relu=True, out=None, out_coff=0):
             if r is None:
                 continue
             sums = torch.zeros(2 * Cp, dtype=torch.float64, device=dev)
-            call("dv_bn_bwd_reduce", ptr(dout), ptr(out_t), ptr(r.y), mask_ss, ptr(sums), rows, Cp, o_ld,
-                 o_coff, 1 if relu else 0, stream_ptr())
+            call("dv_bn_bwd_reduce", ptr(dout), ptr(dout2), ptr(out_t), ptr(r.y), mask_ss, ptr(sums), rows, Cp,
+                 o_ld, o_coff, 1 if relu else 0, stream_ptr())
             sums_g = sums
             if r.sync:
                 sums_g = sums.clone()
@@ -333,13 +351,13 @@ def activate(ctx, r1, r2=None, res=None, relu=True, out=None, out_coff=0):
             want_g = need_g and g_buf is None
             if want_g:
                 g_buf = torch.empty_like(r.y)
-            call("dv_bn_bwd_apply", ptr(dout), ptr(out_t), ptr(r.y), mask_ss, ptr(coef), ptr(dy),
+            call("dv_bn_bwd_apply", ptr(dout), ptr(dout2), ptr(out_t), ptr(r.y), mask_ss, ptr(coef), ptr(dy),
                  ptr(g_buf) if want_g else None, rows, Cp, o_ld, o_coff, 1 if relu else 0, stream_ptr())
             _conv_backward(ctx, r, dy)
         if need_g:
             _acc_grad(res, g_buf)
         if out is None:
-            out_act.grad = None
+            out_act.grad = out_act.grad2 = None
 
     ctx.tape.append(backward)
     return out_act
@@ -373,7 +391,7 @@ def self_gate(ctx, cat, coff, raw, fc):
         return
 
     def backward():
-        dout = cat.grad
+        dout = _materialize_grad(cat)
         dw = torch.empty((N, C), dtype=torch.float32, device=dev)
         call("dv_gate_bwd_reduce", ptr(dout), ptr(raw.y), ptr(raw.ss), ptr(dw), N, S, C, Cp, ld, coff, stream_ptr())
         dpre = torch.empty_like(dw)
@@ -408,7 +426,7 @@ def max_pool(ctx, x, kernel, stride, padding):
     if ctx.record and x.needs_grad:
         def backward():
             dx = torch.empty_like(x.data)
-            call("dv_maxpool3d_bwd", ptr(x.data), ptr(y), ptr(out.grad), ptr(dx), geom, stream_ptr())
+            call("dv_maxpool3d_bwd", ptr(x.data), ptr(y), ptr(_materialize_grad(out)), ptr(dx), geom, stream_ptr())
             _acc_grad(x, dx)
             out.grad = None
         ctx.tape.append(backward)

@@ -83,16 +83,19 @@ int dv_bn_apply(const void* y1, const float* ss1, const void* y2, const float* s
                 void* out, int64_t rows, int Cp, int out_ld, int out_coff, int relu, void* stream);
 /* sums [2][Cp] double += (sum g, sum g*y), g = dout*(out>0) if relu else dout. When the activation was
  * relu(scale*y+shift) with no residual/second branch pass its scale_shift as mask_ss: the mask is then
- * recomputed from y and `out` is not read (one HBM stream less). */
-int dv_bn_bwd_reduce(const void* dout, const void* out, const void* y, const float* mask_ss, double* sums,
-                     int64_t rows, int Cp, int o_ld, int o_coff, int relu, void* stream);
+ * recomputed from y and `out` is not read (one HBM stream less).
+ * dout2 (optional, dense [rows][Cp]) is a second gradient contribution summed on the fly — where two
+ * consumers of an activation meet (block input: main path + shortcut) no separate add pass is needed. */
+int dv_bn_bwd_reduce(const void* dout, const void* dout2, const void* out, const void* y, const float* mask_ss,
+                     double* sums, int64_t rows, int Cp, int o_ld, int o_coff, int relu, void* stream);
 /* dgamma/dbeta (= grad_beta*old + local sums) and coef [3][Cp] of dy = A*g + B*y + C from the global sums */
 int dv_bn_bwd_finalize(const double* sums_local, const double* sums_global, const float* gamma,
                        const float* saved, float* dgamma, float* dbeta, float* coef, int C, int Cp,
                        double count_global, float grad_beta, void* stream);
 /* dy = A*g + B*y + C; g_out (optional) = g, the gradient flowing into the residual branch */
-int dv_bn_bwd_apply(const void* dout, const void* out, const void* y, const float* mask_ss, const float* coef,
-                    void* dy, void* g_out, int64_t rows, int Cp, int o_ld, int o_coff, int relu, void* stream);
+int dv_bn_bwd_apply(const void* dout, const void* dout2, const void* out, const void* y, const float* mask_ss,
+                    const float* coef, void* dy, void* g_out, int64_t rows, int Cp, int o_ld, int o_coff, int relu,
+                    void* stream);
 /* out = a + b over n bf16 elements (n % 8 == 0): gradient accumulation where two consumers meet */
 int dv_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);
 
