@@ -163,28 +163,44 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BwdArgs a) {
     if (cg < G) {
       Vec8 fs, fb;
       if (a.ss) { fs = loadf8(a.ss + cg * 8); fb = loadf8(a.ss + a.Cp + cg * 8); }
-      for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < a.rows;
-           r += (long long)gridDim.x * blockDim.y) {
-        const long long ooff = r * a.o_ld + a.o_coff + cg * 8;
-        Vec8 d = load8(a.dout + ooff);
+      const long long stride = (long long)gridDim.x * blockDim.y;
+      auto masked = [&](Vec8 d, const Vec8& d2, const Vec8& yv, const Vec8& o) {
         if (a.dout2) {
-          const Vec8 d2 = load8(a.dout2 + r * a.Cp + cg * 8);
 #pragma unroll
           for (int i = 0; i < 8; ++i) d.v[i] += d2.v[i];
         }
-        const Vec8 yv = load8(a.y + r * a.Cp + cg * 8);
         if (a.relu) {
           if (a.ss) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) d.v[i] = fmaf(yv.v[i], fs.v[i], fb.v[i]) > 0.f ? d.v[i] : 0.f;
           } else {
-            const Vec8 o = load8(a.out + ooff);
 #pragma unroll
             for (int i = 0; i < 8; ++i) d.v[i] = o.v[i] > 0.f ? d.v[i] : 0.f;
           }
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) { sg[i] += d.v[i]; sgy[i] = fmaf(d.v[i], yv.v[i], sgy[i]); }
+      };
+      const bool need_out = a.relu && !a.ss;
+      long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y;
+      for (; r + stride < a.rows; r += 2 * stride) {   // two independent rows per iteration
+        const long long oa = r * a.o_ld + a.o_coff + cg * 8, ob = (r + stride) * a.o_ld + a.o_coff + cg * 8;
+        const long long ya = r * a.Cp + cg * 8, yb = (r + stride) * a.Cp + cg * 8;
+        const Vec8 d0 = load8(a.dout + oa), d1 = load8(a.dout + ob);
+        const Vec8 y0 = load8(a.y + ya), y1 = load8(a.y + yb);
+        Vec8 e0 = d0, e1 = d1, o0 = d0, o1 = d1;
+        if (a.dout2) { e0 = load8(a.dout2 + ya); e1 = load8(a.dout2 + yb); }
+        if (need_out) { o0 = load8(a.out + oa); o1 = load8(a.out + ob); }
+        masked(d0, e0, y0, o0);
+        masked(d1, e1, y1, o1);
+      }
+      if (r < a.rows) {
+        const long long oa = r * a.o_ld + a.o_coff + cg * 8, ya = r * a.Cp + cg * 8;
+        const Vec8 d0 = load8(a.dout + oa), y0 = load8(a.y + ya);
+        Vec8 e0 = d0, o0 = d0;
+        if (a.dout2) e0 = load8(a.dout2 + ya);
+        if (need_out) o0 = load8(a.out + oa);
+        masked(d0, e0, y0, o0);
       }
     }
     float* mine = red + (size_t)threadIdx.y * 16 * GT;
@@ -242,32 +258,48 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdArgs a) {
                C = loadf8(a.coef + 2 * a.Cp + cg * 8);
     Vec8 fs, fb;
     if (a.ss) { fs = loadf8(a.ss + cg * 8); fb = loadf8(a.ss + a.Cp + cg * 8); }
-    for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < a.rows;
-         r += (long long)gridDim.x * blockDim.y) {
-      const long long ooff = r * a.o_ld + a.o_coff + cg * 8;
-      Vec8 d = load8(a.dout + ooff);
+    const long long stride = (long long)gridDim.x * blockDim.y;
+    const bool need_out = a.relu && !a.ss;
+    auto finish = [&](long long r, Vec8 d, const Vec8& d2, const Vec8& yv, const Vec8& o) {
       const long long off = r * a.Cp + cg * 8;
       if (a.dout2) {
-        const Vec8 d2 = load8(a.dout2 + off);
 #pragma unroll
         for (int i = 0; i < 8; ++i) d.v[i] += d2.v[i];
       }
-      const Vec8 yv = load8(a.y + off);
       if (a.relu) {
         if (a.ss) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) d.v[i] = fmaf(yv.v[i], fs.v[i], fb.v[i]) > 0.f ? d.v[i] : 0.f;
         } else {
-          const Vec8 o = load8(a.out + ooff);
 #pragma unroll
           for (int i = 0; i < 8; ++i) d.v[i] = o.v[i] > 0.f ? d.v[i] : 0.f;
         }
       }
       if (a.g_out) store8(a.g_out + off, d);
-      Vec8 o;
+      Vec8 res;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o.v[i] = fmaf(A.v[i], d.v[i], fmaf(B.v[i], yv.v[i], C.v[i]));
-      store8(a.dy + off, o);
+      for (int i = 0; i < 8; ++i) res.v[i] = fmaf(A.v[i], d.v[i], fmaf(B.v[i], yv.v[i], C.v[i]));
+      store8(a.dy + off, res);
+    };
+    long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y;
+    for (; r + stride < a.rows; r += 2 * stride) {   // two independent rows per iteration
+      const long long oa = r * a.o_ld + a.o_coff + cg * 8, ob = (r + stride) * a.o_ld + a.o_coff + cg * 8;
+      const long long ya = r * a.Cp + cg * 8, yb = (r + stride) * a.Cp + cg * 8;
+      const Vec8 d0 = load8(a.dout + oa), d1 = load8(a.dout + ob);
+      const Vec8 y0 = load8(a.y + ya), y1 = load8(a.y + yb);
+      Vec8 e0 = d0, e1 = d1, o0 = d0, o1 = d1;
+      if (a.dout2) { e0 = load8(a.dout2 + ya); e1 = load8(a.dout2 + yb); }
+      if (need_out) { o0 = load8(a.out + oa); o1 = load8(a.out + ob); }
+      finish(r, d0, e0, y0, o0);
+      finish(r + stride, d1, e1, y1, o1);
+    }
+    if (r < a.rows) {
+      const long long oa = r * a.o_ld + a.o_coff + cg * 8, ya = r * a.Cp + cg * 8;
+      const Vec8 d0 = load8(a.dout + oa), y0 = load8(a.y + ya);
+      Vec8 e0 = d0, o0 = d0;
+      if (a.dout2) e0 = load8(a.dout2 + ya);
+      if (need_out) o0 = load8(a.out + oa);
+      finish(r, d0, e0, y0, o0);
     }
   }
 }
