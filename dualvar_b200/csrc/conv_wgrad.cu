@@ -14,6 +14,8 @@
 #include "host_common.h"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 namespace dv {
 
 constexpr int kWgThreads = 192;
@@ -35,6 +37,14 @@ struct alignas(64) WgradParams {
   int stages;
   float* dw;  // [Cout_p][taps_total][Cin_p]
   int cin_p, cout_p, taps_total;
+  // halo mode (temporal-only filters, stride 1): ONE X box with a t-halo per 64-channel chunk; the unit
+  // (tap, chunk) is the view of that box shifted by whole 8-row groups. All units live in one CTA.
+  int halo;
+  int x_box_bytes;         // bytes of one halo box (multiple of 1024)
+  int8_t x_dt, x_dh, x_dw; // origin offset of the halo box
+  int unit_off[16];        // start of each unit inside the stage, in 16-byte units
+  int16_t unit_widx[16];   // weight tap index of each unit
+  int16_t unit_kc[16];     // 64-channel chunk of each unit
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -61,7 +71,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
-  const int a_bytes = p.units_per_group * kBoxBytes;
+  const int a_bytes = p.halo ? p.k_chunks * p.x_box_bytes : p.units_per_group * kBoxBytes;
   const int b_bytes = ((p.block_n + 63) >> 6) * kBoxBytes;
   const int stage_bytes = a_bytes + b_bytes;
 
@@ -88,7 +98,8 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
     const bool issuer = elect_one();
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t tx = (nu + nbx) * kBoxBytes;
+    const uint32_t tx = p.halo ? (uint32_t)(p.k_chunks * p.x_box_bytes + nbx * kBoxBytes)
+                               : (uint32_t)((nu + nbx) * kBoxBytes);
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       int m_id = tile;
       const int wb = m_id % g.tiles_w; m_id /= g.tiles_w;
@@ -103,13 +114,19 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
         uint8_t* b_s = a_s + a_bytes;
         for (int j = 0; j < nbx; ++j)
           tma_load_5d(b_s + j * kBoxBytes, &p.dy_map, &full_bar[stage], n_tile * p.block_n + j * 64, w0, h0, t0, n0);
-        for (int i = 0; i < nu; ++i) {
-          const int u = unit0 + i;
-          const int tap = u / p.k_chunks;
-          const int kc = u - tap * p.k_chunks;
-          const Tap tp = p.taps[tap];
-          tma_load_5d(a_s + i * kBoxBytes, &p.a_map[tp.map], &full_bar[stage], kc * 64, w0 + tp.dw, h0 + tp.dh,
-                      t0 + tp.dt, n0);
+        if (p.halo) {
+          for (int kc = 0; kc < p.k_chunks; ++kc)
+            tma_load_5d(a_s + kc * p.x_box_bytes, &p.a_map[0], &full_bar[stage], kc * 64, w0 + p.x_dw, h0 + p.x_dh,
+                        t0 + p.x_dt, n0);
+        } else {
+          for (int i = 0; i < nu; ++i) {
+            const int u = unit0 + i;
+            const int tap = u / p.k_chunks;
+            const int kc = u - tap * p.k_chunks;
+            const Tap tp = p.taps[tap];
+            tma_load_5d(a_s + i * kBoxBytes, &p.a_map[tp.map], &full_bar[stage], kc * 64, w0 + tp.dw, h0 + tp.dh,
+                        t0 + tp.dt, n0);
+          }
         }
       }
       __syncwarp();
@@ -134,7 +151,16 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
       const uint32_t b_lo = a_lo + a_enc;
       if (issuer) {
         for (int pr = 0; pr < npairs; ++pr) {
-          const uint32_t al = a_lo + (uint32_t)pr * (2 * kBoxBytes >> 4);
+          uint32_t al;
+          if (p.halo) {
+            // unit = shifted view of a halo box; the pair's second 64-channel group starts (LBO) wherever the
+            // next unit starts (possibly overlapping the first)
+            const uint32_t o0 = (uint32_t)p.unit_off[2 * pr];
+            const uint32_t o1 = (2 * pr + 1 < nu) ? (uint32_t)p.unit_off[2 * pr + 1] : o0 + 64u;
+            al = ((o1 - o0) << 16) | (base_enc + (uint32_t)stage * stage_enc + o0);
+          } else {
+            al = a_lo + (uint32_t)pr * (2 * kBoxBytes >> 4);
+          }
           const uint32_t dt = tmem_base + pr * p.acc_stride;
           // one UMMA K step = 16 positions = 2048 B = +128 in (addr >> 4) units
           umma_bf16_lohi(dt, al, b_lo, desc_hi, idesc, accumulate);
@@ -161,10 +187,16 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
       const bool unit_ok = i < nu;
       int tapw = 0, ci = 0;
       if (unit_ok) {
-        const int u = unit0 + i;
-        const int tap = u / p.k_chunks;
-        const int kc = u - tap * p.k_chunks;
-        tapw = p.taps[tap].widx;
+        int kc;
+        if (p.halo) {
+          tapw = p.unit_widx[i];
+          kc = p.unit_kc[i];
+        } else {
+          const int u = unit0 + i;
+          const int tap = u / p.k_chunks;
+          kc = u - tap * p.k_chunks;
+          tapw = p.taps[tap].widx;
+        }
         ci = kc * 64 + (row & 63);
       }
       const bool row_ok = unit_ok && ci < p.cin_p;
@@ -227,13 +259,19 @@ static int wgrad_launch(WgradParams& P, int ntaps, int cin_p, int cout_p, int ta
   const int nbx = ceil_div(P.block_n, 64);
   int max_pairs = 512 / P.acc_stride;
   int upg = max_pairs * 2;
-  if (upg > kWgMaxUnits) upg = kWgMaxUnits;
-  // keep at least 3 stages in shared memory
-  while (upg > 2 && (kWgSmemBudget - 1024) / ((upg + nbx) * kBoxBytes) < 3) upg -= 2;
-  if (upg > P.total_units) upg = P.total_units;
+  int stage_bytes;
+  if (P.halo) {
+    upg = P.total_units;   // caller checked that all units fit one CTA
+    stage_bytes = P.k_chunks * P.x_box_bytes + nbx * kBoxBytes;
+  } else {
+    if (upg > kWgMaxUnits) upg = kWgMaxUnits;
+    // keep at least 3 stages in shared memory
+    while (upg > 2 && (kWgSmemBudget - 1024) / ((upg + nbx) * kBoxBytes) < 3) upg -= 2;
+    if (upg > P.total_units) upg = P.total_units;
+    stage_bytes = (upg + nbx) * kBoxBytes;
+  }
   P.units_per_group = upg;
   const int groups = ceil_div(P.total_units, upg);
-  const int stage_bytes = (upg + nbx) * kBoxBytes;
   P.stages = (kWgSmemBudget - 1024) / stage_bytes;
   if (P.stages > 8) P.stages = 8;
   if (P.stages < 2) return fail(kUnsupported, "wgrad: stage too large for shared memory");
@@ -265,6 +303,68 @@ int conv_wgrad_bf16(const void* x, const void* dy, float* dw, const ConvGeom& c,
   static thread_local WgradParams P;
   const int taps_total = c.kt * c.kh * c.kw;
   DV_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)c.Cout_p * taps_total * c.Cin_p, stream));
+  P.halo = 0;
+  {
+    static int halo_env = -1;
+    if (halo_env < 0) { const char* e = getenv("DV_CONV_HALO"); halo_env = e ? atoi(e) : 1; }
+    const int k_chunks = ceil_div(c.Cin_p, 64);
+    const int units = c.kt * k_chunks;
+    const int bn = c.Cout_p <= 256 ? round_up(c.Cout_p, 16) : 256;
+    const int acc_stride = round_up(bn, 32);
+    if (halo_env && c.kt > 1 && c.kh == 1 && c.kw == 1 && c.st == 1 && c.sh == 1 && c.sw == 1 && c.Cout_p <= 256 &&
+        units <= 16 && ceil_div(units, 2) * acc_stride <= 512) {
+      // tile (tn=1, tt, th, tw) of 64 positions with th*tw a multiple of 8 rows; minimise padded volume x halo
+      TileGeom& g = P.g;
+      double best = 1e30; int blw = 3, blh = 0, blt = 3;
+      for (int a = 0; a <= 6; ++a)
+        for (int b = 0; a + b <= 6; ++b) {
+          if (a + b < 3) continue;
+          const int cc = 6 - a - b;
+          const int tw = 1 << a, th = 1 << b, tt = 1 << cc;
+          const double vol = (double)round_up(c.Wo, tw) * round_up(c.Ho, th) * round_up(c.To, tt);
+          const double cost = vol * (double)(tt + c.kt - 1) / tt * (1.0 + 0.02 * (6 - a));
+          if (cost < best) { best = cost; blw = a; blh = b; blt = cc; }
+        }
+      g.lw = blw; g.lh = blh; g.lt = blt; g.ln = 0;
+      const int tt = 1 << g.lt, thw = (1 << g.lh) * (1 << g.lw);
+      const int x_box_bytes = (tt + c.kt - 1) * thw * 128;
+      const int nbx = ceil_div(bn, 64);
+      if (3 * (k_chunks * x_box_bytes + nbx * kBoxBytes) <= kWgSmemBudget - 1024) {
+        P.halo = 1;
+        P.x_box_bytes = x_box_bytes;
+        P.x_dt = (int8_t)(-c.pt); P.x_dh = 0; P.x_dw = 0;
+        g.ext_w = c.Wo; g.ext_h = c.Ho; g.ext_t = c.To; g.ext_n = c.N;
+        g.tiles_w = ceil_div(c.Wo, 1 << g.lw);
+        g.tiles_h = ceil_div(c.Ho, 1 << g.lh);
+        g.tiles_t = ceil_div(c.To, tt);
+        g.tiles_n = c.N;
+        const uint32_t ybox[5] = {64, 1u << g.lw, 1u << g.lh, (uint32_t)tt, 1};
+        const uint32_t xbox[5] = {64, 1u << g.lw, 1u << g.lh, (uint32_t)(tt + c.kt - 1), 1};
+        uint64_t ydims[5] = {(uint64_t)c.Cout_p, (uint64_t)c.Wo, (uint64_t)c.Ho, (uint64_t)c.To, (uint64_t)c.N};
+        uint64_t ystr[5] = {2, (uint64_t)c.Cout_p * 2, (uint64_t)c.Wo * c.Cout_p * 2,
+                            (uint64_t)c.Ho * c.Wo * c.Cout_p * 2, (uint64_t)c.To * c.Ho * c.Wo * c.Cout_p * 2};
+        int rc = encode_tmap(&P.dy_map, dy, 2, 5, ydims, ystr, ybox, true);
+        if (rc) return rc;
+        uint64_t xdims[5] = {(uint64_t)c.Cin_p, (uint64_t)c.W, (uint64_t)c.H, (uint64_t)c.T, (uint64_t)c.N};
+        uint64_t xstrd[5] = {2, (uint64_t)c.Cin_p * 2, (uint64_t)c.W * c.Cin_p * 2,
+                             (uint64_t)c.H * c.W * c.Cin_p * 2, (uint64_t)c.T * c.H * c.W * c.Cin_p * 2};
+        rc = encode_tmap(&P.a_map[0], x, 2, 5, xdims, xstrd, xbox, true);
+        if (rc) return rc;
+        for (int i = 1; i < kMaxAMaps; ++i) P.a_map[i] = P.a_map[0];
+        // units ordered by (chunk, tap): start addresses increase, so a pair's LBO is positive
+        int u = 0;
+        for (int kc = 0; kc < k_chunks; ++kc)
+          for (int a = 0; a < c.kt; ++a, ++u) {
+            P.unit_off[u] = (kc * x_box_bytes + a * thw * 128) >> 4;
+            P.unit_widx[u] = (int16_t)a;
+            P.unit_kc[u] = (int16_t)kc;
+          }
+        for (int a = 0; a < c.kt; ++a) { P.taps[a].map = 0; P.taps[a].dt = (int8_t)(a - c.pt); P.taps[a].dh = 0;
+                                         P.taps[a].dw = 0; P.taps[a].widx = (int16_t)a; P.taps[a].shift_rows = 0; }
+        return wgrad_launch(P, c.kt, c.Cin_p, c.Cout_p, taps_total, dw, stream);
+      }
+    }
+  }
 
   TileGeom& g = P.g;
   choose_tile_log2(6, c.N, c.To, c.Ho, c.Wo, &g.ln, &g.lt, &g.lh, &g.lw);
