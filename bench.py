@@ -219,7 +219,8 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     launches0 = _lib.load().dv_launch_count()
-    timer = _lib.KernelTimer(["dv_conv3d_fprop_bf16", "dv_conv3d_dgrad_bf16", "dv_conv3d_wgrad_bf16"])
+    timer = _lib.KernelTimer(["dv_conv3d_fprop_bf16", "dv_conv3d_dgrad_bf16", "dv_conv3d_wgrad_bf16",
+                              "dv_conv3d_stem_fprop_bf16", "dv_conv3d_stem_wgrad_bf16"])
     _lib.set_timer(timer)
     ms_step = timed(args.steps, False, 0)
     _lib.set_timer(None)
@@ -240,22 +241,38 @@ def run_ours(args):
         value = B * world / (ms_step / 1e3)
         e2e_value = B * world / (ms_e2e / 1e3)
         conv_ms = sum(d["ms"] for d in ksum.values())
-        kernels = {}
+        calls = {}
         for name, d in ksum.items():
-            kernels[name] = {"calls_per_step": d["calls"] / args.steps, "ms_per_step": d["ms"] / args.steps,
-                             "tflops": d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0}
-        top = max(ksum, key=lambda n: ksum[n]["ms"]) if ksum else None
+            calls[name] = {"calls_per_step": d["calls"] / args.steps, "ms_per_step": d["ms"] / args.steps,
+                           "tflops": d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0}
+        # group the C-ABI calls by the CUDA kernel that serves them
+        groups = {"conv_tile_kernel": ["dv_conv3d_fprop_bf16", "dv_conv3d_dgrad_bf16", "dv_conv3d_stem_fprop_bf16"],
+                  "conv_wgrad_kernel": ["dv_conv3d_wgrad_bf16", "dv_conv3d_stem_wgrad_bf16"]}
+        kern = {}
+        for kname, members in groups.items():
+            ms = sum(ksum[m]["ms"] for m in members if m in ksum)
+            fl = sum(ksum[m]["flops"] for m in members if m in ksum)
+            n = sum(ksum[m]["calls"] for m in members if m in ksum)
+            if ms > 0:
+                kern[kname] = {"ms_per_step": ms / args.steps, "calls_per_step": n / args.steps,
+                               "tflops": fl / (ms * 1e-3) / 1e12, "avg_launch_us": ms / n * 1e3,
+                               "gflop_per_launch": fl / n / 1e9}
+        top = max(kern, key=lambda k: kern[k]["ms_per_step"]) if kern else None
         roof = None
         if top:
-            ach = kernels[top]["tflops"]
-            roof = {"bound": "tensor", "kernel": {"dv_conv3d_fprop_bf16": "conv_tile_kernel (fprop)",
-                                                  "dv_conv3d_dgrad_bf16": "conv_tile_kernel (dgrad)",
-                                                  "dv_conv3d_wgrad_bf16": "conv_wgrad_kernel"}[top],
-                    "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
-                    "share_of_step": ksum[top]["ms"] / args.steps / ms_step,
-                    "all_conv_kernels": kernels, "conv_share_of_step": conv_ms / args.steps / ms_step,
-                    "whole_step_tflops": GFLOP_PER_SAMPLE * B / ms_step}
+            ach = kern[top]["tflops"]
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+            if os.path.exists(tpath):
+                traffic = json.load(open(tpath)).get(top)
+            roof = {"bound": "tensor", "kernel": top, "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": ach / peaks["bf16_tflops"], "traffic": traffic, "peak_source": peaks["source"],
+                    "share_of_step": kern[top]["ms_per_step"] / ms_step, "kernels": kern, "calls": calls,
+                    "conv_share_of_step": conv_ms / args.steps / ms_step,
+                    "whole_step_tflops": GFLOP_PER_SAMPLE * B / ms_step,
+                    "note": "achieved = algorithmic conv FLOPs (2*positions*Cout*Cin*taps, logical channels) of all "
+                            "launches of the kernel in the timed steps / their summed CUDA-event time; traffic = "
+                            "avg DRAM bytes per launch from ncu (profiles/), null if no capture"}
         line = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
