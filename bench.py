@@ -158,7 +158,8 @@ def run_ours(args):
     net = model
     if world > 1:
         model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank])   # pretrain.py:248
-    opt = torch.optim.SGD(net.parameters(), lr=0.003, weight_decay=1e-4, momentum=0.9)
+    from dualvar_b200.optim import SGD
+    opt = SGD([{"params": p} for p in net.parameters()], lr=0.003, weight_decay=1e-4, momentum=0.9)   # pretrain.py:262-272
     # synthetic decoded+augmented batch as the loader yields it: (B, 3, 3*16, 112, 112) in [0,1], pinned host
     gen = torch.Generator().manual_seed(1234 + rank)
     host = [torch.rand(B, 3, 48, 112, 112, generator=gen).pin_memory() for _ in range(2)]

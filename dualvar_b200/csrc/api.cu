@@ -72,6 +72,8 @@ int rowdot(const float* a, const float* b, float* out, int rows, int d, int ld_o
 int row_axpy(const float* alpha, int ld_alpha, const float* x, float* y, int rows, int d, float beta,
              cudaStream_t stream);
 int probe_overlap(const void* src, void* out, int c1, cudaStream_t stream);
+int sgd_momentum_step(const long long* table, int n_chunks, float lr, float mu, float wd, int first,
+                      cudaStream_t stream);
 void set_conv_profile(long long* p);
 int retrieval_prepare(const float* x, double* mean, double* y, int n, int d, cudaStream_t st);
 int retrieval_sim_topk(const double* test, const double* train, double* sim, float* sim32, long long* idx,
@@ -385,6 +387,13 @@ int dv_retrieval_sim_topk(const double* test, const double* train, double* sim, 
   DV_REQUIRE(test && train && sim && idx && n_test > 0 && n_train > 0 && d > 0 && k > 0 && k <= n_train,
              "bad retrieval_sim_topk arguments");
   return retrieval_sim_topk(test, train, sim, sim32, reinterpret_cast<long long*>(idx), n_test, n_train, d, k, ST);
+}
+
+int dv_sgd_momentum_step(const int64_t* chunk_table, int n_chunks, float lr, float momentum, float weight_decay,
+                         int first_step, void* stream) {
+  DV_REQUIRE(chunk_table && n_chunks >= 0 && lr >= 0.f, "bad sgd_momentum_step arguments");
+  return sgd_momentum_step(reinterpret_cast<const long long*>(chunk_table), n_chunks, lr, momentum, weight_decay,
+                           first_step, ST);
 }
 
 int dv_debug_set_conv_profile(int64_t* buf) {

@@ -64,3 +64,48 @@ int enqueue(const float* keys, float* queue, int B, int d, int K, int ptr, cudaS
 }
 
 }  // namespace dv
+
+// ---------------------------------------------------------------------------------------------------
+// SGD with momentum and weight decay over ALL parameter tensors in one launch (reference: optim.SGD
+// with one param-group per tensor, pretrain.py:262-272 — hundreds of tiny foreach launches).
+// torch semantics (dampening 0, no nesterov): g = grad + wd*p ; buf = first ? g : mu*buf + g ; p -= lr*buf
+// table: [n_chunks][4] int64 = (p pointer, grad pointer, momentum-buffer pointer, element count <= 8192)
+namespace dv {
+
+__global__ void __launch_bounds__(256)
+sgd_momentum_kernel(const long long* __restrict__ table, float lr, float mu, float wd, int first) {
+  const long long* e = table + (long long)blockIdx.x * 4;
+  float* p = reinterpret_cast<float*>(e[0]);
+  const float* g = reinterpret_cast<const float*>(e[1]);
+  float* b = reinterpret_cast<float*>(e[2]);
+  const int n = (int)e[3];
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+  const int n4 = vec ? (n >> 2) : 0;
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    const float4 gv = reinterpret_cast<const float4*>(g)[i];
+    float4 bv = first ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<float4*>(b)[i];
+    const float gx = fmaf(wd, pv.x, gv.x), gy = fmaf(wd, pv.y, gv.y), gz = fmaf(wd, pv.z, gv.z), gw = fmaf(wd, pv.w, gv.w);
+    bv.x = first ? gx : fmaf(mu, bv.x, gx); bv.y = first ? gy : fmaf(mu, bv.y, gy);
+    bv.z = first ? gz : fmaf(mu, bv.z, gz); bv.w = first ? gw : fmaf(mu, bv.w, gw);
+    pv.x -= lr * bv.x; pv.y -= lr * bv.y; pv.z -= lr * bv.z; pv.w -= lr * bv.w;
+    reinterpret_cast<float4*>(b)[i] = bv;
+    reinterpret_cast<float4*>(p)[i] = pv;
+  }
+  for (int i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
+    const float gg = fmaf(wd, p[i], g[i]);
+    const float bb = first ? gg : fmaf(mu, b[i], gg);
+    b[i] = bb;
+    p[i] -= lr * bb;
+  }
+}
+
+int sgd_momentum_step(const long long* table, int n_chunks, float lr, float mu, float wd, int first,
+                      cudaStream_t stream) {
+  if (n_chunks <= 0) return kOk;
+  sgd_momentum_kernel<<<n_chunks, 256, 0, stream>>>(table, lr, mu, wd, first);
+  DV_LAUNCH_OK();
+  return kOk;
+}
+
+}  // namespace dv

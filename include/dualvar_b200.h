@@ -196,6 +196,13 @@ int dv_retrieval_prepare(const float* feat, double* mean, double* out, int n, in
 int dv_retrieval_sim_topk(const double* test, const double* train, double* sim, float* sim32, int64_t* idx,
                           int n_test, int n_train, int d, int k, void* stream);
 
+/* ---- optimizer ----------------------------------------------------------------
+ * optim.SGD(momentum, weight_decay) of pretrain.py:272 over every parameter tensor in one launch:
+ * g = grad + wd*p ; buf = first_step ? g : momentum*buf + g ; p -= lr*buf.
+ * chunk_table: device int64 [n_chunks][4] = (param ptr, grad ptr, momentum-buffer ptr, count <= 8192). */
+int dv_sgd_momentum_step(const int64_t* chunk_table, int n_chunks, float lr, float momentum, float weight_decay,
+                         int first_step, void* stream);
+
 /* debug (tests/diag only): per-CTA role cycle counters of the next conv_tile_kernel launches are written to
  * buf [148][8] (producer total/wait, MMA total/wait-data/wait-accumulator, epilogue total/wait, tiles); NULL = off */
 int dv_debug_set_conv_profile(int64_t* buf);

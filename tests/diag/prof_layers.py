@@ -12,7 +12,8 @@ dev = "cuda:0"
 torch.manual_seed(0); np.random.seed(0); random.seed(0)
 model = PM.SimCLR_TimeSeriesV4(net_name, 128, 0.07, False, True, 2, 64, 0.07, 0.07, "clip-sr-tc",
                                SimpleNamespace(shufflerank_theta=0.05)).to(dev).train()
-opt = torch.optim.SGD(model.parameters(), lr=0.003, weight_decay=1e-4, momentum=0.9)
+from dualvar_b200.optim import SGD
+opt = SGD([{'params': p} for p in model.parameters()], lr=0.003, weight_decay=1e-4, momentum=0.9)
 frames = torch.rand(B, 3, 48, 112, 112, device=dev)
 
 def step():

@@ -208,3 +208,26 @@ def test_maxpool_forward_backward_matches_torch():
         out.grad = K.to_ndhwc(gy)
         E.run_backward(ctx)
         assert _rel2(K.from_ndhwc(xa.grad, 24), xr.grad) < 1e-2
+
+
+def test_fused_sgd_matches_torch_sgd():
+    """dualvar_b200.optim.SGD (one launch for all tensors) vs torch.optim.SGD, three steps with an lr change."""
+    from dualvar_b200.optim import SGD
+    torch.manual_seed(0)
+    shapes = [(83, 3, 1, 7, 7), (64,), (144, 64, 1, 3, 3), (10001,), (7,)]
+    ps = [torch.randn(s, device=dev).requires_grad_(True) for s in shapes]
+    qs = [p.detach().clone().requires_grad_(True) for p in ps]
+    ours = SGD([{"params": p} for p in ps], lr=0.003, momentum=0.9, weight_decay=1e-4)     # pretrain.py:262-272
+    ref = torch.optim.SGD([{"params": q} for q in qs], lr=0.003, momentum=0.9, weight_decay=1e-4)
+    for step in range(3):
+        for p, q in zip(ps, qs):
+            g = torch.randn_like(p)
+            p.grad, q.grad = g.clone(), g.clone()
+        if step == 2:
+            for grp in ours.param_groups + ref.param_groups:
+                grp["lr"] = 0.0003
+        ours.step(); ref.step()
+        for p, q in zip(ps, qs):
+            torch.testing.assert_close(p, q, rtol=1e-6, atol=1e-7)
+    for p, q in zip(ps, qs):
+        torch.testing.assert_close(ours.state[p]["momentum_buffer"], ref.state[q]["momentum_buffer"], rtol=1e-6, atol=1e-7)
