@@ -220,7 +220,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     launches0 = _lib.load().dv_launch_count()
-    timer = _lib.KernelTimer(["dv_conv3d_fprop_bf16", "dv_conv3d_dgrad_bf16", "dv_conv3d_wgrad_bf16",
+    timer = _lib.KernelTimer(["dv_conv3d_fprop_bf16", "dv_conv3d_dgrad_bf16", "dv_conv3d_dgrad_bnred_bf16", "dv_conv3d_wgrad_bf16",
                               "dv_conv3d_stem_fprop_bf16", "dv_conv3d_stem_wgrad_bf16"])
     _lib.set_timer(timer)
     ms_step = timed(args.steps, False, 0)
@@ -247,7 +247,8 @@ def run_ours(args):
             calls[name] = {"calls_per_step": d["calls"] / args.steps, "ms_per_step": d["ms"] / args.steps,
                            "tflops": d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0}
         # group the C-ABI calls by the CUDA kernel that serves them
-        groups = {"conv_tile_kernel": ["dv_conv3d_fprop_bf16", "dv_conv3d_dgrad_bf16", "dv_conv3d_stem_fprop_bf16"],
+        groups = {"conv_tile_kernel": ["dv_conv3d_fprop_bf16", "dv_conv3d_dgrad_bf16", "dv_conv3d_dgrad_bnred_bf16",
+                                       "dv_conv3d_stem_fprop_bf16"],
                   "conv_wgrad_kernel": ["dv_conv3d_wgrad_bf16", "dv_conv3d_stem_wgrad_bf16"]}
         kern = {}
         for kname, members in groups.items():

@@ -11,7 +11,7 @@ const std::string& last_error_ref();
 int conv_fprop_bf16(const void* x, const void* w_packed, void* y, double* stats, const float* bias,
                     const ConvGeom& c, cudaStream_t stream);
 int conv_dgrad_bf16(const void* dy, const void* w_packed_t, void* dx, const ConvGeom& c,
-                    cudaStream_t stream);
+                    cudaStream_t stream, const BnReduce* red);
 int conv_wgrad_bf16(const void* x, const void* dy, float* dw, const ConvGeom& c, cudaStream_t stream);
 int pack_weights(const float* w, void* wf, void* wt, int Cout, int Cin, int taps, int Cout_p,
                  int Cin_p, cudaStream_t stream);
@@ -72,6 +72,7 @@ int rowdot(const float* a, const float* b, float* out, int rows, int d, int ld_o
 int row_axpy(const float* alpha, int ld_alpha, const float* x, float* y, int rows, int d, float beta,
              cudaStream_t stream);
 int probe_overlap(const void* src, void* out, int c1, cudaStream_t stream);
+int mma_rate(int n, int n_mma, int region, int mode, long long* out, int grid, cudaStream_t stream);
 int sgd_momentum_step(const long long* table, int n_chunks, float lr, float mu, float wd, int first,
                       cudaStream_t stream);
 void set_conv_profile(long long* p);
@@ -168,7 +169,15 @@ int dv_conv3d_dgrad_bf16(const void* dy, const void* wt, void* dx, const dv_conv
                          void* stream) {
   if (int rc = check_geom(g)) return rc;
   DV_REQUIRE(dy && wt && dx, "NULL tensor pointer");
-  return conv_dgrad_bf16(dy, wt, dx, to_geom<ConvGeom>(g), (cudaStream_t)stream);
+  return conv_dgrad_bf16(dy, wt, dx, to_geom<ConvGeom>(g), (cudaStream_t)stream, nullptr);
+}
+
+int dv_conv3d_dgrad_bnred_bf16(const void* dy, const void* wt, void* dx, const dv_conv_geom* g,
+                               const void* y_prev, const float* ss_prev, double* sums, void* stream) {
+  if (int rc = check_geom(g)) return rc;
+  DV_REQUIRE(dy && wt && dx && y_prev && sums, "NULL tensor pointer");
+  const BnReduce red = {y_prev, ss_prev, sums};
+  return conv_dgrad_bf16(dy, wt, dx, to_geom<ConvGeom>(g), (cudaStream_t)stream, &red);
 }
 
 int dv_conv3d_wgrad_bf16(const void* x, const void* dy, float* dw_packed, const dv_conv_geom* g,
@@ -403,6 +412,10 @@ int dv_debug_set_conv_profile(int64_t* buf) {
 
 int dv_debug_probe_overlap_tmap(const void* src, void* out, int c1, void* stream) {
   return probe_overlap(src, out, c1, ST);
+}
+
+int dv_debug_mma_rate(int n, int n_mma, int region_bytes, int mode, int64_t* cycles, int grid, void* stream) {
+  return mma_rate(n, n_mma, region_bytes, mode, reinterpret_cast<long long*>(cycles), grid, ST);
 }
 
 }  // extern "C"

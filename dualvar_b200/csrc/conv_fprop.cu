@@ -232,6 +232,7 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
     const int nchunks = (bn_mma + 63) >> 6;
     const int bcol = n_tile * p.block_n;
     const bool do_stats = p.stats != nullptr;
+    const bool red = do_stats && p.red_y != nullptr;
     int it = 0;
     uint32_t obuf = 0;
     long long prof_epi_wait = 0;
@@ -256,6 +257,44 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
         const int ncols = min(64, bn_mma - cc * 64);
         uint8_t* ob = o_smem + obuf * kOutBufBytes;
         obuf = (obuf == kOutBufs - 1) ? 0 : obuf + 1;
+        // fused BN-backward reduce: this thread's 32 (row, channel pair) words of y for the column pass
+        // below are requested now, so their latency hides behind the TMEM load / convert / store phase.
+        // Row bit k of the tile adds red_bitoff[k] elements (tile dims are powers of two), so every row
+        // offset is a sum of kernel-parameter constants: no per-row index arithmetic.
+        uint32_t yv[32];
+        if (red) {
+          const int c = bcol + cc * 64 + (et & 31) * 2;
+          const bool col_ok = ((et & 31) * 2 < ncols) && (c < p.stats_ld);
+          const int rq = et >> 5;
+          const __nv_bfloat16* ybase =
+              reinterpret_cast<const __nv_bfloat16*>(p.red_y) + c + w0 * p.red_stride[0] + h0 * p.red_stride[1] +
+              t0 * p.red_stride[2] + n0 * p.red_stride[3] + ((rq & 1) ? p.red_bitoff[5] : 0) +
+              ((rq & 2) ? p.red_bitoff[6] : 0);
+          // rows of this quarter that fall outside the tensor (partial tiles): per-dimension limits on the
+          // row's bit fields
+          const int lim_w = g.ext_w - w0, lim_h = g.ext_h - h0, lim_t = g.ext_t - t0, lim_n = g.ext_n - n0;
+          const bool full = lim_w >= (1 << g.lw) && lim_h >= (1 << g.lh) && lim_t >= (1 << g.lt) &&
+                            lim_n >= (1 << g.ln);
+          auto row_off = [&](int i) {
+            return ((i & 1) ? p.red_bitoff[0] : 0) + ((i & 2) ? p.red_bitoff[1] : 0) +
+                   ((i & 4) ? p.red_bitoff[2] : 0) + ((i & 8) ? p.red_bitoff[3] : 0) +
+                   ((i & 16) ? p.red_bitoff[4] : 0);
+          };
+          if (full) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) yv[i] = ldg_u32_pred(ybase + row_off(i), col_ok);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int r = rq * 32 + i;
+              const int ok = (int)col_ok & (int)((r & ((1 << g.lw) - 1)) < lim_w) &
+                             (int)(((r >> g.lw) & ((1 << g.lh) - 1)) < lim_h) &
+                             (int)(((r >> (g.lw + g.lh)) & ((1 << g.lt) - 1)) < lim_t) &
+                             (int)((r >> (g.lw + g.lh + g.lt)) < lim_n);
+              yv[i] = ldg_u32_pred(ybase + row_off(i), ok != 0);
+            }
+          }
+        }
         // all TMEM loads of the chunk in flight together, one wait
         uint32_t v[64];
         tmem_ld16(t_addr + cc * 64, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
@@ -301,7 +340,38 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
           // the buffer written two chunks ago has been read before anybody overwrites it (3 buffers)
           tma_store_wait_read<1>();
         }
-        if (do_stats) {
+        if (red) {
+          // column sums of g = dz * relu_mask(y) and g * y over the stored bf16 dz tile (same thread ->
+          // (channel pair, row quarter) ownership as the forward statistics below)
+          const int word = et & 31;
+          const int rq = et >> 5;
+          const int c = bcol + cc * 64 + word * 2;
+          if (word * 2 < ncols && c < p.stats_ld) {
+            float sc0 = 0.f, sc1 = 0.f, sh0 = 1.f, sh1 = 1.f;   // no ReLU: mask always true
+            if (p.red_ss != nullptr) {
+              sc0 = p.red_ss[c]; sc1 = p.red_ss[c + 1];
+              sh0 = p.red_ss[p.stats_ld + c]; sh1 = p.red_ss[p.stats_ld + c + 1];
+            }
+            float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int r = rq * 32 + i;
+              const uint32_t off = r * 128 + ((((word >> 2) ^ (r & 7))) << 4) + ((word & 3) << 2);
+              const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ob + off));
+              const float2 yy = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yv[i]));
+              const float g0 = fmaf(yy.x, sc0, sh0) > 0.f ? d.x : 0.f;
+              const float g1 = fmaf(yy.y, sc1, sh1) > 0.f ? d.y : 0.f;
+              a0 += g0; a1 += g1;
+              b0 = fmaf(g0, yy.x, b0); b1 = fmaf(g1, yy.y, b1);
+            }
+            const int lc = cc * 64 + word * 2;
+            float2* ps = reinterpret_cast<float2*>(&s_part[rq][0][lc]);
+            float2* pq = reinterpret_cast<float2*>(&s_part[rq][1][lc]);
+            float2 s2 = *ps, q2 = *pq;
+            s2.x += a0; s2.y += a1; q2.x += b0; q2.y += b1;
+            *ps = s2; *pq = q2;
+          }
+        } else if (do_stats) {
           // column sums over the stored bf16 tile: thread -> (channel pair, row quarter); every
           // (row quarter, channel) partial is owned by exactly one thread -> no atomics
           const int word = et & 31;
@@ -461,7 +531,8 @@ static void read_env_once() {
 static int conv_multi_tap(ConvTileParams& P, MapEncoder enc, const void* enc_ctx, int n_views,
                           const std::vector<TapSpec>& taps_in, const View5& outv, int out_rows_p,
                           const void* w_packed, int w_rows_p, int w_taps, int kin_p, double* stats,
-                          const float* bias, cudaStream_t stream, bool allow_group = true) {
+                          const float* bias, cudaStream_t stream, bool allow_group = true,
+                          const BnReduce* red = nullptr) {
   read_env_once();
   if (taps_in.empty()) return fail(kBadArg, "convolution has no valid taps");
   if ((int)taps_in.size() > kMaxTaps) return fail(kUnsupported, "too many filter taps (%d)", (int)taps_in.size());
@@ -569,12 +640,25 @@ static int conv_multi_tap(ConvTileParams& P, MapEncoder enc, const void* enc_ctx
   if (P.stages > kMaxStages) P.stages = kMaxStages;
   if (P.stages < 3 && mode != kPlain)   // wide layers: a group's weight tiles do not fit -> one box per tap
     return conv_multi_tap(P, enc, enc_ctx, n_views, taps_in, outv, out_rows_p, w_packed, w_rows_p, w_taps, kin_p,
-                          stats, bias, stream, false);
+                          stats, bias, stream, false, red);
   if (P.stages < 2) return fail(kUnsupported, "conv tile: not enough shared memory for 2 stages");
   P.stats = stats;
   P.stats_ld = out_rows_p;
   P.bias = bias;
   P.prof = g_prof;
+  P.red_y = nullptr;
+  P.red_ss = nullptr;
+  if (red != nullptr) {
+    // red->y is already offset to the output view's origin (stride-parity class)
+    P.stats = red->sums;
+    P.red_y = red->y;
+    P.red_ss = red->ss;
+    for (int i = 0; i < 4; ++i) P.red_stride[i] = outv.stride[i + 1];
+    const int lg[4] = {g.lw, g.lh, g.lt, g.ln};
+    int k = 0;
+    for (int d = 0; d < 4; ++d)
+      for (int b = 0; b < lg[d]; ++b) P.red_bitoff[k++] = outv.stride[d + 1] << b;
+  }
 
   {  // weights: [rows][taps][kin_p] bf16, box (64, 1, block_n)
     uint64_t dims[3] = {(uint64_t)kin_p, (uint64_t)w_taps, (uint64_t)w_rows_p};
@@ -649,7 +733,7 @@ int conv_fprop_bf16(const void* x, const void* w_packed, void* y, double* stats,
 // stride-1 multi-tap GEMM over dY with the subset of taps that reach it.
 // w_packed_t: [Cin_p][taps][Cout_p] bf16 (transposed pack).
 int conv_dgrad_bf16(const void* dy, const void* w_packed_t, void* dx, const ConvGeom& c,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, const BnReduce* red) {
   static thread_local ConvTileParams P;
   ViewSet vs;
   vs.v[0] = make_ndhwc(dy, c.N, c.To, c.Ho, c.Wo, c.Cout_p);
@@ -687,8 +771,16 @@ int conv_dgrad_bf16(const void* dy, const void* w_packed_t, void* dx, const Conv
           }
         }
         if (taps.empty()) continue;  // class receives no gradient (zero-filled above)
+        BnReduce rv;
+        if (red != nullptr) {
+          // y has dx's layout: same parity-class origin and strides as the output view
+          rv = *red;
+          rv.y = static_cast<const uint8_t*>(red->y) +
+                 (static_cast<const uint8_t*>(ov.base) - static_cast<const uint8_t*>(dxv.base));
+        }
         int rc = conv_multi_tap(P, encode_from_viewset, &vs, 1, taps, ov, c.Cin_p, w_packed_t, c.Cin_p,
-                                c.kt * c.kh * c.kw, c.Cout_p, nullptr, nullptr, stream);
+                                c.kt * c.kh * c.kw, c.Cout_p, nullptr, nullptr, stream, true,
+                                red != nullptr ? &rv : nullptr);
         if (rc) return rc;
       }
   return kOk;

@@ -58,6 +58,20 @@ struct alignas(64) ConvTileParams {
   int stats_ld;
   const float* bias;  // nullable: per output channel, added before rounding
   long long* prof;    // nullable debug buffer: [grid][8] cycle counters per role (see conv_fprop.cu)
+  // BatchNorm-backward reduce fused into a dgrad epilogue (nullable): the tile this kernel stores is the
+  // gradient dz of z = relu?(scale*y + shift); `stats` then receives sum(g) and sum(g*y) with
+  // g = dz * (scale*y + shift > 0) instead of sum / sum of squares. red_y is y in the output view's layout.
+  const void* red_y;
+  const float* red_ss;        // nullable [2][stats_ld] scale, shift: ReLU mask (NULL = no ReLU)
+  long long red_stride[4];    // element strides of the output view along w, h, t, n
+  long long red_bitoff[7];    // element offset contributed by bit k of the tile row index (w bits, then h, t, n)
+};
+
+// Optional fused BatchNorm-backward reduction request for conv_dgrad_bf16 (see ConvTileParams::red_y).
+struct BnReduce {
+  const void* y;      // bf16 [N][T][H][W][Cin_p], the raw conv output that BN normalised to produce dgrad's dx tensor
+  const float* ss;    // nullable [2][Cin_p] forward scale/shift (ReLU mask); NULL when the activation had no ReLU
+  double* sums;       // [2][Cin_p] double, caller zeroes: sum(g), sum(g*y)
 };
 
 // Convolution geometry shared by fprop / dgrad / wgrad host code (padded channel counts).

@@ -40,3 +40,75 @@ int probe_overlap(const void* src, void* out, int c1, cudaStream_t stream) {
 }
 
 }  // namespace dv
+
+// ---------------------------------------------------------------------------------------------------
+// Debug microbenchmark (tests/diag/mma_rate.py): steady-state cycles per tcgen05.mma (M=128, N=n, K=16,
+// bf16, both operands in shared memory, SWIZZLE_128B K-major) issued back to back by one thread per CTA,
+// operands cycling through `region` bytes of shared memory. Tells the SS-mode operand-fetch limit apart
+// from issue-loop overhead in conv_tile_kernel. mode 1: every MMA re-uses one B tile (weight-stationary).
+namespace dv {
+
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int n_mma, int region, int mode, long long* out) {
+  extern __shared__ uint8_t dsm[];
+  __shared__ __align__(8) uint64_t done_bar;
+  __shared__ uint32_t tmem_slot;
+  const uint32_t raw = smem_u32(dsm);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  for (int i = threadIdx.x; i < region / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(dsm + (base - raw))[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) {
+    mbar_init(&done_bar, 1);
+    fence_barrier_init();
+  }
+  if (threadIdx.x < 32) {
+    tmem_alloc(&tmem_slot, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = make_idesc_bf16(128, n, 0, 0);
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t flags = 1u << 16;
+    const uint32_t a_bytes = 128 * 128, b_bytes = (uint32_t)n * 128;   // one 64-wide K chunk = 4 K-steps
+    const uint32_t pair = a_bytes + (mode == 1 ? 0 : b_bytes);
+    const uint32_t b_fixed = base + (uint32_t)region - b_bytes;
+    const uint32_t span = (mode == 1 ? (uint32_t)region - b_bytes : (uint32_t)region) / pair * pair;
+    uint32_t off = 0;
+    const long long t0 = clock64();
+    for (int i = 0; i < n_mma; i += 4) {
+      const uint32_t a = flags | ((base + off) >> 4);
+      const uint32_t b = flags | ((mode == 1 ? b_fixed : base + off + a_bytes) >> 4);
+      umma_bf16_lohi(tmem, a, b, hi, idesc, i > 0);
+      umma_bf16_lohi(tmem, a + 2, b + 2, hi, idesc, 1);
+      umma_bf16_lohi(tmem, a + 4, b + 4, hi, idesc, 1);
+      umma_bf16_lohi(tmem, a + 6, b + 6, hi, idesc, 1);
+      off += pair;
+      if (off >= span) off = 0;
+    }
+    const long long t1 = clock64();
+    umma_commit(&done_bar);
+    mbar_wait(&done_bar, 0);
+    const long long t2 = clock64();
+    out[blockIdx.x * 2] = t1 - t0;      // issue time
+    out[blockIdx.x * 2 + 1] = t2 - t0;  // until the last MMA completed
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+int mma_rate(int n, int n_mma, int region, int mode, long long* out, int grid, cudaStream_t stream) {
+  if (n < 16 || n > 256 || (n & 15) || region < 64 * 1024 || region > 200 * 1024) return fail(kBadArg, "mma_rate: bad arguments");
+  DV_CUDA_OK(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  mma_rate_kernel<<<grid, 128, region + 1024, stream>>>(n, n_mma, region, mode, out);
+  DV_LAUNCH_OK();
+  return kOk;
+}
+
+}  // namespace dv

@@ -190,6 +190,17 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 
+// Predicated 4-byte read-only global load (0 when !ok): a single predicated instruction, so a run of
+// these stays straight-line code with all loads in flight together.
+__device__ __forceinline__ uint32_t ldg_u32_pred(const void* ptr, bool ok) {
+  uint32_t v;
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b32 %0, 0;\n\t@q ld.global.nc.b32 %0, [%1];\n\t}"
+      : "=r"(v)
+      : "l"(ptr), "r"(static_cast<int>(ok)));
+  return v;
+}
+
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32.
 __host__ __device__ inline uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
   uint32_t d = 0;

@@ -14,6 +14,7 @@ Primitive <-> reference op:
   global_pool  nn.AdaptiveAvgPool3d((1,1,1))
 """
 import ctypes
+import os
 
 import torch
 import torch.distributed as dist
@@ -28,7 +29,7 @@ call = _lib.call
 class Act:
     """A bf16 NDHWC activation [N,T,H,W,Cp] with C logical channels and an optional gradient."""
 
-    __slots__ = ("data", "C", "grad", "grad2", "needs_grad", "s2d")
+    __slots__ = ("data", "C", "grad", "grad2", "needs_grad", "s2d", "bnred", "fused")
 
     def __init__(self, data, C, needs_grad=True, s2d=None):
         self.data = data
@@ -37,6 +38,8 @@ class Act:
         self.grad2 = None       # second pending contribution (summed lazily by the consumer)
         self.needs_grad = needs_grad
         self.s2d = s2d          # (N, T, H, W) of the original frames when data is the space-to-depth stem layout
+        self.bnred = None       # (RawBN, relu) when this is a plain relu?(BN(y)): lets a consumer's dgrad fuse the BN-backward reduce
+        self.fused = None       # (sums, dx): BN-backward sums a dgrad epilogue already produced for gradient dx
 
     @property
     def shape5(self):
@@ -78,6 +81,10 @@ class Context:
 
 # ----------------------------------------------------------------------------- helpers
 _weight_cache = {}
+# Fused dgrad + BN-backward reduce (dv_conv3d_dgrad_bnred_bf16). Off by default: on B200 the 4-warp epilogue of
+# conv_tile_kernel is already the bottleneck of the low-K (temporal) dgrads, so the fused column pass costs more
+# there than the separate HBM pass it removes (profiles/r01_fused_bn_reduce.txt); DV_FUSE_BN_REDUCE=1 enables it.
+FUSE_BN_REDUCE = os.environ.get("DV_FUSE_BN_REDUCE", "0") != "0"
 
 
 def packed_weights(conv):
@@ -286,7 +293,16 @@ def _conv_backward(ctx, r, dy):
         ctx.add_param_grad(r.conv.bias, torch.zeros_like(r.conv.bias))
     if r.x.needs_grad:
         dx = torch.empty_like(r.x.data)
-        call("dv_conv3d_dgrad_bf16", ptr(dy), ptr(r.packed[1]), ptr(dx), ctypes.byref(g), stream_ptr())
+        if FUSE_BN_REDUCE and r.x.bnred is not None and r.x.grad is None:
+            # x = relu?(BN(y_prev)) and this is (so far) its only gradient: the dgrad epilogue also produces
+            # the BN-backward sums of the layer below, saving dv_bn_bwd_reduce's pass over dx and y_prev
+            rp, relu = r.x.bnred
+            sums = torch.zeros(2 * g.Cin_p, dtype=torch.float64, device=dy.device)
+            call("dv_conv3d_dgrad_bnred_bf16", ptr(dy), ptr(r.packed[1]), ptr(dx), ctypes.byref(g), ptr(rp.y),
+                 ptr(rp.ss) if relu else None, ptr(sums), stream_ptr())
+            r.x.fused = (sums, dx)
+        else:
+            call("dv_conv3d_dgrad_bf16", ptr(dy), ptr(r.packed[1]), ptr(dx), ctypes.byref(g), stream_ptr())
         _acc_grad(r.x, dx)
 
 
@@ -311,6 +327,9 @@ def activate(ctx, r1, r2=None, res=None, relu=True, out=None, out_coff=0):
          1 if relu else 0, stream_ptr())
     if not ctx.record:
         return out_act
+    plain = r2 is None and res is None and out is None
+    if plain:
+        out_act.bnred = (r1, relu)
 
     def backward():
         dout2 = None
@@ -331,9 +350,13 @@ def activate(ctx, r1, r2=None, res=None, relu=True, out=None, out_coff=0):
         for i, r in enumerate((r1, r2)):
             if r is None:
                 continue
-            sums = torch.zeros(2 * Cp, dtype=torch.float64, device=dev)
-            call("dv_bn_bwd_reduce", ptr(dout), ptr(dout2), ptr(out_t), ptr(r.y), mask_ss, ptr(sums), rows, Cp,
-                 o_ld, o_coff, 1 if relu else 0, stream_ptr())
+            fused = out_act.fused if plain else None
+            if fused is not None and dout2 is None and ov is None and fused[1] is dout:
+                sums = fused[0]      # already reduced by the dgrad that produced dout
+            else:
+                sums = torch.zeros(2 * Cp, dtype=torch.float64, device=dev)
+                call("dv_bn_bwd_reduce", ptr(dout), ptr(dout2), ptr(out_t), ptr(r.y), mask_ss, ptr(sums), rows, Cp,
+                     o_ld, o_coff, 1 if relu else 0, stream_ptr())
             sums_g = sums
             if r.sync:
                 sums_g = sums.clone()
@@ -358,6 +381,7 @@ def activate(ctx, r1, r2=None, res=None, relu=True, out=None, out_coff=0):
             _acc_grad(res, g_buf)
         if out is None:
             out_act.grad = out_act.grad2 = None
+        out_act.fused = None
 
     ctx.tape.append(backward)
     return out_act

@@ -62,6 +62,14 @@ int dv_conv3d_fprop_bf16(const void* x, const void* wf, void* y, double* bn_stat
 /* dx = conv_transpose(dy, w) */
 int dv_conv3d_dgrad_bf16(const void* dy, const void* wt, void* dx, const dv_conv_geom* g,
                          void* stream);
+/* dgrad with the BatchNorm-backward reduction of the layer below fused into its epilogue: dx is the
+ * gradient of z = relu?(scale*y_prev + shift) (y_prev: bf16 [N][T][H][W][Cin_p], the raw conv output the
+ * BatchNorm in front of this conv normalised; ss_prev = [2][Cin_p] scale/shift, NULL = no ReLU). Adds
+ * sum(g) and sum(g*y_prev), g = dx * (scale*y_prev + shift > 0), over all positions into
+ * sums[0:Cin_p] / sums[Cin_p:2*Cin_p] (double, caller zeroes) - what dv_bn_bwd_reduce would compute
+ * from dx in a separate pass (autograd of nn.BatchNorm3d + nn.ReLU, backbone/r21d.py:56-57,68). */
+int dv_conv3d_dgrad_bnred_bf16(const void* dy, const void* wt, void* dx, const dv_conv_geom* g,
+                               const void* y_prev, const float* ss_prev, double* sums, void* stream);
 /* dw_packed (fp32 [Cout_p][taps][Cin_p]) = correlation(x, dy); buffer is overwritten */
 int dv_conv3d_wgrad_bf16(const void* x, const void* dy, float* dw_packed, const dv_conv_geom* g,
                          void* stream);
@@ -208,6 +216,9 @@ int dv_sgd_momentum_step(const int64_t* chunk_table, int n_chunks, float lr, flo
 int dv_debug_set_conv_profile(int64_t* buf);
 /* debug probe (tests only): TMA tensor map with overlapping windows */
 int dv_debug_probe_overlap_tmap(const void* src, void* out, int c1, void* stream);
+/* debug microbenchmark (tests/diag/mma_rate.py): cycles for n_mma back-to-back tcgen05.mma M=128 N=n K=16 (bf16,
+ * shared-memory operands cycling through region_bytes) per CTA -> cycles[grid][2] = (issue, completion) */
+int dv_debug_mma_rate(int n, int n_mma, int region_bytes, int mode, int64_t* cycles, int grid, void* stream);
 
 #ifdef __cplusplus
 }

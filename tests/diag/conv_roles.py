@@ -8,6 +8,9 @@ N = int(os.environ.get("NCLIPS", "96"))
 LAYERS = [("fprop temporal 144->64", "f", (N, 16, 56, 56, 144, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0))),
           ("fprop spatial 64->144", "f", (N, 16, 56, 56, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1))),
           ("dgrad spatial 64->144", "d", (N, 16, 56, 56, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1))),
+          ("dgrad temporal 144->64", "d", (N, 16, 56, 56, 144, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0))),
+          ("dgrad+bnred temporal 144->64", "r", (N, 16, 56, 56, 144, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0))),
+          ("dgrad+bnred spatial 64->144", "r", (N, 16, 56, 56, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1))),
           ("fprop temporal 83->64", "f", (N, 16, 56, 56, 83, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0))),
           ("fprop spatial 128->288", "f", (N, 8, 28, 28, 128, 288, (1, 3, 3), (1, 1, 1), (0, 1, 1)))]
 prof = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
@@ -18,7 +21,12 @@ for name, kind, (n, t, h, w, ci, co, k, s, p) in LAYERS:
     wf, wtt = K.pack_conv_weight(wt, g)
     dy = torch.randn(n, g.To, g.Ho, g.Wo, g.Cout_p, device=dev).bfloat16()
     stats = torch.zeros(2 * g.Cout_p, dtype=torch.float64, device=dev)
-    run = (lambda: K.conv3d_fprop(x, wf, g, bn_stats=stats)) if kind == "f" else (lambda: K.conv3d_dgrad(dy, wtt, g))
+    ss = torch.randn(2 * g.Cin_p, device=dev)
+    sums = torch.zeros(2 * g.Cin_p, dtype=torch.float64, device=dev)
+    dxb = torch.empty_like(x)
+    run = {"f": lambda: K.conv3d_fprop(x, wf, g, bn_stats=stats), "d": lambda: K.conv3d_dgrad(dy, wtt, g),
+           "r": lambda: _lib.call("dv_conv3d_dgrad_bnred_bf16", _lib.ptr(dy), _lib.ptr(wtt), _lib.ptr(dxb), ctypes.byref(g),
+                                  _lib.ptr(x), _lib.ptr(ss), _lib.ptr(sums), _lib.stream_ptr())}[kind]
     for _ in range(2): run()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -1,0 +1,21 @@
+"""GPU diagnostic: steady-state tcgen05.mma rate (SS mode, M=128, K=16) vs N — the operand-fetch ceiling the conv
+kernels live under. Ideal = N/2 cycles per MMA (8192 MAC/clk/SM)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import torch
+from dualvar_b200 import _lib
+dev = "cuda:0"
+out = torch.zeros(148 * 2, dtype=torch.int64, device=dev)
+n_mma = 4096
+for grid in (1, 148):
+    for mode in (0, 1):
+        for n in (64, 96, 128, 144, 192, 256):
+            for region in (96 * 1024, 192 * 1024):
+                _lib.call("dv_debug_mma_rate", n, n_mma, region, mode, _lib.ptr(out), grid, _lib.stream_ptr())
+                torch.cuda.synchronize()
+                c = out.view(148, 2)[:grid].double()
+                issue, total = c[:, 0].mean().item() / n_mma, c[:, 1].mean().item() / n_mma
+                bytes_per = 4096 + n * 32
+                print(f"grid {grid:3d} mode {mode} N={n:3d} region {region//1024:3d}K: issue {issue:6.1f} cyc/MMA, "
+                      f"complete {total:6.1f} cyc/MMA (ideal {n/2:.0f}) -> {bytes_per/total:5.1f} B/clk operand fetch, "
+                      f"{n/2/total*100:4.0f}% of peak", flush=True)

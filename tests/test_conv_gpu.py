@@ -69,6 +69,44 @@ def test_conv_trio_matches_torch(case):
     assert _rel(dw, wr.grad) < 1e-4          # fp32 accumulate + fp32 output
 
 
+@pytest.mark.parametrize("relu", [True, False])
+@pytest.mark.parametrize("case", [c for c in CASES if c[6] > 4 and "stem" not in c[0]], ids=lambda c: c[0])
+def test_dgrad_fused_bn_reduce(case, relu):
+    """dv_conv3d_dgrad_bnred_bf16: dx bit-identical to the plain dgrad, and the epilogue's sum(g), sum(g*y)
+    equal to dv_bn_bwd_reduce run on that dx (and to a torch fp64 evaluation of the same sums)."""
+    import ctypes
+    from dualvar_b200 import _lib, kernels as K
+    name, N, T, H, W, Cin, Cout, k, s, p = case
+    dev = "cuda:0"
+    g = K.make_geom(N, T, H, W, Cin, Cout, k, s, p)
+    gen = torch.Generator(device=dev).manual_seed(abs(hash(name)) % (2 ** 31) + 1)
+    w = torch.randn(Cout, Cin, *k, device=dev, generator=gen) / (Cout * k[0] * k[1] * k[2]) ** 0.5
+    _, wt = K.pack_conv_weight(w, g)
+    dy = torch.randn(N, g.To, g.Ho, g.Wo, g.Cout_p, device=dev, generator=gen).bfloat16()
+    dy[..., Cout:] = 0
+    y_prev = torch.randn(N, T, H, W, g.Cin_p, device=dev, generator=gen).bfloat16()
+    y_prev[..., Cin:] = 0
+    ss = torch.randn(2 * g.Cin_p, device=dev, generator=gen)
+    dx_ref = K.conv3d_dgrad(dy, wt, g)
+    dx = torch.full_like(dx_ref, float("nan"))
+    sums = torch.zeros(2 * g.Cin_p, dtype=torch.float64, device=dev)
+    _lib.call("dv_conv3d_dgrad_bnred_bf16", _lib.ptr(dy), _lib.ptr(wt), _lib.ptr(dx), ctypes.byref(g),
+              _lib.ptr(y_prev), _lib.ptr(ss) if relu else None, _lib.ptr(sums), _lib.stream_ptr())
+    assert torch.equal(dx, dx_ref)
+    rows = N * T * H * W
+    want = torch.zeros_like(sums)
+    _lib.call("dv_bn_bwd_reduce", _lib.ptr(dx), None, _lib.ptr(dx), _lib.ptr(y_prev), _lib.ptr(ss) if relu else None,
+              _lib.ptr(want), rows, g.Cin_p, g.Cin_p, 0, 1 if relu else 0, _lib.stream_ptr())
+    yd, dd = y_prev.double().reshape(rows, -1), dx.double().reshape(rows, -1)
+    if relu:
+        zf = torch.addcmul(ss[g.Cin_p:].float(), y_prev.float().reshape(rows, -1), ss[:g.Cin_p].float())  # fma like the kernels
+        dd = dd * (zf > 0)
+    exact = torch.cat([dd.sum(0), (dd * yd).sum(0)])
+    scale = exact.abs().max().item() + 1.0
+    assert (sums - exact).abs().max().item() < 1e-3 * scale      # fp32 partial sums per CTA, double across CTAs
+    assert (sums - want).abs().max().item() < 2e-4 * scale
+
+
 def test_conv_linearity_at_full_size():
     """BASELINE-size property check (no oracle at this size): conv(a*x1 + x2) with power-of-two a is
     exactly a*conv(x1) + conv(x2) up to bf16 rounding of the stored outputs; pad channels stay zero."""
