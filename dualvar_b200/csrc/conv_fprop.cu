@@ -9,7 +9,8 @@
 // warp 0   : TMA producer (A box of the shifted input + weight box per (tap, k-chunk) stage)
 // warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (fp32 accumulators in TMEM,
 //            two accumulator buffers so the epilogue of tile i overlaps the main loop of tile i+1)
-// warps 2-5: epilogue: tcgen05.ld -> (+bias) -> bf16 -> swizzled smem -> TMA store, plus the
+// warps 2-9: epilogue, two groups of four warps taking alternate 64-channel chunks of the tile:
+//            tcgen05.ld -> (+bias) -> bf16 -> swizzled smem -> TMA store, plus the
 //            per-channel sum / sum-of-squares of the stored values for training-mode BatchNorm
 //            (reference: nn.BatchNorm3d after every conv, e.g. backbone/r21d.py:56,106,111).
 // The grid is persistent (<= one CTA per SM); a CTA keeps one channel tile for its whole life so
@@ -27,14 +28,21 @@
 
 namespace dv {
 
-constexpr int kNumThreads = 192;
+constexpr int kNumThreads = 320;            // warp 0 TMA, warp 1 MMA, warps 2-5 and 6-9: two epilogue groups
+constexpr int kEpiThreads = 256;
 constexpr int kAStageBytes = kTileM * 128;  // 16 KB
 constexpr int kOutBufBytes = kTileM * 128;  // one 64-channel chunk of the output tile
 constexpr int kMaxStages = 8;
 constexpr int kTmemCols = 512;
-constexpr int kSmemBudget = 232448 - 12288;  // 227 KB minus static smem (stat partials, tap table, barriers)
-constexpr int kOutBufs = 3;                  // output staging buffers: one named barrier per chunk suffices
+constexpr int kSmemBudget = 232448 - 20480;  // 227 KB minus static smem (stat partials, barriers)
+constexpr int kOutBufs = 4;                  // output staging buffers: two per epilogue group
 
+// kPair: the kernel runs as CTA pairs (cluster of 2, cta_group::2): one M=256 MMA covers the two CTAs' 128-position
+// tiles, each CTA stages its own A box and HALF of the weight tile's rows, so the B operand fetch per CTA halves
+// (tests/diag/mma_rate.py: SS-mode operand fetch saturates at 128 B/clk/SM, N=144 alone needs 121 B/clk). Only the
+// leader CTA (cluster rank 0) issues MMAs; its full / accumulator-free barriers collect both CTAs' signals, commits
+// are multicast to both CTAs' barriers.
+template <bool kPair>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -44,7 +52,7 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ __align__(8) uint64_t bres_bar;
   __shared__ uint32_t tmem_base_slot;
-  __shared__ __align__(16) float s_part[4][2][kMaxBlockN];   // BN partial sums per epilogue warp: [row quarter][sum|sumsq][channel]
+  __shared__ __align__(16) float s_part[8][2][kMaxBlockN];   // BN partial sums per epilogue warp: [group * 4 + row quarter][sum|sumsq][channel]
 
   // warp-uniform role index (shfl makes the uniformity visible to the compiler: loop state of the
   // producer / MMA warps then lives in uniform registers, which is what UTMALDG / UTCHMMA consume)
@@ -55,14 +63,17 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
-  const int b_tap_bytes = p.block_n * 128;                  // one weight tile [block_n][64]
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs)
+  const int unit = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // CTA (pair) index: owns tiles unit, unit+units, ...
+  const int units = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int b_tap_bytes = (kPair ? p.block_n / 2 : p.block_n) * 128;   // one weight tile [block_n (/2)][64] of this CTA
   const int b_stage_bytes = p.b_resident ? 0 : p.max_group * b_tap_bytes;
   const int stage_bytes = p.a_stage_bytes + b_stage_bytes;
   uint8_t* res_b = smem;                                    // resident weights: taps * k_chunks tiles
   uint8_t* ring = res_b + (p.b_resident ? p.num_taps * p.k_chunks * b_tap_bytes : 0);
   uint8_t* o_smem = ring + p.stages * stage_bytes;          // 2 * 16 KB output staging
 
-  const int n_tile = blockIdx.x % p.n_tiles;  // grid is a multiple of n_tiles
+  const int n_tile = unit % p.n_tiles;  // the number of CTAs (pairs) is a multiple of n_tiles
   const int bn_mma = (n_tile == p.n_tiles - 1) ? p.last_n : p.block_n;
 
   if (threadIdx.x == 0) {
@@ -72,20 +83,27 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 128);
+      mbar_init(&tmem_empty_bar[i], kPair ? 2 * kEpiThreads : kEpiThreads);   // the leader's barrier collects both CTAs' epilogues
     }
     mbar_init(&bres_bar, 1);
     fence_barrier_init();
   }
-  for (int c = threadIdx.x; c < 4 * 2 * kMaxBlockN; c += kNumThreads) (&s_part[0][0][0])[c] = 0.f;
+  for (int c = threadIdx.x; c < 8 * 2 * kMaxBlockN; c += kNumThreads) (&s_part[0][0][0])[c] = 0.f;
   if (warp == 1) {
-    tmem_alloc(&tmem_base_slot, kTmemCols);
-    tmem_relinquish();
+    if (kPair) {
+      tmem_alloc2(&tmem_base_slot, kTmemCols);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(&tmem_base_slot, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before_sync();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();   // peer barriers must be initialised before remote signals
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_slot;
+  // tile id -> position-tile index of this CTA (a pair covers two consecutive position tiles)
+  auto m_index = [&](int tile) { return kPair ? (tile / p.n_tiles) * 2 + (int)rank : tile / p.n_tiles; };
 
   const TileGeom& g = p.g;
 
@@ -101,17 +119,22 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
       uint32_t phase = 0;
       long long prof_wait_empty = 0;
       const long long prof_t0 = p.prof ? clock64() : 0;
-      const int bcol = n_tile * p.block_n;
+      // this CTA's rows of the weight tile: all of them, or its half of the MMA's N rows in pair mode
+      const int bcol = n_tile * p.block_n + (kPair ? (int)rank * (bn_mma / 2) : 0);
+      // signals of both CTAs' loads go to the leader's barriers
+      const uint32_t bres_addr = kPair ? mapa_u32(smem_u32(&bres_bar), 0) : smem_u32(&bres_bar);
+      const uint32_t full0_addr = kPair ? mapa_u32(smem_u32(&full_bar[0]), 0) : smem_u32(&full_bar[0]);
+      const uint32_t tx_mult = kPair ? 2u : 1u;
       if (p.b_resident && issuer) {
         // weight-stationary: every (tap, k-chunk) weight tile of this channel tile is loaded once
-        mbar_expect_tx(&bres_bar, p.num_taps * p.k_chunks * b_tap_bytes);
+        if (rank == 0) mbar_expect_tx(&bres_bar, tx_mult * p.num_taps * p.k_chunks * b_tap_bytes);
         for (int tap = 0; tap < p.num_taps; ++tap)
           for (int kc = 0; kc < p.k_chunks; ++kc)
-            tma_load_3d(res_b + (tap * p.k_chunks + kc) * b_tap_bytes, &p.b_map, &bres_bar, kc * kChunkK,
-                        p.taps[tap].widx, bcol);
+            tma_load_3d_to<kPair>(res_b + (tap * p.k_chunks + kc) * b_tap_bytes, &p.b_map, bres_addr, kc * kChunkK,
+                                  p.taps[tap].widx, bcol);
       }
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        int m_id = tile / p.n_tiles;
+      for (int tile = unit; tile < p.total_tiles; tile += units) {
+        int m_id = m_index(tile);
         const int wb = m_id % g.tiles_w; m_id /= g.tiles_w;
         const int hb = m_id % g.tiles_h; m_id /= g.tiles_h;
         const int tb = m_id % g.tiles_t; m_id /= g.tiles_t;
@@ -127,14 +150,15 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (p.prof) prof_wait_empty += clock64() - c0;
             if (issuer) {
-              mbar_expect_tx(&full_bar[stage], tx_bytes);
+              if (rank == 0) mbar_expect_tx(&full_bar[stage], tx_mult * tx_bytes);
+              const uint32_t full_addr = full0_addr + (uint32_t)stage * 8u;
               uint8_t* st = ring + stage * stage_bytes;
-              tma_load_5d(st, &p.a_map[lead.map], &full_bar[stage], kc * kChunkK, w0 + lead.dw, h0 + lead.dh,
-                          t0 + lead.dt, n0);
+              tma_load_5d_to<kPair>(st, &p.a_map[lead.map], full_addr, kc * kChunkK, w0 + lead.dw, h0 + lead.dh,
+                                    t0 + lead.dt, n0);
               if (!p.b_resident)
                 for (int i = 0; i < len; ++i)
-                  tma_load_3d(st + p.a_stage_bytes + i * b_tap_bytes, &p.b_map, &full_bar[stage], kc * kChunkK,
-                              p.taps[gb + i].widx, bcol);
+                  tma_load_3d_to<kPair>(st + p.a_stage_bytes + i * b_tap_bytes, &p.b_map, full_addr, kc * kChunkK,
+                                        p.taps[gb + i].widx, bcol);
             }
             __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -142,16 +166,23 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
           gb += len;
         }
       }
+      if (kPair) {
+        // producer tail: every stage released (all multicast commits delivered) before this CTA may exit
+        for (int i = 0; i < p.stages; ++i) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
       if (p.prof && issuer) {
-        p.prof[blockIdx.x * 8 + 0] = clock64() - prof_t0;   // producer total
-        p.prof[blockIdx.x * 8 + 1] = prof_wait_empty;       // producer waiting for a free stage
+        p.prof[blockIdx.x * 16 + 0] = clock64() - prof_t0;   // producer total
+        p.prof[blockIdx.x * 16 + 1] = prof_wait_empty;       // producer waiting for a free stage
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only in pair mode)
+    if (rank == 0) {
       const bool issuer = elect_one();
-      const uint32_t idesc = make_idesc_bf16(kTileM, bn_mma, 0, 0);
+      const uint32_t idesc = make_idesc_bf16(kPair ? 2 * kTileM : kTileM, bn_mma, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -166,7 +197,7 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
         mbar_wait(&bres_bar, 0);
         tc_fence_after_sync();
       }
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = unit; tile < p.total_tiles; tile += units, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         const long long ca = p.prof ? clock64() : 0;
@@ -197,34 +228,36 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
               const uint32_t al = st_lo + aoff, bl = b_lo + boff;
               if (issuer) {
                 // +32 bytes along K inside the 128B swizzle span = +2 in (addr >> 4) units
-                umma_bf16_lohi(d_tmem, al, bl, desc_hi, idesc, accumulate);
-                if (ksteps > 1) umma_bf16_lohi(d_tmem, al + 2, bl + 2, desc_hi, idesc, 1);
-                if (ksteps > 2) umma_bf16_lohi(d_tmem, al + 4, bl + 4, desc_hi, idesc, 1);
-                if (ksteps > 3) umma_bf16_lohi(d_tmem, al + 6, bl + 6, desc_hi, idesc, 1);
+                umma_issue<kPair>(d_tmem, al, bl, desc_hi, idesc, accumulate);
+                if (ksteps > 1) umma_issue<kPair>(d_tmem, al + 2, bl + 2, desc_hi, idesc, 1);
+                if (ksteps > 2) umma_issue<kPair>(d_tmem, al + 4, bl + 4, desc_hi, idesc, 1);
+                if (ksteps > 3) umma_issue<kPair>(d_tmem, al + 6, bl + 6, desc_hi, idesc, 1);
               }
               accumulate = 1;
             }
-            if (issuer) umma_commit(&empty_bar[stage]);
+            if (issuer) umma_commit_to<kPair>(&empty_bar[stage]);
             __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
           gb += len;
         }
-        if (issuer) umma_commit(&tmem_full_bar[acc]);
+        if (issuer) umma_commit_to<kPair>(&tmem_full_bar[acc]);
         __syncwarp();
       }
       if (p.prof && issuer) {
-        p.prof[blockIdx.x * 8 + 2] = clock64() - prof_t0;   // MMA issuer total
-        p.prof[blockIdx.x * 8 + 3] = prof_wait_full;        // waiting for TMA data
-        p.prof[blockIdx.x * 8 + 4] = prof_wait_acc;         // waiting for the epilogue to free an accumulator
+        p.prof[blockIdx.x * 16 + 2] = clock64() - prof_t0;   // MMA issuer total
+        p.prof[blockIdx.x * 16 + 3] = prof_wait_full;        // waiting for TMA data
+        p.prof[blockIdx.x * 16 + 4] = prof_wait_acc;         // waiting for the epilogue to free an accumulator
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (128 threads)
+    // ------------------------------------------------------------------ epilogue (2 groups x 128 threads)
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;     // tile row == TMEM lane
-    const int et = threadIdx.x - 64;   // 0..127
+    const int grp = (warp - 2) >> 2;   // epilogue group: chunks grp, grp + 2, ... of every tile
+    const int et = (threadIdx.x - 64) & 127;   // thread index inside the group
     const bool leader = (et == 0);
+    uint8_t* const o_grp = o_smem + grp * 2 * kOutBufBytes;
     const int rw = row & ((1 << g.lw) - 1);
     const int rh = (row >> g.lw) & ((1 << g.lh) - 1);
     const int rt = (row >> (g.lw + g.lh)) & ((1 << g.lt) - 1);
@@ -235,10 +268,12 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
     const bool red = do_stats && p.red_y != nullptr;
     int it = 0;
     uint32_t obuf = 0;
-    long long prof_epi_wait = 0;
-    const long long prof_t0 = (p.prof && et == 0) ? clock64() : 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      int m_id = tile / p.n_tiles;
+    long long prof_epi_wait = 0, prof_ld = 0, prof_sts = 0, prof_bar = 0, prof_store = 0, prof_stat = 0, prof_yld = 0;
+    const bool prof_on = p.prof && threadIdx.x == 64;
+    const long long prof_t0 = prof_on ? clock64() : 0;
+    const uint32_t acc_free0 = kPair ? mapa_u32(smem_u32(&tmem_empty_bar[0]), 0) : smem_u32(&tmem_empty_bar[0]);
+    for (int tile = unit; tile < p.total_tiles; tile += units, ++it) {
+      int m_id = m_index(tile);
       const int wb = m_id % g.tiles_w; m_id /= g.tiles_w;
       const int hb = m_id % g.tiles_h; m_id /= g.tiles_h;
       const int tb = m_id % g.tiles_t; m_id /= g.tiles_t;
@@ -248,15 +283,24 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
                          (n0 + rn < g.ext_n);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const long long ce = (p.prof && et == 0) ? clock64() : 0;
+      const long long ce = prof_on ? clock64() : 0;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
-      if (p.prof && et == 0) prof_epi_wait += clock64() - ce;
+      if (prof_on) prof_epi_wait += clock64() - ce;
       tc_fence_after_sync();
       const uint32_t t_addr = tmem_base + acc * kMaxBlockN + (static_cast<uint32_t>(q * 32) << 16);
-      for (int cc = 0; cc < nchunks; ++cc) {
+      // the two groups take alternate chunks, swapping roles every tile so that odd chunk counts balance out
+      const int first_cc = (grp + it) & 1;
+      // last chunk of this tile that this group loads from TMEM (-1: none)
+      const int last_cc = (nchunks - 1 - first_cc >= 0) ? first_cc + ((nchunks - 1 - first_cc) & ~1) : -1;
+      if (last_cc < 0) {
+        tc_fence_before_sync();
+        if (kPair) mbar_arrive_cluster(acc_free0 + (uint32_t)acc * 8u); else mbar_arrive(&tmem_empty_bar[acc]);
+      }
+      for (int cc = first_cc; cc < nchunks; cc += 2) {
         const int ncols = min(64, bn_mma - cc * 64);
-        uint8_t* ob = o_smem + obuf * kOutBufBytes;
-        obuf = (obuf == kOutBufs - 1) ? 0 : obuf + 1;
+        uint8_t* ob = o_grp + obuf * kOutBufBytes;
+        obuf ^= 1;
+        const long long pc0 = prof_on ? clock64() : 0;
         // fused BN-backward reduce: this thread's 32 (row, channel pair) words of y for the column pass
         // below are requested now, so their latency hides behind the TMEM load / convert / store phase.
         // Row bit k of the tile adds red_bitoff[k] elements (tile dims are powers of two), so every row
@@ -295,6 +339,7 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
             }
           }
         }
+        const long long pc1 = prof_on ? clock64() : 0;
         // all TMEM loads of the chunk in flight together, one wait
         uint32_t v[64];
         tmem_ld16(t_addr + cc * 64, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
@@ -302,10 +347,22 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
         if (ncols > 32) tmem_ld16(t_addr + cc * 64 + 32, *reinterpret_cast<uint32_t(*)[16]>(&v[32]));
         if (ncols > 48) tmem_ld16(t_addr + cc * 64 + 48, *reinterpret_cast<uint32_t(*)[16]>(&v[48]));
         tmem_ld_wait();
-        if (cc == nchunks - 1) {
+        const long long pc2 = prof_on ? clock64() : 0;
+        if (p.bias != nullptr) {   // conv bias (C3D): uniform branch, off the common path
+#pragma unroll
+          for (int j = 0; j < 64; ++j) {
+            const int c = bcol + cc * 64 + j;
+            if (j < ncols && c < p.stats_ld) v[j] = __float_as_uint(__uint_as_float(v[j]) + p.bias[c]);
+          }
+        }
+        if (!valid) {              // rows outside the tensor (partial tiles) store zeros
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] = 0u;
+        }
+        if (cc == last_cc) {
           // the accumulator now lives in registers: hand the TMEM buffer back to the MMA warp
           tc_fence_before_sync();
-          mbar_arrive(&tmem_empty_bar[acc]);
+          if (kPair) mbar_arrive_cluster(acc_free0 + (uint32_t)acc * 8u); else mbar_arrive(&tmem_empty_bar[acc]);
         }
         uint8_t* orow = ob + row * 128;
 #pragma unroll
@@ -314,14 +371,8 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
             uint32_t pk[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              float f0 = __uint_as_float(v[gi * 16 + 2 * j]);
-              float f1 = __uint_as_float(v[gi * 16 + 2 * j + 1]);
-              if (p.bias != nullptr) {
-                const int c = bcol + cc * 64 + gi * 16 + 2 * j;
-                f0 += (c < p.stats_ld) ? p.bias[c] : 0.f;
-                f1 += (c + 1 < p.stats_ld) ? p.bias[c + 1] : 0.f;
-              }
-              if (!valid) { f0 = 0.f; f1 = 0.f; }
+              const float f0 = __uint_as_float(v[gi * 16 + 2 * j]);
+              const float f1 = __uint_as_float(v[gi * 16 + 2 * j + 1]);
               __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
               pk[j] = *reinterpret_cast<uint32_t*>(&h);
             }
@@ -332,14 +383,17 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
           }
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, 128);
+        const long long pc3 = prof_on ? clock64() : 0;
+        // the group's previous store (other buffer) has been read before the barrier releases anybody to
+        // overwrite that buffer with the next chunk (2 buffers per group)
+        if (leader) tma_store_wait_read<0>();
+        named_bar_sync(1 + grp, 128);
+        const long long pc4 = prof_on ? clock64() : 0;
         if (leader) {
           tma_store_5d(&p.out_map, ob, bcol + cc * 64, w0, h0, t0, n0);
           tma_store_commit();
-          // <= 1 store pending from here on: together with the next chunk's barrier this guarantees that
-          // the buffer written two chunks ago has been read before anybody overwrites it (3 buffers)
-          tma_store_wait_read<1>();
         }
+        const long long pc5 = prof_on ? clock64() : 0;
         if (red) {
           // column sums of g = dz * relu_mask(y) and g * y over the stored bf16 dz tile (same thread ->
           // (channel pair, row quarter) ownership as the forward statistics below)
@@ -365,8 +419,8 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
               b0 = fmaf(g0, yy.x, b0); b1 = fmaf(g1, yy.y, b1);
             }
             const int lc = cc * 64 + word * 2;
-            float2* ps = reinterpret_cast<float2*>(&s_part[rq][0][lc]);
-            float2* pq = reinterpret_cast<float2*>(&s_part[rq][1][lc]);
+            float2* ps = reinterpret_cast<float2*>(&s_part[grp * 4 + rq][0][lc]);
+            float2* pq = reinterpret_cast<float2*>(&s_part[grp * 4 + rq][1][lc]);
             float2 s2 = *ps, q2 = *pq;
             s2.x += a0; s2.y += a1; q2.x += b0; q2.y += b1;
             *ps = s2; *pq = q2;
@@ -387,30 +441,43 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
               b0 = fmaf(f.x, f.x, b0); b1 = fmaf(f.y, f.y, b1);
             }
             const int c = cc * 64 + word * 2;
-            float2* ps = reinterpret_cast<float2*>(&s_part[rq][0][c]);
-            float2* pq = reinterpret_cast<float2*>(&s_part[rq][1][c]);
+            float2* ps = reinterpret_cast<float2*>(&s_part[grp * 4 + rq][0][c]);
+            float2* pq = reinterpret_cast<float2*>(&s_part[grp * 4 + rq][1][c]);
             float2 s2 = *ps, q2 = *pq;
             s2.x += a0; s2.y += a1; q2.x += b0; q2.y += b1;
             *ps = s2; *pq = q2;
           }
         }
+        if (prof_on) {
+          const long long pc6 = clock64();
+          prof_yld += pc1 - pc0; prof_ld += pc2 - pc1; prof_sts += pc3 - pc2; prof_bar += pc4 - pc3;
+          prof_store += pc5 - pc4; prof_stat += pc6 - pc5;
+        }
       }
     }
-    if (p.prof && et == 0) {
-      p.prof[blockIdx.x * 8 + 5] = clock64() - prof_t0;     // epilogue total
-      p.prof[blockIdx.x * 8 + 6] = prof_epi_wait;           // epilogue waiting for an accumulator
-      p.prof[blockIdx.x * 8 + 7] = it;                      // tiles processed by this CTA
+    if (prof_on) {
+      p.prof[blockIdx.x * 16 + 8] = prof_yld;     // issuing the y loads of the fused BN-backward reduce
+      p.prof[blockIdx.x * 16 + 9] = prof_ld;      // tcgen05.ld + wait
+      p.prof[blockIdx.x * 16 + 10] = prof_sts;    // convert + st.shared + proxy fence
+      p.prof[blockIdx.x * 16 + 11] = prof_bar;    // named barrier (waiting for the other epilogue warps)
+      p.prof[blockIdx.x * 16 + 12] = prof_store;  // TMA store issue + wait for the store before last to drain
+      p.prof[blockIdx.x * 16 + 13] = prof_stat;   // column-sum pass
+      p.prof[blockIdx.x * 16 + 5] = clock64() - prof_t0;     // epilogue total
+      p.prof[blockIdx.x * 16 + 6] = prof_epi_wait;           // epilogue waiting for an accumulator
+      p.prof[blockIdx.x * 16 + 7] = it;                      // tiles processed by this CTA
     }
     if (leader) tma_store_wait_all<0>();
     if (do_stats) {
-      named_bar_sync(1, 128);
-      for (int c = et; c < bn_mma; c += 128) {
+      named_bar_sync(3, kEpiThreads);
+      for (int c = threadIdx.x - 64; c < bn_mma; c += kEpiThreads) {
         const int gc = bcol + c;
         if (gc < p.stats_ld) {
-          const double su = (double)s_part[0][0][c] + (double)s_part[1][0][c] + (double)s_part[2][0][c] +
-                            (double)s_part[3][0][c];
-          const double sq = (double)s_part[0][1][c] + (double)s_part[1][1][c] + (double)s_part[2][1][c] +
-                            (double)s_part[3][1][c];
+          double su = 0.0, sq = 0.0;
+#pragma unroll
+          for (int w8 = 0; w8 < 8; ++w8) {
+            su += (double)s_part[w8][0][c];
+            sq += (double)s_part[w8][1][c];
+          }
           atomicAdd(&p.stats[gc], su);
           atomicAdd(&p.stats[p.stats_ld + gc], sq);
         }
@@ -419,10 +486,10 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
   }
 
   tc_fence_before_sync();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (kPair) tmem_dealloc2(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -513,12 +580,14 @@ static long long* g_prof = nullptr;
 void set_conv_profile(long long* p) { g_prof = p; }
 static int g_halo_enabled = 1;      // DV_CONV_HALO=0 disables tap grouping (A/B testing)
 static int g_resident_enabled = 1;  // DV_CONV_RESIDENT=0 disables weight-stationary CTAs
+static int g_pair_enabled = 1;      // DV_CONV_PAIR=0 disables CTA pairs (cta_group::2)
 static void read_env_once() {
   static bool done = false;
   if (done) return;
   done = true;
   if (const char* e = getenv("DV_CONV_HALO")) g_halo_enabled = atoi(e);
   if (const char* e = getenv("DV_CONV_RESIDENT")) g_resident_enabled = atoi(e);
+  if (const char* e = getenv("DV_CONV_PAIR")) g_pair_enabled = atoi(e);
 }
 
 // out(view) = sum_taps A_view(tap)[box shifted by tap] * W[tap]
@@ -627,14 +696,17 @@ static int conv_multi_tap(ConvTileParams& P, MapEncoder enc, const void* enc_ctx
   P.k_chunks = ceil_div(kin_p, kChunkK);
   P.k_steps_last = ceil_div(kin_p - (P.k_chunks - 1) * kChunkK, 16);
   const long long m_tiles = (long long)g.tiles_w * g.tiles_h * g.tiles_t * g.tiles_n;
-  P.total_tiles = (int)(m_tiles * P.n_tiles);
-  const int b_tap_bytes = P.block_n * 128;
+  // CTA pairs (one M=256 MMA over two position tiles, weight rows split between the CTAs) whenever there is
+  // enough work to fill the chip with pairs
+  const bool pair = g_pair_enabled == 2 || (g_pair_enabled && m_tiles * P.n_tiles >= 2LL * sm_count());   // 2 = force (tests)
+  P.total_tiles = (int)((pair ? (m_tiles + 1) / 2 : m_tiles) * P.n_tiles);
+  const int b_tap_bytes = (pair ? P.block_n / 2 : P.block_n) * 128;
   const int avail = kSmemBudget - 1024 - kOutBufs * kOutBufBytes;
   const int res_bytes = ntaps * P.k_chunks * b_tap_bytes;
   // weight-stationary when the whole filter of this channel tile fits next to >= 3 A stages and the CTA
   // amortises the load over several tiles
   P.b_resident = (g_resident_enabled && P.n_tiles == 1 && res_bytes <= 112 * 1024 &&
-                  avail - res_bytes >= 3 * P.a_stage_bytes && P.total_tiles >= 3 * sm_count()) ? 1 : 0;
+                  avail - res_bytes >= 3 * P.a_stage_bytes && m_tiles >= 3 * sm_count()) ? 1 : 0;
   const int stage_bytes = P.a_stage_bytes + (P.b_resident ? 0 : max_group * b_tap_bytes);
   P.stages = (avail - (P.b_resident ? res_bytes : 0)) / stage_bytes;
   if (P.stages > kMaxStages) P.stages = kMaxStages;
@@ -663,7 +735,7 @@ static int conv_multi_tap(ConvTileParams& P, MapEncoder enc, const void* enc_ctx
   {  // weights: [rows][taps][kin_p] bf16, box (64, 1, block_n)
     uint64_t dims[3] = {(uint64_t)kin_p, (uint64_t)w_taps, (uint64_t)w_rows_p};
     uint64_t strides[3] = {2, (uint64_t)kin_p * 2, (uint64_t)kin_p * w_taps * 2};
-    uint32_t box[3] = {kChunkK, 1, (uint32_t)P.block_n};
+    uint32_t box[3] = {kChunkK, 1, (uint32_t)(pair ? P.block_n / 2 : P.block_n)};
     int rc = encode_tmap(&P.b_map, w_packed, 2, 3, dims, strides, box, true);
     if (rc) return rc;
   }
@@ -675,13 +747,30 @@ static int conv_multi_tap(ConvTileParams& P, MapEncoder enc, const void* enc_ctx
   const int smem_bytes = 1024 + (P.b_resident ? res_bytes : 0) + P.stages * stage_bytes + kOutBufs * kOutBufBytes;
   static bool attr_set = false;
   if (!attr_set) {
-    DV_CUDA_OK(cudaFuncSetAttribute(conv_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DV_CUDA_OK(cudaFuncSetAttribute(conv_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kSmemBudget));
+    DV_CUDA_OK(cudaFuncSetAttribute(conv_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     kSmemBudget));
     attr_set = true;
   }
-  int grid = sm_count() / P.n_tiles * P.n_tiles;
-  if (grid > P.total_tiles) grid = P.total_tiles;  // total_tiles is a multiple of n_tiles
-  conv_tile_kernel<<<grid, kNumThreads, smem_bytes, stream>>>(P);
+  // CTAs (or CTA pairs): one per SM (pair of SMs), a multiple of the channel-tile count
+  int units = (pair ? sm_count() / 2 : sm_count()) / P.n_tiles * P.n_tiles;
+  if (units > P.total_tiles) units = P.total_tiles;  // total_tiles is a multiple of n_tiles
+  if (!pair) {
+    conv_tile_kernel<false><<<units, kNumThreads, smem_bytes, stream>>>(P);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * units);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    DV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tile_kernel<true>, P));
+  }
   DV_LAUNCH_OK();
   return kOk;
 }

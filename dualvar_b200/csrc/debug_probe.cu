@@ -103,7 +103,75 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int n_mma, int 
   }
 }
 
+// mode 2: the same loop as M=256 MMAs over CTA pairs (cta_group::2): each CTA holds its 128 rows of A and half
+// of B's rows; only the leader issues.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+mma_rate_pair_kernel(int n, int n_mma, int region, long long* out) {
+  extern __shared__ uint8_t dsm[];
+  __shared__ __align__(8) uint64_t done_bar;
+  __shared__ uint32_t tmem_slot;
+  const uint32_t raw = smem_u32(dsm);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t rank = cluster_ctarank();
+  for (int i = threadIdx.x; i < region / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(dsm + (base - raw))[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) {
+    mbar_init(&done_bar, 1);
+    fence_barrier_init();
+  }
+  if (threadIdx.x < 32) {
+    tmem_alloc2(&tmem_slot, 512);
+    tmem_relinquish2();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  long long t0 = 0, t1 = 0;
+  if (threadIdx.x == 0) {
+    t0 = clock64();
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(256, n, 0, 0);
+      const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t flags = 1u << 16;
+      const uint32_t a_bytes = 128 * 128, b_bytes = (uint32_t)(n / 2) * 128;
+      const uint32_t pair = a_bytes + ((b_bytes + 1023u) & ~1023u);
+      const uint32_t span = (uint32_t)region / pair * pair;
+      uint32_t off = 0;
+      for (int i = 0; i < n_mma; i += 4) {
+        const uint32_t a = flags | ((base + off) >> 4);
+        const uint32_t b = flags | ((base + off + a_bytes) >> 4);
+        umma2_bf16_lohi(tmem, a, b, hi, idesc, i > 0);
+        umma2_bf16_lohi(tmem, a + 2, b + 2, hi, idesc, 1);
+        umma2_bf16_lohi(tmem, a + 4, b + 4, hi, idesc, 1);
+        umma2_bf16_lohi(tmem, a + 6, b + 6, hi, idesc, 1);
+        off += pair;
+        if (off >= span) off = 0;
+      }
+      t1 = clock64();
+      umma2_commit_both(&done_bar);
+    }
+    mbar_wait(&done_bar, 0);
+    const long long t2 = clock64();
+    out[blockIdx.x * 2] = t1 - t0;
+    out[blockIdx.x * 2 + 1] = t2 - t0;
+  }
+  tc_fence_before_sync();
+  cluster_sync_all();
+  if (threadIdx.x < 32) {
+    tc_fence_after_sync();
+    tmem_dealloc2(tmem, 512);
+  }
+}
+
 int mma_rate(int n, int n_mma, int region, int mode, long long* out, int grid, cudaStream_t stream) {
+  if (mode == 2) {
+    if (n < 32 || n > 256 || (n & 15)) return fail(kBadArg, "mma_rate: bad N for cta_group::2");
+    DV_CUDA_OK(cudaFuncSetAttribute(mma_rate_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    mma_rate_pair_kernel<<<grid & ~1, 128, region + 1024, stream>>>(n, n_mma, region, out);
+    DV_LAUNCH_OK();
+    return kOk;
+  }
   if (n < 16 || n > 256 || (n & 15) || region < 64 * 1024 || region > 200 * 1024) return fail(kBadArg, "mma_rate: bad arguments");
   DV_CUDA_OK(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   mma_rate_kernel<<<grid, 128, region + 1024, stream>>>(n, n_mma, region, mode, out);

@@ -159,6 +159,118 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
       : "memory");
 }
 
+// ---------------------------------------------------------------- CTA pairs (cta_group::2)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  // default semantics (.release.cta) as for a local arrive: what the consumer must observe are this thread's
+  // tcgen05.ld results, which tcgen05.fence::before_thread_sync orders; a cluster-scope release costs > 1000 cycles
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// M=256 MMA over a CTA pair: issued by one thread of the leader CTA (cluster rank 0); each CTA supplies its
+// 128 rows of A and its half of B's N rows at the same shared-memory offsets.
+__device__ __forceinline__ void umma2_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive on the mbarrier at the same shared-memory offset in both CTAs of the pair when all previously issued
+// MMAs have completed.
+__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+// TMA loads issued by either CTA of a pair; the mbarrier (complete_tx) may live in the other CTA.
+__device__ __forceinline__ void tma2_load_3d(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
+                                             int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_5d(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
+                                             int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+      "r"(c4)
+      : "memory");
+}
+
+// Single-CTA / CTA-pair dispatch used by conv_tile_kernel<kPair>. `bar_addr` is a 32-bit shared-window address
+// (shared::cta, or shared::cluster of the leader CTA in pair mode).
+template <bool kPair>
+__device__ __forceinline__ void tma_load_3d_to(void* dst, const CUtensorMap* m, uint32_t bar_addr, int c0, int c1,
+                                               int c2) {
+  if (kPair) {
+    tma2_load_3d(dst, m, bar_addr, c0, c1, c2);
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+  }
+}
+template <bool kPair>
+__device__ __forceinline__ void tma_load_5d_to(void* dst, const CUtensorMap* m, uint32_t bar_addr, int c0, int c1,
+                                               int c2, int c3, int c4) {
+  if (kPair) {
+    tma2_load_5d(dst, m, bar_addr, c0, c1, c2, c3, c4);
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+  }
+}
+template <bool kPair>
+__device__ __forceinline__ void umma_issue(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi,
+                                           uint32_t idesc, uint32_t accumulate) {
+  if (kPair) umma2_bf16_lohi(tmem_d, a_lo, b_lo, hi, idesc, accumulate);
+  else umma_bf16_lohi(tmem_d, a_lo, b_lo, hi, idesc, accumulate);
+}
+template <bool kPair>
+__device__ __forceinline__ void umma_commit_to(uint64_t* bar) {
+  if (kPair) umma2_commit_both(bar);
+  else umma_commit(bar);
+}
+
 // 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread (lane i = TMEM lane base+i).
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
@@ -197,6 +309,16 @@ __device__ __forceinline__ uint32_t ldg_u32_pred(const void* ptr, bool ok) {
   asm volatile(
       "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b32 %0, 0;\n\t@q ld.global.nc.b32 %0, [%1];\n\t}"
       : "=r"(v)
+      : "l"(ptr), "r"(static_cast<int>(ok)));
+  return v;
+}
+
+__device__ __forceinline__ uint4 ldg_u128_pred(const void* ptr, bool ok) {
+  uint4 v;
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\tmov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\tmov.b32 %2, 0;\n\tmov.b32 %3, 0;\n\t"
+      "@q ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];\n\t}"
+      : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
       : "l"(ptr), "r"(static_cast<int>(ok)));
   return v;
 }

@@ -212,7 +212,7 @@ int dv_sgd_momentum_step(const int64_t* chunk_table, int n_chunks, float lr, flo
                          int first_step, void* stream);
 
 /* debug (tests/diag only): per-CTA role cycle counters of the next conv_tile_kernel launches are written to
- * buf [148][8] (producer total/wait, MMA total/wait-data/wait-accumulator, epilogue total/wait, tiles); NULL = off */
+ * buf [148][16] (producer total/wait, MMA total/wait-data/wait-accumulator, epilogue total/wait, tiles, epilogue phases); NULL = off */
 int dv_debug_set_conv_profile(int64_t* buf);
 /* debug probe (tests only): TMA tensor map with overlapping windows */
 int dv_debug_probe_overlap_tmap(const void* src, void* out, int c1, void* stream);

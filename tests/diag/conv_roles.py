@@ -13,7 +13,7 @@ LAYERS = [("fprop temporal 144->64", "f", (N, 16, 56, 56, 144, 64, (3, 1, 1), (1
           ("dgrad+bnred spatial 64->144", "r", (N, 16, 56, 56, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1))),
           ("fprop temporal 83->64", "f", (N, 16, 56, 56, 83, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0))),
           ("fprop spatial 128->288", "f", (N, 8, 28, 28, 128, 288, (1, 3, 3), (1, 1, 1), (0, 1, 1)))]
-prof = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
+prof = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
 for name, kind, (n, t, h, w, ci, co, k, s, p) in LAYERS:
     g = K.make_geom(n, t, h, w, ci, co, k, s, p)
     x = torch.randn(n, t, h, w, g.Cin_p, device=dev).bfloat16()
@@ -36,9 +36,13 @@ for name, kind, (n, t, h, w, ci, co, k, s, p) in LAYERS:
     _lib.load().dv_debug_set_conv_profile(ctypes.c_void_p(prof.data_ptr()))
     run(); torch.cuda.synchronize()
     _lib.load().dv_debug_set_conv_profile(None)
-    P = prof.view(148, 8).double()
+    P = prof.view(148, 16).double()
     tiles = P[:, 7].clamp_min(1)
-    per = lambda i: (P[:, i] / tiles).mean().item()
+    live = P[:, 7] > 0
+    per = lambda i: (P[live, i] / tiles[live]).mean().item()
+    lead = P[:, 2] > 0          # CTAs that issued MMAs (every CTA, or the pair leaders)
+    perl = lambda i: (P[lead, i] / tiles[lead]).mean().item()
     fl = 2.0 * n * g.To * g.Ho * g.Wo * co * ci * k[0] * k[1] * k[2]
     print(f"{name}: {ms:.3f} ms {fl/ms/1e9:.0f} TF/s | cycles/tile: producer {per(0):.0f} (wait-free-stage {per(1):.0f}) | "
-          f"mma {per(2):.0f} (wait-data {per(3):.0f}, wait-acc {per(4):.0f}) | epilogue {per(5):.0f} (wait-acc {per(6):.0f}) | tiles/CTA {tiles.mean().item():.0f}", flush=True)
+          f"mma {perl(2):.0f} (wait-data {perl(3):.0f}, wait-acc {perl(4):.0f}) | epilogue {per(5):.0f} (wait-acc {per(6):.0f}: y-ld {per(8):.0f} "
+          f"tmem-ld {per(9):.0f} cvt+sts {per(10):.0f} bar {per(11):.0f} store {per(12):.0f} colsum {per(13):.0f}) | tiles/CTA {tiles.mean().item():.0f}", flush=True)

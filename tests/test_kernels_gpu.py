@@ -228,6 +228,8 @@ def test_fused_sgd_matches_torch_sgd():
                 grp["lr"] = 0.0003
         ours.step(); ref.step()
         for p, q in zip(ps, qs):
-            torch.testing.assert_close(p, q, rtol=1e-6, atol=1e-7)
+            # fp32 both sides; the kernel contracts g + wd*p and mu*buf + g into FMAs (torch's foreach ops round
+            # each product), so results agree to an ulp or two of the operands, not bit for bit
+            torch.testing.assert_close(p, q, rtol=1e-5, atol=1e-6)
     for p, q in zip(ps, qs):
-        torch.testing.assert_close(ours.state[p]["momentum_buffer"], ref.state[q]["momentum_buffer"], rtol=1e-6, atol=1e-7)
+        torch.testing.assert_close(ours.state[p]["momentum_buffer"], ref.state[q]["momentum_buffer"], rtol=1e-5, atol=1e-6)
