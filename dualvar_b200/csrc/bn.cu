@@ -36,6 +36,27 @@ __device__ __forceinline__ Vec8 load8(const __nv_bfloat16* p) {
   return r;
 }
 
+// streaming 16-byte accesses: every element of these passes is touched once
+__device__ __forceinline__ uint4 ldcs16(const __nv_bfloat16* p) { return __ldcs(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ Vec8 unpack8(const uint4& u) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+  Vec8 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    r.v[2 * i] = f.x;
+    r.v[2 * i + 1] = f.y;
+  }
+  return r;
+}
+__device__ __forceinline__ void stcs8(__nv_bfloat16* p, const Vec8& r) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(r.v[2 * i], r.v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
 __device__ __forceinline__ void store8(__nv_bfloat16* p, const Vec8& r) {
   uint4 u;
   __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
@@ -103,33 +124,52 @@ struct ApplyArgs {
   int relu;
 };
 
+// kRows independent rows per thread and iteration: all their 16-byte loads are issued before the first use, which
+// is what keeps enough bytes in flight per SM to reach the HBM rate (tests/diag/bn_bw.py).
+template <bool kY2, bool kRes, int kRows>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const ApplyArgs a) {
   const int G = a.Cp >> 3;
   for (int cg = threadIdx.x; cg < G; cg += blockDim.x) {
     const Vec8 s1 = loadf8(a.ss1 + cg * 8), b1 = loadf8(a.ss1 + a.Cp + cg * 8);
     Vec8 s2, b2;
-    if (a.y2) { s2 = loadf8(a.ss2 + cg * 8); b2 = loadf8(a.ss2 + a.Cp + cg * 8); }
-    for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < a.rows;
-         r += (long long)gridDim.x * blockDim.y) {
-      const long long off = r * a.Cp + cg * 8;
-      Vec8 x = load8(a.y1 + off);
+    if (kY2) { s2 = loadf8(a.ss2 + cg * 8); b2 = loadf8(a.ss2 + a.Cp + cg * 8); }
+    const long long stride = (long long)gridDim.x * blockDim.y;
+    for (long long r0 = (long long)blockIdx.x * blockDim.y + threadIdx.y; r0 < a.rows; r0 += kRows * stride) {
+      uint4 u1[kRows], u2[kRows], u3[kRows];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) x.v[i] = fmaf(x.v[i], s1.v[i], b1.v[i]);
-      if (a.y2) {
-        const Vec8 t = load8(a.y2 + off);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) x.v[i] += fmaf(t.v[i], s2.v[i], b2.v[i]);
+      for (int k = 0; k < kRows; ++k) {
+        const long long r = r0 + k * stride;
+        if (r < a.rows) {
+          const long long off = r * a.Cp + cg * 8;
+          u1[k] = ldcs16(a.y1 + off);
+          if (kY2) u2[k] = ldcs16(a.y2 + off);
+          if (kRes) u3[k] = ldcs16(a.res + off);
+        }
       }
-      if (a.res) {
-        const Vec8 t = load8(a.res + off);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) x.v[i] += t.v[i];
-      }
-      if (a.relu) {
+      for (int k = 0; k < kRows; ++k) {
+        const long long r = r0 + k * stride;
+        if (r < a.rows) {
+          Vec8 x = unpack8(u1[k]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) x.v[i] = fmaxf(x.v[i], 0.f);
+          for (int i = 0; i < 8; ++i) x.v[i] = fmaf(x.v[i], s1.v[i], b1.v[i]);
+          if (kY2) {
+            const Vec8 t = unpack8(u2[k]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x.v[i] += fmaf(t.v[i], s2.v[i], b2.v[i]);
+          }
+          if (kRes) {
+            const Vec8 t = unpack8(u3[k]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x.v[i] += t.v[i];
+          }
+          if (a.relu) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x.v[i] = fmaxf(x.v[i], 0.f);
+          }
+          stcs8(a.out + r * a.out_ld + a.out_coff + cg * 8, x);
+        }
       }
-      store8(a.out + r * a.out_ld + a.out_coff + cg * 8, x);
     }
   }
 }
@@ -151,6 +191,8 @@ struct BwdArgs {
   __nv_bfloat16* g_out;  // apply: optional masked gradient (residual branch), dense [rows][Cp]
 };
 
+// kMask: 0 = no ReLU, 1 = mask recomputed from (scale, shift, y), 2 = mask read from `out`
+template <bool kD2, int kMask, int kRows>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BwdArgs a) {
   extern __shared__ float red[];  // [blockDim.y][2][8*blockDim.x]
   const int G = a.Cp >> 3;
@@ -162,45 +204,44 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BwdArgs a) {
     for (int i = 0; i < 8; ++i) { sg[i] = 0.f; sgy[i] = 0.f; }
     if (cg < G) {
       Vec8 fs, fb;
-      if (a.ss) { fs = loadf8(a.ss + cg * 8); fb = loadf8(a.ss + a.Cp + cg * 8); }
+      if (kMask == 1) { fs = loadf8(a.ss + cg * 8); fb = loadf8(a.ss + a.Cp + cg * 8); }
       const long long stride = (long long)gridDim.x * blockDim.y;
-      auto masked = [&](Vec8 d, const Vec8& d2, const Vec8& yv, const Vec8& o) {
-        if (a.dout2) {
+      for (long long r0 = (long long)blockIdx.x * blockDim.y + threadIdx.y; r0 < a.rows; r0 += kRows * stride) {
+        uint4 ud[kRows], uy[kRows], ue[kRows], uo[kRows];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) d.v[i] += d2.v[i];
-        }
-        if (a.relu) {
-          if (a.ss) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) d.v[i] = fmaf(yv.v[i], fs.v[i], fb.v[i]) > 0.f ? d.v[i] : 0.f;
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) d.v[i] = o.v[i] > 0.f ? d.v[i] : 0.f;
+        for (int k = 0; k < kRows; ++k) {
+          const long long r = r0 + k * stride;
+          if (r < a.rows) {
+            const long long oo = r * a.o_ld + a.o_coff + cg * 8, yo = r * a.Cp + cg * 8;
+            ud[k] = ldcs16(a.dout + oo);
+            uy[k] = ldcs16(a.y + yo);
+            if (kD2) ue[k] = ldcs16(a.dout2 + yo);
+            if (kMask == 2) uo[k] = ldcs16(a.out + oo);
           }
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { sg[i] += d.v[i]; sgy[i] = fmaf(d.v[i], yv.v[i], sgy[i]); }
-      };
-      const bool need_out = a.relu && !a.ss;
-      long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y;
-      for (; r + stride < a.rows; r += 2 * stride) {   // two independent rows per iteration
-        const long long oa = r * a.o_ld + a.o_coff + cg * 8, ob = (r + stride) * a.o_ld + a.o_coff + cg * 8;
-        const long long ya = r * a.Cp + cg * 8, yb = (r + stride) * a.Cp + cg * 8;
-        const Vec8 d0 = load8(a.dout + oa), d1 = load8(a.dout + ob);
-        const Vec8 y0 = load8(a.y + ya), y1 = load8(a.y + yb);
-        Vec8 e0 = d0, e1 = d1, o0 = d0, o1 = d1;
-        if (a.dout2) { e0 = load8(a.dout2 + ya); e1 = load8(a.dout2 + yb); }
-        if (need_out) { o0 = load8(a.out + oa); o1 = load8(a.out + ob); }
-        masked(d0, e0, y0, o0);
-        masked(d1, e1, y1, o1);
-      }
-      if (r < a.rows) {
-        const long long oa = r * a.o_ld + a.o_coff + cg * 8, ya = r * a.Cp + cg * 8;
-        const Vec8 d0 = load8(a.dout + oa), y0 = load8(a.y + ya);
-        Vec8 e0 = d0, o0 = d0;
-        if (a.dout2) e0 = load8(a.dout2 + ya);
-        if (need_out) o0 = load8(a.out + oa);
-        masked(d0, e0, y0, o0);
+        for (int k = 0; k < kRows; ++k) {
+          const long long r = r0 + k * stride;
+          if (r < a.rows) {
+            Vec8 d = unpack8(ud[k]);
+            const Vec8 yv = unpack8(uy[k]);
+            if (kD2) {
+              const Vec8 e = unpack8(ue[k]);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) d.v[i] += e.v[i];
+            }
+            if (kMask == 1) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) d.v[i] = fmaf(yv.v[i], fs.v[i], fb.v[i]) > 0.f ? d.v[i] : 0.f;
+            } else if (kMask == 2) {
+              const Vec8 o = unpack8(uo[k]);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) d.v[i] = o.v[i] > 0.f ? d.v[i] : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { sg[i] += d.v[i]; sgy[i] = fmaf(d.v[i], yv.v[i], sgy[i]); }
+          }
+        }
       }
     }
     float* mine = red + (size_t)threadIdx.y * 16 * GT;
@@ -251,55 +292,55 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums_local,
   coef[2 * Cp + c] = (float)Cc;
 }
 
+template <bool kD2, int kMask, bool kGout, int kRows>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdArgs a) {
   const int G = a.Cp >> 3;
   for (int cg = threadIdx.x; cg < G; cg += blockDim.x) {
     const Vec8 A = loadf8(a.coef + cg * 8), B = loadf8(a.coef + a.Cp + cg * 8),
                C = loadf8(a.coef + 2 * a.Cp + cg * 8);
     Vec8 fs, fb;
-    if (a.ss) { fs = loadf8(a.ss + cg * 8); fb = loadf8(a.ss + a.Cp + cg * 8); }
+    if (kMask == 1) { fs = loadf8(a.ss + cg * 8); fb = loadf8(a.ss + a.Cp + cg * 8); }
     const long long stride = (long long)gridDim.x * blockDim.y;
-    const bool need_out = a.relu && !a.ss;
-    auto finish = [&](long long r, Vec8 d, const Vec8& d2, const Vec8& yv, const Vec8& o) {
-      const long long off = r * a.Cp + cg * 8;
-      if (a.dout2) {
+    for (long long r0 = (long long)blockIdx.x * blockDim.y + threadIdx.y; r0 < a.rows; r0 += kRows * stride) {
+      uint4 ud[kRows], uy[kRows], ue[kRows], uo[kRows];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) d.v[i] += d2.v[i];
-      }
-      if (a.relu) {
-        if (a.ss) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) d.v[i] = fmaf(yv.v[i], fs.v[i], fb.v[i]) > 0.f ? d.v[i] : 0.f;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) d.v[i] = o.v[i] > 0.f ? d.v[i] : 0.f;
+      for (int k = 0; k < kRows; ++k) {
+        const long long r = r0 + k * stride;
+        if (r < a.rows) {
+          const long long oo = r * a.o_ld + a.o_coff + cg * 8, yo = r * a.Cp + cg * 8;
+          ud[k] = ldcs16(a.dout + oo);
+          uy[k] = ldcs16(a.y + yo);
+          if (kD2) ue[k] = ldcs16(a.dout2 + yo);
+          if (kMask == 2) uo[k] = ldcs16(a.out + oo);
         }
       }
-      if (a.g_out) store8(a.g_out + off, d);
-      Vec8 res;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) res.v[i] = fmaf(A.v[i], d.v[i], fmaf(B.v[i], yv.v[i], C.v[i]));
-      store8(a.dy + off, res);
-    };
-    long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y;
-    for (; r + stride < a.rows; r += 2 * stride) {   // two independent rows per iteration
-      const long long oa = r * a.o_ld + a.o_coff + cg * 8, ob = (r + stride) * a.o_ld + a.o_coff + cg * 8;
-      const long long ya = r * a.Cp + cg * 8, yb = (r + stride) * a.Cp + cg * 8;
-      const Vec8 d0 = load8(a.dout + oa), d1 = load8(a.dout + ob);
-      const Vec8 y0 = load8(a.y + ya), y1 = load8(a.y + yb);
-      Vec8 e0 = d0, e1 = d1, o0 = d0, o1 = d1;
-      if (a.dout2) { e0 = load8(a.dout2 + ya); e1 = load8(a.dout2 + yb); }
-      if (need_out) { o0 = load8(a.out + oa); o1 = load8(a.out + ob); }
-      finish(r, d0, e0, y0, o0);
-      finish(r + stride, d1, e1, y1, o1);
-    }
-    if (r < a.rows) {
-      const long long oa = r * a.o_ld + a.o_coff + cg * 8, ya = r * a.Cp + cg * 8;
-      const Vec8 d0 = load8(a.dout + oa), y0 = load8(a.y + ya);
-      Vec8 e0 = d0, o0 = d0;
-      if (a.dout2) e0 = load8(a.dout2 + ya);
-      if (need_out) o0 = load8(a.out + oa);
-      finish(r, d0, e0, y0, o0);
+      for (int k = 0; k < kRows; ++k) {
+        const long long r = r0 + k * stride;
+        if (r < a.rows) {
+          const long long off = r * a.Cp + cg * 8;
+          Vec8 d = unpack8(ud[k]);
+          const Vec8 yv = unpack8(uy[k]);
+          if (kD2) {
+            const Vec8 e = unpack8(ue[k]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d.v[i] += e.v[i];
+          }
+          if (kMask == 1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d.v[i] = fmaf(yv.v[i], fs.v[i], fb.v[i]) > 0.f ? d.v[i] : 0.f;
+          } else if (kMask == 2) {
+            const Vec8 o = unpack8(uo[k]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d.v[i] = o.v[i] > 0.f ? d.v[i] : 0.f;
+          }
+          if (kGout) store8(a.g_out + off, d);
+          Vec8 res;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) res.v[i] = fmaf(A.v[i], d.v[i], fmaf(B.v[i], yv.v[i], C.v[i]));
+          store8(a.dy + off, res);
+        }
+      }
     }
   }
 }
@@ -353,7 +394,10 @@ int bn_apply(const void* y1, const float* ss1, const void* y2, const float* ss2,
   a.rows = rows; a.Cp = Cp; a.out_ld = out_ld; a.out_coff = out_coff; a.relu = relu;
   dim3 block; int grid;
   row_block(Cp, rows, &block, &grid);
-  bn_apply_kernel<<<grid, block, 0, stream>>>(a);
+  if (a.y2 && a.res) bn_apply_kernel<true, true, 2><<<grid, block, 0, stream>>>(a);
+  else if (a.y2) bn_apply_kernel<true, false, 2><<<grid, block, 0, stream>>>(a);
+  else if (a.res) bn_apply_kernel<false, true, 4><<<grid, block, 0, stream>>>(a);
+  else bn_apply_kernel<false, false, 8><<<grid, block, 0, stream>>>(a);
   DV_LAUNCH_OK();
   return kOk;
 }
@@ -369,7 +413,14 @@ int bn_bwd_reduce(const void* dout, const void* dout2, const void* out, const vo
   dim3 block; int grid;
   row_block(Cp, rows, &block, &grid);
   const size_t smem = (size_t)block.y * 16 * block.x * sizeof(float);
-  bn_bwd_reduce_kernel<<<grid, block, smem, stream>>>(a);
+  const int mask = !relu ? 0 : (ss ? 1 : 2);
+#define DV_RED(D2, M, R) bn_bwd_reduce_kernel<D2, M, R><<<grid, block, smem, stream>>>(a)
+  if (a.dout2) {
+    if (mask == 0) DV_RED(true, 0, 2); else if (mask == 1) DV_RED(true, 1, 2); else DV_RED(true, 2, 2);
+  } else {
+    if (mask == 0) DV_RED(false, 0, 4); else if (mask == 1) DV_RED(false, 1, 4); else DV_RED(false, 2, 2);
+  }
+#undef DV_RED
   DV_LAUNCH_OK();
   return kOk;
 }
@@ -394,7 +445,16 @@ int bn_bwd_apply(const void* dout, const void* dout2, const void* out, const voi
   a.relu = relu; a.coef = coef; a.dy = (__nv_bfloat16*)dy; a.g_out = (__nv_bfloat16*)g_out;
   dim3 block; int grid;
   row_block(Cp, rows, &block, &grid);
-  bn_bwd_apply_kernel<<<grid, block, 0, stream>>>(a);
+  const int mask = !relu ? 0 : (ss ? 1 : 2);
+#define DV_APP(D2, M, GO, R) bn_bwd_apply_kernel<D2, M, GO, R><<<grid, block, 0, stream>>>(a)
+#define DV_APP_M(D2, GO, R)                                                               \
+  do {                                                                                    \
+    if (mask == 0) DV_APP(D2, 0, GO, R); else if (mask == 1) DV_APP(D2, 1, GO, R); else DV_APP(D2, 2, GO, R); \
+  } while (0)
+  if (a.dout2) { if (a.g_out) DV_APP_M(true, true, 2); else DV_APP_M(true, false, 2); }
+  else { if (a.g_out) DV_APP_M(false, true, 2); else DV_APP_M(false, false, 4); }
+#undef DV_APP_M
+#undef DV_APP
   DV_LAUNCH_OK();
   return kOk;
 }

@@ -81,10 +81,19 @@ class Context:
 
 # ----------------------------------------------------------------------------- helpers
 _weight_cache = {}
-# Fused dgrad + BN-backward reduce (dv_conv3d_dgrad_bnred_bf16). Off by default: on B200 the 4-warp epilogue of
-# conv_tile_kernel is already the bottleneck of the low-K (temporal) dgrads, so the fused column pass costs more
-# there than the separate HBM pass it removes (profiles/r01_fused_bn_reduce.txt); DV_FUSE_BN_REDUCE=1 enables it.
-FUSE_BN_REDUCE = os.environ.get("DV_FUSE_BN_REDUCE", "0") != "0"
+# Fused dgrad + BN-backward reduce (dv_conv3d_dgrad_bnred_bf16): 1 = where it pays (default), 0 = never, 2 = always.
+# The fused column pass costs the dgrad epilogue ~1500 cycles per 64-channel chunk of dx (two chunks in flight);
+# that hides behind the MMA main loop of the K-heavy (spatial / full 3-D) dgrads but not behind the temporal ones,
+# where the separate HBM pass is cheaper (profiles/r01_fused_bn_reduce.txt).
+FUSE_BN_REDUCE = int(os.environ.get("DV_FUSE_BN_REDUCE", "1"))
+
+
+def _fuse_reduce_pays(g):
+    if FUSE_BN_REDUCE != 1:
+        return FUSE_BN_REDUCE == 2
+    mma_cycles = g.taps * (g.Cout_p / 16.0) * max(g.Cin_p / 2.0, 53.0)     # per 128-position tile (tests/diag/mma_rate.py)
+    epi_cycles = -(-g.Cin_p // 64) * 1500 / 2.0
+    return mma_cycles >= 1.5 * epi_cycles
 
 
 def packed_weights(conv):
@@ -293,7 +302,7 @@ def _conv_backward(ctx, r, dy):
         ctx.add_param_grad(r.conv.bias, torch.zeros_like(r.conv.bias))
     if r.x.needs_grad:
         dx = torch.empty_like(r.x.data)
-        if FUSE_BN_REDUCE and r.x.bnred is not None and r.x.grad is None:
+        if r.x.bnred is not None and r.x.grad is None and _fuse_reduce_pays(g):
             # x = relu?(BN(y_prev)) and this is (so far) its only gradient: the dgrad epilogue also produces
             # the BN-backward sums of the layer below, saving dv_bn_bwd_reduce's pass over dx and y_prev
             rp, relu = r.x.bnred
