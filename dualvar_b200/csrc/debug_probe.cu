@@ -51,12 +51,14 @@ namespace dv {
 __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int n_mma, int region, int mode, long long* out) {
   extern __shared__ uint8_t dsm[];
   __shared__ __align__(8) uint64_t done_bar;
+  __shared__ __align__(8) uint64_t ring_bar[8];
   __shared__ uint32_t tmem_slot;
   const uint32_t raw = smem_u32(dsm);
   const uint32_t base = (raw + 1023u) & ~1023u;
   for (int i = threadIdx.x; i < region / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(dsm + (base - raw))[i] = 0x3c003c00u;
   if (threadIdx.x == 0) {
     mbar_init(&done_bar, 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&ring_bar[i], 1);
     fence_barrier_init();
   }
   if (threadIdx.x < 32) {
@@ -78,15 +80,26 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int n_mma, int 
     const uint32_t span = (mode == 1 ? (uint32_t)region - b_bytes : (uint32_t)region) / pair * pair;
     uint32_t off = 0;
     const long long t0 = clock64();
+    const int period = mode >= 16 ? (mode & 0xff) : 0;   // commit to a rotating barrier every `period` MMAs
+    const bool alt_acc = (mode & 0x100) != 0;              // switch accumulator (TMEM columns 0 / 256) at every commit
+    int since = 0, slot = 0;
+    uint32_t acc_off = 0;
     for (int i = 0; i < n_mma; i += 4) {
       const uint32_t a = flags | ((base + off) >> 4);
       const uint32_t b = flags | ((mode == 1 ? b_fixed : base + off + a_bytes) >> 4);
-      umma_bf16_lohi(tmem, a, b, hi, idesc, i > 0);
-      umma_bf16_lohi(tmem, a + 2, b + 2, hi, idesc, 1);
-      umma_bf16_lohi(tmem, a + 4, b + 4, hi, idesc, 1);
-      umma_bf16_lohi(tmem, a + 6, b + 6, hi, idesc, 1);
+      umma_bf16_lohi(tmem + acc_off, a, b, hi, idesc, i > 0);
+      umma_bf16_lohi(tmem + acc_off, a + 2, b + 2, hi, idesc, 1);
+      umma_bf16_lohi(tmem + acc_off, a + 4, b + 4, hi, idesc, 1);
+      umma_bf16_lohi(tmem + acc_off, a + 6, b + 6, hi, idesc, 1);
       off += pair;
       if (off >= span) off = 0;
+      since += 4;
+      if (period && since >= period) {
+        umma_commit(&ring_bar[slot]);
+        slot = (slot + 1) & 7;
+        since = 0;
+        if (alt_acc) acc_off ^= 256u;
+      }
     }
     const long long t1 = clock64();
     umma_commit(&done_bar);

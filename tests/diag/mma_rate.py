@@ -7,9 +7,10 @@ from dualvar_b200 import _lib
 dev = "cuda:0"
 out = torch.zeros(148 * 2, dtype=torch.int64, device=dev)
 n_mma = 4096
-for grid in (2, 148):
-    for mode in (0, 2):
-        for n in (64, 96, 128, 144, 192, 256):
+for grid in (148,):
+    # 0x2pp: commit to a rotating mbarrier every pp MMAs; 0x3pp: and switch accumulator at every commit
+    for mode in (0, 0x204, 0x20C, 0x224, 0x30C, 0x324):
+        for n in (64, 144, 256):
             for region in (160 * 1024,):
                 _lib.call("dv_debug_mma_rate", n, n_mma, region, mode, _lib.ptr(out), grid, _lib.stream_ptr())
                 torch.cuda.synchronize()
@@ -19,6 +20,6 @@ for grid in (2, 148):
                 if mode == 2:
                     c = c[0::2]      # leader CTAs
                     issue, total = c[:, 0].mean().item() / n_mma, c[:, 1].mean().item() / n_mma
-                print(f"grid {grid:3d} mode {mode} N={n:3d} region {region//1024:3d}K: issue {issue:6.1f} cyc/MMA, "
+                print(f"grid {grid:3d} mode {mode:#x} N={n:3d} region {region//1024:3d}K: issue {issue:6.1f} cyc/MMA, "
                       f"complete {total:6.1f} cyc/MMA (ideal {n/2:.0f}) -> {bytes_per/total:5.1f} B/clk operand fetch, "
                       f"{n/2/total*100:4.0f}% of peak", flush=True)
