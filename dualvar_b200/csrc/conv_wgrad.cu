@@ -16,6 +16,8 @@
 
 #include <stdlib.h>
 
+#include <algorithm>
+
 namespace dv {
 
 constexpr int kWgThreads = 192;
@@ -37,12 +39,15 @@ struct alignas(64) WgradParams {
   int stages;
   float* dw;  // [Cout_p][taps_total][Cin_p]
   int cin_p, cout_p, taps_total;
-  // halo mode (temporal-only filters, stride 1): ONE X box with a t-halo per 64-channel chunk; the unit
-  // (tap, chunk) is the view of that box shifted by whole 8-row groups. All units live in one CTA.
+  // halo mode (stride 1): X boxes carry a halo along the filter's slow dimension (t for temporal filters, h for
+  // spatial ones); the unit (tap, chunk) is the view of its box shifted by whole 8-row groups, so one box feeds
+  // kt (or kh) units. Unit groups (= CTAs along x) own whole boxes.
   int halo;
   int x_box_bytes;         // bytes of one halo box (multiple of 1024)
-  int8_t x_dt, x_dh, x_dw; // origin offset of the halo box
-  int unit_off[16];        // start of each unit inside the stage, in 16-byte units
+  int n_groups;            // halo mode: unit groups
+  int8_t grp_unit0[9], grp_box0[9];   // first unit / first box of each group (+ end sentinel)
+  int8_t box_dt[16], box_dh[16], box_dw[16], box_kc[16];   // halo box origin offset and 64-channel chunk
+  int unit_off[16];        // start of each unit inside its group's stage, in 16-byte units
   int16_t unit_widx[16];   // weight tap index of each unit
   int16_t unit_kc[16];     // 64-channel chunk of each unit
 };
@@ -59,8 +64,10 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
   const int lane = threadIdx.x & 31;
   const int group = blockIdx.x / p.n_tiles;
   const int n_tile = blockIdx.x % p.n_tiles;
-  const int unit0 = group * p.units_per_group;
-  const int nu = min(p.units_per_group, p.total_units - unit0);
+  const int unit0 = p.halo ? p.grp_unit0[group] : group * p.units_per_group;
+  const int nu = p.halo ? p.grp_unit0[group + 1] - unit0 : min(p.units_per_group, p.total_units - unit0);
+  const int box0 = p.halo ? p.grp_box0[group] : 0;
+  const int nbox = p.halo ? p.grp_box0[group + 1] - box0 : 0;
   const int npairs = (nu + 1) >> 1;
   const int bn = (n_tile == p.n_tiles - 1) ? p.last_n : p.block_n;
   const int nbx = (bn + 63) >> 6;  // dY boxes
@@ -71,7 +78,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
-  const int a_bytes = p.halo ? p.k_chunks * p.x_box_bytes : p.units_per_group * kBoxBytes;
+  const int a_bytes = p.halo ? p.units_per_group * p.x_box_bytes : p.units_per_group * kBoxBytes;   // halo: units_per_group = max boxes per group
   const int b_bytes = ((p.block_n + 63) >> 6) * kBoxBytes;
   const int stage_bytes = a_bytes + b_bytes;
 
@@ -98,7 +105,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
     const bool issuer = elect_one();
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t tx = p.halo ? (uint32_t)(p.k_chunks * p.x_box_bytes + nbx * kBoxBytes)
+    const uint32_t tx = p.halo ? (uint32_t)(nbox * p.x_box_bytes + nbx * kBoxBytes)
                                : (uint32_t)((nu + nbx) * kBoxBytes);
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       int m_id = tile;
@@ -115,9 +122,9 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
         for (int j = 0; j < nbx; ++j)
           tma_load_5d(b_s + j * kBoxBytes, &p.dy_map, &full_bar[stage], n_tile * p.block_n + j * 64, w0, h0, t0, n0);
         if (p.halo) {
-          for (int kc = 0; kc < p.k_chunks; ++kc)
-            tma_load_5d(a_s + kc * p.x_box_bytes, &p.a_map[0], &full_bar[stage], kc * 64, w0 + p.x_dw, h0 + p.x_dh,
-                        t0 + p.x_dt, n0);
+          for (int b = 0; b < nbox; ++b)
+            tma_load_5d(a_s + b * p.x_box_bytes, &p.a_map[0], &full_bar[stage], p.box_kc[box0 + b] * 64,
+                        w0 + p.box_dw[box0 + b], h0 + p.box_dh[box0 + b], t0 + p.box_dt[box0 + b], n0);
         } else {
           for (int i = 0; i < nu; ++i) {
             const int u = unit0 + i;
@@ -155,8 +162,8 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
           if (p.halo) {
             // unit = shifted view of a halo box; the pair's second 64-channel group starts (LBO) wherever the
             // next unit starts (possibly overlapping the first)
-            const uint32_t o0 = (uint32_t)p.unit_off[2 * pr];
-            const uint32_t o1 = (2 * pr + 1 < nu) ? (uint32_t)p.unit_off[2 * pr + 1] : o0 + 64u;
+            const uint32_t o0 = (uint32_t)p.unit_off[unit0 + 2 * pr];
+            const uint32_t o1 = (2 * pr + 1 < nu) ? (uint32_t)p.unit_off[unit0 + 2 * pr + 1] : o0 + 64u;
             al = ((o1 - o0) << 16) | (base_enc + (uint32_t)stage * stage_enc + o0);
           } else {
             al = a_lo + (uint32_t)pr * (2 * kBoxBytes >> 4);
@@ -189,8 +196,8 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
       if (unit_ok) {
         int kc;
         if (p.halo) {
-          tapw = p.unit_widx[i];
-          kc = p.unit_kc[i];
+          tapw = p.unit_widx[unit0 + i];
+          kc = p.unit_kc[unit0 + i];
         } else {
           const int u = unit0 + i;
           const int tap = u / p.k_chunks;
@@ -261,8 +268,11 @@ static int wgrad_launch(WgradParams& P, int ntaps, int cin_p, int cout_p, int ta
   int upg = max_pairs * 2;
   int stage_bytes;
   if (P.halo) {
-    upg = P.total_units;   // caller checked that all units fit one CTA
-    stage_bytes = P.k_chunks * P.x_box_bytes + nbx * kBoxBytes;
+    // caller built the groups; units_per_group carries the largest number of boxes of a group (smem sizing)
+    int max_boxes = 0;
+    for (int gi = 0; gi < P.n_groups; ++gi) max_boxes = std::max(max_boxes, P.grp_box0[gi + 1] - P.grp_box0[gi]);
+    upg = max_boxes;
+    stage_bytes = max_boxes * P.x_box_bytes + nbx * kBoxBytes;
   } else {
     if (upg > kWgMaxUnits) upg = kWgMaxUnits;
     // keep at least 3 stages in shared memory
@@ -271,7 +281,7 @@ static int wgrad_launch(WgradParams& P, int ntaps, int cin_p, int cout_p, int ta
     stage_bytes = (upg + nbx) * kBoxBytes;
   }
   P.units_per_group = upg;
-  const int groups = ceil_div(P.total_units, upg);
+  const int groups = P.halo ? P.n_groups : ceil_div(P.total_units, upg);
   P.stages = (kWgSmemBudget - 1024) / stage_bytes;
   if (P.stages > 8) P.stages = 8;
   if (P.stages < 2) return fail(kUnsupported, "wgrad: stage too large for shared memory");
@@ -308,38 +318,61 @@ int conv_wgrad_bf16(const void* x, const void* dy, float* dw, const ConvGeom& c,
     static int halo_env = -1;
     if (halo_env < 0) { const char* e = getenv("DV_CONV_HALO"); halo_env = e ? atoi(e) : 1; }
     const int k_chunks = ceil_div(c.Cin_p, 64);
-    const int units = c.kt * k_chunks;
+    const int units = taps_total * k_chunks;
     const int bn = c.Cout_p <= 256 ? round_up(c.Cout_p, 16) : 256;
     const int acc_stride = round_up(bn, 32);
-    if (halo_env && c.kt > 1 && c.kh == 1 && c.kw == 1 && c.st == 1 && c.sh == 1 && c.sw == 1 && c.Cout_p <= 256 &&
-        units <= 16 && ceil_div(units, 2) * acc_stride <= 512) {
-      // tile (tn=1, tt, th, tw) of 64 positions with th*tw a multiple of 8 rows; minimise padded volume x halo
+    const int max_pairs = 512 / acc_stride;
+    const bool temporal = c.kt > 1 && c.kh == 1 && c.kw == 1;
+    const bool spatial = c.kt == 1 && c.kh > 1;
+    // halo taps: the filter dimension that shifts by whole 8-row groups (t planes / h rows of 8 positions);
+    // a box feeds `span` units, so a group must be able to hold at least one box worth of units
+    const int span = temporal ? c.kt : c.kh;
+    if (halo_env && (temporal || spatial) && c.st == 1 && c.sh == 1 && c.sw == 1 && c.Cout_p <= 256 && units <= 16 &&
+        span <= 2 * max_pairs) {
       TileGeom& g = P.g;
-      double best = 1e30; int blw = 3, blh = 0, blt = 3;
-      for (int a = 0; a <= 6; ++a)
-        for (int b = 0; a + b <= 6; ++b) {
-          if (a + b < 3) continue;
-          const int cc = 6 - a - b;
-          const int tw = 1 << a, th = 1 << b, tt = 1 << cc;
-          const double vol = (double)round_up(c.Wo, tw) * round_up(c.Ho, th) * round_up(c.To, tt);
-          const double cost = vol * (double)(tt + c.kt - 1) / tt * (1.0 + 0.02 * (6 - a));
-          if (cost < best) { best = cost; blw = a; blh = b; blt = cc; }
-        }
-      g.lw = blw; g.lh = blh; g.lt = blt; g.ln = 0;
-      const int tt = 1 << g.lt, thw = (1 << g.lh) * (1 << g.lw);
-      const int x_box_bytes = (tt + c.kt - 1) * thw * 128;
+      int x_rows;   // rows (positions) of one halo box
+      if (temporal) {
+        // tile (tn=1, tt, th, tw) of 64 positions with th*tw a multiple of 8 rows; minimise padded volume x halo
+        double best = 1e30; int blw = 3, blh = 0, blt = 3;
+        for (int a = 0; a <= 6; ++a)
+          for (int b = 0; a + b <= 6; ++b) {
+            if (a + b < 3) continue;
+            const int cc = 6 - a - b;
+            const int tw = 1 << a, th = 1 << b, tt = 1 << cc;
+            const double vol = (double)round_up(c.Wo, tw) * round_up(c.Ho, th) * round_up(c.To, tt);
+            const double cost = vol * (double)(tt + c.kt - 1) / tt * (1.0 + 0.02 * (6 - a));
+            if (cost < best) { best = cost; blw = a; blh = b; blt = cc; }
+          }
+        g.lw = blw; g.lh = blh; g.lt = blt; g.ln = 0;
+        x_rows = ((1 << g.lt) + c.kt - 1) << (g.lh + g.lw);
+      } else {
+        // tile (1, 1, 8, 8): an h shift of the filter is a shift by one 8-row group; one box per (kw, chunk)
+        g.lw = 3; g.lh = 3; g.lt = 0; g.ln = 0;
+        x_rows = (8 + c.kh - 1) * 8;
+      }
+      const double waste = (double)round_up(c.Wo, 1 << g.lw) * round_up(c.Ho, 1 << g.lh) * round_up(c.To, 1 << g.lt) /
+                           ((double)c.Wo * c.Ho * c.To);
+      const int x_box_bytes = x_rows * 128;
       const int nbx = ceil_div(bn, 64);
-      if (3 * (k_chunks * x_box_bytes + nbx * kBoxBytes) <= kWgSmemBudget - 1024) {
+      // boxes: temporal -> one per chunk; spatial -> one per (kw, chunk). Units of a box are consecutive.
+      const int n_boxes = temporal ? k_chunks : c.kw * k_chunks;
+      // groups: whole boxes, at most 2*max_pairs units each
+      int boxes_per_group = std::max(1, (2 * max_pairs) / span);
+      while (boxes_per_group > 1 && 3 * (boxes_per_group * x_box_bytes + nbx * kBoxBytes) > kWgSmemBudget - 1024)
+        --boxes_per_group;
+      const int n_groups = ceil_div(n_boxes, boxes_per_group);
+      if ((temporal || waste <= 1.16) && n_boxes <= 16 && n_groups <= 8 &&
+          3 * (std::min(boxes_per_group, n_boxes) * x_box_bytes + nbx * kBoxBytes) <= kWgSmemBudget - 1024) {
         P.halo = 1;
         P.x_box_bytes = x_box_bytes;
-        P.x_dt = (int8_t)(-c.pt); P.x_dh = 0; P.x_dw = 0;
         g.ext_w = c.Wo; g.ext_h = c.Ho; g.ext_t = c.To; g.ext_n = c.N;
         g.tiles_w = ceil_div(c.Wo, 1 << g.lw);
         g.tiles_h = ceil_div(c.Ho, 1 << g.lh);
-        g.tiles_t = ceil_div(c.To, tt);
+        g.tiles_t = ceil_div(c.To, 1 << g.lt);
         g.tiles_n = c.N;
-        const uint32_t ybox[5] = {64, 1u << g.lw, 1u << g.lh, (uint32_t)tt, 1};
-        const uint32_t xbox[5] = {64, 1u << g.lw, 1u << g.lh, (uint32_t)(tt + c.kt - 1), 1};
+        const uint32_t ybox[5] = {64, 1u << g.lw, 1u << g.lh, 1u << g.lt, 1};
+        const uint32_t xbox[5] = {64, 1u << g.lw, (uint32_t)((1 << g.lh) + (spatial ? c.kh - 1 : 0)),
+                                  (uint32_t)((1 << g.lt) + (temporal ? c.kt - 1 : 0)), 1};
         uint64_t ydims[5] = {(uint64_t)c.Cout_p, (uint64_t)c.Wo, (uint64_t)c.Ho, (uint64_t)c.To, (uint64_t)c.N};
         uint64_t ystr[5] = {2, (uint64_t)c.Cout_p * 2, (uint64_t)c.Wo * c.Cout_p * 2,
                             (uint64_t)c.Ho * c.Wo * c.Cout_p * 2, (uint64_t)c.To * c.Ho * c.Wo * c.Cout_p * 2};
@@ -351,17 +384,31 @@ int conv_wgrad_bf16(const void* x, const void* dy, float* dw, const ConvGeom& c,
         rc = encode_tmap(&P.a_map[0], x, 2, 5, xdims, xstrd, xbox, true);
         if (rc) return rc;
         for (int i = 1; i < kMaxAMaps; ++i) P.a_map[i] = P.a_map[0];
-        // units ordered by (chunk, tap): start addresses increase, so a pair's LBO is positive
-        int u = 0;
-        for (int kc = 0; kc < k_chunks; ++kc)
-          for (int a = 0; a < c.kt; ++a, ++u) {
-            P.unit_off[u] = (kc * x_box_bytes + a * thw * 128) >> 4;
-            P.unit_widx[u] = (int16_t)a;
-            P.unit_kc[u] = (int16_t)kc;
+        // boxes ordered (kw, chunk); units ordered (box, halo tap): start addresses increase inside a group, so
+        // a pair's LBO is positive
+        const int group_rows = 8 << 7;   // one halo step = 8 rows (temporal: th*tw rows, a multiple of 8) in bytes
+        const int step_bytes = temporal ? ((1 << (g.lh + g.lw)) * 128) : group_rows;
+        int u = 0, b = 0;
+        for (int d = 0; d < (temporal ? 1 : c.kw); ++d)
+          for (int kc = 0; kc < k_chunks; ++kc, ++b) {
+            P.box_dt[b] = (int8_t)(temporal ? -c.pt : 0);
+            P.box_dh[b] = (int8_t)(spatial ? -c.ph : 0);
+            P.box_dw[b] = (int8_t)(spatial ? d - c.pw : 0);
+            P.box_kc[b] = (int8_t)kc;
+            const int slot = b % boxes_per_group;
+            for (int a = 0; a < span; ++a, ++u) {
+              P.unit_off[u] = (slot * x_box_bytes + a * step_bytes) >> 4;
+              P.unit_widx[u] = (int16_t)(temporal ? a : a * c.kw + d);
+              P.unit_kc[u] = (int16_t)kc;
+            }
           }
-        for (int a = 0; a < c.kt; ++a) { P.taps[a].map = 0; P.taps[a].dt = (int8_t)(a - c.pt); P.taps[a].dh = 0;
-                                         P.taps[a].dw = 0; P.taps[a].widx = (int16_t)a; P.taps[a].shift_rows = 0; }
-        return wgrad_launch(P, c.kt, c.Cin_p, c.Cout_p, taps_total, dw, stream);
+        P.n_groups = n_groups;
+        for (int gi = 0; gi <= n_groups; ++gi) {
+          const int bb = std::min(gi * boxes_per_group, n_boxes);
+          P.grp_box0[gi] = (int8_t)bb;
+          P.grp_unit0[gi] = (int8_t)(bb * span);
+        }
+        return wgrad_launch(P, taps_total, c.Cin_p, c.Cout_p, taps_total, dw, stream);
       }
     }
   }

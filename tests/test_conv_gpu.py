@@ -23,6 +23,8 @@ CASES = [
     ("temporal 921->512 s2", 3, 4, 7, 7, 921, 512, (3, 1, 1), (2, 1, 1), (1, 0, 0)),
     ("many tiles per CTA 64->64", 24, 8, 32, 32, 64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
     ("odd extents 5x9x11", 3, 5, 9, 11, 40, 72, (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    ("spatial halo wgrad 64->144 16x16 (2 unit groups)", 2, 4, 16, 16, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    ("spatial halo wgrad 24->40 24x16", 3, 2, 24, 16, 24, 40, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
 ]
 
 
