@@ -46,10 +46,10 @@ struct alignas(64) WgradParams {
   int x_box_bytes;         // bytes of one halo box (multiple of 1024)
   int n_groups;            // halo mode: unit groups
   int8_t grp_unit0[9], grp_box0[9];   // first unit / first box of each group (+ end sentinel)
-  int8_t box_dt[16], box_dh[16], box_dw[16], box_kc[16];   // halo box origin offset and 64-channel chunk
-  int unit_off[16];        // start of each unit inside its group's stage, in 16-byte units
-  int16_t unit_widx[16];   // weight tap index of each unit
-  int16_t unit_kc[16];     // 64-channel chunk of each unit
+  int8_t box_dt[32], box_dh[32], box_dw[32], box_kc[32];   // halo box origin offset and 64-channel chunk
+  int unit_off[32];        // start of each unit inside its group's stage, in 16-byte units
+  int16_t unit_widx[32];   // weight tap index of each unit
+  int16_t unit_kc[32];     // 64-channel chunk of each unit
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -259,8 +259,10 @@ static int wgrad_launch(WgradParams& P, int ntaps, int cin_p, int cout_p, int ta
   if (cout_p <= 256) {
     P.n_tiles = 1; P.block_n = round_up(cout_p, 16); P.last_n = P.block_n;
   } else {
-    P.block_n = 256; P.n_tiles = ceil_div(cout_p, 256);
-    P.last_n = round_up(cout_p - (P.n_tiles - 1) * 256, 16);
+    // equal channel tiles (288 -> 144 + 144, not 256 + 32: a narrow last tile re-loads every X box for 1/8 of the work)
+    P.n_tiles = ceil_div(cout_p, 256);
+    P.block_n = round_up(ceil_div(cout_p, P.n_tiles), 16);
+    P.last_n = round_up(cout_p - (P.n_tiles - 1) * P.block_n, 16);
   }
   P.acc_stride = round_up(P.block_n, 32);
   const int nbx = ceil_div(P.block_n, 64);
@@ -319,7 +321,8 @@ int conv_wgrad_bf16(const void* x, const void* dy, float* dw, const ConvGeom& c,
     if (halo_env < 0) { const char* e = getenv("DV_CONV_HALO"); halo_env = e ? atoi(e) : 1; }
     const int k_chunks = ceil_div(c.Cin_p, 64);
     const int units = taps_total * k_chunks;
-    const int bn = c.Cout_p <= 256 ? round_up(c.Cout_p, 16) : 256;
+    const int n_tiles_h = ceil_div(c.Cout_p, 256);
+    const int bn = round_up(ceil_div(c.Cout_p, n_tiles_h), 16);
     const int acc_stride = round_up(bn, 32);
     const int max_pairs = 512 / acc_stride;
     const bool temporal = c.kt > 1 && c.kh == 1 && c.kw == 1;
@@ -327,7 +330,7 @@ int conv_wgrad_bf16(const void* x, const void* dy, float* dw, const ConvGeom& c,
     // halo taps: the filter dimension that shifts by whole 8-row groups (t planes / h rows of 8 positions);
     // a box feeds `span` units, so a group must be able to hold at least one box worth of units
     const int span = temporal ? c.kt : c.kh;
-    if (halo_env && (temporal || spatial) && c.st == 1 && c.sh == 1 && c.sw == 1 && c.Cout_p <= 256 && units <= 16 &&
+    if (halo_env && (temporal || spatial) && c.st == 1 && c.sh == 1 && c.sw == 1 && units <= 32 &&
         span <= 2 * max_pairs) {
       TileGeom& g = P.g;
       int x_rows;   // rows (positions) of one halo box
@@ -346,9 +349,17 @@ int conv_wgrad_bf16(const void* x, const void* dy, float* dw, const ConvGeom& c,
         g.lw = blw; g.lh = blh; g.lt = blt; g.ln = 0;
         x_rows = ((1 << g.lt) + c.kt - 1) << (g.lh + g.lw);
       } else {
-        // tile (1, 1, 8, 8): an h shift of the filter is a shift by one 8-row group; one box per (kw, chunk)
-        g.lw = 3; g.lh = 3; g.lt = 0; g.ln = 0;
-        x_rows = (8 + c.kh - 1) * 8;
+        // tile (1, 1, th, tw) with tw >= 8: an h shift of the filter is a shift by tw rows = whole 8-row groups;
+        // one box per (kw, chunk). Pick the shape that pads the map least (halo cost included).
+        double best = 1e30; int blw = 3;
+        for (int a = 3; a <= 6; ++a) {
+          const int tw = 1 << a, th = 64 >> a;
+          const double vol = (double)round_up(c.Wo, tw) * round_up(c.Ho, th);
+          const double cost = vol * (double)(th + c.kh - 1) / th;
+          if (cost < best) { best = cost; blw = a; }
+        }
+        g.lw = blw; g.lh = 6 - blw; g.lt = 0; g.ln = 0;
+        x_rows = ((1 << g.lh) + c.kh - 1) << g.lw;
       }
       const double waste = (double)round_up(c.Wo, 1 << g.lw) * round_up(c.Ho, 1 << g.lh) * round_up(c.To, 1 << g.lt) /
                            ((double)c.Wo * c.Ho * c.To);
@@ -361,7 +372,7 @@ int conv_wgrad_bf16(const void* x, const void* dy, float* dw, const ConvGeom& c,
       while (boxes_per_group > 1 && 3 * (boxes_per_group * x_box_bytes + nbx * kBoxBytes) > kWgSmemBudget - 1024)
         --boxes_per_group;
       const int n_groups = ceil_div(n_boxes, boxes_per_group);
-      if ((temporal || waste <= 1.16) && n_boxes <= 16 && n_groups <= 8 &&
+      if ((temporal || waste <= 1.16) && n_boxes <= 32 && n_groups <= 8 &&
           3 * (std::min(boxes_per_group, n_boxes) * x_box_bytes + nbx * kBoxBytes) <= kWgSmemBudget - 1024) {
         P.halo = 1;
         P.x_box_bytes = x_box_bytes;
@@ -386,8 +397,8 @@ int conv_wgrad_bf16(const void* x, const void* dy, float* dw, const ConvGeom& c,
         for (int i = 1; i < kMaxAMaps; ++i) P.a_map[i] = P.a_map[0];
         // boxes ordered (kw, chunk); units ordered (box, halo tap): start addresses increase inside a group, so
         // a pair's LBO is positive
-        const int group_rows = 8 << 7;   // one halo step = 8 rows (temporal: th*tw rows, a multiple of 8) in bytes
-        const int step_bytes = temporal ? ((1 << (g.lh + g.lw)) * 128) : group_rows;
+        // one halo step: temporal = a t plane of th*tw rows, spatial = an h row of tw positions (multiples of 8 rows)
+        const int step_bytes = temporal ? ((1 << (g.lh + g.lw)) * 128) : ((1 << g.lw) * 128);
         int u = 0, b = 0;
         for (int d = 0; d < (temporal ? 1 : c.kw); ++d)
           for (int kc = 0; kc < k_chunks; ++kc, ++b) {
