@@ -23,7 +23,9 @@ namespace dv {
 constexpr int kWgThreads = 192;
 constexpr int kBoxBytes = 64 * 128;  // one 64-position x 64-channel box
 constexpr int kWgMaxUnits = 8;
-constexpr int kWgSmemBudget = 232448 - 2048;
+// Not the whole 227 KB: wgrad runs on a side stream next to the BatchNorm passes of the layers below (engine.py), whose
+// blocks need ~17 KB of shared memory each to become resident on the same SM.
+constexpr int kWgSmemBudget = 232448 - 2048 - 36 * 1024;
 
 struct alignas(64) WgradParams {
   CUtensorMap a_map[kMaxAMaps];

@@ -70,6 +70,7 @@ class Context:
         self.tape = []
         self.param_grads = {}      # id(param) -> fp32 tensor shaped like the parameter
         self.overrides = {}        # (id(concat Act), channel offset) -> dense gradient replacing the slice's
+        self.side_used = False     # weight gradients are in flight on the side stream
 
     def add_param_grad(self, p, g):
         k = id(p)
@@ -284,10 +285,22 @@ def conv_stats(ctx, x, conv, bn):
     return r
 
 
-def _conv_backward(ctx, r, dy):
-    """wgrad into the parameter-gradient sink, dgrad into r.x.grad."""
+# The weight gradient of a layer is off the backward critical path (dgrad -> BN backward of the layer below -> ...),
+# so it runs on a side stream: its tensor-bound CTAs then share the SMs with the HBM-bound BatchNorm passes of the
+# layers below instead of running back to back with them. DV_WGRAD_STREAM=0 keeps everything on one stream.
+WGRAD_SIDE_STREAM = os.environ.get("DV_WGRAD_STREAM", "1") != "0"
+_side_streams = {}
+
+
+def _side_stream(device):
+    s = _side_streams.get(device)
+    if s is None:
+        s = _side_streams[device] = torch.cuda.Stream(device=device)
+    return s
+
+
+def _wgrad(r, dy, gw):
     g = r.geom
-    gw = torch.empty_like(r.conv.weight)
     if r.stem:
         dwp = torch.empty((g.Cout_p, g.kt * 4, 64), dtype=torch.float32, device=dy.device)
         call("dv_conv3d_stem_wgrad_bf16", ptr(r.x.data), ptr(dy), ptr(dwp), ctypes.byref(g), stream_ptr())
@@ -296,6 +309,25 @@ def _conv_backward(ctx, r, dy):
         dwp = torch.empty((g.Cout_p, g.taps, g.Cin_p), dtype=torch.float32, device=dy.device)
         call("dv_conv3d_wgrad_bf16", ptr(r.x.data), ptr(dy), ptr(dwp), ctypes.byref(g), stream_ptr())
         call("dv_unpack_conv_wgrad", ptr(dwp), ptr(gw), ctypes.byref(g), ctypes.c_float(0.0), stream_ptr())
+
+
+def _conv_backward(ctx, r, dy):
+    """wgrad into the parameter-gradient sink, dgrad into r.x.grad."""
+    g = r.geom
+    gw = torch.empty_like(r.conv.weight)
+    if WGRAD_SIDE_STREAM:
+        main = torch.cuda.current_stream()
+        side = _side_stream(dy.device)
+        side.wait_stream(main)                 # dy (and, on the first use, x) are ready
+        with torch.cuda.stream(side):
+            _wgrad(r, dy, gw)
+        # the caching allocator must not hand these blocks to later main-stream work while the side stream reads them
+        dy.record_stream(side)
+        r.x.data.record_stream(side)
+        gw.record_stream(side)
+        ctx.side_used = True
+    else:
+        _wgrad(r, dy, gw)
     ctx.add_param_grad(r.conv.weight, gw)
     if r.conv.bias is not None:
         # a bias in front of training-mode BN has exactly zero gradient (BN removes the mean)
@@ -502,6 +534,10 @@ def run_backward(ctx):
     for fn in reversed(ctx.tape):
         fn()
     ctx.tape.clear()
+    if ctx.side_used:      # join: parameter gradients are consumed on the current stream from here on
+        dev = torch.cuda.current_device()
+        torch.cuda.current_stream().wait_stream(_side_stream(torch.device("cuda", dev)))
+        ctx.side_used = False
 
 
 # ----------------------------------------------------------------------------- autograd bridge
