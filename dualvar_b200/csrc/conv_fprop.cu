@@ -153,8 +153,8 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
               if (rank == 0) mbar_expect_tx(&full_bar[stage], tx_mult * tx_bytes);
               const uint32_t full_addr = full0_addr + (uint32_t)stage * 8u;
               uint8_t* st = ring + stage * stage_bytes;
-              tma_load_5d_to<kPair>(st, &p.a_map[lead.map], full_addr, kc * kChunkK, w0 + lead.dw, h0 + lead.dh,
-                                    t0 + lead.dt, n0);
+              tma_load_5d_to<kPair>(st, &p.a_map[lead.map], full_addr, kc * kChunkK, w0 + lead.dw,
+                                    h0 + g.org_h + lead.dh, t0 + lead.dt, n0);
               if (!p.b_resident)
                 for (int i = 0; i < len; ++i)
                   tma_load_3d_to<kPair>(st + p.a_stage_bytes + i * b_tap_bytes, &p.b_map, full_addr, kc * kChunkK,
@@ -581,6 +581,7 @@ void set_conv_profile(long long* p) { g_prof = p; }
 static int g_halo_enabled = 1;      // DV_CONV_HALO=0 disables tap grouping (A/B testing)
 static int g_resident_enabled = 1;  // DV_CONV_RESIDENT=0 disables weight-stationary CTAs
 static int g_pair_enabled = 1;      // DV_CONV_PAIR=0 disables CTA pairs (cta_group::2)
+static int g_split_enabled = 1;     // DV_CONV_SPLIT=0 disables the two-region tiling of maps with H = 8 (mod 16)
 static void read_env_once() {
   static bool done = false;
   if (done) return;
@@ -588,6 +589,7 @@ static void read_env_once() {
   if (const char* e = getenv("DV_CONV_HALO")) g_halo_enabled = atoi(e);
   if (const char* e = getenv("DV_CONV_RESIDENT")) g_resident_enabled = atoi(e);
   if (const char* e = getenv("DV_CONV_PAIR")) g_pair_enabled = atoi(e);
+  if (const char* e = getenv("DV_CONV_SPLIT")) g_split_enabled = atoi(e);
 }
 
 // out(view) = sum_taps A_view(tap)[box shifted by tap] * W[tap]
@@ -597,11 +599,13 @@ static void read_env_once() {
 //   temporal-only filters  : one group, box (tw, th, tt + kt - 1), tile th*tw multiple of 8
 //   filters with kh > 1    : tile (tt=1, th=16, tw=8), one group per kw, box (8, 16 + kh - 1, kt)
 // Everything else (strided layers = several views, small maps) keeps one box per tap.
-static int conv_multi_tap(ConvTileParams& P, MapEncoder enc, const void* enc_ctx, int n_views,
-                          const std::vector<TapSpec>& taps_in, const View5& outv, int out_rows_p,
-                          const void* w_packed, int w_rows_p, int w_taps, int kin_p, double* stats,
-                          const float* bias, cudaStream_t stream, bool allow_group = true,
-                          const BnReduce* red = nullptr) {
+// rows_lw: log2 of the tile width in "rows" mode (tile = 2^(7-rows_lw) h x 2^rows_lw w); org_h: h offset of the
+// output region inside the full tensor (added to the input box coordinates; outv is already the region's view).
+static int conv_multi_tap_region(ConvTileParams& P, MapEncoder enc, const void* enc_ctx, int n_views,
+                                 const std::vector<TapSpec>& taps_in, const View5& outv, int out_rows_p,
+                                 const void* w_packed, int w_rows_p, int w_taps, int kin_p, double* stats,
+                                 const float* bias, cudaStream_t stream, bool allow_group,
+                                 const BnReduce* red, int rows_lw, int org_h) {
   read_env_once();
   if (taps_in.empty()) return fail(kBadArg, "convolution has no valid taps");
   if ((int)taps_in.size() > kMaxTaps) return fail(kUnsupported, "too many filter taps (%d)", (int)taps_in.size());
@@ -619,8 +623,9 @@ static int conv_multi_tap(ConvTileParams& P, MapEncoder enc, const void* enc_ctx
     if (span_h == 1 && span_w == 1 && span_t > 1) {
       mode = kTemporal;
     } else if (span_h > 1) {
-      const double waste = (double)round_up(eW, 8) * round_up(eH, 16) / ((double)eW * eH);
-      if (waste <= 1.16 && (16 + span_h - 1) * 8 * span_t * 128 <= 64 * 1024) mode = kRows;
+      const int rtw = 1 << rows_lw, rth = 128 >> rows_lw;
+      const double waste = (double)round_up(eW, rtw) * round_up(eH, rth) / ((double)eW * eH);
+      if (waste <= 1.16 && (rth + span_h - 1) * rtw * span_t * 128 <= 64 * 1024) mode = kRows;
     }
   }
   uint32_t abox[5];  // A box (channels, w, h, t, n)
@@ -640,13 +645,14 @@ static int conv_multi_tap(ConvTileParams& P, MapEncoder enc, const void* enc_ctx
     g.lw = blw; g.lh = blh; g.lt = blt; g.ln = 0;
     abox[0] = kChunkK; abox[1] = 1u << g.lw; abox[2] = 1u << g.lh; abox[3] = (1u << g.lt) + span_t - 1; abox[4] = 1;
   } else if (mode == kRows) {
-    g.lw = 3; g.lh = 4; g.lt = 0; g.ln = 0;
-    abox[0] = kChunkK; abox[1] = 8; abox[2] = 16 + span_h - 1; abox[3] = span_t; abox[4] = 1;
+    g.lw = rows_lw; g.lh = 7 - rows_lw; g.lt = 0; g.ln = 0;
+    abox[0] = kChunkK; abox[1] = 1u << g.lw; abox[2] = (1u << g.lh) + span_h - 1; abox[3] = span_t; abox[4] = 1;
   } else {
     choose_tile(eN, eT, eH, eW, &g.ln, &g.lt, &g.lh, &g.lw);
     abox[0] = kChunkK; abox[1] = 1u << g.lw; abox[2] = 1u << g.lh; abox[3] = 1u << g.lt; abox[4] = 1u << g.ln;
   }
   g.ext_w = eW; g.ext_h = eH; g.ext_t = eT; g.ext_n = eN;
+  g.org_h = org_h;
   g.tiles_w = ceil_div(eW, 1 << g.lw);
   g.tiles_h = ceil_div(eH, 1 << g.lh);
   g.tiles_t = ceil_div(eT, 1 << g.lt);
@@ -711,8 +717,8 @@ static int conv_multi_tap(ConvTileParams& P, MapEncoder enc, const void* enc_ctx
   P.stages = (avail - (P.b_resident ? res_bytes : 0)) / stage_bytes;
   if (P.stages > kMaxStages) P.stages = kMaxStages;
   if (P.stages < 3 && mode != kPlain)   // wide layers: a group's weight tiles do not fit -> one box per tap
-    return conv_multi_tap(P, enc, enc_ctx, n_views, taps_in, outv, out_rows_p, w_packed, w_rows_p, w_taps, kin_p,
-                          stats, bias, stream, false, red);
+    return conv_multi_tap_region(P, enc, enc_ctx, n_views, taps_in, outv, out_rows_p, w_packed, w_rows_p, w_taps,
+                                 kin_p, stats, bias, stream, false, red, rows_lw, org_h);
   if (P.stages < 2) return fail(kUnsupported, "conv tile: not enough shared memory for 2 stages");
   P.stats = stats;
   P.stats_ld = out_rows_p;
@@ -773,6 +779,41 @@ static int conv_multi_tap(ConvTileParams& P, MapEncoder enc, const void* enc_ctx
   }
   DV_LAUNCH_OK();
   return kOk;
+}
+
+// out(view) = sum_taps A_view(tap)[box shifted by tap] * W[tap].
+// Spatial filters on maps whose height is 8 (mod 16), e.g. 56: the 16 x 8 "rows" tile would pad the last tile row
+// by half (12.5 % of all MMAs at 56 x 56). The map is split instead: rows [0, H-8) with 16 x 8 tiles and the last 8
+// rows with 8 x 16 tiles, two launches accumulating into the same BatchNorm statistics.
+static int conv_multi_tap(ConvTileParams& P, MapEncoder enc, const void* enc_ctx, int n_views,
+                          const std::vector<TapSpec>& taps_in, const View5& outv, int out_rows_p,
+                          const void* w_packed, int w_rows_p, int w_taps, int kin_p, double* stats,
+                          const float* bias, cudaStream_t stream, bool allow_group = true,
+                          const BnReduce* red = nullptr) {
+  read_env_once();
+  const int eH = (int)outv.dim[2], eW = (int)outv.dim[1];
+  bool spatial = false;
+  for (const TapSpec& t : taps_in) spatial = spatial || t.oh != taps_in[0].oh;
+  if (g_halo_enabled && g_split_enabled && allow_group && n_views == 1 && spatial && eH % 16 == 8 && eH >= 24 &&
+      (double)round_up(eW, 8) / eW <= 1.16 && (double)round_up(eW, 16) / eW <= 1.16) {
+    const int h_main = eH - 8;
+    View5 va = outv, vb = outv;
+    va.dim[2] = h_main;
+    vb.dim[2] = 8;
+    vb.base = static_cast<const uint8_t*>(outv.base) + (long long)h_main * outv.stride[2] * 2;
+    BnReduce rb;
+    if (red != nullptr) {
+      rb = *red;
+      rb.y = static_cast<const uint8_t*>(red->y) + (long long)h_main * outv.stride[2] * 2;
+    }
+    int rc = conv_multi_tap_region(P, enc, enc_ctx, n_views, taps_in, va, out_rows_p, w_packed, w_rows_p, w_taps,
+                                   kin_p, stats, bias, stream, true, red, 3, 0);
+    if (rc) return rc;
+    return conv_multi_tap_region(P, enc, enc_ctx, n_views, taps_in, vb, out_rows_p, w_packed, w_rows_p, w_taps,
+                                 kin_p, stats, bias, stream, true, red != nullptr ? &rb : nullptr, 4, h_main);
+  }
+  return conv_multi_tap_region(P, enc, enc_ctx, n_views, taps_in, outv, out_rows_p, w_packed, w_rows_p, w_taps, kin_p,
+                               stats, bias, stream, allow_group, red, 3, 0);
 }
 
 static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }

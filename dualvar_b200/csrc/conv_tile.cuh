@@ -32,6 +32,7 @@ struct TileGeom {
   // number of tiles along each dim and output extents (for row validity)
   int tiles_w, tiles_h, tiles_t, tiles_n;
   int ext_w, ext_h, ext_t, ext_n;
+  int org_h;   // h offset of the output region in the full tensor (input box coordinates), 0 unless the map is split
 };
 
 struct alignas(64) ConvTileParams {

@@ -25,6 +25,8 @@ CASES = [
     ("odd extents 5x9x11", 3, 5, 9, 11, 40, 72, (3, 3, 3), (1, 1, 1), (1, 1, 1)),
     ("spatial halo wgrad 64->144 16x16 (2 unit groups)", 2, 4, 16, 16, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
     ("spatial halo wgrad 24->40 24x16", 3, 2, 24, 16, 24, 40, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    ("two-region tiling 64->144 24x32", 2, 2, 24, 32, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    ("two-region tiling 3x3x3 40->64 40x16", 2, 3, 40, 16, 40, 64, (3, 3, 3), (1, 1, 1), (1, 1, 1)),
 ]
 
 
@@ -124,14 +126,14 @@ def test_conv_linearity_at_full_size():
     assert torch.equal(y2, y1 * 2)
 
 
-@pytest.mark.parametrize("kt,pt,Cout", [(1, 0, 83), (3, 1, 64)])
-def test_space_to_depth_stem_matches_torch(kt, pt, Cout):
+@pytest.mark.parametrize("kt,pt,Cout,H,W", [(1, 0, 83, 36, 44), (3, 1, 64, 36, 44), (1, 0, 83, 48, 64)])
+def test_space_to_depth_stem_matches_torch(kt, pt, Cout, H, W):
     """Stride-2 7x7 stem on the space-to-depth ingest (overlapping-window TMA map) vs torch conv3d."""
     import ctypes
     from dualvar_b200 import _lib, engine as E, kernels as K
     torch.backends.cudnn.allow_tf32 = False
     dev = "cuda:0"
-    N, T, H, W = 5, 4, 36, 44
+    N, T = 5, 4        # 48x64 frames -> 24x32 map: the two-region tiling path
     gen = torch.Generator(device=dev).manual_seed(kt)
     x = torch.randn(N, 3, T, H, W, device=dev, generator=gen)
     w = torch.randn(Cout, 3, kt, 7, 7, device=dev, generator=gen) / (3 * kt * 49) ** 0.5
