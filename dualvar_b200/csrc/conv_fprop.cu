@@ -605,7 +605,7 @@ static int conv_multi_tap_region(ConvTileParams& P, MapEncoder enc, const void* 
                                  const std::vector<TapSpec>& taps_in, const View5& outv, int out_rows_p,
                                  const void* w_packed, int w_rows_p, int w_taps, int kin_p, double* stats,
                                  const float* bias, cudaStream_t stream, bool allow_group,
-                                 const BnReduce* red, int rows_lw, int org_h) {
+                                 const BnReduce* red, int rows_lw, int org_h, bool rows_forced = false) {
   read_env_once();
   if (taps_in.empty()) return fail(kBadArg, "convolution has no valid taps");
   if ((int)taps_in.size() > kMaxTaps) return fail(kUnsupported, "too many filter taps (%d)", (int)taps_in.size());
@@ -622,10 +622,34 @@ static int conv_multi_tap_region(ConvTileParams& P, MapEncoder enc, const void* 
   if (g_halo_enabled && allow_group && n_views == 1 && taps_in.size() > 1) {
     if (span_h == 1 && span_w == 1 && span_t > 1) {
       mode = kTemporal;
+    } else if (span_h > 1 && rows_forced) {
+      mode = kRows;
     } else if (span_h > 1) {
-      const int rtw = 1 << rows_lw, rth = 128 >> rows_lw;
-      const double waste = (double)round_up(eW, rtw) * round_up(eH, rth) / ((double)eW * eH);
-      if (waste <= 1.16 && (rth + span_h - 1) * rtw * span_t * 128 <= 64 * 1024) mode = kRows;
+      // "rows" tiles (th x tw, halo along h, one box per kw) against one box per tap: estimated cycles per unit of
+      // output = max(MMA issue/tensor time, L2->SM feed at ~42 B/clk/SM); padded tiles cost both
+      // (constants from tests/diag/mma_rate.py and the TMA feed rate measured with conv_roles.py)
+      int nb, bn, ln_;
+      pick_block_n(out_rows_p, &nb, &bn, &ln_);
+      const double mma_per_tile = (double)taps_in.size() * ceil_div(kin_p, 16) * std::max(bn / 2.0, 58.0);
+      const double w_bytes = (double)taps_in.size() * bn * kin_p * 2 * 0.5;   // pair: half the rows per CTA
+      const bool w_res = nb == 1 && w_bytes <= 112 * 1024;
+      auto cost = [&](double tiles, double a_rows) {
+        const double feed = (a_rows * kin_p * 2 + (w_res ? 0.0 : w_bytes)) / 42.0;
+        return tiles * std::max(mma_per_tile, feed);
+      };
+      int pl[4];
+      choose_tile(eN, eT, eH, eW, &pl[0], &pl[1], &pl[2], &pl[3]);
+      const double plain_tiles = (double)ceil_div(eN, 1 << pl[0]) * ceil_div(eT, 1 << pl[1]) * ceil_div(eH, 1 << pl[2]) *
+                                 ceil_div(eW, 1 << pl[3]);
+      double best = cost(plain_tiles, 128.0 * taps_in.size());
+      for (int lw = 3; lw <= 5; ++lw) {
+        const int rtw = 1 << lw, rth = 128 >> lw;
+        const int box_rows = (rth + span_h - 1) * rtw * span_t;
+        if (box_rows * 128 > 64 * 1024) continue;
+        const double tiles = (double)eN * eT * ceil_div(eH, rth) * ceil_div(eW, rtw);
+        const double c = cost(tiles, (double)span_w * box_rows);
+        if (c < best * 0.97) { best = c; mode = kRows; rows_lw = lw; }
+      }
     }
   }
   uint32_t abox[5];  // A box (channels, w, h, t, n)
@@ -807,10 +831,10 @@ static int conv_multi_tap(ConvTileParams& P, MapEncoder enc, const void* enc_ctx
       rb.y = static_cast<const uint8_t*>(red->y) + (long long)h_main * outv.stride[2] * 2;
     }
     int rc = conv_multi_tap_region(P, enc, enc_ctx, n_views, taps_in, va, out_rows_p, w_packed, w_rows_p, w_taps,
-                                   kin_p, stats, bias, stream, true, red, 3, 0);
+                                   kin_p, stats, bias, stream, true, red, 3, 0, true);
     if (rc) return rc;
     return conv_multi_tap_region(P, enc, enc_ctx, n_views, taps_in, vb, out_rows_p, w_packed, w_rows_p, w_taps,
-                                 kin_p, stats, bias, stream, true, red != nullptr ? &rb : nullptr, 4, h_main);
+                                 kin_p, stats, bias, stream, true, red != nullptr ? &rb : nullptr, 4, h_main, true);
   }
   return conv_multi_tap_region(P, enc, enc_ctx, n_views, taps_in, outv, out_rows_p, w_packed, w_rows_p, w_taps, kin_p,
                                stats, bias, stream, allow_group, red, 3, 0);

@@ -71,6 +71,19 @@ class Context:
         self.param_grads = {}      # id(param) -> fp32 tensor shaped like the parameter
         self.overrides = {}        # (id(concat Act), channel offset) -> dense gradient replacing the slice's
         self.side_used = False     # weight gradients are in flight on the side stream
+        self._arena = None         # zeroed fp64 scratch the per-layer statistic buffers are carved from
+        self._arena_used = 0
+
+    def zeros64(self, n, device):
+        """A zero-initialised float64 vector of n elements: one memset per ~64 K elements instead of one tiny
+        fill kernel per BatchNorm layer and pass (statistics and backward sums are 2*Cp doubles each)."""
+        n_al = (n + 31) // 32 * 32
+        if self._arena is None or self._arena.device != device or self._arena_used + n_al > self._arena.numel():
+            self._arena = torch.zeros(max(65536, n_al), dtype=torch.float64, device=device)
+            self._arena_used = 0
+        out = self._arena[self._arena_used:self._arena_used + n]
+        self._arena_used += n_al
+        return out
 
     def add_param_grad(self, p, g):
         k = id(p)
@@ -250,7 +263,7 @@ def conv_stats(ctx, x, conv, bn):
     dev = x.data.device
     y = torch.empty((N, g.To, g.Ho, g.Wo, g.Cout_p), dtype=torch.bfloat16, device=dev)
     training_stats = ctx.training and bn.training if bn is not None else False
-    stats = torch.zeros(2 * g.Cout_p, dtype=torch.float64, device=dev) if training_stats else None
+    stats = ctx.zeros64(2 * g.Cout_p, dev) if training_stats else None
     if stem:
         assert stem_eligible(conv, H, W), "space-to-depth input needs a stride-2 7x7 first conv"
         packed = (packed_stem_weights(conv, g), None)
@@ -338,7 +351,7 @@ def _conv_backward(ctx, r, dy):
             # x = relu?(BN(y_prev)) and this is (so far) its only gradient: the dgrad epilogue also produces
             # the BN-backward sums of the layer below, saving dv_bn_bwd_reduce's pass over dx and y_prev
             rp, relu = r.x.bnred
-            sums = torch.zeros(2 * g.Cin_p, dtype=torch.float64, device=dy.device)
+            sums = ctx.zeros64(2 * g.Cin_p, dy.device)
             call("dv_conv3d_dgrad_bnred_bf16", ptr(dy), ptr(r.packed[1]), ptr(dx), ctypes.byref(g), ptr(rp.y),
                  ptr(rp.ss) if relu else None, ptr(sums), stream_ptr())
             r.x.fused = (sums, dx)
@@ -395,7 +408,7 @@ def activate(ctx, r1, r2=None, res=None, relu=True, out=None, out_coff=0):
             if fused is not None and dout2 is None and ov is None and fused[1] is dout:
                 sums = fused[0]      # already reduced by the dgrad that produced dout
             else:
-                sums = torch.zeros(2 * Cp, dtype=torch.float64, device=dev)
+                sums = ctx.zeros64(2 * Cp, dev)
                 call("dv_bn_bwd_reduce", ptr(dout), ptr(dout2), ptr(out_t), ptr(r.y), mask_ss, ptr(sums), rows, Cp,
                      o_ld, o_coff, 1 if relu else 0, stream_ptr())
             sums_g = sums
