@@ -1,0 +1,72 @@
+"""Latency-bound collectives of the data-parallel path on NVLink peer memory.
+
+``small_allreduce_(t)`` sums a small fp64 vector (the per-layer statistics of cross-replica BatchNorm: 2*Cp doubles in
+forward, 2*Cp in backward, ~400 vectors per pretraining step, each on the critical path) across the ranks of one node
+with one kernel launch (csrc/comm.cu) instead of one NCCL call (~20 us each). The symmetric buffer comes from
+``torch.distributed._symmetric_memory`` (plumbing: allocation + peer mapping); the exchange itself is our kernel.
+
+Reference: nn.SyncBatchNorm's per-layer all_gather / all_reduce after convert_sync_batchnorm (pretrain.py:244).
+DV_SMALL_ALLREDUCE=0 keeps NCCL.
+"""
+import ctypes
+import os
+import warnings
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import ptr, stream_ptr
+
+_ENABLED = os.environ.get("DV_SMALL_ALLREDUCE", "1") != "0"
+_MAX_ELEMS = 4096
+_state = None      # None = not tried, False = unavailable (NCCL is used), else _PeerReduce
+
+
+class _PeerReduce:
+    def __init__(self, device):
+        import torch.distributed._symmetric_memory as symm
+        self.world = dist.get_world_size()
+        self.rank = dist.get_rank()
+        if self.world > 8:
+            raise RuntimeError("single node, at most 8 ranks")
+        nbytes = int(_lib.load().dv_allreduce_small_buffer_bytes())
+        self.buf = symm.empty(nbytes // 8, dtype=torch.float64, device=device)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, dist.group.WORLD)
+        ptrs = list(self.handle.buffer_ptrs)
+        if len(ptrs) != self.world or int(ptrs[self.rank]) != self.buf.data_ptr():
+            raise RuntimeError("unexpected symmetric-memory mapping")
+        self.ptrs = (ctypes.c_int64 * 8)(*[int(p) for p in ptrs], *([0] * (8 - self.world)))
+        self.seq = 0
+        torch.cuda.synchronize(device)
+        dist.barrier()          # every rank's flags are zero before anybody signals
+
+    def __call__(self, t):
+        self.seq += 1
+        _lib.call("dv_allreduce_small_f64", ptr(t), t.numel(), self.ptrs, self.rank, self.world, self.seq, stream_ptr())
+
+
+def small_allreduce_(t):
+    """In-place sum of a contiguous fp64 CUDA vector over the default process group."""
+    global _state
+    assert t.dtype == torch.float64 and t.is_cuda and t.is_contiguous()
+    if _state is None:
+        _state = False
+        if _ENABLED and dist.get_backend() == "nccl":
+            try:
+                _state = _PeerReduce(t.device)
+            except Exception as e:  # noqa: BLE001 - peer mapping is an optimisation; NCCL carries the same sum
+                warnings.warn(f"dualvar_b200: NVLink peer all-reduce unavailable ({e!r}); using NCCL for BatchNorm statistics")
+                _state = False
+    if _state is not False and t.numel() <= _MAX_ELEMS:
+        _state(t)
+    else:
+        dist.all_reduce(t)
+    return t
+
+
+def reset():
+    """Forget the peer mapping (tests; call on all ranks before destroying the process group)."""
+    global _state
+    _state = None

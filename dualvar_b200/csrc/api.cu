@@ -73,6 +73,9 @@ int row_axpy(const float* alpha, int ld_alpha, const float* x, float* y, int row
              cudaStream_t stream);
 int probe_overlap(const void* src, void* out, int c1, cudaStream_t stream);
 int mma_rate(int n, int n_mma, int region, int mode, long long* out, int grid, cudaStream_t stream);
+long long small_allreduce_buffer_bytes();
+int small_allreduce_f64(double* inout, int n, const long long* peer_ptrs, int rank, int world, long long seq,
+                        cudaStream_t stream);
 int sgd_momentum_step(const long long* table, int n_chunks, float lr, float mu, float wd, int first,
                       cudaStream_t stream);
 void set_conv_profile(long long* p);
@@ -403,6 +406,14 @@ int dv_sgd_momentum_step(const int64_t* chunk_table, int n_chunks, float lr, flo
   DV_REQUIRE(chunk_table && n_chunks >= 0 && lr >= 0.f, "bad sgd_momentum_step arguments");
   return sgd_momentum_step(reinterpret_cast<const long long*>(chunk_table), n_chunks, lr, momentum, weight_decay,
                            first_step, ST);
+}
+
+int64_t dv_allreduce_small_buffer_bytes(void) { return small_allreduce_buffer_bytes(); }
+
+int dv_allreduce_small_f64(double* inout, int n, const int64_t* peer_buffers, int rank, int world, int64_t seq,
+                           void* stream) {
+  DV_REQUIRE(inout && peer_buffers, "NULL pointer");
+  return small_allreduce_f64(inout, n, reinterpret_cast<const long long*>(peer_buffers), rank, world, seq, ST);
 }
 
 int dv_debug_set_conv_profile(int64_t* buf) {

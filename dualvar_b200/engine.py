@@ -20,7 +20,7 @@ import torch
 import torch.distributed as dist
 import torch.nn as nn
 
-from . import _lib
+from . import _lib, comm
 from ._lib import make_geom, pad8, ptr, stream_ptr
 
 call = _lib.call
@@ -282,7 +282,7 @@ def conv_stats(ctx, x, conv, bn):
         r.ss = r.saved = None
         return r
     if training_stats and _is_sync(bn):
-        dist.all_reduce(stats)
+        comm.small_allreduce_(stats)
         r.count *= dist.get_world_size()
         r.sync = True
     r.ss = torch.empty(2 * g.Cout_p, dtype=torch.float32, device=dev)
@@ -414,7 +414,7 @@ def activate(ctx, r1, r2=None, res=None, relu=True, out=None, out_coff=0):
             sums_g = sums
             if r.sync:
                 sums_g = sums.clone()
-                dist.all_reduce(sums_g)
+                comm.small_allreduce_(sums_g)
             bn = r.bn
             dgamma = torch.empty_like(bn.weight)
             dbeta = torch.empty_like(bn.bias)

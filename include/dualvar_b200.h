@@ -211,6 +211,16 @@ int dv_retrieval_sim_topk(const double* test, const double* train, double* sim, 
 int dv_sgd_momentum_step(const int64_t* chunk_table, int n_chunks, float lr, float momentum, float weight_decay,
                          int first_step, void* stream);
 
+/* ---- cross-replica BatchNorm statistics: one-shot all-reduce over NVLink peer memory ---------------
+ * Replaces the per-layer collectives of nn.SyncBatchNorm (pretrain.py:244) for vectors of <= 4096 doubles.
+ * Every rank allocates a zero-initialised symmetric buffer of dv_allreduce_small_buffer_bytes() bytes that is
+ * mapped into all peers (peer_buffers[q] = address of rank q's buffer in THIS process, host array of `world`
+ * entries); all ranks call with the same n and seq = 1, 2, 3, ... in the same order. In place, sum in rank
+ * order (bit-identical on all ranks). */
+int64_t dv_allreduce_small_buffer_bytes(void);
+int dv_allreduce_small_f64(double* inout, int n, const int64_t* peer_buffers, int rank, int world, int64_t seq,
+                           void* stream);
+
 /* debug (tests/diag only): per-CTA role cycle counters of the next conv_tile_kernel launches are written to
  * buf [148][16] (producer total/wait, MMA total/wait-data/wait-accumulator, epilogue total/wait, tiles, epilogue phases); NULL = off */
 int dv_debug_set_conv_profile(int64_t* buf);
