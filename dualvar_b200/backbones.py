@@ -209,6 +209,74 @@ class C3D(_Encoder):
         return x
 
 
+# ------------------------------------------------------------------------------------ r2d3d18
+class BasicBlock2d(nn.Module):
+    """2-D basic block container (backbone/resnet_2d3d.py:45-78)."""
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None, use_final_relu=True):
+        super().__init__()
+        self.use_final_relu = use_final_relu
+        self.conv1 = nn.Conv3d(inplanes, planes, (1, 3, 3), stride=(1, stride, stride), padding=(0, 1, 1), bias=False)
+        self.bn1 = nn.BatchNorm3d(planes)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = nn.Conv3d(planes, planes, (1, 3, 3), stride=1, padding=(0, 1, 1), bias=False)
+        self.bn2 = nn.BatchNorm3d(planes)
+        self.downsample = downsample
+
+    def run(self, ctx, x):
+        h = E.activate(ctx, E.conv_stats(ctx, x, self.conv1, self.bn1))
+        main = E.conv_stats(ctx, h, self.conv2, self.bn2)
+        if self.downsample is not None:
+            short = E.conv_stats(ctx, x, self.downsample[0], self.downsample[1])
+            return E.activate(ctx, main, r2=short, relu=self.use_final_relu)
+        return E.activate(ctx, main, res=x, relu=self.use_final_relu)
+
+
+class ResNet2d3dFull(_Encoder):
+    """select_backbone('r2d3d18') (backbone/resnet_2d3d.py:193-271,352-356): stem (1,7,7)/(1,2,2) + max-pool,
+    four stages of two 2-D basic blocks, no ReLU after the last block."""
+
+    def __init__(self, layers=(2, 2, 2, 2)):
+        super().__init__()
+        self.inplanes = 64
+        self.conv1 = nn.Conv3d(3, 64, (1, 7, 7), stride=(1, 2, 2), padding=(0, 3, 3), bias=False)
+        self.bn1 = nn.BatchNorm3d(64)
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool3d((1, 3, 3), stride=(1, 2, 2), padding=(0, 1, 1))
+        self.layer1 = self._make_layer(64, layers[0])
+        self.layer2 = self._make_layer(128, layers[1], stride=2)
+        self.layer3 = self._make_layer(256, layers[2], stride=2)
+        self.layer4 = self._make_layer(256, layers[3], stride=2, is_final=True)
+        for m in self.modules():                      # backbone/resnet_2d3d.py:214-220
+            if isinstance(m, nn.Conv3d):
+                m.weight = nn.init.kaiming_normal_(m.weight, mode="fan_out")
+            elif isinstance(m, nn.BatchNorm3d):
+                m.weight.data.fill_(1)
+                m.bias.data.zero_()
+
+    def _make_layer(self, planes, blocks, stride=1, is_final=False):
+        downsample = None
+        if stride != 1 or self.inplanes != planes:
+            downsample = nn.Sequential(
+                nn.Conv3d(self.inplanes, planes, 1, stride=(1, stride, stride), bias=False), nn.BatchNorm3d(planes))
+        layers = [BasicBlock2d(self.inplanes, planes, stride, downsample)]
+        self.inplanes = planes
+        for i in range(1, blocks):
+            layers.append(BasicBlock2d(planes, planes, use_final_relu=not (is_final and i == blocks - 1)))
+        return nn.Sequential(*layers)
+
+    def first_conv(self):
+        return self.conv1
+
+    def program(self, ctx, x):
+        x = E.activate(ctx, E.conv_stats(ctx, x, self.conv1, self.bn1))
+        x = E.max_pool(ctx, x, (1, 3, 3), (1, 2, 2), (0, 1, 1))
+        for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
+            for block in layer:
+                x = block.run(ctx, x)
+        return x
+
+
 def select_backbone(network, first_channel=3):
     """backbone/select_backbone.py:7-32 — same names, same return value."""
     param = {'feature_size': 1024}
@@ -224,6 +292,11 @@ def select_backbone(network, first_channel=3):
     elif network in ('s3d', 's3dg'):
         from .s3dg import S3D
         model = S3D(input_channel=first_channel, gating=(network == 's3dg'))
+    elif network == 'r2d3d18':
+        param['feature_size'] = 256
+        model = ResNet2d3dFull()
     else:
+        # 'r50' raises TypeError at construction in the reference itself (backbone/select_backbone.py:18 passes
+        # input_channel to a constructor that does not take it)
         raise NotImplementedError
     return model, param

@@ -292,9 +292,68 @@ class S3D(nn.Module):
         return x
 
 
+class BasicBlock2d(nn.Module):
+    """(1,3,3) conv -> BN -> ReLU -> (1,3,3) conv -> BN (+ 1x1x1 strided conv + BN shortcut) -> add -> ReLU?
+    (backbone/resnet_2d3d.py:45-78)."""
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None, use_final_relu=True):
+        super().__init__()
+        self.use_final_relu = use_final_relu
+        self.conv1 = nn.Conv3d(inplanes, planes, (1, 3, 3), stride=(1, stride, stride), padding=(0, 1, 1), bias=False)
+        self.bn1 = nn.BatchNorm3d(planes)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = nn.Conv3d(planes, planes, (1, 3, 3), stride=1, padding=(0, 1, 1), bias=False)
+        self.bn2 = nn.BatchNorm3d(planes)
+        self.downsample = downsample
+
+    def forward(self, x):
+        out = self.bn2(self.conv2(self.relu(self.bn1(self.conv1(x)))))
+        out = out + (x if self.downsample is None else self.downsample(x))
+        return self.relu(out) if self.use_final_relu else out
+
+
+class ResNet2d3dFull(nn.Module):
+    """CVRL-style ResNet of 2-D basic blocks = select_backbone('r2d3d18') (backbone/resnet_2d3d.py:193-271,352-356):
+    (1,7,7)/(1,2,2) stem -> BN -> ReLU -> max-pool (1,3,3)/(1,2,2) -> 4 stages of 2 blocks (64,128,256,256 planes,
+    stages 2-4 stride 2 in H,W only); the last block has no output ReLU; kaiming-normal(fan_out) conv init."""
+
+    def __init__(self, layers=(2, 2, 2, 2)):
+        super().__init__()
+        self.inplanes = 64
+        self.conv1 = nn.Conv3d(3, 64, (1, 7, 7), stride=(1, 2, 2), padding=(0, 3, 3), bias=False)
+        self.bn1 = nn.BatchNorm3d(64)
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool3d((1, 3, 3), stride=(1, 2, 2), padding=(0, 1, 1))
+        self.layer1 = self._make_layer(64, layers[0])
+        self.layer2 = self._make_layer(128, layers[1], stride=2)
+        self.layer3 = self._make_layer(256, layers[2], stride=2)
+        self.layer4 = self._make_layer(256, layers[3], stride=2, is_final=True)
+        for m in self.modules():                      # backbone/resnet_2d3d.py:214-220
+            if isinstance(m, nn.Conv3d):
+                m.weight = nn.init.kaiming_normal_(m.weight, mode="fan_out")
+            elif isinstance(m, nn.BatchNorm3d):
+                m.weight.data.fill_(1)
+                m.bias.data.zero_()
+
+    def _make_layer(self, planes, blocks, stride=1, is_final=False):
+        downsample = None
+        if stride != 1 or self.inplanes != planes:
+            downsample = nn.Sequential(
+                nn.Conv3d(self.inplanes, planes, 1, stride=(1, stride, stride), bias=False), nn.BatchNorm3d(planes))
+        layers = [BasicBlock2d(self.inplanes, planes, stride, downsample)]
+        self.inplanes = planes
+        for i in range(1, blocks):
+            layers.append(BasicBlock2d(planes, planes, use_final_relu=not (is_final and i == blocks - 1)))
+        return nn.Sequential(*layers)
+
+    def forward(self, x):
+        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        return self.layer4(self.layer3(self.layer2(self.layer1(x))))
+
+
 def select_backbone(network, first_channel=3):
-    """Name -> (module, {'feature_size'}) (backbone/select_backbone.py:7-32). 'r50'/'r2d3d18' are
-    outside the north-star backbone list and raise like an unknown name."""
+    """Name -> (module, {'feature_size'}) (backbone/select_backbone.py:7-32). 'r50' is broken in the reference
+    itself (TypeError at construction) and raises like an unknown name."""
     param = {"feature_size": 1024}
     if network == "s3d":
         model = S3D(input_channel=first_channel)
@@ -309,6 +368,9 @@ def select_backbone(network, first_channel=3):
     elif network == "r3d":
         param["feature_size"] = 512
         model = R3DNet()
+    elif network == "r2d3d18":
+        param["feature_size"] = 256
+        model = ResNet2d3dFull()
     else:
         raise NotImplementedError
     return model, param

@@ -145,6 +145,28 @@ def golden_backbones(ref_select):
     np.savez_compressed(os.path.join(HERE, "backbones.npz"), **out)
 
 
+def golden_backbones_next(ref_select):
+    """Backbones outside the north-star list, added as SURVEY §8(f) rows: written to their own fixture file."""
+    out = {}
+    for name in ("r2d3d18",):
+        seed_all(0)
+        net, param = ref_select(name)
+        out[f"{name}_nparams"] = np.array(sum(p.numel() for p in net.parameters()))
+        out[f"{name}_checksum"] = np.array(float(sum(p.detach().double().abs().sum() for p in net.parameters())))
+        out[f"{name}_feature_size"] = np.array(param["feature_size"])
+        out[f"{name}_keys"] = np.array(sorted(net.state_dict().keys()))
+        x = torch.randn(2, 3, 4, 64, 64, generator=torch.Generator().manual_seed(5))
+        net.train()
+        y = net(x)
+        out[f"{name}_out"] = npy(y)
+        net.eval()
+        with torch.no_grad():
+            out[f"{name}_out_eval"] = npy(net(x))
+            out[f"{name}_shape112"] = np.array(net(torch.zeros(1, 3, 16, 112, 112)).shape)
+        print(name, int(out[f"{name}_nparams"]), tuple(y.shape))
+    np.savez_compressed(os.path.join(HERE, "backbones_next.npz"), **out)
+
+
 def grads_digest(model):
     d = {}
     for n, p in model.named_parameters():
@@ -205,6 +227,10 @@ def golden_steps(ref_model):
 if __name__ == "__main__":
     torch.set_num_threads(8)
     ref_model, ref_select, ref_utils = import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "next":      # only the SURVEY §8(f) additions (backbones_next.npz)
+        golden_backbones_next(ref_select)
+        sys.exit(0)
     golden_objectives(ref_model, ref_utils)
     golden_backbones(ref_select)
+    golden_backbones_next(ref_select)
     golden_steps(ref_model)

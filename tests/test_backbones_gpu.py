@@ -89,7 +89,7 @@ def test_s3d_stagewise_error_tracks_bf16_autocast(name):
 
 
 @pytest.mark.parametrize("name,shape", [("c3d", (8, 3, 8, 64, 64)), ("s3d", (4, 3, 16, 64, 64)),
-                                        ("s3dg", (4, 3, 16, 64, 64))])
+                                        ("s3dg", (4, 3, 16, 64, 64)), ("r2d3d18", (6, 3, 4, 96, 96))])
 def test_backbone_forward_backward_vs_autocast_yardstick(name, shape):
     ref, prod = _pair(name)
     x = torch.randn(*shape, device=dev)
@@ -116,6 +116,26 @@ def test_backbone_forward_backward_vs_autocast_yardstick(name, shape):
     for (n, br), (_, bp) in zip(ref.named_buffers(), prod.named_buffers()):
         if not br.dtype.is_floating_point:
             assert int(bp) == int(br), n
+
+
+def test_r2d3d18_eval_matches_golden_and_full_size_shape():
+    """r2d3d18 in eval mode (folded running statistics) on the committed reference vectors, and the
+    16x112x112 output shape with the final block's missing ReLU (negative values survive)."""
+    import os
+    from dualvar_b200 import backbones as PB
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "backbones_next.npz"))
+    ref, prod = _pair("r2d3d18")
+    x = torch.randn(2, 3, 4, 64, 64, generator=torch.Generator().manual_seed(5)).to(dev)
+    with torch.no_grad():
+        yt = prod(x)                                  # train mode: batch statistics + running-stat update
+        assert _rel(yt, torch.from_numpy(g["r2d3d18_out"]).to(dev)) < 6e-2     # 17 bf16 conv layers, 2x2 final map
+        prod.eval()
+        ye = prod(x)
+        assert _rel(ye, torch.from_numpy(g["r2d3d18_out_eval"]).to(dev)) < 6e-2
+        net, param = PB.select_backbone("r2d3d18")
+        y = net.to(dev).train()(torch.randn(2, 3, 16, 112, 112, device=dev))
+    assert param["feature_size"] == 256 and y.shape == (2, 256, 16, 4, 4) and torch.isfinite(y).all()
+    assert bool((y < 0).any())
 
 
 def test_s3dg_full_size_shape():

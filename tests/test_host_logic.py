@@ -33,6 +33,18 @@ def test_backbone_state_dict_and_init_match_reference(golden_dir, name):
     np.testing.assert_allclose(checksum, float(g[f"{name}_checksum"]), rtol=1e-12)
 
 
+def test_r2d3d18_state_dict_and_init_match_reference(golden_dir):
+    """select_backbone('r2d3d18') — keys, parameter count, kaiming-normal(fan_out) init checksum."""
+    g = np.load(os.path.join(golden_dir, "backbones_next.npz"))
+    _seed(0)
+    net, param = PB.select_backbone("r2d3d18")
+    assert param["feature_size"] == int(g["r2d3d18_feature_size"]) == 256
+    assert sorted(net.state_dict().keys()) == list(g["r2d3d18_keys"])
+    assert sum(p.numel() for p in net.parameters()) == int(g["r2d3d18_nparams"]) == 5210176
+    checksum = float(sum(p.detach().double().abs().sum() for p in net.parameters()))
+    np.testing.assert_allclose(checksum, float(g["r2d3d18_checksum"]), rtol=1e-12)
+
+
 def test_select_backbone_contract():
     with pytest.raises(NotImplementedError):
         PB.select_backbone("nope")

@@ -110,6 +110,25 @@ def test_backbone_matches_reference(golden_dir, name):
         np.testing.assert_allclose(net(x).numpy(), g[f"{name}_out_eval"], rtol=1e-4, atol=1e-5)
 
 
+def test_r2d3d18_matches_reference(golden_dir):
+    """the oracle's r2d3d18 against vectors from the real backbone/resnet_2d3d.py."""
+    g = _load(golden_dir, "backbones_next.npz")
+    _seed(0)
+    net, param = select_backbone("r2d3d18")
+    assert param["feature_size"] == int(g["r2d3d18_feature_size"])
+    assert sum(p.numel() for p in net.parameters()) == int(g["r2d3d18_nparams"])
+    assert sorted(net.state_dict().keys()) == list(g["r2d3d18_keys"])
+    checksum = float(sum(p.detach().double().abs().sum() for p in net.parameters()))
+    np.testing.assert_allclose(checksum, float(g["r2d3d18_checksum"]), rtol=1e-12)
+    x = torch.randn(2, 3, 4, 64, 64, generator=torch.Generator().manual_seed(5))
+    net.train()
+    np.testing.assert_allclose(net(x).detach().numpy(), g["r2d3d18_out"], rtol=1e-4, atol=1e-5)
+    net.eval()
+    with torch.no_grad():
+        np.testing.assert_allclose(net(x).numpy(), g["r2d3d18_out_eval"], rtol=1e-4, atol=1e-5)
+        assert tuple(net(torch.zeros(1, 3, 16, 112, 112)).shape) == tuple(g["r2d3d18_shape112"]) == (1, 256, 16, 4, 4)
+
+
 def test_select_backbone_unknown_raises():
     with pytest.raises(NotImplementedError):
         select_backbone("resnet18")
