@@ -1,0 +1,76 @@
+"""Host logic of the pretraining driver on CPU with the oracle model; GPU: two epochs of the product
+model, checkpoint, resume, and the resumed run continues bit for bit."""
+import os
+import random
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from dualvar_b200 import pretrain_loop as L
+
+
+def _seed(s):
+    torch.manual_seed(s); np.random.seed(s); random.seed(s)
+
+
+def test_total_loss_follows_reference_order():
+    ret = {"clip_logits": torch.zeros(2, 3), "clip_labels": torch.zeros(2, dtype=torch.long),
+           "clip_contrast_loss": torch.tensor(1.0), "tc_contrast_loss": torch.tensor(2.0),
+           "aug_ranking_margin_contrast_loss": torch.tensor(4.0), "misc_loss": torch.tensor(8.0)}
+    assert float(L.total_loss(ret)) == 15.0
+    assert float(L.total_loss({"tc_contrast_loss": torch.tensor(2.0)})) == 2.0
+
+
+def test_checkpoint_files_and_resume_cpu(tmp_path):
+    from oracle import models as OM
+    _seed(0)
+    args = SimpleNamespace(shufflerank_theta=0.05)
+    model = OM.SimCLR_TimeSeriesV4("r3d", 128, 0.07, False, True, 2, 64, 0.07, 0.07, "clip-sr-tc", args)
+    opt = L.build_optimizer(model, lr=0.01)
+    assert isinstance(opt, torch.optim.SGD) and len(opt.param_groups) == len(list(model.parameters()))
+    data = [{"seq": torch.randn(2, 3, 3, 4, 32, 32)} for _ in range(2)]
+    hist, best, it = L.fit(model, data, opt, epochs=2, schedule=[1], model_path=str(tmp_path), log=lambda *_: None)
+    assert len(hist) == 2 and it == 5 and {"loss", "clip_contrast_loss", "clip_acc", "tc_acc"} <= set(hist[0])
+    assert abs(opt.param_groups[0]["lr"] - 0.001) < 1e-12            # MultiStepLR gamma 0.1 after epoch 1
+    files = sorted(os.listdir(tmp_path))
+    # pretrain.py:354 calls save_checkpoint(gap=0): the "previous epoch" it prunes is the file it is about to write, so
+    # every epoch's file stays (utils/utils.py:19-24)
+    assert {"latest.pth.tar", "epoch0.pth.tar", "epoch1.pth.tar"} <= set(files)
+    ckpt = torch.load(tmp_path / "latest.pth.tar", weights_only=False)
+    assert set(ckpt) == {"epoch", "state_dict", "best_acc", "optimizer", "iteration"} and ckpt["epoch"] == 1
+    model2 = OM.SimCLR_TimeSeriesV4("r3d", 128, 0.07, False, True, 2, 64, 0.07, 0.07, "clip-sr-tc", args)
+    opt2 = L.build_optimizer(model2, lr=0.01)
+    start, best2, it2 = L.load_checkpoint(str(tmp_path / "latest.pth.tar"), model2, opt2)
+    assert start == 2 and it2 == 5
+    for (n, a), (_, b) in zip(model.state_dict().items(), model2.state_dict().items()):
+        assert torch.equal(a, b), n
+
+
+@pytest.mark.gpu
+def test_product_model_trains_checkpoints_and_resumes(tmp_path):
+    from dualvar_b200 import models as PM
+    from dualvar_b200.engine import RawClips
+    dev = "cuda:0"
+    args = SimpleNamespace(shufflerank_theta=0.05)
+
+    def make():
+        _seed(0)
+        m = PM.SimCLR_TimeSeriesV4("r21d", 128, 0.07, False, True, 2, 64, 0.07, 0.07, "clip-sr-tc", args).to(dev)
+        return m, L.build_optimizer(m, lr=0.01)
+
+    gen = torch.Generator().manual_seed(3)
+    data = [torch.rand(4, 3, 24, 64, 64, generator=gen).to(dev) for _ in range(3)]   # loader frames (B,3,3*T,H,W)
+    to_input = lambda x: RawClips(x, 3)                                                # noqa: E731
+    model, opt = make()
+    np.random.seed(11)
+    L.fit(model, data, opt, epochs=1, model_path=str(tmp_path), to_input=to_input, log=lambda *_: None)
+    np.random.seed(12)
+    h_a, _, _ = L.fit(model, data, opt, epochs=2, start_epoch=1, to_input=to_input, log=lambda *_: None)
+    model2, opt2 = make()
+    start, _, it = L.load_checkpoint(str(tmp_path / "latest.pth.tar"), model2, opt2, map_location=dev)
+    assert start == 1 and it == 4
+    np.random.seed(12)
+    h_b, _, _ = L.fit(model2, data, opt2, epochs=2, start_epoch=1, iteration=it, to_input=to_input, log=lambda *_: None)
+    assert np.isfinite(h_a[0]["loss"]) and abs(h_a[0]["loss"] - h_b[0]["loss"]) <= 2e-3 * abs(h_a[0]["loss"])
