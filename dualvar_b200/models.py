@@ -153,8 +153,8 @@ class SimCLR_TimeSeriesV4(nn.Module):
 class LinearClassifier(nn.Module):
     """backbone -> global average pool -> [L2 norm] -> [BN1d] -> [dropout] -> Linear
     (model/classifier.py:9-84); returns (logit, pooled feature). The encoder runs on the sm_100a
-    kernels; the (B, 512) tail — final BN1d / dropout / fc — is a next-tier row
-    and uses torch modules."""
+    kernels, the Linear layers of the (B, feature_size) tail on the sgemm kernel; BatchNorm1d and
+    Dropout on that tiny tensor stay torch modules (Dropout must draw the reference's mask)."""
 
     def __init__(self, num_class=101, network='resnet50', dropout=0.5, use_dropout=True, use_l2_norm=False,
                  use_final_bn=False, nonlinear=False, proj_dim=128):
@@ -180,8 +180,21 @@ class LinearClassifier(nn.Module):
         feat3d = self.backbone.encode(block, pooled=True)
         if self.use_l2_norm:
             feat3d = O.l2norm(feat3d)
-        logit = self.final_fc(self.final_bn(feat3d) if self.use_final_bn else feat3d)
-        return logit, feat3d
+        h = self.final_bn(feat3d) if self.use_final_bn else feat3d
+        # final_fc: Linear layers on the sgemm kernel (bias / ReLU fused in its epilogue); Dropout stays torch's so the
+        # mask comes from the same Philox stream as the reference's (model/classifier.py:39-52)
+        mods = list(self.final_fc)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, nn.Linear):
+                fuse = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
+                h = O.linear(h, m, relu=fuse)
+                i += 2 if fuse else 1
+            else:
+                h = m(h)
+                i += 1
+        return h, feat3d
 
     def _initialize_weights(self, module):
         for name, param in module.named_parameters():

@@ -195,3 +195,36 @@ def test_moco_naked_and_simclr_naked_match_oracle():
     rr, rp = ref(x), prod(x)
     assert abs(rp["clip_contrast_loss"].item() - rr["clip_contrast_loss"].item()) <= 1e-2 * rr["clip_contrast_loss"].item()
     assert rp["clip_logits"].shape == rr["clip_logits"].shape == (16, 15)
+
+
+@pytest.mark.parametrize("kw", [dict(use_dropout=True, use_final_bn=True), dict(use_dropout=False, nonlinear=True, use_l2_norm=True)])
+def test_linear_classifier_matches_oracle(kw):
+    """classifier.py:888,935 call path: (logit, feat) = model(clips) in eval mode; same weights as the oracle.
+    Tolerance 1e-2 of the logit range (bf16 encoder), feature 1e-2 relative; backward reaches every parameter."""
+    import random
+    import numpy as np
+    from dualvar_b200 import models as PM
+    from oracle import models as OM
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = "cuda:0"
+    torch.manual_seed(0); np.random.seed(0); random.seed(0)
+    ref = OM.LinearClassifier(num_class=101, network="r21d", **kw).to(dev)
+    prod = PM.LinearClassifier(num_class=101, network="r21d", **kw)
+    prod.load_state_dict(ref.state_dict())
+    prod = prod.to(dev)
+    x = torch.randn(6, 3, 8, 64, 64, device=dev)
+    ref.train(); prod.train()
+    with torch.no_grad():
+        ref(x); prod(x)                       # one train-mode pass updates the running statistics on both sides
+    ref.eval(); prod.eval()
+    with torch.no_grad():
+        lr, fr = ref(x)
+        lp, fp = prod(x)
+    assert lp.shape == lr.shape == (6, 101) and fp.shape == fr.shape
+    assert ((fp - fr).norm() / fr.norm()).item() < 2e-2
+    assert ((lp - lr).abs().max() / (lr.abs().max() + 1e-12)).item() < 3e-2
+    prod.train()
+    lp, _ = prod(x)
+    torch.nn.functional.cross_entropy(lp, torch.randint(0, 101, (6,), device=dev)).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in prod.parameters())
