@@ -42,25 +42,36 @@ class _PeerReduce:
         torch.cuda.synchronize(device)
         dist.barrier()          # every rank's flags are zero before anybody signals
 
-    def __call__(self, t):
+    def next_call(self):
+        """(peer_buffers, rank, world, seq) of the next exchange: the trailing arguments of every dv_*_sync entry."""
         self.seq += 1
-        _lib.call("dv_allreduce_small_f64", ptr(t), t.numel(), self.ptrs, self.rank, self.world, self.seq, stream_ptr())
+        return self.ptrs, self.rank, self.world, self.seq
+
+    def __call__(self, t):
+        _lib.call("dv_allreduce_small_f64", ptr(t), t.numel(), *self.next_call(), stream_ptr())
 
 
-def small_allreduce_(t):
-    """In-place sum of a contiguous fp64 CUDA vector over the default process group."""
+def peer_state(device, n):
+    """The peer-memory exchange object if it is usable for vectors of n doubles on this process group, else None
+    (NCCL is then used). Set up lazily on first use - collectively, so all ranks must reach it together."""
     global _state
-    assert t.dtype == torch.float64 and t.is_cuda and t.is_contiguous()
     if _state is None:
         _state = False
         if _ENABLED and dist.get_backend() == "nccl":
             try:
-                _state = _PeerReduce(t.device)
+                _state = _PeerReduce(device)
             except Exception as e:  # noqa: BLE001 - peer mapping is an optimisation; NCCL carries the same sum
                 warnings.warn(f"dualvar_b200: NVLink peer all-reduce unavailable ({e!r}); using NCCL for BatchNorm statistics")
                 _state = False
-    if _state is not False and t.numel() <= _MAX_ELEMS:
-        _state(t)
+    return _state if (_state is not False and n <= _MAX_ELEMS) else None
+
+
+def small_allreduce_(t):
+    """In-place sum of a contiguous fp64 CUDA vector over the default process group."""
+    assert t.dtype == torch.float64 and t.is_cuda and t.is_contiguous()
+    peer = peer_state(t.device, t.numel())
+    if peer is not None:
+        peer(t)
     else:
         dist.all_reduce(t)
     return t

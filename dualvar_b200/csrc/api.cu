@@ -74,6 +74,12 @@ int row_axpy(const float* alpha, int ld_alpha, const float* x, float* y, int row
 int probe_overlap(const void* src, void* out, int c1, cudaStream_t stream);
 int mma_rate(int n, int n_mma, int region, int mode, long long* out, int grid, cudaStream_t stream);
 long long small_allreduce_buffer_bytes();
+int bn_finalize_sync(const double* stats, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                     float* ss, float* saved, int C, int Cp, double count_global, float eps, float momentum,
+                     const long long* peer_ptrs, int rank, int world, long long seq, cudaStream_t stream);
+int bn_bwd_finalize_sync(const double* sums_local, const float* gamma, const float* saved, float* dgamma, float* dbeta,
+                         float* coef, int C, int Cp, double count_global, float grad_beta, const long long* peer_ptrs,
+                         int rank, int world, long long seq, cudaStream_t stream);
 int small_allreduce_f64(double* inout, int n, const long long* peer_ptrs, int rank, int world, long long seq,
                         cudaStream_t stream);
 int sgd_momentum_step(const long long* table, int n_chunks, float lr, float mu, float wd, int first,
@@ -414,6 +420,24 @@ int dv_allreduce_small_f64(double* inout, int n, const int64_t* peer_buffers, in
                            void* stream) {
   DV_REQUIRE(inout && peer_buffers, "NULL pointer");
   return small_allreduce_f64(inout, n, reinterpret_cast<const long long*>(peer_buffers), rank, world, seq, ST);
+}
+
+int dv_bn_finalize_sync(const double* stats, const float* gamma, const float* beta, float* running_mean,
+                        float* running_var, float* scale_shift, float* saved, int C, int Cp, double count_global,
+                        float eps, float momentum, const int64_t* peer_buffers, int rank, int world, int64_t seq,
+                        void* stream) {
+  DV_REQUIRE(stats && gamma && beta && scale_shift && saved && peer_buffers && C > 0 && Cp >= C && Cp % 8 == 0,
+             "bad bn_finalize_sync arguments");
+  return bn_finalize_sync(stats, gamma, beta, running_mean, running_var, scale_shift, saved, C, Cp, count_global, eps,
+                          momentum, reinterpret_cast<const long long*>(peer_buffers), rank, world, seq, ST);
+}
+
+int dv_bn_bwd_finalize_sync(const double* sums_local, const float* gamma, const float* saved, float* dgamma,
+                            float* dbeta, float* coef, int C, int Cp, double count_global, float grad_beta,
+                            const int64_t* peer_buffers, int rank, int world, int64_t seq, void* stream) {
+  DV_REQUIRE(sums_local && gamma && saved && coef && peer_buffers && count_global > 0, "bad bn_bwd_finalize_sync arguments");
+  return bn_bwd_finalize_sync(sums_local, gamma, saved, dgamma, dbeta, coef, C, Cp, count_global, grad_beta,
+                              reinterpret_cast<const long long*>(peer_buffers), rank, world, seq, ST);
 }
 
 int dv_debug_set_conv_profile(int64_t* buf) {

@@ -15,6 +15,7 @@
 // reads contiguous memory.
 #include <cuda_bf16.h>
 
+#include "bn_math.cuh"
 #include "host_common.h"
 
 namespace dv {
@@ -84,31 +85,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, const float
                                    float momentum, int training) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= Cp) return;
-  if (c >= C) {
-    ss[c] = 0.f; ss[Cp + c] = 0.f;
-    if (saved) { saved[c] = 0.f; saved[Cp + c] = 0.f; }
-    return;
-  }
-  float mean, invstd;
-  if (training) {
-    const double m = stats[c] / count;
-    double var = stats[Cp + c] / count - m * m;
-    if (var < 0.0) var = 0.0;
-    mean = (float)m;
-    invstd = (float)(1.0 / sqrt(var + (double)eps));
-    if (running_mean) {
-      const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
-      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
-    }
-  } else {
-    mean = running_mean[c];
-    invstd = rsqrtf(running_var[c] + eps);
-  }
-  const float sc = gamma[c] * invstd;
-  ss[c] = sc;
-  ss[Cp + c] = beta[c] - mean * sc;
-  if (saved) { saved[c] = mean; saved[Cp + c] = invstd; }
+  bn_finalize_channel(c, training ? stats[c] : 0.0, training ? stats[Cp + c] : 0.0, gamma, beta, running_mean,
+                      running_var, ss, saved, C, Cp, count, eps, momentum, training);
 }
 
 // ------------------------------------------------------------------------------ apply
@@ -273,23 +251,10 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums_local,
                                        float grad_beta) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= Cp) return;
-  if (c >= C) {
-    coef[c] = 0.f; coef[Cp + c] = 0.f; coef[2 * Cp + c] = 0.f;
-    return;
-  }
-  const double mean = saved[c], invstd = saved[Cp + c];
-  const double sg_l = sums_local[c], sgy_l = sums_local[Cp + c];
-  const double dg_l = (sgy_l - mean * sg_l) * invstd;
-  if (dgamma) dgamma[c] = (grad_beta != 0.f ? grad_beta * dgamma[c] : 0.f) + (float)dg_l;
-  if (dbeta) dbeta[c] = (grad_beta != 0.f ? grad_beta * dbeta[c] : 0.f) + (float)sg_l;
-  const double sg = sums_global[c], sgy = sums_global[Cp + c];
-  const double dg = (sgy - mean * sg) * invstd;
-  const double A = (double)gamma[c] * invstd;
-  const double B = -A * invstd * dg / count_global;
-  const double Cc = A * (-sg / count_global + mean * invstd * dg / count_global);
-  coef[c] = (float)A;
-  coef[Cp + c] = (float)B;
-  coef[2 * Cp + c] = (float)Cc;
+  const bool real = c < C;
+  bn_bwd_finalize_channel(c, real ? sums_local[c] : 0.0, real ? sums_local[Cp + c] : 0.0, real ? sums_global[c] : 0.0,
+                          real ? sums_global[Cp + c] : 0.0, gamma, saved, dgamma, dbeta, coef, C, Cp, count_global,
+                          grad_beta);
 }
 
 template <bool kD2, int kMask, bool kGout, int kRows>

@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "bn_math.cuh"
 #include "host_common.h"
 
 namespace dv {
@@ -38,19 +39,19 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
   return v;
 }
 
-__global__ void __launch_bounds__(512, 1)
-small_allreduce_kernel(double* __restrict__ inout, int n, ArPeers peers, int rank, int world, unsigned long long seq) {
+// Steps 1-3 for the calling CTA: push `src[0:n]` to every rank, signal, wait for every rank's signal. Afterwards
+// ar_sum(i) returns the sum over ranks (in rank order) of element i.
+__device__ __forceinline__ const double* ar_exchange(const double* __restrict__ src, int n, const ArPeers& peers,
+                                                     int rank, int world, unsigned long long seq) {
   const int parity = (int)(seq & 1ull);
   const size_t slot_elems = (size_t)kArMaxElems;
   const size_t flags_off = 2ull * kArMaxWorld * slot_elems;   // in doubles (= u64 words)
-  // 1. push
   for (int p = 0; p < world; ++p) {
     double* dst = reinterpret_cast<double*>(peers.base[p]) + ((size_t)parity * kArMaxWorld + rank) * slot_elems;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = inout[i];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
   }
   __threadfence_system();
   __syncthreads();
-  // 2. signal, 3. wait
   if ((int)threadIdx.x < world) {
     unsigned long long* remote = reinterpret_cast<unsigned long long*>(peers.base[threadIdx.x]) + flags_off +
                                  (size_t)parity * kArMaxWorld + rank;
@@ -66,12 +67,46 @@ small_allreduce_kernel(double* __restrict__ inout, int n, ArPeers peers, int ran
     }
   }
   __syncthreads();
-  // 4. reduce in rank order
-  const double* base = reinterpret_cast<const double*>(peers.base[rank]) + (size_t)parity * kArMaxWorld * slot_elems;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    double s = 0.0;
-    for (int q = 0; q < world; ++q) s += __ldcv(base + (size_t)q * slot_elems + i);
-    inout[i] = s;
+  return reinterpret_cast<const double*>(peers.base[rank]) + (size_t)parity * kArMaxWorld * slot_elems;
+}
+__device__ __forceinline__ double ar_sum(const double* base, int world, int i) {
+  double s = 0.0;
+  for (int q = 0; q < world; ++q) s += __ldcv(base + (size_t)q * kArMaxElems + i);
+  return s;
+}
+
+__global__ void __launch_bounds__(512, 1)
+small_allreduce_kernel(double* __restrict__ inout, int n, ArPeers peers, int rank, int world, unsigned long long seq) {
+  const double* base = ar_exchange(inout, n, peers, rank, world, seq);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) inout[i] = ar_sum(base, world, i);
+}
+
+// Cross-replica BatchNorm forward: exchange of the local (sum, sumsq) + finalisation in one launch
+// (nn.SyncBatchNorm forward: all_gather of the per-rank statistics, then mean/invstd/running-stat update).
+__global__ void __launch_bounds__(512, 1)
+bn_finalize_sync_kernel(const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+                        float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ ss,
+                        float* __restrict__ saved, int C, int Cp, double count_global, float eps, float momentum,
+                        ArPeers peers, int rank, int world, unsigned long long seq) {
+  const double* base = ar_exchange(stats, 2 * Cp, peers, rank, world, seq);
+  for (int c = threadIdx.x; c < Cp; c += blockDim.x)
+    bn_finalize_channel(c, ar_sum(base, world, c), ar_sum(base, world, Cp + c), gamma, beta, running_mean, running_var, ss,
+                        saved, C, Cp, count_global, eps, momentum, 1);
+}
+
+// Cross-replica BatchNorm backward: exchange of (sum g, sum g*y) + dgamma/dbeta (local sums) + dy coefficients
+// (global sums) in one launch (nn.SyncBatchNorm backward: all_reduce of sum_dy / sum_dy_xmu).
+__global__ void __launch_bounds__(512, 1)
+bn_bwd_finalize_sync_kernel(const double* __restrict__ sums_local, const float* __restrict__ gamma,
+                            const float* __restrict__ saved, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                            float* __restrict__ coef, int C, int Cp, double count_global, float grad_beta,
+                            ArPeers peers, int rank, int world, unsigned long long seq) {
+  const double* base = ar_exchange(sums_local, 2 * Cp, peers, rank, world, seq);
+  for (int c = threadIdx.x; c < Cp; c += blockDim.x) {
+    const bool real = c < C;
+    bn_bwd_finalize_channel(c, real ? sums_local[c] : 0.0, real ? sums_local[Cp + c] : 0.0,
+                            real ? ar_sum(base, world, c) : 0.0, real ? ar_sum(base, world, Cp + c) : 0.0, gamma, saved,
+                            dgamma, dbeta, coef, C, Cp, count_global, grad_beta);
   }
 }
 
@@ -87,6 +122,37 @@ int small_allreduce_f64(double* inout, int n, const long long* peer_ptrs, int ra
   ArPeers peers;
   for (int i = 0; i < kArMaxWorld; ++i) peers.base[i] = i < world ? (unsigned long long)peer_ptrs[i] : 0ull;
   small_allreduce_kernel<<<1, 512, 0, stream>>>(inout, n, peers, rank, world, (unsigned long long)seq);
+  DV_LAUNCH_OK();
+  return kOk;
+}
+
+static int ar_peers(ArPeers* peers, int n, const long long* peer_ptrs, int rank, int world, long long seq) {
+  if (n <= 0 || n > kArMaxElems) return fail(kBadArg, "peer all-reduce: n must be in 1..%d", kArMaxElems);
+  if (world < 1 || world > kArMaxWorld || rank < 0 || rank >= world) return fail(kBadArg, "peer all-reduce: bad rank/world");
+  if (seq < 1) return fail(kBadArg, "peer all-reduce: seq starts at 1");
+  for (int i = 0; i < kArMaxWorld; ++i) peers->base[i] = i < world ? (unsigned long long)peer_ptrs[i] : 0ull;
+  return kOk;
+}
+
+int bn_finalize_sync(const double* stats, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                     float* ss, float* saved, int C, int Cp, double count_global, float eps, float momentum,
+                     const long long* peer_ptrs, int rank, int world, long long seq, cudaStream_t stream) {
+  ArPeers peers;
+  if (int rc = ar_peers(&peers, 2 * Cp, peer_ptrs, rank, world, seq)) return rc;
+  bn_finalize_sync_kernel<<<1, 512, 0, stream>>>(stats, gamma, beta, running_mean, running_var, ss, saved, C, Cp,
+                                                 count_global, eps, momentum, peers, rank, world,
+                                                 (unsigned long long)seq);
+  DV_LAUNCH_OK();
+  return kOk;
+}
+
+int bn_bwd_finalize_sync(const double* sums_local, const float* gamma, const float* saved, float* dgamma, float* dbeta,
+                         float* coef, int C, int Cp, double count_global, float grad_beta, const long long* peer_ptrs,
+                         int rank, int world, long long seq, cudaStream_t stream) {
+  ArPeers peers;
+  if (int rc = ar_peers(&peers, 2 * Cp, peer_ptrs, rank, world, seq)) return rc;
+  bn_bwd_finalize_sync_kernel<<<1, 512, 0, stream>>>(sums_local, gamma, saved, dgamma, dbeta, coef, C, Cp, count_global,
+                                                     grad_beta, peers, rank, world, (unsigned long long)seq);
   DV_LAUNCH_OK();
   return kOk;
 }

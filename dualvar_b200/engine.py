@@ -281,17 +281,25 @@ def conv_stats(ctx, x, conv, bn):
     if bn is None:
         r.ss = r.saved = None
         return r
-    if training_stats and _is_sync(bn):
-        comm.small_allreduce_(stats)
-        r.count *= dist.get_world_size()
-        r.sync = True
     r.ss = torch.empty(2 * g.Cout_p, dtype=torch.float32, device=dev)
     r.saved = torch.empty(2 * g.Cout_p, dtype=torch.float32, device=dev) if training_stats else None
     momentum = bn.momentum if bn.momentum is not None else 0.1
     track = bn.track_running_stats and bn.running_mean is not None
-    call("dv_bn_finalize", ptr(stats), ptr(bn.weight.detach()), ptr(bn.bias.detach()),
-         ptr(bn.running_mean) if track else None, ptr(bn.running_var) if track else None,
-         ptr(r.ss), ptr(r.saved), Cout, g.Cout_p, ctypes.c_double(r.count), ctypes.c_float(bn.eps),
+    fin_args = (ptr(stats), ptr(bn.weight.detach()), ptr(bn.bias.detach()),
+                ptr(bn.running_mean) if track else None, ptr(bn.running_var) if track else None,
+                ptr(r.ss), ptr(r.saved), Cout, g.Cout_p)
+    if training_stats and _is_sync(bn):
+        r.count *= dist.get_world_size()
+        r.sync = True
+        peer = comm.peer_state(dev, 2 * g.Cout_p)
+        if peer is not None:      # exchange + finalisation in one launch over NVLink peer memory
+            call("dv_bn_finalize_sync", *fin_args, ctypes.c_double(r.count), ctypes.c_float(bn.eps),
+                 ctypes.c_float(momentum), *peer.next_call(), stream_ptr())
+            if track:
+                bn.num_batches_tracked += 1
+            return r
+        comm.small_allreduce_(stats)
+    call("dv_bn_finalize", *fin_args, ctypes.c_double(r.count), ctypes.c_float(bn.eps),
          ctypes.c_float(momentum), 1 if training_stats else 0, stream_ptr())
     if training_stats and track:
         bn.num_batches_tracked += 1
@@ -411,17 +419,23 @@ def activate(ctx, r1, r2=None, res=None, relu=True, out=None, out_coff=0):
                 sums = ctx.zeros64(2 * Cp, dev)
                 call("dv_bn_bwd_reduce", ptr(dout), ptr(dout2), ptr(out_t), ptr(r.y), mask_ss, ptr(sums), rows, Cp,
                      o_ld, o_coff, 1 if relu else 0, stream_ptr())
-            sums_g = sums
-            if r.sync:
-                sums_g = sums.clone()
-                comm.small_allreduce_(sums_g)
             bn = r.bn
             dgamma = torch.empty_like(bn.weight)
             dbeta = torch.empty_like(bn.bias)
             coef = torch.empty(3 * Cp, dtype=torch.float32, device=dev)
-            call("dv_bn_bwd_finalize", ptr(sums), ptr(sums_g), ptr(bn.weight.detach()), ptr(r.saved),
-                 ptr(dgamma), ptr(dbeta), ptr(coef), r.geom.Cout, Cp, ctypes.c_double(r.count),
-                 ctypes.c_float(0.0), stream_ptr())
+            peer = comm.peer_state(dev, 2 * Cp) if r.sync else None
+            if peer is not None:  # exchange of the sums + finalisation in one launch over NVLink peer memory
+                call("dv_bn_bwd_finalize_sync", ptr(sums), ptr(bn.weight.detach()), ptr(r.saved), ptr(dgamma),
+                     ptr(dbeta), ptr(coef), r.geom.Cout, Cp, ctypes.c_double(r.count), ctypes.c_float(0.0),
+                     *peer.next_call(), stream_ptr())
+            else:
+                sums_g = sums
+                if r.sync:
+                    sums_g = sums.clone()
+                    comm.small_allreduce_(sums_g)
+                call("dv_bn_bwd_finalize", ptr(sums), ptr(sums_g), ptr(bn.weight.detach()), ptr(r.saved),
+                     ptr(dgamma), ptr(dbeta), ptr(coef), r.geom.Cout, Cp, ctypes.c_double(r.count),
+                     ctypes.c_float(0.0), stream_ptr())
             ctx.add_param_grad(bn.weight, dgamma)
             ctx.add_param_grad(bn.bias, dbeta)
             dy = torch.empty_like(r.y)

@@ -221,6 +221,17 @@ int64_t dv_allreduce_small_buffer_bytes(void);
 int dv_allreduce_small_f64(double* inout, int n, const int64_t* peer_buffers, int rank, int world, int64_t seq,
                            void* stream);
 
+/* dv_bn_finalize (training mode) and dv_bn_bwd_finalize with the cross-replica exchange of their inputs fused in:
+ * one launch pushes this rank's statistics to all peers, waits for theirs, sums in rank order and finalises
+ * (peer_buffers / rank / world / seq as for dv_allreduce_small_f64; count_global = values per channel over all ranks). */
+int dv_bn_finalize_sync(const double* stats, const float* gamma, const float* beta, float* running_mean,
+                        float* running_var, float* scale_shift, float* saved, int C, int Cp, double count_global,
+                        float eps, float momentum, const int64_t* peer_buffers, int rank, int world, int64_t seq,
+                        void* stream);
+int dv_bn_bwd_finalize_sync(const double* sums_local, const float* gamma, const float* saved, float* dgamma,
+                            float* dbeta, float* coef, int C, int Cp, double count_global, float grad_beta,
+                            const int64_t* peer_buffers, int rank, int world, int64_t seq, void* stream);
+
 /* debug (tests/diag only): per-CTA role cycle counters of the next conv_tile_kernel launches are written to
  * buf [148][16] (producer total/wait, MMA total/wait-data/wait-accumulator, epilogue total/wait, tiles, epilogue phases); NULL = off */
 int dv_debug_set_conv_profile(int64_t* buf);
