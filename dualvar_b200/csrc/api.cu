@@ -40,7 +40,8 @@ struct PoolGeom {
 };
 int avgpool_fwd(const void* x, float* out, int N, int S, int C, int Cp, int ld_out, cudaStream_t stream);
 int avgpool_bwd(const float* dout, void* dx, int N, int S, int C, int Cp, int ld_out, cudaStream_t stream);
-int maxpool_fwd(const void* x, void* y, const PoolGeom& g, cudaStream_t stream);
+int maxpool_fwd(const void* x, void* y, uint8_t* idx, const PoolGeom& g, cudaStream_t stream);
+int maxpool_bwd_idx(const uint8_t* idx, const void* dy, void* dx, const PoolGeom& g, cudaStream_t stream);
 int maxpool_bwd(const void* x, const void* y, const void* dy, void* dx, const PoolGeom& g, cudaStream_t stream);
 int ingest(const float* src, void* dst, const int* perm, long long sb, long long sv, long long sc,
            long long st, int B, int C, int T, int H, int W, int view, int nv, int n_series,
@@ -254,7 +255,15 @@ static PoolGeom to_pool(const dv_pool_geom* g) {
 }
 int dv_maxpool3d_fwd(const void* x, void* y, const dv_pool_geom* g, void* stream) {
   DV_REQUIRE(x && y && g && g->Cp % 8 == 0, "bad maxpool arguments");
-  return maxpool_fwd(x, y, to_pool(g), ST);
+  return maxpool_fwd(x, y, nullptr, to_pool(g), ST);
+}
+int dv_maxpool3d_fwd_idx(const void* x, void* y, uint8_t* argmax, const dv_pool_geom* g, void* stream) {
+  DV_REQUIRE(x && y && argmax && g && g->Cp % 8 == 0, "bad maxpool arguments");
+  return maxpool_fwd(x, y, argmax, to_pool(g), ST);
+}
+int dv_maxpool3d_bwd_idx(const uint8_t* argmax, const void* dy, void* dx, const dv_pool_geom* g, void* stream) {
+  DV_REQUIRE(argmax && dy && dx && g && g->Cp % 8 == 0, "bad maxpool arguments");
+  return maxpool_bwd_idx(argmax, dy, dx, to_pool(g), ST);
 }
 int dv_maxpool3d_bwd(const void* x, const void* y, const void* dy, void* dx, const dv_pool_geom* g,
                      void* stream) {

@@ -51,10 +51,11 @@ struct PoolGeom {
   int kt, kh, kw, st, sh, sw, pt, ph, pw;
 };
 
-// One thread = one output position x 8 channels. Saves nothing: backward recomputes the argmax
-// (first maximum in (t,h,w) scan order, as ATen does).
+// One thread = one output position x 8 channels. Optionally records the argmax as the window offset
+// (a*kh + b)*kw + c of the FIRST maximum in (t,h,w) scan order (the element ATen routes the gradient to), one byte
+// per element, which turns backward into a plain gather.
 __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
-                                   const PoolGeom g, long long total) {
+                                   uint8_t* __restrict__ idx, const PoolGeom g, long long total) {
   const int G = g.Cp >> 3;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -65,8 +66,9 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
     const int to = (int)(r % g.To);
     const long long n = r / g.To;
     float m[8];
+    uint32_t am[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+    for (int j = 0; j < 8; ++j) { m[j] = -INFINITY; am[j] = 0u; }
     for (int a = 0; a < g.kt; ++a) {
       const int t = to * g.st - g.pt + a;
       if (t < 0 || t >= g.T) continue;
@@ -79,11 +81,12 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
           const uint4 u = *reinterpret_cast<const uint4*>(
               x + ((((n * g.T + t) * g.H + h) * g.W + w) * (long long)g.Cp + cg * 8));
           const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
+          const uint32_t code = (uint32_t)((a * g.kh + b) * g.kw + c);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float2 f = __bfloat1622float2(hh[j]);
-            m[2 * j] = fmaxf(m[2 * j], f.x);
-            m[2 * j + 1] = fmaxf(m[2 * j + 1], f.y);
+            if (f.x > m[2 * j]) { m[2 * j] = f.x; am[2 * j] = code; }              // strict >: first maximum wins
+            if (f.y > m[2 * j + 1]) { m[2 * j + 1] = f.y; am[2 * j + 1] = code; }
           }
         }
       }
@@ -93,6 +96,12 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
 #pragma unroll
     for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(m[2 * j], m[2 * j + 1]);
     *reinterpret_cast<uint4*>(y + i * 8) = o;
+    if (idx != nullptr) {
+      uint2 k;
+      k.x = am[0] | (am[1] << 8) | (am[2] << 16) | (am[3] << 24);
+      k.y = am[4] | (am[5] << 8) | (am[6] << 16) | (am[7] << 24);
+      *reinterpret_cast<uint2*>(idx + i * 8) = k;
+    }
   }
 }
 
@@ -157,6 +166,55 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             if (eq & (1u << j)) acc[j] += __bfloat162float(dv_[j]);
+        }
+    uint4 o;
+    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+    *reinterpret_cast<uint4*>(dx + i * 8) = o;
+  }
+}
+
+// Backward with the recorded argmax: one thread = one INPUT position x 8 channels; for every window that contains the
+// position, 8 index bytes tell which channels routed their gradient here. (kt*kh*kw) x 24 bytes per thread instead of
+// re-scanning each window for earlier ties.
+__global__ void maxpool_bwd_idx_kernel(const uint8_t* __restrict__ idx, const __nv_bfloat16* __restrict__ dy,
+                                       __nv_bfloat16* __restrict__ dx, const PoolGeom g, long long total) {
+  const int G = g.Cp >> 3;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % G);
+    long long r = i / G;
+    const int w = (int)(r % g.W); r /= g.W;
+    const int h = (int)(r % g.H); r /= g.H;
+    const int t = (int)(r % g.T);
+    const long long n = r / g.T;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const int to_lo = max(0, (t + g.pt - g.kt + g.st) / g.st), to_hi = min(g.To - 1, (t + g.pt) / g.st);
+    const int ho_lo = max(0, (h + g.ph - g.kh + g.sh) / g.sh), ho_hi = min(g.Ho - 1, (h + g.ph) / g.sh);
+    const int wo_lo = max(0, (w + g.pw - g.kw + g.sw) / g.sw), wo_hi = min(g.Wo - 1, (w + g.pw) / g.sw);
+    for (int to = to_lo; to <= to_hi; ++to)
+      for (int ho = ho_lo; ho <= ho_hi; ++ho)
+        for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+          // my offset inside window (to,ho,wo)
+          const uint32_t code = (uint32_t)(((t - (to * g.st - g.pt)) * g.kh + (h - (ho * g.sh - g.ph))) * g.kw +
+                                           (w - (wo * g.sw - g.pw)));
+          const long long oo = ((((n * g.To + to) * g.Ho + ho) * g.Wo + wo) * (long long)g.Cp + cg * 8);
+          const uint2 k = *reinterpret_cast<const uint2*>(idx + oo);
+          const uint32_t pat = code * 0x01010101u;
+          // bytes equal to code -> zero bytes in k ^ pat
+          const uint32_t x0 = k.x ^ pat, x1 = k.y ^ pat;
+          const uint32_t z0 = (x0 - 0x01010101u) & ~x0 & 0x80808080u, z1 = (x1 - 0x01010101u) & ~x1 & 0x80808080u;
+          if ((z0 | z1) == 0u) continue;
+          const uint4 ud = *reinterpret_cast<const uint4*>(dy + oo);
+          const __nv_bfloat16* dv_ = reinterpret_cast<const __nv_bfloat16*>(&ud);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (((x0 >> (8 * j)) & 0xffu) == 0u) acc[j] += __bfloat162float(dv_[j]);
+            if (((x1 >> (8 * j)) & 0xffu) == 0u) acc[4 + j] += __bfloat162float(dv_[4 + j]);
+          }
         }
     uint4 o;
     __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
@@ -288,10 +346,11 @@ int avgpool_bwd(const float* dout, void* dx, int N, int S, int C, int Cp, int ld
   return kOk;
 }
 
-int maxpool_fwd(const void* x, void* y, const PoolGeom& g, cudaStream_t stream) {
+int maxpool_fwd(const void* x, void* y, uint8_t* idx, const PoolGeom& g, cudaStream_t stream) {
   const long long total = (long long)g.N * g.To * g.Ho * g.Wo * (g.Cp / 8);
+  if (idx != nullptr && g.kt * g.kh * g.kw > 255) return fail(kUnsupported, "max-pool window too large for 1-byte argmax");
   maxpool_fwd_kernel<<<flat_grid(total, 256), 256, 0, stream>>>((const __nv_bfloat16*)x,
-                                                                (__nv_bfloat16*)y, g, total);
+                                                                (__nv_bfloat16*)y, idx, g, total);
   DV_LAUNCH_OK();
   return kOk;
 }
@@ -302,6 +361,14 @@ int maxpool_bwd(const void* x, const void* y, const void* dy, void* dx, const Po
   maxpool_bwd_kernel<<<flat_grid(total, 256), 256, 0, stream>>>(
       (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx,
       g, total);
+  DV_LAUNCH_OK();
+  return kOk;
+}
+
+int maxpool_bwd_idx(const uint8_t* idx, const void* dy, void* dx, const PoolGeom& g, cudaStream_t stream) {
+  const long long total = (long long)g.N * g.T * g.H * g.W * (g.Cp / 8);
+  maxpool_bwd_idx_kernel<<<flat_grid(total, 256), 256, 0, stream>>>(idx, (const __nv_bfloat16*)dy,
+                                                                    (__nv_bfloat16*)dx, g, total);
   DV_LAUNCH_OK();
   return kOk;
 }

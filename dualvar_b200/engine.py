@@ -513,12 +513,19 @@ def max_pool(ctx, x, kernel, stride, padding):
     To, Ho, Wo = (T + 2 * pt - kt) // st + 1, (H + 2 * ph - kh) // sh + 1, (W + 2 * pw - kw) // sw + 1
     geom = (ctypes.c_int32 * 17)(N, T, H, W, To, Ho, Wo, Cp, kt, kh, kw, st, sh, sw, pt, ph, pw)
     y = torch.empty((N, To, Ho, Wo, Cp), dtype=torch.bfloat16, device=x.data.device)
-    call("dv_maxpool3d_fwd", ptr(x.data), ptr(y), geom, stream_ptr())
+    track = ctx.record and x.needs_grad
+    # training: 1-byte argmax per output element (backward becomes a gather instead of re-scanning windows for ties,
+    # which is what made the 3x3x3 stride-1 pools of the Inception blocks 20 % of an S3D-G step)
+    idx = torch.empty((N, To, Ho, Wo, Cp), dtype=torch.uint8, device=x.data.device) if track else None
+    if track:
+        call("dv_maxpool3d_fwd_idx", ptr(x.data), ptr(y), ptr(idx), geom, stream_ptr())
+    else:
+        call("dv_maxpool3d_fwd", ptr(x.data), ptr(y), geom, stream_ptr())
     out = Act(y, x.C)
-    if ctx.record and x.needs_grad:
+    if track:
         def backward():
             dx = torch.empty_like(x.data)
-            call("dv_maxpool3d_bwd", ptr(x.data), ptr(y), ptr(_materialize_grad(out)), ptr(dx), geom, stream_ptr())
+            call("dv_maxpool3d_bwd_idx", ptr(idx), ptr(_materialize_grad(out)), ptr(dx), geom, stream_ptr())
             _acc_grad(x, dx)
             out.grad = None
         ctx.tape.append(backward)

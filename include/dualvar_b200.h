@@ -119,6 +119,11 @@ typedef struct dv_pool_geom {
 int dv_maxpool3d_fwd(const void* x, void* y, const dv_pool_geom* g, void* stream);
 int dv_maxpool3d_bwd(const void* x, const void* y, const void* dy, void* dx, const dv_pool_geom* g,
                      void* stream);
+/* Training forward that also records, per output element, the window offset (a*kh + b)*kw + c of the first maximum
+ * (1 byte, [N][To][Ho][Wo][Cp]); backward is then a gather over the windows containing each input position - the
+ * tie rule (first maximum in scan order) is the same as dv_maxpool3d_bwd's and ATen's. */
+int dv_maxpool3d_fwd_idx(const void* x, void* y, uint8_t* argmax, const dv_pool_geom* g, void* stream);
+int dv_maxpool3d_bwd_idx(const uint8_t* argmax, const void* dy, void* dx, const dv_pool_geom* g, void* stream);
 /* fp32 clips -> bf16 NDHWC (C<=4 -> 8 channels): element (b,view,c,t,h,w) of src is at
  * b*sb + view*sv + c*sc + t*st + h*W + w. Output clip n = b*nv + j holds view (view + j) of sample b,
  * i.e. nv consecutive views per sample in the reference's block.view(-1, C, T, H, W) order

@@ -210,6 +210,35 @@ def test_maxpool_forward_backward_matches_torch():
         assert _rel2(K.from_ndhwc(xa.grad, 24), xr.grad) < 1e-2
 
 
+def test_maxpool_backward_tie_rule_matches_torch():
+    """ReLU'd inputs are full of exact ties (zeros): the gradient must go to the FIRST maximum of each window in
+    (t,h,w) scan order, as ATen's max_pool3d does - for the recorded-argmax path and the re-scanning C-ABI entry."""
+    import ctypes
+    from dualvar_b200 import _lib, engine as E, kernels as K
+    gen = torch.Generator(device=dev).manual_seed(6)
+    for kernel, stride, pad in [((3, 3, 3), (1, 1, 1), (1, 1, 1)), ((1, 3, 3), (1, 2, 2), (0, 1, 1))]:
+        x = torch.relu(torch.randn(2, 16, 5, 12, 11, device=dev, generator=gen) - 0.8).bfloat16().float()
+        xr = x.clone().requires_grad_(True)
+        yr = F.max_pool3d(xr, kernel, stride, pad)
+        gy = (torch.randint(-3, 4, yr.shape, device=dev, generator=gen).float() / 4)    # exactly representable sums
+        yr.backward(gy)
+        ctx = E.Context(training=True)
+        xa = E.Act(K.to_ndhwc(x), 16)
+        out = E.max_pool(ctx, xa, kernel, stride, pad)
+        assert torch.equal(K.from_ndhwc(out.data, 16), yr.detach())
+        out.grad = K.to_ndhwc(gy)
+        E.run_backward(ctx)
+        assert torch.equal(K.from_ndhwc(xa.grad, 16), xr.grad)
+        # the index-free entry point (re-scans the window for earlier ties) gives the same answer
+        N, T, H, W, Cp = xa.shape5
+        To, Ho, Wo = out.data.shape[1:4]
+        geom = (ctypes.c_int32 * 17)(N, T, H, W, To, Ho, Wo, Cp, *kernel, *stride, *pad)
+        dx = torch.empty_like(xa.data)
+        _lib.call("dv_maxpool3d_bwd", _lib.ptr(xa.data), _lib.ptr(out.data), _lib.ptr(K.to_ndhwc(gy)), _lib.ptr(dx), geom,
+                  _lib.stream_ptr())
+        assert torch.equal(K.from_ndhwc(dx, 16), xr.grad)
+
+
 def test_fused_sgd_matches_torch_sgd():
     """dualvar_b200.optim.SGD (one launch for all tensors) vs torch.optim.SGD, three steps with an lr change."""
     from dualvar_b200.optim import SGD
