@@ -224,17 +224,19 @@ def run_ours(args):
     launches = _lib.load().dv_launch_count() - launches0
     # Kernel attribution for the roofline: the same steps again with CUDA events around every conv call on its
     # launching stream. The product path runs the weight gradients on a side stream next to the BatchNorm
-    # passes, where per-launch event times overlap other kernels; for this pass they are folded back onto one
+    # passes and the two backbone passes on two streams, where per-launch event times overlap other kernels; for this
+    # pass everything is folded back onto one
     # stream so that a launch's duration is its own (ms_step_serial is the step time of that pass).
     from dualvar_b200 import engine as _engine
-    side_was = _engine.WGRAD_SIDE_STREAM
+    side_was, pass_was = _engine.WGRAD_SIDE_STREAM, _engine.PASS_STREAMS
     _engine.WGRAD_SIDE_STREAM = False
+    _engine.PASS_STREAMS = False
     timer = _lib.KernelTimer(["dv_conv3d_fprop_bf16", "dv_conv3d_dgrad_bf16", "dv_conv3d_dgrad_bnred_bf16", "dv_conv3d_wgrad_bf16",
                               "dv_conv3d_stem_fprop_bf16", "dv_conv3d_stem_wgrad_bf16"])
     _lib.set_timer(timer)
     ms_step_serial = timed(args.steps, False, 0)
     _lib.set_timer(None)
-    _engine.WGRAD_SIDE_STREAM = side_was
+    _engine.WGRAD_SIDE_STREAM, _engine.PASS_STREAMS = side_was, pass_was
     ksum = timer.summary()
     # end-to-end: host buffers, H2D of every step's input inside the timed region (double-buffered on a
     # copy stream), D2H of the loss every step

@@ -46,6 +46,13 @@ class _Encoder(nn.Module):
             make_input = lambda: E.ingest(src, s2d=s2d, **ingest_kw)  # noqa: E731
         return E.run_backbone(self, self.program, make_input, pooled)
 
+    def encode_pair(self, src, kw_a, kw_b):
+        """Pooled features of two independent passes over ``src`` (different ingest arguments) issued on two streams
+        from one autograd node (engine.BackbonePairFunction)."""
+        s2d = self.wants_s2d(src)
+        mk = [lambda kw=kw: E.ingest(src, s2d=s2d, **kw) for kw in (kw_a, kw_b)]
+        return E.run_backbone_pair(self, self.program, mk)
+
     def forward(self, x):
         if not x.is_cuda:
             raise E._lib.DualVarNativeError("dualvar_b200 backbones run on a B200 only (no CPU fallback)")

@@ -20,7 +20,7 @@ from ._lib import ptr, stream_ptr
 
 _ENABLED = os.environ.get("DV_SMALL_ALLREDUCE", "1") != "0"
 _MAX_ELEMS = 4096
-_state = None      # None = not tried, False = unavailable (NCCL is used), else _PeerReduce
+_state = None      # None = not tried, False = unavailable (NCCL is used), else {stream id: _PeerReduce}
 
 
 class _PeerReduce:
@@ -55,15 +55,26 @@ def peer_state(device, n):
     """The peer-memory exchange object if it is usable for vectors of n doubles on this process group, else None
     (NCCL is then used). Set up lazily on first use - collectively, so all ranks must reach it together."""
     global _state
+    if _state is False or n > _MAX_ELEMS:
+        return None
     if _state is None:
-        _state = False
-        if _ENABLED and dist.get_backend() == "nccl":
-            try:
-                _state = _PeerReduce(device)
-            except Exception as e:  # noqa: BLE001 - peer mapping is an optimisation; NCCL carries the same sum
-                warnings.warn(f"dualvar_b200: NVLink peer all-reduce unavailable ({e!r}); using NCCL for BatchNorm statistics")
-                _state = False
-    return _state if (_state is not False and n <= _MAX_ELEMS) else None
+        _state = {}
+        if not (_ENABLED and dist.get_backend() == "nccl"):
+            _state = False
+            return None
+    # one exchange channel (symmetric buffer + call counter) per issuing stream: calls of one channel execute in
+    # order on every rank, which is what makes the two-parity slot reuse safe; concurrent backbone passes
+    # (engine.BackbonePairFunction) therefore must not share a channel
+    key = torch.cuda.current_stream(device).cuda_stream
+    ch = _state.get(key)
+    if ch is None:
+        try:
+            ch = _state[key] = _PeerReduce(device)
+        except Exception as e:  # noqa: BLE001 - peer mapping is an optimisation; NCCL carries the same sum
+            warnings.warn(f"dualvar_b200: NVLink peer all-reduce unavailable ({e!r}); using NCCL for BatchNorm statistics")
+            _state = False
+            return None
+    return ch
 
 
 def small_allreduce_(t):

@@ -71,6 +71,7 @@ class Context:
         self.param_grads = {}      # id(param) -> fp32 tensor shaped like the parameter
         self.overrides = {}        # (id(concat Act), channel offset) -> dense gradient replacing the slice's
         self.side_used = False     # weight gradients are in flight on the side stream
+        self.defer_running = None  # list: running-statistic updates of a concurrent pass, applied in order at the join
         self._arena = None         # zeroed fp64 scratch the per-layer statistic buffers are carved from
         self._arena_used = 0
 
@@ -118,14 +119,28 @@ def packed_weights(conv):
     ver = (w._version, w.data_ptr())
     hit = _weight_cache.get(key)
     if hit is not None and hit[0] == ver:
+        _after_pack(hit[3])
         return hit[1], hit[2]
     Cout, Cin, kt, kh, kw = w.shape
     g = make_geom(1, kt, kh, kw, Cin, Cout, (kt, kh, kw), (1, 1, 1), (0, 0, 0))
     wf = torch.empty((g.Cout_p, g.taps, g.Cin_p), dtype=torch.bfloat16, device=w.device)
     wt = torch.empty((g.Cin_p, g.taps, g.Cout_p), dtype=torch.bfloat16, device=w.device)
     call("dv_pack_conv_weight", ptr(w.detach()), ptr(wf), ptr(wt), ctypes.byref(g), stream_ptr())
-    _weight_cache[key] = (ver, wf, wt)
+    _weight_cache[key] = (ver, wf, wt, _pack_mark())
     return wf, wt
+
+
+def _pack_mark():
+    """(stream, event) of a pack kernel: a consumer on another stream (second backbone pass) orders itself after it."""
+    st = torch.cuda.current_stream()
+    return st, st.record_event()
+
+
+def _after_pack(mark):
+    st, ev = mark
+    cur = torch.cuda.current_stream()
+    if cur != st:
+        cur.wait_event(ev)
 
 
 def invalidate_weights(params):
@@ -143,10 +158,11 @@ def packed_stem_weights(conv, g):
     ver = (w._version, w.data_ptr())
     hit = _weight_cache.get(key)
     if hit is not None and hit[0] == ver:
+        _after_pack(hit[2])
         return hit[1]
     ws = torch.empty((g.Cout_p, g.kt * 4, 64), dtype=torch.bfloat16, device=w.device)
     call("dv_pack_stem_weight", ptr(w.detach()), ptr(ws), ctypes.byref(g), stream_ptr())
-    _weight_cache[key] = (ver, ws)
+    _weight_cache[key] = (ver, ws, _pack_mark())
     return ws
 
 
@@ -285,8 +301,12 @@ def conv_stats(ctx, x, conv, bn):
     r.saved = torch.empty(2 * g.Cout_p, dtype=torch.float32, device=dev) if training_stats else None
     momentum = bn.momentum if bn.momentum is not None else 0.1
     track = bn.track_running_stats and bn.running_mean is not None
+    # a pass that runs concurrently with another one (BackbonePairFunction) must not touch the running statistics
+    # in place: its updates are applied after the other pass's, in the reference's order, at the join
+    deferred = track and training_stats and ctx.defer_running is not None
+    upd = track and not deferred
     fin_args = (ptr(stats), ptr(bn.weight.detach()), ptr(bn.bias.detach()),
-                ptr(bn.running_mean) if track else None, ptr(bn.running_var) if track else None,
+                ptr(bn.running_mean) if upd else None, ptr(bn.running_var) if upd else None,
                 ptr(r.ss), ptr(r.saved), Cout, g.Cout_p)
     if training_stats and _is_sync(bn):
         r.count *= dist.get_world_size()
@@ -295,15 +315,35 @@ def conv_stats(ctx, x, conv, bn):
         if peer is not None:      # exchange + finalisation in one launch over NVLink peer memory
             call("dv_bn_finalize_sync", *fin_args, ctypes.c_double(r.count), ctypes.c_float(bn.eps),
                  ctypes.c_float(momentum), *peer.next_call(), stream_ptr())
-            if track:
-                bn.num_batches_tracked += 1
+            _after_finalize(ctx, r, bn, momentum, upd, deferred)
             return r
         comm.small_allreduce_(stats)
     call("dv_bn_finalize", *fin_args, ctypes.c_double(r.count), ctypes.c_float(bn.eps),
          ctypes.c_float(momentum), 1 if training_stats else 0, stream_ptr())
-    if training_stats and track:
-        bn.num_batches_tracked += 1
+    if training_stats:
+        _after_finalize(ctx, r, bn, momentum, upd, deferred)
     return r
+
+
+def _after_finalize(ctx, r, bn, momentum, upd, deferred):
+    if upd:
+        bn.num_batches_tracked += 1
+    elif deferred:
+        ctx.defer_running.append((bn, r.saved, r.count, momentum))
+
+
+def apply_deferred_running(items):
+    """Running-statistic updates of a concurrent pass, in layer order on the current stream (nn.BatchNorm3d momentum
+    update with the unbiased batch variance; mean / invstd come from the pass's saved statistics)."""
+    for bn, saved, count, momentum in items:
+        C = bn.running_mean.shape[0]
+        Cp = saved.shape[0] // 2
+        mean, invstd = saved[:C], saved[Cp:Cp + C]
+        var = (1.0 / (invstd.double() * invstd.double()) - bn.eps).clamp_min(0.0)
+        unbiased = (var * (count / (count - 1.0) if count > 1.0 else 1.0)).float()
+        bn.running_mean.mul_(1.0 - momentum).add_(mean, alpha=momentum)
+        bn.running_var.mul_(1.0 - momentum).add_(unbiased, alpha=momentum)
+        bn.num_batches_tracked += 1
 
 
 # The weight gradient of a layer is off the backward critical path (dgrad -> BN backward of the layer below -> ...),
@@ -314,9 +354,11 @@ _side_streams = {}
 
 
 def _side_stream(device):
-    s = _side_streams.get(device)
+    """The weight-gradient stream that belongs to the current (issuing) stream."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    s = _side_streams.get(key)
     if s is None:
-        s = _side_streams[device] = torch.cuda.Stream(device=device)
+        s = _side_streams[key] = torch.cuda.Stream(device=device)
     return s
 
 
@@ -606,6 +648,93 @@ class BackboneFunction(torch.autograd.Function):
         ectx.param_grads = {}
         fctx.feat = None
         return (None, None, None, None, None) + grads
+
+
+# Two independent passes of one backbone (SimCLR+DualVar: the 3B clips and the B segment-shuffled clips,
+# model/simclr.py:352-387) issued on two streams from ONE autograd node: the tensor-bound conv kernels of one pass
+# then share the GPU with the HBM-bound BatchNorm passes of the other, forward and backward. The second pass lives
+# entirely on its own stream (its activations are allocated, used and freed there); what crosses streams is ordered
+# explicitly: input frames (event), packed weights (pack events), running statistics (deferred to the join, so the
+# reference's update order pass 1 -> pass 2 is kept), outputs and parameter gradients (joins + record_stream).
+# Measured on B200 (tests/diag/overlap_probe.py, profiles/r01b_stream_overlap.txt): a conv_tile_kernel launch and a
+# BatchNorm pass on two streams take LONGER together than back to back (fprop 0.71 + bn_apply 0.49 ms: 1.18 sequential,
+# 1.33-1.37 concurrent) - the persistent conv CTAs are themselves bound by the memory system (L2 -> SM feed), so the
+# BatchNorm blocks that become resident next to them only slow both down. The whole step: 80.5 ms with the two passes
+# on two streams vs 77.8 ms sequential. Results are identical to the sequential issue (tests/diag/pass_streams_check.py),
+# so the path stays available behind DV_PASS_STREAMS=1, but it is off by default.
+PASS_STREAMS = os.environ.get("DV_PASS_STREAMS", "0") != "0"
+_pass_streams = {}
+
+
+def _pass_stream(device):
+    s = _pass_streams.get(device)
+    if s is None:
+        s = _pass_streams[device] = torch.cuda.Stream(device=device)
+    return s
+
+
+class BackbonePairFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(fctx, program, make_inputs, training, record, *params):
+        main = torch.cuda.current_stream()
+        dev = params[0].device
+        sb = _pass_stream(dev)
+        start = main.record_event()
+        ectx_a = Context(training, record=record)
+        xa = make_inputs[0]()
+        feat_a = program(ectx_a, xa)
+        out_a = global_pool(ectx_a, feat_a)
+        ectx_b = Context(training, record=record)
+        ectx_b.defer_running = []
+        sb.wait_event(start)
+        with torch.cuda.stream(sb):
+            xb = make_inputs[1]()
+            feat_b = program(ectx_b, xb)
+            out_b = global_pool(ectx_b, feat_b)
+        main.wait_stream(sb)
+        out_b.record_stream(main)
+        apply_deferred_running(ectx_b.defer_running)
+        ectx_b.defer_running = None
+        fctx.state = (ectx_a, feat_a if record else None, ectx_b, feat_b if record else None, sb)
+        fctx.params = params
+        fctx.set_materialize_grads(False)
+        return out_a, out_b
+
+    @staticmethod
+    def backward(fctx, da, db):
+        ectx_a, feat_a, ectx_b, feat_b, sb = fctx.state
+        n_lead = 4
+        if feat_a is None:
+            return (None,) * (n_lead + len(fctx.params))
+        main = torch.cuda.current_stream()
+        ready = main.record_event()
+        if da is not None:
+            global_pool_backward(feat_a, da)
+            run_backward(ectx_a)
+        if db is not None:
+            sb.wait_event(ready)
+            db.record_stream(sb)
+            with torch.cuda.stream(sb):
+                global_pool_backward(feat_b, db)
+                run_backward(ectx_b)
+            main.wait_stream(sb)
+        grads = []
+        for p in fctx.params:
+            ga = ectx_a.param_grads.get(id(p)) if p.requires_grad else None
+            gb = ectx_b.param_grads.get(id(p)) if p.requires_grad else None
+            if gb is not None:
+                gb.record_stream(main)
+            grads.append(gb if ga is None else (ga if gb is None else ga.add_(gb)))
+        ectx_a.param_grads, ectx_b.param_grads = {}, {}
+        fctx.state = None
+        return (None,) * n_lead + tuple(grads)
+
+
+def run_backbone_pair(module, program, make_inputs):
+    """Pooled outputs of two independent passes of ``module`` (see BackbonePairFunction)."""
+    params = [p for p in module.parameters()]
+    record = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    return BackbonePairFunction.apply(program, make_inputs, module.training, record, *params)
 
 
 def run_backbone(module, program, make_input, pooled):

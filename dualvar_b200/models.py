@@ -127,7 +127,14 @@ class SimCLR_TimeSeriesV4(nn.Module):
         backbone = self.encoder_q[0]
         dev = block.device
         # pass 1: all 3B clips in (b, view) order, one batch -> BN statistics over 3B (model/simclr.py:352-357)
-        pooled = backbone.encode(block, pooled=True)                                    # (3B, fs)
+        # pass 2 (below) is independent of pass 1's result: when enabled both are issued together on two streams
+        # (the host-side permutation draw moves up; no other host RNG use lies between the two in the reference)
+        perm = pooled_s = None
+        if self.with_sr and E.PASS_STREAMS:
+            perm = _draw_perms(B, s, dev)
+            pooled, pooled_s = backbone.encode_pair(block, dict(), dict(first_view=2, n_views=1, perm=perm, n_series=s))
+        else:
+            pooled = backbone.encode(block, pooled=True)                                # (3B, fs)
         ret = dict()
         if self.with_clip:
             f = _head(self.encoder_q[2:], pooled) if len(self.encoder_q) > 2 else pooled
@@ -139,8 +146,9 @@ class SimCLR_TimeSeriesV4(nn.Module):
         if self.with_sr:
             # pass 2: view 2 with its T/s-frame segments permuted per sample; the permutation is folded
             # into the ingest kernel's addressing (model/simclr.py:378-387)
-            perm = _draw_perms(B, s, dev)
-            pooled_s = backbone.encode(block, pooled=True, first_view=2, n_views=1, perm=perm, n_series=s)  # (B, fs)
+            if pooled_s is None:
+                perm = _draw_perms(B, s, dev)
+                pooled_s = backbone.encode(block, pooled=True, first_view=2, n_views=1, perm=perm, n_series=s)  # (B, fs)
             shuf = _head(self.series_proj_head, pooled_s).view(B, s, e)
             shuf = O.l2norm(O.PermuteSegmentsFn.apply(shuf, perm))
             theta = self.args.shufflerank_theta
