@@ -80,6 +80,27 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int n_mma, int 
     const uint32_t span = (mode == 1 ? (uint32_t)region - b_bytes : (uint32_t)region) / pair * pair;
     uint32_t off = 0;
     const long long t0 = clock64();
+    if (mode == 3) {
+      // straight-line issue: 16 MMAs per iteration whose descriptors were all computed before the loop - the pure
+      // issue rate of tcgen05.mma, without any address arithmetic between two MMAs
+      uint32_t al[16], bl[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const uint32_t o = (uint32_t)(j >> 2) * pair;
+        al[j] = (flags | ((base + o) >> 4)) + 2u * (j & 3);
+        bl[j] = (flags | ((base + o + a_bytes) >> 4)) + 2u * (j & 3);
+      }
+      for (int i = 0; i < n_mma; i += 16) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) umma_bf16_lohi(tmem, al[j], bl[j], hi, idesc, (i | j) > 0);
+      }
+      const long long t1b = clock64();
+      umma_commit(&done_bar);
+      mbar_wait(&done_bar, 0);
+      const long long t2b = clock64();
+      out[blockIdx.x * 2] = t1b - t0;
+      out[blockIdx.x * 2 + 1] = t2b - t0;
+    } else {
     const int period = mode >= 16 ? (mode & 0xff) : 0;   // commit to a rotating barrier every `period` MMAs
     const bool alt_acc = (mode & 0x100) != 0;              // switch accumulator (TMEM columns 0 / 256) at every commit
     int since = 0, slot = 0;
@@ -107,6 +128,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int n_mma, int 
     const long long t2 = clock64();
     out[blockIdx.x * 2] = t1 - t0;      // issue time
     out[blockIdx.x * 2 + 1] = t2 - t0;  // until the last MMA completed
+    }
   }
   tc_fence_before_sync();
   __syncthreads();

@@ -9,7 +9,8 @@ out = torch.zeros(148 * 2, dtype=torch.int64, device=dev)
 n_mma = 4096
 for grid in (148,):
     # 0x2pp: commit to a rotating mbarrier every pp MMAs; 0x3pp: and switch accumulator at every commit
-    for mode in (0, 0x204, 0x20C, 0x224, 0x30C, 0x324):
+    # 3: straight-line issue with precomputed descriptors
+    for mode in (0, 3, 0x20C, 0x224):
         for n in (64, 144, 256):
             for region in (160 * 1024,):
                 _lib.call("dv_debug_mma_rate", n, n_mma, region, mode, _lib.ptr(out), grid, _lib.stream_ptr())
