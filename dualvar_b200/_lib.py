@@ -10,7 +10,9 @@ import re
 
 import torch
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libdualvar_b200.so")
+# DV_LIB_PATH: load another build of the same library (A/B runs of kernel changes in one GPU call)
+_LIB_PATH = os.environ.get("DV_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib",
+                                                          "libdualvar_b200.so")
 _lib = None
 
 
