@@ -274,12 +274,15 @@ def run_ours(args):
         roof = None
         if top:
             ach = kern[top]["tflops"]
-            traffic = None
+            traffic = traffic_detail = None
             tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
             if os.path.exists(tpath):
-                traffic = json.load(open(tpath)).get(top)
+                traffic_detail = json.load(open(tpath)).get(top)
+                if traffic_detail:
+                    traffic = traffic_detail.get("avg_dram_bytes_per_launch")   # dram read + write per launch (ncu)
             roof = {"bound": "tensor", "kernel": top, "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["bf16_tflops"], "traffic": traffic, "peak_source": peaks["source"],
+                    "frac": ach / peaks["bf16_tflops"], "traffic": traffic, "traffic_detail": traffic_detail,
+                    "peak_source": peaks["source"],
                     "share_of_step": kern[top]["ms_per_step"] / ms_step_serial, "kernels": kern, "calls": calls,
                     "conv_share_of_step": conv_ms / args.steps / ms_step_serial, "ms_step_serial": ms_step_serial,
                     "whole_step_tflops": GFLOP_PER_SAMPLE * B / ms_step,
