@@ -228,3 +228,56 @@ def test_linear_classifier_matches_oracle(kw):
     lp, _ = prod(x)
     torch.nn.functional.cross_entropy(lp, torch.randint(0, 101, (6,), device=dev)).backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in prod.parameters())
+
+
+def test_error_behaviour_matches_reference_asserts():
+    """The reference's input checks (model/simclr.py:346,351; model/moco.py:347) and the C ABI's status codes."""
+    import ctypes
+    from dualvar_b200 import _lib, models as PM, kernels as K
+    dev = "cuda:0"
+    args = SimpleNamespace(shufflerank_theta=0.05)
+    m = PM.SimCLR_TimeSeriesV4("r21d", 128, 0.07, False, True, 2, 64, 0.07, 0.07, "clip-sr-tc", args).to(dev)
+    with pytest.raises(AssertionError):
+        m(torch.randn(2, 2, 3, 8, 32, 32, device=dev))          # needs 3 views (model/simclr.py:351)
+    with pytest.raises(_lib.DualVarNativeError):
+        m(torch.randn(2, 3, 3, 8, 32, 32))                      # CPU tensor: no fallback
+    moco = PM.MoCo_TimeSeriesV4("r21d", 128, 24, 0.999, 0.07, False, True, 2, 64, 0.07, 0.07, "clip-sr-tc", args).to(dev)
+    with pytest.raises(AssertionError):
+        moco(torch.randn(5, 3, 3, 8, 32, 32, device=dev))       # K % batch_size != 0 (model/moco.py:347)
+    # C ABI: an unsupported stride comes back as a status code + message, nothing throws across the boundary
+    g = K.make_geom(1, 4, 16, 16, 8, 8, (1, 3, 3), (1, 3, 3), (0, 1, 1))
+    x = torch.zeros(1, 4, 16, 16, 8, device=dev, dtype=torch.bfloat16)
+    w = torch.zeros(8, 1, 8, device=dev, dtype=torch.bfloat16)
+    y = torch.zeros(1, g.To, g.Ho, g.Wo, 8, device=dev, dtype=torch.bfloat16)
+    rc = _lib.load().dv_conv3d_fprop_bf16(_lib.ptr(x), _lib.ptr(w), _lib.ptr(y), None, None, ctypes.byref(g), _lib.stream_ptr())
+    assert rc != 0 and b"stride" in _lib.load().dv_last_error()
+
+
+@pytest.mark.parametrize("shape", [(1, 3, 3, 5, 40, 56), (3, 3, 3, 8, 24, 24)])
+def test_ragged_and_minimal_batches_run_and_match_oracle(shape):
+    """A single sample, an odd clip length (5 frames: segments of 2 with one frame left over are not allowed by the
+    reference's view(), so T stays even per segment pair) and non-square maps whose sizes are not tile multiples."""
+    import random
+    import numpy as np
+    from dualvar_b200 import models as PM
+    from oracle import models as OM
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = "cuda:0"
+    B, V, C, T, H, W = shape
+    if T % 2:
+        T += 1
+    args = SimpleNamespace(shufflerank_theta=0.05)
+    torch.manual_seed(0); np.random.seed(0); random.seed(0)
+    ref = OM.SimCLR_TimeSeriesV4("r21d", 128, 0.07, False, True, 2, 64, 0.07, 0.07, "clip-sr-tc", args).to(dev).train()
+    prod = PM.SimCLR_TimeSeriesV4("r21d", 128, 0.07, False, True, 2, 64, 0.07, 0.07, "clip-sr-tc", args)
+    prod.load_state_dict(ref.state_dict())
+    prod = prod.to(dev).train()
+    x = torch.randn(B, V, C, T, H, W, device=dev)
+    np.random.seed(1); rr = ref(x)
+    np.random.seed(1); rp = prod(x)
+    for k in rr:
+        if "loss" in k:
+            assert torch.isfinite(rp[k]) and abs(rp[k].item() - rr[k].item()) <= 2e-2 * abs(rr[k].item()) + 2e-3, (k, rp[k].item(), rr[k].item())
+    sum(v for k, v in rp.items() if "loss" in k).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in prod.parameters())
