@@ -169,10 +169,12 @@ def run_ours(args):
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
 
+    bufs = {"host": host, "dev": dev_in}       # the e2e leg's source: fp32 loader batches (or uint8 frames, see below)
+
     def prefetch(i):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[i % 2])
-            dev_in[i % 2].copy_(host[i % 2], non_blocking=True)
+            bufs["dev"][i % 2].copy_(bufs["host"][i % 2], non_blocking=True)
             ready[i % 2].record(copy_stream)
 
     loss_host = torch.zeros(1).pin_memory()
@@ -181,7 +183,7 @@ def run_ours(args):
         if e2e:
             torch.cuda.current_stream().wait_event(ready[i % 2])
             prefetch(i + 1)
-        frames = dev_in[i % 2]
+        frames = bufs["dev"][i % 2]
         ret = model(RawClips(frames, 3))
         loss = sum(v for k, v in ret.items() if "loss" in k)
         opt.zero_grad(set_to_none=True)
@@ -245,8 +247,18 @@ def run_ours(args):
     torch.cuda.synchronize()
     prefetch(0)
     ms_e2e = timed(args.steps, True, 0)
-    sampler.stop_flag = True
     final_loss = float(loss_host[0])
+    # the same end-to-end step fed with uint8 frames (what a decoder yields; ToTensor's x/255 moves into the ingest
+    # kernel): 4x fewer bytes over PCIe. Reported next to the fp32 figure, which stays the contract's e2e.
+    u8 = [(h * 255).round().to(torch.uint8).pin_memory() for h in host]
+    bufs["host"], bufs["dev"] = u8, [torch.empty_like(u8[0], device=dev) for _ in range(2)]
+    for i in range(2):
+        consumed[i].record()
+    torch.cuda.synchronize()
+    prefetch(0)
+    ms_e2e_u8 = timed(args.steps, True, 0)
+    bufs["host"], bufs["dev"] = host, dev_in
+    sampler.stop_flag = True
 
     if rank == 0:
         peaks = measured_peaks()
@@ -298,6 +310,8 @@ def run_ours(args):
             "clips_per_s": value * 3, "clip_passes_per_s": value * 4,
             "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+            "e2e_uint8_frames": {"value": B * world / (ms_e2e_u8 / 1e3), "unit": "samples/s", "ms_per_step": ms_e2e_u8,
+                                 "h2d_bytes_per_step": h2d_bytes // 4, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches), "roofline": roof, "clocks": sampler.summary(),
             "final_loss": final_loss,
         }

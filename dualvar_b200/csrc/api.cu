@@ -43,7 +43,7 @@ int avgpool_bwd(const float* dout, void* dx, int N, int S, int C, int Cp, int ld
 int maxpool_fwd(const void* x, void* y, uint8_t* idx, const PoolGeom& g, cudaStream_t stream);
 int maxpool_bwd_idx(const uint8_t* idx, const void* dy, void* dx, const PoolGeom& g, cudaStream_t stream);
 int maxpool_bwd(const void* x, const void* y, const void* dy, void* dx, const PoolGeom& g, cudaStream_t stream);
-int ingest(const float* src, void* dst, const int* perm, long long sb, long long sv, long long sc,
+int ingest(const void* src, int src_u8, void* dst, const int* perm, long long sb, long long sv, long long sc,
            long long st, int B, int C, int T, int H, int W, int view, int nv, int n_series,
            const float* mean, const float* stdv, int s2d, cudaStream_t stream);
 int conv_stem_fprop_bf16(const void* x_s2d, const void* w_stem, void* y, double* stats, const float* bias,
@@ -276,7 +276,16 @@ int dv_ingest_clips(const float* src, void* dst, const int32_t* perm, int64_t sb
   DV_REQUIRE(!s2d || (H % 2 == 0 && W % 2 == 0), "space-to-depth ingest needs even H and W");
   DV_REQUIRE(src && dst && B > 0 && C > 0 && C <= 4 && T > 0 && H > 0 && W > 0 && nv > 0, "bad ingest arguments");
   DV_REQUIRE(perm == nullptr || (n_series > 0 && T % n_series == 0), "ingest: T must divide into n_series segments");
-  return ingest(src, dst, perm, sb, sv, sc, st, B, C, T, H, W, view, nv, n_series, mean_host, std_host, s2d, ST);
+  return ingest(src, 0, dst, perm, sb, sv, sc, st, B, C, T, H, W, view, nv, n_series, mean_host, std_host, s2d, ST);
+}
+int dv_ingest_clips_u8(const uint8_t* src, void* dst, const int32_t* perm, int64_t sb, int64_t sv, int64_t sc,
+                       int64_t st, int B, int C, int T, int H, int W, int view, int nv, int n_series,
+                       const float* mean_host, const float* std_host, int s2d, void* stream) {
+  DV_REQUIRE(!s2d || (H % 2 == 0 && W % 2 == 0), "space-to-depth ingest needs even H and W");
+  DV_REQUIRE(src && dst && B > 0 && C > 0 && C <= 4 && T > 0 && H > 0 && W > 0 && nv > 0, "bad ingest arguments");
+  DV_REQUIRE(perm == nullptr || (n_series > 0 && T % n_series == 0), "ingest: T must divide into n_series segments");
+  DV_REQUIRE(!s2d || (sb % 2 == 0 && sv % 2 == 0 && sc % 2 == 0 && st % 2 == 0), "uint8 space-to-depth ingest needs even strides");
+  return ingest(src, 1, dst, perm, sb, sv, sc, st, B, C, T, H, W, view, nv, n_series, mean_host, std_host, s2d, ST);
 }
 int dv_sgemm(int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
              int ldb, float beta, float* C, int ldc, const float* bias, int relu, void* stream) {

@@ -228,8 +228,17 @@ __global__ void maxpool_bwd_idx_kernel(const uint8_t* __restrict__ idx, const __
 // src: fp32, element (b, v, c, t, h, w) at  b*sb + v*sv + c*sc + t*st + h*W + w  (strides in elements)
 // dst: bf16 [B*nv][T][H][W][8] (clip n = b*nv + j reads view `view + j` of sample b); channel c < C gets (x - mean[c]) * inv_std[c], others 0.
 // perm: optional int32 [B][n_series]; output segment j of sample b reads source segment perm[b][j].
+// source element -> float: fp32 frames as they are, uint8 frames as transforms.ToTensor does (x / 255 in fp32)
+__device__ __forceinline__ float ingest_ld(const float* p) { return *p; }
+__device__ __forceinline__ float ingest_ld(const uint8_t* p) { return __fdiv_rn((float)*p, 255.f); }
+__device__ __forceinline__ float2 ingest_ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ float2 ingest_ld2(const uint8_t* p) {
+  const uchar2 u = *reinterpret_cast<const uchar2*>(p);
+  return make_float2(__fdiv_rn((float)u.x, 255.f), __fdiv_rn((float)u.y, 255.f));
+}
+
 struct IngestArgs {
-  const float* src;
+  const void* src;
   __nv_bfloat16* dst;
   const int* perm;
   long long sb, sv, sc, st;
@@ -237,6 +246,7 @@ struct IngestArgs {
   float mean[4], inv_std[4];
 };
 
+template <typename Src>
 __global__ void __launch_bounds__(256) ingest_kernel(const IngestArgs a) {
   const long long HW = (long long)a.H * a.W;
   const long long total = (long long)a.B * a.nv * a.T * HW;
@@ -253,11 +263,11 @@ __global__ void __launch_bounds__(256) ingest_kernel(const IngestArgs a) {
       const int seg = t / seg_len;
       ts = a.perm[n * a.n_series + seg] * seg_len + (t - seg * seg_len);
     }
-    const float* p = a.src + b * a.sb + vw * a.sv + ts * a.st + hw;
+    const Src* p = static_cast<const Src*>(a.src) + b * a.sb + vw * a.sv + ts * a.st + hw;
     float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int c = 0; c < 4; ++c)
-      if (c < a.C) v[c] = (p[c * a.sc] - a.mean[c]) * a.inv_std[c];
+      if (c < a.C) v[c] = (ingest_ld(p + c * a.sc) - a.mean[c]) * a.inv_std[c];
     uint4 o;
     __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
     oh[0] = __floats2bfloat162_rn(v[0], v[1]);
@@ -272,6 +282,7 @@ __global__ void __launch_bounds__(256) ingest_kernel(const IngestArgs a) {
 // Space-to-depth ingest for the stride-2 7x7 stems: dst bf16 [B*nv][T][H/2][W/2+3][16],
 // dst[n][t][hs][ws+2][(rh*2+rw)*4 + c] = norm(src(b, v, c, t, 2*hs+rh, 2*ws+rw)); two zero columns on the
 // left and one on the right so that every 4-position window the stem reads is in bounds.
+template <typename Src>
 __global__ void __launch_bounds__(256) ingest_s2d_kernel(const IngestArgs a) {
   const int H2 = a.H >> 1, W2 = a.W >> 1, W2p = W2 + 3;
   const long long per_t = (long long)H2 * W2p;
@@ -293,7 +304,7 @@ __global__ void __launch_bounds__(256) ingest_s2d_kernel(const IngestArgs a) {
         const int seg = t / seg_len;
         ts = a.perm[n * a.n_series + seg] * seg_len + (t - seg * seg_len);
       }
-      const float* p = a.src + b * a.sb + vw * a.sv + ts * a.st + (long long)(2 * hs) * a.W + 2 * ws;
+      const Src* p = static_cast<const Src*>(a.src) + b * a.sb + vw * a.sv + ts * a.st + (long long)(2 * hs) * a.W + 2 * ws;
       float v[2][2][4];
 #pragma unroll
       for (int rh = 0; rh < 2; ++rh)
@@ -301,7 +312,7 @@ __global__ void __launch_bounds__(256) ingest_s2d_kernel(const IngestArgs a) {
         for (int c = 0; c < 4; ++c) {
           float2 f = make_float2(0.f, 0.f);
           if (c < a.C) {
-            f = *reinterpret_cast<const float2*>(p + c * a.sc + rh * a.W);
+            f = ingest_ld2(p + c * a.sc + rh * a.W);
             f.x = (f.x - a.mean[c]) * a.inv_std[c];
             f.y = (f.y - a.mean[c]) * a.inv_std[c];
           }
@@ -373,7 +384,7 @@ int maxpool_bwd_idx(const uint8_t* idx, const void* dy, void* dx, const PoolGeom
   return kOk;
 }
 
-int ingest(const float* src, void* dst, const int* perm, long long sb, long long sv, long long sc,
+int ingest(const void* src, int src_u8, void* dst, const int* perm, long long sb, long long sv, long long sc,
            long long st, int B, int C, int T, int H, int W, int view, int nv, int n_series,
            const float* mean, const float* stdv, int s2d, cudaStream_t stream) {
   IngestArgs a;
@@ -386,12 +397,14 @@ int ingest(const float* src, void* dst, const int* perm, long long sb, long long
   }
   if (s2d) {
     const long long total2 = (long long)B * nv * T * (H / 2) * (W / 2 + 3);
-    ingest_s2d_kernel<<<flat_grid(total2, 256), 256, 0, stream>>>(a);
+    if (src_u8) ingest_s2d_kernel<uint8_t><<<flat_grid(total2, 256), 256, 0, stream>>>(a);
+    else ingest_s2d_kernel<float><<<flat_grid(total2, 256), 256, 0, stream>>>(a);
     DV_LAUNCH_OK();
     return kOk;
   }
   const long long total = (long long)B * nv * T * H * W;
-  ingest_kernel<<<flat_grid(total, 256), 256, 0, stream>>>(a);
+  if (src_u8) ingest_kernel<uint8_t><<<flat_grid(total, 256), 256, 0, stream>>>(a);
+  else ingest_kernel<float><<<flat_grid(total, 256), 256, 0, stream>>>(a);
   DV_LAUNCH_OK();
   return kOk;
 }

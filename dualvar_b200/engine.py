@@ -213,7 +213,8 @@ class RawClips:
 
     def __init__(self, frames, n_views, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):
         assert frames.dim() == 5 and frames.shape[2] % n_views == 0
-        self.frames = frames.contiguous().float()
+        # uint8 frames (decoded images) are converted on the GPU as ToTensor would on the host (x / 255)
+        self.frames = frames.contiguous() if frames.dtype == torch.uint8 else frames.contiguous().float()
         self.n_views = n_views
         self.mean, self.std = tuple(mean), tuple(std)
 
@@ -254,7 +255,8 @@ def ingest(src, first_view=0, n_views=None, perm=None, n_series=0, s2d=False, ou
         dst = out
     else:
         dst = torch.empty(shape, dtype=torch.bfloat16, device=t.device)
-    call("dv_ingest_clips", ptr(t), ptr(dst), ptr(perm), sb, sv, sc, st, B, C, T, H, W, first_view, nv,
+    call("dv_ingest_clips_u8" if t.dtype == torch.uint8 else "dv_ingest_clips", ptr(t), ptr(dst), ptr(perm), sb, sv, sc, st,
+         B, C, T, H, W, first_view, nv,
          n_series, mean, std, 1 if s2d else 0, stream_ptr())
     return Act(dst, C, needs_grad=False, s2d=(B * nv, T, H, W) if s2d else None)
 

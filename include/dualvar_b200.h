@@ -136,6 +136,11 @@ int dv_maxpool3d_bwd_idx(const uint8_t* argmax, const void* dy, void* dx, const 
 int dv_ingest_clips(const float* src, void* dst, const int32_t* perm, int64_t sb, int64_t sv, int64_t sc,
                     int64_t st, int B, int C, int T, int H, int W, int view, int nv, int n_series,
                     const float* mean_host, const float* std_host, int s2d, void* stream);
+/* Same from uint8 frames (decoded images, 4x fewer bytes over PCIe): every element is first converted as
+ * transforms.ToTensor does (x / 255 in fp32, utils/augmentation.py:361-364), then normalised. */
+int dv_ingest_clips_u8(const uint8_t* src, void* dst, const int32_t* perm, int64_t sb, int64_t sv, int64_t sc,
+                       int64_t st, int B, int C, int T, int H, int W, int view, int nv, int n_series,
+                       const float* mean_host, const float* std_host, int s2d, void* stream);
 
 /* ---- fp32 heads and objectives --------------------------------------------------------------- */
 /* C = alpha*op(A)*op(B) + beta*C (+bias[n]) (relu). Row-major. ta: A stored [K][M]; tb: B stored [N][K].

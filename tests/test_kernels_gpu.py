@@ -152,6 +152,22 @@ def test_ingest_matches_reference_transform_and_shuffle():
     assert torch.equal(got_s[..., :3].float(), shuf.bfloat16().float())
 
 
+@pytest.mark.parametrize("s2d", [False, True])
+def test_uint8_ingest_equals_totensor_then_float_ingest(s2d):
+    """uint8 frames (decoded images): dv_ingest_clips_u8 == ToTensor (x / 255 in fp32, utils/augmentation.py:361-364)
+    followed by the fp32 ingest, bit for bit, in both output layouts and with the segment shuffle."""
+    from dualvar_b200 import engine as E
+    gen = torch.Generator(device=dev).manual_seed(9)
+    B, T, H, W = 3, 8, 12, 10
+    u8 = torch.randint(0, 256, (B, 3, 3 * T, H, W), device=dev, generator=gen, dtype=torch.uint8)
+    as_float = u8.float().div(255)
+    perm = torch.from_numpy(np.array([np.random.RandomState(i).permutation(2) for i in range(B)], dtype=np.int32)).to(dev)
+    for kw in (dict(), dict(first_view=2, n_views=1, perm=perm, n_series=2)):
+        a = E.ingest(E.RawClips(u8, 3), s2d=s2d, **kw).data
+        b = E.ingest(E.RawClips(as_float, 3), s2d=s2d, **kw).data
+        assert a.dtype == torch.bfloat16 and torch.equal(a, b)
+
+
 def test_conv_bn_relu_residual_block_forward_backward():
     """One fused unit (conv -> BN(train) -> (+res) -> ReLU) forward and backward vs torch fp32 on the
     same bf16-rounded input; checks running statistics too."""
