@@ -114,13 +114,13 @@ def exported_symbols():
 
 
 def stream_ptr():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """cudaStream_t of torch's current stream on the current device (raw query: no Stream object per launch)."""
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
 
 
 def ptr(t):
-    if t is None:
-        return None
-    return ctypes.c_void_p(t.data_ptr())
+    """Device address of a tensor as a plain int (ctypes converts it for the void* parameters), None for NULL."""
+    return None if t is None else t.data_ptr()
 
 
 def check(rc, what):
@@ -192,24 +192,30 @@ def set_timer(timer):
     _timer = timer
 
 
+_fn_cache = {}
+
+
 def call(name, *args):
     """Invoke a C-ABI function that returns a status code; raise on failure."""
     global launch_count
-    lib = load()
+    fn = _fn_cache.get(name)
+    if fn is None:
+        fn = _fn_cache[name] = getattr(load(), name)
     launch_count += 1
     if _timer is not None and name in _timer.names:
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-        rc = getattr(lib, name)(*args)
+        rc = fn(*args)
         e1.record()
         check(rc, name)
         _timer.records.append((_timer.key_of(name, args), e0, e1, _timer.flops_of(args)))
         return
     if _TRACE:
         print(f"[dv] {name}(" + ", ".join(_fmt(a) for a in args) + ")", flush=True)
-    rc = getattr(lib, name)(*args)
-    check(rc, name)
+    rc = fn(*args)
+    if rc != 0:
+        check(rc, name)
     if _TRACE:
         torch.cuda.synchronize()
         print(f"[dv] {name} done", flush=True)
