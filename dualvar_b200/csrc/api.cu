@@ -9,10 +9,11 @@ namespace dv {
 const std::string& last_error_ref();
 
 int conv_fprop_bf16(const void* x, const void* w_packed, void* y, double* stats, const float* bias,
-                    const ConvGeom& c, cudaStream_t stream);
+                    const ConvGeom& c, cudaStream_t stream, bool y_f32_acc = false);
 int conv_dgrad_bf16(const void* dy, const void* w_packed_t, void* dx, const ConvGeom& c,
-                    cudaStream_t stream, const BnReduce* red);
-int conv_wgrad_bf16(const void* x, const void* dy, float* dw, const ConvGeom& c, cudaStream_t stream);
+                    cudaStream_t stream, const BnReduce* red, bool dx_f32_acc = false);
+int conv_wgrad_bf16(const void* x, const void* dy, float* dw, const ConvGeom& c, cudaStream_t stream,
+                    bool accumulate = false);
 int pack_weights(const float* w, void* wf, void* wt, int Cout, int Cin, int taps, int Cout_p,
                  int Cin_p, cudaStream_t stream);
 int unpack_wgrad(const float* dwp, float* dw, int Cout, int Cin, int taps, int Cin_p, float beta,
@@ -45,11 +46,33 @@ int maxpool_bwd_idx(const uint8_t* idx, const void* dy, void* dx, const PoolGeom
 int maxpool_bwd(const void* x, const void* y, const void* dy, void* dx, const PoolGeom& g, cudaStream_t stream);
 int ingest(const void* src, int src_u8, void* dst, const int* perm, long long sb, long long sv, long long sc,
            long long st, int B, int C, int T, int H, int W, int view, int nv, int n_series,
-           const float* mean, const float* stdv, int s2d, cudaStream_t stream);
+           const float* mean, const float* stdv, int s2d, cudaStream_t stream, int n_planes = 1,
+           long long plane_stride = 0);
 int conv_stem_fprop_bf16(const void* x_s2d, const void* w_stem, void* y, double* stats, const float* bias,
-                         int N, int T, int H2, int W2, int Cout_p, int kt, int pt, cudaStream_t stream);
+                         int N, int T, int H2, int W2, int Cout_p, int kt, int pt, cudaStream_t stream,
+                         bool y_f32_acc = false);
 int conv_stem_wgrad_bf16(const void* x_s2d, const void* dy, float* dw, int N, int T, int H2, int W2,
-                         int Cout_p, int kt, int pt, cudaStream_t stream);
+                         int Cout_p, int kt, int pt, cudaStream_t stream, bool accumulate = false);
+// fp32 mode (fp32_mode.cu)
+int f32_max_planes();
+int f32_split_planes(const float* src, float* dst, long long n, int K, cudaStream_t stream);
+int f32_colstats(const float* y, double* stats, long long rows, int Cp, cudaStream_t stream);
+int f32_bn_apply(const float* y1, const float* ss1, const float* y2, const float* ss2, const float* res, float* out,
+                 void* planes, long long plane_stride, int K, long long rows, int Cp, int relu, cudaStream_t stream);
+int f32_bn_bwd_reduce(const float* dout, const float* dout2, const float* out, const float* y, const float* ss,
+                      double* sums, long long rows, int Cp, int relu, cudaStream_t stream);
+int f32_bn_bwd_apply(const float* dout, const float* dout2, const float* out, const float* y, const float* ss,
+                     const float* coef, void* dy_planes, long long plane_stride, int K, float* g_out, long long rows,
+                     int Cp, int relu, cudaStream_t stream);
+int f32_add(const float* x, const float* y, float* out, long long n, cudaStream_t stream);
+int f32_split(const float* x, void* planes, long long plane_stride, int K, long long n, cudaStream_t stream);
+int f32_avgpool_fwd(const float* x, float* out, int N, int S, int C, int Cp, int ld_out, cudaStream_t stream);
+int f32_avgpool_bwd(const float* dout, float* dx, int N, int S, int C, int Cp, int ld_out, cudaStream_t stream);
+int f32_maxpool_fwd(const float* x, float* y, uint8_t* idx, void* planes, long long plane_stride, int K,
+                    const PoolGeom& g, cudaStream_t stream);
+int f32_maxpool_bwd(const uint8_t* idx, const float* dy, float* dx, const PoolGeom& g, cudaStream_t stream);
+int f32_ndhwc_to_ncdhw(const float* y, float* x, int N, int C, int Cp, long long S, cudaStream_t stream);
+int f32_ncdhw_to_ndhwc(const float* x, float* y, int N, int C, int Cp, long long S, cudaStream_t stream);
 int pack_stem_weights(const float* w, void* ws, int Cout, int Cin, int kt, int Cout_p, cudaStream_t stream);
 int unpack_stem_wgrad(const float* dws, float* dw, int Cout, int Cin, int kt, float beta, cudaStream_t stream);
 int sgemm(int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
@@ -374,6 +397,126 @@ int dv_conv3d_stem_wgrad_bf16(const void* x_s2d, const void* dy, float* dws, con
   if (int rc = check_stem(g)) return rc;
   DV_REQUIRE(x_s2d && dy && dws, "NULL tensor pointer");
   return conv_stem_wgrad_bf16(x_s2d, dy, dws, g->N, g->T, g->H / 2, g->W / 2, g->Cout_p, g->kt, g->pt, ST);
+}
+
+/* ---- fp32 mode ------------------------------------------------------------------------------------------ */
+static int check_planes(int n_planes, int64_t plane_stride, int64_t plane_elems) {
+  DV_REQUIRE(n_planes >= 1 && n_planes <= f32_max_planes(), "n_planes must be 1..%d", f32_max_planes());
+  DV_REQUIRE(n_planes == 1 || (plane_stride >= plane_elems && plane_stride % 8 == 0),
+             "plane_stride must cover one plane and keep 16-byte alignment");
+  return kOk;
+}
+int dv_f32_split_planes(const float* src, float* dst_planes, int64_t n, int n_planes, void* stream) {
+  DV_REQUIRE(src && dst_planes && n > 0 && n_planes >= 1 && n_planes <= f32_max_planes(), "bad f32_split_planes arguments");
+  return f32_split_planes(src, dst_planes, n, n_planes, ST);
+}
+int dv_conv3d_fprop_f32acc(const void* x_plane, const void* wf_plane, float* y, const float* bias_padded,
+                           const dv_conv_geom* g, void* stream) {
+  if (int rc = check_geom(g)) return rc;
+  DV_REQUIRE(x_plane && wf_plane && y, "NULL tensor pointer");
+  return conv_fprop_bf16(x_plane, wf_plane, y, nullptr, bias_padded, to_geom<ConvGeom>(g), ST, true);
+}
+int dv_conv3d_dgrad_f32acc(const void* dy_plane, const void* wt_plane, float* dx, const dv_conv_geom* g, void* stream) {
+  if (int rc = check_geom(g)) return rc;
+  DV_REQUIRE(dy_plane && wt_plane && dx, "NULL tensor pointer");
+  return conv_dgrad_bf16(dy_plane, wt_plane, dx, to_geom<ConvGeom>(g), ST, nullptr, true);
+}
+int dv_conv3d_wgrad_bf16_acc(const void* x_plane, const void* dy_plane, float* dw_packed, const dv_conv_geom* g,
+                             void* stream) {
+  if (int rc = check_geom(g)) return rc;
+  DV_REQUIRE(x_plane && dy_plane && dw_packed, "NULL tensor pointer");
+  return conv_wgrad_bf16(x_plane, dy_plane, dw_packed, to_geom<ConvGeom>(g), ST, true);
+}
+int dv_conv3d_stem_fprop_f32acc(const void* x_s2d_plane, const void* ws_plane, float* y, const float* bias_padded,
+                                const dv_conv_geom* g, void* stream) {
+  if (int rc = check_stem(g)) return rc;
+  DV_REQUIRE(x_s2d_plane && ws_plane && y, "NULL tensor pointer");
+  return conv_stem_fprop_bf16(x_s2d_plane, ws_plane, y, nullptr, bias_padded, g->N, g->T, g->H / 2, g->W / 2, g->Cout_p,
+                              g->kt, g->pt, ST, true);
+}
+int dv_conv3d_stem_wgrad_bf16_acc(const void* x_s2d_plane, const void* dy_plane, float* dws, const dv_conv_geom* g,
+                                  void* stream) {
+  if (int rc = check_stem(g)) return rc;
+  DV_REQUIRE(x_s2d_plane && dy_plane && dws, "NULL tensor pointer");
+  return conv_stem_wgrad_bf16(x_s2d_plane, dy_plane, dws, g->N, g->T, g->H / 2, g->W / 2, g->Cout_p, g->kt, g->pt, ST,
+                              true);
+}
+int dv_f32_colstats(const float* y, double* stats, int64_t rows, int Cp, void* stream) {
+  DV_REQUIRE(y && stats && rows > 0 && Cp > 0 && Cp % 8 == 0, "bad f32_colstats arguments");
+  return f32_colstats(y, stats, rows, Cp, ST);
+}
+int dv_f32_bn_apply(const float* y1, const float* ss1, const float* y2, const float* ss2, const float* res, float* out,
+                    void* out_planes, int64_t plane_stride, int n_planes, int64_t rows, int Cp, int relu, void* stream) {
+  DV_REQUIRE(y1 && ss1 && out && rows > 0 && Cp > 0 && Cp % 8 == 0, "bad f32_bn_apply arguments");
+  DV_REQUIRE((y2 == nullptr) == (ss2 == nullptr), "f32_bn_apply: y2 and ss2 go together");
+  if (out_planes != nullptr)
+    if (int rc = check_planes(n_planes, plane_stride, rows * Cp)) return rc;
+  return f32_bn_apply(y1, ss1, y2, ss2, res, out, out_planes, plane_stride, n_planes, rows, Cp, relu, ST);
+}
+int dv_f32_bn_bwd_reduce(const float* dout, const float* dout2, const float* out, const float* y, const float* mask_ss,
+                         double* sums, int64_t rows, int Cp, int relu, void* stream) {
+  DV_REQUIRE(dout && y && sums && (!relu || out || mask_ss) && rows > 0 && Cp > 0 && Cp % 8 == 0,
+             "bad f32_bn_bwd_reduce arguments");
+  return f32_bn_bwd_reduce(dout, dout2, out, y, mask_ss, sums, rows, Cp, relu, ST);
+}
+int dv_f32_bn_bwd_apply(const float* dout, const float* dout2, const float* out, const float* y, const float* mask_ss,
+                        const float* coef, void* dy_planes, int64_t plane_stride, int n_planes, float* g_out,
+                        int64_t rows, int Cp, int relu, void* stream) {
+  DV_REQUIRE(dout && y && coef && dy_planes && (!relu || out || mask_ss) && rows > 0 && Cp > 0 && Cp % 8 == 0,
+             "bad f32_bn_bwd_apply arguments");
+  if (int rc = check_planes(n_planes, plane_stride, rows * Cp)) return rc;
+  return f32_bn_bwd_apply(dout, dout2, out, y, mask_ss, coef, dy_planes, plane_stride, n_planes, g_out, rows, Cp, relu,
+                          ST);
+}
+int dv_f32_add(const float* a, const float* b, float* out, int64_t n, void* stream) {
+  DV_REQUIRE(a && b && out && n > 0 && n % 4 == 0, "bad f32_add arguments");
+  return f32_add(a, b, out, n, ST);
+}
+int dv_f32_split(const float* x, void* planes, int64_t plane_stride, int n_planes, int64_t n, void* stream) {
+  DV_REQUIRE(x && planes && n > 0 && n % 8 == 0, "bad f32_split arguments");
+  if (int rc = check_planes(n_planes, plane_stride, n)) return rc;
+  return f32_split(x, planes, plane_stride, n_planes, n, ST);
+}
+int dv_f32_avgpool_fwd(const float* x, float* out, int N, int S, int C, int Cp, int ld_out, void* stream) {
+  DV_REQUIRE(x && out && N > 0 && S > 0 && C > 0 && Cp >= C && ld_out >= C, "bad avgpool arguments");
+  return f32_avgpool_fwd(x, out, N, S, C, Cp, ld_out, ST);
+}
+int dv_f32_avgpool_bwd(const float* dout, float* dx, int N, int S, int C, int Cp, int ld_out, void* stream) {
+  DV_REQUIRE(dout && dx && N > 0 && S > 0 && C > 0 && Cp >= C && ld_out >= C, "bad avgpool arguments");
+  return f32_avgpool_bwd(dout, dx, N, S, C, Cp, ld_out, ST);
+}
+int dv_f32_maxpool3d_fwd(const float* x, float* y, uint8_t* argmax, void* y_planes, int64_t plane_stride, int n_planes,
+                         const dv_pool_geom* g, void* stream) {
+  DV_REQUIRE(x && y && g && g->Cp % 8 == 0, "bad maxpool arguments");
+  if (y_planes != nullptr)
+    if (int rc = check_planes(n_planes, plane_stride, (int64_t)g->N * g->To * g->Ho * g->Wo * g->Cp)) return rc;
+  return f32_maxpool_fwd(x, y, argmax, y_planes, plane_stride, n_planes, to_pool(g), ST);
+}
+int dv_f32_maxpool3d_bwd(const uint8_t* argmax, const float* dy, float* dx, const dv_pool_geom* g, void* stream) {
+  DV_REQUIRE(argmax && dy && dx && g && g->Cp % 8 == 0, "bad maxpool arguments");
+  return f32_maxpool_bwd(argmax, dy, dx, to_pool(g), ST);
+}
+int dv_f32_ndhwc_to_ncdhw(const float* y, float* x, int N, int C, int Cp, int64_t S, void* stream) {
+  DV_REQUIRE(x && y && N > 0 && C > 0 && Cp >= C && S > 0, "bad arguments");
+  return f32_ndhwc_to_ncdhw(y, x, N, C, Cp, S, ST);
+}
+int dv_f32_ncdhw_to_ndhwc(const float* x, float* y, int N, int C, int Cp, int64_t S, void* stream) {
+  DV_REQUIRE(x && y && N > 0 && C > 0 && Cp >= C && S > 0, "bad arguments");
+  return f32_ncdhw_to_ndhwc(x, y, N, C, Cp, S, ST);
+}
+int dv_ingest_clips_planes(const void* src, int src_is_u8, void* dst_planes, int64_t plane_stride, int n_planes,
+                           const int32_t* perm, int64_t sb, int64_t sv, int64_t sc, int64_t st, int B, int C, int T,
+                           int H, int W, int view, int nv, int n_series, const float* mean_host, const float* std_host,
+                           int s2d, void* stream) {
+  DV_REQUIRE(!s2d || (H % 2 == 0 && W % 2 == 0), "space-to-depth ingest needs even H and W");
+  DV_REQUIRE(src && dst_planes && B > 0 && C > 0 && C <= 4 && T > 0 && H > 0 && W > 0 && nv > 0, "bad ingest arguments");
+  DV_REQUIRE(perm == nullptr || (n_series > 0 && T % n_series == 0), "ingest: T must divide into n_series segments");
+  DV_REQUIRE(!(s2d && src_is_u8) || (sb % 2 == 0 && sv % 2 == 0 && sc % 2 == 0 && st % 2 == 0),
+             "uint8 space-to-depth ingest needs even strides");
+  const int64_t plane = s2d ? (int64_t)B * nv * T * (H / 2) * (W / 2 + 3) * 16 : (int64_t)B * nv * T * H * W * 8;
+  if (int rc = check_planes(n_planes, plane_stride, plane)) return rc;
+  return ingest(src, src_is_u8 ? 1 : 0, dst_planes, perm, sb, sv, sc, st, B, C, T, H, W, view, nv, n_series, mean_host,
+                std_host, s2d, ST, n_planes, plane_stride);
 }
 
 int dv_moco_momentum_update(const int64_t* chunk_table, int n_chunks, float m, void* stream) {

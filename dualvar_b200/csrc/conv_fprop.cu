@@ -42,7 +42,8 @@ constexpr int kOutBufs = 4;                  // output staging buffers: two per 
 // (tests/diag/mma_rate.py: SS-mode operand fetch saturates at 128 B/clk/SM, N=144 alone needs 121 B/clk). Only the
 // leader CTA (cluster rank 0) issues MMAs; its full / accumulator-free barriers collect both CTAs' signals, commits
 // are multicast to both CTAs' barriers.
-template <bool kPair>
+// kF32: fp32-mode instance - the epilogue adds its fp32 rows to ConvTileParams::out_f32 (compiled out of the bf16 one).
+template <bool kPair, bool kF32 = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -364,6 +365,20 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
           tc_fence_before_sync();
           if (kPair) mbar_arrive_cluster(acc_free0 + (uint32_t)acc * 8u); else mbar_arrive(&tmem_empty_bar[acc]);
         }
+        if (kF32) {
+          // fp32 mode: the accumulator row goes straight from registers into the fp32 output (this thread's
+          // position, 64 consecutive channels = whole 32-byte sectors), added to what earlier launches left there
+          if (valid) {
+            float* dst = p.out_f32 + (long long)(w0 + rw) * p.red_stride[0] + (long long)(h0 + rh) * p.red_stride[1] +
+                         (long long)(t0 + rt) * p.red_stride[2] + (long long)(n0 + rn) * p.red_stride[3] + bcol + cc * 64;
+#pragma unroll
+            for (int j = 0; j < 64; j += 4)
+              if (j < ncols && bcol + cc * 64 + j < p.stats_ld)
+                red_add_v4_f32(dst + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                               __uint_as_float(v[j + 3]));
+          }
+          continue;
+        }
         uint8_t* orow = ob + row * 128;
 #pragma unroll
         for (int gi = 0; gi < 4; ++gi) {
@@ -500,11 +515,13 @@ struct View5 {
   const void* base;
   long long dim[5];
   long long stride[5];
+  int esize;   // element bytes: 2 (bf16) or 4 (fp32 output of the fp32 mode)
 };
 
 static View5 make_ndhwc(const void* ptr, int N, int T, int H, int W, int Cp) {
   View5 v;
   v.base = ptr;
+  v.esize = 2;
   v.dim[0] = Cp; v.dim[1] = W; v.dim[2] = H; v.dim[3] = T; v.dim[4] = N;
   v.stride[0] = 1;
   v.stride[1] = Cp;
@@ -516,7 +533,7 @@ static View5 make_ndhwc(const void* ptr, int N, int T, int H, int W, int Cp) {
 
 // sub-sample dim d: start r, step s
 static void subsample(View5& v, int d, int r, int s) {
-  v.base = static_cast<const uint8_t*>(v.base) + (long long)r * v.stride[d] * 2;
+  v.base = static_cast<const uint8_t*>(v.base) + (long long)r * v.stride[d] * v.esize;
   v.dim[d] = (v.dim[d] - r + s - 1) / s;
   v.stride[d] *= s;
 }
@@ -750,12 +767,15 @@ static int conv_multi_tap_region(ConvTileParams& P, MapEncoder enc, const void* 
   P.prof = g_prof;
   P.red_y = nullptr;
   P.red_ss = nullptr;
+  for (int i = 0; i < 4; ++i) P.red_stride[i] = outv.stride[i + 1];
+  P.out_f32 = outv.esize == 4 ? static_cast<float*>(const_cast<void*>(outv.base)) : nullptr;
+  if (P.out_f32 != nullptr && (stats != nullptr || red != nullptr))
+    return fail(kBadArg, "fp32 accumulate output has no fused statistics");
   if (red != nullptr) {
     // red->y is already offset to the output view's origin (stride-parity class)
     P.stats = red->sums;
     P.red_y = red->y;
     P.red_ss = red->ss;
-    for (int i = 0; i < 4; ++i) P.red_stride[i] = outv.stride[i + 1];
     const int lg[4] = {g.lw, g.lh, g.lt, g.ln};
     int k = 0;
     for (int d = 0; d < 4; ++d)
@@ -769,7 +789,7 @@ static int conv_multi_tap_region(ConvTileParams& P, MapEncoder enc, const void* 
     int rc = encode_tmap(&P.b_map, w_packed, 2, 3, dims, strides, box, true);
     if (rc) return rc;
   }
-  {
+  if (P.out_f32 == nullptr) {
     uint32_t box[5] = {kChunkK, 1u << g.lw, 1u << g.lh, 1u << g.lt, 1u << g.ln};
     int rc = encode_view(&P.out_map, outv, box);
     if (rc) return rc;
@@ -781,13 +801,19 @@ static int conv_multi_tap_region(ConvTileParams& P, MapEncoder enc, const void* 
                                     kSmemBudget));
     DV_CUDA_OK(cudaFuncSetAttribute(conv_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     kSmemBudget));
+    DV_CUDA_OK(cudaFuncSetAttribute(conv_tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kSmemBudget));
+    DV_CUDA_OK(cudaFuncSetAttribute(conv_tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kSmemBudget));
     attr_set = true;
   }
   // CTAs (or CTA pairs): one per SM (pair of SMs), a multiple of the channel-tile count
   int units = (pair ? sm_count() / 2 : sm_count()) / P.n_tiles * P.n_tiles;
   if (units > P.total_tiles) units = P.total_tiles;  // total_tiles is a multiple of n_tiles
+  const bool f32 = P.out_f32 != nullptr;
   if (!pair) {
-    conv_tile_kernel<false><<<units, kNumThreads, smem_bytes, stream>>>(P);
+    if (f32) conv_tile_kernel<false, true><<<units, kNumThreads, smem_bytes, stream>>>(P);
+    else conv_tile_kernel<false><<<units, kNumThreads, smem_bytes, stream>>>(P);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * units);
@@ -799,7 +825,8 @@ static int conv_multi_tap_region(ConvTileParams& P, MapEncoder enc, const void* 
     attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    DV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tile_kernel<true>, P));
+    if (f32) DV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tile_kernel<true, true>, P));
+    else DV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tile_kernel<true>, P));
   }
   DV_LAUNCH_OK();
   return kOk;
@@ -824,7 +851,7 @@ static int conv_multi_tap(ConvTileParams& P, MapEncoder enc, const void* enc_ctx
     View5 va = outv, vb = outv;
     va.dim[2] = h_main;
     vb.dim[2] = 8;
-    vb.base = static_cast<const uint8_t*>(outv.base) + (long long)h_main * outv.stride[2] * 2;
+    vb.base = static_cast<const uint8_t*>(outv.base) + (long long)h_main * outv.stride[2] * outv.esize;
     BnReduce rb;
     if (red != nullptr) {
       rb = *red;
@@ -851,10 +878,11 @@ static int encode_from_viewset(CUtensorMap* m, const void* ctx, int view, const 
 }
 
 int conv_fprop_bf16(const void* x, const void* w_packed, void* y, double* stats, const float* bias,
-                    const ConvGeom& c, cudaStream_t stream) {
+                    const ConvGeom& c, cudaStream_t stream, bool y_f32_acc) {
   static thread_local ConvTileParams P;
   const View5 inv = make_ndhwc(x, c.N, c.T, c.H, c.W, c.Cin_p);
-  const View5 outv = make_ndhwc(y, c.N, c.To, c.Ho, c.Wo, c.Cout_p);
+  View5 outv = make_ndhwc(y, c.N, c.To, c.Ho, c.Wo, c.Cout_p);
+  if (y_f32_acc) outv.esize = 4;   // y is float [N][To][Ho][Wo][Cout_p], the result is added to it
   ViewSet vs;
   int map_of_parity[8];
   for (int i = 0; i < 8; ++i) map_of_parity[i] = -1;
@@ -887,11 +915,12 @@ int conv_fprop_bf16(const void* x, const void* w_packed, void* y, double* stats,
 // stride-1 multi-tap GEMM over dY with the subset of taps that reach it.
 // w_packed_t: [Cin_p][taps][Cout_p] bf16 (transposed pack).
 int conv_dgrad_bf16(const void* dy, const void* w_packed_t, void* dx, const ConvGeom& c,
-                    cudaStream_t stream, const BnReduce* red) {
+                    cudaStream_t stream, const BnReduce* red, bool dx_f32_acc) {
   static thread_local ConvTileParams P;
   ViewSet vs;
   vs.v[0] = make_ndhwc(dy, c.N, c.To, c.Ho, c.Wo, c.Cout_p);
-  const View5 dxv = make_ndhwc(dx, c.N, c.T, c.H, c.W, c.Cin_p);
+  View5 dxv = make_ndhwc(dx, c.N, c.T, c.H, c.W, c.Cin_p);
+  if (dx_f32_acc) dxv.esize = 4;   // dx is float [N][T][H][W][Cin_p], zeroed by the caller; the result is added
   bool need_zero = false;
   for (int rt = 0; rt < c.st; ++rt)
     for (int rh = 0; rh < c.sh; ++rh)
@@ -902,7 +931,7 @@ int conv_dgrad_bf16(const void* dy, const void* w_packed_t, void* dx, const Conv
             for (int d = 0; d < c.kw; ++d) if (posmod(rw + c.pw - d, c.sw) == 0) ++cnt;
         if (cnt == 0) need_zero = true;
       }
-  if (need_zero)
+  if (need_zero && !dx_f32_acc)
     DV_CUDA_OK(cudaMemsetAsync(dx, 0, (size_t)c.N * c.T * c.H * c.W * c.Cin_p * 2, stream));
   for (int rt = 0; rt < c.st; ++rt)
     for (int rh = 0; rh < c.sh; ++rh)
@@ -960,10 +989,12 @@ static int encode_stem_map(CUtensorMap* m, const void* ctx, int /*view*/, const 
 }
 
 int conv_stem_fprop_bf16(const void* x_s2d, const void* w_stem, void* y, double* stats, const float* bias,
-                         int N, int T, int H2, int W2, int Cout_p, int kt, int pt, cudaStream_t stream) {
+                         int N, int T, int H2, int W2, int Cout_p, int kt, int pt, cudaStream_t stream,
+                         bool y_f32_acc) {
   static thread_local ConvTileParams P;
   const int To = T + 2 * pt - kt + 1;
-  const View5 outv = make_ndhwc(y, N, To, H2, W2, Cout_p);
+  View5 outv = make_ndhwc(y, N, To, H2, W2, Cout_p);
+  if (y_f32_acc) outv.esize = 4;
   StemCtx sc = {x_s2d, N, T, H2, W2};
   std::vector<TapSpec> taps;
   for (int a = 0; a < kt; ++a)

@@ -64,8 +64,13 @@ struct alignas(64) ConvTileParams {
   // g = dz * (scale*y + shift > 0) instead of sum / sum of squares. red_y is y in the output view's layout.
   const void* red_y;
   const float* red_ss;        // nullable [2][stats_ld] scale, shift: ReLU mask (NULL = no ReLU)
-  long long red_stride[4];    // element strides of the output view along w, h, t, n
+  long long red_stride[4];    // element strides of the output view along w, h, t, n (always set)
   long long red_bitoff[7];    // element offset contributed by bit k of the tile row index (w bits, then h, t, n)
+  // fp32 mode (nullable): the output view is an fp32 NDHWC tensor and the tile is ADDED to it from registers
+  // (red.global.add.v4.f32 per row) instead of being rounded to bf16 and stored by TMA; several launches on
+  // bf16 split planes of the operands (x = x0 + x1 + x2, w = w0 + w1 + w2) then sum to an fp32-accurate result.
+  // out_map, the staging buffers and the BatchNorm statistics are unused in this mode.
+  float* out_f32;
 };
 
 // Optional fused BatchNorm-backward reduction request for conv_dgrad_bf16 (see ConvTileParams::red_y).

@@ -313,10 +313,11 @@ static int wgrad_launch(WgradParams& P, int ntaps, int cin_p, int cout_p, int ta
 }
 
 int conv_wgrad_bf16(const void* x, const void* dy, float* dw, const ConvGeom& c,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, bool accumulate) {
   static thread_local WgradParams P;
   const int taps_total = c.kt * c.kh * c.kw;
-  DV_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)c.Cout_p * taps_total * c.Cin_p, stream));
+  // accumulate (fp32 mode): dw already holds the sum of earlier operand-plane products; the kernel only adds
+  if (!accumulate) DV_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)c.Cout_p * taps_total * c.Cin_p, stream));
   P.halo = 0;
   {
     static int halo_env = -1;
@@ -489,11 +490,11 @@ int conv_wgrad_bf16(const void* x, const void* dy, float* dw, const ConvGeom& c,
 }
 
 int conv_stem_wgrad_bf16(const void* x_s2d, const void* dy, float* dw, int N, int T, int H2, int W2,
-                         int Cout_p, int kt, int pt, cudaStream_t stream) {
+                         int Cout_p, int kt, int pt, cudaStream_t stream, bool accumulate) {
   static thread_local WgradParams P;
   const int To = T + 2 * pt - kt + 1;
   const int taps_total = kt * 4;
-  DV_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout_p * taps_total * 64, stream));
+  if (!accumulate) DV_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout_p * taps_total * 64, stream));
   TileGeom& g = P.g;
   choose_tile_log2(6, N, To, H2, W2, &g.ln, &g.lt, &g.lh, &g.lw);
   g.ext_w = W2; g.ext_h = H2; g.ext_t = To; g.ext_n = N;

@@ -61,7 +61,7 @@ contrast_rows_kernel(float* __restrict__ S, float* __restrict__ logits, const in
   for (int w = 0; w < nwarps; ++w) se += red[w];
   const float lse = mx + logf(se);
   if (threadIdx.x == 0) {
-    atomicAdd(loss_sum, lse - zp);
+    atomicAdd(loss_sum, (mx - zp) + logf(se));   // not lse - zp: exact when the positive is the row maximum
     if (hits) {
       if (above < 1) atomicAdd(&hits[0], 1);
       if (above < 5) atomicAdd(&hits[1], 1);

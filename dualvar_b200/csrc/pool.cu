@@ -244,7 +244,14 @@ struct IngestArgs {
   long long sb, sv, sc, st;
   int B, C, T, H, W, view, n_series, nv;
   float mean[4], inv_std[4];
+  // fp32 mode: n_planes bf16 split planes of the normalised value (plane k = bf16 of what planes < k left over),
+  // plane k at dst + k * plane_stride elements; the bf16 mode writes one plane
+  int n_planes;
+  long long plane_stride;
 };
+
+// the part of v that bf16 did not capture (exact in fp32)
+__device__ __forceinline__ float ingest_residual(float v) { return v - __bfloat162float(__float2bfloat16_rn(v)); }
 
 template <typename Src>
 __global__ void __launch_bounds__(256) ingest_kernel(const IngestArgs a) {
@@ -268,13 +275,19 @@ __global__ void __launch_bounds__(256) ingest_kernel(const IngestArgs a) {
 #pragma unroll
     for (int c = 0; c < 4; ++c)
       if (c < a.C) v[c] = (ingest_ld(p + c * a.sc) - a.mean[c]) * a.inv_std[c];
-    uint4 o;
-    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
-    oh[0] = __floats2bfloat162_rn(v[0], v[1]);
-    oh[1] = __floats2bfloat162_rn(v[2], v[3]);
-    oh[2] = __floats2bfloat162_rn(0.f, 0.f);
-    oh[3] = oh[2];
-    *reinterpret_cast<uint4*>(a.dst + i * 8) = o;
+    for (int k = 0; k < a.n_planes; ++k) {
+      uint4 o;
+      __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+      oh[0] = __floats2bfloat162_rn(v[0], v[1]);
+      oh[1] = __floats2bfloat162_rn(v[2], v[3]);
+      oh[2] = __floats2bfloat162_rn(0.f, 0.f);
+      oh[3] = oh[2];
+      *reinterpret_cast<uint4*>(a.dst + k * a.plane_stride + i * 8) = o;
+      if (k + 1 < a.n_planes) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] = ingest_residual(v[c]);
+      }
+    }
   }
 }
 
@@ -296,6 +309,7 @@ __global__ void __launch_bounds__(256) ingest_s2d_kernel(const IngestArgs a) {
     const int n = (int)(i / (per_t * a.T));
     uint4 o0 = make_uint4(0, 0, 0, 0), o1 = o0;
     const int ws = wsp - 2;
+    float v[2][2][4] = {};
     if (ws >= 0 && ws < W2) {
       const int b = n / a.nv;
       const int vw = a.view + (n - b * a.nv);
@@ -305,7 +319,6 @@ __global__ void __launch_bounds__(256) ingest_s2d_kernel(const IngestArgs a) {
         ts = a.perm[n * a.n_series + seg] * seg_len + (t - seg * seg_len);
       }
       const Src* p = static_cast<const Src*>(a.src) + b * a.sb + vw * a.sv + ts * a.st + (long long)(2 * hs) * a.W + 2 * ws;
-      float v[2][2][4];
 #pragma unroll
       for (int rh = 0; rh < 2; ++rh)
 #pragma unroll
@@ -319,16 +332,26 @@ __global__ void __launch_bounds__(256) ingest_s2d_kernel(const IngestArgs a) {
           v[rh][0][c] = f.x;
           v[rh][1][c] = f.y;
         }
+    }
+    for (int k = 0; k < a.n_planes; ++k) {
       __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
       __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
       h0[0] = __floats2bfloat162_rn(v[0][0][0], v[0][0][1]); h0[1] = __floats2bfloat162_rn(v[0][0][2], v[0][0][3]);
       h0[2] = __floats2bfloat162_rn(v[0][1][0], v[0][1][1]); h0[3] = __floats2bfloat162_rn(v[0][1][2], v[0][1][3]);
       h1[0] = __floats2bfloat162_rn(v[1][0][0], v[1][0][1]); h1[1] = __floats2bfloat162_rn(v[1][0][2], v[1][0][3]);
       h1[2] = __floats2bfloat162_rn(v[1][1][0], v[1][1][1]); h1[3] = __floats2bfloat162_rn(v[1][1][2], v[1][1][3]);
+      uint4* d = reinterpret_cast<uint4*>(a.dst + k * a.plane_stride + i * 16);
+      d[0] = o0;
+      d[1] = o1;
+      if (k + 1 < a.n_planes) {
+#pragma unroll
+        for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+          for (int rw = 0; rw < 2; ++rw)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[rh][rw][c] = ingest_residual(v[rh][rw][c]);
+      }
     }
-    uint4* d = reinterpret_cast<uint4*>(a.dst + i * 16);
-    d[0] = o0;
-    d[1] = o1;
   }
 }
 
@@ -386,8 +409,9 @@ int maxpool_bwd_idx(const uint8_t* idx, const void* dy, void* dx, const PoolGeom
 
 int ingest(const void* src, int src_u8, void* dst, const int* perm, long long sb, long long sv, long long sc,
            long long st, int B, int C, int T, int H, int W, int view, int nv, int n_series,
-           const float* mean, const float* stdv, int s2d, cudaStream_t stream) {
+           const float* mean, const float* stdv, int s2d, cudaStream_t stream, int n_planes, long long plane_stride) {
   IngestArgs a;
+  a.n_planes = n_planes; a.plane_stride = plane_stride;
   a.src = src; a.dst = (__nv_bfloat16*)dst; a.perm = perm;
   a.sb = sb; a.sv = sv; a.sc = sc; a.st = st;
   a.B = B; a.C = C; a.T = T; a.H = H; a.W = W; a.view = view; a.n_series = n_series; a.nv = nv;

@@ -316,6 +316,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 
 // Predicated 4-byte read-only global load (0 when !ok): a single predicated instruction, so a run of
 // these stays straight-line code with all loads in flight together.
+// fp32 vector reduction into global memory (one 16-byte red per call; address 16-byte aligned)
+__device__ __forceinline__ void red_add_v4_f32(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 __device__ __forceinline__ uint32_t ldg_u32_pred(const void* ptr, bool ok) {
   uint32_t v;
   asm volatile(

@@ -25,14 +25,48 @@ from ._lib import make_geom, pad8, ptr, stream_ptr
 
 call = _lib.call
 
+# ----------------------------------------------------------------------------- precision mode
+# "bf16" (default, the throughput mode): bf16 NDHWC activations, bf16 x bf16 -> fp32 tensor-core convolutions.
+# "fp32" (the 1e-4 parity mode of the north star): fp32 NDHWC activations and gradients; every conv operand is also
+# kept as F32_PLANES bf16 split planes (x = p0 + p1 + p2, csrc/fp32_mode.cu) and a convolution is the sum of the
+# plane products with i + j < F32_PLANES, each one launch of the same tcgen05 kernel adding its fp32 accumulator tile
+# to the fp32 output. 3 planes carry 24 mantissa bits (6 launches per conv), 2 planes 16 bits (3 launches).
+# Covers the ResNet-style encoders and C3D (select_backbone r21d / r3d / c3d / r2d3d18); S3D / S3D-G stay bf16-only.
+PRECISION = os.environ.get("DV_PRECISION", "bf16")
+F32_PLANES = int(os.environ.get("DV_FP32_PLANES", "3"))
+
+
+def set_precision(mode, planes=None):
+    """Select the arithmetic of the encoder passes built from now on: "bf16" or "fp32" (see above)."""
+    global PRECISION, F32_PLANES
+    if mode not in ("bf16", "fp32"):
+        raise ValueError("precision must be 'bf16' or 'fp32'")
+    if planes is not None:
+        if planes not in (1, 2, 3):
+            raise ValueError("fp32 mode uses 1, 2 or 3 split planes")
+        F32_PLANES = int(planes)
+    PRECISION = mode
+
+
+def fp32_mode():
+    return PRECISION == "fp32"
+
+
+def _terms():
+    """Plane products (operand plane i, weight plane j) of one convolution, smallest contributions first."""
+    K = F32_PLANES
+    return sorted(((i, j) for i in range(K) for j in range(K - i)), key=lambda t: -(t[0] + t[1]))
+
 
 class Act:
-    """A bf16 NDHWC activation [N,T,H,W,Cp] with C logical channels and an optional gradient."""
+    """An NDHWC activation [N,T,H,W,Cp] with C logical channels and an optional gradient: bf16 ``data`` in the bf16
+    mode; in the fp32 mode fp32 ``data`` (None for the ingested clips) plus its bf16 split ``planes`` [K,N,T,H,W,Cp]."""
 
-    __slots__ = ("data", "C", "grad", "grad2", "needs_grad", "s2d", "bnred", "fused")
+    __slots__ = ("data", "C", "grad", "grad2", "needs_grad", "s2d", "bnred", "fused", "planes")
 
-    def __init__(self, data, C, needs_grad=True, s2d=None):
+    def __init__(self, data, C, needs_grad=True, s2d=None, planes=None):
         self.data = data
+        self.planes = planes
         self.C = C
         self.grad = None
         self.grad2 = None       # second pending contribution (summed lazily by the consumer)
@@ -43,16 +77,20 @@ class Act:
 
     @property
     def shape5(self):
-        return tuple(self.data.shape)
+        return tuple(self.data.shape) if self.data is not None else tuple(self.planes.shape[1:])
 
     @property
     def rows(self):
-        s = self.data.shape
+        s = self.shape5
         return s[0] * s[1] * s[2] * s[3]
 
     @property
     def Cp(self):
-        return self.data.shape[4]
+        return self.shape5[4]
+
+    @property
+    def device(self):
+        return self.data.device if self.data is not None else self.planes.device
 
 
 class RawBN:
@@ -149,6 +187,8 @@ def invalidate_weights(params):
     for p in params:
         _weight_cache.pop(id(p), None)
         _weight_cache.pop(("stem", id(p)), None)
+        _weight_cache.pop(("f32", id(p)), None)
+        _weight_cache.pop(("f32stem", id(p)), None)
 
 
 def packed_stem_weights(conv, g):
@@ -164,6 +204,56 @@ def packed_stem_weights(conv, g):
     call("dv_pack_stem_weight", ptr(w.detach()), ptr(ws), ctypes.byref(g), stream_ptr())
     _weight_cache[key] = (ver, ws, _pack_mark())
     return ws
+
+
+def _split_weight(w, K):
+    """fp32 [K][numel]: the bf16-representable parts of the weight (the pack kernels then round them exactly)."""
+    planes = torch.empty((K, w.numel()), dtype=torch.float32, device=w.device)
+    call("dv_f32_split_planes", ptr(w.detach().contiguous()), ptr(planes), w.numel(), K, stream_ptr())
+    return planes
+
+
+def packed_weight_planes(conv):
+    """fp32 mode: [(wf_k, wt_k)] bf16 packed copies of the K split planes of a conv weight."""
+    w = conv.weight
+    K = F32_PLANES
+    key = ("f32", id(w))
+    ver = (w._version, w.data_ptr(), K)
+    hit = _weight_cache.get(key)
+    if hit is not None and hit[0] == ver:
+        _after_pack(hit[2])
+        return hit[1]
+    Cout, Cin, kt, kh, kw = w.shape
+    g = make_geom(1, kt, kh, kw, Cin, Cout, (kt, kh, kw), (1, 1, 1), (0, 0, 0))
+    planes = _split_weight(w, K)
+    out = []
+    for k in range(K):
+        wf = torch.empty((g.Cout_p, g.taps, g.Cin_p), dtype=torch.bfloat16, device=w.device)
+        wt = torch.empty((g.Cin_p, g.taps, g.Cout_p), dtype=torch.bfloat16, device=w.device)
+        call("dv_pack_conv_weight", ptr(planes[k]), ptr(wf), ptr(wt), ctypes.byref(g), stream_ptr())
+        out.append((wf, wt))
+    _weight_cache[key] = (ver, out, _pack_mark())
+    return out
+
+
+def packed_stem_weight_planes(conv, g):
+    """fp32 mode: [(ws_k, None)] space-to-depth stem packs of the K split planes."""
+    w = conv.weight
+    K = F32_PLANES
+    key = ("f32stem", id(w))
+    ver = (w._version, w.data_ptr(), K)
+    hit = _weight_cache.get(key)
+    if hit is not None and hit[0] == ver:
+        _after_pack(hit[2])
+        return hit[1]
+    planes = _split_weight(w, K)
+    out = []
+    for k in range(K):
+        ws = torch.empty((g.Cout_p, g.kt * 4, 64), dtype=torch.bfloat16, device=w.device)
+        call("dv_pack_stem_weight", ptr(planes[k]), ptr(ws), ctypes.byref(g), stream_ptr())
+        out.append((ws, None))
+    _weight_cache[key] = (ver, out, _pack_mark())
+    return out
 
 
 def stem_eligible(conv, H, W):
@@ -185,6 +275,11 @@ def _is_sync(bn):
         and dist.get_world_size() > 1
 
 
+def _add_into(a, b):
+    """a += b on the gradient's own element type (bf16 mode / fp32 mode)."""
+    call("dv_f32_add" if a.dtype == torch.float32 else "dv_add_bf16", ptr(a), ptr(b), ptr(a), a.numel(), stream_ptr())
+
+
 def _acc_grad(act, g):
     """Accumulate a gradient contribution. The second contribution is kept separate: the BN-backward
     kernels sum two streams on the fly, so the usual "main path + shortcut" meeting needs no add pass."""
@@ -194,13 +289,13 @@ def _acc_grad(act, g):
         act.grad2 = g
     else:
         _materialize_grad(act)
-        call("dv_add_bf16", ptr(act.grad), ptr(g), ptr(act.grad), act.grad.numel(), stream_ptr())
+        _add_into(act.grad, g)
 
 
 def _materialize_grad(act):
     """Fold the pending second contribution into act.grad (consumers that read a single tensor)."""
     if act.grad2 is not None:
-        call("dv_add_bf16", ptr(act.grad), ptr(act.grad2), ptr(act.grad), act.grad.numel(), stream_ptr())
+        _add_into(act.grad, act.grad2)
         act.grad2 = None
     return act.grad
 
@@ -250,6 +345,17 @@ def ingest(src, first_view=0, n_views=None, perm=None, n_series=0, s2d=False, ou
         sb, sv, sc, st = C * T * H * W, 0, T * H * W, H * W
     nv = V - first_view if n_views is None else n_views
     shape = (B * nv, T, H // 2, W // 2 + 3, 16) if s2d else (B * nv, T, H, W, 8)
+    if fp32_mode():
+        # split planes [K][clips][...]; ``out`` is a clip range of an ingest_buffer() (planes stay plane_stride apart)
+        K = F32_PLANES
+        if out is not None:
+            assert tuple(out.shape) == (K,) + shape and out.dtype == torch.bfloat16 and out[0].is_contiguous()
+            dst = out
+        else:
+            dst = torch.empty((K,) + shape, dtype=torch.bfloat16, device=t.device)
+        call("dv_ingest_clips_planes", ptr(t), 1 if t.dtype == torch.uint8 else 0, ptr(dst), dst.stride(0), K, ptr(perm),
+             sb, sv, sc, st, B, C, T, H, W, first_view, nv, n_series, mean, std, 1 if s2d else 0, stream_ptr())
+        return Act(None, C, needs_grad=False, s2d=(B * nv, T, H, W) if s2d else None, planes=dst)
     if out is not None:
         assert tuple(out.shape) == shape and out.is_contiguous() and out.dtype == torch.bfloat16
         dst = out
@@ -267,6 +373,35 @@ def ingest_shape(src, n_clips, s2d):
     return (n_clips, T, H // 2, W // 2 + 3, 16) if s2d else (n_clips, T, H, W, 8)
 
 
+def ingest_buffer(src, n_clips, s2d, device):
+    """Uninitialised ingest destination for n_clips clips (several ingest() calls fill clip ranges of it)."""
+    shape = ingest_shape(src, n_clips, s2d)
+    if fp32_mode():
+        shape = (F32_PLANES,) + shape
+    return torch.empty(shape, dtype=torch.bfloat16, device=device)
+
+
+def clip_range(buf, lo, hi):
+    """Clips [lo, hi) of an ingest_buffer() as the ``out`` argument of ingest()."""
+    return buf[:, lo:hi] if fp32_mode() else buf[lo:hi]
+
+
+def input_act(buf, C, s2d_dims=None):
+    """The (gradient-free) input activation over a filled ingest buffer."""
+    if fp32_mode():
+        return Act(None, C, needs_grad=False, s2d=s2d_dims, planes=buf)
+    return Act(buf, C, needs_grad=False, s2d=s2d_dims)
+
+
+def input_tensor(act):
+    """The tensor that holds an input activation's clips (clip dimension: see clip_dim())."""
+    return act.planes if act.data is None else act.data
+
+
+def clip_dim():
+    return 1 if fp32_mode() else 0
+
+
 def conv_stats(ctx, x, conv, bn):
     """y = conv(x) (raw, bf16) with fused per-channel sum/sumsq, then BN finalize -> scale/shift.
     Reference: nn.Conv3d + the statistics half of nn.BatchNorm3d (e.g. backbone/r21d.py:68)."""
@@ -278,17 +413,30 @@ def conv_stats(ctx, x, conv, bn):
     else:
         N, T, H, W, Cin_p = x.shape5
     g = make_geom(N, T, H, W, Cin, Cout, tuple(w.shape[2:]), tuple(conv.stride), tuple(conv.padding))
-    dev = x.data.device
-    y = torch.empty((N, g.To, g.Ho, g.Wo, g.Cout_p), dtype=torch.bfloat16, device=dev)
+    dev = x.device
     training_stats = ctx.training and bn.training if bn is not None else False
     stats = ctx.zeros64(2 * g.Cout_p, dev) if training_stats else None
     if stem:
         assert stem_eligible(conv, H, W), "space-to-depth input needs a stride-2 7x7 first conv"
+    else:
+        assert g.Cin_p == Cin_p, (g.Cin_p, Cin_p)
+    if fp32_mode():
+        # y (fp32) = sum of the plane products; the batch statistics are a separate pass over the finished sum
+        y = torch.zeros((N, g.To, g.Ho, g.Wo, g.Cout_p), dtype=torch.float32, device=dev)
+        packed = packed_stem_weight_planes(conv, g) if stem else packed_weight_planes(conv)
+        bias = _bias_padded(conv, g.Cout_p)
+        for n, (i, j) in enumerate(_terms()):
+            call("dv_conv3d_stem_fprop_f32acc" if stem else "dv_conv3d_fprop_f32acc", ptr(x.planes[i]),
+                 ptr(packed[j][0]), ptr(y), ptr(bias) if n == 0 else None, ctypes.byref(g), stream_ptr())
+        if training_stats:
+            call("dv_f32_colstats", ptr(y), ptr(stats), y.numel() // g.Cout_p, g.Cout_p, stream_ptr())
+    elif stem:
+        y = torch.empty((N, g.To, g.Ho, g.Wo, g.Cout_p), dtype=torch.bfloat16, device=dev)
         packed = (packed_stem_weights(conv, g), None)
         call("dv_conv3d_stem_fprop_bf16", ptr(x.data), ptr(packed[0]), ptr(y), ptr(stats),
              ptr(_bias_padded(conv, g.Cout_p)), ctypes.byref(g), stream_ptr())
     else:
-        assert g.Cin_p == Cin_p, (g.Cin_p, Cin_p)
+        y = torch.empty((N, g.To, g.Ho, g.Wo, g.Cout_p), dtype=torch.bfloat16, device=dev)
         packed = packed_weights(conv)
         call("dv_conv3d_fprop_bf16", ptr(x.data), ptr(packed[0]), ptr(y), ptr(stats),
              ptr(_bias_padded(conv, g.Cout_p)), ctypes.byref(g), stream_ptr())
@@ -376,6 +524,33 @@ def _wgrad(r, dy, gw):
         call("dv_unpack_conv_wgrad", ptr(dwp), ptr(gw), ctypes.byref(g), ctypes.c_float(0.0), stream_ptr())
 
 
+def _conv_backward_f32(ctx, r, dyp):
+    """fp32 mode: dyp = split planes [K, ...] of dy. Weight and data gradient as sums of plane products."""
+    g = r.geom
+    gw = torch.empty_like(r.conv.weight)
+    terms = _terms()
+    if r.stem:
+        dwp = torch.empty((g.Cout_p, g.kt * 4, 64), dtype=torch.float32, device=dyp.device)
+        for n, (i, j) in enumerate(terms):
+            call("dv_conv3d_stem_wgrad_bf16" if n == 0 else "dv_conv3d_stem_wgrad_bf16_acc", ptr(r.x.planes[i]),
+                 ptr(dyp[j]), ptr(dwp), ctypes.byref(g), stream_ptr())
+        call("dv_unpack_stem_wgrad", ptr(dwp), ptr(gw), ctypes.byref(g), ctypes.c_float(0.0), stream_ptr())
+    else:
+        dwp = torch.empty((g.Cout_p, g.taps, g.Cin_p), dtype=torch.float32, device=dyp.device)
+        for n, (i, j) in enumerate(terms):
+            call("dv_conv3d_wgrad_bf16" if n == 0 else "dv_conv3d_wgrad_bf16_acc", ptr(r.x.planes[i]), ptr(dyp[j]),
+                 ptr(dwp), ctypes.byref(g), stream_ptr())
+        call("dv_unpack_conv_wgrad", ptr(dwp), ptr(gw), ctypes.byref(g), ctypes.c_float(0.0), stream_ptr())
+    ctx.add_param_grad(r.conv.weight, gw)
+    if r.conv.bias is not None:
+        ctx.add_param_grad(r.conv.bias, torch.zeros_like(r.conv.bias))
+    if r.x.needs_grad:
+        dx = torch.zeros(r.x.shape5, dtype=torch.float32, device=dyp.device)
+        for i, j in terms:
+            call("dv_conv3d_dgrad_f32acc", ptr(dyp[i]), ptr(r.packed[j][1]), ptr(dx), ctypes.byref(g), stream_ptr())
+        _acc_grad(r.x, dx)
+
+
 def _conv_backward(ctx, r, dy):
     """wgrad into the parameter-gradient sink, dgrad into r.x.grad."""
     g = r.geom
@@ -412,10 +587,83 @@ def _conv_backward(ctx, r, dy):
         _acc_grad(r.x, dx)
 
 
+def _bn_bwd_finalize(ctx, r, sums, Cp, dev):
+    """Backward sums of one BatchNorm -> dgamma / dbeta (into the gradient sink) and the coefficients of
+    dy = A*g + B*y + C; cross-replica BatchNorm exchanges the sums first (fused over NVLink peer memory)."""
+    bn = r.bn
+    dgamma = torch.empty_like(bn.weight)
+    dbeta = torch.empty_like(bn.bias)
+    coef = torch.empty(3 * Cp, dtype=torch.float32, device=dev)
+    peer = comm.peer_state(dev, 2 * Cp) if r.sync else None
+    if peer is not None:  # exchange of the sums + finalisation in one launch over NVLink peer memory
+        call("dv_bn_bwd_finalize_sync", ptr(sums), ptr(bn.weight.detach()), ptr(r.saved), ptr(dgamma),
+             ptr(dbeta), ptr(coef), r.geom.Cout, Cp, ctypes.c_double(r.count), ctypes.c_float(0.0),
+             *peer.next_call(), stream_ptr())
+    else:
+        sums_g = sums
+        if r.sync:
+            sums_g = sums.clone()
+            comm.small_allreduce_(sums_g)
+        call("dv_bn_bwd_finalize", ptr(sums), ptr(sums_g), ptr(bn.weight.detach()), ptr(r.saved),
+             ptr(dgamma), ptr(dbeta), ptr(coef), r.geom.Cout, Cp, ctypes.c_double(r.count),
+             ctypes.c_float(0.0), stream_ptr())
+    ctx.add_param_grad(bn.weight, dgamma)
+    ctx.add_param_grad(bn.bias, dbeta)
+    return coef
+
+
+def _activate_f32(ctx, r1, r2, res, relu):
+    """fp32 mode of activate(): out = relu?(BN(r1) [+ BN(r2)] [+ res]) as fp32 plus its split planes."""
+    g = r1.geom
+    Cp = g.Cout_p
+    dev = r1.y.device
+    K = F32_PLANES
+    out_t = torch.empty_like(r1.y)
+    planes = torch.empty((K,) + tuple(r1.y.shape), dtype=torch.bfloat16, device=dev)
+    rows = r1.y.numel() // Cp
+    call("dv_f32_bn_apply", ptr(r1.y), ptr(r1.ss), ptr(r2.y) if r2 else None, ptr(r2.ss) if r2 else None,
+         ptr(res.data) if res is not None else None, ptr(out_t), ptr(planes), planes.stride(0), K, rows, Cp,
+         1 if relu else 0, stream_ptr())
+    out_act = Act(out_t, g.Cout, planes=planes)
+    if not ctx.record:
+        return out_act
+
+    def backward():
+        dout, dout2 = out_act.grad, out_act.grad2
+        assert dout is not None, "activation has no gradient"
+        need_g = res is not None and res.needs_grad
+        g_buf = None
+        mask_ss = ptr(r1.ss) if (relu and r2 is None and res is None) else None
+        for r in (r1, r2):
+            if r is None:
+                continue
+            sums = ctx.zeros64(2 * Cp, dev)
+            call("dv_f32_bn_bwd_reduce", ptr(dout), ptr(dout2), ptr(out_t), ptr(r.y), mask_ss, ptr(sums), rows, Cp,
+                 1 if relu else 0, stream_ptr())
+            coef = _bn_bwd_finalize(ctx, r, sums, Cp, dev)
+            dyp = torch.empty((K,) + tuple(r.y.shape), dtype=torch.bfloat16, device=dev)
+            want_g = need_g and g_buf is None
+            if want_g:
+                g_buf = torch.empty_like(r.y)
+            call("dv_f32_bn_bwd_apply", ptr(dout), ptr(dout2), ptr(out_t), ptr(r.y), mask_ss, ptr(coef), ptr(dyp),
+                 dyp.stride(0), K, ptr(g_buf) if want_g else None, rows, Cp, 1 if relu else 0, stream_ptr())
+            _conv_backward_f32(ctx, r, dyp)
+        if need_g:
+            _acc_grad(res, g_buf)
+        out_act.grad = out_act.grad2 = None
+
+    ctx.tape.append(backward)
+    return out_act
+
+
 def activate(ctx, r1, r2=None, res=None, relu=True, out=None, out_coff=0):
     """out = relu?(BN(r1) [+ BN(r2)] [+ res]). ``out``/``out_coff`` let several branches write
     channel slices of one tensor (concat-free Inception, backbone/s3dg.py:130).
     Reference: BatchNorm3d affine + ReLU + residual add (backbone/r21d.py:116-122)."""
+    if fp32_mode():
+        if out is not None:
+            raise _lib.DualVarNativeError("the fp32 mode has no concat-slice outputs (S3D / S3D-G run in the bf16 mode)")
+        return _activate_f32(ctx, r1, r2, res, relu)
     g = r1.geom
     Cp = g.Cout_p
     dev = r1.y.device
@@ -463,25 +711,7 @@ def activate(ctx, r1, r2=None, res=None, relu=True, out=None, out_coff=0):
                 sums = ctx.zeros64(2 * Cp, dev)
                 call("dv_bn_bwd_reduce", ptr(dout), ptr(dout2), ptr(out_t), ptr(r.y), mask_ss, ptr(sums), rows, Cp,
                      o_ld, o_coff, 1 if relu else 0, stream_ptr())
-            bn = r.bn
-            dgamma = torch.empty_like(bn.weight)
-            dbeta = torch.empty_like(bn.bias)
-            coef = torch.empty(3 * Cp, dtype=torch.float32, device=dev)
-            peer = comm.peer_state(dev, 2 * Cp) if r.sync else None
-            if peer is not None:  # exchange of the sums + finalisation in one launch over NVLink peer memory
-                call("dv_bn_bwd_finalize_sync", ptr(sums), ptr(bn.weight.detach()), ptr(r.saved), ptr(dgamma),
-                     ptr(dbeta), ptr(coef), r.geom.Cout, Cp, ctypes.c_double(r.count), ctypes.c_float(0.0),
-                     *peer.next_call(), stream_ptr())
-            else:
-                sums_g = sums
-                if r.sync:
-                    sums_g = sums.clone()
-                    comm.small_allreduce_(sums_g)
-                call("dv_bn_bwd_finalize", ptr(sums), ptr(sums_g), ptr(bn.weight.detach()), ptr(r.saved),
-                     ptr(dgamma), ptr(dbeta), ptr(coef), r.geom.Cout, Cp, ctypes.c_double(r.count),
-                     ctypes.c_float(0.0), stream_ptr())
-            ctx.add_param_grad(bn.weight, dgamma)
-            ctx.add_param_grad(bn.bias, dbeta)
+            coef = _bn_bwd_finalize(ctx, r, sums, Cp, dev)
             dy = torch.empty_like(r.y)
             want_g = need_g and g_buf is None
             if want_g:
@@ -502,6 +732,8 @@ def activate(ctx, r1, r2=None, res=None, relu=True, out=None, out_coff=0):
 def new_concat(x, C_total):
     """Empty activation with x's N,T,H,W that several branches fill slice by slice
     (torch.cat of the Inception branches, backbone/s3dg.py:130)."""
+    if fp32_mode():
+        raise _lib.DualVarNativeError("the fp32 mode does not cover S3D / S3D-G (concat branches run in the bf16 mode)")
     N, T, H, W, _ = x.shape5
     assert C_total % 8 == 0
     return Act(torch.empty((N, T, H, W, C_total), dtype=torch.bfloat16, device=x.data.device), C_total)
@@ -556,6 +788,8 @@ def max_pool(ctx, x, kernel, stride, padding):
     pt, ph, pw = padding
     To, Ho, Wo = (T + 2 * pt - kt) // st + 1, (H + 2 * ph - kh) // sh + 1, (W + 2 * pw - kw) // sw + 1
     geom = (ctypes.c_int32 * 17)(N, T, H, W, To, Ho, Wo, Cp, kt, kh, kw, st, sh, sw, pt, ph, pw)
+    if fp32_mode():
+        return _max_pool_f32(ctx, x, geom, (N, To, Ho, Wo, Cp))
     y = torch.empty((N, To, Ho, Wo, Cp), dtype=torch.bfloat16, device=x.data.device)
     track = ctx.record and x.needs_grad
     # training: 1-byte argmax per output element (backward becomes a gather instead of re-scanning windows for ties,
@@ -576,12 +810,31 @@ def max_pool(ctx, x, kernel, stride, padding):
     return out
 
 
+def _max_pool_f32(ctx, x, geom, oshape):
+    dev = x.data.device
+    K = F32_PLANES
+    y = torch.empty(oshape, dtype=torch.float32, device=dev)
+    planes = torch.empty((K,) + tuple(oshape), dtype=torch.bfloat16, device=dev)
+    track = ctx.record and x.needs_grad
+    idx = torch.empty(oshape, dtype=torch.uint8, device=dev) if track else None
+    call("dv_f32_maxpool3d_fwd", ptr(x.data), ptr(y), ptr(idx), ptr(planes), planes.stride(0), K, geom, stream_ptr())
+    out = Act(y, x.C, planes=planes)
+    if track:
+        def backward():
+            dx = torch.empty_like(x.data)
+            call("dv_f32_maxpool3d_bwd", ptr(idx), ptr(_materialize_grad(out)), ptr(dx), geom, stream_ptr())
+            _acc_grad(x, dx)
+            out.grad = None
+        ctx.tape.append(backward)
+    return out
+
+
 def global_pool(ctx, x):
     """AdaptiveAvgPool3d((1,1,1)) -> fp32 [N, C] (model/simclr.py:166)."""
     N, T, H, W, Cp = x.shape5
     S = T * H * W
     out = torch.empty((N, x.C), dtype=torch.float32, device=x.data.device)
-    call("dv_avgpool_fwd", ptr(x.data), ptr(out), N, S, x.C, Cp, x.C, stream_ptr())
+    call("dv_f32_avgpool_fwd" if x.data.dtype == torch.float32 else "dv_avgpool_fwd", ptr(x.data), ptr(out), N, S, x.C, Cp, x.C, stream_ptr())
     return out
 
 
@@ -589,14 +842,15 @@ def global_pool_backward(x, dpooled):
     N, T, H, W, Cp = x.shape5
     dx = torch.empty_like(x.data)
     d = dpooled.contiguous()
-    call("dv_avgpool_bwd", ptr(d), ptr(dx), N, T * H * W, x.C, Cp, x.C, stream_ptr())
+    call("dv_f32_avgpool_bwd" if dx.dtype == torch.float32 else "dv_avgpool_bwd", ptr(d), ptr(dx), N, T * H * W, x.C, Cp, x.C, stream_ptr())
     _acc_grad(x, dx)
 
 
 def to_ncdhw(x):
     N, T, H, W, Cp = x.shape5
     out = torch.empty((N, x.C, T, H, W), dtype=torch.float32, device=x.data.device)
-    call("dv_ndhwc_bf16_to_ncdhw", ptr(x.data), ptr(out), N, x.C, Cp, T * H * W, stream_ptr())
+    call("dv_f32_ndhwc_to_ncdhw" if x.data.dtype == torch.float32 else "dv_ndhwc_bf16_to_ncdhw", ptr(x.data), ptr(out),
+         N, x.C, Cp, T * H * W, stream_ptr())
     return out
 
 
@@ -604,7 +858,8 @@ def from_ncdhw_grad(x, d):
     N, T, H, W, Cp = x.shape5
     dx = torch.empty_like(x.data)
     d = d.contiguous()
-    call("dv_ncdhw_to_ndhwc_bf16", ptr(d), ptr(dx), N, x.C, Cp, T * H * W, stream_ptr())
+    call("dv_f32_ncdhw_to_ndhwc" if dx.dtype == torch.float32 else "dv_ncdhw_to_ndhwc_bf16", ptr(d), ptr(dx), N, x.C, Cp,
+         T * H * W, stream_ptr())
     _acc_grad(x, dx)
 
 

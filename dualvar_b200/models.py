@@ -130,7 +130,7 @@ class SimCLR_TimeSeriesV4(nn.Module):
         # pass 2 (below) is independent of pass 1's result: when enabled both are issued together on two streams
         # (the host-side permutation draw moves up; no other host RNG use lies between the two in the reference)
         perm = pooled_s = None
-        if self.with_sr and E.PASS_STREAMS:
+        if self.with_sr and E.PASS_STREAMS and not E.fp32_mode():
             perm = _draw_perms(B, s, dev)
             pooled, pooled_s = backbone.encode_pair(block, dict(), dict(first_view=2, n_views=1, perm=perm, n_series=s))
         else:
@@ -299,9 +299,11 @@ class _MoCoBase(nn.Module):
 
         def make():
             local = E.ingest(block, first_view=view, n_views=1, s2d=s2d)
-            allx = concat_all_gather(local.data)
-            sel = allx.index_select(0, mine).contiguous()
-            return E.Act(sel, local.C, needs_grad=False, s2d=local.s2d)
+            cd = E.clip_dim()      # fp32 mode: split planes [K][clips][...]
+            t = E.input_tensor(local)
+            allx = concat_all_gather(t) if cd == 0 else concat_all_gather(t.transpose(0, 1).contiguous()).transpose(0, 1)
+            sel = allx.index_select(cd, mine).contiguous()
+            return E.input_act(sel, local.C, local.s2d)
         return make, unshuf
 
 
@@ -461,10 +463,10 @@ class MoCo_TimeSeriesV4(_MoCoBase):
         s2d = bq.wants_s2d(block)
 
         def make_dual():
-            buf = torch.empty(E.ingest_shape(block, 2 * B, s2d), dtype=torch.bfloat16, device=dev)
-            a = E.ingest(block, first_view=2, n_views=1, s2d=s2d, out=buf[:B])
-            E.ingest(block, first_view=2, n_views=1, perm=perm, n_series=s, s2d=s2d, out=buf[B:])
-            return E.Act(buf, a.C, needs_grad=False, s2d=(2 * B,) + a.s2d[1:] if a.s2d else None)
+            buf = E.ingest_buffer(block, 2 * B, s2d, dev)
+            a = E.ingest(block, first_view=2, n_views=1, s2d=s2d, out=E.clip_range(buf, 0, B))
+            E.ingest(block, first_view=2, n_views=1, perm=perm, n_series=s, s2d=s2d, out=E.clip_range(buf, B, 2 * B))
+            return E.input_act(buf, a.C, (2 * B,) + a.s2d[1:] if a.s2d else None)
 
         pooled_d = bq.encode(None, pooled=True, make_input=make_dual)
         series_d = O.l2norm(_head(self.series_proj_head_q, pooled_d).view(2 * B * s, e)).view(2 * B, s, e)

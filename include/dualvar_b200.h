@@ -251,6 +251,59 @@ int dv_debug_probe_overlap_tmap(const void* src, void* out, int c1, void* stream
  * shared-memory operands cycling through region_bytes) per CTA -> cycles[grid][2] = (issue, completion) */
 int dv_debug_mma_rate(int n, int n_mma, int region_bytes, int mode, int64_t* cycles, int grid, void* stream);
 
+/* ---- fp32 mode ("1e-4 mode") ----------------------------------------------------------------
+ * Activations and gradients are fp32 NDHWC [N][T][H][W][Cp]; every conv operand is also kept as n_planes (1..3)
+ * bf16 SPLIT PLANES, x = p0 + p1 + p2 with p_k = bf16(x - p0 - .. - p(k-1)), plane k at base + k*plane_stride
+ * elements. A convolution is the sum over i + j < n_planes of bf16 products (x plane i) * (w plane j), each ONE call
+ * of an *_f32acc / *_acc entry point below: the tcgen05 kernels of the bf16 mode, whose epilogue ADDS the fp32
+ * accumulator tile to the fp32 destination instead of rounding it to bf16 (the caller zeroes the destination).
+ * Replaces the same reference calls as the bf16 entry points, for the fp32 (TF32-off) reference path. */
+/* fp32 values -> n_planes fp32 tensors [n_planes][n] holding the bf16-representable parts (feed each plane to
+ * dv_pack_conv_weight / dv_pack_stem_weight, which then rounds exactly) */
+int dv_f32_split_planes(const float* src, float* dst_planes, int64_t n, int n_planes, void* stream);
+/* y += conv(x_plane, w_plane) (+ bias); y fp32 [N][To][Ho][Wo][Cout_p] */
+int dv_conv3d_fprop_f32acc(const void* x_plane, const void* wf_plane, float* y, const float* bias_padded,
+                           const dv_conv_geom* g, void* stream);
+/* dx += conv_transpose(dy_plane, w_plane); dx fp32 [N][T][H][W][Cin_p] */
+int dv_conv3d_dgrad_f32acc(const void* dy_plane, const void* wt_plane, float* dx, const dv_conv_geom* g, void* stream);
+/* dw_packed += correlation(x_plane, dy_plane) (dv_conv3d_wgrad_bf16 without the zero fill) */
+int dv_conv3d_wgrad_bf16_acc(const void* x_plane, const void* dy_plane, float* dw_packed, const dv_conv_geom* g,
+                             void* stream);
+/* the stride-2 7x7 stem on space-to-depth planes (dv_conv3d_stem_fprop_bf16 / _wgrad_bf16), accumulating */
+int dv_conv3d_stem_fprop_f32acc(const void* x_s2d_plane, const void* ws_plane, float* y, const float* bias_padded,
+                                const dv_conv_geom* g, void* stream);
+int dv_conv3d_stem_wgrad_bf16_acc(const void* x_s2d_plane, const void* dy_plane, float* dws, const dv_conv_geom* g,
+                                  void* stream);
+/* BatchNorm batch statistics of an fp32 conv output: adds per-channel sum / sum of squares (double, caller zeroes)
+ * into stats[0:Cp] / stats[Cp:2Cp]; dv_bn_finalize(_sync) then applies unchanged */
+int dv_f32_colstats(const float* y, double* stats, int64_t rows, int Cp, void* stream);
+/* out = relu?(ss1*y1 [+ ss2*y2] [+ res]) as fp32 and (out_planes != NULL) as split planes (dv_bn_apply) */
+int dv_f32_bn_apply(const float* y1, const float* ss1, const float* y2, const float* ss2, const float* res, float* out,
+                    void* out_planes, int64_t plane_stride, int n_planes, int64_t rows, int Cp, int relu, void* stream);
+/* dv_bn_bwd_reduce / dv_bn_bwd_apply on fp32 tensors; dy leaves as split planes (it only feeds dgrad and wgrad),
+ * g_out (nullable) is the masked gradient for the residual branch */
+int dv_f32_bn_bwd_reduce(const float* dout, const float* dout2, const float* out, const float* y, const float* mask_ss,
+                         double* sums, int64_t rows, int Cp, int relu, void* stream);
+int dv_f32_bn_bwd_apply(const float* dout, const float* dout2, const float* out, const float* y, const float* mask_ss,
+                        const float* coef, void* dy_planes, int64_t plane_stride, int n_planes, float* g_out,
+                        int64_t rows, int Cp, int relu, void* stream);
+int dv_f32_add(const float* a, const float* b, float* out, int64_t n, void* stream);
+/* fp32 tensor -> split planes */
+int dv_f32_split(const float* x, void* planes, int64_t plane_stride, int n_planes, int64_t n, void* stream);
+int dv_f32_avgpool_fwd(const float* x, float* out, int N, int S, int C, int Cp, int ld_out, void* stream);
+int dv_f32_avgpool_bwd(const float* dout, float* dx, int N, int S, int C, int Cp, int ld_out, void* stream);
+/* nn.MaxPool3d on fp32 NDHWC; argmax (nullable) as in dv_maxpool3d_fwd_idx, y_planes (nullable) = split planes of y */
+int dv_f32_maxpool3d_fwd(const float* x, float* y, uint8_t* argmax, void* y_planes, int64_t plane_stride, int n_planes,
+                         const dv_pool_geom* g, void* stream);
+int dv_f32_maxpool3d_bwd(const uint8_t* argmax, const float* dy, float* dx, const dv_pool_geom* g, void* stream);
+int dv_f32_ndhwc_to_ncdhw(const float* y, float* x, int N, int C, int Cp, int64_t S, void* stream);
+int dv_f32_ncdhw_to_ndhwc(const float* x, float* y, int N, int C, int Cp, int64_t S, void* stream);
+/* dv_ingest_clips / dv_ingest_clips_u8 writing n_planes split planes of the normalised clips */
+int dv_ingest_clips_planes(const void* src, int src_is_u8, void* dst_planes, int64_t plane_stride, int n_planes,
+                           const int32_t* perm, int64_t sb, int64_t sv, int64_t sc, int64_t st, int B, int C, int T,
+                           int H, int W, int view, int nv, int n_series, const float* mean_host, const float* std_host,
+                           int s2d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
