@@ -26,13 +26,15 @@ contrast_rows_kernel(float* __restrict__ S, float* __restrict__ logits, const in
   __shared__ float red[32];
   __shared__ int redi[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const float zp = row[pos] * inv_T;
+  // __fmul_rn: every pass must see the SAME rounded logit (a contracted fma(row, inv_T, -mx) would leave the
+  // product's rounding residual in exp(z - mx) of the maximum itself: 5e-7 absolute, 3e-4 of a 1e-3 loss)
+  const float zp = __fmul_rn(row[pos], inv_T);
   // pass 1: max and how many negatives beat the positive
   float mx = -INFINITY;
   int above = 0;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     if (c == self) continue;
-    const float z = row[c] * inv_T;
+    const float z = __fmul_rn(row[c], inv_T);
     mx = fmaxf(mx, z);
     if (c != pos && z > zp) ++above;
   }
@@ -51,7 +53,7 @@ contrast_rows_kernel(float* __restrict__ S, float* __restrict__ logits, const in
   float se = 0.f;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     if (c == self) continue;
-    se += __expf(row[c] * inv_T - mx);
+    se += __expf(__fmul_rn(row[c], inv_T) - mx);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
@@ -59,7 +61,7 @@ contrast_rows_kernel(float* __restrict__ S, float* __restrict__ logits, const in
   __syncthreads();
   se = 0.f;
   for (int w = 0; w < nwarps; ++w) se += red[w];
-  const float lse = mx + logf(se);
+  const float inv_se = 1.f / se;
   if (threadIdx.x == 0) {
     atomicAdd(loss_sum, (mx - zp) + logf(se));   // not lse - zp: exact when the positive is the row maximum
     if (hits) {
@@ -71,7 +73,7 @@ contrast_rows_kernel(float* __restrict__ S, float* __restrict__ logits, const in
   float* lrow = logits ? logits + (long long)r * ld_logits : nullptr;
   const float gs = grad_scale * inv_T;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float z = row[c] * inv_T;
+    const float z = __fmul_rn(row[c], inv_T);
     if (c == self) { row[c] = 0.f; continue; }
     if (lrow) {
       int j;
@@ -79,7 +81,7 @@ contrast_rows_kernel(float* __restrict__ S, float* __restrict__ logits, const in
       else j = 1 + c - (self >= 0 && c > self ? 1 : 0) - (c > pos ? 1 : 0);
       lrow[j] = z;
     }
-    const float pr = __expf(z - lse);
+    const float pr = __expf(z - mx) * inv_se;
     row[c] = (pr - (c == pos ? 1.f : 0.f)) * gs;
   }
 }
