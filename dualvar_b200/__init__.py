@@ -5,3 +5,10 @@ LinearClassifier); all arithmetic runs in hand-written CUDA kernels behind the C
 include/dualvar_b200.h.
 """
 __version__ = "0.1.0"
+
+
+def set_precision(mode, planes=None):
+    """"bf16" (default, throughput mode) or "fp32" (the 1e-4 parity mode: fp32 activations, convolutions as sums of
+    bf16 split-plane products on the tcgen05 kernels; planes = 3 (24 mantissa bits, default) or 2). See engine.py."""
+    from . import engine
+    engine.set_precision(mode, planes)
