@@ -135,6 +135,47 @@ def workload_config(args, batch):
             "parallelism": f"dp{args.gpus}", "l2": "inputs (462 MB/step/GPU fp32 at 64 samples) exceed the 126 MB L2"}
 
 
+def fp32_mode_leg(dev, host_frames, steps=3, batch=16):
+    """The same step in the fp32 mode (engine.set_precision("fp32"): fp32 activations, convolutions as sums of bf16
+    split-plane products): a side figure next to the bf16 headline, 16 samples per step, resident inputs."""
+    from dualvar_b200 import engine as E, models as PM
+    from dualvar_b200.engine import RawClips
+    from dualvar_b200.optim import SGD
+    E.set_precision("fp32", 3)
+    try:
+        seed_all(0)
+        m = PM.SimCLR_TimeSeriesV4("r21d", 128, 0.07, False, True, 2, 64, 0.07, 0.07, "clip-sr-tc",
+                                   SimpleNamespace(shufflerank_theta=0.05)).to(dev).train()
+        opt = SGD([{"params": p} for p in m.parameters()], lr=0.003, weight_decay=1e-4, momentum=0.9)
+        frames = host_frames[:batch].to(dev)
+
+        def st():
+            ret = m(RawClips(frames, 3))
+            loss = sum(v for k, v in ret.items() if "loss" in k)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+            return loss
+        for _ in range(2):
+            st()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = st()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {"value": batch / (ms / 1e3), "unit": "samples/s", "ms_per_step": ms, "samples_per_gpu": batch,
+                "steps": steps, "split_planes": 3, "final_loss": float(loss),
+                "dtype": "f32 activations; conv = 6 bf16 plane products, fp32 accumulate",
+                "parity": "losses within 1e-4 of the fp32 oracle (tests/test_fp32_mode_gpu.py)"}
+    except Exception as e:  # noqa: BLE001 - a side figure must not take the headline line down
+        return {"error": f"{type(e).__name__}: {e}"}
+    finally:
+        E.set_precision("bf16")
+
+
 # --------------------------------------------------------------------------------------- our arm
 def run_ours(args):
     from dualvar_b200 import _lib, models as PM
@@ -315,6 +356,8 @@ def run_ours(args):
             "gpu_launches": int(launches), "roofline": roof, "clocks": sampler.summary(),
             "final_loss": final_loss,
         }
+        if world == 1:
+            line["fp32_mode"] = fp32_mode_leg(dev, host[0])
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             cstep = oracle_step_fn(2, cores)

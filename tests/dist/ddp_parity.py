@@ -2,6 +2,7 @@
 SyncBatchNorm + DDP (pretrain.py:244-248) vs the oracle wrapped the same way, same per-rank data.
 
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist/ddp_parity.py
+    DV_PRECISION=fp32 ... ddp_parity.py [simclr|moco]     # the fp32 mode against the 1e-4 bar
 """
 import os, sys, random
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
@@ -16,6 +17,12 @@ dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 from oracle import models as OM
 from dualvar_b200 import models as PM
+
+FP32 = os.environ.get("DV_PRECISION", "bf16") == "fp32"
+# tolerances: bf16 mode 1e-2 (north star), fp32 mode 1e-4; the absolute terms cover losses near zero (a fresh MoCo has
+# key encoder == query encoder: the clip loss is a ~1e-3 difference of two ~14 logits)
+LOSS_RTOL, LOSS_ATOL, LOGIT_TOL, GRAD_MED = (1e-4, 2e-6, 1e-4, 2e-2) if FP32 else (1e-2, 2e-3, 2e-2, 0.6)
+
 
 def rel(a, b): return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
 args = SimpleNamespace(shufflerank_theta=0.05)
@@ -42,12 +49,12 @@ for k in rr:
     if "labels" in k:
         good = torch.equal(rr[k], rp[k])
     elif "loss" in k:
-        good = abs(rp[k].item() - rr[k].item()) <= 1e-2 * abs(rr[k].item()) + 2e-3
+        good = abs(rp[k].item() - rr[k].item()) <= LOSS_RTOL * abs(rr[k].item()) + LOSS_ATOL
     else:
-        good = rr[k].shape == rp[k].shape and ((rp[k] - rr[k]).abs().max() / rr[k].abs().max()).item() < 2e-2
+        good = rr[k].shape == rp[k].shape and ((rp[k] - rr[k]).abs().max() / rr[k].abs().max()).item() < LOGIT_TOL
     ok &= bool(good)
     if "loss" in k or not good:
-        print(f"[rank {rank}] {k}: ref {rr[k].float().mean().item():.5f} prod {rp[k].float().mean().item():.5f} {'ok' if good else 'MISMATCH'}", flush=True)
+        print(f"[rank {rank}] {k}: ref {rr[k].float().mean().item():.7f} prod {rp[k].float().mean().item():.7f} {'ok' if good else 'MISMATCH'}", flush=True)
 lr = sum(v for k, v in rr.items() if "loss" in k); lp = sum(v for k, v in rp.items() if "loss" in k)
 lr.backward(); lp.backward()
 errs = sorted(rel(pp.grad, pr.grad) for pr, pp in zip(ref.parameters(), prod.parameters()) if pr.grad is not None)
@@ -57,8 +64,8 @@ gs = [torch.empty_like(g0) for _ in range(world)]
 dist.all_gather(gs, g0)
 same = all(torch.equal(gs[0], g) for g in gs)
 print(f"[rank {rank}] median grad rel err vs oracle-DDP {errs[len(errs)//2]:.3e}; grads identical across ranks: {same}", flush=True)
-ok &= same and errs[len(errs) // 2] < 0.6
+ok &= same and errs[len(errs) // 2] < GRAD_MED
 t = torch.tensor([1.0 if ok else 0.0], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print("DDP_PARITY", which, "PASS" if t.item() == 1.0 else "FAIL", flush=True)
+    print("DDP_PARITY", which, "fp32 mode" if FP32 else "bf16 mode", "PASS" if t.item() == 1.0 else "FAIL", flush=True)
 dist.destroy_process_group()
