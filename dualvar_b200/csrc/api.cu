@@ -58,12 +58,20 @@ int f32_max_planes();
 int f32_split_planes(const float* src, float* dst, long long n, int K, cudaStream_t stream);
 int f32_colstats(const float* y, double* stats, long long rows, int Cp, cudaStream_t stream);
 int f32_bn_apply(const float* y1, const float* ss1, const float* y2, const float* ss2, const float* res, float* out,
-                 void* planes, long long plane_stride, int K, long long rows, int Cp, int relu, cudaStream_t stream);
+                 void* planes, long long plane_stride, int K, long long rows, int Cp, int out_ld, int out_coff, int relu,
+                 cudaStream_t stream);
 int f32_bn_bwd_reduce(const float* dout, const float* dout2, const float* out, const float* y, const float* ss,
-                      double* sums, long long rows, int Cp, int relu, cudaStream_t stream);
+                      double* sums, long long rows, int Cp, int o_ld, int o_coff, int relu, cudaStream_t stream);
 int f32_bn_bwd_apply(const float* dout, const float* dout2, const float* out, const float* y, const float* ss,
                      const float* coef, void* dy_planes, long long plane_stride, int K, float* g_out, long long rows,
-                     int Cp, int relu, cudaStream_t stream);
+                     int Cp, int o_ld, int o_coff, int relu, cudaStream_t stream);
+int f32_slice_mean(const float* x, float* out, int N, int S, int C, int ld, int coff, cudaStream_t stream);
+int f32_gate_scale(float* x, void* planes, long long plane_stride, int K, const float* w, int N, int S, int C, int ld,
+                   int coff, cudaStream_t stream);
+int f32_gate_bwd_reduce(const float* dout, const float* y, const float* ss, float* dw, int N, int S, int C, int Cp,
+                        int ld, int coff, cudaStream_t stream);
+int f32_gate_bwd_apply(const float* dout, const float* w, const float* dmean, float* dz, int N, int S, int C, int Cp,
+                       int ld, int coff, cudaStream_t stream);
 int f32_add(const float* x, const float* y, float* out, long long n, cudaStream_t stream);
 int f32_split(const float* x, void* planes, long long plane_stride, int K, long long n, cudaStream_t stream);
 int f32_avgpool_fwd(const float* x, float* out, int N, int S, int C, int Cp, int ld_out, cudaStream_t stream);
@@ -446,27 +454,55 @@ int dv_f32_colstats(const float* y, double* stats, int64_t rows, int Cp, void* s
   return f32_colstats(y, stats, rows, Cp, ST);
 }
 int dv_f32_bn_apply(const float* y1, const float* ss1, const float* y2, const float* ss2, const float* res, float* out,
-                    void* out_planes, int64_t plane_stride, int n_planes, int64_t rows, int Cp, int relu, void* stream) {
-  DV_REQUIRE(y1 && ss1 && out && rows > 0 && Cp > 0 && Cp % 8 == 0, "bad f32_bn_apply arguments");
+                    void* out_planes, int64_t plane_stride, int n_planes, int64_t rows, int Cp, int out_ld, int out_coff,
+                    int relu, void* stream) {
+  DV_REQUIRE(y1 && ss1 && out && rows > 0 && Cp > 0 && Cp % 8 == 0 && out_ld % 8 == 0 && out_coff % 8 == 0 &&
+                 out_ld >= out_coff + Cp,
+             "bad f32_bn_apply arguments");
   DV_REQUIRE((y2 == nullptr) == (ss2 == nullptr), "f32_bn_apply: y2 and ss2 go together");
   if (out_planes != nullptr)
-    if (int rc = check_planes(n_planes, plane_stride, rows * Cp)) return rc;
-  return f32_bn_apply(y1, ss1, y2, ss2, res, out, out_planes, plane_stride, n_planes, rows, Cp, relu, ST);
+    if (int rc = check_planes(n_planes, plane_stride, rows * out_ld)) return rc;
+  return f32_bn_apply(y1, ss1, y2, ss2, res, out, out_planes, plane_stride, n_planes, rows, Cp, out_ld, out_coff, relu,
+                      ST);
 }
 int dv_f32_bn_bwd_reduce(const float* dout, const float* dout2, const float* out, const float* y, const float* mask_ss,
-                         double* sums, int64_t rows, int Cp, int relu, void* stream) {
-  DV_REQUIRE(dout && y && sums && (!relu || out || mask_ss) && rows > 0 && Cp > 0 && Cp % 8 == 0,
+                         double* sums, int64_t rows, int Cp, int o_ld, int o_coff, int relu, void* stream) {
+  DV_REQUIRE(dout && y && sums && (!relu || out || mask_ss) && rows > 0 && Cp > 0 && Cp % 8 == 0 && o_ld % 4 == 0 &&
+                 o_coff % 4 == 0 && o_ld >= o_coff + Cp,
              "bad f32_bn_bwd_reduce arguments");
-  return f32_bn_bwd_reduce(dout, dout2, out, y, mask_ss, sums, rows, Cp, relu, ST);
+  return f32_bn_bwd_reduce(dout, dout2, out, y, mask_ss, sums, rows, Cp, o_ld, o_coff, relu, ST);
 }
 int dv_f32_bn_bwd_apply(const float* dout, const float* dout2, const float* out, const float* y, const float* mask_ss,
                         const float* coef, void* dy_planes, int64_t plane_stride, int n_planes, float* g_out,
-                        int64_t rows, int Cp, int relu, void* stream) {
-  DV_REQUIRE(dout && y && coef && dy_planes && (!relu || out || mask_ss) && rows > 0 && Cp > 0 && Cp % 8 == 0,
+                        int64_t rows, int Cp, int o_ld, int o_coff, int relu, void* stream) {
+  DV_REQUIRE(dout && y && coef && dy_planes && (!relu || out || mask_ss) && rows > 0 && Cp > 0 && Cp % 8 == 0 &&
+                 o_ld % 4 == 0 && o_coff % 4 == 0 && o_ld >= o_coff + Cp,
              "bad f32_bn_bwd_apply arguments");
   if (int rc = check_planes(n_planes, plane_stride, rows * Cp)) return rc;
-  return f32_bn_bwd_apply(dout, dout2, out, y, mask_ss, coef, dy_planes, plane_stride, n_planes, g_out, rows, Cp, relu,
-                          ST);
+  return f32_bn_bwd_apply(dout, dout2, out, y, mask_ss, coef, dy_planes, plane_stride, n_planes, g_out, rows, Cp, o_ld,
+                          o_coff, relu, ST);
+}
+int dv_f32_slice_mean(const float* x, float* out, int N, int S, int C, int ld, int coff, void* stream) {
+  DV_REQUIRE(x && out && N > 0 && S > 0 && C > 0 && ld >= coff + C, "bad f32_slice_mean arguments");
+  return f32_slice_mean(x, out, N, S, C, ld, coff, ST);
+}
+int dv_f32_gate_scale(float* x, void* x_planes, int64_t plane_stride, int n_planes, const float* w, int N, int S, int C,
+                      int ld, int coff, void* stream) {
+  DV_REQUIRE(x && x_planes && w && N > 0 && S > 0 && C > 0 && C % 8 == 0 && ld % 8 == 0 && coff % 8 == 0 &&
+                 ld >= coff + C,
+             "bad f32_gate_scale arguments");
+  if (int rc = check_planes(n_planes, plane_stride, (int64_t)N * S * ld)) return rc;
+  return f32_gate_scale(x, x_planes, plane_stride, n_planes, w, N, S, C, ld, coff, ST);
+}
+int dv_f32_gate_bwd_reduce(const float* dout, const float* y, const float* ss, float* dw, int N, int S, int C, int Cp,
+                           int ld, int coff, void* stream) {
+  DV_REQUIRE(dout && y && ss && dw && N > 0 && S > 0 && C > 0 && Cp >= C, "bad f32_gate_bwd_reduce arguments");
+  return f32_gate_bwd_reduce(dout, y, ss, dw, N, S, C, Cp, ld, coff, ST);
+}
+int dv_f32_gate_bwd_apply(const float* dout, const float* w, const float* dmean, float* dz, int N, int S, int C, int Cp,
+                          int ld, int coff, void* stream) {
+  DV_REQUIRE(dout && w && dmean && dz && N > 0 && S > 0 && C > 0 && Cp >= C, "bad f32_gate_bwd_apply arguments");
+  return f32_gate_bwd_apply(dout, w, dmean, dz, N, S, C, Cp, ld, coff, ST);
 }
 int dv_f32_add(const float* a, const float* b, float* out, int64_t n, void* stream) {
   DV_REQUIRE(a && b && out && n > 0 && n % 4 == 0, "bad f32_add arguments");

@@ -80,6 +80,7 @@ struct RedArgs {
   double* sums;
   long long rows;
   int Cp, relu;
+  int o_ld, o_coff;   // dout / out are channel slices [o_coff, o_coff + Cp) of rows with o_ld channels (concat tensors)
 };
 
 template <int kMode>
@@ -94,12 +95,13 @@ __global__ void __launch_bounds__(256) f32_colreduce_kernel(const RedArgs a) {
     if (mask_ss) { fs = ld4(a.ss + c); fb = ld4(a.ss + a.Cp + c); }
     for (long long r = (long long)blockIdx.y * 8 + threadIdx.y; r < a.rows; r += (long long)gridDim.y * 8) {
       const long long off = r * a.Cp + c;
+      const long long ooff = r * a.o_ld + a.o_coff + c;
       const float4 y = ld4(a.y + off);
       if (kMode == 0) {
         s[0] += y.x; s[1] += y.y; s[2] += y.z; s[3] += y.w;
         q[0] += (double)y.x * y.x; q[1] += (double)y.y * y.y; q[2] += (double)y.z * y.z; q[3] += (double)y.w * y.w;
       } else {
-        float4 g = ld4(a.dout + off);
+        float4 g = ld4(a.dout + ooff);
         if (a.dout2 != nullptr) {
           const float4 e = ld4(a.dout2 + off);
           g.x += e.x; g.y += e.y; g.z += e.z; g.w += e.w;
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(256) f32_colreduce_kernel(const RedArgs a) {
             g.z = fmaf(y.z, fs.z, fb.z) > 0.f ? g.z : 0.f;
             g.w = fmaf(y.w, fs.w, fb.w) > 0.f ? g.w : 0.f;
           } else {
-            const float4 o = ld4(a.out + off);
+            const float4 o = ld4(a.out + ooff);
             g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f;
             g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
           }
@@ -159,11 +161,13 @@ __global__ void __launch_bounds__(256) f32_bn_apply_kernel(const float* __restri
                                                            const float* __restrict__ y2, const float* __restrict__ ss2,
                                                            const float* __restrict__ res, float* __restrict__ out,
                                                            __nv_bfloat16* __restrict__ planes, long long plane_stride,
-                                                           int K, long long total4, int Cp, int relu) {
+                                                           int K, long long total4, int Cp, int out_ld, int out_coff,
+                                                           int relu) {
   const int G = Cp >> 2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
        i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % G) * 4;
+    const long long o = (i / G) * out_ld + out_coff + c;   // destination: a channel slice of a (concat) tensor
     const float4 y = ld4(y1 + i * 4), s = ld4(ss1 + c), b = ld4(ss1 + Cp + c);
     float4 v = make_float4(fmaf(y.x, s.x, b.x), fmaf(y.y, s.y, b.y), fmaf(y.z, s.z, b.z), fmaf(y.w, s.w, b.w));
     if (y2 != nullptr) {
@@ -176,8 +180,8 @@ __global__ void __launch_bounds__(256) f32_bn_apply_kernel(const float* __restri
       v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
     }
     if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-    st4(out + i * 4, v);
-    if (planes != nullptr) split_store4(v, planes, plane_stride, K, i * 4);
+    st4(out + o, v);
+    if (planes != nullptr) split_store4(v, planes, plane_stride, K, o);
   }
 }
 
@@ -193,7 +197,8 @@ __global__ void __launch_bounds__(256) f32_bn_bwd_apply_kernel(const RedArgs a, 
        i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % G) * 4;
     const float4 y = ld4(a.y + i * 4);
-    float4 g = ld4(a.dout + i * 4);
+    const long long ooff = (i / G) * a.o_ld + a.o_coff + c;
+    float4 g = ld4(a.dout + ooff);
     if (a.dout2 != nullptr) {
       const float4 e = ld4(a.dout2 + i * 4);
       g.x += e.x; g.y += e.y; g.z += e.z; g.w += e.w;
@@ -206,7 +211,7 @@ __global__ void __launch_bounds__(256) f32_bn_bwd_apply_kernel(const RedArgs a, 
         g.z = fmaf(y.z, fs.z, fb.z) > 0.f ? g.z : 0.f;
         g.w = fmaf(y.w, fs.w, fb.w) > 0.f ? g.w : 0.f;
       } else {
-        const float4 o = ld4(a.out + i * 4);
+        const float4 o = ld4(a.out + ooff);
         g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f;
         g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
       }
@@ -231,6 +236,87 @@ __global__ void __launch_bounds__(256) f32_split_kernel(const float* __restrict_
                                                         long long plane_stride, int K, long long n4) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
     split_store4(ld4(x + i * 4), planes, plane_stride, K, i * 4);
+}
+
+// ------------------------------------------------------------------ S3D-G self-gating on fp32 concat slices
+// (backbone/s3dg.py:68-78; the bf16 versions are in gating.cu). x: rows of `ld` channels, slice [coff, coff + C).
+__global__ void f32_slice_mean_kernel(const float* __restrict__ x, float* __restrict__ out, int S, int C, int ld,
+                                      int coff) {
+  const int n = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float part[8][128];
+  float s = 0.f;
+  if (c < C) {
+    const float* p = x + (long long)n * S * ld + coff + c;
+    for (int i = threadIdx.y; i < S; i += blockDim.y) s += p[(long long)i * ld];
+  }
+  part[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+    for (int j = 0; j < (int)blockDim.y; ++j) t += part[j][threadIdx.x];
+    out[(long long)n * C + c] = t / (float)S;
+  }
+}
+
+// x[n][s][coff+c] *= w[n][c] in place, split planes of the slice rewritten
+__global__ void __launch_bounds__(256) f32_gate_scale_kernel(float* __restrict__ x, __nv_bfloat16* __restrict__ planes,
+                                                             long long plane_stride, int K, const float* __restrict__ w,
+                                                             int S, int C, int ld, int coff, long long total4) {
+  const int G = C >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % G) * 4;
+    const long long r = i / G;
+    const long long n = r / S;
+    const long long o = r * ld + coff + c;
+    float4 v = ld4(x + o);
+    const float4 g = ld4(w + n * C + c);
+    v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
+    st4(x + o, v);
+    split_store4(v, planes, plane_stride, K, o);
+  }
+}
+
+// dw[n][c] = sum_s dout[n][s][coff+c] * z[n][s][c],  z = relu(scale[c]*y + shift[c]) recomputed from y
+__global__ void f32_gate_bwd_reduce_kernel(const float* __restrict__ dout, const float* __restrict__ y,
+                                           const float* __restrict__ ss, float* __restrict__ dw, int S, int C, int Cp,
+                                           int ld, int coff) {
+  const int n = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float part[8][128];
+  float s = 0.f;
+  if (c < C) {
+    const float sc = ss[c], sh = ss[Cp + c];
+    const float* pd = dout + (long long)n * S * ld + coff + c;
+    const float* py = y + (long long)n * S * Cp + c;
+    for (int i = threadIdx.y; i < S; i += blockDim.y) {
+      const float z = fmaxf(fmaf(py[(long long)i * Cp], sc, sh), 0.f);
+      s = fmaf(pd[(long long)i * ld], z, s);
+    }
+  }
+  part[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+    for (int j = 0; j < (int)blockDim.y; ++j) t += part[j][threadIdx.x];
+    dw[(long long)n * C + c] = t;
+  }
+}
+
+// dz[n][s][c] = w[n][c] * dout[n][s][coff+c] + dmean[n][c] / S   (dense [rows][Cp], pad channels zero)
+__global__ void __launch_bounds__(256) f32_gate_bwd_apply_kernel(const float* __restrict__ dout,
+                                                                 const float* __restrict__ w,
+                                                                 const float* __restrict__ dmean, float* __restrict__ dz,
+                                                                 int S, int C, int Cp, int ld, int coff, long long total) {
+  const float inv = 1.f / (float)S;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cp);
+    const long long r = i / Cp;
+    const long long n = r / S;
+    dz[i] = c < C ? w[n * C + c] * dout[r * ld + coff + c] + dmean[n * C + c] * inv : 0.f;
+  }
 }
 
 // ------------------------------------------------------------------ pooling
@@ -378,32 +464,34 @@ int f32_split_planes(const float* src, float* dst, long long n, int K, cudaStrea
 
 int f32_colstats(const float* y, double* stats, long long rows, int Cp, cudaStream_t stream) {
   RedArgs a = {};
-  a.y = y; a.sums = stats; a.rows = rows; a.Cp = Cp;
+  a.y = y; a.sums = stats; a.rows = rows; a.Cp = Cp; a.o_ld = Cp;
   return launch_colreduce(0, a, stream);
 }
 
 int f32_bn_apply(const float* y1, const float* ss1, const float* y2, const float* ss2, const float* res, float* out,
-                 void* planes, long long plane_stride, int K, long long rows, int Cp, int relu, cudaStream_t stream) {
+                 void* planes, long long plane_stride, int K, long long rows, int Cp, int out_ld, int out_coff, int relu,
+                 cudaStream_t stream) {
   const long long total4 = rows * (Cp / 4);
   f32_bn_apply_kernel<<<flat_grid32(total4, 256), 256, 0, stream>>>(y1, ss1, y2, ss2, res, out, (__nv_bfloat16*)planes,
-                                                                    plane_stride, K, total4, Cp, relu);
+                                                                    plane_stride, K, total4, Cp, out_ld, out_coff, relu);
   DV_LAUNCH_OK();
   return kOk;
 }
 
 int f32_bn_bwd_reduce(const float* dout, const float* dout2, const float* out, const float* y, const float* ss,
-                      double* sums, long long rows, int Cp, int relu, cudaStream_t stream) {
+                      double* sums, long long rows, int Cp, int o_ld, int o_coff, int relu, cudaStream_t stream) {
   RedArgs a = {};
   a.y = y; a.dout = dout; a.dout2 = dout2; a.out = out; a.ss = ss; a.sums = sums; a.rows = rows; a.Cp = Cp;
-  a.relu = relu;
+  a.relu = relu; a.o_ld = o_ld; a.o_coff = o_coff;
   return launch_colreduce(1, a, stream);
 }
 
 int f32_bn_bwd_apply(const float* dout, const float* dout2, const float* out, const float* y, const float* ss,
                      const float* coef, void* dy_planes, long long plane_stride, int K, float* g_out, long long rows,
-                     int Cp, int relu, cudaStream_t stream) {
+                     int Cp, int o_ld, int o_coff, int relu, cudaStream_t stream) {
   RedArgs a = {};
   a.y = y; a.dout = dout; a.dout2 = dout2; a.out = out; a.ss = ss; a.rows = rows; a.Cp = Cp; a.relu = relu;
+  a.o_ld = o_ld; a.o_coff = o_coff;
   const long long total4 = rows * (Cp / 4);
   f32_bn_bwd_apply_kernel<<<flat_grid32(total4, 256), 256, 0, stream>>>(a, coef, (__nv_bfloat16*)dy_planes,
                                                                         plane_stride, K, g_out, total4);
@@ -465,6 +553,37 @@ int f32_ndhwc_to_ncdhw(const float* y, float* x, int N, int C, int Cp, long long
 int f32_ncdhw_to_ndhwc(const float* x, float* y, int N, int C, int Cp, long long S, cudaStream_t stream) {
   const long long total = (long long)N * S * Cp;
   f32_ncdhw_to_ndhwc_kernel<<<flat_grid32(total, 256), 256, 0, stream>>>(x, y, C, Cp, S, total);
+  DV_LAUNCH_OK();
+  return kOk;
+}
+
+int f32_slice_mean(const float* x, float* out, int N, int S, int C, int ld, int coff, cudaStream_t stream) {
+  f32_slice_mean_kernel<<<dim3(ceil_div(C, 128), N), dim3(128, 8), 0, stream>>>(x, out, S, C, ld, coff);
+  DV_LAUNCH_OK();
+  return kOk;
+}
+
+int f32_gate_scale(float* x, void* planes, long long plane_stride, int K, const float* w, int N, int S, int C, int ld,
+                   int coff, cudaStream_t stream) {
+  const long long total4 = (long long)N * S * (C / 4);
+  f32_gate_scale_kernel<<<flat_grid32(total4, 256), 256, 0, stream>>>(x, (__nv_bfloat16*)planes, plane_stride, K, w, S,
+                                                                      C, ld, coff, total4);
+  DV_LAUNCH_OK();
+  return kOk;
+}
+
+int f32_gate_bwd_reduce(const float* dout, const float* y, const float* ss, float* dw, int N, int S, int C, int Cp,
+                        int ld, int coff, cudaStream_t stream) {
+  f32_gate_bwd_reduce_kernel<<<dim3(ceil_div(C, 128), N), dim3(128, 8), 0, stream>>>(dout, y, ss, dw, S, C, Cp, ld,
+                                                                                      coff);
+  DV_LAUNCH_OK();
+  return kOk;
+}
+
+int f32_gate_bwd_apply(const float* dout, const float* w, const float* dmean, float* dz, int N, int S, int C, int Cp,
+                       int ld, int coff, cudaStream_t stream) {
+  const long long total = (long long)N * S * Cp;
+  f32_gate_bwd_apply_kernel<<<flat_grid32(total, 256), 256, 0, stream>>>(dout, w, dmean, dz, S, C, Cp, ld, coff, total);
   DV_LAUNCH_OK();
   return kOk;
 }

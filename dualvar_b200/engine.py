@@ -31,7 +31,7 @@ call = _lib.call
 # kept as F32_PLANES bf16 split planes (x = p0 + p1 + p2, csrc/fp32_mode.cu) and a convolution is the sum of the
 # plane products with i + j < F32_PLANES, each one launch of the same tcgen05 kernel adding its fp32 accumulator tile
 # to the fp32 output. 3 planes carry 24 mantissa bits (6 launches per conv), 2 planes 16 bits (3 launches).
-# Covers the ResNet-style encoders and C3D (select_backbone r21d / r3d / c3d / r2d3d18); S3D / S3D-G stay bf16-only.
+# Covers every select_backbone network (r21d / r3d / c3d / s3d / s3dg / r2d3d18).
 PRECISION = os.environ.get("DV_PRECISION", "bf16")
 F32_PLANES = int(os.environ.get("DV_FP32_PLANES", "3"))
 
@@ -612,45 +612,61 @@ def _bn_bwd_finalize(ctx, r, sums, Cp, dev):
     return coef
 
 
-def _activate_f32(ctx, r1, r2, res, relu):
-    """fp32 mode of activate(): out = relu?(BN(r1) [+ BN(r2)] [+ res]) as fp32 plus its split planes."""
+def _activate_f32(ctx, r1, r2, res, relu, out=None, out_coff=0):
+    """fp32 mode of activate(): out = relu?(BN(r1) [+ BN(r2)] [+ res]) as fp32 plus its split planes, dense or into
+    the channel slice [out_coff, out_coff + Cp) of the concat activation ``out``."""
     g = r1.geom
     Cp = g.Cout_p
     dev = r1.y.device
     K = F32_PLANES
-    out_t = torch.empty_like(r1.y)
-    planes = torch.empty((K,) + tuple(r1.y.shape), dtype=torch.bfloat16, device=dev)
     rows = r1.y.numel() // Cp
+    if out is None:
+        out_t = torch.empty_like(r1.y)
+        planes = torch.empty((K,) + tuple(r1.y.shape), dtype=torch.bfloat16, device=dev)
+        out_act = Act(out_t, g.Cout, planes=planes)
+        out_ld = Cp
+    else:
+        out_act, out_t, planes, out_ld = out, out.data, out.planes, out.Cp
     call("dv_f32_bn_apply", ptr(r1.y), ptr(r1.ss), ptr(r2.y) if r2 else None, ptr(r2.ss) if r2 else None,
-         ptr(res.data) if res is not None else None, ptr(out_t), ptr(planes), planes.stride(0), K, rows, Cp,
-         1 if relu else 0, stream_ptr())
-    out_act = Act(out_t, g.Cout, planes=planes)
+         ptr(res.data) if res is not None else None, ptr(out_t), ptr(planes), planes.stride(0), K, rows, Cp, out_ld,
+         out_coff, 1 if relu else 0, stream_ptr())
     if not ctx.record:
         return out_act
 
     def backward():
-        dout, dout2 = out_act.grad, out_act.grad2
+        dout2 = None
+        if out is None:
+            dout, dout2 = out_act.grad, out_act.grad2
+        else:
+            dout = _materialize_grad(out_act)
+        o_ld, o_coff = out_ld, out_coff
+        ov = ctx.overrides.pop((id(out_act), out_coff), None)
+        if ov is not None:      # a gate in front of this slice already produced the dense gradient
+            dout, dout2, o_ld, o_coff = ov, None, Cp, 0
         assert dout is not None, "activation has no gradient"
         need_g = res is not None and res.needs_grad
         g_buf = None
         mask_ss = ptr(r1.ss) if (relu and r2 is None and res is None) else None
+        assert ov is None or mask_ss is not None
         for r in (r1, r2):
             if r is None:
                 continue
             sums = ctx.zeros64(2 * Cp, dev)
             call("dv_f32_bn_bwd_reduce", ptr(dout), ptr(dout2), ptr(out_t), ptr(r.y), mask_ss, ptr(sums), rows, Cp,
-                 1 if relu else 0, stream_ptr())
+                 o_ld, o_coff, 1 if relu else 0, stream_ptr())
             coef = _bn_bwd_finalize(ctx, r, sums, Cp, dev)
             dyp = torch.empty((K,) + tuple(r.y.shape), dtype=torch.bfloat16, device=dev)
             want_g = need_g and g_buf is None
             if want_g:
                 g_buf = torch.empty_like(r.y)
             call("dv_f32_bn_bwd_apply", ptr(dout), ptr(dout2), ptr(out_t), ptr(r.y), mask_ss, ptr(coef), ptr(dyp),
-                 dyp.stride(0), K, ptr(g_buf) if want_g else None, rows, Cp, 1 if relu else 0, stream_ptr())
+                 dyp.stride(0), K, ptr(g_buf) if want_g else None, rows, Cp, o_ld, o_coff, 1 if relu else 0,
+                 stream_ptr())
             _conv_backward_f32(ctx, r, dyp)
         if need_g:
             _acc_grad(res, g_buf)
-        out_act.grad = out_act.grad2 = None
+        if out is None:
+            out_act.grad = out_act.grad2 = None
 
     ctx.tape.append(backward)
     return out_act
@@ -661,9 +677,7 @@ def activate(ctx, r1, r2=None, res=None, relu=True, out=None, out_coff=0):
     channel slices of one tensor (concat-free Inception, backbone/s3dg.py:130).
     Reference: BatchNorm3d affine + ReLU + residual add (backbone/r21d.py:116-122)."""
     if fp32_mode():
-        if out is not None:
-            raise _lib.DualVarNativeError("the fp32 mode has no concat-slice outputs (S3D / S3D-G run in the bf16 mode)")
-        return _activate_f32(ctx, r1, r2, res, relu)
+        return _activate_f32(ctx, r1, r2, res, relu, out, out_coff)
     g = r1.geom
     Cp = g.Cout_p
     dev = r1.y.device
@@ -732,10 +746,12 @@ def activate(ctx, r1, r2=None, res=None, relu=True, out=None, out_coff=0):
 def new_concat(x, C_total):
     """Empty activation with x's N,T,H,W that several branches fill slice by slice
     (torch.cat of the Inception branches, backbone/s3dg.py:130)."""
-    if fp32_mode():
-        raise _lib.DualVarNativeError("the fp32 mode does not cover S3D / S3D-G (concat branches run in the bf16 mode)")
     N, T, H, W, _ = x.shape5
     assert C_total % 8 == 0
+    if fp32_mode():
+        dev = x.device
+        return Act(torch.empty((N, T, H, W, C_total), dtype=torch.float32, device=dev), C_total,
+                   planes=torch.empty((F32_PLANES, N, T, H, W, C_total), dtype=torch.bfloat16, device=dev))
     return Act(torch.empty((N, T, H, W, C_total), dtype=torch.bfloat16, device=x.data.device), C_total)
 
 
@@ -746,22 +762,28 @@ def self_gate(ctx, cat, coff, raw, fc):
     S = T * H * W
     C, Cp = raw.geom.Cout, raw.geom.Cout_p
     dev = cat.data.device
+    f32 = cat.data.dtype == torch.float32      # fp32 mode: same flow on the fp32 kernels, planes kept in step
+    pre_ = "dv_f32_" if f32 else "dv_"
     mean = torch.empty((N, C), dtype=torch.float32, device=dev)
-    call("dv_slice_mean", ptr(cat.data), ptr(mean), N, S, C, ld, coff, stream_ptr())
+    call(pre_ + "slice_mean", ptr(cat.data), ptr(mean), N, S, C, ld, coff, stream_ptr())
     pre = torch.empty((N, C), dtype=torch.float32, device=dev)
     f = ctypes.c_float
     call("dv_sgemm", 0, 1, N, C, C, f(1.0), ptr(mean), C, ptr(fc.weight.detach()), C, f(0.0), ptr(pre), C,
          ptr(fc.bias.detach()), 0, stream_ptr())
     w = torch.empty_like(pre)
     call("dv_sigmoid_fwd", ptr(pre), ptr(w), N * C, stream_ptr())
-    call("dv_gate_scale", ptr(cat.data), ptr(w), N, S, C, ld, coff, stream_ptr())
+    if f32:
+        call("dv_f32_gate_scale", ptr(cat.data), ptr(cat.planes), cat.planes.stride(0), F32_PLANES, ptr(w), N, S, C, ld,
+             coff, stream_ptr())
+    else:
+        call("dv_gate_scale", ptr(cat.data), ptr(w), N, S, C, ld, coff, stream_ptr())
     if not ctx.record:
         return
 
     def backward():
         dout = _materialize_grad(cat)
         dw = torch.empty((N, C), dtype=torch.float32, device=dev)
-        call("dv_gate_bwd_reduce", ptr(dout), ptr(raw.y), ptr(raw.ss), ptr(dw), N, S, C, Cp, ld, coff, stream_ptr())
+        call(pre_ + "gate_bwd_reduce", ptr(dout), ptr(raw.y), ptr(raw.ss), ptr(dw), N, S, C, Cp, ld, coff, stream_ptr())
         dpre = torch.empty_like(dw)
         call("dv_sigmoid_bwd", ptr(dw), ptr(w), ptr(dpre), N * C, stream_ptr())
         gW = torch.empty_like(fc.weight)
@@ -773,8 +795,8 @@ def self_gate(ctx, cat, coff, raw, fc):
         dmean = torch.empty_like(dw)
         call("dv_sgemm", 0, 0, N, C, C, f(1.0), ptr(dpre), C, ptr(fc.weight.detach()), C, f(0.0), ptr(dmean), C,
              None, 0, stream_ptr())
-        dz = torch.empty((N, T, H, W, Cp), dtype=torch.bfloat16, device=dev)
-        call("dv_gate_bwd_apply", ptr(dout), ptr(w), ptr(dmean), ptr(dz), N, S, C, Cp, ld, coff, stream_ptr())
+        dz = torch.empty((N, T, H, W, Cp), dtype=cat.data.dtype, device=dev)
+        call(pre_ + "gate_bwd_apply", ptr(dout), ptr(w), ptr(dmean), ptr(dz), N, S, C, Cp, ld, coff, stream_ptr())
         ctx.overrides[(id(cat), coff)] = dz
 
     ctx.tape.append(backward)

@@ -277,16 +277,27 @@ int dv_conv3d_stem_wgrad_bf16_acc(const void* x_s2d_plane, const void* dy_plane,
 /* BatchNorm batch statistics of an fp32 conv output: adds per-channel sum / sum of squares (double, caller zeroes)
  * into stats[0:Cp] / stats[Cp:2Cp]; dv_bn_finalize(_sync) then applies unchanged */
 int dv_f32_colstats(const float* y, double* stats, int64_t rows, int Cp, void* stream);
-/* out = relu?(ss1*y1 [+ ss2*y2] [+ res]) as fp32 and (out_planes != NULL) as split planes (dv_bn_apply) */
+/* out = relu?(ss1*y1 [+ ss2*y2] [+ res]) as fp32 and (out_planes != NULL) as split planes (dv_bn_apply); out / out_planes
+ * are the channel slice [out_coff, out_coff + Cp) of rows with out_ld channels (out_ld = Cp, out_coff = 0: dense) */
 int dv_f32_bn_apply(const float* y1, const float* ss1, const float* y2, const float* ss2, const float* res, float* out,
-                    void* out_planes, int64_t plane_stride, int n_planes, int64_t rows, int Cp, int relu, void* stream);
+                    void* out_planes, int64_t plane_stride, int n_planes, int64_t rows, int Cp, int out_ld, int out_coff,
+                    int relu, void* stream);
 /* dv_bn_bwd_reduce / dv_bn_bwd_apply on fp32 tensors; dy leaves as split planes (it only feeds dgrad and wgrad),
  * g_out (nullable) is the masked gradient for the residual branch */
 int dv_f32_bn_bwd_reduce(const float* dout, const float* dout2, const float* out, const float* y, const float* mask_ss,
-                         double* sums, int64_t rows, int Cp, int relu, void* stream);
+                         double* sums, int64_t rows, int Cp, int o_ld, int o_coff, int relu, void* stream);
 int dv_f32_bn_bwd_apply(const float* dout, const float* dout2, const float* out, const float* y, const float* mask_ss,
                         const float* coef, void* dy_planes, int64_t plane_stride, int n_planes, float* g_out,
-                        int64_t rows, int Cp, int relu, void* stream);
+                        int64_t rows, int Cp, int o_ld, int o_coff, int relu, void* stream);
+/* S3D-G self-gating on an fp32 concat slice (dv_slice_mean / dv_gate_scale / dv_gate_bwd_*); gate_scale also rewrites
+ * the slice's split planes */
+int dv_f32_slice_mean(const float* x, float* out, int N, int S, int C, int ld, int coff, void* stream);
+int dv_f32_gate_scale(float* x, void* x_planes, int64_t plane_stride, int n_planes, const float* w, int N, int S, int C,
+                      int ld, int coff, void* stream);
+int dv_f32_gate_bwd_reduce(const float* dout, const float* y, const float* ss, float* dw, int N, int S, int C, int Cp,
+                           int ld, int coff, void* stream);
+int dv_f32_gate_bwd_apply(const float* dout, const float* w, const float* dmean, float* dz, int N, int S, int C, int Cp,
+                          int ld, int coff, void* stream);
 int dv_f32_add(const float* a, const float* b, float* out, int64_t n, void* stream);
 /* fp32 tensor -> split planes */
 int dv_f32_split(const float* x, void* planes, int64_t plane_stride, int n_planes, int64_t n, void* stream);
