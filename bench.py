@@ -167,7 +167,7 @@ def fp32_mode_leg(dev, host_frames, steps=3, batch=16):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
         return {"value": batch / (ms / 1e3), "unit": "samples/s", "ms_per_step": ms, "samples_per_gpu": batch,
-                "steps": steps, "split_planes": 3, "final_loss": float(loss),
+                "steps": steps, "split_planes": 3, "final_loss": float(loss.detach()),
                 "dtype": "f32 activations; conv = 6 bf16 plane products, fp32 accumulate",
                 "parity": "losses within 1e-4 of the fp32 oracle (tests/test_fp32_mode_gpu.py)"}
     except Exception as e:  # noqa: BLE001 - a side figure must not take the headline line down
