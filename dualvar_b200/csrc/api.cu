@@ -53,6 +53,9 @@ int conv_stem_fprop_bf16(const void* x_s2d, const void* w_stem, void* y, double*
                          bool y_f32_acc = false);
 int conv_stem_wgrad_bf16(const void* x_s2d, const void* dy, float* dw, int N, int T, int H2, int W2,
                          int Cout_p, int kt, int pt, cudaStream_t stream, bool accumulate = false);
+int frames_scale_crop_u8(const uint8_t* frames, uint8_t* tmp, uint8_t* out, const int* crop_lu, int B, int V, int T,
+                         int Hs, int Ws, int scale_w, int scale_h, int crop_w, int crop_h, cudaStream_t stream);
+int frames_axis_table_host(int in_size, int out_size, int* tab, int capacity, int* ksize);
 // fp32 mode (fp32_mode.cu)
 int f32_max_planes();
 int f32_split_planes(const float* src, float* dst, long long n, int K, cudaStream_t stream);
@@ -553,6 +556,20 @@ int dv_ingest_clips_planes(const void* src, int src_is_u8, void* dst_planes, int
   if (int rc = check_planes(n_planes, plane_stride, plane)) return rc;
   return ingest(src, src_is_u8 ? 1 : 0, dst_planes, perm, sb, sv, sc, st, B, C, T, H, W, view, nv, n_series, mean_host,
                 std_host, s2d, ST, n_planes, plane_stride);
+}
+
+int dv_frames_scale_crop_u8(const uint8_t* frames, uint8_t* tmp, uint8_t* out, const int32_t* crop_lu, int B, int n_views,
+                            int T, int Hs, int Ws, int scale_w, int scale_h, int crop_w, int crop_h, void* stream) {
+  DV_REQUIRE(frames && tmp && out && crop_lu, "NULL pointer");
+  DV_REQUIRE(B > 0 && n_views > 0 && T > 0 && Hs > 0 && Ws > 0, "empty frame batch");
+  DV_REQUIRE(scale_w > 0 && scale_h > 0 && crop_w > 0 && crop_h > 0 && crop_w <= scale_w && crop_h <= scale_h,
+             "crop %dx%d does not fit the scaled frame %dx%d", crop_w, crop_h, scale_w, scale_h);
+  return frames_scale_crop_u8(frames, tmp, out, crop_lu, B, n_views, T, Hs, Ws, scale_w, scale_h, crop_w, crop_h, ST);
+}
+
+int dv_frames_axis_table_host(int in_size, int out_size, int32_t* table_host, int capacity, int32_t* ksize_host) {
+  DV_REQUIRE(in_size > 0 && out_size > 0 && table_host && ksize_host && capacity > 0, "bad axis_table arguments");
+  return frames_axis_table_host(in_size, out_size, table_host, capacity, ksize_host);
 }
 
 int dv_moco_momentum_update(const int64_t* chunk_table, int n_chunks, float m, void* stream) {

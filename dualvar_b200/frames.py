@@ -1,0 +1,71 @@
+"""Frame staging in front of the encoders (first stage): the runnable part of the reference loader's
+per-clip transform - ``A.Scale((128, 171))`` + ``A.RandomCrop(112)`` + ``A.ToTensor()`` (the ``null_transform`` of
+pretrain.py:491-497, utils/augmentation.py:125-176,361-364) - on the GPU from decoded uint8 frames, bit-exact with
+Pillow's bicubic resampler. The reference does this on the host CPU with PIL for every one of the 48 frames of a sample
+(dataset/local_dataset.py:289-300), which at ~850 samples/s per GPU is the first thing to starve the step.
+
+    crops = frames.draw_crops(B, 3)                                   # random.randint in the reference's order
+    clips = frames.stage_clips(frames_u8.cuda(), crops, n_views=3)    # engine.RawClips over uint8 (B,3,48,112,112)
+    ret = model(clips)
+
+ColorJitter / GaussianBlur are not covered: the reference's ColorJitter cannot run as shipped (its numpy adjust_*
+functions assert an HWC array, utils/augmentation.py:90-92, and are handed CHW tensors at :617), so there is nothing to
+pin a restatement against.
+"""
+import ctypes
+import random
+
+import torch
+
+from . import _lib
+from .engine import RawClips
+
+call, ptr, stream_ptr = _lib.call, _lib.ptr, _lib.stream_ptr
+
+
+def draw_crops(B, n_views, rng=random, scaled=(128, 171), crop=(112, 112)):
+    """(B, n_views, 2) int32 (h_start, w_start) pairs in the order A.RandomCrop draws them: one pair per clip,
+    ``random.randint(0, h - size0)`` then ``random.randint(0, w - size1)`` with h = img.size[0] = 128 (the PIL width) and
+    w = img.size[1] = 171 (utils/augmentation.py:160-166). crop() takes them as (left, upper)."""
+    out = torch.zeros((B, n_views, 2), dtype=torch.int32)
+    for b in range(B):
+        for v in range(n_views):
+            out[b, v, 0] = rng.randint(0, scaled[0] - crop[0])
+            out[b, v, 1] = rng.randint(0, scaled[1] - crop[1])
+    return out
+
+
+def scale_crop(frames, crops, n_views, scale_size=(128, 171), crop_size=(112, 112)):
+    """frames: uint8 CUDA tensor (B, n_views*T, Hs, Ws, 3) of decoded frames; crops: int32 (B, n_views, 2).
+    Returns uint8 (B, 3, n_views*T, crop_h, crop_w): every frame resized to scale_size = (width, height) with PIL's
+    bicubic filter and cropped at its clip's (left, upper)."""
+    if not frames.is_cuda:
+        raise _lib.DualVarNativeError("scale_crop: frames must be on a B200 (no CPU fallback)")
+    assert frames.dtype == torch.uint8 and frames.dim() == 5 and frames.shape[4] == 3, "frames: uint8 (B, F, H, W, 3)"
+    frames = frames.contiguous()
+    B, F, Hs, Ws, _ = frames.shape
+    assert F % n_views == 0
+    crops = crops.to(device=frames.device, dtype=torch.int32).contiguous()
+    assert tuple(crops.shape) == (B, n_views, 2)
+    sw, sh = scale_size
+    cw, ch = crop_size
+    tmp = torch.empty((B * F, Hs, sw, 3), dtype=torch.uint8, device=frames.device)
+    out = torch.empty((B, 3, F, ch, cw), dtype=torch.uint8, device=frames.device)
+    call("dv_frames_scale_crop_u8", ptr(frames), ptr(tmp), ptr(out), ptr(crops), B, n_views, F // n_views, Hs, Ws, sw, sh,
+         cw, ch, stream_ptr())
+    return out
+
+
+def stage_clips(frames, crops, n_views, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):
+    """Decoded frames -> the model input: Scale + RandomCrop here, ToTensor + Normalize + layout in the ingest kernel."""
+    return RawClips(scale_crop(frames, crops, n_views), n_views, mean, std)
+
+
+def axis_table(in_size, out_size):
+    """Host-side fixed-point bicubic table of one axis as the library computes it: (ksize, int32 [out_size][ksize+2])."""
+    cap = out_size * (4 * max(1, -(-in_size // out_size)) + 8)
+    buf = (ctypes.c_int32 * cap)()
+    ks = ctypes.c_int32(0)
+    call("dv_frames_axis_table_host", in_size, out_size, buf, cap, ctypes.byref(ks))
+    t = torch.tensor(list(buf[:out_size * (ks.value + 2)]), dtype=torch.int32).view(out_size, ks.value + 2)
+    return ks.value, t

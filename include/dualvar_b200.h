@@ -315,6 +315,18 @@ int dv_ingest_clips_planes(const void* src, int src_is_u8, void* dst_planes, int
                            int H, int W, int view, int nv, int n_series, const float* mean_host, const float* std_host,
                            int s2d, void* stream);
 
+/* ---- frame staging (first stage) ---------------------------------------------------
+ * A.Scale((128,171)) (PIL bicubic) + A.RandomCrop(112) of the loader's null_transform (utils/augmentation.py:125-176,
+ * pretrain.py:491-497), bit-exact with Pillow's 8-bit resampler. frames: uint8 [B][n_views*T][Hs][Ws][3] decoded
+ * frames; tmp: uint8 scratch [B*n_views*T][Hs][scale_w][3]; crop_lu: int32 [B][n_views][2] = (left, upper) of each
+ * clip's crop in the scaled frame (what RandomCrop draws as h_start, w_start); out: uint8 [B][3][n_views*T][crop_h][crop_w],
+ * the layout dv_ingest_clips_u8 reads (ToTensor, Normalize and the NDHWC conversion happen there). */
+int dv_frames_scale_crop_u8(const uint8_t* frames, uint8_t* tmp, uint8_t* out, const int32_t* crop_lu, int B, int n_views,
+                            int T, int Hs, int Ws, int scale_w, int scale_h, int crop_w, int crop_h, void* stream);
+/* host-only (no GPU needed): the 22-bit fixed-point bicubic table of one axis, out_size rows of
+ * [first input index, tap count, taps[ksize]] - what Pillow's precompute_coeffs + normalize_coeffs_8bpc produce */
+int dv_frames_axis_table_host(int in_size, int out_size, int32_t* table_host, int capacity, int32_t* ksize_host);
+
 #ifdef __cplusplus
 }
 #endif
