@@ -96,7 +96,7 @@ def oracle_step_fn(batch, threads):
         opt.zero_grad()
         loss.backward()
         opt.step()
-        return float(loss)
+        return float(loss.detach())
 
     return step
 
@@ -210,7 +210,8 @@ def run_ours(args):
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
 
-    bufs = {"host": host, "dev": dev_in}       # the e2e leg's source: fp32 loader batches (or uint8 frames, see below)
+    # the e2e legs' source: fp32 loader batches, uint8 crops or decoded uint8 frames (see below)
+    bufs = {"host": host, "dev": dev_in, "wrap": lambda fr: RawClips(fr, 3)}
 
     def prefetch(i):
         with torch.cuda.stream(copy_stream):
@@ -225,7 +226,7 @@ def run_ours(args):
             torch.cuda.current_stream().wait_event(ready[i % 2])
             prefetch(i + 1)
         frames = bufs["dev"][i % 2]
-        ret = model(RawClips(frames, 3))
+        ret = model(bufs["wrap"](frames))
         loss = sum(v for k, v in ret.items() if "loss" in k)
         opt.zero_grad(set_to_none=True)
         loss.backward()
@@ -298,6 +299,26 @@ def run_ours(args):
     torch.cuda.synchronize()
     prefetch(0)
     ms_e2e_u8 = timed(args.steps, True, 0)
+    # the same step fed with DECODED frames (uint8 HWC 320x240, what a JPEG decoder yields): Scale((128,171)) bicubic +
+    # RandomCrop(112) of the reference loader run on the GPU (dualvar_b200/frames.py, bit-exact with Pillow) instead of in
+    # 16 PIL worker processes; crop offsets drawn on the host every step as A.RandomCrop does
+    ms_e2e_dec = None
+    if world == 1:
+        from dualvar_b200 import frames as FR
+        dec = torch.randint(0, 256, (B, 48, 240, 320, 3), dtype=torch.uint8, generator=gen).pin_memory()
+        dec_h = [dec, dec.clone().pin_memory()]
+        del u8
+        bufs["host"], bufs["dev"] = dec_h, [torch.empty_like(dec, device=dev) for _ in range(2)]
+        bufs["wrap"] = lambda fr: FR.stage_clips(fr, FR.draw_crops(B, 3), 3)
+        for i in range(2):
+            consumed[i].record()
+        torch.cuda.synchronize()
+        prefetch(0)
+        timed(2, True, 0)                     # warm-up of the staging kernels and their tables
+        prefetch(0)
+        ms_e2e_dec = timed(args.steps, True, 0)
+        dec_bytes = dec.numel()
+        bufs["wrap"] = lambda fr: RawClips(fr, 3)
     bufs["host"], bufs["dev"] = host, dev_in
     sampler.stop_flag = True
 
@@ -353,6 +374,11 @@ def run_ours(args):
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
             "e2e_uint8_frames": {"value": B * world / (ms_e2e_u8 / 1e3), "unit": "samples/s", "ms_per_step": ms_e2e_u8,
                                  "h2d_bytes_per_step": h2d_bytes // 4, "d2h_bytes_per_step": 4},
+            "e2e_decoded_frames": None if ms_e2e_dec is None else {
+                "value": B * world / (ms_e2e_dec / 1e3), "unit": "samples/s", "ms_per_step": ms_e2e_dec,
+                "h2d_bytes_per_step": dec_bytes, "d2h_bytes_per_step": 4,
+                "what": "48 decoded uint8 320x240 frames per sample copied from pinned host memory; Scale((128,171)) "
+                        "bicubic + RandomCrop(112) + ToTensor + Normalize on the GPU (bit-exact with Pillow)"},
             "gpu_launches": int(launches), "roofline": roof, "clocks": sampler.summary(),
             "final_loss": final_loss,
         }

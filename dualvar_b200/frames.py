@@ -27,12 +27,9 @@ def draw_crops(B, n_views, rng=random, scaled=(128, 171), crop=(112, 112)):
     """(B, n_views, 2) int32 (h_start, w_start) pairs in the order A.RandomCrop draws them: one pair per clip,
     ``random.randint(0, h - size0)`` then ``random.randint(0, w - size1)`` with h = img.size[0] = 128 (the PIL width) and
     w = img.size[1] = 171 (utils/augmentation.py:160-166). crop() takes them as (left, upper)."""
-    out = torch.zeros((B, n_views, 2), dtype=torch.int32)
-    for b in range(B):
-        for v in range(n_views):
-            out[b, v, 0] = rng.randint(0, scaled[0] - crop[0])
-            out[b, v, 1] = rng.randint(0, scaled[1] - crop[1])
-    return out
+    hi0, hi1 = scaled[0] - crop[0], scaled[1] - crop[1]
+    vals = [(rng.randint(0, hi0), rng.randint(0, hi1)) for _ in range(B * n_views)]
+    return torch.tensor(vals, dtype=torch.int32).view(B, n_views, 2)
 
 
 def scale_crop(frames, crops, n_views, scale_size=(128, 171), crop_size=(112, 112)):
