@@ -395,3 +395,37 @@ def test_fp32_mode_s3dg_step_matches_oracle():
     if r64 is not None:
         sum(v for k, v in r64.items() if "loss" in k).backward()
     _grad_report("simclr/s3dg", ref, prod, ref64 if r64 is not None else None)
+
+
+def test_fp32_mode_features_give_the_oracles_retrieval_ranking():
+    """Config 5 end to end in the fp32 mode: eval-mode R3D features of 96 'train' and 32 'test' clips from the product
+    and from the oracle, then the top-k ranking of each (classifier.py:963-983): the fp32-mode features are close
+    enough to the oracle's that the retrieved indices agree (top-1 everywhere; deeper ranks except exact near-ties)."""
+    from dualvar_b200 import backbones as PB
+    from dualvar_b200.retrieval import retrieval_topk
+    from oracle import backbones as OB
+    _seed(2)
+    ref, _ = OB.select_backbone("r3d")
+    ref = ref.to(dev).train()
+    with torch.no_grad():
+        for _ in range(2):                      # give the running statistics some content
+            ref(torch.randn(8, 3, 8, 64, 64, device=dev))
+    ref.eval()
+    prod, _ = PB.select_backbone("r3d")
+    prod.load_state_dict(ref.state_dict())
+    prod = prod.to(dev).eval()
+    feats = {}
+    with torch.no_grad():
+        for name, n, seed in (("train", 96, 3), ("test", 32, 4)):
+            x = torch.randn(n, 3, 8, 64, 64, device=dev, generator=torch.Generator(device=dev).manual_seed(seed))
+            fr = torch.cat([ref(x[i:i + 32]).mean((2, 3, 4)) for i in range(0, n, 32)])
+            fp = torch.cat([prod.encode(x[i:i + 32].contiguous(), pooled=True) for i in range(0, n, 32)])
+            print(f"{name} features: max err / range {_relmax(fp, fr):.2e}")
+            assert _relmax(fp, fr) < TOL
+            feats[name] = (fr, fp)
+    _, top_r = retrieval_topk(feats["test"][0], feats["train"][0])
+    _, top_p = retrieval_topk(feats["test"][1], feats["train"][1])
+    assert torch.equal(top_r[1], top_p[1])
+    agree = (top_r[50] == top_p[50]).float().mean().item()
+    print(f"top-50 index agreement {agree:.4f}")
+    assert agree > 0.99

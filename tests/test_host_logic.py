@@ -109,3 +109,46 @@ def test_moco_state_dict_interchanges_with_oracle():
     assert all(torch.equal(sr[k], sp[k]) for k in sr)
     assert not any(p.requires_grad for p in prod.encoder_k.parameters())
     assert sum(p.numel() for p in prod.parameters() if p.requires_grad) == 15021943
+
+
+def test_precision_switch_and_plane_products():
+    """fp32 mode host logic: the switch validates its arguments, and a convolution over K split planes is the sum of
+    the products (i, j) with i + j < K - every term above the 2^-8K truncation, smallest contributions first."""
+    import dualvar_b200
+    from dualvar_b200 import engine as E
+    assert E.PRECISION == "bf16" and not E.fp32_mode()
+    try:
+        dualvar_b200.set_precision("fp32")
+        assert E.fp32_mode() and E.F32_PLANES == 3
+        t3 = E._terms()
+        assert sorted(t3) == [(0, 0), (0, 1), (0, 2), (1, 0), (1, 1), (2, 0)] and t3[-1] == (0, 0)
+        assert all(a[0] + a[1] >= b[0] + b[1] for a, b in zip(t3, t3[1:]))
+        dualvar_b200.set_precision("fp32", planes=2)
+        assert sorted(E._terms()) == [(0, 0), (0, 1), (1, 0)]
+        with pytest.raises(ValueError):
+            dualvar_b200.set_precision("fp16")
+        with pytest.raises(ValueError):
+            dualvar_b200.set_precision("fp32", planes=4)
+    finally:
+        dualvar_b200.set_precision("bf16", planes=3)
+    assert not E.fp32_mode()
+
+
+def test_split_planes_identity_in_numpy():
+    """The split the fp32 mode rests on, restated in numpy: p_k = bf16(x - p_0 - .. - p_(k-1)) has exact residuals,
+    three planes reproduce every normal fp32 value bit for bit, two planes leave at most 2^-16 relative."""
+    import numpy as np
+
+    def bf16(a):
+        u = a.astype(np.float32).view(np.uint32).astype(np.uint64)
+        u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000          # round to nearest even on the top 16 bits
+        return u.astype(np.uint32).view(np.float32)
+
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal(1 << 16) * np.logspace(-3, 3, 1 << 16)).astype(np.float32)
+    p0 = bf16(x); r1 = x - p0
+    p1 = bf16(r1); r2 = r1 - p1
+    p2 = bf16(r2)
+    assert np.array_equal((p0.astype(np.float64) + p1 + p2).astype(np.float32), x)
+    assert np.array_equal(p0 + p1 + p2, x)
+    assert np.all(np.abs((p0.astype(np.float64) + p1) - x) <= np.abs(x) * 2.0 ** -16)
