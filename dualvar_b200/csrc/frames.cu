@@ -3,11 +3,13 @@
 // (utils/augmentation.py:125-176, the null_transform of pretrain.py:491-497; dataset/local_dataset.py:289-300),
 // bit-exact with Pillow's 8-bit resampler (src/libImaging/Resample.c): per output pixel a bicubic window
 // (a = -0.5, support 2 * max(scale, 1)) evaluated in double on the host, normalised, converted to 22-bit fixed point,
-// accumulated in int32 from 1 << 21, shifted and saturated; horizontal pass first through a uint8 intermediate, then the
-// vertical pass - computed only for the cropped window and written in the planar uint8 layout dv_ingest_clips_u8 reads
+// accumulated in int32 from 1 << 21, shifted and saturated; horizontal pass first through a uint8 intermediate (kept as
+// RGBX words so that both passes move aligned 32-bit pixels), then the vertical pass - computed only for the cropped window and written in the planar uint8 layout dv_ingest_clips_u8 reads
 // (ToTensor's x / 255, Normalize and the NDHWC / space-to-depth conversion happen there).
 // Integer byte work, HBM-bound and tiny next to the encoder (1.8 MB of output per 48-frame sample).
 #include <math.h>
+
+#include <algorithm>
 
 #include <map>
 #include <mutex>
@@ -96,10 +98,73 @@ __device__ __forceinline__ uint8_t clip8(int v) {
   return (uint8_t)min(max(v, 0), 255);
 }
 
-// src [rows][Ws][3] -> tmp [rows][out_w][3]; one thread = one output pixel
-__global__ void __launch_bounds__(256) frames_resize_h_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ tmp,
-                                                              const int* __restrict__ tab, int ksize, long long total,
+// Horizontal pass: src [rows][Ws][3] -> tmp [rows][out_w] RGBX words. A block owns output columns (thread = column,
+// its fixed-point taps live in registers for the block's whole life) and walks over rows: the row is staged in shared
+// memory with 4-byte loads, every thread forms its 3 sums from shared bytes, the result leaves as one 32-bit store per
+// thread (coalesced). kTaps bounds the unrolled tap loop (8: up-scaling / mild down-scaling, 12: 320 -> 128, 16: down-scaling
+// by <= 3.5). The shared row has 64 bytes of slack behind it: windows are read as whole words.
+template <int kTaps>
+__global__ void __launch_bounds__(256) frames_resize_h_kernel(const uint8_t* __restrict__ src, uint32_t* __restrict__ tmp,
+                                                              const int* __restrict__ tab, int ksize, long long rows,
                                                               int Ws, int out_w) {
+  extern __shared__ __align__(16) uint8_t s_row[];
+  const int xx = blockIdx.y * blockDim.x + threadIdx.x;
+  const bool live = xx < out_w;
+  int k[kTaps];
+  int xmin = 0, xmax = 0;
+  if (live) {
+    const int* t = tab + (long long)xx * (ksize + 2);
+    xmin = t[0]; xmax = t[1];
+#pragma unroll
+    for (int x = 0; x < kTaps; ++x) k[x] = x < xmax ? t[2 + x] : 0;
+  } else {
+#pragma unroll
+    for (int x = 0; x < kTaps; ++x) k[x] = 0;
+  }
+  const int row_bytes = Ws * 3;
+  const bool words = (row_bytes & 3) == 0;      // rows start 4-byte aligned when the row length is a multiple of 4
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const uint8_t* p = src + row * row_bytes;
+    if (words) {
+      const uint32_t* pw = reinterpret_cast<const uint32_t*>(p);
+      uint32_t* sw = reinterpret_cast<uint32_t*>(s_row);
+      for (int i = threadIdx.x; i < (row_bytes >> 2); i += blockDim.x) sw[i] = pw[i];
+    } else {
+      for (int i = threadIdx.x; i < row_bytes; i += blockDim.x) s_row[i] = p[i];
+    }
+    __syncthreads();
+    if (live) {
+      // the thread's window (3 * kTaps bytes from byte xmin * 3) as aligned words, realigned with funnel shifts: a
+      // quarter of the shared-memory instructions of byte loads (the LSU, not HBM, bounded the byte version)
+      int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
+      constexpr int kWords = (3 * kTaps + 3) / 4;
+      const int boff = xmin * 3;
+      const uint32_t* sw = reinterpret_cast<const uint32_t*>(s_row) + (boff >> 2);
+      const int sh = (boff & 3) * 8;
+      uint32_t w[kWords + 1];
+#pragma unroll
+      for (int i = 0; i <= kWords; ++i) w[i] = sw[i];
+      uint32_t a[kWords];
+#pragma unroll
+      for (int i = 0; i < kWords; ++i) a[i] = __funnelshift_r(w[i], w[i + 1], sh);
+#pragma unroll
+      for (int x = 0; x < kTaps; ++x) {          // taps beyond xmax have k = 0 (their bytes may be the next pixels)
+        const int j = 3 * x;
+        s0 += (int)((a[j >> 2] >> ((j & 3) * 8)) & 0xffu) * k[x];
+        s1 += (int)((a[(j + 1) >> 2] >> (((j + 1) & 3) * 8)) & 0xffu) * k[x];
+        s2 += (int)((a[(j + 2) >> 2] >> (((j + 2) & 3) * 8)) & 0xffu) * k[x];
+      }
+      tmp[row * out_w + xx] = (uint32_t)clip8(s0) | ((uint32_t)clip8(s1) << 8) | ((uint32_t)clip8(s2) << 16);
+    }
+    __syncthreads();
+  }
+}
+
+// generic fallback (any tap count): one thread = one output pixel, taps read from the table
+__global__ void __launch_bounds__(256) frames_resize_h_generic_kernel(const uint8_t* __restrict__ src,
+                                                                      uint32_t* __restrict__ tmp,
+                                                                      const int* __restrict__ tab, int ksize,
+                                                                      long long total, int Ws, int out_w) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int xx = (int)(i % out_w);
@@ -112,37 +177,54 @@ __global__ void __launch_bounds__(256) frames_resize_h_kernel(const uint8_t* __r
       const int k = t[2 + x];
       s0 += p[3 * x] * k; s1 += p[3 * x + 1] * k; s2 += p[3 * x + 2] * k;
     }
-    uint8_t* o = tmp + i * 3;
-    o[0] = clip8(s0); o[1] = clip8(s1); o[2] = clip8(s2);
+    tmp[i] = (uint32_t)clip8(s0) | ((uint32_t)clip8(s1) << 8) | ((uint32_t)clip8(s2) << 16);
   }
 }
 
-// tmp [B*F][Hs][out_w][3] -> out [B][3][F][crop_h][crop_w]: vertical pass of the rows / columns inside each clip's crop
-__global__ void __launch_bounds__(256) frames_resize_v_crop_kernel(const uint8_t* __restrict__ tmp,
+// Vertical pass + crop: tmp [B*F][Hs][out_w] RGBX -> out [B][3][F][crop_h][crop_w]; only the rows / columns inside each
+// clip's crop. One thread = one output pixel: one aligned 32-bit load per tap (coalesced along the row), taps are
+// warp-uniform table reads, three planar byte stores (consecutive threads -> consecutive bytes).
+template <int kTaps>
+__global__ void __launch_bounds__(256) frames_resize_v_crop_kernel(const uint32_t* __restrict__ tmp,
                                                                    uint8_t* __restrict__ out, const int* __restrict__ tab,
                                                                    int ksize, const int* __restrict__ crop_lu, int F,
                                                                    int T, int V, int Hs, int out_w, int out_h, int crop_w,
-                                                                   int crop_h, long long total) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int xx = (int)(i % crop_w);
-    long long r = i / crop_w;
-    const int yy = (int)(r % crop_h); r /= crop_h;
-    const int f = (int)(r % F);
-    const long long b = r / F;
+                                                                   int crop_h, int n_frames) {
+  // blockIdx.x: 256 crop pixels of a frame, blockIdx.y: frame (32-bit index arithmetic only on the per-pixel path).
+  // kTaps > 0: the tap loop is unrolled (all row loads in flight together); kTaps == 0: any tap count.
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  if (p >= crop_w * crop_h) return;
+  const int yy = p / crop_w, xx = p - yy * crop_w;
+  const long long plane = (long long)F * crop_h * crop_w;
+  for (int n = blockIdx.y; n < n_frames; n += gridDim.y) {
+    const int b = n / F, f = n - b * F;
     const int* lu = crop_lu + (b * V + f / T) * 2;
     const int left = min(max(lu[0], 0), out_w - crop_w), upper = min(max(lu[1], 0), out_h - crop_h);
-    const int* t = tab + (long long)(upper + yy) * (ksize + 2);
+    const int* t = tab + (upper + yy) * (ksize + 2);
     const int ymin = t[0], ymax = t[1];
     int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
-    const uint8_t* p = tmp + (((b * F + f) * Hs + ymin) * out_w + left + xx) * 3;
-    const long long rs = (long long)out_w * 3;
-    for (int y = 0; y < ymax; ++y) {
-      const int k = t[2 + y];
-      s0 += p[y * rs] * k; s1 += p[y * rs + 1] * k; s2 += p[y * rs + 2] * k;
+    const uint32_t* q = tmp + ((long long)n * Hs + ymin) * out_w + left + xx;
+    if (kTaps > 0) {
+      uint32_t px[kTaps > 0 ? kTaps : 1];
+      int k[kTaps > 0 ? kTaps : 1];
+#pragma unroll
+      for (int y = 0; y < kTaps; ++y) {
+        px[y] = y < ymax ? q[y * out_w] : 0u;
+        k[y] = y < ymax ? t[2 + y] : 0;
+      }
+#pragma unroll
+      for (int y = 0; y < kTaps; ++y) {
+        s0 += (int)(px[y] & 0xffu) * k[y]; s1 += (int)((px[y] >> 8) & 0xffu) * k[y];
+        s2 += (int)((px[y] >> 16) & 0xffu) * k[y];
+      }
+    } else {
+      for (int y = 0; y < ymax; ++y) {
+        const int k = t[2 + y];
+        const uint32_t px = q[y * out_w];
+        s0 += (int)(px & 0xffu) * k; s1 += (int)((px >> 8) & 0xffu) * k; s2 += (int)((px >> 16) & 0xffu) * k;
+      }
     }
-    const long long plane = (long long)F * crop_h * crop_w;
-    uint8_t* o = out + (b * 3) * plane + ((long long)f * crop_h + yy) * crop_w + xx;
+    uint8_t* o = out + (long long)b * 3 * plane + (long long)f * crop_h * crop_w + p;
     o[0] = clip8(s0); o[plane] = clip8(s1); o[2 * plane] = clip8(s2);
   }
 }
@@ -174,12 +256,32 @@ int frames_scale_crop_u8(const uint8_t* frames, uint8_t* tmp, uint8_t* out, cons
   if (int rc = get_table(Hs, scale_h, &tv)) return rc;
   const int F = V * T;
   const long long rows = (long long)B * F * Hs;
-  frames_resize_h_kernel<<<fgrid(rows * scale_w), 256, 0, stream>>>(frames, tmp, th.ptr, th.ksize, rows * scale_w, Ws,
-                                                                    scale_w);
+  uint32_t* tmp32 = reinterpret_cast<uint32_t*>(tmp);
+  const int smem = round_up(Ws * 3, 16) + 64;     // slack: windows are read as whole words past the last pixel
+  if (th.ksize <= 16 && smem <= 48 * 1024) {
+    const int threads = std::min(256, round_up(scale_w, 32));
+    const int col_blocks = ceil_div(scale_w, threads);
+    long long gx = std::min<long long>(rows, (long long)sm_count() * 16 / col_blocks);
+    if (gx < 1) gx = 1;
+    dim3 grid((unsigned)gx, col_blocks);
+    if (th.ksize <= 8)
+      frames_resize_h_kernel<8><<<grid, threads, smem, stream>>>(frames, tmp32, th.ptr, th.ksize, rows, Ws, scale_w);
+    else if (th.ksize <= 12)
+      frames_resize_h_kernel<12><<<grid, threads, smem, stream>>>(frames, tmp32, th.ptr, th.ksize, rows, Ws, scale_w);
+    else
+      frames_resize_h_kernel<16><<<grid, threads, smem, stream>>>(frames, tmp32, th.ptr, th.ksize, rows, Ws, scale_w);
+  } else {
+    frames_resize_h_generic_kernel<<<fgrid(rows * scale_w), 256, 0, stream>>>(frames, tmp32, th.ptr, th.ksize,
+                                                                              rows * scale_w, Ws, scale_w);
+  }
   DV_LAUNCH_OK();
-  const long long total = (long long)B * F * crop_h * crop_w;
-  frames_resize_v_crop_kernel<<<fgrid(total), 256, 0, stream>>>(tmp, out, tv.ptr, tv.ksize, crop_lu, F, T, V, Hs, scale_w,
-                                                                scale_h, crop_w, crop_h, total);
+  const int n_frames = B * F;
+  dim3 vgrid(ceil_div(crop_w * crop_h, 256), std::min(n_frames, 32768));
+#define DV_VPASS(K)                                                                                             \
+  frames_resize_v_crop_kernel<K><<<vgrid, 256, 0, stream>>>(tmp32, out, tv.ptr, tv.ksize, crop_lu, F, T, V, Hs, \
+                                                            scale_w, scale_h, crop_w, crop_h, n_frames)
+  if (tv.ksize <= 8) DV_VPASS(8); else if (tv.ksize <= 16) DV_VPASS(16); else DV_VPASS(0);
+#undef DV_VPASS
   DV_LAUNCH_OK();
   return kOk;
 }

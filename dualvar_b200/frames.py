@@ -46,7 +46,7 @@ def scale_crop(frames, crops, n_views, scale_size=(128, 171), crop_size=(112, 11
     assert tuple(crops.shape) == (B, n_views, 2)
     sw, sh = scale_size
     cw, ch = crop_size
-    tmp = torch.empty((B * F, Hs, sw, 3), dtype=torch.uint8, device=frames.device)
+    tmp = torch.empty((B * F, Hs, sw, 4), dtype=torch.uint8, device=frames.device)      # RGBX intermediate
     out = torch.empty((B, 3, F, ch, cw), dtype=torch.uint8, device=frames.device)
     call("dv_frames_scale_crop_u8", ptr(frames), ptr(tmp), ptr(out), ptr(crops), B, n_views, F // n_views, Hs, Ws, sw, sh,
          cw, ch, stream_ptr())

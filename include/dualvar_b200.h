@@ -318,7 +318,7 @@ int dv_ingest_clips_planes(const void* src, int src_is_u8, void* dst_planes, int
 /* ---- frame staging (first stage) ---------------------------------------------------
  * A.Scale((128,171)) (PIL bicubic) + A.RandomCrop(112) of the loader's null_transform (utils/augmentation.py:125-176,
  * pretrain.py:491-497), bit-exact with Pillow's 8-bit resampler. frames: uint8 [B][n_views*T][Hs][Ws][3] decoded
- * frames; tmp: uint8 scratch [B*n_views*T][Hs][scale_w][3]; crop_lu: int32 [B][n_views][2] = (left, upper) of each
+ * frames; tmp: uint8 scratch [B*n_views*T][Hs][scale_w][4] (RGBX, 4-byte aligned); crop_lu: int32 [B][n_views][2] = (left, upper) of each
  * clip's crop in the scaled frame (what RandomCrop draws as h_start, w_start); out: uint8 [B][3][n_views*T][crop_h][crop_w],
  * the layout dv_ingest_clips_u8 reads (ToTensor, Normalize and the NDHWC conversion happen there). */
 int dv_frames_scale_crop_u8(const uint8_t* frames, uint8_t* tmp, uint8_t* out, const int32_t* crop_lu, int B, int n_views,

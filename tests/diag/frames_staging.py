@@ -17,7 +17,7 @@ for _ in range(10):
     out = FR.scale_crop(frames, crops, V)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
-rd = frames.numel() + B * V * T * Hs * 128 * 3 * 2      # frames read + intermediate written and (partly) re-read
+rd = frames.numel() + B * V * T * Hs * 128 * 4 + B * V * T * 160 * 112 * 4   # frames read, RGBX intermediate written, ~160 rows x 112 columns of it re-read
 wr = out.numel()
 print(f"GPU scale_crop: {B} samples x {V * T} frames {Ws}x{Hs}: {ms:.3f} ms/batch = {B / ms * 1e3:.0f} samples/s, "
       f"{(rd + wr) / ms / 1e6:.0f} GB/s of byte traffic", flush=True)

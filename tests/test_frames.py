@@ -78,7 +78,8 @@ def test_scale_crop_refuses_cpu_tensors():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("src", [(240, 320), (256, 340), (80, 100), (171, 128), (239, 317), (60, 320)])
+@pytest.mark.parametrize("src", [(240, 320), (256, 340), (80, 100), (171, 128), (239, 317), (60, 320),
+                                 (480, 200), (700, 600)])       # 13-tap vertical windows; > 16 taps: the generic kernels
 def test_gpu_scale_crop_bit_exact(src):
     from PIL import Image
     from dualvar_b200 import frames as FR
