@@ -9,9 +9,9 @@ namespace dv {
 const std::string& last_error_ref();
 
 int conv_fprop_bf16(const void* x, const void* w_packed, void* y, double* stats, const float* bias,
-                    const ConvGeom& c, cudaStream_t stream, bool y_f32_acc = false);
+                    const ConvGeom& c, cudaStream_t stream, int y_f32 = 0);
 int conv_dgrad_bf16(const void* dy, const void* w_packed_t, void* dx, const ConvGeom& c,
-                    cudaStream_t stream, const BnReduce* red, bool dx_f32_acc = false);
+                    cudaStream_t stream, const BnReduce* red, int dx_f32 = 0);
 int conv_wgrad_bf16(const void* x, const void* dy, float* dw, const ConvGeom& c, cudaStream_t stream,
                     bool accumulate = false);
 int pack_weights(const float* w, void* wf, void* wt, int Cout, int Cin, int taps, int Cout_p,
@@ -50,7 +50,7 @@ int ingest(const void* src, int src_u8, void* dst, const int* perm, long long sb
            long long plane_stride = 0);
 int conv_stem_fprop_bf16(const void* x_s2d, const void* w_stem, void* y, double* stats, const float* bias,
                          int N, int T, int H2, int W2, int Cout_p, int kt, int pt, cudaStream_t stream,
-                         bool y_f32_acc = false);
+                         int y_f32 = 0);
 int conv_stem_wgrad_bf16(const void* x_s2d, const void* dy, float* dw, int N, int T, int H2, int W2,
                          int Cout_p, int kt, int pt, cudaStream_t stream, bool accumulate = false);
 int frames_scale_crop_u8(const uint8_t* frames, uint8_t* tmp, uint8_t* out, const int* crop_lu, int B, int V, int T,
@@ -422,15 +422,16 @@ int dv_f32_split_planes(const float* src, float* dst_planes, int64_t n, int n_pl
   return f32_split_planes(src, dst_planes, n, n_planes, ST);
 }
 int dv_conv3d_fprop_f32acc(const void* x_plane, const void* wf_plane, float* y, const float* bias_padded,
-                           const dv_conv_geom* g, void* stream) {
+                           const dv_conv_geom* g, int accumulate, void* stream) {
   if (int rc = check_geom(g)) return rc;
   DV_REQUIRE(x_plane && wf_plane && y, "NULL tensor pointer");
-  return conv_fprop_bf16(x_plane, wf_plane, y, nullptr, bias_padded, to_geom<ConvGeom>(g), ST, true);
+  return conv_fprop_bf16(x_plane, wf_plane, y, nullptr, bias_padded, to_geom<ConvGeom>(g), ST, accumulate ? 1 : 2);
 }
-int dv_conv3d_dgrad_f32acc(const void* dy_plane, const void* wt_plane, float* dx, const dv_conv_geom* g, void* stream) {
+int dv_conv3d_dgrad_f32acc(const void* dy_plane, const void* wt_plane, float* dx, const dv_conv_geom* g, int accumulate,
+                           void* stream) {
   if (int rc = check_geom(g)) return rc;
   DV_REQUIRE(dy_plane && wt_plane && dx, "NULL tensor pointer");
-  return conv_dgrad_bf16(dy_plane, wt_plane, dx, to_geom<ConvGeom>(g), ST, nullptr, true);
+  return conv_dgrad_bf16(dy_plane, wt_plane, dx, to_geom<ConvGeom>(g), ST, nullptr, accumulate ? 1 : 2);
 }
 int dv_conv3d_wgrad_bf16_acc(const void* x_plane, const void* dy_plane, float* dw_packed, const dv_conv_geom* g,
                              void* stream) {
@@ -439,11 +440,11 @@ int dv_conv3d_wgrad_bf16_acc(const void* x_plane, const void* dy_plane, float* d
   return conv_wgrad_bf16(x_plane, dy_plane, dw_packed, to_geom<ConvGeom>(g), ST, true);
 }
 int dv_conv3d_stem_fprop_f32acc(const void* x_s2d_plane, const void* ws_plane, float* y, const float* bias_padded,
-                                const dv_conv_geom* g, void* stream) {
+                                const dv_conv_geom* g, int accumulate, void* stream) {
   if (int rc = check_stem(g)) return rc;
   DV_REQUIRE(x_s2d_plane && ws_plane && y, "NULL tensor pointer");
   return conv_stem_fprop_bf16(x_s2d_plane, ws_plane, y, nullptr, bias_padded, g->N, g->T, g->H / 2, g->W / 2, g->Cout_p,
-                              g->kt, g->pt, ST, true);
+                              g->kt, g->pt, ST, accumulate ? 1 : 2);
 }
 int dv_conv3d_stem_wgrad_bf16_acc(const void* x_s2d_plane, const void* dy_plane, float* dws, const dv_conv_geom* g,
                                   void* stream) {

@@ -371,11 +371,19 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
           if (valid) {
             float* dst = p.out_f32 + (long long)(w0 + rw) * p.red_stride[0] + (long long)(h0 + rh) * p.red_stride[1] +
                          (long long)(t0 + rt) * p.red_stride[2] + (long long)(n0 + rn) * p.red_stride[3] + bcol + cc * 64;
+            if (p.f32_store) {     // first product of the sum: overwrite (no zero fill, no read-modify-write)
 #pragma unroll
-            for (int j = 0; j < 64; j += 4)
-              if (j < ncols && bcol + cc * 64 + j < p.stats_ld)
-                red_add_v4_f32(dst + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                               __uint_as_float(v[j + 3]));
+              for (int j = 0; j < 64; j += 4)
+                if (j < ncols && bcol + cc * 64 + j < p.stats_ld)
+                  st_global_v4_f32(dst + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                   __uint_as_float(v[j + 3]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 64; j += 4)
+                if (j < ncols && bcol + cc * 64 + j < p.stats_ld)
+                  red_add_v4_f32(dst + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                 __uint_as_float(v[j + 3]));
+            }
           }
           continue;
         }
@@ -516,12 +524,14 @@ struct View5 {
   long long dim[5];
   long long stride[5];
   int esize;   // element bytes: 2 (bf16) or 4 (fp32 output of the fp32 mode)
+  int store;   // fp32 output: 1 = overwrite, 0 = add
 };
 
 static View5 make_ndhwc(const void* ptr, int N, int T, int H, int W, int Cp) {
   View5 v;
   v.base = ptr;
   v.esize = 2;
+  v.store = 0;
   v.dim[0] = Cp; v.dim[1] = W; v.dim[2] = H; v.dim[3] = T; v.dim[4] = N;
   v.stride[0] = 1;
   v.stride[1] = Cp;
@@ -769,6 +779,7 @@ static int conv_multi_tap_region(ConvTileParams& P, MapEncoder enc, const void* 
   P.red_ss = nullptr;
   for (int i = 0; i < 4; ++i) P.red_stride[i] = outv.stride[i + 1];
   P.out_f32 = outv.esize == 4 ? static_cast<float*>(const_cast<void*>(outv.base)) : nullptr;
+  P.f32_store = outv.store;
   if (P.out_f32 != nullptr && (stats != nullptr || red != nullptr))
     return fail(kBadArg, "fp32 accumulate output has no fused statistics");
   if (red != nullptr) {
@@ -878,11 +889,11 @@ static int encode_from_viewset(CUtensorMap* m, const void* ctx, int view, const 
 }
 
 int conv_fprop_bf16(const void* x, const void* w_packed, void* y, double* stats, const float* bias,
-                    const ConvGeom& c, cudaStream_t stream, bool y_f32_acc) {
+                    const ConvGeom& c, cudaStream_t stream, int y_f32) {
   static thread_local ConvTileParams P;
   const View5 inv = make_ndhwc(x, c.N, c.T, c.H, c.W, c.Cin_p);
   View5 outv = make_ndhwc(y, c.N, c.To, c.Ho, c.Wo, c.Cout_p);
-  if (y_f32_acc) outv.esize = 4;   // y is float [N][To][Ho][Wo][Cout_p], the result is added to it
+  if (y_f32) { outv.esize = 4; outv.store = y_f32 == 2; }   // y is float [N][To][Ho][Wo][Cout_p]: 1 = added to, 2 = overwritten
   ViewSet vs;
   int map_of_parity[8];
   for (int i = 0; i < 8; ++i) map_of_parity[i] = -1;
@@ -915,12 +926,12 @@ int conv_fprop_bf16(const void* x, const void* w_packed, void* y, double* stats,
 // stride-1 multi-tap GEMM over dY with the subset of taps that reach it.
 // w_packed_t: [Cin_p][taps][Cout_p] bf16 (transposed pack).
 int conv_dgrad_bf16(const void* dy, const void* w_packed_t, void* dx, const ConvGeom& c,
-                    cudaStream_t stream, const BnReduce* red, bool dx_f32_acc) {
+                    cudaStream_t stream, const BnReduce* red, int dx_f32) {
   static thread_local ConvTileParams P;
   ViewSet vs;
   vs.v[0] = make_ndhwc(dy, c.N, c.To, c.Ho, c.Wo, c.Cout_p);
   View5 dxv = make_ndhwc(dx, c.N, c.T, c.H, c.W, c.Cin_p);
-  if (dx_f32_acc) dxv.esize = 4;   // dx is float [N][T][H][W][Cin_p], zeroed by the caller; the result is added
+  if (dx_f32) { dxv.esize = 4; dxv.store = dx_f32 == 2; }   // dx is float [N][T][H][W][Cin_p]: 1 = added to, 2 = overwritten
   bool need_zero = false;
   for (int rt = 0; rt < c.st; ++rt)
     for (int rh = 0; rh < c.sh; ++rh)
@@ -931,8 +942,9 @@ int conv_dgrad_bf16(const void* dy, const void* w_packed_t, void* dx, const Conv
             for (int d = 0; d < c.kw; ++d) if (posmod(rw + c.pw - d, c.sw) == 0) ++cnt;
         if (cnt == 0) need_zero = true;
       }
-  if (need_zero && !dx_f32_acc)
-    DV_CUDA_OK(cudaMemsetAsync(dx, 0, (size_t)c.N * c.T * c.H * c.W * c.Cin_p * 2, stream));
+  // positions no tap reaches (e.g. 1x1 stride-2 convs) receive no tile: zero them (not in add mode: the caller did)
+  if (need_zero && dx_f32 != 1)
+    DV_CUDA_OK(cudaMemsetAsync(dx, 0, (size_t)c.N * c.T * c.H * c.W * c.Cin_p * (dx_f32 ? 4 : 2), stream));
   for (int rt = 0; rt < c.st; ++rt)
     for (int rh = 0; rh < c.sh; ++rh)
       for (int rw = 0; rw < c.sw; ++rw) {
@@ -990,11 +1002,11 @@ static int encode_stem_map(CUtensorMap* m, const void* ctx, int /*view*/, const 
 
 int conv_stem_fprop_bf16(const void* x_s2d, const void* w_stem, void* y, double* stats, const float* bias,
                          int N, int T, int H2, int W2, int Cout_p, int kt, int pt, cudaStream_t stream,
-                         bool y_f32_acc) {
+                         int y_f32) {
   static thread_local ConvTileParams P;
   const int To = T + 2 * pt - kt + 1;
   View5 outv = make_ndhwc(y, N, To, H2, W2, Cout_p);
-  if (y_f32_acc) outv.esize = 4;
+  if (y_f32) { outv.esize = 4; outv.store = y_f32 == 2; }
   StemCtx sc = {x_s2d, N, T, H2, W2};
   std::vector<TapSpec> taps;
   for (int a = 0; a < kt; ++a)

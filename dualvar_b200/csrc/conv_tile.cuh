@@ -71,6 +71,7 @@ struct alignas(64) ConvTileParams {
   // bf16 split planes of the operands (x = x0 + x1 + x2, w = w0 + w1 + w2) then sum to an fp32-accurate result.
   // out_map, the staging buffers and the BatchNorm statistics are unused in this mode.
   float* out_f32;
+  int f32_store;   // 1: the first product of a sum overwrites the destination (plain 16-byte stores), 0: adds to it
 };
 
 // Optional fused BatchNorm-backward reduction request for conv_dgrad_bf16 (see ConvTileParams::red_y).

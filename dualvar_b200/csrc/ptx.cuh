@@ -321,6 +321,10 @@ __device__ __forceinline__ void red_add_v4_f32(float* p, float a, float b, float
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+__device__ __forceinline__ void st_global_v4_f32(float* p, float a, float b, float c, float d) {
+  asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 __device__ __forceinline__ uint32_t ldg_u32_pred(const void* ptr, bool ok) {
   uint32_t v;
   asm volatile(

@@ -422,12 +422,12 @@ def conv_stats(ctx, x, conv, bn):
         assert g.Cin_p == Cin_p, (g.Cin_p, Cin_p)
     if fp32_mode():
         # y (fp32) = sum of the plane products; the batch statistics are a separate pass over the finished sum
-        y = torch.zeros((N, g.To, g.Ho, g.Wo, g.Cout_p), dtype=torch.float32, device=dev)
+        y = torch.empty((N, g.To, g.Ho, g.Wo, g.Cout_p), dtype=torch.float32, device=dev)
         packed = packed_stem_weight_planes(conv, g) if stem else packed_weight_planes(conv)
         bias = _bias_padded(conv, g.Cout_p)
-        for n, (i, j) in enumerate(_terms()):
+        for n, (i, j) in enumerate(_terms()):      # the first product overwrites y, the others add to it
             call("dv_conv3d_stem_fprop_f32acc" if stem else "dv_conv3d_fprop_f32acc", ptr(x.planes[i]),
-                 ptr(packed[j][0]), ptr(y), ptr(bias) if n == 0 else None, ctypes.byref(g), stream_ptr())
+                 ptr(packed[j][0]), ptr(y), ptr(bias) if n == 0 else None, ctypes.byref(g), 1 if n else 0, stream_ptr())
         if training_stats:
             call("dv_f32_colstats", ptr(y), ptr(stats), y.numel() // g.Cout_p, g.Cout_p, stream_ptr())
     elif stem:
@@ -545,9 +545,10 @@ def _conv_backward_f32(ctx, r, dyp):
     if r.conv.bias is not None:
         ctx.add_param_grad(r.conv.bias, torch.zeros_like(r.conv.bias))
     if r.x.needs_grad:
-        dx = torch.zeros(r.x.shape5, dtype=torch.float32, device=dyp.device)
-        for i, j in terms:
-            call("dv_conv3d_dgrad_f32acc", ptr(dyp[i]), ptr(r.packed[j][1]), ptr(dx), ctypes.byref(g), stream_ptr())
+        dx = torch.empty(r.x.shape5, dtype=torch.float32, device=dyp.device)
+        for n, (i, j) in enumerate(terms):
+            call("dv_conv3d_dgrad_f32acc", ptr(dyp[i]), ptr(r.packed[j][1]), ptr(dx), ctypes.byref(g), 1 if n else 0,
+                 stream_ptr())
         _acc_grad(r.x, dx)
 
 

@@ -256,22 +256,25 @@ int dv_debug_mma_rate(int n, int n_mma, int region_bytes, int mode, int64_t* cyc
  * bf16 SPLIT PLANES, x = p0 + p1 + p2 with p_k = bf16(x - p0 - .. - p(k-1)), plane k at base + k*plane_stride
  * elements. A convolution is the sum over i + j < n_planes of bf16 products (x plane i) * (w plane j), each ONE call
  * of an *_f32acc / *_acc entry point below: the tcgen05 kernels of the bf16 mode, whose epilogue ADDS the fp32
- * accumulator tile to the fp32 destination instead of rounding it to bf16 (the caller zeroes the destination).
+ * accumulator tile to the fp32 destination (or, for the first product, stores it there) instead of rounding it to bf16.
  * Replaces the same reference calls as the bf16 entry points, for the fp32 (TF32-off) reference path. */
 /* fp32 values -> n_planes fp32 tensors [n_planes][n] holding the bf16-representable parts (feed each plane to
  * dv_pack_conv_weight / dv_pack_stem_weight, which then rounds exactly) */
 int dv_f32_split_planes(const float* src, float* dst_planes, int64_t n, int n_planes, void* stream);
-/* y += conv(x_plane, w_plane) (+ bias); y fp32 [N][To][Ho][Wo][Cout_p] */
+/* y (+)= conv(x_plane, w_plane) (+ bias); y fp32 [N][To][Ho][Wo][Cout_p]. accumulate = 0: the first product of a sum,
+ * y is overwritten (no zero fill needed); accumulate = 1: added to y */
 int dv_conv3d_fprop_f32acc(const void* x_plane, const void* wf_plane, float* y, const float* bias_padded,
-                           const dv_conv_geom* g, void* stream);
-/* dx += conv_transpose(dy_plane, w_plane); dx fp32 [N][T][H][W][Cin_p] */
-int dv_conv3d_dgrad_f32acc(const void* dy_plane, const void* wt_plane, float* dx, const dv_conv_geom* g, void* stream);
+                           const dv_conv_geom* g, int accumulate, void* stream);
+/* dx (+)= conv_transpose(dy_plane, w_plane); dx fp32 [N][T][H][W][Cin_p]; accumulate as above (positions that no tap
+ * reaches are zeroed by the accumulate = 0 call) */
+int dv_conv3d_dgrad_f32acc(const void* dy_plane, const void* wt_plane, float* dx, const dv_conv_geom* g, int accumulate,
+                           void* stream);
 /* dw_packed += correlation(x_plane, dy_plane) (dv_conv3d_wgrad_bf16 without the zero fill) */
 int dv_conv3d_wgrad_bf16_acc(const void* x_plane, const void* dy_plane, float* dw_packed, const dv_conv_geom* g,
                              void* stream);
 /* the stride-2 7x7 stem on space-to-depth planes (dv_conv3d_stem_fprop_bf16 / _wgrad_bf16), accumulating */
 int dv_conv3d_stem_fprop_f32acc(const void* x_s2d_plane, const void* ws_plane, float* y, const float* bias_padded,
-                                const dv_conv_geom* g, void* stream);
+                                const dv_conv_geom* g, int accumulate, void* stream);
 int dv_conv3d_stem_wgrad_bf16_acc(const void* x_s2d_plane, const void* dy_plane, float* dws, const dv_conv_geom* g,
                                   void* stream);
 /* BatchNorm batch statistics of an fp32 conv output: adds per-channel sum / sum of squares (double, caller zeroes)

@@ -103,10 +103,10 @@ def test_conv_trio_fp32_mode_matches_fp64(case, K, tol):
     wp = E.packed_weight_planes(conv)
     bias_p = torch.zeros(g.Cout_p, device=dev)
     bias_p[:Cout] = bias
-    y = torch.zeros((N, g.To, g.Ho, g.Wo, g.Cout_p), dtype=torch.float32, device=dev)
+    y = torch.full((N, g.To, g.Ho, g.Wo, g.Cout_p), float("nan"), dtype=torch.float32, device=dev)   # the first product overwrites
     for n, (i, j) in enumerate(E._terms()):
         call("dv_conv3d_fprop_f32acc", ptr(xp[i]), ptr(wp[j][0]), ptr(y), ptr(bias_p) if n == 0 else None,
-             ctypes.byref(g), st())
+             ctypes.byref(g), 1 if n else 0, st())
     assert _relmax(y[..., :Cout].permute(0, 4, 1, 2, 3), yr.detach()) < tol
     if g.Cout_p > Cout:
         assert bool((y[..., Cout:] == 0).all())
@@ -118,9 +118,9 @@ def test_conv_trio_fp32_mode_matches_fp64(case, K, tol):
     torch.testing.assert_close(stats[g.Cout_p:], (ys * ys).sum(0), rtol=1e-9, atol=1e-6)
 
     dyp = _planes(_to_ndhwc_f32(dy, g.Cout_p), K)
-    dx = torch.zeros((N, T, H, W, g.Cin_p), dtype=torch.float32, device=dev)
-    for i, j in E._terms():
-        call("dv_conv3d_dgrad_f32acc", ptr(dyp[i]), ptr(wp[j][1]), ptr(dx), ctypes.byref(g), st())
+    dx = torch.full((N, T, H, W, g.Cin_p), float("nan"), dtype=torch.float32, device=dev)
+    for n, (i, j) in enumerate(E._terms()):
+        call("dv_conv3d_dgrad_f32acc", ptr(dyp[i]), ptr(wp[j][1]), ptr(dx), ctypes.byref(g), 1 if n else 0, st())
     assert _relmax(dx[..., :Cin].permute(0, 4, 1, 2, 3), xr.grad) < tol
     dwp = torch.empty((g.Cout_p, g.taps, g.Cin_p), dtype=torch.float32, device=dev)
     for n, (i, j) in enumerate(E._terms()):
