@@ -138,41 +138,61 @@ __global__ void __launch_bounds__(256) frames_resize_h_kernel(const uint8_t* __r
 #pragma unroll
     for (int x = 0; x < kTaps; ++x) k[x] = 0;
   }
+  // kRowsPerIter consecutive rows (one contiguous chunk of the source) are staged per iteration: with one row per
+  // iteration the kernel was bound by the latency of its own row load (too few bytes in flight per SM), not by HBM
+  constexpr int kRowsPerIter = 4;
   const int row_bytes = Ws * 3;
+  const int row_stride = (row_bytes + 64 + 15) & ~15;     // shared-memory row pitch (slack for whole-word windows)
   const bool words = (row_bytes & 3) == 0;      // rows start 4-byte aligned when the row length is a multiple of 4
-  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
-    if (!rf.needed((int)row)) continue;       // block-uniform: rows outside the clip's vertical windows are never read
-    const uint8_t* p = src + row * row_bytes;
-    if (words) {
-      const uint32_t* pw = reinterpret_cast<const uint32_t*>(p);
-      uint32_t* sw = reinterpret_cast<uint32_t*>(s_row);
-      for (int i = threadIdx.x; i < (row_bytes >> 2); i += blockDim.x) sw[i] = pw[i];
-    } else {
-      for (int i = threadIdx.x; i < row_bytes; i += blockDim.x) s_row[i] = p[i];
+  const long long groups = (rows + kRowsPerIter - 1) / kRowsPerIter;
+  for (long long grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+    const long long row0 = grp * kRowsPerIter;
+    const int nr = (int)min((long long)kRowsPerIter, rows - row0);
+    unsigned need = 0;                                       // block-uniform bit per row
+#pragma unroll
+    for (int r = 0; r < kRowsPerIter; ++r)
+      if (r < nr && rf.needed((int)(row0 + r))) need |= 1u << r;
+    if (need == 0) continue;
+#pragma unroll
+    for (int r = 0; r < kRowsPerIter; ++r) {
+      if (!((need >> r) & 1u)) continue;
+      const uint8_t* p = src + (row0 + r) * row_bytes;
+      uint8_t* d = s_row + r * row_stride;
+      if (words) {
+        const uint32_t* pw = reinterpret_cast<const uint32_t*>(p);
+        uint32_t* sw = reinterpret_cast<uint32_t*>(d);
+        for (int i = threadIdx.x; i < (row_bytes >> 2); i += blockDim.x) sw[i] = pw[i];
+      } else {
+        for (int i = threadIdx.x; i < row_bytes; i += blockDim.x) d[i] = p[i];
+      }
     }
     __syncthreads();
     if (live) {
-      // the thread's window (3 * kTaps bytes from byte xmin * 3) as aligned words, realigned with funnel shifts: a
-      // quarter of the shared-memory instructions of byte loads (the LSU, not HBM, bounded the byte version)
-      int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
-      constexpr int kWords = (3 * kTaps + 3) / 4;
-      const int boff = xmin * 3;
-      const uint32_t* sw = reinterpret_cast<const uint32_t*>(s_row) + (boff >> 2);
-      const int sh = (boff & 3) * 8;
-      uint32_t w[kWords + 1];
+#pragma unroll 1
+      for (int r = 0; r < kRowsPerIter; ++r) {
+        if (!((need >> r) & 1u)) continue;
+        // the thread's window (3 * kTaps bytes from byte xmin * 3) as aligned words, realigned with funnel shifts: a
+        // quarter of the shared-memory instructions of byte loads
+        int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
+        constexpr int kWords = (3 * kTaps + 3) / 4;
+        const int boff = xmin * 3;
+        const uint32_t* sw = reinterpret_cast<const uint32_t*>(s_row + r * row_stride) + (boff >> 2);
+        const int sh = (boff & 3) * 8;
+        uint32_t w[kWords + 1];
 #pragma unroll
-      for (int i = 0; i <= kWords; ++i) w[i] = sw[i];
-      uint32_t a[kWords];
+        for (int i = 0; i <= kWords; ++i) w[i] = sw[i];
+        uint32_t a[kWords];
 #pragma unroll
-      for (int i = 0; i < kWords; ++i) a[i] = __funnelshift_r(w[i], w[i + 1], sh);
+        for (int i = 0; i < kWords; ++i) a[i] = __funnelshift_r(w[i], w[i + 1], sh);
 #pragma unroll
-      for (int x = 0; x < kTaps; ++x) {          // taps beyond xmax have k = 0 (their bytes may be the next pixels)
-        const int j = 3 * x;
-        s0 += (int)((a[j >> 2] >> ((j & 3) * 8)) & 0xffu) * k[x];
-        s1 += (int)((a[(j + 1) >> 2] >> (((j + 1) & 3) * 8)) & 0xffu) * k[x];
-        s2 += (int)((a[(j + 2) >> 2] >> (((j + 2) & 3) * 8)) & 0xffu) * k[x];
+        for (int x = 0; x < kTaps; ++x) {          // taps beyond xmax have k = 0 (their bytes may be the next pixels)
+          const int j = 3 * x;
+          s0 += (int)((a[j >> 2] >> ((j & 3) * 8)) & 0xffu) * k[x];
+          s1 += (int)((a[(j + 1) >> 2] >> (((j + 1) & 3) * 8)) & 0xffu) * k[x];
+          s2 += (int)((a[(j + 2) >> 2] >> (((j + 2) & 3) * 8)) & 0xffu) * k[x];
+        }
+        tmp[(row0 + r) * out_w + xx] = (uint32_t)clip8(s0) | ((uint32_t)clip8(s1) << 8) | ((uint32_t)clip8(s2) << 16);
       }
-      tmp[row * out_w + xx] = (uint32_t)clip8(s0) | ((uint32_t)clip8(s1) << 8) | ((uint32_t)clip8(s2) << 16);
     }
     __syncthreads();
   }
@@ -275,11 +295,11 @@ int frames_scale_crop_u8(const uint8_t* frames, uint8_t* tmp, uint8_t* out, cons
   const int F = V * T;
   const long long rows = (long long)B * F * Hs;
   uint32_t* tmp32 = reinterpret_cast<uint32_t*>(tmp);
-  const int smem = round_up(Ws * 3, 16) + 64;     // slack: windows are read as whole words past the last pixel
+  const int smem = 4 * ((Ws * 3 + 64 + 15) & ~15);     // 4 rows per iteration, each with slack for whole-word windows
   if (th.ksize <= 16 && smem <= 48 * 1024) {
     const int threads = std::min(256, round_up(scale_w, 32));
     const int col_blocks = ceil_div(scale_w, threads);
-    long long gx = std::min<long long>(rows, (long long)sm_count() * 16 / col_blocks);
+    long long gx = std::min<long long>(ceil_div_ll(rows, 4), (long long)sm_count() * 16 / col_blocks);
     if (gx < 1) gx = 1;
     dim3 grid((unsigned)gx, col_blocks);
     RowFilter rf;
