@@ -104,6 +104,15 @@ struct RowFilter {
   const int* tabv;      // vertical table (NULL: every row is needed)
   const int* crop_lu;
   int ksize_v, Hs, F, T, V, out_h, crop_h;
+  // [lo, hi) of frame n (block-uniform: evaluated once per frame, not per row)
+  __device__ __forceinline__ void range(int n, int* lo, int* hi) const {
+    if (tabv == nullptr) { *lo = 0; *hi = Hs; return; }
+    const int b = n / F, f = n - b * F;
+    const int upper = min(max(crop_lu[(b * V + f / T) * 2 + 1], 0), out_h - crop_h);
+    *lo = tabv[upper * (ksize_v + 2)];
+    const int* last = tabv + (upper + crop_h - 1) * (ksize_v + 2);
+    *hi = last[0] + last[1];
+  }
   __device__ __forceinline__ bool needed(int row) const {
     if (tabv == nullptr) return true;
     const int n = row / Hs, y = row - n * Hs;
@@ -122,10 +131,12 @@ struct RowFilter {
 // by <= 3.5). The shared row has 64 bytes of slack behind it: windows are read as whole words.
 template <int kTaps>
 __global__ void __launch_bounds__(256) frames_resize_h_kernel(const uint8_t* __restrict__ src, uint32_t* __restrict__ tmp,
-                                                              const int* __restrict__ tab, int ksize, long long rows,
+                                                              const int* __restrict__ tab, int ksize, int n_frames,
                                                               int Ws, int out_w, const RowFilter rf) {
+  // grid: x = row slices of a frame, y = frames, z = 256-column blocks. All index arithmetic that is not per pixel is
+  // block-uniform and done once per frame (the first version spent two thirds of its instructions on it).
   extern __shared__ __align__(16) uint8_t s_row[];
-  const int xx = blockIdx.y * blockDim.x + threadIdx.x;
+  const int xx = blockIdx.z * blockDim.x + threadIdx.x;
   const bool live = xx < out_w;
   int k[kTaps];
   int xmin = 0, xmax = 0;
@@ -138,63 +149,59 @@ __global__ void __launch_bounds__(256) frames_resize_h_kernel(const uint8_t* __r
 #pragma unroll
     for (int x = 0; x < kTaps; ++x) k[x] = 0;
   }
-  // kRowsPerIter consecutive rows (one contiguous chunk of the source) are staged per iteration: with one row per
-  // iteration the kernel was bound by the latency of its own row load (too few bytes in flight per SM), not by HBM
+  // kRowsPerIter consecutive rows are staged per iteration (more bytes in flight per block)
   constexpr int kRowsPerIter = 4;
+  constexpr int kWords = (3 * kTaps + 3) / 4;
   const int row_bytes = Ws * 3;
   const int row_stride = (row_bytes + 64 + 15) & ~15;     // shared-memory row pitch (slack for whole-word windows)
   const bool words = (row_bytes & 3) == 0;      // rows start 4-byte aligned when the row length is a multiple of 4
-  const long long groups = (rows + kRowsPerIter - 1) / kRowsPerIter;
-  for (long long grp = blockIdx.x; grp < groups; grp += gridDim.x) {
-    const long long row0 = grp * kRowsPerIter;
-    const int nr = (int)min((long long)kRowsPerIter, rows - row0);
-    unsigned need = 0;                                       // block-uniform bit per row
+  const int boff = xmin * 3;
+  const int w_off = boff >> 2, sh = (boff & 3) * 8;
+  for (int n = blockIdx.y; n < n_frames; n += gridDim.y) {
+    int lo, hi;
+    rf.range(n, &lo, &hi);
+    const uint8_t* fsrc = src + (long long)n * rf.Hs * row_bytes;
+    uint32_t* fdst = tmp + (long long)n * rf.Hs * out_w;
+    for (int y0 = lo + kRowsPerIter * blockIdx.x; y0 < hi; y0 += kRowsPerIter * gridDim.x) {
+      const int nr = min(kRowsPerIter, hi - y0);
 #pragma unroll
-    for (int r = 0; r < kRowsPerIter; ++r)
-      if (r < nr && rf.needed((int)(row0 + r))) need |= 1u << r;
-    if (need == 0) continue;
-#pragma unroll
-    for (int r = 0; r < kRowsPerIter; ++r) {
-      if (!((need >> r) & 1u)) continue;
-      const uint8_t* p = src + (row0 + r) * row_bytes;
-      uint8_t* d = s_row + r * row_stride;
-      if (words) {
-        const uint32_t* pw = reinterpret_cast<const uint32_t*>(p);
-        uint32_t* sw = reinterpret_cast<uint32_t*>(d);
-        for (int i = threadIdx.x; i < (row_bytes >> 2); i += blockDim.x) sw[i] = pw[i];
-      } else {
-        for (int i = threadIdx.x; i < row_bytes; i += blockDim.x) d[i] = p[i];
-      }
-    }
-    __syncthreads();
-    if (live) {
-#pragma unroll 1
       for (int r = 0; r < kRowsPerIter; ++r) {
-        if (!((need >> r) & 1u)) continue;
-        // the thread's window (3 * kTaps bytes from byte xmin * 3) as aligned words, realigned with funnel shifts: a
-        // quarter of the shared-memory instructions of byte loads
-        int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
-        constexpr int kWords = (3 * kTaps + 3) / 4;
-        const int boff = xmin * 3;
-        const uint32_t* sw = reinterpret_cast<const uint32_t*>(s_row + r * row_stride) + (boff >> 2);
-        const int sh = (boff & 3) * 8;
-        uint32_t w[kWords + 1];
-#pragma unroll
-        for (int i = 0; i <= kWords; ++i) w[i] = sw[i];
-        uint32_t a[kWords];
-#pragma unroll
-        for (int i = 0; i < kWords; ++i) a[i] = __funnelshift_r(w[i], w[i + 1], sh);
-#pragma unroll
-        for (int x = 0; x < kTaps; ++x) {          // taps beyond xmax have k = 0 (their bytes may be the next pixels)
-          const int j = 3 * x;
-          s0 += (int)((a[j >> 2] >> ((j & 3) * 8)) & 0xffu) * k[x];
-          s1 += (int)((a[(j + 1) >> 2] >> (((j + 1) & 3) * 8)) & 0xffu) * k[x];
-          s2 += (int)((a[(j + 2) >> 2] >> (((j + 2) & 3) * 8)) & 0xffu) * k[x];
+        if (r >= nr) break;
+        const uint8_t* p = fsrc + (long long)(y0 + r) * row_bytes;
+        uint8_t* d = s_row + r * row_stride;
+        if (words) {
+          const uint32_t* pw = reinterpret_cast<const uint32_t*>(p);
+          uint32_t* sw = reinterpret_cast<uint32_t*>(d);
+          for (int i = threadIdx.x; i < (row_bytes >> 2); i += blockDim.x) sw[i] = pw[i];
+        } else {
+          for (int i = threadIdx.x; i < row_bytes; i += blockDim.x) d[i] = p[i];
         }
-        tmp[(row0 + r) * out_w + xx] = (uint32_t)clip8(s0) | ((uint32_t)clip8(s1) << 8) | ((uint32_t)clip8(s2) << 16);
       }
+      __syncthreads();
+      if (live) {
+#pragma unroll 1
+        for (int r = 0; r < nr; ++r) {
+          // the thread's window (3 * kTaps bytes from byte xmin * 3) as aligned words, realigned with funnel shifts
+          int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
+          const uint32_t* sw = reinterpret_cast<const uint32_t*>(s_row + r * row_stride) + w_off;
+          uint32_t w[kWords + 1];
+#pragma unroll
+          for (int i = 0; i <= kWords; ++i) w[i] = sw[i];
+          uint32_t a[kWords];
+#pragma unroll
+          for (int i = 0; i < kWords; ++i) a[i] = __funnelshift_r(w[i], w[i + 1], sh);
+#pragma unroll
+          for (int x = 0; x < kTaps; ++x) {          // taps beyond xmax have k = 0 (their bytes may be the next pixels)
+            const int j = 3 * x;
+            s0 += (int)__byte_perm(a[j >> 2], 0, 0x4440 + (j & 3)) * k[x];
+            s1 += (int)__byte_perm(a[(j + 1) >> 2], 0, 0x4440 + ((j + 1) & 3)) * k[x];
+            s2 += (int)__byte_perm(a[(j + 2) >> 2], 0, 0x4440 + ((j + 2) & 3)) * k[x];
+          }
+          fdst[(y0 + r) * out_w + xx] = (uint32_t)clip8(s0) | ((uint32_t)clip8(s1) << 8) | ((uint32_t)clip8(s2) << 16);
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
 }
 
@@ -228,42 +235,45 @@ __global__ void __launch_bounds__(256) frames_resize_v_crop_kernel(const uint32_
                                                                    int ksize, const int* __restrict__ crop_lu, int F,
                                                                    int T, int V, int Hs, int out_w, int out_h, int crop_w,
                                                                    int crop_h, int n_frames) {
-  // blockIdx.x: 256 crop pixels of a frame, blockIdx.y: frame (32-bit index arithmetic only on the per-pixel path).
-  // kTaps > 0: the tap loop is unrolled (all row loads in flight together); kTaps == 0: any tap count.
-  const int p = blockIdx.x * 256 + threadIdx.x;
-  if (p >= crop_w * crop_h) return;
-  const int yy = p / crop_w, xx = p - yy * crop_w;
+  // grid: x = groups of kRowsPerBlock crop rows, y = frames, z = 256-column blocks; thread = crop column. Everything
+  // but the pixel loads and multiply-adds is block-uniform (frame decomposition, crop origin, the row's taps).
+  // kTaps > 0: the tap loop is unrolled (all row loads of a pixel in flight together); kTaps == 0: any tap count.
+  constexpr int kRowsPerBlock = 8;
+  const int xx = blockIdx.z * blockDim.x + threadIdx.x;
+  if (xx >= crop_w) return;
   const long long plane = (long long)F * crop_h * crop_w;
   for (int n = blockIdx.y; n < n_frames; n += gridDim.y) {
     const int b = n / F, f = n - b * F;
     const int* lu = crop_lu + (b * V + f / T) * 2;
     const int left = min(max(lu[0], 0), out_w - crop_w), upper = min(max(lu[1], 0), out_h - crop_h);
-    const int* t = tab + (upper + yy) * (ksize + 2);
-    const int ymin = t[0], ymax = t[1];
-    int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
-    const uint32_t* q = tmp + ((long long)n * Hs + ymin) * out_w + left + xx;
-    if (kTaps > 0) {
-      uint32_t px[kTaps > 0 ? kTaps : 1];
-      int k[kTaps > 0 ? kTaps : 1];
+    const uint32_t* fsrc = tmp + (long long)n * Hs * out_w + left + xx;
+    uint8_t* fdst = out + (long long)b * 3 * plane + (long long)f * crop_h * crop_w + xx;
+    const int y_end = min(crop_h, (int)(blockIdx.x + 1) * kRowsPerBlock);
+    for (int yy = blockIdx.x * kRowsPerBlock; yy < y_end; ++yy) {
+      const int* t = tab + (upper + yy) * (ksize + 2);
+      const int ymin = t[0], ymax = t[1];
+      int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
+      const uint32_t* q = fsrc + ymin * out_w;
+      if (kTaps > 0) {
+        uint32_t px[kTaps > 0 ? kTaps : 1];
 #pragma unroll
-      for (int y = 0; y < kTaps; ++y) {
-        px[y] = y < ymax ? q[y * out_w] : 0u;
-        k[y] = y < ymax ? t[2 + y] : 0;
-      }
+        for (int y = 0; y < kTaps; ++y) px[y] = y < ymax ? q[y * out_w] : 0u;
 #pragma unroll
-      for (int y = 0; y < kTaps; ++y) {
-        s0 += (int)(px[y] & 0xffu) * k[y]; s1 += (int)((px[y] >> 8) & 0xffu) * k[y];
-        s2 += (int)((px[y] >> 16) & 0xffu) * k[y];
+        for (int y = 0; y < kTaps; ++y) {
+          const int k = y < ymax ? t[2 + y] : 0;          // uniform load
+          s0 += (int)__byte_perm(px[y], 0, 0x4440) * k; s1 += (int)__byte_perm(px[y], 0, 0x4441) * k;
+          s2 += (int)__byte_perm(px[y], 0, 0x4442) * k;
+        }
+      } else {
+        for (int y = 0; y < ymax; ++y) {
+          const int k = t[2 + y];
+          const uint32_t px = q[y * out_w];
+          s0 += (int)(px & 0xffu) * k; s1 += (int)((px >> 8) & 0xffu) * k; s2 += (int)((px >> 16) & 0xffu) * k;
+        }
       }
-    } else {
-      for (int y = 0; y < ymax; ++y) {
-        const int k = t[2 + y];
-        const uint32_t px = q[y * out_w];
-        s0 += (int)(px & 0xffu) * k; s1 += (int)((px >> 8) & 0xffu) * k; s2 += (int)((px >> 16) & 0xffu) * k;
-      }
+      uint8_t* o = fdst + yy * crop_w;
+      o[0] = clip8(s0); o[plane] = clip8(s1); o[2 * plane] = clip8(s2);
     }
-    uint8_t* o = out + (long long)b * 3 * plane + (long long)f * crop_h * crop_w + p;
-    o[0] = clip8(s0); o[plane] = clip8(s1); o[2 * plane] = clip8(s2);
   }
 }
 
@@ -296,32 +306,31 @@ int frames_scale_crop_u8(const uint8_t* frames, uint8_t* tmp, uint8_t* out, cons
   const long long rows = (long long)B * F * Hs;
   uint32_t* tmp32 = reinterpret_cast<uint32_t*>(tmp);
   const int smem = 4 * ((Ws * 3 + 64 + 15) & ~15);     // 4 rows per iteration, each with slack for whole-word windows
+  const int n_frames = B * F;
   if (th.ksize <= 16 && smem <= 48 * 1024) {
     const int threads = std::min(256, round_up(scale_w, 32));
-    const int col_blocks = ceil_div(scale_w, threads);
-    long long gx = std::min<long long>(ceil_div_ll(rows, 4), (long long)sm_count() * 16 / col_blocks);
-    if (gx < 1) gx = 1;
-    dim3 grid((unsigned)gx, col_blocks);
     RowFilter rf;
-    rf.tabv = rows < (1LL << 31) ? tv.ptr : nullptr;
+    rf.tabv = tv.ptr;
     rf.crop_lu = crop_lu; rf.ksize_v = tv.ksize; rf.Hs = Hs; rf.F = F; rf.T = T; rf.V = V; rf.out_h = scale_h;
     rf.crop_h = crop_h;
+    // 8 row slices per frame: ~5 four-row iterations per block for a 112-row crop of a 240-row frame
+    dim3 grid(8, std::min(n_frames, 32768), ceil_div(scale_w, threads));
     if (th.ksize <= 8)
-      frames_resize_h_kernel<8><<<grid, threads, smem, stream>>>(frames, tmp32, th.ptr, th.ksize, rows, Ws, scale_w, rf);
+      frames_resize_h_kernel<8><<<grid, threads, smem, stream>>>(frames, tmp32, th.ptr, th.ksize, n_frames, Ws, scale_w, rf);
     else if (th.ksize <= 12)
-      frames_resize_h_kernel<12><<<grid, threads, smem, stream>>>(frames, tmp32, th.ptr, th.ksize, rows, Ws, scale_w, rf);
+      frames_resize_h_kernel<12><<<grid, threads, smem, stream>>>(frames, tmp32, th.ptr, th.ksize, n_frames, Ws, scale_w, rf);
     else
-      frames_resize_h_kernel<16><<<grid, threads, smem, stream>>>(frames, tmp32, th.ptr, th.ksize, rows, Ws, scale_w, rf);
+      frames_resize_h_kernel<16><<<grid, threads, smem, stream>>>(frames, tmp32, th.ptr, th.ksize, n_frames, Ws, scale_w, rf);
   } else {
     frames_resize_h_generic_kernel<<<fgrid(rows * scale_w), 256, 0, stream>>>(frames, tmp32, th.ptr, th.ksize,
                                                                               rows * scale_w, Ws, scale_w);
   }
   DV_LAUNCH_OK();
-  const int n_frames = B * F;
-  dim3 vgrid(ceil_div(crop_w * crop_h, 256), std::min(n_frames, 32768));
-#define DV_VPASS(K)                                                                                             \
-  frames_resize_v_crop_kernel<K><<<vgrid, 256, 0, stream>>>(tmp32, out, tv.ptr, tv.ksize, crop_lu, F, T, V, Hs, \
-                                                            scale_w, scale_h, crop_w, crop_h, n_frames)
+  const int vthreads = std::min(256, round_up(crop_w, 32));
+  dim3 vgrid(ceil_div(crop_h, 8), std::min(n_frames, 32768), ceil_div(crop_w, vthreads));
+#define DV_VPASS(K)                                                                                                  \
+  frames_resize_v_crop_kernel<K><<<vgrid, vthreads, 0, stream>>>(tmp32, out, tv.ptr, tv.ksize, crop_lu, F, T, V, Hs, \
+                                                                 scale_w, scale_h, crop_w, crop_h, n_frames)
   if (tv.ksize <= 8) DV_VPASS(8); else if (tv.ksize <= 16) DV_VPASS(16); else DV_VPASS(0);
 #undef DV_VPASS
   DV_LAUNCH_OK();
