@@ -123,3 +123,31 @@ def test_gpu_staged_clips_feed_the_encoder_like_the_reference_loader():
     x = ((x - mean) * (1.0 / std)).view(B, 3, V, T, 112, 112).permute(0, 2, 3, 4, 5, 1).reshape(B * V, T, 112, 112, 3)
     assert torch.equal(act.data[..., :3], x.bfloat16())
     assert bool((act.data[..., 3:] == 0).all())
+
+
+def test_oracle_matches_committed_pillow_golden(golden_dir):
+    """tests/golden/frames.npz was written by tests/golden/make_golden_frames.py with Pillow / torchvision (the libraries
+    the reference's transform chain calls) and RandomCrop's own draw order; the oracle reproduces it without them."""
+    import os
+    from oracle.frames import draw_crops, pil_bicubic_resize, scale_crop
+    g = np.load(os.path.join(golden_dir, "frames.npz"))
+    random.seed(int(g["seed"]))
+    crops = draw_crops(g["frames"].shape[0], 3, random)
+    assert np.array_equal(crops, g["crops"])
+    out = scale_crop(g["frames"], crops, 3)
+    assert np.array_equal(out, g["out_u8"])
+    assert abs(float((out.astype(np.float32) / 255).astype(np.float64).sum()) - float(g["out_tensor_checksum"][0])) < 1e-6
+    assert np.array_equal(pil_bicubic_resize(g["big"], 128, 171), g["big_resized"])
+
+
+@pytest.mark.gpu
+def test_gpu_scale_crop_matches_committed_pillow_golden(golden_dir):
+    import os
+    from dualvar_b200 import frames as FR
+    g = np.load(os.path.join(golden_dir, "frames.npz"))
+    got = FR.scale_crop(torch.from_numpy(g["frames"]).cuda(), torch.from_numpy(g["crops"]), 3).cpu().numpy()
+    assert np.array_equal(got, g["out_u8"])
+    # the 320-wide frame (11-tap horizontal windows) through a full-height "crop": scale 120 -> 171 rows, crop all of it
+    big = torch.from_numpy(g["big"]).cuda()[None, None]
+    full = FR.scale_crop(big, torch.zeros((1, 1, 2), dtype=torch.int32), 1, crop_size=(128, 171)).cpu().numpy()
+    assert np.array_equal(full[0, :, 0].transpose(1, 2, 0), g["big_resized"])
