@@ -8,9 +8,8 @@ Pillow's bicubic resampler. The reference does this on the host CPU with PIL for
     clips = frames.stage_clips(frames_u8.cuda(), crops, n_views=3)    # engine.RawClips over uint8 (B,3,48,112,112)
     ret = model(clips)
 
-ColorJitter / GaussianBlur are not covered: the reference's ColorJitter cannot run as shipped (its numpy adjust_*
-functions assert an HWC array, utils/augmentation.py:90-92, and are handed CHW tensors at :617), so there is nothing to
-pin a restatement against.
+ColorJitter / GaussianBlur (the stages that follow in the loader's two other transform branches, utils/augmentation.py:429-721)
+are not covered yet: a pipeline that uses them keeps the reference's host-side code for those two stages.
 """
 import ctypes
 import random

@@ -1,5 +1,5 @@
-"""Oracle for the frame-staging row next to the hot path (first stage): the part of the reference's
-augmentation chain that runs as shipped - ``A.Scale((128, 171))`` (PIL bicubic), ``A.RandomCrop(112)``, ``A.ToTensor()``
+"""Oracle for the frame-staging row next to the hot path (first stage): the first
+stages of the reference's augmentation chain - ``A.Scale((128, 171))`` (PIL bicubic), ``A.RandomCrop(112)``, ``A.ToTensor()``
 (utils/augmentation.py:125-176,361-364; the ``null_transform`` of pretrain.py:491-497) - restated in numpy.
 
 TEST INFRASTRUCTURE ONLY (tests/, __graft_entry__.smoke(), bench.py's cpu_baseline leg): the product path never imports
