@@ -1,4 +1,4 @@
-"""Frame staging in front of the encoders (first stage): the runnable part of the reference loader's
+"""Frame staging in front of the encoders (first stage): the first stages of the reference loader's
 per-clip transform - ``A.Scale((128, 171))`` + ``A.RandomCrop(112)`` + ``A.ToTensor()`` (the ``null_transform`` of
 pretrain.py:491-497, utils/augmentation.py:125-176,361-364) - on the GPU from decoded uint8 frames, bit-exact with
 Pillow's bicubic resampler. The reference does this on the host CPU with PIL for every one of the 48 frames of a sample

@@ -69,3 +69,43 @@ def test_product_does_not_import_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+
+
+def test_new_entry_points_validate_arguments_without_a_gpu():
+    """Status codes + dv_last_error() of the fp32-mode and frame-staging entry points: every bad call is refused on the
+    host side, before any CUDA call (so this runs on the CPU-only build box)."""
+    lib = _lib.load()
+    P = ctypes.c_void_p(64)      # a non-NULL, never dereferenced pointer
+
+    def err():
+        return lib.dv_last_error().decode()
+
+    # split planes: 1..3 planes, planes must not overlap and must keep 16-byte alignment
+    assert lib.dv_f32_split(P, P, 1024, 4, 1024, None) != 0 and "n_planes" in err()
+    assert lib.dv_f32_split(P, P, 100, 2, 1024, None) != 0 and "plane_stride" in err()
+    assert lib.dv_f32_split(P, P, 1028, 2, 1024, None) != 0 and "plane_stride" in err()
+    assert lib.dv_f32_split_planes(None, P, 8, 2, None) != 0
+    # BatchNorm apply into a concat slice: slice must fit the row and stay 8-channel aligned
+    assert lib.dv_f32_bn_apply(P, P, None, None, None, P, None, 0, 3, 10, 64, 64, 8, 1, None) != 0 and "f32_bn_apply" in err()
+    assert lib.dv_f32_bn_apply(P, P, P, None, None, P, None, 0, 3, 10, 64, 64, 0, 1, None) != 0 and "go together" in err()
+    assert lib.dv_f32_bn_bwd_reduce(P, None, None, P, None, P, 10, 64, 64, 0, 1, None) != 0       # relu without a mask source
+    assert lib.dv_f32_bn_bwd_apply(P, None, None, P, P, P, None, 640, 3, None, 10, 64, 64, 0, 1, None) != 0   # no dy planes
+    # convolutions: geometry is checked exactly like the bf16 entry points
+    bad = _lib.make_geom(1, 4, 4, 4, 8, 8, (3, 3, 3), (3, 1, 1), (1, 1, 1))
+    assert lib.dv_conv3d_fprop_f32acc(P, P, P, None, ctypes.byref(bad), 0, None) != 0 and "stride" in err()
+    assert lib.dv_conv3d_dgrad_f32acc(P, P, P, ctypes.byref(bad), 1, None) != 0 and "stride" in err()
+    good = _lib.make_geom(1, 4, 8, 8, 8, 8, (3, 3, 3), (1, 1, 1), (1, 1, 1))
+    assert lib.dv_conv3d_fprop_f32acc(None, P, P, None, ctypes.byref(good), 0, None) != 0 and "NULL" in err()
+    assert lib.dv_conv3d_stem_fprop_f32acc(P, P, P, None, ctypes.byref(good), 0, None) != 0 and "stem path" in err()
+    # frame staging: the crop must fit the scaled frame
+    assert lib.dv_frames_scale_crop_u8(P, P, P, P, 1, 3, 16, 240, 320, 128, 171, 144, 112, None) != 0 and "does not fit" in err()
+    assert lib.dv_frames_scale_crop_u8(P, P, P, None, 1, 3, 16, 240, 320, 128, 171, 112, 112, None) != 0 and "NULL" in err()
+    assert lib.dv_frames_scale_crop_u8(P, P, P, P, 0, 3, 16, 240, 320, 128, 171, 112, 112, None) != 0 and "empty" in err()
+    # the host-only table accessor reports a short buffer instead of overrunning it
+    buf = (ctypes.c_int32 * 16)()
+    ks = ctypes.c_int32(0)
+    assert lib.dv_frames_axis_table_host(320, 128, buf, 16, ctypes.byref(ks)) != 0 and "buffer holds" in err()
+    assert ks.value == 11
+    # ingest into planes: plane stride must cover one plane
+    assert lib.dv_ingest_clips_planes(P, 0, P, 8, 2, None, 1, 1, 1, 1, 1, 3, 4, 8, 8, 0, 1, 0, None, None, 0, None) != 0 \
+        and "plane_stride" in err()
