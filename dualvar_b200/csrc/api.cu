@@ -56,6 +56,8 @@ int conv_stem_wgrad_bf16(const void* x_s2d, const void* dy, float* dw, int N, in
 int frames_scale_crop_u8(const uint8_t* frames, uint8_t* tmp, uint8_t* out, const int* crop_lu, int B, int V, int T,
                          int Hs, int Ws, int scale_w, int scale_h, int crop_w, int crop_h, cudaStream_t stream);
 int frames_axis_table_host(int in_size, int out_size, int* tab, int capacity, int* ksize);
+int frames_color_jitter(const uint8_t* clips, float* out, const float* params, int B, int F, int H, int W,
+                        cudaStream_t stream);
 // fp32 mode (fp32_mode.cu)
 int f32_max_planes();
 int f32_split_planes(const float* src, float* dst, long long n, int K, cudaStream_t stream);
@@ -566,6 +568,13 @@ int dv_frames_scale_crop_u8(const uint8_t* frames, uint8_t* tmp, uint8_t* out, c
   DV_REQUIRE(scale_w > 0 && scale_h > 0 && crop_w > 0 && crop_h > 0 && crop_w <= scale_w && crop_h <= scale_h,
              "crop %dx%d does not fit the scaled frame %dx%d", crop_w, crop_h, scale_w, scale_h);
   return frames_scale_crop_u8(frames, tmp, out, crop_lu, B, n_views, T, Hs, Ws, scale_w, scale_h, crop_w, crop_h, ST);
+}
+
+int dv_frames_color_jitter(const uint8_t* clips_u8, float* out, const float* params, int B, int n_frames_per_sample, int H,
+                           int W, void* stream) {
+  DV_REQUIRE(clips_u8 && out && params, "NULL pointer");
+  DV_REQUIRE(B > 0 && n_frames_per_sample > 0 && H > 0 && W > 0, "empty clip batch");
+  return frames_color_jitter(clips_u8, out, params, B, n_frames_per_sample, H, W, ST);
 }
 
 int dv_frames_axis_table_host(int in_size, int out_size, int32_t* table_host, int capacity, int32_t* ksize_host) {

@@ -8,8 +8,11 @@ Pillow's bicubic resampler. The reference does this on the host CPU with PIL for
     clips = frames.stage_clips(frames_u8.cuda(), crops, n_views=3)    # engine.RawClips over uint8 (B,3,48,112,112)
     ret = model(clips)
 
-ColorJitter / GaussianBlur (the stages that follow in the loader's two other transform branches, utils/augmentation.py:429-721)
-are not covered yet: a pipeline that uses them keeps the reference's host-side code for those two stages.
+Second stage: ``A.ColorJitter`` (utils/augmentation.py:429-660, the jitter of ``base_transform`` /
+``same_series_transform``, pretrain.py:505) - ``draw_color_jitter`` draws the per-frame factors and op order in the
+reference's RNG order, ``color_jitter`` / ``stage_clips(..., jitter=...)`` apply them on the GPU (one CTA per frame, frame
+resident in shared memory). ``A.GaussianBlur`` (:706-721, a PIL filter through a uint8 round trip) is not covered yet: a
+pipeline that uses it keeps the reference's host-side code for that stage.
 """
 import ctypes
 import random
@@ -52,9 +55,56 @@ def scale_crop(frames, crops, n_views, scale_size=(128, 171), crop_size=(112, 11
     return out
 
 
-def stage_clips(frames, crops, n_views, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):
-    """Decoded frames -> the model input: Scale + RandomCrop here, ToTensor + Normalize + layout in the ingest kernel."""
-    return RawClips(scale_crop(frames, crops, n_views), n_views, mean, std)
+def draw_color_jitter(n_frames, py_random=random, np_random=None, brightness=0.8, contrast=0.8, saturation=0.8, hue=0.2,
+                      p=0.8, consistent=False, seq_len=16):
+    """The random draws of ``A.ColorJitter.__call__`` (block = 1) for a list of n_frames images, in its order: per frame
+    (per seq_len frames when ``consistent``) ``np.random.uniform(0, 1) < p`` decides whether a transform is drawn;
+    ``get_params`` then takes ``random.uniform`` for brightness, contrast, saturation, hue and ``random.shuffle``s the four
+    ops (utils/augmentation.py:480-510,595-599). Returns float32 (n_frames, 12): apply, b, 1-b, c, 1-c, s, 1-s, h,
+    op0..op3 with op codes 0..3 = brightness, contrast, saturation, hue (1 - x formed in double, as torchvision's _blend does)."""
+    import numpy as np
+    np_random = np.random if np_random is None else np_random
+    lo = lambda v: max(0.0, 1.0 - v)  # noqa: E731
+    rows, cur = [], None
+    for idx in range(n_frames):
+        if not consistent or idx % seq_len == 0:
+            if np_random.uniform(0., 1.) < p:
+                fb = py_random.uniform(lo(brightness), 1.0 + brightness)
+                fc = py_random.uniform(lo(contrast), 1.0 + contrast)
+                fs = py_random.uniform(lo(saturation), 1.0 + saturation)
+                fh = py_random.uniform(-hue, hue)
+                order = [0, 1, 2, 3]
+                py_random.shuffle(order)
+                cur = [1.0, fb, 1.0 - fb, fc, 1.0 - fc, fs, 1.0 - fs, fh] + [float(o) for o in order]
+            else:
+                cur = [0.0] * 12
+        rows.append(cur)
+    return torch.tensor(rows, dtype=torch.float64).to(torch.float32)
+
+
+def color_jitter(clips_u8, params):
+    """clips_u8: uint8 CUDA tensor (B, 3, F, H, W) (scale_crop's output); params: float32 (B*F, 12) from draw_color_jitter
+    (frame order b-major, as the loader walks a sample's frames). Returns float32 (B, 3, F, H, W) in [0, 1]:
+    ToTensor followed by the frame's jitter - what the reference hands to Normalize."""
+    if not clips_u8.is_cuda:
+        raise _lib.DualVarNativeError("color_jitter: clips must be on a B200 (no CPU fallback)")
+    assert clips_u8.dtype == torch.uint8 and clips_u8.dim() == 5 and clips_u8.shape[1] == 3
+    clips_u8 = clips_u8.contiguous()
+    B, _, F, H, W = clips_u8.shape
+    params = params.to(device=clips_u8.device, dtype=torch.float32).contiguous()
+    assert tuple(params.shape) == (B * F, 12)
+    out = torch.empty((B, 3, F, H, W), dtype=torch.float32, device=clips_u8.device)
+    call("dv_frames_color_jitter", ptr(clips_u8), ptr(out), ptr(params), B, F, H, W, stream_ptr())
+    return out
+
+
+def stage_clips(frames, crops, n_views, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225), jitter=None):
+    """Decoded frames -> the model input: Scale + RandomCrop (+ ColorJitter when ``jitter`` = draw_color_jitter(...)
+    parameters are given) here, ToTensor + Normalize + layout in the ingest kernel."""
+    clips = scale_crop(frames, crops, n_views)
+    if jitter is not None:
+        clips = color_jitter(clips, jitter)
+    return RawClips(clips, n_views, mean, std)
 
 
 def axis_table(in_size, out_size):

@@ -326,6 +326,13 @@ int dv_ingest_clips_planes(const void* src, int src_is_u8, void* dst_planes, int
  * the layout dv_ingest_clips_u8 reads (ToTensor, Normalize and the NDHWC conversion happen there). */
 int dv_frames_scale_crop_u8(const uint8_t* frames, uint8_t* tmp, uint8_t* out, const int32_t* crop_lu, int B, int n_views,
                             int T, int Hs, int Ws, int scale_w, int scale_h, int crop_w, int crop_h, void* stream);
+/* A.ColorJitter (utils/augmentation.py:429-660, block = 1) on the planar uint8 clips dv_frames_scale_crop_u8 wrote:
+ * ToTensor (x / 255) then, per frame, torchvision's tensor adjust_brightness / contrast / saturation / hue in the order
+ * and with the factors of params[frame][12] = {apply, b, 1-b, c, 1-c, s, 1-s, h, op0..op3} (op: 0 brightness, 1 contrast,
+ * 2 saturation, 3 hue; drawn on the host in the reference's RNG order). out: float32 [B][3][F][H][W] in [0, 1] - what the
+ * reference hands to Normalize; dv_ingest_clips consumes it. One CTA keeps a frame in shared memory (3*H*W*4 B <= 200 KB). */
+int dv_frames_color_jitter(const uint8_t* clips_u8, float* out, const float* params, int B, int n_frames_per_sample, int H,
+                           int W, void* stream);
 /* host-only (no GPU needed): the 22-bit fixed-point bicubic table of one axis, out_size rows of
  * [first input index, tap count, taps[ksize]] - what Pillow's precompute_coeffs + normalize_coeffs_8bpc produce */
 int dv_frames_axis_table_host(int in_size, int out_size, int32_t* table_host, int capacity, int32_t* ksize_host);
