@@ -56,6 +56,9 @@ int conv_stem_wgrad_bf16(const void* x_s2d, const void* dy, float* dw, int N, in
 int frames_scale_crop_u8(const uint8_t* frames, uint8_t* tmp, uint8_t* out, const int* crop_lu, int B, int V, int T,
                          int Hs, int Ws, int scale_w, int scale_h, int crop_w, int crop_h, cudaStream_t stream);
 int frames_axis_table_host(int in_size, int out_size, int* tab, int capacity, int* ksize);
+void blur_params_host(float sigma, int* out4);
+int frames_gaussian_blur_host(const float* frame, float* out, int H, int W, float sigma);
+int frames_gaussian_blur(const float* in, float* out, const int* params, int B, int F, int H, int W, cudaStream_t stream);
 int frames_color_jitter(const uint8_t* clips, float* out, const float* params, int B, int F, int H, int W,
                         cudaStream_t stream);
 // fp32 mode (fp32_mode.cu)
@@ -575,6 +578,22 @@ int dv_frames_color_jitter(const uint8_t* clips_u8, float* out, const float* par
   DV_REQUIRE(clips_u8 && out && params, "NULL pointer");
   DV_REQUIRE(B > 0 && n_frames_per_sample > 0 && H > 0 && W > 0, "empty clip batch");
   return frames_color_jitter(clips_u8, out, params, B, n_frames_per_sample, H, W, ST);
+}
+
+int dv_frames_gaussian_blur(const float* clips, float* out, const int32_t* params, int B, int n_frames_per_sample, int H,
+                            int W, void* stream) {
+  DV_REQUIRE(clips && out && params && clips != out, "NULL or aliased pointers");
+  DV_REQUIRE(B > 0 && n_frames_per_sample > 0 && H > 0 && W > 0, "empty clip batch");
+  return frames_gaussian_blur(clips, out, params, B, n_frames_per_sample, H, W, ST);
+}
+int dv_frames_gaussian_blur_params_host(float sigma, int32_t* params4_host) {
+  DV_REQUIRE(params4_host != nullptr, "NULL pointer");
+  blur_params_host(sigma, params4_host);
+  return kOk;
+}
+int dv_frames_gaussian_blur_host(const float* frame_host, float* out_host, int H, int W, float sigma) {
+  DV_REQUIRE(frame_host && out_host && H > 0 && W > 0, "bad gaussian_blur_host arguments");
+  return frames_gaussian_blur_host(frame_host, out_host, H, W, sigma);
 }
 
 int dv_frames_axis_table_host(int in_size, int out_size, int32_t* table_host, int capacity, int32_t* ksize_host) {

@@ -11,8 +11,9 @@ Pillow's bicubic resampler. The reference does this on the host CPU with PIL for
 Second stage: ``A.ColorJitter`` (utils/augmentation.py:429-660, the jitter of ``base_transform`` /
 ``same_series_transform``, pretrain.py:505) - ``draw_color_jitter`` draws the per-frame factors and op order in the
 reference's RNG order, ``color_jitter`` / ``stage_clips(..., jitter=...)`` apply them on the GPU (one CTA per frame, frame
-resident in shared memory). ``A.GaussianBlur`` (:706-721, a PIL filter through a uint8 round trip) is not covered yet: a
-pipeline that uses it keeps the reference's host-side code for that stage.
+resident in shared memory). Third stage: ``A.GaussianBlur`` (:706-721: ToPILImage -> PIL's Gaussian -> ToTensor) -
+``draw_gaussian_blur`` / ``gaussian_blur`` / ``stage_clips(..., blur=...)``; its line filter is one host/device function
+that the CPU tests pin against Pillow through ``dv_frames_gaussian_blur_host``.
 """
 import ctypes
 import random
@@ -98,12 +99,65 @@ def color_jitter(clips_u8, params):
     return out
 
 
-def stage_clips(frames, crops, n_views, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225), jitter=None):
+def draw_gaussian_blur(n_frames, py_random=random, sigma=(0.1, 2.0), seq_len=16):
+    """Per-frame sigma in ``A.GaussianBlur``'s draw order (utils/augmentation.py:713-718): one
+    ``random.uniform(sigma[0], sigma[1])`` per seq_len frames. Set the entries of clips whose RandomApply skipped the
+    stage to 0."""
+    out, cur = [], 0.0
+    for idx in range(n_frames):
+        if idx % seq_len == 0:
+            cur = py_random.uniform(sigma[0], sigma[1])
+        out.append(cur)
+    return out
+
+
+def blur_params(sigmas):
+    """int32 (n_frames, 4) = {apply, box radius, ww, fw}: the fixed-point extended-box parameters Pillow derives from each
+    sigma (computed by the library's host code, the same the CPU test pins against Pillow); sigma <= 0 -> not applied."""
+    buf = (ctypes.c_int32 * 4)()
+    rows = []
+    for sg in sigmas:
+        call("dv_frames_gaussian_blur_params_host", ctypes.c_float(float(sg)), buf)
+        rows.append(list(buf))
+    return torch.tensor(rows, dtype=torch.int32)
+
+
+def gaussian_blur(clips, sigmas):
+    """clips: float32 CUDA tensor (B, 3, F, H, W) in [0, 1] (ToTensor / colour-jitter output); sigmas: B*F values (0 = frame
+    not blurred). Returns a new float32 tensor: every blurred frame went ToPILImage -> PIL GaussianBlur -> ToTensor."""
+    if not clips.is_cuda:
+        raise _lib.DualVarNativeError("gaussian_blur: clips must be on a B200 (no CPU fallback)")
+    assert clips.dtype == torch.float32 and clips.dim() == 5 and clips.shape[1] == 3
+    clips = clips.contiguous()
+    B, _, F, H, W = clips.shape
+    prm = blur_params(sigmas).to(clips.device)
+    assert tuple(prm.shape) == (B * F, 4)
+    out = torch.empty_like(clips)
+    call("dv_frames_gaussian_blur", ptr(clips), ptr(out), ptr(prm), B, F, H, W, stream_ptr())
+    return out
+
+
+def gaussian_blur_host(frame, sigma):
+    """The same stage on one float32 CHW frame on the host, running the line filter the kernel runs (CPU parity tests)."""
+    frame = frame.contiguous().float()
+    assert not frame.is_cuda and frame.dim() == 3 and frame.shape[0] == 3
+    out = torch.empty_like(frame)
+    call("dv_frames_gaussian_blur_host", ctypes.c_void_p(frame.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+         frame.shape[1], frame.shape[2], ctypes.c_float(float(sigma)))
+    return out
+
+
+def stage_clips(frames, crops, n_views, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225), jitter=None, blur=None):
     """Decoded frames -> the model input: Scale + RandomCrop (+ ColorJitter when ``jitter`` = draw_color_jitter(...)
-    parameters are given) here, ToTensor + Normalize + layout in the ingest kernel."""
+    parameters are given, + GaussianBlur when ``blur`` = per-frame sigmas from draw_gaussian_blur(...)) here,
+    ToTensor + Normalize + layout in the ingest kernel."""
     clips = scale_crop(frames, crops, n_views)
-    if jitter is not None:
+    if jitter is not None or blur is not None:
+        if jitter is None:        # ToTensor only: a parameter table with every `apply` flag clear
+            jitter = torch.zeros((clips.shape[0] * clips.shape[2], 12), dtype=torch.float32)
         clips = color_jitter(clips, jitter)
+    if blur is not None:
+        clips = gaussian_blur(clips, blur)
     return RawClips(clips, n_views, mean, std)
 
 

@@ -333,6 +333,17 @@ int dv_frames_scale_crop_u8(const uint8_t* frames, uint8_t* tmp, uint8_t* out, c
  * reference hands to Normalize; dv_ingest_clips consumes it. One CTA keeps a frame in shared memory (3*H*W*4 B <= 200 KB). */
 int dv_frames_color_jitter(const uint8_t* clips_u8, float* out, const float* params, int B, int n_frames_per_sample, int H,
                            int W, void* stream);
+/* A.GaussianBlur (utils/augmentation.py:706-721) on float32 planar clips [B][3][F][H][W] in [0, 1]: per frame ToPILImage
+ * (x * 255 truncated to uint8) -> PIL's Gaussian (three extended-box passes per direction, BoxBlur.c) -> ToTensor (/ 255).
+ * params[frame][4] = {apply, box radius, ww, fw} from dv_frames_gaussian_blur_params_host(sigma) (apply = 0: the frame is
+ * copied unchanged - RandomApply skipped the stage). out must not alias clips. One CTA keeps a frame in shared memory. */
+int dv_frames_gaussian_blur(const float* clips, float* out, const int32_t* params, int B, int n_frames_per_sample, int H,
+                            int W, void* stream);
+/* host-only: the fixed-point box parameters Pillow derives from a Gaussian sigma (sigma <= 0: {0,0,0,0}) */
+int dv_frames_gaussian_blur_params_host(float sigma, int32_t* params4_host);
+/* host-only (no GPU needed): the same stage on ONE float32 CHW frame in host memory, running the line filter the kernel
+ * runs (one __host__ __device__ function) - lets the CPU test pin that code against Pillow */
+int dv_frames_gaussian_blur_host(const float* frame_host, float* out_host, int H, int W, float sigma);
 /* host-only (no GPU needed): the 22-bit fixed-point bicubic table of one axis, out_size rows of
  * [first input index, tap count, taps[ksize]] - what Pillow's precompute_coeffs + normalize_coeffs_8bpc produce */
 int dv_frames_axis_table_host(int in_size, int out_size, int32_t* table_host, int capacity, int32_t* ksize_host);

@@ -11,6 +11,8 @@ _blend, rgb_to_grayscale, _rgb2hsv, _hsv2rgb), restated here operation by operat
 follow the same rounding sequence. Pinned against torchvision itself and against the real reference class
 (tests/golden/color_jitter.npz, written by tests/golden/make_golden_color_jitter.py) in tests/test_color_jitter.py.
 """
+import math
+
 import numpy as np
 import torch
 
@@ -112,5 +114,107 @@ def color_jitter(frames, params):
             for op in prm[8:12].astype(int):
                 f, om = fac[int(op)]
                 x = _FN[int(op)](x, float(f), None if om is None else float(om))
+        out.append(x)
+    return torch.stack(out)
+
+
+# ----------------------------------------------------------------------------------------------- Gaussian blur
+# A.GaussianBlur (utils/augmentation.py:706-721): per clip sigma = random.uniform(0.1, 2); every frame goes
+# ToPILImage -> PIL ImageFilter.GaussianBlur(radius=sigma) -> ToTensor. Pillow (12.2.0; src/libImaging/BoxBlur.c)
+# approximates the Gaussian with three passes of an "extended box" filter per direction; restated from the published
+# algorithm and pinned bit for bit against Pillow itself in tests/test_stage_blur.py.
+_f = np.float32
+
+
+def gaussian_box_radius(radius, passes=3):
+    """BoxBlur.c _gaussian_blur_radius (float variables, double literals: the C expression types are kept)."""
+    radius = _f(radius)
+    sigma2 = _f(_f(radius * radius) / _f(passes))
+    L = _f(math.sqrt(12.0 * float(sigma2) + 1.0))
+    l = _f(math.floor((float(L) - 1.0) / 2.0))                                              # noqa: E741
+    a = _f(float(_f(_f(2) * l + _f(1))) * (float(_f(l * _f(l + _f(1)))) - 3.0 * float(sigma2)))
+    a = _f(float(a) / (6.0 * float(_f(sigma2 - _f(_f(l + _f(1)) * _f(l + _f(1)))))))
+    return _f(l + a)
+
+
+def _line_box_blur(line, radius, ww, fw):
+    """ImagingLineBoxBlur32 on an (n, C) int64 array of uint8 values; uint32 wrap-around arithmetic."""
+    n = line.shape[0]
+    lastx = n - 1
+    edge_a, edge_b = min(radius + 1, n), max(n - radius - 1, 0)
+    M = 1 << 32
+    out = np.zeros_like(line)
+    acc = (line[0] * (radius + 1)) % M
+    for x in range(edge_a - 1):
+        acc = (acc + line[x]) % M
+    acc = (acc + line[lastx] * (radius - edge_a + 1)) % M
+
+    def step(x, sub, add, left, right):
+        nonlocal acc
+        acc = (acc + line[add] - line[sub]) % M
+        bulk = (acc * ww + (line[left] + line[right]) * fw) % M
+        out[x] = ((bulk + (1 << 23)) % M) >> 24
+
+    if edge_a <= edge_b:
+        for x in range(0, edge_a):
+            step(x, 0, x + radius, 0, x + radius + 1)
+        for x in range(edge_a, edge_b):
+            step(x, x - radius - 1, x + radius, x - radius - 1, x + radius + 1)
+        for x in range(edge_b, lastx + 1):
+            step(x, x - radius - 1, lastx, x - radius - 1, lastx)
+    else:
+        for x in range(0, edge_b):
+            step(x, 0, x + radius, 0, x + radius + 1)
+        for x in range(edge_b, edge_a):
+            step(x, 0, lastx, 0, lastx)
+        for x in range(edge_a, lastx + 1):
+            step(x, x - radius - 1, lastx, x - radius - 1, lastx)
+    return out
+
+
+def _horizontal_box_blur(img, float_radius):
+    radius = int(float_radius)
+    ww = int(_f(_f(1 << 24) / _f(float_radius * _f(2) + _f(1))))
+    fw = (((1 << 24) - (radius * 2 + 1) * ww) % (1 << 32)) // 2
+    src = img.astype(np.int64)
+    out = np.empty_like(src)
+    for y in range(img.shape[0]):
+        out[y] = _line_box_blur(src[y], radius, ww, fw)
+    return out.astype(np.uint8)
+
+
+def pil_gaussian_blur(img, sigma, passes=3):
+    """``Image.fromarray(img).filter(ImageFilter.GaussianBlur(radius=sigma))`` for an (H, W, 3) uint8 array."""
+    if sigma == 0:
+        return img.copy()
+    r = gaussian_box_radius(sigma, passes)
+    out = img
+    if r != 0:
+        for _ in range(passes):
+            out = _horizontal_box_blur(out, r)
+        t = out.transpose(1, 0, 2)
+        for _ in range(passes):
+            t = _horizontal_box_blur(t, r)
+        out = t.transpose(1, 0, 2)
+    return out
+
+
+def draw_gaussian_blur(n_frames, py_random, sigma=(0.1, 2.0), seq_len=16):
+    """Per-frame sigma in A.GaussianBlur's draw order: one ``random.uniform(sigma[0], sigma[1])`` per seq_len frames."""
+    out, cur = [], 0.0
+    for idx in range(n_frames):
+        if idx % seq_len == 0:
+            cur = py_random.uniform(sigma[0], sigma[1])
+        out.append(cur)
+    return out
+
+
+def gaussian_blur(frames, sigmas):
+    """frames: (n, 3, H, W) float32 in [0, 1]; sigma <= 0 leaves a frame untouched (stage skipped)."""
+    out = []
+    for x, sg in zip(frames, sigmas):
+        if sg > 0:
+            u8 = x.mul(255).byte().permute(1, 2, 0).numpy()                      # ToPILImage
+            x = torch.from_numpy(pil_gaussian_blur(u8, sg)).permute(2, 0, 1).float().div(255)      # ToTensor
         out.append(x)
     return torch.stack(out)
