@@ -79,6 +79,8 @@ def test_gaussian_blur_refuses_cpu_tensors():
 
 
 @pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="provisional: the kernel launch was written after the round's GPU budget was spent and "
+                                        "has never been executed; XPASS = verified (drop this marker), XFAIL = fix the launch code")
 def test_gpu_gaussian_blur_bit_exact(golden_dir):
     from dualvar_b200 import frames as FR
     from oracle import augment as A
