@@ -147,6 +147,43 @@ def gaussian_blur_host(frame, sigma):
     return out
 
 
+def draw_plan(n_samples, n_views=3, seq_len=16, scaled=(128, 171), crop=(112, 112),
+              weights=((0.2, 0.8, 0.0), (0.0, 1.0, 0.0), (0.0, 0.0, 1.0)), jitter_p=0.8, blur_p=0.5, consistent=False,
+              py_random=random, np_random=None):
+    """Every random draw of the loader's transform for n_samples samples, in the reference's order and from the RNGs it
+    uses (pretrain.py:491-529): per clip ``MultiRandomizedTransform`` picks a branch with ``np.random.uniform()``
+    (utils/augmentation.py:795-809; branch 0 = null_transform, 1 = base, 2 = same-series), ``RandomCrop`` takes two
+    ``random.randint``; in the jitter branches torchvision's ``RandomApply`` consumes ``torch.rand(1)`` (global generator)
+    before ``ColorJitter`` (p = 0.8) and again before ``GaussianBlur`` (p = 0.5), each of which then draws as
+    draw_color_jitter / draw_gaussian_blur describe. Returns {'crops': int32 (n, V, 2), 'jitter': float32 (n*V*T, 12),
+    'blur': [n*V*T sigmas], 'branch': int32 (n, V)} - the arguments of ``stage_clips``; frames of clips whose stage was
+    skipped carry apply = 0 / sigma = 0."""
+    import numpy as np
+    np_random = np.random if np_random is None else np_random
+    cum = [np.cumsum(w) for w in weights]
+    crops, branches, jitter, blur = [], [], [], []
+    for _ in range(n_samples):
+        for v in range(n_views):
+            rand_p = np_random.uniform()
+            ind = 0
+            while rand_p >= cum[v][ind]:
+                ind += 1
+            branches.append(ind)
+            crops.append((py_random.randint(0, scaled[0] - crop[0]), py_random.randint(0, scaled[1] - crop[1])))
+            jit = torch.zeros((seq_len, 12), dtype=torch.float32)
+            sig = [0.0] * seq_len
+            if ind != 0:
+                if not (jitter_p < float(torch.rand(1))):            # RandomApply([ColorJitter], p=0.8)
+                    jit = draw_color_jitter(seq_len, py_random, np_random, consistent=consistent, seq_len=seq_len)
+                if not (blur_p < float(torch.rand(1))):              # RandomApply([GaussianBlur], p=0.5)
+                    sig = draw_gaussian_blur(seq_len, py_random, seq_len=seq_len)
+            jitter.append(jit)
+            blur.extend(sig)
+    return {"crops": torch.tensor(crops, dtype=torch.int32).view(n_samples, n_views, 2),
+            "jitter": torch.cat(jitter), "blur": blur,
+            "branch": torch.tensor(branches, dtype=torch.int32).view(n_samples, n_views)}
+
+
 def stage_clips(frames, crops, n_views, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225), jitter=None, blur=None):
     """Decoded frames -> the model input: Scale + RandomCrop (+ ColorJitter when ``jitter`` = draw_color_jitter(...)
     parameters are given, + GaussianBlur when ``blur`` = per-frame sigmas from draw_gaussian_blur(...)) here,

@@ -103,3 +103,63 @@ def test_gpu_gaussian_blur_bit_exact(golden_dir):
     assert torch.equal(got, want)
     for n in (0, 7):
         assert torch.equal(got[n // F, :, n % F], FR.gaussian_blur_host(frames[n], sig[n]))
+
+
+def _plan_and_oracle_chain(golden_dir):
+    from dualvar_b200 import frames as FR
+    from oracle import augment as A
+    from oracle.frames import scale_crop
+    g = np.load(os.path.join(golden_dir, "transform_plan.npz"))
+    seq, scaled, crop = int(g["seq_len"]), tuple(int(v) for v in g["scaled"]), int(g["crop"])
+    n = g["frames"].shape[0]
+    random.seed(int(g["seeds"][0])); np.random.seed(int(g["seeds"][1])); torch.manual_seed(int(g["seeds"][2]))
+    plan = FR.draw_plan(n, 3, seq_len=seq, scaled=scaled, crop=(crop, crop))
+    u8 = scale_crop(g["frames"], plan["crops"].numpy(), 3, scale_size=scaled, crop_size=(crop, crop))
+    x = torch.from_numpy(u8).permute(0, 2, 1, 3, 4).reshape(n * 3 * seq, 3, crop, crop).float().div(255)
+    x = A.gaussian_blur(A.color_jitter(x, plan["jitter"].numpy()), plan["blur"])
+    return g, plan, x.view(n, 3 * seq, 3, crop, crop).permute(0, 2, 1, 3, 4), (seq, scaled, crop)
+
+
+def test_transform_plan_reproduces_the_reference_loader_chain(golden_dir):
+    """The whole transform of pretrain.py:491-529 - MultiRandomizedTransform over [null, base, same-series] branches of
+    Scale / RandomCrop / ToTensor / RandomApply(ColorJitter) / RandomApply(GaussianBlur), built from the UNMODIFIED reference
+    classes by tests/golden/make_golden_plan.py - equals draw_plan (np.random + random + torch.rand in the reference's
+    order) driving the oracle stages, bit for bit."""
+    g, plan, out, _ = _plan_and_oracle_chain(golden_dir)
+    assert torch.equal(out, torch.from_numpy(g["out"]))
+    br = plan["branch"]
+    assert set(br[:, 0].tolist()) == {0, 1} and set(br[:, 1].tolist()) == {1} and set(br[:, 2].tolist()) == {2}
+    assert 0 < int(plan["jitter"][:, 0].sum()) < plan["jitter"].shape[0]       # some clips jittered, some not
+    assert 0 < sum(1 for s in plan["blur"] if s > 0) < len(plan["blur"])
+    nul = (br == 0).view(-1).repeat_interleave(int(g["seq_len"]))
+    assert float(plan["jitter"][nul, 0].sum()) == 0 and all(plan["blur"][i] == 0 for i in torch.nonzero(nul).view(-1).tolist())
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="provisional: goes through the never-executed Gaussian-blur launch (see above)")
+def test_gpu_whole_transform_chain_matches_reference_golden(golden_dir):
+    """decoded frames -> scale_crop -> color_jitter -> gaussian_blur on the GPU with the drawn plan == the reference chain
+    (2e-6: the contrast mean is the only non-bit-exact step; a blur after it can move a value by 1/255 only if that 2e-6
+    crosses a truncation boundary, which the seeded golden does not hit)."""
+    from dualvar_b200 import frames as FR
+    g, plan, want, (seq, scaled, crop) = _plan_and_oracle_chain(golden_dir)
+    clips = FR.scale_crop(torch.from_numpy(g["frames"]).cuda(), plan["crops"], 3, scale_size=scaled, crop_size=(crop, crop))
+    clips = FR.gaussian_blur(FR.color_jitter(clips, plan["jitter"]), plan["blur"]).cpu()
+    assert float((clips - torch.from_numpy(g["out"])).abs().max()) <= 2e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="provisional: written after the round's GPU budget was spent, never executed (the two "
+                                        "kernels it calls are verified at other geometries in test_frames / test_color_jitter)")
+def test_gpu_scale_crop_and_jitter_chain_matches_reference_golden(golden_dir):
+    """The verified part of the chain on the samples whose clips drew no blur: Scale + RandomCrop + ToTensor + ColorJitter."""
+    from dualvar_b200 import frames as FR
+    g, plan, want, (seq, scaled, crop) = _plan_and_oracle_chain(golden_dir)
+    clips = FR.scale_crop(torch.from_numpy(g["frames"]).cuda(), plan["crops"], 3, scale_size=scaled, crop_size=(crop, crop))
+    got = FR.color_jitter(clips, plan["jitter"]).cpu()                                 # (n, 3, F, crop, crop)
+    ref = torch.from_numpy(g["out"])
+    F = 3 * seq
+    unblurred = [i for i, s in enumerate(plan["blur"]) if s == 0]
+    assert len(unblurred) >= seq
+    for i in unblurred:
+        assert float((got[i // F, :, i % F] - ref[i // F, :, i % F]).abs().max()) <= 2e-6
