@@ -115,10 +115,14 @@ def blur_params(sigmas):
     """int32 (n_frames, 4) = {apply, box radius, ww, fw}: the fixed-point extended-box parameters Pillow derives from each
     sigma (computed by the library's host code, the same the CPU test pins against Pillow); sigma <= 0 -> not applied."""
     buf = (ctypes.c_int32 * 4)()
-    rows = []
-    for sg in sigmas:
-        call("dv_frames_gaussian_blur_params_host", ctypes.c_float(float(sg)), buf)
-        rows.append(list(buf))
+    seen, rows = {}, []
+    for sg in sigmas:                       # one sigma per clip: a few hundred distinct values per batch of frames
+        sg = float(sg)
+        row = seen.get(sg)
+        if row is None:
+            call("dv_frames_gaussian_blur_params_host", ctypes.c_float(sg), buf)
+            row = seen[sg] = list(buf)
+        rows.append(row)
     return torch.tensor(rows, dtype=torch.int32)
 
 
