@@ -56,6 +56,27 @@ def scale_crop(frames, crops, n_views, scale_size=(128, 171), crop_size=(112, 11
     return out
 
 
+def _jitter_rows(n_frames, py_random, np_random, brightness, contrast, saturation, hue, p, consistent, seq_len):
+    lo = lambda v: max(0.0, 1.0 - v)  # noqa: E731
+    b0, b1, c0, c1, s0, s1 = lo(brightness), 1.0 + brightness, lo(contrast), 1.0 + contrast, lo(saturation), 1.0 + saturation
+    zero = [0.0] * 12
+    rows, cur = [], None
+    for idx in range(n_frames):
+        if not consistent or idx % seq_len == 0:
+            if np_random.uniform(0., 1.) < p:
+                fb = py_random.uniform(b0, b1)
+                fc = py_random.uniform(c0, c1)
+                fs = py_random.uniform(s0, s1)
+                fh = py_random.uniform(-hue, hue)
+                order = [0.0, 1.0, 2.0, 3.0]
+                py_random.shuffle(order)
+                cur = [1.0, fb, 1.0 - fb, fc, 1.0 - fc, fs, 1.0 - fs, fh] + order
+            else:
+                cur = zero
+        rows.append(cur)
+    return rows
+
+
 def draw_color_jitter(n_frames, py_random=random, np_random=None, brightness=0.8, contrast=0.8, saturation=0.8, hue=0.2,
                       p=0.8, consistent=False, seq_len=16):
     """The random draws of ``A.ColorJitter.__call__`` (block = 1) for a list of n_frames images, in its order: per frame
@@ -65,21 +86,7 @@ def draw_color_jitter(n_frames, py_random=random, np_random=None, brightness=0.8
     op0..op3 with op codes 0..3 = brightness, contrast, saturation, hue (1 - x formed in double, as torchvision's _blend does)."""
     import numpy as np
     np_random = np.random if np_random is None else np_random
-    lo = lambda v: max(0.0, 1.0 - v)  # noqa: E731
-    rows, cur = [], None
-    for idx in range(n_frames):
-        if not consistent or idx % seq_len == 0:
-            if np_random.uniform(0., 1.) < p:
-                fb = py_random.uniform(lo(brightness), 1.0 + brightness)
-                fc = py_random.uniform(lo(contrast), 1.0 + contrast)
-                fs = py_random.uniform(lo(saturation), 1.0 + saturation)
-                fh = py_random.uniform(-hue, hue)
-                order = [0, 1, 2, 3]
-                py_random.shuffle(order)
-                cur = [1.0, fb, 1.0 - fb, fc, 1.0 - fc, fs, 1.0 - fs, fh] + [float(o) for o in order]
-            else:
-                cur = [0.0] * 12
-        rows.append(cur)
+    rows = _jitter_rows(n_frames, py_random, np_random, brightness, contrast, saturation, hue, p, consistent, seq_len)
     return torch.tensor(rows, dtype=torch.float64).to(torch.float32)
 
 
@@ -161,11 +168,13 @@ def draw_plan(n_samples, n_views=3, seq_len=16, scaled=(128, 171), crop=(112, 11
     before ``ColorJitter`` (p = 0.8) and again before ``GaussianBlur`` (p = 0.5), each of which then draws as
     draw_color_jitter / draw_gaussian_blur describe. Returns {'crops': int32 (n, V, 2), 'jitter': float32 (n*V*T, 12),
     'blur': [n*V*T sigmas], 'branch': int32 (n, V)} - the arguments of ``stage_clips``; frames of clips whose stage was
-    skipped carry apply = 0 / sigma = 0."""
+    skipped carry apply = 0 / sigma = 0. Pure host work (~0.4 ms per sample, the cost of Python's own RNG calls): it belongs
+    where the reference runs its transform, in the DataLoader workers, next to the JPEG decode."""
     import numpy as np
     np_random = np.random if np_random is None else np_random
     cum = [np.cumsum(w) for w in weights]
     crops, branches, jitter, blur = [], [], [], []
+    zero_rows = [[0.0] * 12] * seq_len
     for _ in range(n_samples):
         for v in range(n_views):
             rand_p = np_random.uniform()
@@ -174,17 +183,17 @@ def draw_plan(n_samples, n_views=3, seq_len=16, scaled=(128, 171), crop=(112, 11
                 ind += 1
             branches.append(ind)
             crops.append((py_random.randint(0, scaled[0] - crop[0]), py_random.randint(0, scaled[1] - crop[1])))
-            jit = torch.zeros((seq_len, 12), dtype=torch.float32)
+            jit = zero_rows
             sig = [0.0] * seq_len
             if ind != 0:
                 if not (jitter_p < float(torch.rand(1))):            # RandomApply([ColorJitter], p=0.8)
-                    jit = draw_color_jitter(seq_len, py_random, np_random, consistent=consistent, seq_len=seq_len)
+                    jit = _jitter_rows(seq_len, py_random, np_random, 0.8, 0.8, 0.8, 0.2, 0.8, consistent, seq_len)
                 if not (blur_p < float(torch.rand(1))):              # RandomApply([GaussianBlur], p=0.5)
                     sig = draw_gaussian_blur(seq_len, py_random, seq_len=seq_len)
-            jitter.append(jit)
+            jitter.extend(jit)
             blur.extend(sig)
     return {"crops": torch.tensor(crops, dtype=torch.int32).view(n_samples, n_views, 2),
-            "jitter": torch.cat(jitter), "blur": blur,
+            "jitter": torch.tensor(jitter, dtype=torch.float64).to(torch.float32), "blur": blur,
             "branch": torch.tensor(branches, dtype=torch.int32).view(n_samples, n_views)}
 
 
