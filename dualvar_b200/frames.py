@@ -35,6 +35,13 @@ def draw_crops(B, n_views, rng=random, scaled=(128, 171), crop=(112, 112)):
     return torch.tensor(vals, dtype=torch.int32).view(B, n_views, 2)
 
 
+def center_crops(B, n_views, scaled=(128, 171), crop=(112, 112)):
+    """(B, n_views, 2) int32 (left, upper) of ``A.CenterCrop`` (utils/augmentation.py:185-191: ``int(round((w - tw) / 2.))``,
+    Python's round-half-to-even) - the crop of the evaluation / retrieval transforms (classifier.py:683-695,809-817)."""
+    left, upper = int(round((scaled[0] - crop[0]) / 2.)), int(round((scaled[1] - crop[1]) / 2.))
+    return torch.tensor([left, upper], dtype=torch.int32).repeat(B, n_views, 1)
+
+
 def scale_crop(frames, crops, n_views, scale_size=(128, 171), crop_size=(112, 112)):
     """frames: uint8 CUDA tensor (B, n_views*T, Hs, Ws, 3) of decoded frames; crops: int32 (B, n_views, 2).
     Returns uint8 (B, 3, n_views*T, crop_h, crop_w): every frame resized to scale_size = (width, height) with PIL's

@@ -151,3 +151,26 @@ def test_gpu_scale_crop_matches_committed_pillow_golden(golden_dir):
     big = torch.from_numpy(g["big"]).cuda()[None, None]
     full = FR.scale_crop(big, torch.zeros((1, 1, 2), dtype=torch.int32), 1, crop_size=(128, 171)).cpu().numpy()
     assert np.array_equal(full[0, :, 0].transpose(1, 2, 0), g["big_resized"])
+
+
+def test_center_crops_follow_reference_center_crop():
+    """A.Scale((128,171)) + A.CenterCrop(112) + ToTensor of the evaluation / retrieval transforms (classifier.py:683-695,
+    809-817), written with PIL exactly as utils/augmentation.py:185-191 does, equals oracle.scale_crop at center_crops()."""
+    from PIL import Image
+    from torchvision import transforms
+    from dualvar_b200 import frames as FR
+    from oracle.frames import scale_crop
+    cc = FR.center_crops(2, 1)
+    assert cc.shape == (2, 1, 2) and cc[0, 0].tolist() == [8, 30]            # round(29.5) == 30: half to even
+    assert FR.center_crops(1, 1, scaled=(128, 171), crop=(113, 112))[0, 0].tolist() == [8, 30]   # round(7.5) == 8
+    rng = np.random.default_rng(2)
+    frames = rng.integers(0, 256, (2, 3, 90, 120, 3), dtype=np.uint8)
+    got = scale_crop(frames, cc.numpy(), 1)
+    for b in range(2):
+        for f in range(3):
+            im = Image.fromarray(frames[b, f]).resize((128, 171), Image.BICUBIC)
+            w, h = im.size
+            th, tw = 112, 112
+            x1, y1 = int(round((w - tw) / 2.)), int(round((h - th) / 2.))
+            ten = transforms.ToTensor()(im.crop((x1, y1, x1 + tw, y1 + th)))
+            assert torch.equal(ten, torch.from_numpy(got[b, :, f]).float() / 255)
