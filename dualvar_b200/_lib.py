@@ -85,6 +85,11 @@ def _parse_header(path=_HEADER):
 
 
 _SIGNATURES = _parse_header()
+# DV_LIB_PATH pointing at the diagnostics build (libdualvar_b200_diag.so, `make diag`): the dv_debug_* entry points of
+# include/dualvar_b200_diag.h are bound as well. The product library has none of them.
+_DIAG_HEADER = os.path.join(os.path.dirname(_HEADER), "dualvar_b200_diag.h")
+if "_diag" in os.path.basename(_LIB_PATH) and os.path.exists(_DIAG_HEADER):
+    _SIGNATURES.update(_parse_header(_DIAG_HEADER))
 
 
 def lib_path():

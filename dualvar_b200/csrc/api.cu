@@ -111,8 +111,6 @@ int segment_bcast(const float* in, float* out, long long rows, int s, int e, flo
 int rowdot(const float* a, const float* b, float* out, int rows, int d, int ld_out, cudaStream_t stream);
 int row_axpy(const float* alpha, int ld_alpha, const float* x, float* y, int rows, int d, float beta,
              cudaStream_t stream);
-int probe_overlap(const void* src, void* out, int c1, cudaStream_t stream);
-int mma_rate(int n, int n_mma, int region, int mode, long long* out, int grid, cudaStream_t stream);
 long long small_allreduce_buffer_bytes();
 int bn_finalize_sync(const double* stats, const float* gamma, const float* beta, float* running_mean, float* running_var,
                      float* ss, float* saved, int C, int Cp, double count_global, float eps, float momentum,
@@ -120,11 +118,12 @@ int bn_finalize_sync(const double* stats, const float* gamma, const float* beta,
 int bn_bwd_finalize_sync(const double* sums_local, const float* gamma, const float* saved, float* dgamma, float* dbeta,
                          float* coef, int C, int Cp, double count_global, float grad_beta, const long long* peer_ptrs,
                          int rank, int world, long long seq, cudaStream_t stream);
+void comm_set_timeout(double seconds);
+int comm_status(int* peer, long long* seq, int clear);
 int small_allreduce_f64(double* inout, int n, const long long* peer_ptrs, int rank, int world, long long seq,
                         cudaStream_t stream);
 int sgd_momentum_step(const long long* table, int n_chunks, float lr, float mu, float wd, int first,
                       cudaStream_t stream);
-void set_conv_profile(long long* p);
 int retrieval_prepare(const float* x, double* mean, double* y, int n, int d, cudaStream_t st);
 int retrieval_sim_topk(const double* test, const double* train, double* sim, float* sim32, long long* idx,
                        int nt, int ntr, int d, int k, cudaStream_t st);
@@ -683,17 +682,17 @@ int dv_bn_bwd_finalize_sync(const double* sums_local, const float* gamma, const 
                               reinterpret_cast<const long long*>(peer_buffers), rank, world, seq, ST);
 }
 
-int dv_debug_set_conv_profile(int64_t* buf) {
-  set_conv_profile(reinterpret_cast<long long*>(buf));
+int dv_comm_set_timeout(double seconds) {
+  comm_set_timeout(seconds);
   return 0;
 }
 
-int dv_debug_probe_overlap_tmap(const void* src, void* out, int c1, void* stream) {
-  return probe_overlap(src, out, c1, ST);
+int dv_comm_status(int* peer, int64_t* seq, int clear) {
+  long long s = 0;
+  const int code = comm_status(peer, &s, clear);
+  if (seq) *seq = s;
+  return code;
 }
 
-int dv_debug_mma_rate(int n, int n_mma, int region_bytes, int mode, int64_t* cycles, int grid, void* stream) {
-  return mma_rate(n, n_mma, region_bytes, mode, reinterpret_cast<long long*>(cycles), grid, ST);
-}
 
 }  // extern "C"

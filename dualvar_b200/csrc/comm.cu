@@ -14,7 +14,12 @@
 //   3. acquire-spin on my own flags [parity][q] == seq for all q,
 //   4. sum my slots in rank order (bit-identical result on all ranks) back into the caller's vector.
 // A rank can only enter call seq + 2 after every peer's flag of call seq + 1 arrived, i.e. after every peer left
-// call seq - so two parities make slot reuse safe. One CTA; the spin has a time-out that traps instead of hanging.
+// call seq - so two parities make slot reuse safe. One CTA. The spin has a time-out (dv_comm_set_timeout, default
+// 600 s like NCCL's watchdog: ranks legitimately drift apart by many seconds around checkpoints and loader start-up);
+// when it expires the kernel records (code, peer, call) in a host-mapped status word and returns - the CUDA context
+// survives and the host raises from dv_comm_status() at its next exchange. With each vector every rank also pushes
+// one scalar `tag` (the local per-channel count of cross-replica BatchNorm); ranks whose tags differ are reported the
+// same way (nn.SyncBatchNorm weights ranks by their counts; this path requires equal per-rank batches).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -28,7 +33,23 @@ constexpr int kArMaxElems = 4096;
 
 struct ArPeers {
   unsigned long long base[kArMaxWorld];   // peer-mapped address of every rank's symmetric buffer
+  unsigned long long timeout_ns;          // spin time-out
+  int* status;                            // host-mapped [4]: code (0 ok, 1 time-out, 2 tag mismatch), peer, seq lo, seq hi
 };
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void ar_report(const ArPeers& peers, int code, int peer, unsigned long long seq) {
+  if (peers.status != nullptr && atomicCAS(peers.status, 0, code) == 0) {   // first error wins
+    peers.status[1] = peer;
+    peers.status[2] = (int)(seq & 0xffffffffull);
+    peers.status[3] = (int)(seq >> 32);
+    __threadfence_system();
+  }
+}
 
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -42,13 +63,14 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
 // Steps 1-3 for the calling CTA: push `src[0:n]` to every rank, signal, wait for every rank's signal. Afterwards
 // ar_sum(i) returns the sum over ranks (in rank order) of element i.
 __device__ __forceinline__ const double* ar_exchange(const double* __restrict__ src, int n, const ArPeers& peers,
-                                                     int rank, int world, unsigned long long seq) {
+                                                     int rank, int world, unsigned long long seq, double tag = 0.0) {
   const int parity = (int)(seq & 1ull);
   const size_t slot_elems = (size_t)kArMaxElems;
   const size_t flags_off = 2ull * kArMaxWorld * slot_elems;   // in doubles (= u64 words)
   for (int p = 0; p < world; ++p) {
     double* dst = reinterpret_cast<double*>(peers.base[p]) + ((size_t)parity * kArMaxWorld + rank) * slot_elems;
     for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+    if (threadIdx.x == 0) dst[kArMaxElems - 1] = tag;     // n < kArMaxElems: the last element of a slot is the tag
   }
   __threadfence_system();
   __syncthreads();
@@ -58,12 +80,22 @@ __device__ __forceinline__ const double* ar_exchange(const double* __restrict__ 
     st_release_sys_u64(remote, seq);
     const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(peers.base[rank]) + flags_off +
                                      (size_t)parity * kArMaxWorld + threadIdx.x;
-    const long long t0 = clock64();
+    const unsigned long long t0 = global_timer_ns();
+    int polls = 0;
+    bool arrived = true;
     while (ld_acquire_sys_u64(mine) != seq) {
-      if (clock64() - t0 > 20000000000ll) {   // ~10 s: a peer never arrived; fail loudly instead of hanging the GPU
-        printf("dv small_allreduce: rank %d timed out waiting for rank %d (call %llu)\n", rank, (int)threadIdx.x, seq);
-        __trap();
+      if ((++polls & 1023) == 0 && global_timer_ns() - t0 > peers.timeout_ns) {
+        // a peer never arrived: report to the host and give up on this call (its result is undefined);
+        // the context stays usable so the host can raise, checkpoint or tear down in order
+        ar_report(peers, 1, (int)threadIdx.x, seq);
+        arrived = false;
+        break;
       }
+    }
+    if (arrived) {
+      const double* slots = reinterpret_cast<const double*>(peers.base[rank]) + (size_t)parity * kArMaxWorld * slot_elems;
+      if (__ldcv(slots + (size_t)threadIdx.x * kArMaxElems + kArMaxElems - 1) != tag)
+        ar_report(peers, 2, (int)threadIdx.x, seq);
     }
   }
   __syncthreads();
@@ -88,7 +120,7 @@ bn_finalize_sync_kernel(const double* __restrict__ stats, const float* __restric
                         float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ ss,
                         float* __restrict__ saved, int C, int Cp, double count_global, float eps, float momentum,
                         ArPeers peers, int rank, int world, unsigned long long seq) {
-  const double* base = ar_exchange(stats, 2 * Cp, peers, rank, world, seq);
+  const double* base = ar_exchange(stats, 2 * Cp, peers, rank, world, seq, count_global / world);
   for (int c = threadIdx.x; c < Cp; c += blockDim.x)
     bn_finalize_channel(c, ar_sum(base, world, c), ar_sum(base, world, Cp + c), gamma, beta, running_mean, running_var, ss,
                         saved, C, Cp, count_global, eps, momentum, 1);
@@ -101,7 +133,7 @@ bn_bwd_finalize_sync_kernel(const double* __restrict__ sums_local, const float* 
                             const float* __restrict__ saved, float* __restrict__ dgamma, float* __restrict__ dbeta,
                             float* __restrict__ coef, int C, int Cp, double count_global, float grad_beta,
                             ArPeers peers, int rank, int world, unsigned long long seq) {
-  const double* base = ar_exchange(sums_local, 2 * Cp, peers, rank, world, seq);
+  const double* base = ar_exchange(sums_local, 2 * Cp, peers, rank, world, seq, count_global / world);
   for (int c = threadIdx.x; c < Cp; c += blockDim.x) {
     const bool real = c < C;
     bn_bwd_finalize_channel(c, real ? sums_local[c] : 0.0, real ? sums_local[Cp + c] : 0.0,
@@ -110,28 +142,62 @@ bn_bwd_finalize_sync_kernel(const double* __restrict__ sums_local, const float* 
   }
 }
 
+// ---- host state: time-out and the host-mapped status word
+static double g_timeout_s = 600.0;
+static int* g_status_host = nullptr;
+static int* g_status_dev = nullptr;
+
+static int ensure_status() {
+  if (g_status_host != nullptr) return kOk;
+  DV_CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&g_status_host), 4 * sizeof(int), cudaHostAllocMapped));
+  for (int i = 0; i < 4; ++i) g_status_host[i] = 0;
+  DV_CUDA_OK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_status_dev), g_status_host, 0));
+  return kOk;
+}
+
+void comm_set_timeout(double seconds) { g_timeout_s = seconds > 0.0 ? seconds : 600.0; }
+
+// code: 0 ok, 1 = a peer did not arrive within the time-out, 2 = ranks exchanged different per-rank counts
+int comm_status(int* peer, long long* seq, int clear) {
+  if (g_status_host == nullptr) return 0;
+  const int code = *reinterpret_cast<volatile int*>(g_status_host);
+  if (code != 0) {
+    if (peer) *peer = g_status_host[1];
+    if (seq) *seq = (long long)(((unsigned long long)(unsigned)g_status_host[3] << 32) | (unsigned)g_status_host[2]);
+    if (clear) for (int i = 0; i < 4; ++i) g_status_host[i] = 0;
+  }
+  return code;
+}
+
+static int fill_peers(ArPeers* peers, const long long* peer_ptrs, int world) {
+  for (int i = 0; i < kArMaxWorld; ++i) peers->base[i] = i < world ? (unsigned long long)peer_ptrs[i] : 0ull;
+  if (int rc = ensure_status()) return rc;
+  peers->timeout_ns = (unsigned long long)(g_timeout_s * 1e9);
+  peers->status = g_status_dev;
+  return kOk;
+}
+
 long long small_allreduce_buffer_bytes() {
   return (long long)(2ll * kArMaxWorld * kArMaxElems + 2ll * kArMaxWorld) * 8;
 }
 
 int small_allreduce_f64(double* inout, int n, const long long* peer_ptrs, int rank, int world, long long seq,
                         cudaStream_t stream) {
-  if (n <= 0 || n > kArMaxElems) return fail(kBadArg, "small_allreduce: n must be in 1..%d", kArMaxElems);
+  if (n <= 0 || n >= kArMaxElems) return fail(kBadArg, "small_allreduce: n must be in 1..%d", kArMaxElems - 1);
   if (world < 1 || world > kArMaxWorld || rank < 0 || rank >= world) return fail(kBadArg, "small_allreduce: bad rank/world");
   if (seq < 1) return fail(kBadArg, "small_allreduce: seq starts at 1");
   ArPeers peers;
-  for (int i = 0; i < kArMaxWorld; ++i) peers.base[i] = i < world ? (unsigned long long)peer_ptrs[i] : 0ull;
+  if (int rc = fill_peers(&peers, peer_ptrs, world)) return rc;
   small_allreduce_kernel<<<1, 512, 0, stream>>>(inout, n, peers, rank, world, (unsigned long long)seq);
   DV_LAUNCH_OK();
   return kOk;
 }
 
 static int ar_peers(ArPeers* peers, int n, const long long* peer_ptrs, int rank, int world, long long seq) {
-  if (n <= 0 || n > kArMaxElems) return fail(kBadArg, "peer all-reduce: n must be in 1..%d", kArMaxElems);
+  if (n <= 0 || n >= kArMaxElems) return fail(kBadArg, "peer all-reduce: n must be in 1..%d", kArMaxElems - 1);
   if (world < 1 || world > kArMaxWorld || rank < 0 || rank >= world) return fail(kBadArg, "peer all-reduce: bad rank/world");
   if (seq < 1) return fail(kBadArg, "peer all-reduce: seq starts at 1");
-  for (int i = 0; i < kArMaxWorld; ++i) peers->base[i] = i < world ? (unsigned long long)peer_ptrs[i] : 0ull;
-  return kOk;
+  return fill_peers(peers, peer_ptrs, world);
 }
 
 int bn_finalize_sync(const double* stats, const float* gamma, const float* beta, float* running_mean, float* running_var,

@@ -28,6 +28,12 @@
 
 namespace dv {
 
+#ifdef DV_DIAG
+constexpr bool kDiag = true;    // diagnostics build (libdualvar_b200_diag.so): per-role cycle counters available
+#else
+constexpr bool kDiag = false;   // product build: the counters and their branches are compiled out
+#endif
+
 constexpr int kNumThreads = 320;            // warp 0 TMA, warp 1 MMA, warps 2-5 and 6-9: two epilogue groups
 constexpr int kEpiThreads = 256;
 constexpr int kAStageBytes = kTileM * 128;  // 16 KB
@@ -119,7 +125,7 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
       int stage = 0;
       uint32_t phase = 0;
       long long prof_wait_empty = 0;
-      const long long prof_t0 = p.prof ? clock64() : 0;
+      const long long prof_t0 = (kDiag && p.prof) ? clock64() : 0;
       // this CTA's rows of the weight tile: all of them, or its half of the MMA's N rows in pair mode
       const int bcol = n_tile * p.block_n + (kPair ? (int)rank * (bn_mma / 2) : 0);
       // signals of both CTAs' loads go to the leader's barriers
@@ -147,9 +153,9 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
           const Tap lead = p.taps[gb];
           const uint32_t tx_bytes = p.a_tx_bytes + (p.b_resident ? 0 : len * b_tap_bytes);
           for (int kc = 0; kc < p.k_chunks; ++kc) {
-            const long long c0 = p.prof ? clock64() : 0;
+            const long long c0 = (kDiag && p.prof) ? clock64() : 0;
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            if (p.prof) prof_wait_empty += clock64() - c0;
+            if (kDiag && p.prof) prof_wait_empty += clock64() - c0;
             if (issuer) {
               if (rank == 0) mbar_expect_tx(&full_bar[stage], tx_mult * tx_bytes);
               const uint32_t full_addr = full0_addr + (uint32_t)stage * 8u;
@@ -174,7 +180,7 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
-      if (p.prof && issuer) {
+      if (kDiag && p.prof && issuer) {
         p.prof[blockIdx.x * 16 + 0] = clock64() - prof_t0;   // producer total
         p.prof[blockIdx.x * 16 + 1] = prof_wait_empty;       // producer waiting for a free stage
       }
@@ -188,7 +194,7 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
       uint32_t phase = 0;
       int it = 0;
       long long prof_wait_full = 0, prof_wait_acc = 0;
-      const long long prof_t0 = p.prof ? clock64() : 0;
+      const long long prof_t0 = (kDiag && p.prof) ? clock64() : 0;
       const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO=1024 B, version 1, SWIZZLE_128B
       const uint32_t desc_lo_flags = 1u << 16;                           // LBO field (unused for K-major swizzled)
       const uint32_t ring_enc = smem_u32(ring) >> 4, res_enc = smem_u32(res_b) >> 4;
@@ -201,9 +207,9 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
       for (int tile = unit; tile < p.total_tiles; tile += units, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        const long long ca = p.prof ? clock64() : 0;
+        const long long ca = (kDiag && p.prof) ? clock64() : 0;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
-        if (p.prof) prof_wait_acc += clock64() - ca;
+        if (kDiag && p.prof) prof_wait_acc += clock64() - ca;
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * kMaxBlockN;
         uint32_t accumulate = 0;
@@ -211,9 +217,9 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
         for (int grp = 0; grp < p.num_groups; ++grp) {
           const int len = p.group_len[grp];
           for (int kc = 0; kc < p.k_chunks; ++kc) {
-            const long long cf = p.prof ? clock64() : 0;
+            const long long cf = (kDiag && p.prof) ? clock64() : 0;
             mbar_wait(&full_bar[stage], phase);
-            if (p.prof) prof_wait_full += clock64() - cf;
+            if (kDiag && p.prof) prof_wait_full += clock64() - cf;
             tc_fence_after_sync();
             // descriptor low words (start address >> 4 | LBO field); the high word is a constant
             const uint32_t st_lo = desc_lo_flags | (ring_enc + (uint32_t)stage * stage_enc);
@@ -245,7 +251,7 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
         if (issuer) umma_commit_to<kPair>(&tmem_full_bar[acc]);
         __syncwarp();
       }
-      if (p.prof && issuer) {
+      if (kDiag && p.prof && issuer) {
         p.prof[blockIdx.x * 16 + 2] = clock64() - prof_t0;   // MMA issuer total
         p.prof[blockIdx.x * 16 + 3] = prof_wait_full;        // waiting for TMA data
         p.prof[blockIdx.x * 16 + 4] = prof_wait_acc;         // waiting for the epilogue to free an accumulator
@@ -270,7 +276,7 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
     int it = 0;
     uint32_t obuf = 0;
     long long prof_epi_wait = 0, prof_ld = 0, prof_sts = 0, prof_bar = 0, prof_store = 0, prof_stat = 0, prof_yld = 0;
-    const bool prof_on = p.prof && threadIdx.x == 64;
+    const bool prof_on = kDiag && p.prof && threadIdx.x == 64;
     const long long prof_t0 = prof_on ? clock64() : 0;
     const uint32_t acc_free0 = kPair ? mapa_u32(smem_u32(&tmem_empty_bar[0]), 0) : smem_u32(&tmem_empty_bar[0]);
     for (int tile = unit; tile < p.total_tiles; tile += units, ++it) {
@@ -604,7 +610,9 @@ struct TapSpec {
 using MapEncoder = int (*)(CUtensorMap*, const void* ctx, int view, const uint32_t box[5]);
 
 static long long* g_prof = nullptr;
+#ifdef DV_DIAG
 void set_conv_profile(long long* p) { g_prof = p; }
+#endif
 static int g_halo_enabled = 1;      // DV_CONV_HALO=0 disables tap grouping (A/B testing)
 static int g_resident_enabled = 1;  // DV_CONV_RESIDENT=0 disables weight-stationary CTAs
 static int g_pair_enabled = 1;      // DV_CONV_PAIR=0 disables CTA pairs (cta_group::2)

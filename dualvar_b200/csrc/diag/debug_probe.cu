@@ -1,7 +1,7 @@
 // Debug probe (not on the product path): does TMA accept a tensor map whose dim-1 stride is smaller
 // than the dim-0 extent (overlapping 128-byte windows)? Used to validate the space-to-depth stem.
-#include "host_common.h"
-#include "ptx.cuh"
+#include "../host_common.h"
+#include "../ptx.cuh"
 
 namespace dv {
 

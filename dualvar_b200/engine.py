@@ -15,6 +15,7 @@ Primitive <-> reference op:
 """
 import ctypes
 import os
+import weakref
 
 import torch
 import torch.distributed as dist
@@ -149,22 +150,44 @@ def _fuse_reduce_pays(g):
     return mma_cycles >= 1.5 * epi_cycles
 
 
+def _cache_get(key, w, ver):
+    """Cached entry for parameter ``w`` under ``key``, or None. An entry belongs to one live parameter object: it
+    holds a weak reference to it and is dropped when the parameter is freed, so a new model whose parameters reuse
+    the ids / addresses of a deleted one (CPython and the caching allocator both recycle) never sees its packs."""
+    hit = _weight_cache.get(key)
+    if hit is not None and hit[0]() is w and hit[1] == ver:
+        return hit[2]
+    return None
+
+
+def _cache_put(key, w, ver, payload):
+    if key not in _weight_cache or _weight_cache[key][0]() is not w:
+        weakref.finalize(w, _cache_drop, key, id(w))
+    _weight_cache[key] = (weakref.ref(w), ver, payload)
+
+
+def _cache_drop(key, wid):
+    hit = _weight_cache.get(key)
+    if hit is not None and hit[0]() is None:      # not already replaced by a live parameter with the same id
+        _weight_cache.pop(key, None)
+
+
 def packed_weights(conv):
     """bf16 packed copies of a conv weight, refreshed when the fp32 parameter changes
     (optimizer.step() bumps Tensor._version)."""
     w = conv.weight
     key = id(w)
     ver = (w._version, w.data_ptr())
-    hit = _weight_cache.get(key)
-    if hit is not None and hit[0] == ver:
-        _after_pack(hit[3])
-        return hit[1], hit[2]
+    hit = _cache_get(key, w, ver)
+    if hit is not None:
+        _after_pack(hit[2])
+        return hit[0], hit[1]
     Cout, Cin, kt, kh, kw = w.shape
     g = make_geom(1, kt, kh, kw, Cin, Cout, (kt, kh, kw), (1, 1, 1), (0, 0, 0))
     wf = torch.empty((g.Cout_p, g.taps, g.Cin_p), dtype=torch.bfloat16, device=w.device)
     wt = torch.empty((g.Cin_p, g.taps, g.Cout_p), dtype=torch.bfloat16, device=w.device)
     call("dv_pack_conv_weight", ptr(w.detach()), ptr(wf), ptr(wt), ctypes.byref(g), stream_ptr())
-    _weight_cache[key] = (ver, wf, wt, _pack_mark())
+    _cache_put(key, w, ver, (wf, wt, _pack_mark()))
     return wf, wt
 
 
@@ -185,10 +208,10 @@ def invalidate_weights(params):
     """Drop cached packed copies of parameters that were modified through raw pointers (kernels do not
     bump Tensor._version)."""
     for p in params:
-        _weight_cache.pop(id(p), None)
-        _weight_cache.pop(("stem", id(p)), None)
-        _weight_cache.pop(("f32", id(p)), None)
-        _weight_cache.pop(("f32stem", id(p)), None)
+        for key in (id(p), ("stem", id(p)), ("f32", id(p)), ("f32stem", id(p))):
+            hit = _weight_cache.get(key)
+            if hit is not None:      # keep the weak reference (and its finalizer), drop version and payload
+                _weight_cache[key] = (hit[0], None, None)
 
 
 def packed_stem_weights(conv, g):
@@ -196,13 +219,13 @@ def packed_stem_weights(conv, g):
     w = conv.weight
     key = ("stem", id(w))
     ver = (w._version, w.data_ptr())
-    hit = _weight_cache.get(key)
-    if hit is not None and hit[0] == ver:
-        _after_pack(hit[2])
-        return hit[1]
+    hit = _cache_get(key, w, ver)
+    if hit is not None:
+        _after_pack(hit[1])
+        return hit[0]
     ws = torch.empty((g.Cout_p, g.kt * 4, 64), dtype=torch.bfloat16, device=w.device)
     call("dv_pack_stem_weight", ptr(w.detach()), ptr(ws), ctypes.byref(g), stream_ptr())
-    _weight_cache[key] = (ver, ws, _pack_mark())
+    _cache_put(key, w, ver, (ws, _pack_mark()))
     return ws
 
 
@@ -219,10 +242,10 @@ def packed_weight_planes(conv):
     K = F32_PLANES
     key = ("f32", id(w))
     ver = (w._version, w.data_ptr(), K)
-    hit = _weight_cache.get(key)
-    if hit is not None and hit[0] == ver:
-        _after_pack(hit[2])
-        return hit[1]
+    hit = _cache_get(key, w, ver)
+    if hit is not None:
+        _after_pack(hit[1])
+        return hit[0]
     Cout, Cin, kt, kh, kw = w.shape
     g = make_geom(1, kt, kh, kw, Cin, Cout, (kt, kh, kw), (1, 1, 1), (0, 0, 0))
     planes = _split_weight(w, K)
@@ -232,7 +255,7 @@ def packed_weight_planes(conv):
         wt = torch.empty((g.Cin_p, g.taps, g.Cout_p), dtype=torch.bfloat16, device=w.device)
         call("dv_pack_conv_weight", ptr(planes[k]), ptr(wf), ptr(wt), ctypes.byref(g), stream_ptr())
         out.append((wf, wt))
-    _weight_cache[key] = (ver, out, _pack_mark())
+    _cache_put(key, w, ver, (out, _pack_mark()))
     return out
 
 
@@ -242,17 +265,17 @@ def packed_stem_weight_planes(conv, g):
     K = F32_PLANES
     key = ("f32stem", id(w))
     ver = (w._version, w.data_ptr(), K)
-    hit = _weight_cache.get(key)
-    if hit is not None and hit[0] == ver:
-        _after_pack(hit[2])
-        return hit[1]
+    hit = _cache_get(key, w, ver)
+    if hit is not None:
+        _after_pack(hit[1])
+        return hit[0]
     planes = _split_weight(w, K)
     out = []
     for k in range(K):
         ws = torch.empty((g.Cout_p, g.kt * 4, 64), dtype=torch.bfloat16, device=w.device)
         call("dv_pack_stem_weight", ptr(planes[k]), ptr(ws), ctypes.byref(g), stream_ptr())
         out.append((ws, None))
-    _weight_cache[key] = (ver, out, _pack_mark())
+    _cache_put(key, w, ver, (out, _pack_mark()))
     return out
 
 

@@ -17,11 +17,22 @@ _CHUNK = 8192
 
 
 class SGD(torch.optim.Optimizer):
-    def __init__(self, params, lr, momentum=0.0, weight_decay=0.0):
+    def __init__(self, params, lr, momentum=0.0, weight_decay=0.0, dampening=0.0, nesterov=False, maximize=False):
         if lr < 0.0:
             raise ValueError(f"Invalid learning rate: {lr}")
-        super().__init__(params, dict(lr=lr, momentum=momentum, weight_decay=weight_decay))
+        # the full torch.optim.SGD group layout, so state_dict() loads into torch.optim.SGD and back
+        # (checkpoint interchange with the reference, pretrain.py:262-272, :301); the kernel implements the
+        # reference's setting of the three extra knobs only
+        super().__init__(params, dict(lr=lr, momentum=momentum, dampening=dampening, weight_decay=weight_decay,
+                                      nesterov=nesterov, maximize=maximize, foreach=None, differentiable=False,
+                                      fused=None))
         self._tables = {}
+
+    @staticmethod
+    def _check_group(group):
+        if group.get("dampening", 0.0) != 0.0 or group.get("nesterov", False) or group.get("maximize", False):
+            raise _lib.DualVarNativeError("dualvar_b200.optim.SGD implements dampening=0, nesterov=False, maximize=False "
+                                          "(the reference's optimizer, pretrain.py:272)")
 
     def _table(self, key, plist):
         sig = tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["momentum_buffer"].data_ptr(), p.numel())
@@ -44,6 +55,7 @@ class SGD(torch.optim.Optimizer):
                 loss = closure()
         batches = {}
         for group in self.param_groups:
+            self._check_group(group)
             for p in group["params"]:
                 if p.grad is None:
                     continue

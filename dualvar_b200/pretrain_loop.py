@@ -144,4 +144,8 @@ def fit(model, loader, optimizer, epochs, schedule=(), start_epoch=0, model_path
                      "optimizer": optimizer.state_dict(), "iteration": iteration}
             save_checkpoint(state, is_best, os.path.join(model_path, "epoch%d.pth.tar" % epoch),
                             is_save=((epoch + 1) % save_freq == 0))
+        if model_path and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            # rank 0 may spend seconds writing checkpoints: the other ranks wait here (host side) instead of inside
+            # the first cross-replica BatchNorm exchange of the next epoch
+            dist.barrier()
     return history, best_acc, iteration

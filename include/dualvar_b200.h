@@ -241,15 +241,14 @@ int dv_bn_finalize_sync(const double* stats, const float* gamma, const float* be
 int dv_bn_bwd_finalize_sync(const double* sums_local, const float* gamma, const float* saved, float* dgamma,
                             float* dbeta, float* coef, int C, int Cp, double count_global, float grad_beta,
                             const int64_t* peer_buffers, int rank, int world, int64_t seq, void* stream);
+/* Failure reporting of the peer exchange (NCCL's watchdog / ProcessGroup error state on the reference path):
+ * a rank that waits longer than the time-out (default 600 s) for a peer, or whose peers exchanged a different
+ * per-rank BatchNorm count, records the fact in a host-mapped word and returns - the context is not destroyed.
+ * dv_comm_status returns 0 (ok), 1 (time-out) or 2 (unequal per-rank counts) and the peer / call number involved
+ * (NULL = not wanted); clear != 0 resets it. */
+int dv_comm_set_timeout(double seconds);
+int dv_comm_status(int* peer, int64_t* seq, int clear);
 
-/* debug (tests/diag only): per-CTA role cycle counters of the next conv_tile_kernel launches are written to
- * buf [148][16] (producer total/wait, MMA total/wait-data/wait-accumulator, epilogue total/wait, tiles, epilogue phases); NULL = off */
-int dv_debug_set_conv_profile(int64_t* buf);
-/* debug probe (tests only): TMA tensor map with overlapping windows */
-int dv_debug_probe_overlap_tmap(const void* src, void* out, int c1, void* stream);
-/* debug microbenchmark (tests/diag/mma_rate.py): cycles for n_mma back-to-back tcgen05.mma M=128 N=n K=16 (bf16,
- * shared-memory operands cycling through region_bytes) per CTA -> cycles[grid][2] = (issue, completion) */
-int dv_debug_mma_rate(int n, int n_mma, int region_bytes, int mode, int64_t* cycles, int grid, void* stream);
 
 /* ---- fp32 mode ("1e-4 mode") ----------------------------------------------------------------
  * Activations and gradients are fp32 NDHWC [N][T][H][W][Cp]; every conv operand is also kept as n_planes (1..3)

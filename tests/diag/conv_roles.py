@@ -1,8 +1,12 @@
 """GPU diagnostic: where do the producer / MMA / epilogue roles of conv_tile_kernel spend their cycles?"""
 import os, sys, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+# the dv_debug_* entry points live in the diagnostics build only (`make diag`)
+os.environ.setdefault("DV_LIB_PATH", os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "dualvar_b200", "lib", "libdualvar_b200_diag.so"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # tests helpers (kernel_handles)
 import torch
-from dualvar_b200 import _lib, kernels as K
+from dualvar_b200 import _lib
+import kernel_handles as K
 dev = "cuda:0"
 N = int(os.environ.get("NCLIPS", "96"))
 LAYERS = [("fprop temporal 144->64", "f", (N, 16, 56, 56, 144, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0))),

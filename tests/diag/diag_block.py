@@ -1,7 +1,9 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # tests helpers (kernel_handles)
 import torch, torch.nn as nn, torch.nn.functional as F
-from dualvar_b200 import engine as E, kernels as K
+from dualvar_b200 import engine as E
+import kernel_handles as K
 torch.backends.cudnn.allow_tf32 = False
 dev = "cuda:0"
 gen = torch.Generator(device=dev).manual_seed(4)

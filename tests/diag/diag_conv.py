@@ -2,9 +2,10 @@
 error summaries against torch fp32 conv on bf16-rounded operands. Usage: python tests/diag/diag_conv.py"""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # tests helpers (kernel_handles)
 import torch
 import torch.nn.functional as F
-from dualvar_b200 import kernels as K
+import kernel_handles as K
 
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False

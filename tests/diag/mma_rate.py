@@ -2,6 +2,8 @@
 kernels live under. Ideal = N/2 cycles per MMA (8192 MAC/clk/SM)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+# the dv_debug_* entry points live in the diagnostics build only (`make diag`)
+os.environ.setdefault("DV_LIB_PATH", os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "dualvar_b200", "lib", "libdualvar_b200_diag.so"))
 import torch
 from dualvar_b200 import _lib
 dev = "cuda:0"

@@ -2,8 +2,10 @@
 conv fprop / dgrad / wgrad 64->144 3x3 and the three BatchNorm passes on 9.63 M x 144. First a warm-up of each."""
 import os, sys, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # tests helpers (kernel_handles)
 import torch
-from dualvar_b200 import _lib, kernels as K
+from dualvar_b200 import _lib
+import kernel_handles as K
 from dualvar_b200._lib import ptr, call, stream_ptr
 dev = "cuda:0"
 n, t, h, w, ci, co = 192, 16, 56, 56, 64, 144

@@ -1,8 +1,10 @@
 """GPU diagnostic: do a conv_tile_kernel launch (one stream) and a BatchNorm pass (another stream) overlap on B200?"""
 import os, sys, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # tests helpers (kernel_handles)
 import torch
-from dualvar_b200 import _lib, kernels as K
+from dualvar_b200 import _lib
+import kernel_handles as K
 from dualvar_b200._lib import ptr, call
 dev = "cuda:0"
 n, t, h, w, ci, co = 96, 16, 56, 56, 64, 144

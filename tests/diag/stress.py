@@ -1,8 +1,9 @@
 """GPU stress: loop each conv kernel on a small geometry, compare every iteration with the first."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # tests helpers (kernel_handles)
 import torch
-from dualvar_b200 import kernels as K
+import kernel_handles as K
 dev = "cuda:0"
 which = sys.argv[1]
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 300

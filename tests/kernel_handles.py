@@ -1,4 +1,6 @@
-"""Python-side handles on the C-ABI kernels: allocate outputs with torch, pass raw pointers.
+"""TEST HELPERS (not product code): Python-side handles on single C-ABI kernels for the unit tests and tests/diag -
+allocate outputs with torch, pass raw pointers. The product path calls the C ABI from dualvar_b200/engine.py,
+objectives.py and frames.py directly; nothing under dualvar_b200/ imports this module.
 
 torch is used for device memory and streams only; every arithmetic op below is a kernel from
 dualvar_b200/csrc launched through the C ABI (include/dualvar_b200.h).
@@ -7,8 +9,8 @@ import ctypes
 
 import torch
 
-from . import _lib
-from ._lib import ConvGeom, make_geom, pad8, ptr, stream_ptr  # noqa: F401
+from dualvar_b200 import _lib
+from dualvar_b200._lib import ConvGeom, make_geom, pad8, ptr, stream_ptr  # noqa: F401
 
 
 def _require_cuda(t, name):

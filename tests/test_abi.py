@@ -12,8 +12,8 @@ from dualvar_b200 import _lib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared():
-    text = open(os.path.join(ROOT, "include", "dualvar_b200.h")).read()
+def _declared(header="dualvar_b200.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
     return sorted(set(re.findall(r"\b(dv_[a-z0-9_]+)\s*\(", text)))
 
@@ -25,6 +25,32 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
     assert sorted(_lib.exported_symbols()) == names
+
+
+def test_diagnostics_live_in_their_own_library():
+    """The product library exports no dv_debug_* symbol; the diagnostics build (make diag) exports the product ABI plus
+    everything include/dualvar_b200_diag.h declares."""
+    lib = _lib.load()
+    dbg = [n for n in _declared("dualvar_b200_diag.h") if n.startswith("dv_debug_")]
+    assert len(dbg) >= 3
+    for n in dbg:
+        assert not hasattr(lib, n), f"{n} must not be in the product library"
+    path = os.path.join(ROOT, "dualvar_b200", "lib", "libdualvar_b200_diag.so")
+    if not os.path.exists(path):
+        pytest.skip("diagnostics library not built (make diag)")
+    diag = ctypes.CDLL(path)
+    for n in dbg + _declared():
+        assert hasattr(diag, n), n
+
+
+def test_comm_status_word_starts_clean_and_timeout_is_settable():
+    """dv_comm_status / dv_comm_set_timeout (peer-exchange failure reporting) work without a GPU: no exchange has run, so
+    the status is 0 and asking for it allocates nothing."""
+    lib = _lib.load()
+    peer, seq = ctypes.c_int(7), ctypes.c_int64(7)
+    assert lib.dv_comm_set_timeout(ctypes.c_double(12.5)) == 0
+    assert lib.dv_comm_status(ctypes.byref(peer), ctypes.byref(seq), 1) == 0
+    assert lib.dv_comm_set_timeout(ctypes.c_double(600.0)) == 0
 
 
 def test_version_and_error_string():

@@ -36,7 +36,7 @@ def _rel(a, b):
 
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_conv_trio_matches_torch(case):
-    from dualvar_b200 import kernels as K
+    import kernel_handles as K
     torch.backends.cudnn.allow_tf32 = False
     name, N, T, H, W, Cin, Cout, k, s, p = case
     dev = "cuda:0"
@@ -79,7 +79,8 @@ def test_dgrad_fused_bn_reduce(case, relu):
     """dv_conv3d_dgrad_bnred_bf16: dx bit-identical to the plain dgrad, and the epilogue's sum(g), sum(g*y)
     equal to dv_bn_bwd_reduce run on that dx (and to a torch fp64 evaluation of the same sums)."""
     import ctypes
-    from dualvar_b200 import _lib, kernels as K
+    from dualvar_b200 import _lib
+    import kernel_handles as K
     name, N, T, H, W, Cin, Cout, k, s, p = case
     dev = "cuda:0"
     g = K.make_geom(N, T, H, W, Cin, Cout, k, s, p)
@@ -114,7 +115,7 @@ def test_dgrad_fused_bn_reduce(case, relu):
 def test_conv_linearity_at_full_size():
     """BASELINE-size property check (no oracle at this size): conv(a*x1 + x2) with power-of-two a is
     exactly a*conv(x1) + conv(x2) up to bf16 rounding of the stored outputs; pad channels stay zero."""
-    from dualvar_b200 import kernels as K
+    import kernel_handles as K
     dev = "cuda:0"
     g = K.make_geom(16, 16, 56, 56, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1))
     gen = torch.Generator(device=dev).manual_seed(3)
@@ -130,7 +131,8 @@ def test_conv_linearity_at_full_size():
 def test_space_to_depth_stem_matches_torch(kt, pt, Cout, H, W):
     """Stride-2 7x7 stem on the space-to-depth ingest (overlapping-window TMA map) vs torch conv3d."""
     import ctypes
-    from dualvar_b200 import _lib, engine as E, kernels as K
+    from dualvar_b200 import _lib, engine as E
+    import kernel_handles as K
     torch.backends.cudnn.allow_tf32 = False
     dev = "cuda:0"
     N, T = 5, 4        # 48x64 frames -> 24x32 map: the two-region tiling path

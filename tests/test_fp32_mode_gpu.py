@@ -81,7 +81,7 @@ def test_conv_trio_fp32_mode_matches_fp64(case, K, tol):
     output range). 3 planes: fp32-level (5e-6: fp32 accumulation over up to 2592 terms, measured 3.4e-6); 2 planes:
     16 mantissa bits (4e-5)."""
     from dualvar_b200 import _lib, engine as E
-    from dualvar_b200 import kernels as KK
+    import kernel_handles as KK
     E.set_precision("fp32", planes=K)
     name, N, T, H, W, Cin, Cout, k, s, p = case
     g = KK.make_geom(N, T, H, W, Cin, Cout, k, s, p)

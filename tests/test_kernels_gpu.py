@@ -188,7 +188,7 @@ def test_conv_bn_relu_residual_block_forward_backward():
     yr.backward(gy)
 
     ctx = E.Context(training=True)
-    from dualvar_b200 import kernels as K
+    import kernel_handles as K
     xa = E.Act(K.to_ndhwc(x), C)
     out = E.activate(ctx, E.conv_stats(ctx, xa, conv, bn), res=xa)
     y = K.from_ndhwc(out.data, C)
@@ -207,7 +207,8 @@ def test_conv_bn_relu_residual_block_forward_backward():
 
 
 def test_maxpool_forward_backward_matches_torch():
-    from dualvar_b200 import engine as E, kernels as K
+    from dualvar_b200 import engine as E
+    import kernel_handles as K
     gen = torch.Generator(device=dev).manual_seed(5)
     for kernel, stride, pad in [((1, 2, 2), (1, 2, 2), (0, 0, 0)), ((2, 2, 2), (2, 2, 2), (0, 0, 0)),
                                 ((3, 3, 3), (1, 1, 1), (1, 1, 1)), ((1, 3, 3), (1, 2, 2), (0, 1, 1)),
@@ -230,7 +231,8 @@ def test_maxpool_backward_tie_rule_matches_torch():
     """ReLU'd inputs are full of exact ties (zeros): the gradient must go to the FIRST maximum of each window in
     (t,h,w) scan order, as ATen's max_pool3d does - for the recorded-argmax path and the re-scanning C-ABI entry."""
     import ctypes
-    from dualvar_b200 import _lib, engine as E, kernels as K
+    from dualvar_b200 import _lib, engine as E
+    import kernel_handles as K
     gen = torch.Generator(device=dev).manual_seed(6)
     for kernel, stride, pad in [((3, 3, 3), (1, 1, 1), (1, 1, 1)), ((1, 3, 3), (1, 2, 2), (0, 1, 1))]:
         x = torch.relu(torch.randn(2, 16, 5, 12, 11, device=dev, generator=gen) - 0.8).bfloat16().float()

@@ -266,7 +266,8 @@ def test_linear_classifier_matches_oracle(kw):
 def test_error_behaviour_matches_reference_asserts():
     """The reference's input checks (model/simclr.py:346,351; model/moco.py:347) and the C ABI's status codes."""
     import ctypes
-    from dualvar_b200 import _lib, models as PM, kernels as K
+    from dualvar_b200 import _lib, models as PM
+    import kernel_handles as K
     dev = "cuda:0"
     args = SimpleNamespace(shufflerank_theta=0.05)
     m = PM.SimCLR_TimeSeriesV4("r21d", 128, 0.07, False, True, 2, 64, 0.07, 0.07, "clip-sr-tc", args).to(dev)

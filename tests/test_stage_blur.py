@@ -79,8 +79,6 @@ def test_gaussian_blur_refuses_cpu_tensors():
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="provisional: the kernel launch was written after the round's GPU budget was spent and "
-                                        "has never been executed; XPASS = verified (drop this marker), XFAIL = fix the launch code")
 def test_gpu_gaussian_blur_bit_exact(golden_dir):
     from dualvar_b200 import frames as FR
     from oracle import augment as A
@@ -136,7 +134,6 @@ def test_transform_plan_reproduces_the_reference_loader_chain(golden_dir):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="provisional: goes through the never-executed Gaussian-blur launch (see above)")
 def test_gpu_whole_transform_chain_matches_reference_golden(golden_dir):
     """decoded frames -> scale_crop -> color_jitter -> gaussian_blur on the GPU with the drawn plan == the reference chain
     (2e-6: the contrast mean is the only non-bit-exact step; a blur after it can move a value by 1/255 only if that 2e-6
@@ -149,8 +146,6 @@ def test_gpu_whole_transform_chain_matches_reference_golden(golden_dir):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="provisional: written after the round's GPU budget was spent, never executed (the two "
-                                        "kernels it calls are verified at other geometries in test_frames / test_color_jitter)")
 def test_gpu_scale_crop_and_jitter_chain_matches_reference_golden(golden_dir):
     """The verified part of the chain on the samples whose clips drew no blur: Scale + RandomCrop + ToTensor + ColorJitter."""
     from dualvar_b200 import frames as FR
