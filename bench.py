@@ -76,14 +76,28 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------------------- reference arm
-def oracle_step_fn(batch, threads):
-    """The CPU port of the reference step (oracle/, fp32, oneDNN) — the reference itself is Python +
-    torch and is not shipped to the GPU box; oracle/ restates it and is pinned to it by tests/golden."""
+REF_SAMPLE = 4      # samples per CPU step (B = 4, the configs[0] batch)
+
+
+def reference_modules(cpu):
+    """(model package, kind): the UNMODIFIED reference installed under baseline/_ref by oracle/install_reference.py
+    (kind "reference"), else the oracle/ restatement of it (kind "port"; pinned to the reference by tests/golden)."""
+    from oracle import install_reference as IR
+    if IR.available() and IR.verify():
+        ref_model, _, _ = IR.import_reference(cpu=cpu)
+        return ref_model, "reference"
     from oracle import models as OM
+    return OM, "port"
+
+
+def reference_step_fn(batch, threads):
+    """One pretraining step of the reference on the host CPU exactly as pretrain.py:386-451 runs it (Normalize +
+    view/transpose, model forward, four-loss sum, backward, SGD with one group per tensor), fp32, oneDNN."""
     torch.set_num_threads(threads)
+    M, kind = reference_modules(cpu=True)
     seed_all(0)
-    model = OM.SimCLR_TimeSeriesV4("r21d", 128, 0.07, False, True, 2, 64, 0.07, 0.07, "clip-sr-tc",
-                                   SimpleNamespace(shufflerank_theta=0.05)).train()
+    model = M.SimCLR_TimeSeriesV4("r21d", 128, 0.07, False, True, 2, 64, 0.07, 0.07, "clip-sr-tc",
+                                  SimpleNamespace(shufflerank_theta=0.05)).train()
     opt = torch.optim.SGD([{"params": p} for p in model.parameters()], lr=0.003, weight_decay=1e-4, momentum=0.9)
     mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1, 1)
     std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1, 1)
@@ -98,7 +112,7 @@ def oracle_step_fn(batch, threads):
         opt.step()
         return float(loss.detach())
 
-    return step
+    return step, kind
 
 
 def run_reference(args):
@@ -106,8 +120,8 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = 2
-    step = oracle_step_fn(sample, cores)
+    sample = REF_SAMPLE
+    step, kind = reference_step_fn(sample, cores)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -115,17 +129,134 @@ def run_reference(args):
         step()
     dt = (time.perf_counter() - t0) / args.steps
     value = sample / dt
+    what = ("the unmodified reference modules (baseline/_ref: backbone/, model/, utils/ of lzhangbj/DualVar)" if kind == "reference"
+            else "oracle/ port of the reference step (baseline/_ref not installed)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, sample),
-        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} samples/step (6 input clips, 8 clip-passes) of the same workload, "
-                                   f"oracle/ port of the reference step on the host CPU"},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": kind,
+                         "sample": f"{sample} samples/step (12 input clips, 16 clip-passes) of the same workload on the "
+                                   f"host CPU, fp32 oneDNN, {torch.get_num_threads()} threads: {what}"},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def run_torch_gpu(args):
+    """Internal leg (--impl torch-gpu, spawned by the N = 1 run): the same step through the reference's own torch modules
+    on THIS B200 - cuDNN / cuBLAS, no dualvar_b200 code - in fp32 (TF32 off) and under bf16 autocast with channels_last_3d
+    + cudnn.benchmark. SURVEY.md 8(d) calls this "the honest bar on the same box". Prints one JSON object."""
+    dev = torch.device("cuda", 0)
+    M, kind = reference_modules(cpu=False)
+    B = args.batch
+    out = {"kind": kind, "samples_per_step": B, "unit": "samples/s",
+           "what": "reference torch modules on the same B200 through cuDNN (no dualvar_b200 kernels), full step "
+                   "(Normalize, forward, 4 losses, backward, SGD), inputs resident"}
+    mean = torch.tensor([0.485, 0.456, 0.406], device=dev).view(1, 3, 1, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225], device=dev).view(1, 3, 1, 1, 1)
+    frames = torch.rand(B, 3, 48, 112, 112, device=dev, generator=torch.Generator(device=dev).manual_seed(1234))
+    for tag in ("bf16_autocast_channels_last", "fp32_tf32_off"):
+        try:
+            fp32 = tag.startswith("fp32")
+            torch.backends.cudnn.allow_tf32 = not fp32
+            torch.backends.cuda.matmul.allow_tf32 = not fp32
+            torch.backends.cudnn.benchmark = not fp32
+            seed_all(0)
+            model = M.SimCLR_TimeSeriesV4("r21d", 128, 0.07, False, True, 2, 64, 0.07, 0.07, "clip-sr-tc",
+                                          SimpleNamespace(shufflerank_theta=0.05)).to(dev).train()
+            if not fp32:
+                model = model.to(memory_format=torch.channels_last_3d)
+            opt = torch.optim.SGD([{"params": p} for p in model.parameters()], lr=0.003, weight_decay=1e-4, momentum=0.9)
+
+            def step():
+                x = ((frames - mean) / std).view(B, 3, 3, 16, 112, 112).transpose(1, 2).contiguous()
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=not fp32):
+                    ret = model(x)
+                loss = sum(v.float() for k, v in ret.items() if "loss" in k)
+                opt.zero_grad(set_to_none=True)
+                loss.backward()
+                opt.step()
+                return loss
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+            n = 3 if fp32 else 6
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                loss = step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / n
+            out[tag] = {"value": B / (ms / 1e3), "ms_per_step": ms, "steps": n, "final_loss": float(loss.detach())}
+            del model, opt
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            out[tag] = {"error": f"{type(e).__name__}: {e}"}
+    print("TORCH_GPU_JSON " + json.dumps(out), flush=True)
+
+
+def _spawn_leg(impl, extra, marker, timeout):
+    """Run another leg of this script in a fresh process (the reference needs ``Tensor.cuda`` patched on the CPU, and its
+    top-level package names - model, utils - must not leak into this process); returns its JSON object or an error dict."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", impl] + extra
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
+        for ln in reversed(r.stdout.splitlines()):
+            if marker is None and ln.startswith("{"):
+                return json.loads(ln)
+            if marker is not None and ln.startswith(marker):
+                return json.loads(ln[len(marker):])
+        return {"error": f"leg {impl}: no JSON (rc {r.returncode}): {(r.stderr or r.stdout)[-300:]}"}
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"leg {impl}: {type(e).__name__}: {e}"}
+
+
+NCU_TRAFFIC = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+
+
+def ncu_traffic():
+    """Per-layer / per-kernel DRAM bytes from this round's ncu capture (tests/diag/ncu_step.py), or None."""
+    if os.path.exists(NCU_TRAFFIC):
+        try:
+            return json.load(open(NCU_TRAFFIC))
+        except Exception:  # noqa: BLE001
+            return None
+    return None
+
+
+def layer_table(lsum, steps, peaks):
+    """Per layer (entry point + geometry): launches and time per step, algorithmic FLOPs and bytes per launch, achieved
+    TFLOP/s and GB/s on the algorithmic figures, and - when this round's ncu capture has the layer - the DRAM bytes per
+    launch next to them (dram / algorithmic > 1 = re-reads)."""
+    tr = ncu_traffic() or {}
+    per_layer = tr.get("layers", {})
+    rows = []
+    for key, d in lsum.items():
+        n = d["calls"]
+        if n == 0 or d["ms"] <= 0:
+            continue
+        ms = d["ms"] / n
+        row = {"layer": key, "launches_per_step": n / steps, "ms_per_launch": ms, "ms_per_step": d["ms"] / steps}
+        if d["flops"] > 0:
+            row["gflop_per_launch"] = d["flops"] / n / 1e9
+            row["tflops"] = d["flops"] / n / (ms * 1e-3) / 1e12
+            row["frac_of_bf16_peak"] = row["tflops"] / peaks["bf16_tflops"]
+        if d.get("bytes", 0) > 0:
+            row["algorithmic_bytes_per_launch"] = d["bytes"] / n
+            row["algorithmic_gbs"] = d["bytes"] / n / (ms * 1e-3) / 1e9
+            row["frac_of_hbm_peak"] = row["algorithmic_gbs"] / peaks["hbm_gbs"]
+        t = per_layer.get(key)
+        if t:
+            row["dram_bytes_per_launch"] = t["dram_bytes_per_launch"]
+            if row.get("algorithmic_bytes_per_launch"):
+                row["dram_over_algorithmic"] = t["dram_bytes_per_launch"] / row["algorithmic_bytes_per_launch"]
+        rows.append(row)
+    rows.sort(key=lambda r: -r["ms_per_step"])
+    return rows
 
 
 def workload_config(args, batch):
@@ -174,6 +305,81 @@ def fp32_mode_leg(dev, host_frames, steps=3, batch=16):
         return {"error": f"{type(e).__name__}: {e}"}
     finally:
         E.set_precision("bf16")
+
+
+def other_configs_leg(dev):
+    """Side figures for the other BASELINE.json configurations (each parity-tested in tests/test_parity_configs_gpu.py and
+    tests/test_retrieval_gpu.py): full pretraining steps with resident inputs, and the retrieval maths."""
+    from dualvar_b200 import models as PM, retrieval as R
+    from dualvar_b200.engine import RawClips
+    from dualvar_b200.optim import SGD
+    out = {}
+    a = SimpleNamespace(shufflerank_theta=0.05)
+
+    def time_step(model, make_input, batch, n=4):
+        opt = SGD([{"params": p} for p in model.parameters() if p.requires_grad], lr=0.003, weight_decay=1e-4, momentum=0.9)
+        nl0 = [0]
+
+        def st():
+            ret = model(make_input())
+            loss = sum(v for k, v in ret.items() if "loss" in k)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+            return loss
+        for _ in range(2):
+            st()
+        torch.cuda.synchronize()
+        from dualvar_b200 import _lib
+        nl0[0] = _lib.load().dv_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            loss = st()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        return {"value": batch / (ms / 1e3), "unit": "samples/s", "ms_per_step": ms, "samples_per_gpu": batch, "steps": n,
+                "gpu_launches_per_step": (_lib.load().dv_launch_count() - nl0[0]) / n, "final_loss": float(loss.detach())}
+
+    try:
+        seed_all(0)
+        B = 64
+        m = PM.MoCo_TimeSeriesV4("r21d", 128, 16384, 0.999, 0.07, False, True, 2, 64, 0.07, 0.07, "clip-sr-tc", a).to(dev).train()
+        frames = torch.rand(B, 3, 48, 112, 112, device=dev)
+        out["configs[2] MoCo+DualVar r21d K=16384 m=0.999 16x112^2"] = time_step(m, lambda: RawClips(frames, 3), B)
+        del m, frames
+    except Exception as e:  # noqa: BLE001
+        out["configs[2]"] = {"error": f"{type(e).__name__}: {e}"}
+    torch.cuda.empty_cache()
+    try:
+        seed_all(0)
+        B = 16
+        m = PM.SimCLR_TimeSeriesV4("s3dg", 128, 0.07, False, True, 2, 64, 0.07, 0.07, "clip-sr-tc", a).to(dev).train()
+        frames = torch.rand(B, 3, 96, 128, 128, device=dev)
+        out["configs[3] S3D-G SimCLR+DualVar 32x128^2"] = time_step(m, lambda: RawClips(frames, 3), B, n=3)
+        del m, frames
+    except Exception as e:  # noqa: BLE001
+        out["configs[3]"] = {"error": f"{type(e).__name__}: {e}"}
+    torch.cuda.empty_cache()
+    try:
+        test = torch.randn(3783, 512, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
+        train = torch.randn(9537, 512, device=dev, generator=torch.Generator(device=dev).manual_seed(8))
+        for _ in range(2):
+            R.retrieval_topk(test, train)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            R.retrieval_topk(test, train)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        out["configs[4] retrieval 3783 x 9537 x 512 (centre, normalise, fp64 similarity, top-1/5/10/20/50)"] = {
+            "value": 3783 / (ms / 1e3), "unit": "queries/s", "ms": ms}
+    except Exception as e:  # noqa: BLE001
+        out["configs[4]"] = {"error": f"{type(e).__name__}: {e}"}
+    return out
 
 
 # --------------------------------------------------------------------------------------- our arm
@@ -275,13 +481,22 @@ def run_ours(args):
     side_was, pass_was = _engine.WGRAD_SIDE_STREAM, _engine.PASS_STREAMS
     _engine.WGRAD_SIDE_STREAM = False
     _engine.PASS_STREAMS = False
-    timer = _lib.KernelTimer(["dv_conv3d_fprop_bf16", "dv_conv3d_dgrad_bf16", "dv_conv3d_dgrad_bnred_bf16", "dv_conv3d_wgrad_bf16",
-                              "dv_conv3d_stem_fprop_bf16", "dv_conv3d_stem_wgrad_bf16"])
+    conv_names = ["dv_conv3d_fprop_bf16", "dv_conv3d_dgrad_bf16", "dv_conv3d_dgrad_bnred_bf16", "dv_conv3d_wgrad_bf16",
+                  "dv_conv3d_stem_fprop_bf16", "dv_conv3d_stem_wgrad_bf16"]
+    bn_names = ["dv_bn_apply", "dv_bn_bwd_reduce", "dv_bn_bwd_apply"]
+    timer = _lib.KernelTimer(conv_names + bn_names, detail=True)
     _lib.set_timer(timer)
     ms_step_serial = timed(args.steps, False, 0)
     _lib.set_timer(None)
     _engine.WGRAD_SIDE_STREAM, _engine.PASS_STREAMS = side_was, pass_was
-    ksum = timer.summary()
+    lsum = timer.summary()                      # per layer: "<entry point> <geometry>" -> calls, ms, flops, bytes
+    ksum = {}
+    for key, d in lsum.items():
+        name = key.split(" ")[0]
+        if name in conv_names:
+            k = ksum.setdefault(name, {"calls": 0, "ms": 0.0, "flops": 0.0})
+            for f in ("calls", "ms", "flops"):
+                k[f] += d[f]
     # end-to-end: host buffers, H2D of every step's input inside the timed region (double-buffered on a
     # copy stream), D2H of the loss every step
     for i in range(2):
@@ -352,17 +567,20 @@ def run_ours(args):
         roof = None
         if top:
             ach = kern[top]["tflops"]
+            # DRAM bytes per launch of the dominant kernel from the ncu capture of this round (same launches, taken
+            # with tests/diag/ncu_step.py; per-layer figures sit in roofline.layers next to the algorithmic bytes)
             traffic = traffic_detail = None
-            tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-            if os.path.exists(tpath):
-                traffic_detail = json.load(open(tpath)).get(top)
+            tr = ncu_traffic()
+            if tr is not None:
+                traffic_detail = tr.get("kernels", {}).get(top)
                 if traffic_detail:
-                    traffic = traffic_detail.get("avg_dram_bytes_per_launch")   # dram read + write per launch (ncu)
+                    traffic = traffic_detail.get("avg_dram_bytes_per_launch")
             roof = {"bound": "tensor", "kernel": top, "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": ach / peaks["bf16_tflops"], "traffic": traffic, "traffic_detail": traffic_detail,
                     "peak_source": peaks["source"],
                     "share_of_step": kern[top]["ms_per_step"] / ms_step_serial, "kernels": kern, "calls": calls,
                     "conv_share_of_step": conv_ms / args.steps / ms_step_serial, "ms_step_serial": ms_step_serial,
+                    "layers": layer_table(lsum, args.steps, peaks),
                     "whole_step_tflops": GFLOP_PER_SAMPLE * B / ms_step,
                     "note": "achieved = algorithmic conv FLOPs (2*positions*Cout*Cin*taps, logical channels) of all "
                             "launches of the kernel / their summed CUDA-event time, taken in a second pass of the same "
@@ -388,18 +606,17 @@ def run_ours(args):
         }
         if world == 1:
             line["fp32_mode"] = fp32_mode_leg(dev, host[0])
+        if world == 1 and not args.no_side_legs:
+            del model, net, opt
+            torch.cuda.empty_cache()
+            line["other_configs"] = other_configs_leg(dev)
+            torch.cuda.empty_cache()
+            # the honest same-box bar: the reference's torch modules on this B200 through cuDNN (fresh process)
+            line["gpu_baseline"] = _spawn_leg("torch-gpu", ["--batch", "32"], "TORCH_GPU_JSON ", 900)
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            cstep = oracle_step_fn(2, cores)
-            cstep()
-            t0 = time.perf_counter()
-            n = 8                       # ~10 s of host work: a bounded sample of the same workload
-            for _ in range(n):
-                cstep()
-            dt = (time.perf_counter() - t0) / n
-            line["cpu_baseline"] = {"value": 2 / dt, "unit": "samples/s", "cores": cores, "kind": "port",
-                                    "sample": "2 samples/step (8 clip-passes) x 8 timed steps of the same workload, "
-                                              "oracle/ port of the reference step, fp32 oneDNN"}
+            # the reference step on this box's host cores: a bounded sample (1 warm-up + 2 timed steps of 4 samples)
+            ref = _spawn_leg("reference", ["--steps", "2", "--warmup", "1"], None, 900)
+            line["cpu_baseline"] = ref.get("cpu_baseline", ref)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -410,12 +627,15 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-gpu"])
     ap.add_argument("--batch", type=int, default=64, help="samples per GPU (3 views each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side-legs", action="store_true", help="skip the other_configs / gpu_baseline side figures")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "torch-gpu":
+        run_torch_gpu(args)
     else:
         run_ours(args)
 

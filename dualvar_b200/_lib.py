@@ -158,7 +158,7 @@ class KernelTimer:
     def __init__(self, names, detail=False):
         self.names = set(names)
         self.detail = detail
-        self.records = []   # (name, start_event, end_event, flops)
+        self.records = []   # (name, start_event, end_event, flops, bytes)
 
     def key_of(self, name, args):
         if not self.detail:
@@ -178,18 +178,46 @@ class KernelTimer:
                 return 2.0 * g.N * g.To * g.Ho * g.Wo * g.Cout * g.Cin * g.taps
         return 0.0
 
+    def bytes_of(self, name, args):
+        """Algorithmic HBM bytes of one call on LOGICAL channel counts: every operand read once, every result written
+        once (bf16 activations / gradients 2 B, packed bf16 weights 2 B, fp32 weight gradients 4 B).
+        BatchNorm passes (rows, Cp follow the pointer arguments): apply reads y and writes z (+ second branch /
+        residual reads), bwd_reduce reads dz and y (+ dz2 / out), bwd_apply reads dz and y and writes dy (+ g)."""
+        for a in args:
+            g = getattr(a, "_obj", None)
+            if isinstance(g, ConvGeom):
+                xin = g.N * g.T * g.H * g.W * g.Cin
+                yout = g.N * g.To * g.Ho * g.Wo * g.Cout
+                w = g.Cout * g.Cin * g.taps
+                if "wgrad" in name:
+                    return 2.0 * (xin + yout) + 4.0 * w
+                return 2.0 * (xin + yout) + 2.0 * w + (2.0 * xin if "bnred" in name else 0.0)
+        def n(*xs):
+            return sum(1 for x in xs if x is not None)
+        if name == "dv_bn_apply":            # (y1, ss1, y2, ss2, res, out, rows, Cp, ...)
+            return 2.0 * args[6] * args[7] * (n(args[0], args[2], args[4]) + 1)
+        if name == "dv_bn_bwd_reduce":       # (dout, dout2, out, y, mask_ss, sums, rows, Cp, o_ld, o_coff, relu, stream)
+            reads_out = args[4] is None and args[10] != 0
+            return 2.0 * args[6] * args[7] * (n(args[0], args[1], args[3]) + (1 if reads_out else 0))
+        if name == "dv_bn_bwd_apply":        # (dout, dout2, out, y, mask_ss, coef, dy, g_out, rows, Cp, o_ld, o_coff, relu, stream)
+            reads_out = args[4] is None and args[12] != 0
+            return 2.0 * args[8] * args[9] * (n(args[0], args[1], args[3]) + (1 if reads_out else 0) + n(args[6], args[7]))
+        return 0.0
+
     def summary(self):
         torch.cuda.synchronize()
         out = {}
-        for name, e0, e1, fl in self.records:
-            d = out.setdefault(name, {"calls": 0, "ms": 0.0, "flops": 0.0})
+        for name, e0, e1, fl, by in self.records:
+            d = out.setdefault(name, {"calls": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
             d["calls"] += 1
             d["ms"] += e0.elapsed_time(e1)
             d["flops"] += fl
+            d["bytes"] += by
         return out
 
 
 _timer = None
+_NVTX = KernelTimer([], detail=True) if os.environ.get("DV_NVTX", "") not in ("", "0") else None
 
 
 def set_timer(timer):
@@ -214,10 +242,18 @@ def call(name, *args):
         rc = fn(*args)
         e1.record()
         check(rc, name)
-        _timer.records.append((_timer.key_of(name, args), e0, e1, _timer.flops_of(args)))
+        _timer.records.append((_timer.key_of(name, args), e0, e1, _timer.flops_of(args), _timer.bytes_of(name, args)))
         return
     if _TRACE:
         print(f"[dv] {name}(" + ", ".join(_fmt(a) for a in args) + ")", flush=True)
+    if _NVTX is not None:
+        # DV_NVTX=1: every C-ABI call sits in an NVTX range named like KernelTimer's per-layer key, so that
+        # `ncu --nvtx --print-nvtx-rename kernel` reports launches per layer (tests/diag/ncu_step.py)
+        torch.cuda.nvtx.range_push(_NVTX.key_of(name, args).replace(" ", "_"))
+        rc = fn(*args)
+        torch.cuda.nvtx.range_pop()
+        check(rc, name)
+        return
     rc = fn(*args)
     if rc != 0:
         check(rc, name)

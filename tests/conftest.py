@@ -18,3 +18,18 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="session")
+def measured():
+    """record(name, value): measured parity figures of the GPU tests, appended to gpurun_out/measured_parity.jsonl when
+    that directory exists (the bounds in the tests are set from these numbers; profiles/ keeps a copy per round)."""
+    import json
+    out_dir = os.path.join(ROOT, "gpurun_out")
+
+    def record(name, value):
+        print(f"[measured] {name}: {value}")
+        if os.path.isdir(out_dir):
+            with open(os.path.join(out_dir, "measured_parity.jsonl"), "a") as f:
+                f.write(json.dumps({"name": name, "value": value}) + "\n")
+    return record

@@ -9,6 +9,12 @@ import torch
 
 pytestmark = pytest.mark.gpu
 dev = "cuda:0"
+# Rows (of 3783) whose top-50 / top-1 lists differ from the reference's own fp32 path (cuBLAS sgemm + torch.topk) on the
+# seed-7 features: measured value + 1 (profiles/r02_measured_parity.jsonl). Every such row is an fp32 near-tie of the
+# reference (asserted below: the swapped similarities differ by < 1e-6); against the fp64 evaluation of the reference
+# formula the indices are bit-exact for all 3783 rows.
+MAX_ROWS_DIFF_TOP50 = 190
+MAX_ROWS_DIFF_TOP1 = 4
 
 
 def _f64_reference(te, tr, kmax):
@@ -31,7 +37,7 @@ def test_retrieval_matches_golden_reference(golden_dir):
         assert np.array_equal(idx[k].cpu().numpy(), g[f"ret_top{k}"])
 
 
-def test_retrieval_ucf101_shape_bit_exact_indices():
+def test_retrieval_ucf101_shape_bit_exact_indices(measured):
     """Config 5 shape: 3783 test x 9537 train x 512-d features (UCF101 split 1), seed 7."""
     from dualvar_b200.retrieval import retrieval_topk, retrieval_accuracy
     from oracle import objectives as OO
@@ -47,15 +53,19 @@ def test_retrieval_ucf101_shape_bit_exact_indices():
     # fp32 oracle (the reference's own arithmetic): identical except at its fp32 near-ties
     torch.backends.cuda.matmul.allow_tf32 = False
     sim32, idx32 = OO.retrieval_topk(te, tr)
-    same_rows = (idx32[50] == idx[50]).all(dim=1).float().mean().item()
-    assert same_rows > 0.95
+    n_rows_diff = int((idx32[50] != idx[50]).any(dim=1).sum())
+    n_top1_diff = int((idx32[1] != idx[1]).sum())
+    measured("retrieval.rows_differing_from_fp32_oracle_top50", n_rows_diff)
+    measured("retrieval.rows_differing_from_fp32_oracle_top1", n_top1_diff)
+    # exact counts on this image's cuBLAS (sgemm summation order): see MAX_ROWS_DIFF below
+    assert n_rows_diff <= MAX_ROWS_DIFF_TOP50, n_rows_diff
+    assert n_top1_diff <= MAX_ROWS_DIFF_TOP1, n_top1_diff
     diff = idx32[50] != idx[50]
     if diff.any():
         # every disagreement swaps two gallery items whose reference similarities differ by < 1e-6
         a = sim32.gather(1, idx32[50])[diff]
         b = sim32.gather(1, idx[50])[diff]
         assert (a - b).abs().max().item() < 1e-6
-    assert torch.equal(idx32[1], idx[1]) or (idx32[1] != idx[1]).float().mean().item() < 1e-3
     labels_tr = torch.randint(0, 101, (9537,), device=dev, generator=gen)
     labels_te = torch.randint(0, 101, (3783,), device=dev, generator=gen)
     acc = retrieval_accuracy(idx, labels_tr, labels_te)
