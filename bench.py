@@ -250,13 +250,30 @@ def layer_table(lsum, steps, peaks):
             row["algorithmic_gbs"] = d["bytes"] / n / (ms * 1e-3) / 1e9
             row["frac_of_hbm_peak"] = row["algorithmic_gbs"] / peaks["hbm_gbs"]
         t = per_layer.get(key)
-        if t:
-            row["dram_bytes_per_launch"] = t["dram_bytes_per_launch"]
+        if t:      # ncu captured ONE step: DRAM bytes of all kernel launches behind this layer's calls / calls per step
+            row["dram_bytes_per_launch"] = t["dram_bytes_per_step"] / (n / steps)
+            row["ncu_kernel_launches_per_step"] = t["launches"]
             if row.get("algorithmic_bytes_per_launch"):
-                row["dram_over_algorithmic"] = t["dram_bytes_per_launch"] / row["algorithmic_bytes_per_launch"]
+                row["dram_over_algorithmic"] = row["dram_bytes_per_launch"] / row["algorithmic_bytes_per_launch"]
+        # the layer's own roofline: the slower of its tensor time and its HBM time on the algorithmic figures
+        t_roof = max(d["flops"] / n / (peaks["bf16_tflops"] * 1e12), d.get("bytes", 0) / n / (peaks["hbm_gbs"] * 1e9)) * 1e3
+        if t_roof > 0:
+            row["roofline_ms_per_launch"] = t_roof
+            row["frac_of_layer_roofline"] = t_roof / ms
+            row["bound"] = "tensor" if d["flops"] / n / (peaks["bf16_tflops"] * 1e12) * 1e3 >= t_roof else "hbm"
         rows.append(row)
     rows.sort(key=lambda r: -r["ms_per_step"])
     return rows
+
+
+def roofline_summary(rows, prefixes):
+    """Time-weighted fraction of the per-layer roofline over the layers whose entry point starts with one of prefixes."""
+    sel = [r for r in rows if r["layer"].split(" ")[0].startswith(prefixes) and "roofline_ms_per_launch" in r]
+    t = sum(r["ms_per_step"] for r in sel)
+    roof = sum(r["roofline_ms_per_launch"] * r["launches_per_step"] for r in sel)
+    return {"ms_per_step": t, "roofline_ms_per_step": roof, "frac": roof / t if t else None,
+            "hbm_bound_ms_per_step": sum(r["ms_per_step"] for r in sel if r.get("bound") == "hbm"),
+            "tensor_bound_ms_per_step": sum(r["ms_per_step"] for r in sel if r.get("bound") == "tensor")}
 
 
 def workload_config(args, batch):
@@ -564,6 +581,7 @@ def run_ours(args):
                                "tflops": fl / (ms * 1e-3) / 1e12, "avg_launch_us": ms / n * 1e3,
                                "gflop_per_launch": fl / n / 1e9}
         top = max(kern, key=lambda k: kern[k]["ms_per_step"]) if kern else None
+        layers = layer_table(lsum, args.steps, peaks)
         roof = None
         if top:
             ach = kern[top]["tflops"]
@@ -580,7 +598,13 @@ def run_ours(args):
                     "peak_source": peaks["source"],
                     "share_of_step": kern[top]["ms_per_step"] / ms_step_serial, "kernels": kern, "calls": calls,
                     "conv_share_of_step": conv_ms / args.steps / ms_step_serial, "ms_step_serial": ms_step_serial,
-                    "layers": layer_table(lsum, args.steps, peaks),
+                    "layers": layers,
+                    "per_layer_roofline": {
+                        "what": "each layer against ITS OWN roofline = max(algorithmic FLOPs / bf16 peak, algorithmic "
+                                "bytes / HBM peak): several conv layers of this network are HBM-bound even as convolutions "
+                                "(K = 192 temporal convs on 144-channel maps), so a pure tensor fraction understates them",
+                        "conv": roofline_summary(layers, ("dv_conv3d",)),
+                        "batchnorm": roofline_summary(layers, ("dv_bn_",))},
                     "whole_step_tflops": GFLOP_PER_SAMPLE * B / ms_step,
                     "note": "achieved = algorithmic conv FLOPs (2*positions*Cout*Cin*taps, logical channels) of all "
                             "launches of the kernel / their summed CUDA-event time, taken in a second pass of the same "

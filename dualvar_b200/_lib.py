@@ -168,7 +168,12 @@ class KernelTimer:
             if isinstance(g, ConvGeom):
                 return (f"{name} N{g.N} {g.T}x{g.H}x{g.W} {g.Cin}->{g.Cout} k{g.kt}{g.kh}{g.kw} "
                         f"s{g.st}{g.sh}{g.sw}")
-        ints = [str(a) for a in args if isinstance(a, int)][:3]
+        pos = {"dv_bn_apply": (6, 7), "dv_bn_bwd_reduce": (6, 7), "dv_bn_bwd_apply": (8, 9)}.get(name)
+        if pos is not None:      # rows x padded channels + which optional streams are present
+            opt = {"dv_bn_apply": (2, 4), "dv_bn_bwd_reduce": (1,), "dv_bn_bwd_apply": (1, 7)}[name]
+            flags = "".join("1" if args[i] is not None else "0" for i in opt)
+            return f"{name} rows{args[pos[0]]} C{args[pos[1]]} opt{flags}"
+        ints = [str(a) for a in args if isinstance(a, int) and 0 <= a < (1 << 32)][:3]
         return name + " " + ",".join(ints)
 
     def flops_of(self, args):

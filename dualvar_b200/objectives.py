@@ -297,3 +297,35 @@ def queue_contrast(q, k, queue, temperature, prefix):
     loss, logits, hits = QueueContrastFn.apply(q, k, queue, temperature)
     return {f"{prefix}logits": logits, f"{prefix}labels": _zeros_labels(logits.shape[0], logits.device),
             f"{prefix}contrast_loss": loss}, hits
+
+
+class CrossEntropyFn(torch.autograd.Function):
+    """nn.CrossEntropyLoss (mean) + calc_topk_accuracy(logit, target, (1, 5)) of the finetune / linear-probe loop
+    (classifier.py:465-467,525-527; utils/utils.py:75-92) in one launch of the contrastive row kernel: the "positive"
+    column of row r is target[r], no column is dropped, T = 1; the kernel also leaves dLoss/dlogits behind.
+    Returns (loss, hits[top1, top5])."""
+
+    @staticmethod
+    def forward(ctx, logits, target):
+        B, C = logits.shape
+        dev = logits.device
+        S = logits.detach().float().contiguous().clone()
+        scratch = torch.empty((B, C), dtype=torch.float32, device=dev)
+        loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
+        hits = torch.zeros(2, dtype=torch.int32, device=dev)
+        pos = target.to(torch.int32).contiguous()
+        call("dv_contrast_rows", ptr(S), ptr(scratch), None, ptr(pos), B, C, C, C, _f(1.0), _f(1.0 / B), ptr(loss_sum),
+             ptr(hits), stream_ptr())
+        ctx.save_for_backward(S)
+        ctx.mark_non_differentiable(hits)
+        return (loss_sum / B).squeeze(0), hits
+
+    @staticmethod
+    def backward(ctx, dloss, _dh):
+        (dS,) = ctx.saved_tensors
+        return dS * dloss, None
+
+
+def cross_entropy(logits, target):
+    """(mean CE loss, int32 [top-1 hits, top-5 hits]) for (B, num_class) logits and int64 targets."""
+    return CrossEntropyFn.apply(logits, target)

@@ -38,7 +38,7 @@ def main(src, dst):
     layers, total_us = {}, 0.0
     for d in launches.values():
         total_us += d["us"]
-        name = d["name"]
+        name = d["name"].split("/")[0]        # "<NVTX range>/<CUDA kernel>"
         if not name.startswith("dv_"):
             continue
         # NVTX names carry '_' for ' ': "<entry>_N192_16x56x56_64->144_k133_s111" or "<entry>_<rows>,<Cp>,<ld>"
@@ -54,7 +54,10 @@ def main(src, dst):
         L["dram_write_bytes"] += d["write"]
         L["us"] += d["us"]
     for L in layers.values():
-        L["dram_bytes_per_launch"] = (L["dram_read_bytes"] + L["dram_write_bytes"]) / L["launches"]
+        # one C-ABI call may be several kernel launches (two-region tiling, one launch per stride-parity class):
+        # bench.py divides the per-step totals by ITS calls per step
+        L["dram_bytes_per_step"] = L["dram_read_bytes"] + L["dram_write_bytes"]
+        L["dram_bytes_per_launch"] = L["dram_bytes_per_step"] / L["launches"]
         L["us_per_launch"] = L["us"] / L["launches"]
     kernels = {}
     for g, eps in GROUPS.items():

@@ -14,7 +14,9 @@ model = PM.SimCLR_TimeSeriesV4(net_name, 128, 0.07, False, True, 2, 64, 0.07, 0.
                                SimpleNamespace(shufflerank_theta=0.05)).to(dev).train()
 from dualvar_b200.optim import SGD
 opt = SGD([{'params': p} for p in model.parameters()], lr=0.003, weight_decay=1e-4, momentum=0.9)
-frames = torch.rand(B, 3, 48, 112, 112, device=dev)
+T = int(sys.argv[3]) if len(sys.argv) > 3 else 16          # frames per clip
+H = int(sys.argv[4]) if len(sys.argv) > 4 else 112
+frames = torch.rand(B, 3, 3 * T, H, H, device=dev)
 
 def step():
     ret = model(RawClips(frames, 3))
