@@ -280,7 +280,7 @@ def workload_config(args, batch):
     return {"workload": "configs[1]: R(2+1)D (select_backbone('r21d'), 14.4M) SimCLR+DualVar mode clip-sr-tc, "
                         "3 views x 16x112x112 per sample, n_series=2, T=0.07, SGD lr 0.003 m 0.9 wd 1e-4",
             "samples_per_gpu": batch, "clips_per_gpu_step": batch * 3, "clip_passes_per_gpu_step": batch * 4,
-            "parallelism": f"dp{args.gpus}", "l2": "inputs (462 MB/step/GPU fp32 at 64 samples) exceed the 126 MB L2"}
+            "parallelism": f"dp{args.gpus}" + (f" ({args.dp} gradient all-reduce)" if args.gpus > 1 and hasattr(args, "dp") else ""), "l2": "inputs (462 MB/step/GPU fp32 at 64 samples) exceed the 126 MB L2"}
 
 
 def fp32_mode_leg(dev, host_frames, steps=3, batch=16):
@@ -421,7 +421,14 @@ def run_ours(args):
     model = model.to(dev).train()
     net = model
     if world > 1:
-        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank])   # pretrain.py:248
+        # pretrain.py:248. Default: dualvar_b200.parallel.DataParallel - DDP's contract with the gradient all-reduce
+        # bucketed INSIDE the engine's backward (overlapped); --dp torch uses torch's DistributedDataParallel, whose
+        # reducer only sees the backbone gradients when the one-node backbone backward has finished
+        if args.dp == "overlap":
+            from dualvar_b200.parallel import DataParallel
+            model = DataParallel(model, device_ids=[local_rank])
+        else:
+            model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank])
     from dualvar_b200.optim import SGD
     opt = SGD([{"params": p} for p in net.parameters()], lr=0.003, weight_decay=1e-4, momentum=0.9)   # pretrain.py:262-272
     # synthetic decoded+augmented batch as the loader yields it: (B, 3, 3*16, 112, 112) in [0,1], pinned host
@@ -443,17 +450,32 @@ def run_ours(args):
             ready[i % 2].record(copy_stream)
 
     loss_host = torch.zeros(1).pin_memory()
+    # One CUDA graph per step (dualvar_b200/graph_step.py) on a single GPU: the whole step - ingest, both encoder passes,
+    # heads, the four losses, backward, fused SGD - is captured once and replayed; the batch is copied into the graph's
+    # static input buffer and the host RNG draws of the step (segment permutations) are refreshed before every replay.
+    # Multi-GPU runs stay eager (see graph_step.py). --no-graph / DV_BENCH_GRAPH=0 times the eager step.
+    from dualvar_b200.graph_step import GraphedTrainStep
+    use_graph = world == 1 and not args.no_graph and os.environ.get("DV_BENCH_GRAPH", "1") != "0"
+    graphed = {"step": None}
 
-    def step(i, e2e):
+    def new_graphed():
+        if graphed["step"] is not None:
+            graphed["step"].release()
+        graphed["step"] = GraphedTrainStep(model, opt, n_views=3, warmup=0, wrap=bufs["wrap"]) if use_graph else None
+
+    def step(i, e2e, eager=False):
         if e2e:
             torch.cuda.current_stream().wait_event(ready[i % 2])
             prefetch(i + 1)
         frames = bufs["dev"][i % 2]
-        ret = model(bufs["wrap"](frames))
-        loss = sum(v for k, v in ret.items() if "loss" in k)
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        opt.step()
+        if graphed["step"] is not None and not eager:
+            loss = graphed["step"](frames)["loss"]      # D2D copy into the static input buffer + graph replay
+        else:
+            ret = model(bufs["wrap"](frames))
+            loss = sum(v for k, v in ret.items() if "loss" in k)
+            opt.zero_grad(set_to_none=not use_graph)
+            loss.backward()
+            opt.step()
         consumed[i % 2].record()
         if e2e:
             loss_host.copy_(loss.detach().view(1), non_blocking=True)
@@ -464,12 +486,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(nsteps, e2e, first):
+    def timed(nsteps, e2e, first, eager=False):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(first, first + nsteps):
-            step(i, e2e)
+            step(i, e2e, eager)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -482,13 +504,20 @@ def run_ours(args):
     # resident inputs for the kernel-side number
     dev_in[0].copy_(host[0]); dev_in[1].copy_(host[1])
     for i in range(args.warmup):
-        step(i, False)
+        step(i, False, eager=True)
+    new_graphed()
+    if graphed["step"] is not None:
+        for i in range(2):                       # capture + first replays outside the timed region
+            step(i, False)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = _lib.load().dv_launch_count()
     ms_step = timed(args.steps, False, 0)
     launches = _lib.load().dv_launch_count() - launches0
+    if graphed["step"] is not None:              # replays issue no C-ABI calls: the graph holds the step's launches
+        launches = graphed["step"].launches_per_step * args.steps
+    ms_step_eager = timed(args.steps, False, 0, eager=True) if graphed["step"] is not None else ms_step
     # Kernel attribution for the roofline: the same steps again with CUDA events around every conv call on its
     # launching stream. The product path runs the weight gradients on a side stream next to the BatchNorm
     # passes and the two backbone passes on two streams, where per-launch event times overlap other kernels; for this
@@ -503,7 +532,7 @@ def run_ours(args):
     bn_names = ["dv_bn_apply", "dv_bn_bwd_reduce", "dv_bn_bwd_apply"]
     timer = _lib.KernelTimer(conv_names + bn_names, detail=True)
     _lib.set_timer(timer)
-    ms_step_serial = timed(args.steps, False, 0)
+    ms_step_serial = timed(args.steps, False, 0, eager=True)
     _lib.set_timer(None)
     _engine.WGRAD_SIDE_STREAM, _engine.PASS_STREAMS = side_was, pass_was
     lsum = timer.summary()                      # per layer: "<entry point> <geometry>" -> calls, ms, flops, bytes
@@ -526,11 +555,19 @@ def run_ours(args):
     # kernel): 4x fewer bytes over PCIe. Reported next to the fp32 figure, which stays the contract's e2e.
     u8 = [(h * 255).round().to(torch.uint8).pin_memory() for h in host]
     bufs["host"], bufs["dev"] = u8, [torch.empty_like(u8[0], device=dev) for _ in range(2)]
+    new_graphed()                                # another input dtype: its own graph
+    if graphed["step"] is not None:
+        bufs["dev"][0].copy_(u8[0])
+        for i in range(2):
+            step(0, False)
     for i in range(2):
         consumed[i].record()
     torch.cuda.synchronize()
     prefetch(0)
     ms_e2e_u8 = timed(args.steps, True, 0)
+    if graphed["step"] is not None:
+        graphed["step"].release()
+        graphed["step"] = None                   # the remaining legs are eager (host-drawn crop offsets per step)
     # the same step fed with DECODED frames (uint8 HWC 320x240, what a JPEG decoder yields): Scale((128,171)) bicubic +
     # RandomCrop(112) of the reference loader run on the GPU (dualvar_b200/frames.py, bit-exact with Pillow) instead of in
     # 16 PIL worker processes; crop offsets drawn on the host every step as A.RandomCrop does
@@ -626,6 +663,9 @@ def run_ours(args):
                 "what": "48 decoded uint8 320x240 frames per sample copied from pinned host memory; Scale((128,171)) "
                         "bicubic + RandomCrop(112) + ToTensor + Normalize on the GPU (bit-exact with Pillow)"},
             "gpu_launches": int(launches), "roofline": roof, "clocks": sampler.summary(),
+            "step_issue": {"mode": "cuda_graph" if use_graph else "eager", "ms_per_step_eager": ms_step_eager,
+                           "what": "value / e2e replay ONE CUDA graph per step (dualvar_b200/graph_step.py); "
+                                   "ms_per_step_eager is the same step issued call by call from Python"},
             "final_loss": final_loss,
         }
         if world == 1:
@@ -654,6 +694,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-gpu"])
     ap.add_argument("--batch", type=int, default=64, help="samples per GPU (3 views each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dp", default=os.environ.get("DV_BENCH_DP", "overlap"), choices=["overlap", "torch"],
+                    help="data-parallel wrapper for --gpus > 1")
+    ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
     ap.add_argument("--no-side-legs", action="store_true", help="skip the other_configs / gpu_baseline side figures")
     args = ap.parse_args()
     if args.impl == "reference":

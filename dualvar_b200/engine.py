@@ -113,6 +113,7 @@ class Context:
         self.defer_running = None  # list: running-statistic updates of a concurrent pass, applied in order at the join
         self._arena = None         # zeroed fp64 scratch the per-layer statistic buffers are carved from
         self._arena_used = 0
+        self.rpass = None          # parallel._Pass during backward: parameter gradients go into its flat buckets
 
     def zeros64(self, n, device):
         """A zero-initialised float64 vector of n elements: one memset per ~64 K elements instead of one tiny
@@ -128,9 +129,23 @@ class Context:
     def add_param_grad(self, p, g):
         k = id(p)
         if k in self.param_grads:
-            self.param_grads[k].add_(g)
+            if self.rpass is not None and self.rpass.in_flight(p):
+                self.rpass.extra.append((p, g))        # its bucket is already being all-reduced
+            else:
+                self.param_grads[k].add_(g)
         else:
             self.param_grads[k] = g
+
+    def grad_out(self, p):
+        """Destination for p's gradient: its slice of the data-parallel reducer's flat bucket buffer during a reduced
+        backward (the all-reduce then needs no gather copy), a fresh tensor otherwise."""
+        v = self.rpass.view(p) if self.rpass is not None else None
+        return v if v is not None else torch.empty_like(p)
+
+    def grad_ready(self, p, stream=None):
+        """p's gradient is complete once the work queued so far on ``stream`` has run: its bucket may be reduced."""
+        if self.rpass is not None:
+            self.rpass.ready(p, stream)
 
 
 # ----------------------------------------------------------------------------- helpers
@@ -578,7 +593,8 @@ def _conv_backward_f32(ctx, r, dyp):
 def _conv_backward(ctx, r, dy):
     """wgrad into the parameter-gradient sink, dgrad into r.x.grad."""
     g = r.geom
-    gw = torch.empty_like(r.conv.weight)
+    first = id(r.conv.weight) not in ctx.param_grads
+    gw = ctx.grad_out(r.conv.weight) if first else torch.empty_like(r.conv.weight)
     if WGRAD_SIDE_STREAM:
         main = torch.cuda.current_stream()
         side = _side_stream(dy.device)
@@ -591,8 +607,11 @@ def _conv_backward(ctx, r, dy):
         gw.record_stream(side)
         ctx.side_used = True
     else:
+        side = None
         _wgrad(r, dy, gw)
     ctx.add_param_grad(r.conv.weight, gw)
+    if first:
+        ctx.grad_ready(r.conv.weight, side)
     if r.conv.bias is not None:
         # a bias in front of training-mode BN has exactly zero gradient (BN removes the mean)
         ctx.add_param_grad(r.conv.bias, torch.zeros_like(r.conv.bias))
@@ -615,8 +634,9 @@ def _bn_bwd_finalize(ctx, r, sums, Cp, dev):
     """Backward sums of one BatchNorm -> dgamma / dbeta (into the gradient sink) and the coefficients of
     dy = A*g + B*y + C; cross-replica BatchNorm exchanges the sums first (fused over NVLink peer memory)."""
     bn = r.bn
-    dgamma = torch.empty_like(bn.weight)
-    dbeta = torch.empty_like(bn.bias)
+    first = id(bn.weight) not in ctx.param_grads
+    dgamma = ctx.grad_out(bn.weight) if first else torch.empty_like(bn.weight)
+    dbeta = ctx.grad_out(bn.bias) if first else torch.empty_like(bn.bias)
     coef = torch.empty(3 * Cp, dtype=torch.float32, device=dev)
     peer = comm.peer_state(dev, 2 * Cp) if r.sync else None
     if peer is not None:  # exchange of the sums + finalisation in one launch over NVLink peer memory
@@ -633,6 +653,9 @@ def _bn_bwd_finalize(ctx, r, sums, Cp, dev):
              ctypes.c_float(0.0), stream_ptr())
     ctx.add_param_grad(bn.weight, dgamma)
     ctx.add_param_grad(bn.bias, dbeta)
+    if first:
+        ctx.grad_ready(bn.weight)
+        ctx.grad_ready(bn.bias)
     return coef
 
 
@@ -926,11 +949,11 @@ class BackboneFunction(torch.autograd.Function):
     normal autograd accumulation (DDP hooks, optimizers and .grad all keep working)."""
 
     @staticmethod
-    def forward(fctx, program, make_input, pooled, training, record, *params):
+    def forward(fctx, program, make_input, pooled, training, record, reducer, *params):
         ectx = Context(training, record=record)
         x = make_input()
         feat = program(ectx, x)
-        fctx.ectx, fctx.feat, fctx.pooled, fctx.params = ectx, feat, pooled, params
+        fctx.ectx, fctx.feat, fctx.pooled, fctx.params, fctx.reducer = ectx, feat, pooled, params, reducer
         fctx.set_materialize_grads(False)
         out = global_pool(ectx, feat) if pooled else to_ncdhw(feat)
         if not record:
@@ -941,16 +964,29 @@ class BackboneFunction(torch.autograd.Function):
     def backward(fctx, dout):
         ectx, feat = fctx.ectx, fctx.feat
         if dout is None or feat is None:
-            return (None,) * (5 + len(fctx.params))
+            return (None,) * (6 + len(fctx.params))
+        # data-parallel training (parallel.DataParallel): parameter gradients are written into flat buckets and every
+        # bucket is all-reduced on a communication stream as soon as it is complete, under the rest of this backward
+        rp = ectx.rpass = fctx.reducer.begin_pass() if fctx.reducer is not None else None
         if fctx.pooled:
             global_pool_backward(feat, dout)
         else:
             from_ncdhw_grad(feat, dout)
         run_backward(ectx)
+        if rp is not None:
+            for p in fctx.params:       # gradients produced outside the bucket views (gating fc, zero biases, fp32 mode)
+                g = ectx.param_grads.get(id(p))
+                if g is not None and rp.manages(p) and id(p) not in rp.seen:
+                    v = rp.view(p)
+                    v.copy_(g)
+                    ectx.param_grads[id(p)] = v
+                    rp.ready(p)
+            rp.finish()
+            ectx.rpass = None
         grads = tuple(ectx.param_grads.get(id(p)) if p.requires_grad else None for p in fctx.params)
         ectx.param_grads = {}
         fctx.feat = None
-        return (None, None, None, None, None) + grads
+        return (None, None, None, None, None, None) + grads
 
 
 # Two independent passes of one backbone (SimCLR+DualVar: the 3B clips and the B segment-shuffled clips,
@@ -1043,4 +1079,5 @@ def run_backbone_pair(module, program, make_inputs):
 def run_backbone(module, program, make_input, pooled):
     params = [p for p in module.parameters()]
     record = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-    return BackboneFunction.apply(program, make_input, pooled, module.training, record, *params)
+    return BackboneFunction.apply(program, make_input, pooled, module.training, record,
+                                  getattr(module, "_dv_reducer", None), *params)

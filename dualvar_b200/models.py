@@ -40,15 +40,21 @@ def _check_input(block):
     return block, tuple(block.shape)
 
 
+_perm_source = None     # graph_step.GraphedTrainStep: the permutations live in a static device buffer it refreshes
+
+
 def _draw_perms(B, n_series, device):
     """One np.random.permutation per sample from the global NumPy stream, in batch order
     (model/simclr.py:379-381, model/moco.py:544-546)."""
+    if _perm_source is not None:
+        return _perm_source(B, n_series, device)
     perms = np.array([np.random.permutation(n_series) for _ in range(B)], dtype=np.int32)
     return torch.from_numpy(perms).to(device, non_blocking=True)
 
 
 class SimCLR_Naked(nn.Module):
     """Two-view SimCLR (model/simclr.py:19-127)."""
+    graph_safe = True      # a step can be captured as one CUDA graph (graph_step.GraphedTrainStep)
 
     def __init__(self, network='s3d', dim=128, T=0.07, distributed=True, nonlinear=True):
         super().__init__()
@@ -77,6 +83,7 @@ class SimCLR_Naked(nn.Module):
 
 class SimCLR_TimeSeriesV4(nn.Module):
     """SimCLR + DualVar (model/simclr.py:130-400)."""
+    graph_safe = True
 
     def __init__(self, network='s3d', dim=128, T=0.07, distributed=True, nonlinear=True, n_series=2, series_dim=64,
                  series_T=0.07, aligned_T=0.07, mode="clip-sr-tc", args=None):
@@ -163,6 +170,7 @@ class LinearClassifier(nn.Module):
     (model/classifier.py:9-84); returns (logit, pooled feature). The encoder runs on the sm_100a
     kernels, the Linear layers of the (B, feature_size) tail on the sgemm kernel; BatchNorm1d and
     Dropout on that tiny tensor stay torch modules (Dropout must draw the reference's mask)."""
+    graph_safe = True
 
     def __init__(self, num_class=101, network='resnet50', dropout=0.5, use_dropout=True, use_l2_norm=False,
                  use_final_bn=False, nonlinear=False, proj_dim=128):

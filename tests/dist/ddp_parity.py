@@ -3,6 +3,9 @@ SyncBatchNorm + DDP (pretrain.py:244-248) vs the oracle wrapped the same way, sa
 
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist/ddp_parity.py
     DV_PRECISION=fp32 ... ddp_parity.py [simclr|moco]     # the fp32 mode against the 1e-4 bar
+    ... ddp_parity.py simclr overlap     # the product under dualvar_b200.parallel.DataParallel (bucketed all-reduce inside
+                                         # the engine's backward) instead of torch's DDP; its gradients are also compared
+                                         # with the product's own torch-DDP gradients (same data): equal up to fp32 sum order
 """
 import os, sys, random
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
@@ -27,6 +30,7 @@ LOSS_RTOL, LOSS_ATOL, LOGIT_TOL, GRAD_MED = (1e-4, 2e-6, 1e-4, 2e-2) if FP32 els
 def rel(a, b): return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
 args = SimpleNamespace(shufflerank_theta=0.05)
 which = sys.argv[1] if len(sys.argv) > 1 else "simclr"
+wrapper = sys.argv[2] if len(sys.argv) > 2 else "ddp"
 torch.manual_seed(0); np.random.seed(0); random.seed(0)
 if which == "simclr":
     ref = OM.SimCLR_TimeSeriesV4("r21d", 128, 0.07, True, True, 2, 64, 0.07, 0.07, "clip-sr-tc", args)
@@ -38,7 +42,14 @@ prod.load_state_dict(ref.state_dict())
 ref = torch.nn.SyncBatchNorm.convert_sync_batchnorm(ref).to(dev).train()
 prod = torch.nn.SyncBatchNorm.convert_sync_batchnorm(prod).to(dev).train()
 ref_ddp = torch.nn.parallel.DistributedDataParallel(ref, device_ids=[local])
-prod_ddp = torch.nn.parallel.DistributedDataParallel(prod, device_ids=[local])
+if wrapper == "overlap":
+    import copy
+    from dualvar_b200.parallel import DataParallel
+    prod_twin = copy.deepcopy(prod)                     # the same product model under torch DDP, for a tight gradient check
+    twin_ddp = torch.nn.parallel.DistributedDataParallel(prod_twin, device_ids=[local])
+    prod_ddp = DataParallel(prod, device_ids=[local])
+else:
+    prod_ddp = torch.nn.parallel.DistributedDataParallel(prod, device_ids=[local])
 x = torch.randn(4, 3, 3, 8, 64, 64, device=dev, generator=torch.Generator(device=dev).manual_seed(100 + rank))
 ok = True
 torch.manual_seed(50)      # MoCo shuffle-BN draws torch.randperm on every rank (rank 0's is broadcast)
@@ -65,7 +76,17 @@ dist.all_gather(gs, g0)
 same = all(torch.equal(gs[0], g) for g in gs)
 print(f"[rank {rank}] median grad rel err vs oracle-DDP {errs[len(errs)//2]:.3e}; grads identical across ranks: {same}", flush=True)
 ok &= same and errs[len(errs) // 2] < GRAD_MED
+if wrapper == "overlap":
+    torch.manual_seed(50)
+    np.random.seed(10 * rank + 1); rt = twin_ddp(x)
+    sum(v for k, v in rt.items() if "loss" in k).backward()
+    # same kernels, same data: the two reductions differ by fp32 summation order (and the atomics order of a second run)
+    worst = max(rel(pp.grad, pt.grad) for pp, pt in zip(prod.parameters(), prod_twin.parameters()) if pt.grad is not None)
+    missing = [n for (n, pp), pt in zip(prod.named_parameters(), prod_twin.parameters()) if (pp.grad is None) != (pt.grad is None)]
+    print(f"[rank {rank}] overlapped reducer vs torch DDP on the product: worst per-tensor rel diff {worst:.3e}, missing {missing}", flush=True)
+    ok &= worst < 2e-2 and not missing
 t = torch.tensor([1.0 if ok else 0.0], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print("DDP_PARITY", which, "fp32 mode" if FP32 else "bf16 mode", "PASS" if t.item() == 1.0 else "FAIL", flush=True)
+    print("DDP_PARITY", which, "fp32 mode" if FP32 else "bf16 mode", "PASS" if t.item() == 1.0 else "FAIL",
+          "(dualvar_b200.parallel.DataParallel)" if wrapper == "overlap" else "", flush=True)
 dist.destroy_process_group()

