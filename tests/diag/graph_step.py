@@ -70,6 +70,8 @@ try:
         loss = step(False)
     torch.cuda.synchronize()
     l0 = float(loss)
+    if os.environ.get("DV_NCU"):      # ncu --profile-from-start off: the kernels of ONE replay, without host gaps
+        torch.cuda.profiler.start(); g.replay(); torch.cuda.synchronize(); torch.cuda.profiler.stop()
     ms3, issue3 = timed(g.replay, 10)
     print(f"CUDA graph replay: {ms3:.2f} ms/step ({B / ms3 * 1e3:.1f} samples/s), host {issue3:.3f} ms; loss after capture {l0:.4f} "
           f"after replays {float(loss):.4f}", flush=True)

@@ -56,6 +56,6 @@ for k in losses + ["total"]:
         if R[n].grad is None:
             continue
         print(f"   {n:32s} prod/ref {rel(P[n].grad, R[n].grad):.3f}  emu/ref {rel(E_[n].grad, R[n].grad):.3f}  prod/emu {rel(P[n].grad, E_[n].grad):.3f}  |g| {R[n].grad.norm().item():.3e}")
-    bb = [n for n in R if n.startswith("encoder_q.0.") and R[n].grad is not None]
+    bb = [n for n in R if n.startswith("encoder_q.0.") and R[n].grad is not None and P[n].grad is not None and E_[n].grad is not None]
     ep = sorted(rel(P[n].grad, R[n].grad) for n in bb); ee = sorted(rel(E_[n].grad, R[n].grad) for n in bb)
     print(f"   backbone median prod/ref {ep[len(ep)//2]:.3f} emu/ref {ee[len(ee)//2]:.3f}")

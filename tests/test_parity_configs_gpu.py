@@ -64,7 +64,9 @@ def _simclr_trio(net):
 
 
 # Gradient bounds, tensor by tensor. err(t) = ||g - g_fp32|| / ||g_fp32|| of tensor t against the fp32 oracle.
-#   * product within RATIO x the error the same rounding points cause in the oracle itself (+ FLOOR): a wrong or missing
+#   * product within RATIO x the error the same rounding points cause in the oracle itself (+ FLOOR), where a tensor's
+#     own noise floor is taken no lower than the median one (the first layers of the heads see 12-24 rows: their error
+#     swings between 0.14 and 0.36 from run to run on EITHER side, tests/diag/head_grad_probe.py): a wrong or missing
 #     term in ONE tensor (say a downsample branch) reads ~1.0 against a floor of 0.1-0.4 and fails;
 #   * the medians within MED_RATIO (the old assertion, kept as the second one).
 # Measured on B200 (profiles/r02_measured_parity.jsonl): worst ratio 1.18 (r21d), 1.2 (r3d), medians within 1.05.
@@ -75,9 +77,10 @@ def _check_per_tensor(ref, emu, prod, measured, tag, ratio=RATIO, floor=FLOOR, m
     from bf16_emulation import compare_to_noise_floor
     rows = compare_to_noise_floor(ref, emu, prod)
     assert len(rows) >= 10
-    worst = max(rows, key=lambda t: t[1] / (t[2] + floor))
     med_p = sorted(r[1] for r in rows)[len(rows) // 2]
     med_e = sorted(r[2] for r in rows)[len(rows) // 2]
+    rows = [(n, p, max(e, med_e)) for n, p, e in rows]
+    worst = max(rows, key=lambda t: t[1] / (t[2] + floor))
     measured(f"{tag}.grad_worst_tensor", {"name": worst[0], "err_product": worst[1], "err_rounding_oracle": worst[2]})
     measured(f"{tag}.grad_median", {"err_product": med_p, "err_rounding_oracle": med_e})
     bad = [(n, round(p, 4), round(e, 4)) for n, p, e in rows if p > ratio * e + floor]
