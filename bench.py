@@ -453,9 +453,10 @@ def run_ours(args):
     # One CUDA graph per step (dualvar_b200/graph_step.py) on a single GPU: the whole step - ingest, both encoder passes,
     # heads, the four losses, backward, fused SGD - is captured once and replayed; the batch is copied into the graph's
     # static input buffer and the host RNG draws of the step (segment permutations) are refreshed before every replay.
-    # Multi-GPU runs stay eager (see graph_step.py). --no-graph / DV_BENCH_GRAPH=0 times the eager step.
+    # Multi-GPU runs capture per rank with the collectives inside (see graph_step.py); under --dp torch they stay eager.
+    # --no-graph / DV_BENCH_GRAPH=0 times the eager step.
     from dualvar_b200.graph_step import GraphedTrainStep
-    use_graph = world == 1 and not args.no_graph and os.environ.get("DV_BENCH_GRAPH", "1") != "0"
+    use_graph = (world == 1 or args.dp == "overlap") and not args.no_graph and os.environ.get("DV_BENCH_GRAPH", "1") != "0"
     graphed = {"step": None}
 
     def new_graphed():
@@ -508,7 +509,7 @@ def run_ours(args):
     ms_step_eager = timed(args.steps, False, 0, eager=True) if use_graph else None     # the same step issued call by call
     new_graphed()
     if graphed["step"] is not None:
-        for i in range(2):                       # capture + first replays outside the timed region
+        for i in range(3):                       # one eager step on the capture stream, the capture, a first replay
             step(i, False)
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -560,7 +561,7 @@ def run_ours(args):
     new_graphed()                                # another input dtype: its own graph
     if graphed["step"] is not None:
         bufs["dev"][0].copy_(u8[0])
-        for i in range(2):
+        for i in range(3):
             step(0, False)
     for i in range(2):
         consumed[i].record()

@@ -62,10 +62,12 @@ class _PeerReduce:
         self.seq = 0
 
     def next_call(self):
-        """(peer_buffers, rank, world, seq) of the next exchange: the trailing arguments of every dv_*_sync entry."""
+        """(peer_buffers, rank, world, seq) of the next exchange: the trailing arguments of every dv_*_sync entry.
+        seq = 0: the kernels number the calls themselves (device-side counter in the symmetric buffer), so a captured
+        step replays correctly; self.seq only counts for diagnostics."""
         check_status()
         self.seq += 1
-        return self.ptrs, self.rank, self.world, self.seq
+        return self.ptrs, self.rank, self.world, 0
 
     def __call__(self, t):
         _lib.call("dv_allreduce_small_f64", ptr(t), t.numel(), *self.next_call(), stream_ptr())

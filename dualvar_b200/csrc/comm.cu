@@ -7,8 +7,11 @@
 // statistics), so the cost is pure latency: NCCL's ~20 us per call is 6-8 ms of an 80 ms step.
 //
 // Every rank owns a symmetric buffer (same layout on all ranks, mapped into every peer's address space):
-//   slots [2 parities][world][kMaxElems] fp64, then flags [2][world] u64.
-// Call number `seq` (1, 2, ...; all ranks call in the same order) uses parity seq & 1:
+//   slots [2 parities][world][kMaxElems] fp64, then flags [2][world] u64, then one u64 call counter.
+// Call number `seq` (1, 2, ...; all ranks call in the same order) uses parity seq & 1. The host may number the calls
+// itself (seq >= 1) or pass seq = 0: the kernel then takes the next number from the call counter in its own buffer
+// (one CTA per call, calls of a channel run in stream order), which is what lets a step that contains these
+// exchanges be captured ONCE as a CUDA graph and replayed (graph_step.py) - a host-side number would be baked in.
 //   1. push: copy my vector into slot [parity][my rank] of EVERY rank (remote stores over NVLink),
 //   2. fence.sys, then release-store flag [parity][my rank] = seq on every rank,
 //   3. acquire-spin on my own flags [parity][q] == seq for all q,
@@ -64,9 +67,19 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
 // ar_sum(i) returns the sum over ranks (in rank order) of element i.
 __device__ __forceinline__ const double* ar_exchange(const double* __restrict__ src, int n, const ArPeers& peers,
                                                      int rank, int world, unsigned long long seq, double tag = 0.0) {
-  const int parity = (int)(seq & 1ull);
   const size_t slot_elems = (size_t)kArMaxElems;
   const size_t flags_off = 2ull * kArMaxWorld * slot_elems;   // in doubles (= u64 words)
+  if (seq == 0ull) {     // device-side numbering (graph-replayable): next value of this channel's call counter
+    __shared__ unsigned long long s_seq;
+    if (threadIdx.x == 0) {
+      unsigned long long* ctr = reinterpret_cast<unsigned long long*>(peers.base[rank]) + flags_off + 2ull * kArMaxWorld;
+      s_seq = *ctr + 1ull;
+      *ctr = s_seq;
+    }
+    __syncthreads();
+    seq = s_seq;
+  }
+  const int parity = (int)(seq & 1ull);
   for (int p = 0; p < world; ++p) {
     double* dst = reinterpret_cast<double*>(peers.base[p]) + ((size_t)parity * kArMaxWorld + rank) * slot_elems;
     for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
@@ -178,14 +191,14 @@ static int fill_peers(ArPeers* peers, const long long* peer_ptrs, int world) {
 }
 
 long long small_allreduce_buffer_bytes() {
-  return (long long)(2ll * kArMaxWorld * kArMaxElems + 2ll * kArMaxWorld) * 8;
+  return (long long)(2ll * kArMaxWorld * kArMaxElems + 2ll * kArMaxWorld + 1ll) * 8;   // slots, flags, call counter
 }
 
 int small_allreduce_f64(double* inout, int n, const long long* peer_ptrs, int rank, int world, long long seq,
                         cudaStream_t stream) {
   if (n <= 0 || n >= kArMaxElems) return fail(kBadArg, "small_allreduce: n must be in 1..%d", kArMaxElems - 1);
   if (world < 1 || world > kArMaxWorld || rank < 0 || rank >= world) return fail(kBadArg, "small_allreduce: bad rank/world");
-  if (seq < 1) return fail(kBadArg, "small_allreduce: seq starts at 1");
+  if (seq < 0) return fail(kBadArg, "small_allreduce: seq is 0 (device-side numbering) or starts at 1");
   ArPeers peers;
   if (int rc = fill_peers(&peers, peer_ptrs, world)) return rc;
   small_allreduce_kernel<<<1, 512, 0, stream>>>(inout, n, peers, rank, world, (unsigned long long)seq);
@@ -196,7 +209,7 @@ int small_allreduce_f64(double* inout, int n, const long long* peer_ptrs, int ra
 static int ar_peers(ArPeers* peers, int n, const long long* peer_ptrs, int rank, int world, long long seq) {
   if (n <= 0 || n >= kArMaxElems) return fail(kBadArg, "peer all-reduce: n must be in 1..%d", kArMaxElems - 1);
   if (world < 1 || world > kArMaxWorld || rank < 0 || rank >= world) return fail(kBadArg, "peer all-reduce: bad rank/world");
-  if (seq < 1) return fail(kBadArg, "peer all-reduce: seq starts at 1");
+  if (seq < 0) return fail(kBadArg, "peer all-reduce: seq is 0 (device-side numbering) or starts at 1");
   return fill_peers(peers, peer_ptrs, world);
 }
 

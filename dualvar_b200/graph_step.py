@@ -21,8 +21,12 @@ The first ``warmup`` calls run eagerly (they are real training steps; they also 
 gradients live in fixed ``.grad`` tensors that are zeroed in place, so the optimizer's pointer table is static.
 Returned tensors are the graph's own output buffers: valid until the next call.
 
-Single process only: cross-replica BatchNorm's peer exchange numbers its calls on the host (csrc/comm.cu), which a
-replayed graph cannot do - under torch.distributed the step stays eager.
+Data-parallel runs: the step is captured per rank with its collectives inside - NCCL all-gathers of the embeddings,
+the bucketed gradient all-reduce of ``parallel.DataParallel`` and the cross-replica BatchNorm peer exchanges, which
+number their calls from a device-side counter for exactly this purpose (csrc/comm.cu). Every rank must capture and
+replay in lockstep (they do: same loop). Under torch's own DistributedDataParallel the step stays eager (its reducer
+needs its own warm-up protocol for capture). All eager warm-up steps and the capture run on ONE dedicated stream, so
+that per-stream resources (the weight-gradient side stream, the BatchNorm exchange channel) exist before the capture.
 """
 import numpy as np
 import torch
@@ -37,7 +41,8 @@ class GraphedTrainStep:
     def __init__(self, model, optimizer, n_views=3, loss_fn=total_loss, warmup=3, wrap=None):
         self.model, self.opt, self.n_views, self.loss_fn = model, optimizer, n_views, loss_fn
         self.wrap = wrap if wrap is not None else (lambda fr: RawClips(fr, n_views))
-        self.warmup_left = warmup
+        self.warmup_left = max(1, warmup)      # at least one eager step on the capture stream (see the module docstring)
+        self.stream = None
         self.graph = None
         self.frames = None
         self.perm = self.perm_host = None
@@ -45,8 +50,9 @@ class GraphedTrainStep:
         self.out = None
         target = model.module if hasattr(model, "module") else model
         # graph_safe: the model's forward passes no per-step host value to a kernel by value (MoCo's queue pointer is one)
+        distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self.enabled = bool(getattr(target, "graph_safe", False)) and \
-            not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
+            not (distributed and isinstance(model, torch.nn.parallel.DistributedDataParallel))
         self.n_series = getattr(target, "n_series", 0) or 0
         self.replays = self.eager_steps = self.captures = 0
         self.launches_per_step = 0          # kernel launches recorded into the graph (C-ABI launch counter during capture)
@@ -77,8 +83,21 @@ class GraphedTrainStep:
         return out
 
     def _eager(self, frames):
-        """A plain step on the caller's tensors (warm-up calls, odd batch shapes, multi-process runs)."""
+        """A plain step on the caller's tensors (warm-up calls, odd batch shapes, refused models), issued on the
+        dedicated stream when graphs are in use."""
         self.eager_steps += 1
+        if not self.enabled:
+            return self._eager_body(frames)
+        cur = torch.cuda.current_stream()
+        if self.stream is None:
+            self.stream = torch.cuda.Stream()
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            out = self._eager_body(frames)
+        cur.wait_stream(self.stream)
+        return out
+
+    def _eager_body(self, frames):
         ret = self.model(self.wrap(frames))
         loss = self.loss_fn(ret)
         self.opt.zero_grad(set_to_none=False)
@@ -98,7 +117,7 @@ class GraphedTrainStep:
         n0 = _lib.load().dv_launch_count()
         try:
             torch.cuda.synchronize()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=self.stream):
                 out = self._step(set_to_none=False)
         finally:
             PM._perm_source = prev

@@ -225,8 +225,9 @@ int dv_sgd_momentum_step(const int64_t* chunk_table, int n_chunks, float lr, flo
  * Replaces the per-layer collectives of nn.SyncBatchNorm (pretrain.py:244) for vectors of <= 4096 doubles.
  * Every rank allocates a zero-initialised symmetric buffer of dv_allreduce_small_buffer_bytes() bytes that is
  * mapped into all peers (peer_buffers[q] = address of rank q's buffer in THIS process, host array of `world`
- * entries); all ranks call with the same n and seq = 1, 2, 3, ... in the same order. In place, sum in rank
- * order (bit-identical on all ranks). */
+ * entries); all ranks call with the same n and seq = 1, 2, 3, ... in the same order - or all with seq = 0, in which
+ * case the kernel numbers the calls itself from a counter in its buffer (replayable inside a CUDA graph). In place,
+ * sum in rank order (bit-identical on all ranks). */
 int64_t dv_allreduce_small_buffer_bytes(void);
 int dv_allreduce_small_f64(double* inout, int n, const int64_t* peer_buffers, int rank, int world, int64_t seq,
                            void* stream);
