@@ -136,7 +136,8 @@ int gate_bwd_apply(const void* dout, const float* w, const float* dmean, void* d
 int sigmoid_fwd(const float* x, float* y, long long n, cudaStream_t st);
 int sigmoid_bwd(const float* dy, const float* y, float* dx, long long n, cudaStream_t st);
 int momentum_update(const long long* table, int n_chunks, float m, cudaStream_t stream);
-int enqueue(const float* keys, float* queue, int B, int d, int K, int ptr, cudaStream_t stream);
+int enqueue(const float* keys, float* queue, int B, int d, int K, int ptr, const long long* ptr_dev, cudaStream_t stream);
+int advance_queue_ptr(long long* ptr, int batch, int K, cudaStream_t stream);
 }  // namespace dv
 
 using namespace dv;
@@ -604,11 +605,20 @@ int dv_moco_momentum_update(const int64_t* chunk_table, int n_chunks, float m, v
   DV_REQUIRE(chunk_table && n_chunks >= 0 && m >= 0.f && m <= 1.f, "bad momentum_update arguments");
   return momentum_update(reinterpret_cast<const long long*>(chunk_table), n_chunks, m, ST);
 }
+int dv_moco_enqueue_at(const float* keys, float* queue, int B, int d, int K, const int64_t* queue_ptr, void* stream) {
+  DV_REQUIRE(keys && queue && queue_ptr && B > 0 && d > 0 && K > 0, "bad enqueue arguments");
+  DV_REQUIRE(K % B == 0, "queue size K=%d must be a multiple of the global batch %d", K, B);
+  return enqueue(keys, queue, B, d, K, 0, reinterpret_cast<const long long*>(queue_ptr), ST);
+}
+int dv_moco_advance_ptr(int64_t* queue_ptr, int batch, int K, void* stream) {
+  DV_REQUIRE(queue_ptr && batch > 0 && K > 0 && K % batch == 0, "bad advance_ptr arguments");
+  return advance_queue_ptr(reinterpret_cast<long long*>(queue_ptr), batch, K, ST);
+}
 int dv_moco_enqueue(const float* keys, float* queue, int B, int d, int K, int ptr, void* stream) {
   DV_REQUIRE(keys && queue && B > 0 && d > 0 && K > 0, "bad enqueue arguments");
   DV_REQUIRE(K % B == 0, "queue size K=%d must be a multiple of the global batch %d", K, B);
   DV_REQUIRE(ptr >= 0 && ptr + B <= K, "queue pointer %d out of range", ptr);
-  return enqueue(keys, queue, B, d, K, ptr, ST);
+  return enqueue(keys, queue, B, d, K, ptr, nullptr, ST);
 }
 
 int dv_slice_mean(const void* x, float* out, int N, int S, int C, int ld, int coff, void* stream) {

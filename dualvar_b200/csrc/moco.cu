@@ -32,10 +32,12 @@ momentum_update_kernel(const long long* __restrict__ table, float m) {
   }
 }
 
-// keys: [B][d] row-major -> queue: [d][K] columns ptr .. ptr+B-1
+// keys: [B][d] row-major -> queue: [d][K] columns ptr .. ptr+B-1. ptr_dev != NULL: the pointer is read from the
+// model's own queue_ptr buffer (int64) - no host value in the launch, so a MoCo step replays as a CUDA graph.
 __global__ void enqueue_kernel(const float* __restrict__ keys, float* __restrict__ queue, int B, int d, int K,
-                               int ptr) {
+                               int ptr, const long long* __restrict__ ptr_dev) {
   __shared__ float tile[32][33];
+  if (ptr_dev != nullptr) ptr = (int)(*ptr_dev % K);
   const int b0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int b = b0 + j, c = c0 + threadIdx.x;
@@ -55,10 +57,20 @@ int momentum_update(const long long* table, int n_chunks, float m, cudaStream_t 
   return kOk;
 }
 
-int enqueue(const float* keys, float* queue, int B, int d, int K, int ptr, cudaStream_t stream) {
+int enqueue(const float* keys, float* queue, int B, int d, int K, int ptr, const long long* ptr_dev,
+            cudaStream_t stream) {
   dim3 block(32, 8);
   dim3 grid(ceil_div(B, 32), ceil_div(d, 32));
-  enqueue_kernel<<<grid, block, 0, stream>>>(keys, queue, B, d, K, ptr);
+  enqueue_kernel<<<grid, block, 0, stream>>>(keys, queue, B, d, K, ptr, ptr_dev);
+  DV_LAUNCH_OK();
+  return kOk;
+}
+
+// queue_ptr = (queue_ptr + batch) % K on the device (model/moco.py:352-353)
+__global__ void advance_ptr_kernel(long long* ptr, int batch, int K) { *ptr = (*ptr + batch) % K; }
+
+int advance_queue_ptr(long long* ptr, int batch, int K, cudaStream_t stream) {
+  advance_ptr_kernel<<<1, 1, 0, stream>>>(ptr, batch, K);
   DV_LAUNCH_OK();
   return kOk;
 }

@@ -260,23 +260,24 @@ class _MoCoBase(nn.Module):
         E.call("dv_moco_momentum_update", E.ptr(t), t.shape[0], ctypes.c_float(self.m), E.stream_ptr())
         E.invalidate_weights(pk for _, pk in self._pairs())
 
-    def _queue_ptr_host(self):
-        """Host mirror of queue_ptr (the reference does int(self.queue_ptr): a D2H sync every step)."""
-        ver = self.queue_ptr._version
-        if getattr(self, "_ptr_ver", None) != ver:
-            self._ptr_host = int(self.queue_ptr)
-        return self._ptr_host
+    @property
+    def graph_safe(self):
+        """A step can be replayed as one CUDA graph (graph_step.GraphedTrainStep): the queue pointer never leaves the
+        device. Not under shuffle-BN, whose permutation is drawn on the host every step (model/moco.py:371-381)."""
+        return not self._distributed_on()
 
     def _advance_ptr(self, batch):
-        ptr = (self._queue_ptr_host() + batch) % self.K
-        self.queue_ptr.fill_(ptr)
-        self._ptr_host, self._ptr_ver = ptr, self.queue_ptr._version
+        """queue_ptr = (queue_ptr + batch) % K on the device (model/moco.py:352-353; the reference reads the pointer
+        back with int(self.queue_ptr) every step - a device-to-host sync this path does not have)."""
+        E.call("dv_moco_advance_ptr", E.ptr(self.queue_ptr), batch, self.K, E.stream_ptr())
 
     @torch.no_grad()
-    def _enqueue(self, queue, keys, ptr):
+    def _enqueue(self, queue, keys):
+        """queue[:, ptr:ptr+B] = keys^T with ptr read from self.queue_ptr on the device (model/moco.py:343-351)."""
         B, d = keys.shape
         assert self.K % B == 0  # for simplicity (model/moco.py:347)
-        E.call("dv_moco_enqueue", E.ptr(keys.contiguous()), E.ptr(queue), B, d, self.K, ptr, E.stream_ptr())
+        E.call("dv_moco_enqueue_at", E.ptr(keys.contiguous()), E.ptr(queue), B, d, self.K, E.ptr(self.queue_ptr),
+               E.stream_ptr())
 
     def _distributed_on(self):
         return O._dist_on(self.distributed)
@@ -361,7 +362,7 @@ class MoCo_Naked(_MoCoBase):
         ret, self.last_hits = O.queue_contrast(q, k, self.queue, self.T, 'clip_')
         if in_train_mode:
             keys = concat_all_gather(k) if self._distributed_on() else k
-            self._enqueue(self.queue, keys, self._queue_ptr_host())
+            self._enqueue(self.queue, keys)
             self._advance_ptr(keys.shape[0])
         return ret
 
@@ -462,9 +463,8 @@ class MoCo_TimeSeriesV4(_MoCoBase):
             keys, skeys = k, series_k
             if self._distributed_on():
                 keys, skeys = concat_all_gather(keys), concat_all_gather(skeys)
-            ptr = self._queue_ptr_host()
-            self._enqueue(self.queue, keys, ptr)
-            self._enqueue(self.series_queue, skeys, ptr)
+            self._enqueue(self.queue, keys)
+            self._enqueue(self.series_queue, skeys)
             self._advance_ptr(keys.shape[0])
         # view 2 twice in one batch: as is, and with its segments shuffled (model/moco.py:543-557)
         perm = _draw_perms(B, s, dev)

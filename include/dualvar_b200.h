@@ -192,6 +192,11 @@ int dv_conv3d_stem_wgrad_bf16(const void* x_s2d, const void* dy, float* dws, con
 int dv_moco_momentum_update(const int64_t* chunk_table, int n_chunks, float m, void* stream);
 /* queue[:, ptr:ptr+B] = keys^T; queue fp32 (d, K), keys fp32 (B, d); K % B == 0 (model/moco.py:343-351) */
 int dv_moco_enqueue(const float* keys, float* queue, int B, int d, int K, int ptr, void* stream);
+/* the same with the pointer read on the device from the model's queue_ptr buffer (int64, model/moco.py:345), and
+ * queue_ptr = (queue_ptr + batch) % K (model/moco.py:352-353): no host value in the launches, so a MoCo step can be
+ * captured as a CUDA graph and the reference's per-step int(queue_ptr) device-to-host sync disappears */
+int dv_moco_enqueue_at(const float* keys, float* queue, int B, int d, int K, const int64_t* queue_ptr, void* stream);
+int dv_moco_advance_ptr(int64_t* queue_ptr, int batch, int K, void* stream);
 
 /* ---- S3D-G self-gating on channel slices of the Inception concat tensor (backbone/s3dg.py:68-78,130) ----
  * x rows have `ld` channels, the branch occupies [coff, coff+C). */

@@ -61,8 +61,11 @@ def test_graphed_step_trains_like_eager(net):
     # (the eager reference took its last two steps at the old learning rate: the first five steps are comparable.
     # Two EAGER runs already differ by ~1e-3 after a step - float atomics order in the statistics, amplified by the
     # update - so the bound is that run-to-run noise, not bit equality)
+    # (S3D-G at 4 samples of 8x64x64 is chaotic: its second EAGER step already differs by 2 % between two runs)
+    tol = 1e-2 if net == "r21d" else 0.15
+    assert graphed[0] == eager[0] or abs(graphed[0] - eager[0]) <= 1e-4 * abs(eager[0])
     for a, b_ in zip(eager[:5], graphed[:5]):
-        assert abs(a - b_) <= 1e-2 * abs(a), (eager, graphed)
+        assert abs(a - b_) <= tol * abs(a), (eager, graphed)
     assert int(m2.encoder_q[0].bn1.num_batches_tracked if net == "r21d" else m2.encoder_q[0].Conv_1a.bn1.num_batches_tracked) == 14
     # a batch of another shape falls back to an eager step, and the graph keeps working afterwards
     out = step(torch.rand(2, 3, 24, 64, 64).pin_memory())
@@ -71,14 +74,35 @@ def test_graphed_step_trains_like_eager(net):
     assert torch.isfinite(out["loss"]) and step.replays == 6
 
 
-def test_graph_refused_for_moco():
+def test_moco_step_replays_with_device_side_queue_pointer():
+    """MoCo+DualVar as a graph: the queue pointer is read and advanced on the device (dv_moco_enqueue_at /
+    dv_moco_advance_ptr), so replays enqueue at successive positions exactly like eager steps."""
     from dualvar_b200 import models as PM
     from dualvar_b200.graph_step import GraphedTrainStep
     from dualvar_b200.optim import SGD
     _seed(0)
     m = PM.MoCo_TimeSeriesV4("r3d", 128, 64, 0.99, 0.07, False, True, 2, 64, 0.07, 0.07, "clip-sr-tc", ARGS).to(dev).train()
-    opt = SGD([{"params": p} for p in m.parameters() if p.requires_grad], lr=0.01, momentum=0.9)
-    step = GraphedTrainStep(m, opt, n_views=3, warmup=0)
+    q0 = m.queue.clone()
+    opt = SGD([{"params": p} for p in m.parameters() if p.requires_grad], lr=1e-4, momentum=0.9)
+    step = GraphedTrainStep(m, opt, n_views=3, warmup=1)
+    assert step.enabled
+    g = torch.Generator().manual_seed(1)
+    for i in range(5):
+        out = step(torch.rand(4, 3, 24, 32, 32, generator=g).pin_memory())
+        assert torch.isfinite(out["loss"])
+        assert int(m.queue_ptr) == (4 * (i + 1)) % 64
+    assert step.eager_steps == 1 and step.captures == 1 and step.replays == 4
+    changed = (m.queue != q0).any(dim=0)
+    assert bool(changed[:20].all()) and not bool(changed[20:].any())          # five batches of four keys, nothing else
+    assert torch.allclose(m.queue[:, :20].norm(dim=0), torch.ones(20, device=dev), atol=1e-4)
+
+
+def test_graph_refused_for_torch_ddp_wrapper_and_unknown_models():
+    from dualvar_b200.graph_step import GraphedTrainStep
+
+    class Plain(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(3, device=dev))
+    step = GraphedTrainStep(Plain(), torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=0.1))
     assert not step.enabled
-    out = step(torch.rand(4, 3, 24, 32, 32).pin_memory())
-    assert torch.isfinite(out["loss"]) and step.eager_steps == 1 and step.captures == 0 and int(m.queue_ptr) == 4
