@@ -9,11 +9,11 @@ namespace dv {
 const std::string& last_error_ref();
 
 int conv_fprop_bf16(const void* x, const void* w_packed, void* y, double* stats, const float* bias,
-                    const ConvGeom& c, cudaStream_t stream, int y_f32 = 0);
+                    const ConvGeom& c, cudaStream_t stream, int y_f32 = 0, const float* xf_ss = nullptr, int xf_relu = 0);
 int conv_dgrad_bf16(const void* dy, const void* w_packed_t, void* dx, const ConvGeom& c,
                     cudaStream_t stream, const BnReduce* red, int dx_f32 = 0);
 int conv_wgrad_bf16(const void* x, const void* dy, float* dw, const ConvGeom& c, cudaStream_t stream,
-                    bool accumulate = false);
+                    bool accumulate = false, const float* xf_ss = nullptr, int xf_relu = 0);
 int pack_weights(const float* w, void* wf, void* wt, int Cout, int Cin, int taps, int Cout_p,
                  int Cin_p, cudaStream_t stream);
 int unpack_wgrad(const float* dwp, float* dw, int Cout, int Cin, int taps, int Cin_p, float beta,
@@ -212,6 +212,21 @@ int dv_conv3d_fprop_bf16(const void* x, const void* wf, void* y, double* bn_stat
   if (int rc = check_geom(g)) return rc;
   DV_REQUIRE(x && wf && y, "NULL tensor pointer");
   return conv_fprop_bf16(x, wf, y, bn_stats, bias_padded, to_geom<ConvGeom>(g), (cudaStream_t)stream);
+}
+
+int dv_conv3d_fprop_bnrelu_bf16(const void* y_prev, const float* ss_prev, int relu, const void* wf, void* y,
+                                double* bn_stats, const float* bias_padded, const dv_conv_geom* g, void* stream) {
+  if (int rc = check_geom(g)) return rc;
+  DV_REQUIRE(y_prev && ss_prev && wf && y, "NULL tensor pointer");
+  return conv_fprop_bf16(y_prev, wf, y, bn_stats, bias_padded, to_geom<ConvGeom>(g), (cudaStream_t)stream, 0, ss_prev,
+                         relu ? 1 : 0);
+}
+
+int dv_conv3d_wgrad_bnrelu_bf16(const void* y_prev, const float* ss_prev, int relu, const void* dy, float* dw_packed,
+                                const dv_conv_geom* g, void* stream) {
+  if (int rc = check_geom(g)) return rc;
+  DV_REQUIRE(y_prev && ss_prev && dy && dw_packed, "NULL tensor pointer");
+  return conv_wgrad_bf16(y_prev, dy, dw_packed, to_geom<ConvGeom>(g), (cudaStream_t)stream, false, ss_prev, relu ? 1 : 0);
 }
 
 int dv_conv3d_dgrad_bf16(const void* dy, const void* wt, void* dx, const dv_conv_geom* g,

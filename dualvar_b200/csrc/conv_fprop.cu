@@ -15,6 +15,7 @@
 //            (reference: nn.BatchNorm3d after every conv, e.g. backbone/r21d.py:56,106,111).
 // The grid is persistent (<= one CTA per SM); a CTA keeps one channel tile for its whole life so
 // BN partial sums stay in shared memory and are flushed to HBM once per CTA.
+#include "bn_xform.cuh"
 #include "conv_tile.cuh"
 #include "host_common.h"
 #include "ptx.cuh"
@@ -35,6 +36,7 @@ constexpr bool kDiag = false;   // product build: the counters and their branche
 #endif
 
 constexpr int kNumThreads = 320;            // warp 0 TMA, warp 1 MMA, warps 2-5 and 6-9: two epilogue groups
+constexpr int kXfThreads = 128;             // kXf instance: warps 10-13 transform the A boxes (consumer-side BatchNorm)
 constexpr int kEpiThreads = 256;
 constexpr int kAStageBytes = kTileM * 128;  // 16 KB
 constexpr int kOutBufBytes = kTileM * 128;  // one 64-channel chunk of the output tile
@@ -49,8 +51,11 @@ constexpr int kOutBufs = 4;                  // output staging buffers: two per 
 // leader CTA (cluster rank 0) issues MMAs; its full / accumulator-free barriers collect both CTAs' signals, commits
 // are multicast to both CTAs' barriers.
 // kF32: fp32-mode instance - the epilogue adds its fp32 rows to ConvTileParams::out_f32 (compiled out of the bf16 one).
-template <bool kPair, bool kF32 = false>
-__global__ void __launch_bounds__(kNumThreads, 1)
+// kXf: consumer-side BatchNorm instance (bn_xform.cuh): A boxes land on a CTA-local barrier, warps 10-13 apply
+//      relu?(scale*y + shift) in place and signal the (leader's) transform barrier the MMA warp waits for; the fused
+//      BatchNorm-backward reduce of the epilogue is compiled out of this instance (forward only).
+template <bool kPair, bool kF32 = false, bool kXf = false>
+__global__ void __launch_bounds__(kXf ? kNumThreads + kXfThreads : kNumThreads, 1)
 conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
@@ -58,6 +63,8 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ __align__(8) uint64_t bres_bar;
+  __shared__ __align__(8) uint64_t afull_bar[kXf ? kMaxStages : 1];   // kXf: this CTA's A box landed
+  __shared__ __align__(8) uint64_t xf_bar[kXf ? kMaxStages : 1];      // kXf (leader): A boxes of the stage transformed
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float s_part[8][2][kMaxBlockN];   // BN partial sums per epilogue warp: [group * 4 + row quarter][sum|sumsq][channel]
 
@@ -76,6 +83,8 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
   const int b_tap_bytes = (kPair ? p.block_n / 2 : p.block_n) * 128;   // one weight tile [block_n (/2)][64] of this CTA
   const int b_stage_bytes = p.b_resident ? 0 : p.max_group * b_tap_bytes;
   const int stage_bytes = p.a_stage_bytes + b_stage_bytes;
+  float* xf_table = reinterpret_cast<float*>(smem);         // kXf: [k_chunks][scale 64 | shift 64]
+  if (kXf) smem += (p.k_chunks * 512 + 1023) & ~1023;
   uint8_t* res_b = smem;                                    // resident weights: taps * k_chunks tiles
   uint8_t* ring = res_b + (p.b_resident ? p.num_taps * p.k_chunks * b_tap_bytes : 0);
   uint8_t* o_smem = ring + p.stages * stage_bytes;          // 2 * 16 KB output staging
@@ -93,9 +102,15 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
       mbar_init(&tmem_empty_bar[i], kPair ? 2 * kEpiThreads : kEpiThreads);   // the leader's barrier collects both CTAs' epilogues
     }
     mbar_init(&bres_bar, 1);
+    if (kXf)
+      for (int i = 0; i < p.stages; ++i) {
+        mbar_init(&afull_bar[i], 1);
+        mbar_init(&xf_bar[i], kPair ? 2 * kXfThreads : kXfThreads);   // the leader's barrier collects both CTAs' transforms
+      }
     fence_barrier_init();
   }
-  for (int c = threadIdx.x; c < 8 * 2 * kMaxBlockN; c += kNumThreads) (&s_part[0][0][0])[c] = 0.f;
+  for (int c = threadIdx.x; c < 8 * 2 * kMaxBlockN; c += blockDim.x) (&s_part[0][0][0])[c] = 0.f;
+  if (kXf) stage_ss_table(xf_table, p.xf_ss, p.xf_cp, p.k_chunks, threadIdx.x, blockDim.x);
   if (warp == 1) {
     if (kPair) {
       tmem_alloc2(&tmem_base_slot, kTmemCols);
@@ -151,15 +166,22 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
         for (int grp = 0; grp < p.num_groups; ++grp) {
           const int len = p.group_len[grp];
           const Tap lead = p.taps[gb];
-          const uint32_t tx_bytes = p.a_tx_bytes + (p.b_resident ? 0 : len * b_tap_bytes);
+          // kXf: the A box signals this CTA's own barrier (its transform warps wait there); only weight tiles count
+          // towards the leader's full barrier
+          const uint32_t tx_bytes = (kXf ? 0 : p.a_tx_bytes) + (p.b_resident ? 0 : len * b_tap_bytes);
           for (int kc = 0; kc < p.k_chunks; ++kc) {
             const long long c0 = (kDiag && p.prof) ? clock64() : 0;
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (kDiag && p.prof) prof_wait_empty += clock64() - c0;
             if (issuer) {
-              if (rank == 0) mbar_expect_tx(&full_bar[stage], tx_mult * tx_bytes);
+              if (rank == 0 && (!kXf || tx_bytes != 0)) mbar_expect_tx(&full_bar[stage], tx_mult * tx_bytes);
               const uint32_t full_addr = full0_addr + (uint32_t)stage * 8u;
               uint8_t* st = ring + stage * stage_bytes;
+              if (kXf) {
+                mbar_expect_tx(&afull_bar[stage], p.a_tx_bytes);
+                tma_load_5d(st, &p.a_map[lead.map], &afull_bar[stage], kc * kChunkK, w0 + lead.dw,
+                            h0 + g.org_h + lead.dh, t0 + lead.dt, n0);
+              } else
               tma_load_5d_to<kPair>(st, &p.a_map[lead.map], full_addr, kc * kChunkK, w0 + lead.dw,
                                     h0 + g.org_h + lead.dh, t0 + lead.dt, n0);
               if (!p.b_resident)
@@ -218,7 +240,8 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
           const int len = p.group_len[grp];
           for (int kc = 0; kc < p.k_chunks; ++kc) {
             const long long cf = (kDiag && p.prof) ? clock64() : 0;
-            mbar_wait(&full_bar[stage], phase);
+            if (!kXf || !p.b_resident) mbar_wait(&full_bar[stage], phase);   // TMA data (kXf: weight tiles only)
+            if (kXf) mbar_wait(&xf_bar[stage], phase);                       // both CTAs' A boxes transformed
             if (kDiag && p.prof) prof_wait_full += clock64() - cf;
             tc_fence_after_sync();
             // descriptor low words (start address >> 4 | LBO field); the high word is a constant
@@ -257,6 +280,36 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
         p.prof[blockIdx.x * 16 + 4] = prof_wait_acc;         // waiting for the epilogue to free an accumulator
       }
     }
+  } else if (kXf && warp >= 10) {
+    // ------------------------------------------------------------------ A-operand transform (kXf: warps 10-13)
+    const int tid = threadIdx.x - kNumThreads;
+    const uint32_t xf0_addr = kPair ? mapa_u32(smem_u32(&xf_bar[0]), 0) : smem_u32(&xf_bar[0]);
+    int stage = 0;
+    uint32_t phase = 0;
+    XfBox b;
+    b.rows = p.a_tx_bytes >> 7; b.lw = 31 - __clz(p.a_box[0]); b.bh = p.a_box[1]; b.bt = p.a_box[2];
+    for (int tile = unit; tile < p.total_tiles; tile += units) {
+      int m_id = m_index(tile);
+      const int wb = m_id % g.tiles_w; m_id /= g.tiles_w;
+      const int hb = m_id % g.tiles_h; m_id /= g.tiles_h;
+      const int tb = m_id % g.tiles_t; m_id /= g.tiles_t;
+      const int nb = m_id;
+      const int w0 = wb << g.lw, h0 = hb << g.lh, t0 = tb << g.lt, n0 = nb << g.ln;
+      int gb = 0;
+      for (int grp = 0; grp < p.num_groups; ++grp) {
+        const Tap lead = p.taps[gb];
+        b.ow = w0 + lead.dw; b.oh = h0 + g.org_h + lead.dh; b.ot = t0 + lead.dt; b.on = n0;
+        b.dw = p.a_dims[lead.map][0]; b.dh = p.a_dims[lead.map][1]; b.dt = p.a_dims[lead.map][2]; b.dn = p.a_dims[lead.map][3];
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(&afull_bar[stage], phase);
+          bnrelu_box_inplace(ring + stage * stage_bytes, b, xf_table + kc * 128, p.xf_relu, tid, kXfThreads);
+          fence_proxy_async_smem();      // generic-proxy writes -> visible to tcgen05.mma's async-proxy reads
+          if (kPair) mbar_arrive_cluster(xf0_addr + (uint32_t)stage * 8u); else mbar_arrive(&xf_bar[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        gb += p.group_len[grp];
+      }
+    }
   } else {
     // ------------------------------------------------------------------ epilogue (2 groups x 128 threads)
     const int q = warp & 3;            // TMEM lane quarter this warp may access
@@ -272,7 +325,7 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
     const int nchunks = (bn_mma + 63) >> 6;
     const int bcol = n_tile * p.block_n;
     const bool do_stats = p.stats != nullptr;
-    const bool red = do_stats && p.red_y != nullptr;
+    const bool red = !kXf && do_stats && p.red_y != nullptr;
     int it = 0;
     uint32_t obuf = 0;
     long long prof_epi_wait = 0, prof_ld = 0, prof_sts = 0, prof_bar = 0, prof_store = 0, prof_stat = 0, prof_yld = 0;
@@ -710,6 +763,7 @@ static int conv_multi_tap_region(ConvTileParams& P, MapEncoder enc, const void* 
     choose_tile(eN, eT, eH, eW, &g.ln, &g.lt, &g.lh, &g.lw);
     abox[0] = kChunkK; abox[1] = 1u << g.lw; abox[2] = 1u << g.lh; abox[3] = 1u << g.lt; abox[4] = 1u << g.ln;
   }
+  for (int i = 0; i < 4; ++i) P.a_box[i] = (int)abox[1 + i];
   g.ext_w = eW; g.ext_h = eH; g.ext_t = eT; g.ext_n = eN;
   g.org_h = org_h;
   g.tiles_w = ceil_div(eW, 1 << g.lw);
@@ -766,7 +820,9 @@ static int conv_multi_tap_region(ConvTileParams& P, MapEncoder enc, const void* 
   const bool pair = g_pair_enabled == 2 || (g_pair_enabled && m_tiles * P.n_tiles >= 2LL * sm_count());   // 2 = force (tests)
   P.total_tiles = (int)((pair ? (m_tiles + 1) / 2 : m_tiles) * P.n_tiles);
   const int b_tap_bytes = (pair ? P.block_n / 2 : P.block_n) * 128;
-  const int avail = kSmemBudget - 1024 - kOutBufs * kOutBufBytes;
+  const bool xf = P.xf_ss != nullptr;
+  const int xf_bytes = xf ? round_up(P.k_chunks * 512, 1024) : 0;      // staged scale / shift table
+  const int avail = kSmemBudget - 1024 - kOutBufs * kOutBufBytes - xf_bytes;
   const int res_bytes = ntaps * P.k_chunks * b_tap_bytes;
   // weight-stationary when the whole filter of this channel tile fits next to >= 3 A stages and the CTA
   // amortises the load over several tiles
@@ -790,6 +846,8 @@ static int conv_multi_tap_region(ConvTileParams& P, MapEncoder enc, const void* 
   P.f32_store = outv.store;
   if (P.out_f32 != nullptr && (stats != nullptr || red != nullptr))
     return fail(kBadArg, "fp32 accumulate output has no fused statistics");
+  if (xf && (P.out_f32 != nullptr || red != nullptr))
+    return fail(kBadArg, "consumer-side BatchNorm is a forward, bf16-output launch");
   if (red != nullptr) {
     // red->y is already offset to the output view's origin (stride-parity class)
     P.stats = red->sums;
@@ -813,7 +871,7 @@ static int conv_multi_tap_region(ConvTileParams& P, MapEncoder enc, const void* 
     int rc = encode_view(&P.out_map, outv, box);
     if (rc) return rc;
   }
-  const int smem_bytes = 1024 + (P.b_resident ? res_bytes : 0) + P.stages * stage_bytes + kOutBufs * kOutBufBytes;
+  const int smem_bytes = 1024 + xf_bytes + (P.b_resident ? res_bytes : 0) + P.stages * stage_bytes + kOutBufs * kOutBufBytes;
   static bool attr_set = false;
   if (!attr_set) {
     DV_CUDA_OK(cudaFuncSetAttribute(conv_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -824,6 +882,10 @@ static int conv_multi_tap_region(ConvTileParams& P, MapEncoder enc, const void* 
                                     kSmemBudget));
     DV_CUDA_OK(cudaFuncSetAttribute(conv_tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     kSmemBudget));
+    DV_CUDA_OK(cudaFuncSetAttribute(conv_tile_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kSmemBudget));
+    DV_CUDA_OK(cudaFuncSetAttribute(conv_tile_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kSmemBudget));
     attr_set = true;
   }
   // CTAs (or CTA pairs): one per SM (pair of SMs), a multiple of the channel-tile count
@@ -831,12 +893,13 @@ static int conv_multi_tap_region(ConvTileParams& P, MapEncoder enc, const void* 
   if (units > P.total_tiles) units = P.total_tiles;  // total_tiles is a multiple of n_tiles
   const bool f32 = P.out_f32 != nullptr;
   if (!pair) {
-    if (f32) conv_tile_kernel<false, true><<<units, kNumThreads, smem_bytes, stream>>>(P);
+    if (xf) conv_tile_kernel<false, false, true><<<units, kNumThreads + kXfThreads, smem_bytes, stream>>>(P);
+    else if (f32) conv_tile_kernel<false, true><<<units, kNumThreads, smem_bytes, stream>>>(P);
     else conv_tile_kernel<false><<<units, kNumThreads, smem_bytes, stream>>>(P);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * units);
-    cfg.blockDim = dim3(kNumThreads);
+    cfg.blockDim = dim3(xf ? kNumThreads + kXfThreads : kNumThreads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr;
@@ -844,7 +907,8 @@ static int conv_multi_tap_region(ConvTileParams& P, MapEncoder enc, const void* 
     attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    if (f32) DV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tile_kernel<true, true>, P));
+    if (xf) DV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tile_kernel<true, false, true>, P));
+    else if (f32) DV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tile_kernel<true, true>, P));
     else DV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tile_kernel<true>, P));
   }
   DV_LAUNCH_OK();
@@ -897,8 +961,12 @@ static int encode_from_viewset(CUtensorMap* m, const void* ctx, int view, const 
 }
 
 int conv_fprop_bf16(const void* x, const void* w_packed, void* y, double* stats, const float* bias,
-                    const ConvGeom& c, cudaStream_t stream, int y_f32) {
+                    const ConvGeom& c, cudaStream_t stream, int y_f32, const float* xf_ss, int xf_relu) {
   static thread_local ConvTileParams P;
+  // xf_ss != NULL: x is the RAW output of the convolution below and the operand is relu?(scale*x + shift) (bn_xform.cuh)
+  P.xf_ss = xf_ss;
+  P.xf_cp = c.Cin_p;
+  P.xf_relu = xf_relu;
   const View5 inv = make_ndhwc(x, c.N, c.T, c.H, c.W, c.Cin_p);
   View5 outv = make_ndhwc(y, c.N, c.To, c.Ho, c.Wo, c.Cout_p);
   if (y_f32) { outv.esize = 4; outv.store = y_f32 == 2; }   // y is float [N][To][Ho][Wo][Cout_p]: 1 = added to, 2 = overwritten
@@ -921,6 +989,7 @@ int conv_fprop_bf16(const void* x, const void* w_packed, void* y, double* stats,
           subsample(v, 2, rh, c.sh);
           subsample(v, 1, rw, c.sw);
           vs.v[nviews] = v;
+          for (int i = 0; i < 4; ++i) P.a_dims[nviews][i] = (int)v.dim[1 + i];
           map_of_parity[key] = nviews++;
         }
         taps.push_back({map_of_parity[key], floordiv(ot, c.st), floordiv(oh, c.sh), floordiv(ow, c.sw),
@@ -936,6 +1005,7 @@ int conv_fprop_bf16(const void* x, const void* w_packed, void* y, double* stats,
 int conv_dgrad_bf16(const void* dy, const void* w_packed_t, void* dx, const ConvGeom& c,
                     cudaStream_t stream, const BnReduce* red, int dx_f32) {
   static thread_local ConvTileParams P;
+  P.xf_ss = nullptr;
   ViewSet vs;
   vs.v[0] = make_ndhwc(dy, c.N, c.To, c.Ho, c.Wo, c.Cout_p);
   View5 dxv = make_ndhwc(dx, c.N, c.T, c.H, c.W, c.Cin_p);
@@ -1012,6 +1082,7 @@ int conv_stem_fprop_bf16(const void* x_s2d, const void* w_stem, void* y, double*
                          int N, int T, int H2, int W2, int Cout_p, int kt, int pt, cudaStream_t stream,
                          int y_f32) {
   static thread_local ConvTileParams P;
+  P.xf_ss = nullptr;
   const int To = T + 2 * pt - kt + 1;
   View5 outv = make_ndhwc(y, N, To, H2, W2, Cout_p);
   if (y_f32) { outv.esize = 4; outv.store = y_f32 == 2; }

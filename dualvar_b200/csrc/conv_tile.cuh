@@ -72,6 +72,13 @@ struct alignas(64) ConvTileParams {
   // out_map, the staging buffers and the BatchNorm statistics are unused in this mode.
   float* out_f32;
   int f32_store;   // 1: the first product of a sum overwrites the destination (plain 16-byte stores), 0: adds to it
+  // Consumer-side BatchNorm (bn_xform.cuh, kernel instance kXf): the A operand is the RAW output y of the convolution
+  // below; four extra warps turn every A box into z = relu?(scale*y + shift) in shared memory between the TMA and the
+  // MMA, so z is never written to HBM (reference: BatchNorm3d + ReLU between the two convs of SpatioTemporalConv).
+  const float* xf_ss;        // fp32 [2][xf_cp] scale, shift of the BatchNorm in front of this convolution
+  int xf_cp, xf_relu;
+  int a_box[4];              // A box extents along w (power of two), h, t, n
+  int a_dims[kMaxAMaps][4];  // W, H, T, N extents of every A tensor map (rows outside stay zero = conv padding)
 };
 
 // Optional fused BatchNorm-backward reduction request for conv_dgrad_bf16 (see ConvTileParams::red_y).

@@ -10,6 +10,7 @@
 //   D          = fp32 accumulators in TMEM, one per unit pair, all sharing the same dY tile
 // Split-K over position tiles across gridDim.y; partial results are reduced with fp32 red.global
 // into a zero-initialised [Cout_p][taps][Cin_p] buffer.
+#include "bn_xform.cuh"
 #include "conv_tile.cuh"
 #include "host_common.h"
 #include "ptx.cuh"
@@ -52,6 +53,12 @@ struct alignas(64) WgradParams {
   int unit_off[32];        // start of each unit inside its group's stage, in 16-byte units
   int16_t unit_widx[32];   // weight tap index of each unit
   int16_t unit_kc[32];     // 64-channel chunk of each unit
+  // Consumer-side BatchNorm (bn_xform.cuh): X is the RAW output y of the convolution below and the operand of this
+  // weight gradient is z = relu?(scale*y + shift), recomputed in shared memory (NULL: X is used as it is).
+  const float* xf_ss;      // fp32 [2][cin_p] scale, shift
+  int xf_relu;
+  int xb_h, xb_t;          // halo mode: box extents along h and t
+  int a_dims[kMaxAMaps][4];   // W, H, T, N extents of every X tensor map (row validity = the convolution's zero padding)
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -60,6 +67,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
   __shared__ __align__(8) uint64_t full_bar[8];
   __shared__ __align__(8) uint64_t empty_bar[8];
   __shared__ __align__(8) uint64_t acc_bar;
+  __shared__ __align__(8) uint64_t xf_bar[8];   // X boxes of a stage transformed (128 arrivals)
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform role index
@@ -79,7 +87,9 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
 
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (base - raw);
+  const bool xf = p.xf_ss != nullptr;
+  float* xf_table = reinterpret_cast<float*>(smem_raw + (base - raw));           // [k_chunks][scale 64 | shift 64]
+  uint8_t* smem = smem_raw + (base - raw) + (xf ? ((p.k_chunks * 512 + 1023) & ~1023) : 0);
   const int a_bytes = p.halo ? p.units_per_group * p.x_box_bytes : p.units_per_group * kBoxBytes;   // halo: units_per_group = max boxes per group
   const int b_bytes = ((p.block_n + 63) >> 6) * kBoxBytes;
   const int stage_bytes = a_bytes + b_bytes;
@@ -88,6 +98,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
+      mbar_init(&xf_bar[i], 128);
     }
     mbar_init(&acc_bar, 1);
     fence_barrier_init();
@@ -96,6 +107,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
     tmem_alloc(&tmem_base_slot, 512);
     tmem_relinquish();
   }
+  if (xf) stage_ss_table(xf_table, p.xf_ss, p.cin_p, p.k_chunks, threadIdx.x, kWgThreads);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -154,7 +166,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
     uint32_t phase = 0;
     uint32_t accumulate = 0;
     for (int tile = tile_begin; tile < tile_end; ++tile) {
-      mbar_wait(&full_bar[stage], phase);
+      mbar_wait(xf ? &xf_bar[stage] : &full_bar[stage], phase);
       tc_fence_after_sync();
       const uint32_t a_lo = lo_flags | (base_enc + (uint32_t)stage * stage_enc);
       const uint32_t b_lo = a_lo + a_enc;
@@ -186,6 +198,47 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
     if (issuer) umma_commit(&acc_bar);
     __syncwarp();
   } else {
+    if (xf) {
+      // ---- operand transform (warps 2-5 are otherwise idle until the accumulators are complete): every X box of a
+      // stage becomes z = relu?(scale*y + shift) in place once its TMA landed; the MMA warp waits for xf_bar
+      const int tid = threadIdx.x - 64;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        int m_id = tile;
+        const int wb = m_id % g.tiles_w; m_id /= g.tiles_w;
+        const int hb = m_id % g.tiles_h; m_id /= g.tiles_h;
+        const int tb = m_id % g.tiles_t; m_id /= g.tiles_t;
+        const int nb = m_id;
+        const int w0 = wb << g.lw, h0 = hb << g.lh, t0 = tb << g.lt, n0 = nb << g.ln;
+        mbar_wait(&full_bar[stage], phase);
+        uint8_t* a_s = smem + stage * stage_bytes;
+        XfBox b;
+        b.lw = g.lw;
+        if (p.halo) {
+          b.rows = p.x_box_bytes >> 7; b.bh = p.xb_h; b.bt = p.xb_t;
+          b.dw = p.a_dims[0][0]; b.dh = p.a_dims[0][1]; b.dt = p.a_dims[0][2]; b.dn = p.a_dims[0][3];
+          for (int i = 0; i < nbox; ++i) {
+            b.ow = w0 + p.box_dw[box0 + i]; b.oh = h0 + p.box_dh[box0 + i]; b.ot = t0 + p.box_dt[box0 + i]; b.on = n0;
+            bnrelu_box_inplace(a_s + i * p.x_box_bytes, b, xf_table + p.box_kc[box0 + i] * 128, p.xf_relu, tid, 128);
+          }
+        } else {
+          b.rows = 64; b.bh = 1 << g.lh; b.bt = 1 << g.lt;
+          for (int i = 0; i < nu; ++i) {
+            const int u = unit0 + i;
+            const int tap = u / p.k_chunks;
+            const int kc = u - tap * p.k_chunks;
+            const Tap tp = p.taps[tap];
+            b.dw = p.a_dims[tp.map][0]; b.dh = p.a_dims[tp.map][1]; b.dt = p.a_dims[tp.map][2]; b.dn = p.a_dims[tp.map][3];
+            b.ow = w0 + tp.dw; b.oh = h0 + tp.dh; b.ot = t0 + tp.dt; b.on = n0;
+            bnrelu_box_inplace(a_s + i * kBoxBytes, b, xf_table + kc * 128, p.xf_relu, tid, 128);
+          }
+        }
+        fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        mbar_arrive(&xf_bar[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
     const int q = warp & 3;
     const int row = q * 32 + lane;
     mbar_wait(&acc_bar, 0);
@@ -280,13 +333,15 @@ static int wgrad_launch(WgradParams& P, int ntaps, int cin_p, int cout_p, int ta
   } else {
     if (upg > kWgMaxUnits) upg = kWgMaxUnits;
     // keep at least 3 stages in shared memory
-    while (upg > 2 && (kWgSmemBudget - 1024) / ((upg + nbx) * kBoxBytes) < 3) upg -= 2;
+    const int budget = kWgSmemBudget - 1024 - (P.xf_ss != nullptr ? round_up(P.k_chunks * 512, 1024) : 0);
+    while (upg > 2 && budget / ((upg + nbx) * kBoxBytes) < 3) upg -= 2;
     if (upg > P.total_units) upg = P.total_units;
     stage_bytes = (upg + nbx) * kBoxBytes;
   }
   P.units_per_group = upg;
   const int groups = P.halo ? P.n_groups : ceil_div(P.total_units, upg);
-  P.stages = (kWgSmemBudget - 1024) / stage_bytes;
+  const int xf_bytes = P.xf_ss != nullptr ? round_up(P.k_chunks * 512, 1024) : 0;
+  P.stages = (kWgSmemBudget - 1024 - xf_bytes) / stage_bytes;
   if (P.stages > 8) P.stages = 8;
   if (P.stages < 2) return fail(kUnsupported, "wgrad: stage too large for shared memory");
   P.pos_tiles = g.tiles_w * g.tiles_h * g.tiles_t * g.tiles_n;
@@ -305,7 +360,7 @@ static int wgrad_launch(WgradParams& P, int ntaps, int cin_p, int cout_p, int ta
                                     kWgSmemBudget));
     attr_set = true;
   }
-  const int smem_bytes = 1024 + P.stages * stage_bytes;
+  const int smem_bytes = 1024 + xf_bytes + P.stages * stage_bytes;
   dim3 grid(items, ksplit);
   conv_wgrad_kernel<<<grid, kWgThreads, smem_bytes, stream>>>(P);
   DV_LAUNCH_OK();
@@ -313,9 +368,12 @@ static int wgrad_launch(WgradParams& P, int ntaps, int cin_p, int cout_p, int ta
 }
 
 int conv_wgrad_bf16(const void* x, const void* dy, float* dw, const ConvGeom& c,
-                    cudaStream_t stream, bool accumulate) {
+                    cudaStream_t stream, bool accumulate, const float* xf_ss, int xf_relu) {
   static thread_local WgradParams P;
   const int taps_total = c.kt * c.kh * c.kw;
+  P.xf_ss = xf_ss;
+  P.xf_relu = xf_relu;
+  for (int i = 0; i < kMaxAMaps; ++i) { P.a_dims[i][0] = c.W; P.a_dims[i][1] = c.H; P.a_dims[i][2] = c.T; P.a_dims[i][3] = c.N; }
   // accumulate (fp32 mode): dw already holds the sum of earlier operand-plane products; the kernel only adds
   if (!accumulate) DV_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)c.Cout_p * taps_total * c.Cin_p, stream));
   P.halo = 0;
@@ -372,13 +430,16 @@ int conv_wgrad_bf16(const void* x, const void* dy, float* dw, const ConvGeom& c,
       const int n_boxes = temporal ? k_chunks : c.kw * k_chunks;
       // groups: whole boxes, at most 2*max_pairs units each
       int boxes_per_group = std::max(1, (2 * max_pairs) / span);
-      while (boxes_per_group > 1 && 3 * (boxes_per_group * x_box_bytes + nbx * kBoxBytes) > kWgSmemBudget - 1024)
+      const int budget = kWgSmemBudget - 1024 - (xf_ss != nullptr ? round_up(k_chunks * 512, 1024) : 0);
+      while (boxes_per_group > 1 && 3 * (boxes_per_group * x_box_bytes + nbx * kBoxBytes) > budget)
         --boxes_per_group;
       const int n_groups = ceil_div(n_boxes, boxes_per_group);
       if ((temporal || waste <= 1.16) && n_boxes <= 32 && n_groups <= 8 &&
-          3 * (std::min(boxes_per_group, n_boxes) * x_box_bytes + nbx * kBoxBytes) <= kWgSmemBudget - 1024) {
+          3 * (std::min(boxes_per_group, n_boxes) * x_box_bytes + nbx * kBoxBytes) <= budget) {
         P.halo = 1;
         P.x_box_bytes = x_box_bytes;
+        P.xb_h = (1 << g.lh) + (spatial ? c.kh - 1 : 0);
+        P.xb_t = (1 << g.lt) + (temporal ? c.kt - 1 : 0);
         g.ext_w = c.Wo; g.ext_h = c.Ho; g.ext_t = c.To; g.ext_n = c.N;
         g.tiles_w = ceil_div(c.Wo, 1 << g.lw);
         g.tiles_h = ceil_div(c.Ho, 1 << g.lh);
@@ -474,6 +535,7 @@ int conv_wgrad_bf16(const void* x, const void* dy, float* dw, const ConvGeom& c,
           }
           rc = encode5(&P.a_map[nmaps], bp, dim, str);
           if (rc) return rc;
+          for (int i = 0; i < 3; ++i) P.a_dims[nmaps][i] = (int)dim[1 + i];
           map_of_parity[key] = nmaps++;
         }
         Tap& tp = P.taps[ntaps++];
@@ -492,6 +554,7 @@ int conv_wgrad_bf16(const void* x, const void* dy, float* dw, const ConvGeom& c,
 int conv_stem_wgrad_bf16(const void* x_s2d, const void* dy, float* dw, int N, int T, int H2, int W2,
                          int Cout_p, int kt, int pt, cudaStream_t stream, bool accumulate) {
   static thread_local WgradParams P;
+  P.xf_ss = nullptr;
   const int To = T + 2 * pt - kt + 1;
   const int taps_total = kt * 4;
   if (!accumulate) DV_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout_p * taps_total * 64, stream));

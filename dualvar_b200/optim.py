@@ -68,7 +68,7 @@ class SGD(torch.optim.Optimizer):
                 key = (group["lr"], group["momentum"], group["weight_decay"], first)
                 batches.setdefault(key, []).append(p)
         for (lr, mu, wd, first), plist in batches.items():
-            t = self._table((first, len(plist), plist[0].data_ptr()), plist)      # pointers only: survives an lr change
+            t = self._table((len(plist), plist[0].data_ptr()), plist)      # pointers only: survives an lr change and the first step
             f = ctypes.c_float
             _lib.call("dv_sgd_momentum_step", ptr(t), t.shape[0], f(lr), f(mu), f(wd), 1 if first else 0, stream_ptr())
         from . import engine

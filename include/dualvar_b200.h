@@ -59,6 +59,16 @@ int dv_ndhwc_bf16_to_ncdhw(const void* y, float* x, int N, int C, int Cp, int64_
  * of the stored outputs into bn_stats[0:Cout_p] and bn_stats[Cout_p:2*Cout_p] (double, caller zeroes). */
 int dv_conv3d_fprop_bf16(const void* x, const void* wf, void* y, double* bn_stats,
                          const float* bias_padded, const dv_conv_geom* g, void* stream);
+/* Consumer-side BatchNorm: the convolution whose INPUT is z = relu?(scale*y_prev + shift) with y_prev the raw output
+ * of the convolution below and ss_prev = [2][Cin_p] scale, shift from dv_bn_finalize (reference: nn.BatchNorm3d +
+ * nn.ReLU between the spatial and temporal convs of SpatioTemporalConv, backbone/r21d.py:56-57,67-70). z is never
+ * written to HBM: the kernels load the raw tile by TMA and apply the affine + ReLU in shared memory in front of
+ * tcgen05.mma (rows the TMA zero-filled - the conv padding - stay zero). Results are bit-identical to
+ * dv_bn_apply followed by dv_conv3d_fprop_bf16 / dv_conv3d_wgrad_bf16 on its output. */
+int dv_conv3d_fprop_bnrelu_bf16(const void* y_prev, const float* ss_prev, int relu, const void* wf, void* y,
+                                double* bn_stats, const float* bias_padded, const dv_conv_geom* g, void* stream);
+int dv_conv3d_wgrad_bnrelu_bf16(const void* y_prev, const float* ss_prev, int relu, const void* dy, float* dw_packed,
+                                const dv_conv_geom* g, void* stream);
 /* dx = conv_transpose(dy, w) */
 int dv_conv3d_dgrad_bf16(const void* dy, const void* wt, void* dx, const dv_conv_geom* g,
                          void* stream);

@@ -1,6 +1,7 @@
 """Multi-GPU diagnostic (torchrun, one rank per GPU): where does the weak-scaling loss of the bench step go?
 
-Times the bench step (r21d SimCLR+DualVar, 64 samples per GPU, SyncBatchNorm, resident inputs, eager issue) in variants:
+Times the bench step (r21d SimCLR+DualVar, 64 samples per GPU, SyncBatchNorm, resident inputs; replayed as one CUDA graph
+per rank like bench.py does - GRAPH=0 issues it eagerly, which hides most of the differences behind host time) in variants:
   full/overlap   dualvar_b200.parallel.DataParallel (bucketed gradient all-reduce inside the backward) - the default
   full/torch     torch DistributedDataParallel (all-reduce after the one-node backbone backward)
   no_grad_sync   gradient all-reduce skipped (no_sync) - what the reduction costs end to end
@@ -24,6 +25,8 @@ from dualvar_b200 import engine as E, models as PM
 from dualvar_b200.engine import RawClips
 from dualvar_b200.optim import SGD
 from dualvar_b200.parallel import DataParallel
+from dualvar_b200.graph_step import GraphedTrainStep
+GRAPH = os.environ.get("GRAPH", "1") != "0"
 
 B = int(os.environ.get("B", "64"))
 STEPS = int(os.environ.get("STEPS", "8"))
@@ -44,15 +47,20 @@ def run(tag, wrapper, grad_sync=True, bn_sync=True):
     E._is_sync = real_is_sync if bn_sync else (lambda bn: False)
     model, opt = build(wrapper)
 
+    graphed = GraphedTrainStep(model, opt, n_views=3, warmup=1) if GRAPH and wrapper == "overlap" else None
+
     def step():
         ctx = contextlib.nullcontext() if grad_sync else model.no_sync()
         with ctx:
+            if graphed is not None:
+                graphed(frames)
+                return
             ret = model(RawClips(frames, 3))
             loss = sum(v for k, v in ret.items() if "loss" in k)
             opt.zero_grad(set_to_none=True)
             loss.backward()
         opt.step()
-    for _ in range(3):
+    for _ in range(4):
         step()
     dist.barrier(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -65,7 +73,9 @@ def run(tag, wrapper, grad_sync=True, bn_sync=True):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
         print(f"{tag:14s} {float(t):8.2f} ms/step  {B * world / float(t) * 1e3:9.1f} samples/s  ({world} GPUs)", flush=True)
-    del model, opt
+    if graphed is not None:
+        graphed.release()
+    del model, opt, graphed
     torch.cuda.empty_cache()
     E._is_sync = real_is_sync
 
