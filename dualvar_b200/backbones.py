@@ -77,7 +77,8 @@ class SpatioTemporalConv(nn.Module):
 
     def run(self, ctx, x, out_bn):
         """spatial conv -> BN -> ReLU -> temporal conv; returns the raw output paired with out_bn."""
-        h = E.activate(ctx, E.conv_stats(ctx, x, self.spatial_conv, self.bn))
+        # the BatchNorm + ReLU between the two convs feeds the temporal conv only: applied inside it (consumer-side)
+        h = E.activate(ctx, E.conv_stats(ctx, x, self.spatial_conv, self.bn), conv_only=True)
         return E.conv_stats(ctx, h, self.temporal_conv, out_bn)
 
 

@@ -63,11 +63,12 @@ class Act:
     """An NDHWC activation [N,T,H,W,Cp] with C logical channels and an optional gradient: bf16 ``data`` in the bf16
     mode; in the fp32 mode fp32 ``data`` (None for the ingested clips) plus its bf16 split ``planes`` [K,N,T,H,W,Cp]."""
 
-    __slots__ = ("data", "C", "grad", "grad2", "needs_grad", "s2d", "bnred", "fused", "planes")
+    __slots__ = ("data", "C", "grad", "grad2", "needs_grad", "s2d", "bnred", "fused", "planes", "lazy")
 
-    def __init__(self, data, C, needs_grad=True, s2d=None, planes=None):
+    def __init__(self, data, C, needs_grad=True, s2d=None, planes=None, lazy=None):
         self.data = data
         self.planes = planes
+        self.lazy = lazy        # (RawBN, relu): z = relu?(BN(y)) exists only inside its consumer conv (never in HBM)
         self.C = C
         self.grad = None
         self.grad2 = None       # second pending contribution (summed lazily by the consumer)
@@ -78,7 +79,14 @@ class Act:
 
     @property
     def shape5(self):
+        if self.lazy is not None:
+            return tuple(self.lazy[0].y.shape)
         return tuple(self.data.shape) if self.data is not None else tuple(self.planes.shape[1:])
+
+    @property
+    def stored(self):
+        """The tensor in HBM that stands for this activation: z itself, or the raw y of a lazy one."""
+        return self.lazy[0].y if self.lazy is not None else self.data
 
     @property
     def rows(self):
@@ -91,6 +99,8 @@ class Act:
 
     @property
     def device(self):
+        if self.lazy is not None:
+            return self.lazy[0].y.device
         return self.data.device if self.data is not None else self.planes.device
 
 
@@ -473,6 +483,14 @@ def conv_stats(ctx, x, conv, bn):
         packed = (packed_stem_weights(conv, g), None)
         call("dv_conv3d_stem_fprop_bf16", ptr(x.data), ptr(packed[0]), ptr(y), ptr(stats),
              ptr(_bias_padded(conv, g.Cout_p)), ctypes.byref(g), stream_ptr())
+    elif x.lazy is not None:
+        # consumer-side BatchNorm: this conv reads the RAW output of the conv below and applies its BatchNorm + ReLU
+        # to the operand tile in shared memory (csrc/bn_xform.cuh) - the activation in between never exists in HBM
+        y = torch.empty((N, g.To, g.Ho, g.Wo, g.Cout_p), dtype=torch.bfloat16, device=dev)
+        packed = packed_weights(conv)
+        rp, relu_p = x.lazy
+        call("dv_conv3d_fprop_bnrelu_bf16", ptr(rp.y), ptr(rp.ss), 1 if relu_p else 0, ptr(packed[0]), ptr(y), ptr(stats),
+             ptr(_bias_padded(conv, g.Cout_p)), ctypes.byref(g), stream_ptr())
     else:
         y = torch.empty((N, g.To, g.Ho, g.Wo, g.Cout_p), dtype=torch.bfloat16, device=dev)
         packed = packed_weights(conv)
@@ -558,7 +576,12 @@ def _wgrad(r, dy, gw):
         call("dv_unpack_stem_wgrad", ptr(dwp), ptr(gw), ctypes.byref(g), ctypes.c_float(0.0), stream_ptr())
     else:
         dwp = torch.empty((g.Cout_p, g.taps, g.Cin_p), dtype=torch.float32, device=dy.device)
-        call("dv_conv3d_wgrad_bf16", ptr(r.x.data), ptr(dy), ptr(dwp), ctypes.byref(g), stream_ptr())
+        if r.x.lazy is not None:      # the operand z is recomputed from the raw y of the conv below (never stored)
+            rp, relu_p = r.x.lazy
+            call("dv_conv3d_wgrad_bnrelu_bf16", ptr(rp.y), ptr(rp.ss), 1 if relu_p else 0, ptr(dy), ptr(dwp),
+                 ctypes.byref(g), stream_ptr())
+        else:
+            call("dv_conv3d_wgrad_bf16", ptr(r.x.data), ptr(dy), ptr(dwp), ctypes.byref(g), stream_ptr())
         call("dv_unpack_conv_wgrad", ptr(dwp), ptr(gw), ctypes.byref(g), ctypes.c_float(0.0), stream_ptr())
 
 
@@ -603,7 +626,7 @@ def _conv_backward(ctx, r, dy):
             _wgrad(r, dy, gw)
         # the caching allocator must not hand these blocks to later main-stream work while the side stream reads them
         dy.record_stream(side)
-        r.x.data.record_stream(side)
+        r.x.stored.record_stream(side)
         gw.record_stream(side)
         ctx.side_used = True
     else:
@@ -616,7 +639,7 @@ def _conv_backward(ctx, r, dy):
         # a bias in front of training-mode BN has exactly zero gradient (BN removes the mean)
         ctx.add_param_grad(r.conv.bias, torch.zeros_like(r.conv.bias))
     if r.x.needs_grad:
-        dx = torch.empty_like(r.x.data)
+        dx = torch.empty_like(r.x.stored)
         if r.x.bnred is not None and r.x.grad is None and _fuse_reduce_pays(g):
             # x = relu?(BN(y_prev)) and this is (so far) its only gradient: the dgrad epilogue also produces
             # the BN-backward sums of the layer below, saving dv_bn_bwd_reduce's pass over dx and y_prev
@@ -719,16 +742,29 @@ def _activate_f32(ctx, r1, r2, res, relu, out=None, out_coff=0):
     return out_act
 
 
-def activate(ctx, r1, r2=None, res=None, relu=True, out=None, out_coff=0):
+# Consumer-side BatchNorm (csrc/bn_xform.cuh): a plain relu?(BN(y)) whose only consumer is a convolution is not
+# written to HBM - the consumer's fprop and wgrad load the raw y and normalise the operand tile in shared memory.
+# DV_FUSE_BN_APPLY=0 restores the stand-alone dv_bn_apply pass (bit-identical results).
+FUSE_BN_APPLY = os.environ.get("DV_FUSE_BN_APPLY", "1") != "0"
+
+
+def activate(ctx, r1, r2=None, res=None, relu=True, out=None, out_coff=0, conv_only=False):
     """out = relu?(BN(r1) [+ BN(r2)] [+ res]). ``out``/``out_coff`` let several branches write
-    channel slices of one tensor (concat-free Inception, backbone/s3dg.py:130).
-    Reference: BatchNorm3d affine + ReLU + residual add (backbone/r21d.py:116-122)."""
+    channel slices of one tensor (concat-free Inception, backbone/s3dg.py:130). ``conv_only``: the caller promises
+    that the result feeds exactly one conv_stats() and nothing else (the BatchNorm + ReLU between the two convs of a
+    factorised convolution) - it is then applied inside that convolution instead of being stored.
+    Reference: BatchNorm3d affine + ReLU + residual add (backbone/r21d.py:56-57,116-122)."""
     if fp32_mode():
         return _activate_f32(ctx, r1, r2, res, relu, out, out_coff)
     g = r1.geom
     Cp = g.Cout_p
     dev = r1.y.device
-    if out is None:
+    lazy = conv_only and FUSE_BN_APPLY and r2 is None and res is None and out is None
+    if lazy:
+        out_t = None
+        out_act = Act(None, g.Cout, lazy=(r1, relu))
+        out_ld = Cp
+    elif out is None:
         out_t = torch.empty_like(r1.y)
         out_act = Act(out_t, g.Cout)
         out_ld = Cp
@@ -737,9 +773,10 @@ def activate(ctx, r1, r2=None, res=None, relu=True, out=None, out_coff=0):
         out_t = out.data
         out_ld = out.Cp
     rows = r1.y.numel() // Cp
-    call("dv_bn_apply", ptr(r1.y), ptr(r1.ss), ptr(r2.y) if r2 else None, ptr(r2.ss) if r2 else None,
-         ptr(res.data) if res is not None else None, ptr(out_t), rows, Cp, out_ld, out_coff,
-         1 if relu else 0, stream_ptr())
+    if not lazy:
+        call("dv_bn_apply", ptr(r1.y), ptr(r1.ss), ptr(r2.y) if r2 else None, ptr(r2.ss) if r2 else None,
+             ptr(res.data) if res is not None else None, ptr(out_t), rows, Cp, out_ld, out_coff,
+             1 if relu else 0, stream_ptr())
     if not ctx.record:
         return out_act
     plain = r2 is None and res is None and out is None

@@ -52,7 +52,7 @@ class STConv3d(nn.Module):
             bn.bias.data.zero_()
 
     def run(self, ctx, x, out=None, coff=0):
-        h = E.activate(ctx, E.conv_stats(ctx, x, self.conv1, self.bn1))
+        h = E.activate(ctx, E.conv_stats(ctx, x, self.conv1, self.bn1), conv_only=True)   # feeds conv2 only: applied inside it
         raw = E.conv_stats(ctx, h, self.conv2, self.bn2)
         return E.activate(ctx, raw, out=out, out_coff=coff), raw
 

@@ -164,3 +164,54 @@ def test_space_to_depth_stem_matches_torch(kt, pt, Cout, H, W):
     _lib.call("dv_unpack_stem_wgrad", _lib.ptr(dws), _lib.ptr(dw), ctypes.byref(g), ctypes.c_float(0.0),
               _lib.stream_ptr())
     assert _rel(dw, wr.grad) < 1e-4
+
+
+XF_CASES = [c for c in CASES if "stem" not in c[0]] + [
+    ("temporal 144->64 56x56 (CTA pairs, weight-stationary)", 12, 16, 56, 56, 144, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0)),
+    ("temporal 83->64 (Cin_p = 88)", 4, 8, 28, 28, 83, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0)),
+    ("temporal s2 460->256 14x14", 3, 8, 14, 14, 460, 256, (3, 1, 1), (2, 1, 1), (1, 0, 0)),
+]
+
+
+@pytest.mark.parametrize("relu", [True, False])
+@pytest.mark.parametrize("case", XF_CASES, ids=lambda c: c[0])
+def test_consumer_side_batchnorm_is_bit_identical_to_the_two_pass_path(case, relu):
+    """dv_conv3d_fprop_bnrelu_bf16 / dv_conv3d_wgrad_bnrelu_bf16 (the BatchNorm + ReLU of the activation applied to the
+    operand tile in shared memory, csrc/bn_xform.cuh) against dv_bn_apply followed by the plain kernels: the forward
+    output and its fused statistics bit for bit (same MMA order on identical operand bits), the weight gradient up to the
+    fp32 atomics order of its split-K reduction. Zero padding, partial tiles, strided views and padded channels are all
+    in the case list; the shift is made large so that a padding row wrongly normalised (relu(shift) != 0) shows."""
+    import ctypes
+    import kernel_handles as K
+    from dualvar_b200 import _lib
+    from dualvar_b200._lib import ptr, stream_ptr
+    name, N, T, H, W, Cin, Cout, k, s, p = case
+    dev = "cuda:0"
+    g = K.make_geom(N, T, H, W, Cin, Cout, k, s, p)
+    gen = torch.Generator(device=dev).manual_seed(abs(hash(name)) % (2 ** 31))
+    y_prev = K.to_ndhwc(torch.randn(N, Cin, T, H, W, device=dev, generator=gen))         # raw output of the conv below
+    ss = torch.zeros(2 * g.Cin_p, device=dev)
+    ss[:Cin] = torch.rand(Cin, device=dev, generator=gen) + 0.5                            # scale
+    ss[g.Cin_p:g.Cin_p + Cin] = torch.randn(Cin, device=dev, generator=gen) + 0.7         # shift (mostly positive)
+    w = torch.randn(Cout, Cin, *k, device=dev, generator=gen) / (Cin * k[0] * k[1] * k[2]) ** 0.5
+    wf, wt = K.pack_conv_weight(w, g)
+    rows = y_prev.numel() // g.Cin_p
+    z = torch.empty_like(y_prev)
+    _lib.call("dv_bn_apply", ptr(y_prev), ptr(ss), None, None, None, ptr(z), rows, g.Cin_p, g.Cin_p, 0, 1 if relu else 0,
+              stream_ptr())
+    st_a = torch.zeros(2 * g.Cout_p, dtype=torch.float64, device=dev)
+    y_a = K.conv3d_fprop(z, wf, g, bn_stats=st_a)
+    st_b = torch.zeros(2 * g.Cout_p, dtype=torch.float64, device=dev)
+    y_b = torch.empty_like(y_a)
+    _lib.call("dv_conv3d_fprop_bnrelu_bf16", ptr(y_prev), ptr(ss), 1 if relu else 0, ptr(wf), ptr(y_b), ptr(st_b), None,
+              ctypes.byref(g), stream_ptr())
+    assert torch.equal(y_a, y_b), (y_a.float() - y_b.float()).abs().max().item()
+    torch.testing.assert_close(st_b, st_a, rtol=1e-12, atol=1e-6)
+    dy = torch.randn(y_a.shape, device=dev, generator=gen).bfloat16()
+    if g.Cout_p > Cout:
+        dy[..., Cout:] = 0
+    dw_a = K.conv3d_wgrad_packed(z, dy, g)
+    dw_b = torch.empty_like(dw_a)
+    _lib.call("dv_conv3d_wgrad_bnrelu_bf16", ptr(y_prev), ptr(ss), 1 if relu else 0, ptr(dy), ptr(dw_b), ctypes.byref(g),
+              stream_ptr())
+    assert ((dw_a - dw_b).abs().max() / dw_a.abs().max()).item() < 2e-5
