@@ -531,7 +531,8 @@ def run_ours(args):
     _engine.WGRAD_SIDE_STREAM = False
     _engine.PASS_STREAMS = False
     conv_names = ["dv_conv3d_fprop_bf16", "dv_conv3d_dgrad_bf16", "dv_conv3d_dgrad_bnred_bf16", "dv_conv3d_wgrad_bf16",
-                  "dv_conv3d_stem_fprop_bf16", "dv_conv3d_stem_wgrad_bf16"]
+                  "dv_conv3d_stem_fprop_bf16", "dv_conv3d_stem_wgrad_bf16", "dv_conv3d_fprop_bnrelu_bf16",
+                  "dv_conv3d_wgrad_bnrelu_bf16"]
     bn_names = ["dv_bn_apply", "dv_bn_bwd_reduce", "dv_bn_bwd_apply"]
     timer = _lib.KernelTimer(conv_names + bn_names, detail=True)
     _lib.set_timer(timer)
@@ -609,8 +610,8 @@ def run_ours(args):
                            "tflops": d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0}
         # group the C-ABI calls by the CUDA kernel that serves them
         groups = {"conv_tile_kernel": ["dv_conv3d_fprop_bf16", "dv_conv3d_dgrad_bf16", "dv_conv3d_dgrad_bnred_bf16",
-                                       "dv_conv3d_stem_fprop_bf16"],
-                  "conv_wgrad_kernel": ["dv_conv3d_wgrad_bf16", "dv_conv3d_stem_wgrad_bf16"]}
+                                       "dv_conv3d_stem_fprop_bf16", "dv_conv3d_fprop_bnrelu_bf16"],
+                  "conv_wgrad_kernel": ["dv_conv3d_wgrad_bf16", "dv_conv3d_stem_wgrad_bf16", "dv_conv3d_wgrad_bnrelu_bf16"]}
         kern = {}
         for kname, members in groups.items():
             ms = sum(ksum[m]["ms"] for m in members if m in ksum)

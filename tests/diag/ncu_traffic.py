@@ -13,8 +13,8 @@ import sys
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "second": 1e6,
         "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
 GROUPS = {"conv_tile_kernel": ("dv_conv3d_fprop_bf16", "dv_conv3d_dgrad_bf16", "dv_conv3d_dgrad_bnred_bf16",
-                               "dv_conv3d_stem_fprop_bf16"),
-          "conv_wgrad_kernel": ("dv_conv3d_wgrad_bf16", "dv_conv3d_stem_wgrad_bf16"),
+                               "dv_conv3d_stem_fprop_bf16", "dv_conv3d_fprop_bnrelu_bf16"),
+          "conv_wgrad_kernel": ("dv_conv3d_wgrad_bf16", "dv_conv3d_stem_wgrad_bf16", "dv_conv3d_wgrad_bnrelu_bf16"),
           "bn_passes": ("dv_bn_apply", "dv_bn_bwd_reduce", "dv_bn_bwd_apply")}
 
 
