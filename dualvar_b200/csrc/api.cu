@@ -118,6 +118,12 @@ int bn_finalize_sync(const double* stats, const float* gamma, const float* beta,
 int bn_bwd_finalize_sync(const double* sums_local, const float* gamma, const float* saved, float* dgamma, float* dbeta,
                          float* coef, int C, int Cp, double count_global, float grad_beta, const long long* peer_ptrs,
                          int rank, int world, long long seq, cudaStream_t stream);
+int jpeg_probe_host(const uint8_t* data, long long len, int* info8, long long* coef_count);
+int jpeg_huffman_decode_host(const uint8_t* const* files, const long long* lens, int n, const int* info8, int16_t* coef,
+                             long long coef_stride, uint16_t* qt, int n_threads);
+long long jpeg_plane_bytes(const int* info8);
+int jpeg_idct_rgb_u8(const int16_t* coef, const uint16_t* qt, uint8_t* planes, uint8_t* rgb, int n, const int* info8,
+                     long long coef_stride, cudaStream_t stream);
 void comm_set_timeout(double seconds);
 int comm_status(int* peer, long long* seq, int clear);
 int small_allreduce_f64(double* inout, int n, const long long* peer_ptrs, int rank, int world, long long seq,
@@ -705,6 +711,30 @@ int dv_bn_bwd_finalize_sync(const double* sums_local, const float* gamma, const 
   DV_REQUIRE(sums_local && gamma && saved && coef && peer_buffers && count_global > 0, "bad bn_bwd_finalize_sync arguments");
   return bn_bwd_finalize_sync(sums_local, gamma, saved, dgamma, dbeta, coef, C, Cp, count_global, grad_beta,
                               reinterpret_cast<const long long*>(peer_buffers), rank, world, seq, ST);
+}
+
+int dv_jpeg_probe_host(const uint8_t* data, int64_t len, int32_t* info8, int64_t* coef_count) {
+  DV_REQUIRE(data && len > 0 && info8 && coef_count, "bad jpeg_probe arguments");
+  long long cc = 0;
+  const int rc = jpeg_probe_host(data, len, info8, &cc);
+  *coef_count = cc;
+  return rc;
+}
+
+int dv_jpeg_huffman_decode_host(const uint8_t* const* files, const int64_t* lens, int n, const int32_t* info8,
+                                int16_t* coef_host, int64_t coef_stride, uint16_t* qt_host, int n_threads) {
+  DV_REQUIRE(files && lens && n > 0 && info8 && coef_host && qt_host && coef_stride > 0, "bad jpeg_huffman_decode arguments");
+  return jpeg_huffman_decode_host(files, reinterpret_cast<const long long*>(lens), n, info8, coef_host, coef_stride, qt_host,
+                                  n_threads);
+}
+
+int64_t dv_jpeg_plane_bytes(const int32_t* info8) { return info8 ? jpeg_plane_bytes(info8) : 0; }
+
+int dv_jpeg_idct_rgb_u8(const int16_t* coef, const uint16_t* qt, uint8_t* planes_tmp, uint8_t* rgb_out, int n,
+                        const int32_t* info8, int64_t coef_stride, void* stream) {
+  DV_REQUIRE(coef && qt && planes_tmp && rgb_out && n > 0 && info8 && coef_stride > 0, "bad jpeg_idct_rgb arguments");
+  DV_REQUIRE(info8[0] > 0 && info8[1] > 0 && (info8[2] == 1 || info8[2] == 3), "bad jpeg geometry");
+  return jpeg_idct_rgb_u8(coef, qt, planes_tmp, rgb_out, n, info8, coef_stride, ST);
 }
 
 int dv_comm_set_timeout(double seconds) {

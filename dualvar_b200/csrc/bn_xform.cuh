@@ -2,14 +2,14 @@
 //
 // Reference: x -> nn.BatchNorm3d -> nn.ReLU -> nn.Conv3d inside SpatioTemporalConv (backbone/r21d.py:56-57,67-70):
 // the reference (and the stand-alone dv_bn_apply pass) materialises z = relu(scale * y + shift) in HBM between the two
-// convolutions. Here the consumer convolution loads the RAW tile of y itself and these routines turn it into z on the
-// way into shared memory, in front of tcgen05.mma - so z never exists in HBM (4 B per element less traffic in forward,
-// and the weight gradient of the consumer recomputes z the same way instead of reading it).
+// convolutions. Here the consumer convolution's TMA loads the RAW tile of y, and these routines turn it into z in
+// place - after the TMA landed, before tcgen05.mma reads it - so z never exists in HBM (4 B per element less traffic
+// in forward, and the weight gradient of the consumer recomputes z the same way instead of reading it).
 //
 // A tile is a SWIZZLE_128B box: row r = one input position (128 B = 64 consecutive channels), the 16-byte group g of
-// row r sits at physical group g ^ (r & 7). Rows outside the tensor (= the convolution's zero padding, and the halo of
-// partial tiles) must be zero: relu(shift) is not zero. Channels past the logical count carry scale = shift = 0 in the
-// staged table, so they come out zero as well.
+// row r sits at physical group g ^ (r & 7). Rows outside the tensor were zero-filled by TMA (= the convolution's zero
+// padding, and the halo of partial tiles): they must stay zero, relu(shift) is not zero. Channels past the logical
+// count carry scale = shift = 0 in the staged table, so they stay zero as well.
 // The arithmetic is dv_bn_apply's (fmaf(y, scale, shift), max with 0, round to nearest even bf16): bit-identical.
 #pragma once
 #include <cuda_bf16.h>
@@ -42,33 +42,17 @@ __device__ __forceinline__ uint4 bnrelu_vec(uint4 v, const float (&sc)[8], const
   return v;
 }
 
-// Where a box comes from: an NDHWC view (possibly a stride-parity sub-view) of the raw tensor y.
-struct XfSrc {
-  const uint8_t* base;          // first element of the view
-  long long sw, sh, st, sn;     // BYTE strides of the view along w, h, t, n
-  int c_bytes;                  // bytes of one position's channel vector (Cp * 2): 16-byte groups beyond it are zero
-};
-
-__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
-  uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-  return v;
-}
-
-// FILL a SWIZZLE_128B box (what a TMA box copy of chunk `kc` would have written) with z = relu?(scale*y + shift):
-// global -> registers -> (affine, ReLU, bf16) -> shared memory. Measured on B200: transforming a TMA-landed tile IN shared
-// memory costs one more read and write of the tile there, and the tensor core's operand fetch already saturates the
-// shared-memory port (128 B/clk/SM) on these layers - the in-place variant made the fused kernels 1.5-2.3x slower.
-// Loading through registers writes the tile to shared memory exactly once, like TMA does.
 // ss_chunk: shared-memory table of THIS 64-channel chunk: scale[64] then shift[64] (fp32).
-// Called by `nthreads` threads (a multiple of 64) with tid in [0, nthreads). Rows outside the view (the convolution's
-// zero padding, tile overhang) and channel groups beyond the tensor are written as zeros.
-__device__ __forceinline__ void bnrelu_box_fill(uint8_t* box, const XfBox& b, const XfSrc& src, int kc, const float* ss_chunk,
-                                                int relu, int tid, int nthreads) {
-  const int logical = tid & 7;                // 16-byte channel group of the chunk this thread owns
+// Called by `nthreads` threads (a multiple of 64) with tid in [0, nthreads).
+// Fast path (the common case): w and h of the box lie inside the tensor and the box holds one n - the valid rows are
+// then ONE contiguous range given by the t extent (the halo planes of a temporal filter), so a row needs two compares;
+// rows are processed three at a time with their loads issued together (the loop is latency-, not issue-bound).
+__device__ __forceinline__ void bnrelu_box_inplace(uint8_t* box, const XfBox& b, const float* ss_chunk, int relu,
+                                                   int tid, int nthreads) {
+  const int phys = tid & 7;
   int r = tid >> 3;
-  const int step = nthreads >> 3;             // multiple of 8: (r & 7), hence the swizzled position, is fixed per thread
-  const int phys = logical ^ (r & 7);
+  const int step = nthreads >> 3;            // multiple of 8: (r & 7) is the same for every row of this thread
+  const int logical = phys ^ (r & 7);
   float sc[8], sh[8];
   {
     const float4* t4 = reinterpret_cast<const float4*>(ss_chunk + logical * 8);
@@ -76,43 +60,51 @@ __device__ __forceinline__ void bnrelu_box_fill(uint8_t* box, const XfBox& b, co
     sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
     sh[0] = c0.x; sh[1] = c0.y; sh[2] = c0.z; sh[3] = c0.w; sh[4] = c1.x; sh[5] = c1.y; sh[6] = c1.z; sh[7] = c1.w;
   }
-  const int cbyte = kc * 128 + logical * 16;
-  const bool c_ok = cbyte < src.c_bytes;
-  const uint8_t* gbase = src.base + cbyte;
-  uint8_t* sbase = box + phys * 16;
   const int bw = 1 << b.lw;
+  uint8_t* base = box + phys * 16;
+  const int plane = b.bh << b.lw;                       // rows per t plane
+  const bool one_n = b.rows == plane * b.bt;
+  const bool wh_inside = b.ow >= 0 && b.ow + bw <= b.dw && b.oh >= 0 && b.oh + b.bh <= b.dh;
+  if (one_n && wh_inside) {
+    if ((unsigned)b.on >= (unsigned)b.dn) return;        // the whole box lies outside (tail tile of a CTA pair)
+    const int t_lo = max(0, -b.ot), t_hi = min(b.bt, b.dt - b.ot);
+    const int r_lo = t_lo * plane, r_hi = t_hi * plane;
+    // first row of this thread inside the range
+    if (r < r_lo) r += (r_lo - r + step - 1) / step * step;
+    for (; r + 2 * step < r_hi; r += 3 * step) {
+      uint4* p0 = reinterpret_cast<uint4*>(base + r * 128);
+      uint4* p1 = reinterpret_cast<uint4*>(base + (r + step) * 128);
+      uint4* p2 = reinterpret_cast<uint4*>(base + (r + 2 * step) * 128);
+      const uint4 v0 = *p0, v1 = *p1, v2 = *p2;
+      *p0 = bnrelu_vec(v0, sc, sh, relu);
+      *p1 = bnrelu_vec(v1, sc, sh, relu);
+      *p2 = bnrelu_vec(v2, sc, sh, relu);
+    }
+    for (; r < r_hi; r += step) {
+      uint4* p0 = reinterpret_cast<uint4*>(base + r * 128);
+      *p0 = bnrelu_vec(*p0, sc, sh, relu);
+    }
+    return;
+  }
+  // general path: row -> (iw, ih, it, in) kept incrementally, every coordinate checked
   int iw = r & (bw - 1);
   int q = r >> b.lw;
   int ih = q % b.bh; q /= b.bh;
   int it = q % b.bt;
   int in = q / b.bt;
-  constexpr int kBatch = 4;
-  while (r < b.rows) {
-    uint4 v[kBatch];
-    bool ok[kBatch];
-    int rr[kBatch];
-#pragma unroll
-    for (int j = 0; j < kBatch; ++j) {
-      rr[j] = r;
-      const int w = b.ow + iw, h = b.oh + ih, t = b.ot + it, n = b.on + in;
-      ok[j] = r < b.rows && c_ok && (unsigned)w < (unsigned)b.dw && (unsigned)h < (unsigned)b.dh &&
-              (unsigned)t < (unsigned)b.dt && (unsigned)n < (unsigned)b.dn;
-      v[j] = make_uint4(0u, 0u, 0u, 0u);
-      if (ok[j]) v[j] = ldg_nc_v4(gbase + n * src.sn + t * src.st + h * src.sh + w * src.sw);
-      r += step;
-      iw += step;
-      ih += iw >> b.lw;
-      iw &= bw - 1;
-      while (ih >= b.bh) { ih -= b.bh; ++it; }
-      while (it >= b.bt) { it -= b.bt; ++in; }
+  for (; r < b.rows; r += step) {
+    const bool ok = (unsigned)(b.ow + iw) < (unsigned)b.dw && (unsigned)(b.oh + ih) < (unsigned)b.dh &&
+                    (unsigned)(b.ot + it) < (unsigned)b.dt && (unsigned)(b.on + in) < (unsigned)b.dn;
+    if (ok) {
+      uint4* p = reinterpret_cast<uint4*>(base + r * 128);
+      *p = bnrelu_vec(*p, sc, sh, relu);
     }
-#pragma unroll
-    for (int j = 0; j < kBatch; ++j) {
-      if (rr[j] < b.rows) {
-        if (ok[j]) v[j] = bnrelu_vec(v[j], sc, sh, relu);
-        *reinterpret_cast<uint4*>(sbase + rr[j] * 128) = v[j];
-      }
-    }
+    // (rows outside the tensor: TMA wrote zeros, nothing to do)
+    iw += step;
+    ih += iw >> b.lw;
+    iw &= bw - 1;
+    while (ih >= b.bh) { ih -= b.bh; ++it; }
+    while (it >= b.bt) { it -= b.bt; ++in; }
   }
 }
 

@@ -51,9 +51,8 @@ constexpr int kOutBufs = 4;                  // output staging buffers: two per 
 // leader CTA (cluster rank 0) issues MMAs; its full / accumulator-free barriers collect both CTAs' signals, commits
 // are multicast to both CTAs' barriers.
 // kF32: fp32-mode instance - the epilogue adds its fp32 rows to ConvTileParams::out_f32 (compiled out of the bf16 one).
-// kXf: consumer-side BatchNorm instance (bn_xform.cuh): warps 10-13 produce the A boxes instead of TMA - they load the
-//      raw tile through registers, apply relu?(scale*y + shift) and store it swizzled into the stage, then signal the
-//      (leader's) transform barrier the MMA warp waits for; the TMA warp only feeds weight tiles. The fused
+// kXf: consumer-side BatchNorm instance (bn_xform.cuh): A boxes land on a CTA-local barrier, warps 10-13 apply
+//      relu?(scale*y + shift) in place and signal the (leader's) transform barrier the MMA warp waits for; the fused
 //      BatchNorm-backward reduce of the epilogue is compiled out of this instance (forward only).
 template <bool kPair, bool kF32 = false, bool kXf = false>
 __global__ void __launch_bounds__(kXf ? kNumThreads + kXfThreads : kNumThreads, 1)
@@ -64,7 +63,8 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ __align__(8) uint64_t bres_bar;
-  __shared__ __align__(8) uint64_t xf_bar[kXf ? kMaxStages : 1];      // kXf (leader): both CTAs' A boxes of the stage are in place
+  __shared__ __align__(8) uint64_t afull_bar[kXf ? kMaxStages : 1];   // kXf: this CTA's A box landed
+  __shared__ __align__(8) uint64_t xf_bar[kXf ? kMaxStages : 1];      // kXf (leader): A boxes of the stage transformed
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float s_part[8][2][kMaxBlockN];   // BN partial sums per epilogue warp: [group * 4 + row quarter][sum|sumsq][channel]
 
@@ -103,8 +103,10 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
     }
     mbar_init(&bres_bar, 1);
     if (kXf)
-      for (int i = 0; i < p.stages; ++i)
+      for (int i = 0; i < p.stages; ++i) {
+        mbar_init(&afull_bar[i], 1);
         mbar_init(&xf_bar[i], kPair ? 2 * kXfThreads : kXfThreads);   // the leader's barrier collects both CTAs' transforms
+      }
     fence_barrier_init();
   }
   for (int c = threadIdx.x; c < 8 * 2 * kMaxBlockN; c += blockDim.x) (&s_part[0][0][0])[c] = 0.f;
@@ -164,7 +166,8 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
         for (int grp = 0; grp < p.num_groups; ++grp) {
           const int len = p.group_len[grp];
           const Tap lead = p.taps[gb];
-          // kXf: the A box is produced by the transform warps, only weight tiles come by TMA
+          // kXf: the A box signals this CTA's own barrier (its transform warps wait there); only weight tiles count
+          // towards the leader's full barrier
           const uint32_t tx_bytes = (kXf ? 0 : p.a_tx_bytes) + (p.b_resident ? 0 : len * b_tap_bytes);
           for (int kc = 0; kc < p.k_chunks; ++kc) {
             const long long c0 = (kDiag && p.prof) ? clock64() : 0;
@@ -174,9 +177,13 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
               if (rank == 0 && (!kXf || tx_bytes != 0)) mbar_expect_tx(&full_bar[stage], tx_mult * tx_bytes);
               const uint32_t full_addr = full0_addr + (uint32_t)stage * 8u;
               uint8_t* st = ring + stage * stage_bytes;
-              if (!kXf)
-                tma_load_5d_to<kPair>(st, &p.a_map[lead.map], full_addr, kc * kChunkK, w0 + lead.dw,
-                                      h0 + g.org_h + lead.dh, t0 + lead.dt, n0);
+              if (kXf) {
+                mbar_expect_tx(&afull_bar[stage], p.a_tx_bytes);
+                tma_load_5d(st, &p.a_map[lead.map], &afull_bar[stage], kc * kChunkK, w0 + lead.dw,
+                            h0 + g.org_h + lead.dh, t0 + lead.dt, n0);
+              } else
+              tma_load_5d_to<kPair>(st, &p.a_map[lead.map], full_addr, kc * kChunkK, w0 + lead.dw,
+                                    h0 + g.org_h + lead.dh, t0 + lead.dt, n0);
               if (!p.b_resident)
                 for (int i = 0; i < len; ++i)
                   tma_load_3d_to<kPair>(st + p.a_stage_bytes + i * b_tap_bytes, &p.b_map, full_addr, kc * kChunkK,
@@ -293,14 +300,9 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
         const Tap lead = p.taps[gb];
         b.ow = w0 + lead.dw; b.oh = h0 + g.org_h + lead.dh; b.ot = t0 + lead.dt; b.on = n0;
         b.dw = p.a_dims[lead.map][0]; b.dh = p.a_dims[lead.map][1]; b.dt = p.a_dims[lead.map][2]; b.dn = p.a_dims[lead.map][3];
-        XfSrc src;
-        src.base = static_cast<const uint8_t*>(p.a_base[lead.map]);
-        src.sw = p.a_stride[lead.map][0]; src.sh = p.a_stride[lead.map][1]; src.st = p.a_stride[lead.map][2];
-        src.sn = p.a_stride[lead.map][3];
-        src.c_bytes = p.xf_cp * 2;
         for (int kc = 0; kc < p.k_chunks; ++kc) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);       // the MMAs that read this stage have retired
-          bnrelu_box_fill(ring + stage * stage_bytes, b, src, kc, xf_table + kc * 128, p.xf_relu, tid, kXfThreads);
+          mbar_wait(&afull_bar[stage], phase);
+          bnrelu_box_inplace(ring + stage * stage_bytes, b, xf_table + kc * 128, p.xf_relu, tid, kXfThreads);
           fence_proxy_async_smem();      // generic-proxy writes -> visible to tcgen05.mma's async-proxy reads
           if (kPair) mbar_arrive_cluster(xf0_addr + (uint32_t)stage * 8u); else mbar_arrive(&xf_bar[stage]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -987,11 +989,7 @@ int conv_fprop_bf16(const void* x, const void* w_packed, void* y, double* stats,
           subsample(v, 2, rh, c.sh);
           subsample(v, 1, rw, c.sw);
           vs.v[nviews] = v;
-          for (int i = 0; i < 4; ++i) {
-            P.a_dims[nviews][i] = (int)v.dim[1 + i];
-            P.a_stride[nviews][i] = v.stride[1 + i] * 2;
-          }
-          P.a_base[nviews] = v.base;
+          for (int i = 0; i < 4; ++i) P.a_dims[nviews][i] = (int)v.dim[1 + i];
           map_of_parity[key] = nviews++;
         }
         taps.push_back({map_of_parity[key], floordiv(ot, c.st), floordiv(oh, c.sh), floordiv(ow, c.sw),

@@ -73,14 +73,12 @@ struct alignas(64) ConvTileParams {
   float* out_f32;
   int f32_store;   // 1: the first product of a sum overwrites the destination (plain 16-byte stores), 0: adds to it
   // Consumer-side BatchNorm (bn_xform.cuh, kernel instance kXf): the A operand is the RAW output y of the convolution
-  // below; four extra warps load every A box themselves (global -> registers), apply z = relu?(scale*y + shift) and
-  // store it swizzled where TMA would have put it, so z is never written to HBM (reference: BatchNorm3d + ReLU between the two convs of SpatioTemporalConv).
+  // below; four extra warps turn every A box into z = relu?(scale*y + shift) in shared memory between the TMA and the
+  // MMA, so z is never written to HBM (reference: BatchNorm3d + ReLU between the two convs of SpatioTemporalConv).
   const float* xf_ss;        // fp32 [2][xf_cp] scale, shift of the BatchNorm in front of this convolution
   int xf_cp, xf_relu;
   int a_box[4];              // A box extents along w (power of two), h, t, n
-  int a_dims[kMaxAMaps][4];  // W, H, T, N extents of every A view (rows outside are zero = conv padding)
-  const void* a_base[kMaxAMaps];       // first element of every A view (the kXf instance loads A itself, not by TMA)
-  long long a_stride[kMaxAMaps][4];    // byte strides of every A view along w, h, t, n
+  int a_dims[kMaxAMaps][4];  // W, H, T, N extents of every A tensor map (rows outside stay zero = conv padding)
 };
 
 // Optional fused BatchNorm-backward reduction request for conv_dgrad_bf16 (see ConvTileParams::red_y).

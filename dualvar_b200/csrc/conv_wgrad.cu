@@ -58,9 +58,7 @@ struct alignas(64) WgradParams {
   const float* xf_ss;      // fp32 [2][cin_p] scale, shift
   int xf_relu;
   int xb_h, xb_t;          // halo mode: box extents along h and t
-  int a_dims[kMaxAMaps][4];   // W, H, T, N extents of every X view (row validity = the convolution's zero padding)
-  const void* a_base[kMaxAMaps];      // first element / byte strides (w, h, t, n) of every X view: the transform warps
-  long long a_stride[kMaxAMaps][4];   // load the X boxes themselves (global -> registers -> shared memory), not TMA
+  int a_dims[kMaxAMaps][4];   // W, H, T, N extents of every X tensor map (row validity = the convolution's zero padding)
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -69,7 +67,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
   __shared__ __align__(8) uint64_t full_bar[8];
   __shared__ __align__(8) uint64_t empty_bar[8];
   __shared__ __align__(8) uint64_t acc_bar;
-  __shared__ __align__(8) uint64_t xf_bar[8];   // X boxes of a stage in place (128 arrivals)
+  __shared__ __align__(8) uint64_t xf_bar[8];   // X boxes of a stage transformed (128 arrivals)
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform role index
@@ -121,9 +119,8 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
     const bool issuer = elect_one();
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t tx = xf ? (uint32_t)(nbx * kBoxBytes)        // consumer-side BatchNorm: X comes from the transform warps
-                           : p.halo ? (uint32_t)(nbox * p.x_box_bytes + nbx * kBoxBytes)
-                                    : (uint32_t)((nu + nbx) * kBoxBytes);
+    const uint32_t tx = p.halo ? (uint32_t)(nbox * p.x_box_bytes + nbx * kBoxBytes)
+                               : (uint32_t)((nu + nbx) * kBoxBytes);
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       int m_id = tile;
       const int wb = m_id % g.tiles_w; m_id /= g.tiles_w;
@@ -138,9 +135,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
         uint8_t* b_s = a_s + a_bytes;
         for (int j = 0; j < nbx; ++j)
           tma_load_5d(b_s + j * kBoxBytes, &p.dy_map, &full_bar[stage], n_tile * p.block_n + j * 64, w0, h0, t0, n0);
-        if (xf) {
-          // nothing: the X boxes are produced by warps 2-5
-        } else if (p.halo) {
+        if (p.halo) {
           for (int b = 0; b < nbox; ++b)
             tma_load_5d(a_s + b * p.x_box_bytes, &p.a_map[0], &full_bar[stage], p.box_kc[box0 + b] * 64,
                         w0 + p.box_dw[box0 + b], h0 + p.box_dh[box0 + b], t0 + p.box_dt[box0 + b], n0);
@@ -171,8 +166,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
     uint32_t phase = 0;
     uint32_t accumulate = 0;
     for (int tile = tile_begin; tile < tile_end; ++tile) {
-      mbar_wait(&full_bar[stage], phase);
-      if (xf) mbar_wait(&xf_bar[stage], phase);
+      mbar_wait(xf ? &xf_bar[stage] : &full_bar[stage], phase);
       tc_fence_after_sync();
       const uint32_t a_lo = lo_flags | (base_enc + (uint32_t)stage * stage_enc);
       const uint32_t b_lo = a_lo + a_enc;
@@ -205,9 +199,8 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
     __syncwarp();
   } else {
     if (xf) {
-      // ---- operand producer (warps 2-5 are otherwise idle until the accumulators are complete): every X box of a
-      // stage is loaded through registers, becomes z = relu?(scale*y + shift) and is stored swizzled where TMA would
-      // have put it; the MMA warp waits for xf_bar (and for the dY boxes on full_bar)
+      // ---- operand transform (warps 2-5 are otherwise idle until the accumulators are complete): every X box of a
+      // stage becomes z = relu?(scale*y + shift) in place once its TMA landed; the MMA warp waits for xf_bar
       const int tid = threadIdx.x - 64;
       int stage = 0;
       uint32_t phase = 0;
@@ -218,21 +211,16 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
         const int tb = m_id % g.tiles_t; m_id /= g.tiles_t;
         const int nb = m_id;
         const int w0 = wb << g.lw, h0 = hb << g.lh, t0 = tb << g.lt, n0 = nb << g.ln;
-        mbar_wait(&empty_bar[stage], phase ^ 1);        // the MMAs that read this stage have retired
+        mbar_wait(&full_bar[stage], phase);
         uint8_t* a_s = smem + stage * stage_bytes;
         XfBox b;
-        XfSrc src;
-        src.c_bytes = p.cin_p * 2;
         b.lw = g.lw;
         if (p.halo) {
           b.rows = p.x_box_bytes >> 7; b.bh = p.xb_h; b.bt = p.xb_t;
           b.dw = p.a_dims[0][0]; b.dh = p.a_dims[0][1]; b.dt = p.a_dims[0][2]; b.dn = p.a_dims[0][3];
-          src.base = static_cast<const uint8_t*>(p.a_base[0]);
-          src.sw = p.a_stride[0][0]; src.sh = p.a_stride[0][1]; src.st = p.a_stride[0][2]; src.sn = p.a_stride[0][3];
           for (int i = 0; i < nbox; ++i) {
             b.ow = w0 + p.box_dw[box0 + i]; b.oh = h0 + p.box_dh[box0 + i]; b.ot = t0 + p.box_dt[box0 + i]; b.on = n0;
-            bnrelu_box_fill(a_s + i * p.x_box_bytes, b, src, p.box_kc[box0 + i], xf_table + p.box_kc[box0 + i] * 128,
-                            p.xf_relu, tid, 128);
+            bnrelu_box_inplace(a_s + i * p.x_box_bytes, b, xf_table + p.box_kc[box0 + i] * 128, p.xf_relu, tid, 128);
           }
         } else {
           b.rows = 64; b.bh = 1 << g.lh; b.bt = 1 << g.lt;
@@ -243,10 +231,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
             const Tap tp = p.taps[tap];
             b.dw = p.a_dims[tp.map][0]; b.dh = p.a_dims[tp.map][1]; b.dt = p.a_dims[tp.map][2]; b.dn = p.a_dims[tp.map][3];
             b.ow = w0 + tp.dw; b.oh = h0 + tp.dh; b.ot = t0 + tp.dt; b.on = n0;
-            src.base = static_cast<const uint8_t*>(p.a_base[tp.map]);
-            src.sw = p.a_stride[tp.map][0]; src.sh = p.a_stride[tp.map][1]; src.st = p.a_stride[tp.map][2];
-            src.sn = p.a_stride[tp.map][3];
-            bnrelu_box_fill(a_s + i * kBoxBytes, b, src, kc, xf_table + kc * 128, p.xf_relu, tid, 128);
+            bnrelu_box_inplace(a_s + i * kBoxBytes, b, xf_table + kc * 128, p.xf_relu, tid, 128);
           }
         }
         fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's async-proxy reads
@@ -388,12 +373,7 @@ int conv_wgrad_bf16(const void* x, const void* dy, float* dw, const ConvGeom& c,
   const int taps_total = c.kt * c.kh * c.kw;
   P.xf_ss = xf_ss;
   P.xf_relu = xf_relu;
-  for (int i = 0; i < kMaxAMaps; ++i) {
-    P.a_dims[i][0] = c.W; P.a_dims[i][1] = c.H; P.a_dims[i][2] = c.T; P.a_dims[i][3] = c.N;
-    P.a_base[i] = x;
-    P.a_stride[i][0] = (long long)c.Cin_p * 2; P.a_stride[i][1] = (long long)c.W * c.Cin_p * 2;
-    P.a_stride[i][2] = (long long)c.H * c.W * c.Cin_p * 2; P.a_stride[i][3] = (long long)c.T * c.H * c.W * c.Cin_p * 2;
-  }
+  for (int i = 0; i < kMaxAMaps; ++i) { P.a_dims[i][0] = c.W; P.a_dims[i][1] = c.H; P.a_dims[i][2] = c.T; P.a_dims[i][3] = c.N; }
   // accumulate (fp32 mode): dw already holds the sum of earlier operand-plane products; the kernel only adds
   if (!accumulate) DV_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)c.Cout_p * taps_total * c.Cin_p, stream));
   P.halo = 0;
@@ -555,8 +535,7 @@ int conv_wgrad_bf16(const void* x, const void* dy, float* dw, const ConvGeom& c,
           }
           rc = encode5(&P.a_map[nmaps], bp, dim, str);
           if (rc) return rc;
-          for (int i = 0; i < 3; ++i) { P.a_dims[nmaps][i] = (int)dim[1 + i]; P.a_stride[nmaps][i] = str[1 + i] * 2; }
-          P.a_base[nmaps] = bp;
+          for (int i = 0; i < 3; ++i) P.a_dims[nmaps][i] = (int)dim[1 + i];
           map_of_parity[key] = nmaps++;
         }
         Tap& tp = P.taps[ntaps++];

@@ -743,9 +743,13 @@ def _activate_f32(ctx, r1, r2, res, relu, out=None, out_coff=0):
 
 
 # Consumer-side BatchNorm (csrc/bn_xform.cuh): a plain relu?(BN(y)) whose only consumer is a convolution is not
-# written to HBM - the consumer's fprop and wgrad load the raw y and normalise the operand tile in shared memory.
-# DV_FUSE_BN_APPLY=0 restores the stand-alone dv_bn_apply pass (bit-identical results).
-FUSE_BN_APPLY = os.environ.get("DV_FUSE_BN_APPLY", "1") != "0"
+# written to HBM - the consumer's fprop (and wgrad) load the raw y and normalise the operand tile in shared memory.
+# Results are bit-identical to the stand-alone dv_bn_apply pass. Measured on B200 (profiles/r02_bn_fusion_*.txt): the
+# fused fprop costs +0.3-0.4 ms where the pass it replaces costs 0.6-1.0 ms - a win - but the fused wgrad costs +0.6-1.1 ms
+# with nothing more to save (the transform's shared-memory traffic competes with the tensor core's operand fetch), so a
+# TRAINING step is slower with it. Hence: 1 (default) = forward-only passes (evaluation, feature extraction, MoCo's key
+# encoder), 2 = training passes too, 0 = never.
+FUSE_BN_APPLY = int(os.environ.get("DV_FUSE_BN_APPLY", "1"))
 
 
 def activate(ctx, r1, r2=None, res=None, relu=True, out=None, out_coff=0, conv_only=False):
@@ -759,7 +763,8 @@ def activate(ctx, r1, r2=None, res=None, relu=True, out=None, out_coff=0, conv_o
     g = r1.geom
     Cp = g.Cout_p
     dev = r1.y.device
-    lazy = conv_only and FUSE_BN_APPLY and r2 is None and res is None and out is None
+    lazy = conv_only and r2 is None and res is None and out is None and \
+        (FUSE_BN_APPLY == 2 or (FUSE_BN_APPLY == 1 and not ctx.record))
     if lazy:
         out_t = None
         out_act = Act(None, g.Cout, lazy=(r1, relu))

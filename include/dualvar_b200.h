@@ -363,6 +363,23 @@ int dv_frames_gaussian_blur_host(const float* frame_host, float* out_host, int H
  * [first input index, tap count, taps[ksize]] - what Pillow's precompute_coeffs + normalize_coeffs_8bpc produce */
 int dv_frames_axis_table_host(int in_size, int out_size, int32_t* table_host, int capacity, int32_t* ksize_host);
 
+/* ---- JPEG frame decoding (replaces PIL.Image.open of the reference loader, dataset/local_dataset.py:283-286) ----
+ * Bit-identical to the IJG / libjpeg-turbo decoder with its default settings (islow IDCT, fancy upsampling), i.e. to Pillow.
+ * Baseline sequential (SOF0), 8 bit, 1 or 3 components, 4:4:4 / 4:2:2 / 4:2:0, restart intervals; anything else is refused.
+ * Host half (serial bit streams, no GPU needed): dv_jpeg_probe_host reads one file's header into
+ * info8 = {width, height, components, hmax, vmax, mcus per row, mcu rows, 0} and the int16 coefficient count per frame;
+ * dv_jpeg_huffman_decode_host entropy-decodes n files of that geometry on n_threads host threads into
+ * coef_host [n][coef_stride] (quantised DCT coefficients, natural order, component after component; meant to be pinned
+ * memory) and qt_host [n][3][64] (quantisation tables per component).
+ * Device half: dv_jpeg_idct_rgb_u8 dequantises, runs the inverse DCT (planes_tmp: n * dv_jpeg_plane_bytes(info8) bytes),
+ * upsamples the chroma planes and converts to RGB: rgb_out uint8 [n][height][width][3] - what dv_frames_scale_crop_u8 reads. */
+int dv_jpeg_probe_host(const uint8_t* data, int64_t len, int32_t* info8, int64_t* coef_count);
+int dv_jpeg_huffman_decode_host(const uint8_t* const* files, const int64_t* lens, int n, const int32_t* info8,
+                                int16_t* coef_host, int64_t coef_stride, uint16_t* qt_host, int n_threads);
+int64_t dv_jpeg_plane_bytes(const int32_t* info8);
+int dv_jpeg_idct_rgb_u8(const int16_t* coef, const uint16_t* qt, uint8_t* planes_tmp, uint8_t* rgb_out, int n,
+                        const int32_t* info8, int64_t coef_stride, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -315,3 +315,39 @@ def test_ragged_and_minimal_batches_run_and_match_oracle(shape):
             assert torch.isfinite(rp[k]) and abs(rp[k].item() - rr[k].item()) <= 2e-2 * abs(rr[k].item()) + 2e-3, (k, rp[k].item(), rr[k].item())
     sum(v for k, v in rp.items() if "loss" in k).backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in prod.parameters())
+
+
+def test_consumer_side_batchnorm_leaves_the_step_unchanged():
+    """engine.FUSE_BN_APPLY: the BatchNorm + ReLU between the two convs of a factorised convolution applied inside the
+    consumer conv (forward-only passes by default, training passes with 2) - losses and outputs bit-identical to the
+    stand-alone pass, gradients equal up to the fp32 atomics order of the weight-gradient reduction."""
+    from dualvar_b200 import engine as E
+    ref, prod = _pair("r21d")
+    del ref
+    x = torch.randn(4, 3, 3, 8, 64, 64, device=dev)
+    clip = torch.randn(6, 3, 8, 64, 64, device=dev)
+    state = {k: v.clone() for k, v in prod.state_dict().items()}
+    res = {}
+    old = E.FUSE_BN_APPLY
+    try:
+        for mode in (0, 2):
+            E.FUSE_BN_APPLY = mode
+            prod.load_state_dict(state)
+            prod.train()
+            for p in prod.parameters():
+                p.grad = None
+            np.random.seed(4); r = prod(x)
+            sum(v for k, v in r.items() if "loss" in k).backward()
+            grads = [p.grad.clone() for p in prod.parameters()]
+            E.FUSE_BN_APPLY = 1 if mode else 0          # forward-only default
+            prod.eval()
+            with torch.no_grad():
+                feat = prod.encoder_q[0](clip)
+            res[mode] = ({k: v.detach().clone() for k, v in r.items()}, grads, feat)
+    finally:
+        E.FUSE_BN_APPLY = old
+    for k in res[0][0]:
+        assert torch.equal(res[0][0][k], res[2][0][k]), k
+    assert torch.equal(res[0][2], res[2][2])
+    for (n, _), a, b in zip(prod.named_parameters(), res[0][1], res[2][1]):
+        assert _rel(b, a) < 1e-3, n
