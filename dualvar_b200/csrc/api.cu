@@ -118,6 +118,9 @@ int bn_finalize_sync(const double* stats, const float* gamma, const float* beta,
 int bn_bwd_finalize_sync(const double* sums_local, const float* gamma, const float* saved, float* dgamma, float* dbeta,
                          float* coef, int C, int Cp, double count_global, float grad_beta, const long long* peer_ptrs,
                          int rank, int world, long long seq, cudaStream_t stream);
+int gate_fc_fwd(const float* mean, const float* W, const float* b, float* w, int N, int C, cudaStream_t st);
+int gate_fc_bwd(const float* dw, const float* w, const float* mean, const float* W, float* dpre, float* gW, float* gb,
+                float* dmean, int N, int C, cudaStream_t st);
 int jpeg_probe_host(const uint8_t* data, long long len, int* info8, long long* coef_count);
 int jpeg_huffman_decode_host(const uint8_t* const* files, const long long* lens, int n, const int* info8, int16_t* coef,
                              long long coef_stride, uint16_t* qt, int n_threads);
@@ -625,6 +628,15 @@ int dv_frames_axis_table_host(int in_size, int out_size, int32_t* table_host, in
 int dv_moco_momentum_update(const int64_t* chunk_table, int n_chunks, float m, void* stream) {
   DV_REQUIRE(chunk_table && n_chunks >= 0 && m >= 0.f && m <= 1.f, "bad momentum_update arguments");
   return momentum_update(reinterpret_cast<const long long*>(chunk_table), n_chunks, m, ST);
+}
+int dv_gate_fc_fwd(const float* mean, const float* fc_weight, const float* fc_bias, float* w, int N, int C, void* stream) {
+  DV_REQUIRE(mean && fc_weight && fc_bias && w && N > 0 && C > 0, "bad gate_fc_fwd arguments");
+  return gate_fc_fwd(mean, fc_weight, fc_bias, w, N, C, ST);
+}
+int dv_gate_fc_bwd(const float* dw, const float* w, const float* mean, const float* fc_weight, float* dpre, float* grad_weight,
+                   float* grad_bias, float* dmean, int N, int C, void* stream) {
+  DV_REQUIRE(dw && w && mean && fc_weight && dpre && grad_weight && grad_bias && dmean && N > 0 && C > 0, "bad gate_fc_bwd arguments");
+  return gate_fc_bwd(dw, w, mean, fc_weight, dpre, grad_weight, grad_bias, dmean, N, C, ST);
 }
 int dv_moco_enqueue_at(const float* keys, float* queue, int B, int d, int K, const int64_t* queue_ptr, void* stream) {
   DV_REQUIRE(keys && queue && queue_ptr && B > 0 && d > 0 && K > 0, "bad enqueue arguments");

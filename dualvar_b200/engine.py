@@ -855,12 +855,8 @@ def self_gate(ctx, cat, coff, raw, fc):
     pre_ = "dv_f32_" if f32 else "dv_"
     mean = torch.empty((N, C), dtype=torch.float32, device=dev)
     call(pre_ + "slice_mean", ptr(cat.data), ptr(mean), N, S, C, ld, coff, stream_ptr())
-    pre = torch.empty((N, C), dtype=torch.float32, device=dev)
-    f = ctypes.c_float
-    call("dv_sgemm", 0, 1, N, C, C, f(1.0), ptr(mean), C, ptr(fc.weight.detach()), C, f(0.0), ptr(pre), C,
-         ptr(fc.bias.detach()), 0, stream_ptr())
-    w = torch.empty_like(pre)
-    call("dv_sigmoid_fwd", ptr(pre), ptr(w), N * C, stream_ptr())
+    w = torch.empty((N, C), dtype=torch.float32, device=dev)
+    call("dv_gate_fc_fwd", ptr(mean), ptr(fc.weight.detach()), ptr(fc.bias.detach()), ptr(w), N, C, stream_ptr())
     if f32:
         call("dv_f32_gate_scale", ptr(cat.data), ptr(cat.planes), cat.planes.stride(0), F32_PLANES, ptr(w), N, S, C, ld,
              coff, stream_ptr())
@@ -874,16 +870,13 @@ def self_gate(ctx, cat, coff, raw, fc):
         dw = torch.empty((N, C), dtype=torch.float32, device=dev)
         call(pre_ + "gate_bwd_reduce", ptr(dout), ptr(raw.y), ptr(raw.ss), ptr(dw), N, S, C, Cp, ld, coff, stream_ptr())
         dpre = torch.empty_like(dw)
-        call("dv_sigmoid_bwd", ptr(dw), ptr(w), ptr(dpre), N * C, stream_ptr())
         gW = torch.empty_like(fc.weight)
-        call("dv_sgemm", 1, 0, C, C, N, f(1.0), ptr(dpre), C, ptr(mean), C, f(0.0), ptr(gW), C, None, 0, stream_ptr())
         gb = torch.empty_like(fc.bias)
-        call("dv_colsum", ptr(dpre), ptr(gb), N, C, C, f(0.0), stream_ptr())
+        dmean = torch.empty_like(dw)
+        call("dv_gate_fc_bwd", ptr(dw), ptr(w), ptr(mean), ptr(fc.weight.detach()), ptr(dpre), ptr(gW), ptr(gb), ptr(dmean),
+             N, C, stream_ptr())
         ctx.add_param_grad(fc.weight, gW)
         ctx.add_param_grad(fc.bias, gb)
-        dmean = torch.empty_like(dw)
-        call("dv_sgemm", 0, 0, N, C, C, f(1.0), ptr(dpre), C, ptr(fc.weight.detach()), C, f(0.0), ptr(dmean), C,
-             None, 0, stream_ptr())
         dz = torch.empty((N, T, H, W, Cp), dtype=cat.data.dtype, device=dev)
         call(pre_ + "gate_bwd_apply", ptr(dout), ptr(w), ptr(dmean), ptr(dz), N, S, C, Cp, ld, coff, stream_ptr())
         ctx.overrides[(id(cat), coff)] = dz

@@ -51,20 +51,26 @@ def _top1(logits, labels):
     return (logits.argmax(dim=1) == labels).float().mean() * 100.0
 
 
-def train_one_epoch(loader, model, optimizer, to_input=None, log_every=0, log=print, iteration=1):
+def train_one_epoch(loader, model, optimizer, to_input=None, log_every=0, log=print, iteration=1, graph_step=None):
     """One pass over ``loader`` (pretrain.py:364-460). ``loader`` yields either ``{'seq': tensor}`` batches like the
     reference's dataset or tensors; ``to_input(batch)`` turns a batch into what ``model`` takes (the reference block
-    (B,3,C,T,H,W), or ``engine.RawClips`` for the fused ingest). Returns (meters dict of floats, next iteration)."""
+    (B,3,C,T,H,W), or ``engine.RawClips`` for the fused ingest). ``graph_step``: a graph_step.GraphedTrainStep built on
+    (model, optimizer) - the batches are then the raw loader frames (B, 3, V*T, H, W) and every step is one CUDA-graph
+    replay (forward, losses, backward and optimizer inside). Returns (meters dict of floats, next iteration)."""
     model.train()
     sums, n_it = {}, 0
     for idx, batch in enumerate(loader):
         x = batch["seq"] if isinstance(batch, dict) else batch
-        x = to_input(x) if to_input is not None else x
-        ret = model(x)
-        loss = total_loss(ret)
-        optimizer.zero_grad(set_to_none=True)
-        loss.backward()
-        optimizer.step()
+        if graph_step is not None:
+            ret = dict(graph_step(x))
+            loss = ret.pop("loss")
+        else:
+            x = to_input(x) if to_input is not None else x
+            ret = model(x)
+            loss = total_loss(ret)
+            optimizer.zero_grad(set_to_none=True)
+            loss.backward()
+            optimizer.step()
         with torch.no_grad():
             stats = {"loss": loss.detach()}
             for k, v in ret.items():
@@ -117,7 +123,7 @@ def load_checkpoint(path, model, optimizer=None, map_location="cpu"):
 
 
 def fit(model, loader, optimizer, epochs, schedule=(), start_epoch=0, model_path=None, save_freq=1, eval_freq=1,
-        to_input=None, best_acc=0.0, iteration=1, log=print, log_every=0):
+        to_input=None, best_acc=0.0, iteration=1, log=print, log_every=0, graph_step=None):
     """pretrain.py:328-360: epochs of train_one_epoch with MultiStepLR(gamma=0.1) and rank-0 checkpoints."""
     sched = torch.optim.lr_scheduler.MultiStepLR(optimizer, list(schedule), gamma=0.1, last_epoch=start_epoch - 1) \
         if start_epoch == 0 else None
@@ -131,7 +137,7 @@ def fit(model, loader, optimizer, epochs, schedule=(), start_epoch=0, model_path
         sampler = getattr(loader, "sampler", None)
         if hasattr(sampler, "set_epoch"):
             sampler.set_epoch(epoch)                  # pretrain.py:333
-        meters, iteration = train_one_epoch(loader, model, optimizer, to_input, log_every, log, iteration)
+        meters, iteration = train_one_epoch(loader, model, optimizer, to_input, log_every, log, iteration, graph_step)
         sched.step()
         history.append(meters)
         log("epoch %d  " % epoch + "  ".join(f"{k} {v:.4f}" for k, v in meters.items()))

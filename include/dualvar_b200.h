@@ -211,6 +211,12 @@ int dv_moco_advance_ptr(int64_t* queue_ptr, int batch, int K, void* stream);
 /* ---- S3D-G self-gating on channel slices of the Inception concat tensor (backbone/s3dg.py:68-78,130) ----
  * x rows have `ld` channels, the branch occupies [coff, coff+C). */
 int dv_slice_mean(const void* x, float* out, int N, int S, int C, int ld, int coff, void* stream);
+/* the gate's Linear + sigmoid in one launch: w[n][j] = sigmoid(fc_bias[j] + sum_k mean[n][k] * fc_weight[j][k]); and its
+ * backward from dw = dLoss/dw: dpre = dw * w * (1 - w), grad_weight = dpre^T mean, grad_bias = column sums of dpre,
+ * dmean = dpre fc_weight (backbone/s3dg.py:74-77; N, C <= 1024) */
+int dv_gate_fc_fwd(const float* mean, const float* fc_weight, const float* fc_bias, float* w, int N, int C, void* stream);
+int dv_gate_fc_bwd(const float* dw, const float* w, const float* mean, const float* fc_weight, float* dpre, float* grad_weight,
+                   float* grad_bias, float* dmean, int N, int C, void* stream);
 int dv_gate_scale(void* x, const float* w, int N, int S, int C, int ld, int coff, void* stream);
 /* dw[n][c] = sum_s dout * relu(scale*y+shift)  (the un-gated activation is recomputed from y) */
 int dv_gate_bwd_reduce(const void* dout, const void* y, const float* ss, float* dw, int N, int S, int C, int Cp,

@@ -280,3 +280,52 @@ def test_fused_sgd_matches_torch_sgd():
             torch.testing.assert_close(p, q, rtol=1e-5, atol=1e-6)
     for p, q in zip(ps, qs):
         torch.testing.assert_close(ours.state[p]["momentum_buffer"], ref.state[q]["momentum_buffer"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("N,S,C,ld,coff", [(5, 300, 64, 256, 64), (3, 77, 208, 512, 96), (48, 64, 24, 24, 0), (2, 4096, 384, 1024, 256)])
+def test_self_gating_kernels_match_torch(N, S, C, ld, coff):
+    """S3D-G SelfGating on a channel slice of the concat tensor (backbone/s3dg.py:68-78): slice mean, Linear + sigmoid,
+    in-place scale, and the backward of all three, kernel by kernel against torch."""
+    import ctypes
+    from dualvar_b200 import _lib
+    from dualvar_b200._lib import ptr, stream_ptr
+    dev = "cuda:0"
+    g = torch.Generator(device=dev).manual_seed(N * 1000 + C)
+    cat = torch.randn(N, S, ld, device=dev, generator=g).bfloat16()
+    W = torch.randn(C, C, device=dev, generator=g) / C ** 0.5
+    b = torch.randn(C, device=dev, generator=g)
+    # forward
+    mean = torch.empty(N, C, device=dev)
+    _lib.call("dv_slice_mean", ptr(cat), ptr(mean), N, S, C, ld, coff, stream_ptr())
+    sl = cat[:, :, coff:coff + C].float()
+    torch.testing.assert_close(mean, sl.mean(1), rtol=1e-5, atol=1e-5)
+    w = torch.empty(N, C, device=dev)
+    _lib.call("dv_gate_fc_fwd", ptr(mean), ptr(W), ptr(b), ptr(w), N, C, stream_ptr())
+    w_ref = torch.sigmoid(mean @ W.t() + b)
+    torch.testing.assert_close(w, w_ref, rtol=1e-5, atol=1e-6)
+    scaled = cat.clone()
+    _lib.call("dv_gate_scale", ptr(scaled), ptr(w), N, S, C, ld, coff, stream_ptr())
+    assert torch.equal(scaled[:, :, coff:coff + C], (sl * w[:, None, :]).bfloat16())
+    keep = torch.ones(ld, dtype=torch.bool, device=dev); keep[coff:coff + C] = False
+    assert torch.equal(scaled[:, :, keep], cat[:, :, keep])                      # other slices untouched
+    # backward: z = relu(scale*y + shift) recomputed from the branch's raw output y
+    y = torch.randn(N, S, C, device=dev, generator=g).bfloat16()
+    ss = torch.cat([torch.rand(C, device=dev, generator=g) + 0.5, torch.randn(C, device=dev, generator=g)])
+    dout = torch.randn(N, S, ld, device=dev, generator=g).bfloat16()
+    z = torch.relu(y.float() * ss[:C] + ss[C:])
+    dw = torch.empty(N, C, device=dev)
+    _lib.call("dv_gate_bwd_reduce", ptr(dout), ptr(y), ptr(ss), ptr(dw), N, S, C, C, ld, coff, stream_ptr())
+    dsl = dout[:, :, coff:coff + C].float()
+    torch.testing.assert_close(dw, (dsl * z).sum(1), rtol=2e-4, atol=2e-3)
+    mean_r = mean.clone().requires_grad_(True); W_r = W.clone().requires_grad_(True); b_r = b.clone().requires_grad_(True)
+    torch.sigmoid(mean_r @ W_r.t() + b_r).backward(dw)
+    dpre, gW, gb, dmean = torch.empty(N, C, device=dev), torch.empty_like(W), torch.empty_like(b), torch.empty(N, C, device=dev)
+    _lib.call("dv_gate_fc_bwd", ptr(dw), ptr(w), ptr(mean), ptr(W), ptr(dpre), ptr(gW), ptr(gb), ptr(dmean), N, C, stream_ptr())
+    scale = dw.abs().max().item()
+    torch.testing.assert_close(gW, W_r.grad, rtol=1e-4, atol=1e-4 * scale)
+    torch.testing.assert_close(gb, b_r.grad, rtol=1e-4, atol=1e-4 * scale)
+    torch.testing.assert_close(dmean, mean_r.grad, rtol=1e-4, atol=1e-4 * scale)
+    dz = torch.empty(N, S, C, device=dev, dtype=torch.bfloat16)
+    _lib.call("dv_gate_bwd_apply", ptr(dout), ptr(w), ptr(dmean), ptr(dz), N, S, C, C, ld, coff, stream_ptr())
+    want = (w[:, None, :] * dsl + dmean[:, None, :] / S)
+    assert ((dz.float() - want).abs().max() / want.abs().max()).item() < 1e-2      # bf16 output

@@ -83,3 +83,25 @@ def test_product_model_trains_checkpoints_and_resumes(tmp_path):
     # the continued and the resumed epoch see the same data and permutations; bf16 kernels with atomic reductions are not
     # run-to-run deterministic, so the averaged losses agree to a few parts in a thousand, not bit for bit
     assert np.isfinite(h_a[0]["loss"]) and abs(h_a[0]["loss"] - h_b[0]["loss"]) <= 3e-2 * abs(h_a[0]["loss"])
+
+
+@pytest.mark.gpu
+def test_fit_with_graphed_step_and_lr_schedule():
+    """fit(..., graph_step=GraphedTrainStep): epochs of CUDA-graph replays, MultiStepLR milestones re-capture the graph,
+    meters and checkpoint state behave like the eager loop."""
+    from dualvar_b200 import models as PM
+    from dualvar_b200.graph_step import GraphedTrainStep
+    dev = "cuda:0"
+    _seed(0)
+    m = PM.SimCLR_TimeSeriesV4("r3d", 128, 0.07, False, True, 2, 64, 0.07, 0.07, "clip-sr-tc",
+                               SimpleNamespace(shufflerank_theta=0.05)).to(dev)
+    opt = L.build_optimizer(m, lr=1e-3)
+    gen = torch.Generator().manual_seed(3)
+    data = [torch.rand(4, 3, 24, 32, 32, generator=gen).pin_memory() for _ in range(4)]
+    step = GraphedTrainStep(m, opt, n_views=3, warmup=1)
+    hist, _, it = L.fit(m, data, opt, epochs=3, schedule=(1,), graph_step=step, log=lambda *_: None)
+    assert it == 13 and len(hist) == 3 and all(np.isfinite(h["loss"]) for h in hist)
+    assert step.eager_steps == 1 and step.captures == 2 and step.replays == 11        # lr changed once after epoch 0
+    assert abs(opt.param_groups[0]["lr"] - 1e-4) < 1e-12
+    assert {"loss", "clip_contrast_loss", "clip_acc", "tc_contrast_loss"} <= set(hist[0])
+    assert int(m.encoder_q[0].bn1.num_batches_tracked) == 24
