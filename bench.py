@@ -333,38 +333,55 @@ def other_configs_leg(dev):
     out = {}
     a = SimpleNamespace(shufflerank_theta=0.05)
 
-    def time_step(model, make_input, batch, n=4):
+    def time_step(model, frames, batch, n=4):
+        """ms per full step, replayed as one CUDA graph (graph_step.GraphedTrainStep) and issued eagerly."""
+        from dualvar_b200 import _lib
+        from dualvar_b200.graph_step import GraphedTrainStep
         opt = SGD([{"params": p} for p in model.parameters() if p.requires_grad], lr=0.003, weight_decay=1e-4, momentum=0.9)
-        nl0 = [0]
 
-        def st():
-            ret = model(make_input())
+        def eager():
+            ret = model(RawClips(frames, 3))
             loss = sum(v for k, v in ret.items() if "loss" in k)
-            opt.zero_grad(set_to_none=True)
+            opt.zero_grad(set_to_none=False)
             loss.backward()
             opt.step()
             return loss
+
+        def timed(fn, k):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(k):
+                out = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / k, out
         for _ in range(2):
-            st()
-        torch.cuda.synchronize()
-        from dualvar_b200 import _lib
-        nl0[0] = _lib.load().dv_launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(n):
-            loss = st()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / n
-        return {"value": batch / (ms / 1e3), "unit": "samples/s", "ms_per_step": ms, "samples_per_gpu": batch, "steps": n,
-                "gpu_launches_per_step": (_lib.load().dv_launch_count() - nl0[0]) / n, "final_loss": float(loss.detach())}
+            eager()
+        nl0 = _lib.load().dv_launch_count()
+        ms_eager, loss = timed(eager, n)
+        launches = (_lib.load().dv_launch_count() - nl0) / n
+        res = {"unit": "samples/s", "samples_per_gpu": batch, "steps": n, "gpu_launches_per_step": launches,
+               "eager": {"value": batch / (ms_eager / 1e3), "ms_per_step": ms_eager}}
+        gs = GraphedTrainStep(model, opt, n_views=3, warmup=1)
+        if gs.enabled:
+            for _ in range(3):
+                gs(frames)
+            ms_graph, out = timed(lambda: gs(frames), n)
+            loss = out["loss"]
+            res.update(value=batch / (ms_graph / 1e3), ms_per_step=ms_graph, mode="cuda_graph")
+            gs.release()
+        else:
+            res.update(value=res["eager"]["value"], ms_per_step=ms_eager, mode="eager")
+        res["final_loss"] = float(loss.detach())
+        return res
 
     try:
         seed_all(0)
         B = 64
         m = PM.MoCo_TimeSeriesV4("r21d", 128, 16384, 0.999, 0.07, False, True, 2, 64, 0.07, 0.07, "clip-sr-tc", a).to(dev).train()
         frames = torch.rand(B, 3, 48, 112, 112, device=dev)
-        out["configs[2] MoCo+DualVar r21d K=16384 m=0.999 16x112^2"] = time_step(m, lambda: RawClips(frames, 3), B)
+        out["configs[2] MoCo+DualVar r21d K=16384 m=0.999 16x112^2"] = time_step(m, frames, B)
         del m, frames
     except Exception as e:  # noqa: BLE001
         out["configs[2]"] = {"error": f"{type(e).__name__}: {e}"}
@@ -374,7 +391,7 @@ def other_configs_leg(dev):
         B = 16
         m = PM.SimCLR_TimeSeriesV4("s3dg", 128, 0.07, False, True, 2, 64, 0.07, 0.07, "clip-sr-tc", a).to(dev).train()
         frames = torch.rand(B, 3, 96, 128, 128, device=dev)
-        out["configs[3] S3D-G SimCLR+DualVar 32x128^2"] = time_step(m, lambda: RawClips(frames, 3), B, n=3)
+        out["configs[3] S3D-G SimCLR+DualVar 32x128^2"] = time_step(m, frames, B, n=3)
         del m, frames
     except Exception as e:  # noqa: BLE001
         out["configs[3]"] = {"error": f"{type(e).__name__}: {e}"}

@@ -16,7 +16,11 @@ LAYERS = [("fprop temporal 144->64", "f", (N, 16, 56, 56, 144, 64, (3, 1, 1), (1
           ("dgrad+bnred temporal 144->64", "r", (N, 16, 56, 56, 144, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0))),
           ("dgrad+bnred spatial 64->144", "r", (N, 16, 56, 56, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1))),
           ("fprop temporal 83->64", "f", (N, 16, 56, 56, 83, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0))),
-          ("fprop spatial 128->288", "f", (N, 8, 28, 28, 128, 288, (1, 3, 3), (1, 1, 1), (0, 1, 1)))]
+          ("fprop spatial 128->288", "f", (N, 8, 28, 28, 128, 288, (1, 3, 3), (1, 1, 1), (0, 1, 1))),
+          ("dgrad spatial s2 64->230", "d", (N, 16, 56, 56, 64, 230, (1, 3, 3), (1, 2, 2), (0, 1, 1))),
+          ("stem fprop 3->83 7x7 s2", "s", (N, 16, 112, 112, 3, 83, (1, 7, 7), (1, 2, 2), (0, 3, 3)))]
+if os.environ.get("ONLY"):
+    LAYERS = [l for l in LAYERS if any(k in l[0] for k in os.environ["ONLY"].split(","))]
 prof = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
 for name, kind, (n, t, h, w, ci, co, k, s, p) in LAYERS:
     g = K.make_geom(n, t, h, w, ci, co, k, s, p)
@@ -28,7 +32,13 @@ for name, kind, (n, t, h, w, ci, co, k, s, p) in LAYERS:
     ss = torch.randn(2 * g.Cin_p, device=dev)
     sums = torch.zeros(2 * g.Cin_p, dtype=torch.float64, device=dev)
     dxb = torch.empty_like(x)
+    if kind == "s":
+        xs = torch.randn(n, t, h // 2, w // 2 + 3, 16, device=dev).bfloat16()
+        ws = (torch.randn(g.Cout_p, k[0] * 4, 64, device=dev) / 20).bfloat16()
+        ys = torch.empty(n, g.To, g.Ho, g.Wo, g.Cout_p, device=dev, dtype=torch.bfloat16)
     run = {"f": lambda: K.conv3d_fprop(x, wf, g, bn_stats=stats), "d": lambda: K.conv3d_dgrad(dy, wtt, g),
+           "s": lambda: _lib.call("dv_conv3d_stem_fprop_bf16", _lib.ptr(xs), _lib.ptr(ws), _lib.ptr(ys), _lib.ptr(stats), None,
+                                  ctypes.byref(g), _lib.stream_ptr()),
            "r": lambda: _lib.call("dv_conv3d_dgrad_bnred_bf16", _lib.ptr(dy), _lib.ptr(wtt), _lib.ptr(dxb), ctypes.byref(g),
                                   _lib.ptr(x), _lib.ptr(ss), _lib.ptr(sums), _lib.stream_ptr())}[kind]
     for _ in range(2): run()
