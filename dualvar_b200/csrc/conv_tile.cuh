@@ -41,6 +41,7 @@ struct alignas(64) ConvTileParams {
   CUtensorMap out_map;   // output NDHWC, box (64, tw, th, tt, tn), 128B swizzle
   Tap taps[kMaxTaps];
   uint8_t group_len[kMaxTaps];  // taps are grouped in runs; a group shares ONE A box (halo re-use)
+  uint32_t prog[kMaxTaps + 1];  // per tap: A offset inside its group's box | weight-tile offset << 16, in 16-byte units
   TileGeom g;
   int num_taps;
   int num_groups;
@@ -54,6 +55,8 @@ struct alignas(64) ConvTileParams {
   int block_n;        // columns per full channel tile (multiple of 16, <= 256; multiple of 64 if n_tiles > 1)
   int last_n;         // MMA N of the last channel tile (multiple of 16)
   int stages;         // smem ring depth
+  int out_bufs;       // output staging buffers per epilogue group (2; 1 for single-chunk tiles)
+  int split;          // 1: two MMA-issuing threads, two half-width accumulators summed by the epilogue (block_n <= 128)
   int total_tiles;
   double* stats;      // nullable: [2][stats_ld] per-channel sum and sum of squares (of the stored bf16)
   int stats_ld;

@@ -139,18 +139,27 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int n_mma, int 
 }
 
 // mode 2: the same loop as M=256 MMAs over CTA pairs (cta_group::2): each CTA holds its 128 rows of A and half
-// of B's rows; only the leader issues.
+// of B's rows; only the leader issues. Sub-modes (mode >> 8 after the low byte 2):
+//   0x002  one issuing thread, loop of 4 MMAs per operand pair, no commits
+//   0x102  one issuing thread, 12 straight-line MMAs (descriptors formed before them) + one multicast commit to a
+//          rotating barrier per 12 - the shape of one 3-tap stage of conv_tile_kernel
+//   0x202  TWO issuing threads (warps 0 and 1 of the leader), each the 0x102 loop on half of the MMAs, separate
+//          accumulators (TMEM columns 0 / 256) and separate operand regions
+//   0x302  two issuing threads, each 6 of the 12 MMAs of every stage (same operand tiles), separate accumulators
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
-mma_rate_pair_kernel(int n, int n_mma, int region, long long* out) {
+mma_rate_pair_kernel(int n, int n_mma, int region, int sub, long long* out) {
   extern __shared__ uint8_t dsm[];
   __shared__ __align__(8) uint64_t done_bar;
+  __shared__ __align__(8) uint64_t ring_bar[8];
   __shared__ uint32_t tmem_slot;
   const uint32_t raw = smem_u32(dsm);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t rank = cluster_ctarank();
   for (int i = threadIdx.x; i < region / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(dsm + (base - raw))[i] = 0x3c003c00u;
+  const int issuers = sub >= 2 ? 2 : 1;
   if (threadIdx.x == 0) {
-    mbar_init(&done_bar, 1);
+    mbar_init(&done_bar, issuers);
+    for (int i = 0; i < 8; ++i) mbar_init(&ring_bar[i], issuers);
     fence_barrier_init();
   }
   if (threadIdx.x < 32) {
@@ -163,33 +172,75 @@ mma_rate_pair_kernel(int n, int n_mma, int region, long long* out) {
   tc_fence_after_sync();
   const uint32_t tmem = tmem_slot;
   long long t0 = 0, t1 = 0;
-  if (threadIdx.x == 0) {
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0 && w < 2) {
     t0 = clock64();
-    if (rank == 0) {
+    if (rank == 0 && w < issuers) {
       const uint32_t idesc = make_idesc_bf16(256, n, 0, 0);
       const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
       const uint32_t flags = 1u << 16;
       const uint32_t a_bytes = 128 * 128, b_bytes = (uint32_t)(n / 2) * 128;
       const uint32_t pair = a_bytes + ((b_bytes + 1023u) & ~1023u);
-      const uint32_t span = (uint32_t)region / pair * pair;
-      uint32_t off = 0;
-      for (int i = 0; i < n_mma; i += 4) {
-        const uint32_t a = flags | ((base + off) >> 4);
-        const uint32_t b = flags | ((base + off + a_bytes) >> 4);
-        umma2_bf16_lohi(tmem, a, b, hi, idesc, i > 0);
-        umma2_bf16_lohi(tmem, a + 2, b + 2, hi, idesc, 1);
-        umma2_bf16_lohi(tmem, a + 4, b + 4, hi, idesc, 1);
-        umma2_bf16_lohi(tmem, a + 6, b + 6, hi, idesc, 1);
-        off += pair;
-        if (off >= span) off = 0;
+      if (sub == 0) {
+        const uint32_t span = (uint32_t)region / pair * pair;
+        uint32_t off = 0;
+        for (int i = 0; i < n_mma; i += 4) {
+          const uint32_t a = flags | ((base + off) >> 4);
+          const uint32_t b = flags | ((base + off + a_bytes) >> 4);
+          umma2_bf16_lohi(tmem, a, b, hi, idesc, i > 0);
+          umma2_bf16_lohi(tmem, a + 2, b + 2, hi, idesc, 1);
+          umma2_bf16_lohi(tmem, a + 4, b + 4, hi, idesc, 1);
+          umma2_bf16_lohi(tmem, a + 6, b + 6, hi, idesc, 1);
+          off += pair;
+          if (off >= span) off = 0;
+        }
+      } else {
+        // a "stage" = one A box of 18 KB with three tap views shifted by 1024 B + three B tiles
+        const uint32_t stage = 18 * 1024 + 3 * ((b_bytes + 1023u) & ~1023u);
+        const uint32_t half = (uint32_t)region / 2 / stage * stage;
+        const uint32_t org = (sub == 2) ? (uint32_t)w * half : 0u;
+        const uint32_t span = (sub == 2) ? half : (uint32_t)region / stage * stage;
+        const uint32_t acc = tmem + (uint32_t)w * 256u;
+        const int per_stage = (sub == 3) ? 6 : 12;
+        const int mine = n_mma / issuers;
+        uint32_t off = 0;
+        int slot = 0;
+        for (int i = 0; i < mine; i += per_stage) {
+          const uint32_t a = flags | ((base + org + off) >> 4);
+          const uint32_t b = flags | ((base + org + off + 18 * 1024) >> 4);
+          const uint32_t bt = ((b_bytes + 1023u) & ~1023u) >> 4;
+          if (sub == 3) {
+            // this thread's half of the stage: K-steps {0,1} (w = 0) or {2,3} (w = 1) of the three taps
+            const uint32_t k0 = (uint32_t)w * 4u;
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+              umma2_bf16_lohi(acc, a + t * 64 + k0, b + t * bt + k0, hi, idesc, (i | t) > 0);
+              umma2_bf16_lohi(acc, a + t * 64 + k0 + 2, b + t * bt + k0 + 2, hi, idesc, 1);
+            }
+          } else {
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+              umma2_bf16_lohi(acc, a + t * 64, b + t * bt, hi, idesc, (i | t) > 0);
+              umma2_bf16_lohi(acc, a + t * 64 + 2, b + t * bt + 2, hi, idesc, 1);
+              umma2_bf16_lohi(acc, a + t * 64 + 4, b + t * bt + 4, hi, idesc, 1);
+              umma2_bf16_lohi(acc, a + t * 64 + 6, b + t * bt + 6, hi, idesc, 1);
+            }
+          }
+          umma2_commit_both(&ring_bar[slot]);
+          slot = (slot + 1) & 7;
+          off += stage;
+          if (off >= span) off = 0;
+        }
       }
       t1 = clock64();
       umma2_commit_both(&done_bar);
     }
     mbar_wait(&done_bar, 0);
     const long long t2 = clock64();
-    out[blockIdx.x * 2] = t1 - t0;
-    out[blockIdx.x * 2 + 1] = t2 - t0;
+    if (w == 0) {
+      out[blockIdx.x * 2] = t1 - t0;
+      out[blockIdx.x * 2 + 1] = t2 - t0;
+    }
   }
   tc_fence_before_sync();
   cluster_sync_all();
@@ -200,10 +251,10 @@ mma_rate_pair_kernel(int n, int n_mma, int region, long long* out) {
 }
 
 int mma_rate(int n, int n_mma, int region, int mode, long long* out, int grid, cudaStream_t stream) {
-  if (mode == 2) {
+  if ((mode & 0xff) == 2 && mode < 0x400) {
     if (n < 32 || n > 256 || (n & 15)) return fail(kBadArg, "mma_rate: bad N for cta_group::2");
     DV_CUDA_OK(cudaFuncSetAttribute(mma_rate_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    mma_rate_pair_kernel<<<grid & ~1, 128, region + 1024, stream>>>(n, n_mma, region, out);
+    mma_rate_pair_kernel<<<grid & ~1, 128, region + 1024, stream>>>(n, n_mma, region, mode >> 8, out);
     DV_LAUNCH_OK();
     return kOk;
   }
