@@ -25,6 +25,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 namespace dv {
@@ -42,6 +43,7 @@ constexpr int kEpiThreads = 256;
 constexpr int kAStageBytes = kTileM * 128;  // 16 KB
 constexpr int kOutBufBytes = kTileM * 128;  // one 64-channel chunk of the output tile
 constexpr int kMaxStages = 8;
+constexpr int kOutBufs = 4;                  // output staging buffers: two per epilogue group
 constexpr int kTmemCols = 512;
 constexpr int kSmemBudget = 232448 - 20480;  // 227 KB minus static smem (stat partials, barriers)
 
@@ -59,8 +61,8 @@ constexpr int kSmemBudget = 232448 - 20480;  // 227 KB minus static smem (stat p
 // kXf: consumer-side BatchNorm instance (bn_xform.cuh): A boxes land on a CTA-local barrier, warps 10-13 apply
 //      relu?(scale*y + shift) in place and signal the (leader's) transform barrier the MMA warp waits for; the fused
 //      BatchNorm-backward reduce of the epilogue is compiled out of this instance (forward only).
-template <bool kPair, bool kF32 = false, bool kXf = false>
-__global__ void __launch_bounds__((kXf ? kNumThreads + kXfThreads : kNumThreads) + kIssue2Threads, 1)
+template <bool kPair, bool kF32 = false, bool kXf = false, bool kSplit = false>
+__global__ void __launch_bounds__((kXf ? kNumThreads + kXfThreads : kNumThreads) + (kSplit ? kIssue2Threads : 0), 1)
 conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
@@ -101,10 +103,10 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], p.split ? 2 : 1);        // one commit per issuing thread
+      mbar_init(&empty_bar[i], kSplit ? 2 : 1);         // one commit per issuing thread
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&tmem_full_bar[i], p.split ? 2 : 1);
+      mbar_init(&tmem_full_bar[i], kSplit ? 2 : 1);
       mbar_init(&tmem_empty_bar[i], kPair ? 2 * kEpiThreads : kEpiThreads);   // the leader's barrier collects both CTAs' epilogues
     }
     mbar_init(&bres_bar, 1);
@@ -213,22 +215,92 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
         p.prof[blockIdx.x * 16 + 1] = prof_wait_empty;       // producer waiting for a free stage
       }
     }
-  } else if (warp == 1 || warp == kIssue2Warp) {
-    // ------------------------------------------------------------------ MMA issuer(s) (leader CTA only in pair mode)
-    // The issuing thread is the limit of every N <= 128 launch and close to it at N = 144 (tests/diag/mma_rate_pair.py),
-    // so the loop is kept free of everything but the MMAs: per tap ONE constant-bank word (ConvTileParams::prog, fetched
-    // one tap ahead - a dependent LDCU in front of each tap's first MMA cost ~300 cycles per tap) holding both operand
-    // offsets, per MMA two adds.
-    const uint32_t which = warp == 1 ? 0u : 1u;    // split issue: this thread takes K steps which, which + 2 of every tap
-    if (rank == 0 && (which == 0 || p.split)) {
+  } else if (!kSplit && warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only in pair mode)
+    if (rank == 0) {
       const bool issuer = elect_one();
-      const bool split = p.split != 0;
       const uint32_t idesc = make_idesc_bf16(kPair ? 2 * kTileM : kTileM, bn_mma, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       long long prof_wait_full = 0, prof_wait_acc = 0;
       const long long prof_t0 = (kDiag && p.prof) ? clock64() : 0;
+      const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO=1024 B, version 1, SWIZZLE_128B
+      const uint32_t desc_lo_flags = 1u << 16;                           // LBO field (unused for K-major swizzled)
+      const uint32_t ring_enc = smem_u32(ring) >> 4, res_enc = smem_u32(res_b) >> 4;
+      const uint32_t stage_enc = (uint32_t)stage_bytes >> 4, btb_enc = (uint32_t)b_tap_bytes >> 4;
+      const uint32_t a_stage_enc = (uint32_t)p.a_stage_bytes >> 4;
+      if (p.b_resident) {
+        mbar_wait(&bres_bar, 0);
+        tc_fence_after_sync();
+      }
+      for (int tile = unit; tile < p.total_tiles; tile += units, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        const long long ca = (kDiag && p.prof) ? clock64() : 0;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        if (kDiag && p.prof) prof_wait_acc += clock64() - ca;
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * kMaxBlockN;
+        uint32_t accumulate = 0;
+        int gb = 0;
+        for (int grp = 0; grp < p.num_groups; ++grp) {
+          const int len = p.group_len[grp];
+          for (int kc = 0; kc < p.k_chunks; ++kc) {
+            const long long cf = (kDiag && p.prof) ? clock64() : 0;
+            if (!kXf || !p.b_resident) mbar_wait(&full_bar[stage], phase);   // TMA data (kXf: weight tiles only)
+            if (kXf) mbar_wait(&xf_bar[stage], phase);                       // both CTAs' A boxes transformed
+            if (kDiag && p.prof) prof_wait_full += clock64() - cf;
+            tc_fence_after_sync();
+            // descriptor low words (start address >> 4 | LBO field); the high word is a constant
+            const uint32_t st_lo = desc_lo_flags | (ring_enc + (uint32_t)stage * stage_enc);
+            const uint32_t b_lo = p.b_resident ? (desc_lo_flags | (res_enc + (uint32_t)kc * btb_enc)) : st_lo;
+            const int ksteps = (kc == p.k_chunks - 1) ? p.k_steps_last : 4;
+            for (int i = 0; i < len; ++i) {
+              // the tap's 128 rows start shift_rows rows into the shared (halo) A box; shifts are multiples
+              // of 8 rows = 1024 B, so the 128B-swizzle phase of every row is unchanged.
+              // (offsets come from the kernel-parameter constant bank: uniform loads, no smem round trip)
+              const uint32_t aoff = (uint32_t)p.taps[gb + i].shift_rows * 8u;
+              const uint32_t boff = p.b_resident ? (uint32_t)((gb + i) * p.k_chunks) * btb_enc
+                                                 : a_stage_enc + (uint32_t)i * btb_enc;
+              const uint32_t al = st_lo + aoff, bl = b_lo + boff;
+              if (issuer) {
+                // +32 bytes along K inside the 128B swizzle span = +2 in (addr >> 4) units
+                umma_issue<kPair>(d_tmem, al, bl, desc_hi, idesc, accumulate);
+                if (ksteps > 1) umma_issue<kPair>(d_tmem, al + 2, bl + 2, desc_hi, idesc, 1);
+                if (ksteps > 2) umma_issue<kPair>(d_tmem, al + 4, bl + 4, desc_hi, idesc, 1);
+                if (ksteps > 3) umma_issue<kPair>(d_tmem, al + 6, bl + 6, desc_hi, idesc, 1);
+              }
+              accumulate = 1;
+            }
+            if (issuer) umma_commit_to<kPair>(&empty_bar[stage]);
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+          gb += len;
+        }
+        if (issuer) umma_commit_to<kPair>(&tmem_full_bar[acc]);
+        __syncwarp();
+      }
+      if (kDiag && p.prof && issuer) {
+        p.prof[blockIdx.x * 16 + 2] = clock64() - prof_t0;   // MMA issuer total
+        p.prof[blockIdx.x * 16 + 3] = prof_wait_full;        // waiting for TMA data
+        p.prof[blockIdx.x * 16 + 4] = prof_wait_acc;         // waiting for the epilogue to free an accumulator
+      }
+    }
+  } else if (kSplit && (warp == 1 || warp == kIssue2Warp)) {
+    // ------------------------------------------------------------------ split issue: two MMA issuers (leader CTA only)
+    // One thread cannot issue 64-column MMAs as fast as the tensor pipe retires them (tests/diag/mma_rate_pair.py), so
+    // warp 1 and the last warp each issue every second MMA of a tile, into separate accumulators, and each commits
+    // to the stage / accumulator barriers (count 2). The loop holds nothing but the MMAs: per tap ONE constant-bank word
+    // (ConvTileParams::prog, fetched a tap ahead) with both operand offsets.
+    const uint32_t which = warp == 1 ? 0u : 1u;
+    if (rank == 0) {
+      const bool issuer = elect_one();
+      const uint32_t idesc = make_idesc_bf16(kPair ? 2 * kTileM : kTileM, bn_mma, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
       const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO=1024 B, version 1, SWIZZLE_128B
       const uint32_t desc_lo_flags = 1u << 16;                           // LBO field (unused for K-major swizzled)
       const uint32_t ring_lo = desc_lo_flags | (smem_u32(ring) >> 4);
@@ -243,9 +315,7 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
       for (int tile = unit; tile < p.total_tiles; tile += units, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        const long long ca = (kDiag && p.prof) ? clock64() : 0;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
-        if (kDiag && p.prof) prof_wait_acc += clock64() - ca;
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * kMaxBlockN + which * (kMaxBlockN / 2);
         uint32_t accumulate = 0;
@@ -253,11 +323,8 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
         for (int grp = 0; grp < num_groups; ++grp) {
           const int len = p.group_len[grp];
           for (int kc = 0; kc < k_chunks; ++kc) {
-            uint32_t nxt = p.prog[gb];                                       // first tap's offsets: in flight during the wait
-            const long long cf = (kDiag && p.prof) ? clock64() : 0;
-            if (!kXf || !resident) mbar_wait(&full_bar[stage], phase);      // TMA data (kXf: weight tiles only)
-            if (kXf) mbar_wait(&xf_bar[stage], phase);                       // both CTAs' A boxes transformed
-            if (kDiag && p.prof) prof_wait_full += clock64() - cf;
+            uint32_t nxt = p.prog[gb];     // first tap's offsets: in flight during the wait
+            mbar_wait(&full_bar[stage], phase);
             tc_fence_after_sync();
             // descriptor low words (start address >> 4 | LBO field); the high word is a constant. A tap's word of the
             // program holds its A offset inside the (halo) box - shifts are multiples of 8 rows = 1024 B, so the
@@ -265,47 +332,32 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
             // base, chunk kc adds btb; streamed: from the stage base)
             const uint32_t st_lo = ring_lo + (uint32_t)stage * stage_enc;
             const uint32_t b_lo = resident ? res_lo + (uint32_t)kc * btb_enc : st_lo;
-            if (kc != k_chunks - 1 || k_last == 4) {
-              // full 64-channel chunk: four K steps per tap (+32 bytes along K inside the swizzle span = +2 in addr >> 4)
-              if (split) {
-                const uint32_t k0 = 2u * which;
-                for (int i = 0; i < len; ++i) {
-                  const uint32_t cur = nxt;
-                  nxt = p.prog[gb + i + 1];
-                  const uint32_t al = st_lo + (cur & 0xffffu) + k0, bl = b_lo + (cur >> 16) + k0;
-                  if (issuer) {
-                    umma_issue<kPair>(d_tmem, al, bl, desc_hi, idesc, accumulate);
-                    umma_issue<kPair>(d_tmem, al + 4, bl + 4, desc_hi, idesc, 1);
-                  }
-                  accumulate = 1;
-                }
-              } else {
-                for (int i = 0; i < len; ++i) {
-                  const uint32_t cur = nxt;
-                  nxt = p.prog[gb + i + 1];
-                  const uint32_t al = st_lo + (cur & 0xffffu), bl = b_lo + (cur >> 16);
-                  if (issuer) {
-                    umma_issue<kPair>(d_tmem, al, bl, desc_hi, idesc, accumulate);
-                    umma_issue<kPair>(d_tmem, al + 2, bl + 2, desc_hi, idesc, 1);
-                    umma_issue<kPair>(d_tmem, al + 4, bl + 4, desc_hi, idesc, 1);
-                    umma_issue<kPair>(d_tmem, al + 6, bl + 6, desc_hi, idesc, 1);
-                  }
-                  accumulate = 1;
-                }
-              }
-            } else {
-              // last chunk with 1..3 K steps; split issue: MMA number i * k_last + ks of the stage goes to thread (.. & 1)
+            // KS K steps of every tap of the stage (+32 bytes along K inside the swizzle span = +2 in addr >> 4).
+            // MMA number i * KS + ks of the stage belongs to thread (i * KS + ks) & 1, i.e. this thread takes the K
+            // steps q, q + 2 of a tap with q = parity of (i * KS) ^ which.
+            auto run = [&](auto ks_c) {
+              constexpr int KS = decltype(ks_c)::value;
+              uint32_t q = which;
               for (int i = 0; i < len; ++i) {
                 const uint32_t cur = nxt;
                 nxt = p.prog[gb + i + 1];
                 const uint32_t al = st_lo + (cur & 0xffffu), bl = b_lo + (cur >> 16);
-                for (int ks = 0; ks < k_last; ++ks) {
-                  if (split && (((uint32_t)(i * k_last + ks) & 1u) != which)) continue;
-                  if (issuer) umma_issue<kPair>(d_tmem, al + 2 * ks, bl + 2 * ks, desc_hi, idesc, accumulate);
+                if (q < (uint32_t)KS) {
+                  if (issuer) umma_issue<kPair>(d_tmem, al + 2 * q, bl + 2 * q, desc_hi, idesc, accumulate);
                   accumulate = 1;
                 }
+                if (KS > 2 && q + 2 < (uint32_t)KS) {
+                  if (issuer) umma_issue<kPair>(d_tmem, al + 2 * q + 4, bl + 2 * q + 4, desc_hi, idesc, 1);
+                }
+                if (KS & 1) q ^= 1u;
               }
-            }
+            };
+            const int ksteps = (kc == k_chunks - 1) ? k_last : 4;
+            using std::integral_constant;
+            if (ksteps == 4) run(integral_constant<int, 4>{});
+            else if (ksteps == 1) run(integral_constant<int, 1>{});
+            else if (ksteps == 2) run(integral_constant<int, 2>{});
+            else run(integral_constant<int, 3>{});
             if (issuer) umma_commit_to<kPair>(&empty_bar[stage]);
             __syncwarp();
             if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -315,13 +367,8 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
         if (issuer) umma_commit_to<kPair>(&tmem_full_bar[acc]);
         __syncwarp();
       }
-      if (kDiag && p.prof && issuer && which == 0) {
-        p.prof[blockIdx.x * 16 + 2] = clock64() - prof_t0;   // MMA issuer total
-        p.prof[blockIdx.x * 16 + 3] = prof_wait_full;        // waiting for TMA data
-        p.prof[blockIdx.x * 16 + 4] = prof_wait_acc;         // waiting for the epilogue to free an accumulator
-      }
     }
-  } else if (kXf && warp >= 10 && warp < kIssue2Warp) {
+  } else if (kXf && warp >= 10 && warp < 14) {
     // ------------------------------------------------------------------ A-operand transform (kXf: warps 10-13)
     const int tid = threadIdx.x - kNumThreads;
     const uint32_t xf0_addr = kPair ? mapa_u32(smem_u32(&xf_bar[0]), 0) : smem_u32(&xf_bar[0]);
@@ -358,8 +405,7 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
     const int grp = (warp - 2) >> 2;   // epilogue group: chunks grp, grp + 2, ... of every tile
     const int et = (threadIdx.x - 64) & 127;   // thread index inside the group
     const bool leader = (et == 0);
-    uint8_t* const o_grp = o_smem + grp * p.out_bufs * kOutBufBytes;
-    const bool one_buf = p.out_bufs == 1;
+    uint8_t* const o_grp = o_smem + grp * 2 * kOutBufBytes;
     const int rw = row & ((1 << g.lw) - 1);
     const int rh = (row >> g.lw) & ((1 << g.lh) - 1);
     const int rt = (row >> (g.lw + g.lh)) & ((1 << g.lt) - 1);
@@ -401,14 +447,7 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
       for (int cc = first_cc; cc < nchunks; cc += 2) {
         const int ncols = min(64, bn_mma - cc * 64);
         uint8_t* ob = o_grp + obuf * kOutBufBytes;
-        if (one_buf) {
-          // a single staging buffer per group (64-channel tiles: the shared memory goes to resident weights instead):
-          // the group's previous store must have read it before anybody overwrites it
-          if (leader) tma_store_wait_read<0>();
-          named_bar_sync(1 + grp, 128);
-        } else {
-          obuf ^= 1;
-        }
+        obuf ^= 1;
         const long long pc0 = prof_on ? clock64() : 0;
         // fused BN-backward reduce: this thread's 32 (row, channel pair) words of y for the column pass
         // below are requested now, so their latency hides behind the TMEM load / convert / store phase.
@@ -456,7 +495,7 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
         if (ncols > 32) tmem_ld16(t_addr + cc * 64 + 32, *reinterpret_cast<uint32_t(*)[16]>(&v[32]));
         if (ncols > 48) tmem_ld16(t_addr + cc * 64 + 48, *reinterpret_cast<uint32_t(*)[16]>(&v[48]));
         tmem_ld_wait();
-        if (p.split) {
+        if (kSplit) {
           // split issue: the second issuing thread's half of the sum sits 128 columns further
 #pragma unroll
           for (int part = 0; part < 4; ++part) {
@@ -887,10 +926,7 @@ static int conv_multi_tap_region(ConvTileParams& P, MapEncoder enc, const void* 
   const int b_tap_bytes = (pair ? P.block_n / 2 : P.block_n) * 128;
   const bool xf = P.xf_ss != nullptr;
   const int xf_bytes = xf ? round_up(P.k_chunks * 512, 1024) : 0;      // staged scale / shift table
-  // output staging: two 16 KB buffers per epilogue group, or one each for tiles of a single 64-channel chunk (every
-  // group then stores once per two tiles and the 32 KB go to resident weights / A stages instead)
-  P.out_bufs = (P.n_tiles == 1 && P.block_n <= 64) ? 1 : 2;
-  const int out_bytes = 2 * P.out_bufs * kOutBufBytes;
+  const int out_bytes = kOutBufs * kOutBufBytes;
   const int avail = kSmemBudget - 1024 - out_bytes - xf_bytes;
   const int res_bytes = ntaps * P.k_chunks * b_tap_bytes;
   // weight-stationary when the whole filter of this channel tile fits next to >= 3 A stages and the CTA
@@ -905,12 +941,16 @@ static int conv_multi_tap_region(ConvTileParams& P, MapEncoder enc, const void* 
                                  kin_p, stats, bias, stream, false, red, rows_lw, org_h);
   if (P.stages < 2) return fail(kUnsupported, "conv tile: not enough shared memory for 2 stages");
   // split issue: two issuing threads on two half-width accumulators where one thread is the limit - 64-column tiles
-  // (one thread: >= 50 cycles per MMA against 32 of tensor time / 40 of operand fetch) - and the first stage has an MMA
-  // for each of them; wider tiles (the 88-channel stem) are epilogue-bound and lose to the second accumulator's loads
-  // (DV_CONV_SPLIT_ISSUE=2 extends it to N <= 128)
-  P.split = (g_split_issue && P.n_tiles == 1 && P.block_n <= (g_split_issue == 2 ? kMaxBlockN / 2 : 64) &&
+  // (one thread: >= 50 cycles per MMA against 32 of tensor time / 40 of operand fetch) with enough MMAs per tile that
+  // the MMA loop, not the epilogue, paces the tile (144->64 temporal fprop, 27 MMAs: -20 %; 83->64, 18 MMAs: +10 %).
+  // Wider tiles (the 88-channel stem) are epilogue-bound and lose to the second accumulator's loads
+  // (DV_CONV_SPLIT_ISSUE=2 extends it to N <= 128 and any MMA count; tests/diag/layer_ab.py).
+  const int mma_per_tile = ntaps * ((P.k_chunks - 1) * 4 + P.k_steps_last);
+  P.split = (g_split_issue && !xf && outv.esize == 2 && P.n_tiles == 1 &&
+             P.block_n <= (g_split_issue == 2 ? kMaxBlockN / 2 : 64) && (g_split_issue == 2 || mma_per_tile >= 24) &&
              P.group_len[0] * (P.k_chunks > 1 ? 4 : P.k_steps_last) >= 2) ? 1 : 0;
-  {  // the issue program: per tap, A offset inside its group's box | weight-tile offset << 16 (16-byte units)
+  if (P.split) {
+    // the split kernel's issue program: per tap, A offset inside its group's box | weight-tile offset << 16 (16-byte units)
     int t = 0;
     for (int grp = 0; grp < ngroups; ++grp)
       for (int i = 0; i < P.group_len[grp]; ++i, ++t) {
@@ -972,6 +1012,10 @@ static int conv_multi_tap_region(ConvTileParams& P, MapEncoder enc, const void* 
                                     kSmemBudget));
     DV_CUDA_OK(cudaFuncSetAttribute(conv_tile_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     kSmemBudget));
+    DV_CUDA_OK(cudaFuncSetAttribute(conv_tile_kernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kSmemBudget));
+    DV_CUDA_OK(cudaFuncSetAttribute(conv_tile_kernel<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kSmemBudget));
     attr_set = true;
   }
   // CTAs (or CTA pairs): one per SM (pair of SMs), a multiple of the channel-tile count
@@ -979,13 +1023,14 @@ static int conv_multi_tap_region(ConvTileParams& P, MapEncoder enc, const void* 
   if (units > P.total_tiles) units = P.total_tiles;  // total_tiles is a multiple of n_tiles
   const bool f32 = P.out_f32 != nullptr;
   if (!pair) {
-    if (xf) conv_tile_kernel<false, false, true><<<units, kNumThreads + kXfThreads + kIssue2Threads, smem_bytes, stream>>>(P);
-    else if (f32) conv_tile_kernel<false, true><<<units, kNumThreads + kIssue2Threads, smem_bytes, stream>>>(P);
-    else conv_tile_kernel<false><<<units, kNumThreads + kIssue2Threads, smem_bytes, stream>>>(P);
+    if (xf) conv_tile_kernel<false, false, true><<<units, kNumThreads + kXfThreads, smem_bytes, stream>>>(P);
+    else if (f32) conv_tile_kernel<false, true><<<units, kNumThreads, smem_bytes, stream>>>(P);
+    else if (P.split) conv_tile_kernel<false, false, false, true><<<units, kNumThreads + kIssue2Threads, smem_bytes, stream>>>(P);
+    else conv_tile_kernel<false><<<units, kNumThreads, smem_bytes, stream>>>(P);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * units);
-    cfg.blockDim = dim3((xf ? kNumThreads + kXfThreads : kNumThreads) + kIssue2Threads);
+    cfg.blockDim = dim3((xf ? kNumThreads + kXfThreads : kNumThreads) + (P.split ? kIssue2Threads : 0));
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr;
@@ -995,6 +1040,7 @@ static int conv_multi_tap_region(ConvTileParams& P, MapEncoder enc, const void* 
     cfg.numAttrs = 1;
     if (xf) DV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tile_kernel<true, false, true>, P));
     else if (f32) DV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tile_kernel<true, true>, P));
+    else if (P.split) DV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tile_kernel<true, false, false, true>, P));
     else DV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tile_kernel<true>, P));
   }
   DV_LAUNCH_OK();

@@ -55,8 +55,7 @@ struct alignas(64) ConvTileParams {
   int block_n;        // columns per full channel tile (multiple of 16, <= 256; multiple of 64 if n_tiles > 1)
   int last_n;         // MMA N of the last channel tile (multiple of 16)
   int stages;         // smem ring depth
-  int out_bufs;       // output staging buffers per epilogue group (2; 1 for single-chunk tiles)
-  int split;          // 1: two MMA-issuing threads, two half-width accumulators summed by the epilogue (block_n <= 128)
+  int split;          // 1: kSplit kernel instance - two MMA-issuing threads, two half-width accumulators summed by the epilogue
   int total_tiles;
   double* stats;      // nullable: [2][stats_ld] per-channel sum and sum of squares (of the stored bf16)
   int stats_ld;

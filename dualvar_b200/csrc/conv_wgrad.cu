@@ -24,7 +24,6 @@ namespace dv {
 constexpr int kWgThreads = 192;
 constexpr int kBoxBytes = 64 * 128;  // one 64-position x 64-channel box
 constexpr int kWgMaxUnits = 8;
-constexpr int kWgMaxPairs = 16;   // unit pairs of one CTA: 512 TMEM columns / 32-column accumulators (halo groups)
 // Not the whole 227 KB: wgrad runs on a side stream next to the BatchNorm passes of the layers below (engine.py), whose
 // blocks need ~17 KB of shared memory each to become resident on the same SM.
 constexpr int kWgSmemBudget = 232448 - 2048 - 36 * 1024;
@@ -166,50 +165,35 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
     int stage = 0;
     uint32_t phase = 0;
     uint32_t accumulate = 0;
-    // The descriptor low word of every unit pair relative to its stage (LBO << 16 | offset) does not depend on the tile:
-    // formed once, so that the issue loop holds nothing but adds and MMAs (a constant-bank lookup in front of each
-    // pair's first MMA stalled the issuing thread for longer than the pair's four MMAs take)
-    uint32_t pair_lo[kWgMaxPairs];
-#pragma unroll
-    for (int pr = 0; pr < kWgMaxPairs; ++pr) {
-      pair_lo[pr] = 0;
-      if (pr < npairs) {
-        if (p.halo) {
-          // unit = shifted view of a halo box; the pair's second 64-channel group starts (LBO) wherever the
-          // next unit starts (possibly overlapping the first)
-          const uint32_t o0 = (uint32_t)p.unit_off[unit0 + 2 * pr];
-          const uint32_t o1 = (2 * pr + 1 < nu) ? (uint32_t)p.unit_off[unit0 + 2 * pr + 1] : o0 + 64u;
-          pair_lo[pr] = ((o1 - o0) << 16) | o0;
-        } else {
-          pair_lo[pr] = lo_flags | ((uint32_t)pr * (2 * kBoxBytes >> 4));
-        }
-      }
-    }
-    const uint32_t acc_stride = (uint32_t)p.acc_stride;
-    const int stages = p.stages;
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       mbar_wait(xf ? &xf_bar[stage] : &full_bar[stage], phase);
       tc_fence_after_sync();
-      const uint32_t st = base_enc + (uint32_t)stage * stage_enc;
-      const uint32_t b_lo = (lo_flags | st) + a_enc;
+      const uint32_t a_lo = lo_flags | (base_enc + (uint32_t)stage * stage_enc);
+      const uint32_t b_lo = a_lo + a_enc;
       if (issuer) {
-#pragma unroll
-        for (int pr = 0; pr < kWgMaxPairs; ++pr) {
-          if (pr < npairs) {
-            const uint32_t al = pair_lo[pr] + st;
-            const uint32_t dt = tmem_base + pr * acc_stride;
-            // one UMMA K step = 16 positions = 2048 B = +128 in (addr >> 4) units
-            umma_bf16_lohi(dt, al, b_lo, desc_hi, idesc, accumulate);
-            umma_bf16_lohi(dt, al + 128, b_lo + 128, desc_hi, idesc, 1);
-            umma_bf16_lohi(dt, al + 256, b_lo + 256, desc_hi, idesc, 1);
-            umma_bf16_lohi(dt, al + 384, b_lo + 384, desc_hi, idesc, 1);
+        for (int pr = 0; pr < npairs; ++pr) {
+          uint32_t al;
+          if (p.halo) {
+            // unit = shifted view of a halo box; the pair's second 64-channel group starts (LBO) wherever the
+            // next unit starts (possibly overlapping the first)
+            const uint32_t o0 = (uint32_t)p.unit_off[unit0 + 2 * pr];
+            const uint32_t o1 = (2 * pr + 1 < nu) ? (uint32_t)p.unit_off[unit0 + 2 * pr + 1] : o0 + 64u;
+            al = ((o1 - o0) << 16) | (base_enc + (uint32_t)stage * stage_enc + o0);
+          } else {
+            al = a_lo + (uint32_t)pr * (2 * kBoxBytes >> 4);
           }
+          const uint32_t dt = tmem_base + pr * p.acc_stride;
+          // one UMMA K step = 16 positions = 2048 B = +128 in (addr >> 4) units
+          umma_bf16_lohi(dt, al, b_lo, desc_hi, idesc, accumulate);
+          umma_bf16_lohi(dt, al + 128, b_lo + 128, desc_hi, idesc, 1);
+          umma_bf16_lohi(dt, al + 256, b_lo + 256, desc_hi, idesc, 1);
+          umma_bf16_lohi(dt, al + 384, b_lo + 384, desc_hi, idesc, 1);
         }
         umma_commit(&empty_bar[stage]);
       }
       accumulate = 1;
       __syncwarp();
-      if (++stage == stages) { stage = 0; phase ^= 1; }
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
     if (issuer) umma_commit(&acc_bar);
     __syncwarp();

@@ -27,6 +27,13 @@ CASES = [
     ("spatial halo wgrad 24->40 24x16", 3, 2, 24, 16, 24, 40, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
     ("two-region tiling 64->144 24x32", 2, 2, 24, 32, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
     ("two-region tiling 3x3x3 40->64 40x16", 2, 3, 40, 16, 40, 64, (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    # narrow 1x1x1 convolutions over many input channels (S3D Inception branches): >= 24 MMAs per 64-column tile, i.e. the
+    # two-issuer kernel instance, on maps of one or two tiles, 16..64 output columns, partial last K chunk
+    ("1x1x1 480->16 4x4x4", 4, 4, 4, 4, 480, 16, (1, 1, 1), (1, 1, 1), (0, 0, 0)),
+    ("1x1x1 480->64 4x4x4", 4, 4, 4, 4, 480, 64, (1, 1, 1), (1, 1, 1), (0, 0, 0)),
+    ("1x1x1 512->24 4x4x4", 4, 4, 4, 4, 512, 24, (1, 1, 1), (1, 1, 1), (0, 0, 0)),
+    ("1x1x1 832->48 2x2x2", 4, 2, 2, 2, 832, 48, (1, 1, 1), (1, 1, 1), (0, 0, 0)),
+    ("1x1x1 400->40 8x8x8", 4, 8, 8, 8, 400, 40, (1, 1, 1), (1, 1, 1), (0, 0, 0)),
 ]
 
 
@@ -205,8 +212,17 @@ def test_consumer_side_batchnorm_is_bit_identical_to_the_two_pass_path(case, rel
     y_b = torch.empty_like(y_a)
     _lib.call("dv_conv3d_fprop_bnrelu_bf16", ptr(y_prev), ptr(ss), 1 if relu else 0, ptr(wf), ptr(y_b), ptr(st_b), None,
               ctypes.byref(g), stream_ptr())
-    assert torch.equal(y_a, y_b), (y_a.float() - y_b.float()).abs().max().item()
-    torch.testing.assert_close(st_b, st_a, rtol=1e-12, atol=1e-6)
+    if g.Cout_p > 64:
+        assert torch.equal(y_a, y_b), (y_a.float() - y_b.float()).abs().max().item()
+        torch.testing.assert_close(st_b, st_a, rtol=1e-12, atol=1e-6)
+    else:
+        # 64-column tiles: the plain kernel may run as its two-issuer instance (two accumulators summed in the epilogue),
+        # i.e. another fp32 summation order than the fused kernel's single accumulator: a last-place difference in a
+        # few elements, not bit identity
+        diff = (y_a.float() - y_b.float()).abs()
+        assert diff.max().item() <= 2.0 ** -7 * y_a.float().abs().max().item()
+        assert (diff > 0).float().mean().item() < 0.02
+        torch.testing.assert_close(st_b, st_a, rtol=1e-3, atol=5e-2)     # a few last-place flips of stored values
     dy = torch.randn(y_a.shape, device=dev, generator=gen).bfloat16()
     if g.Cout_p > Cout:
         dy[..., Cout:] = 0
