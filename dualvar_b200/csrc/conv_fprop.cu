@@ -324,7 +324,8 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
           const int len = p.group_len[grp];
           for (int kc = 0; kc < k_chunks; ++kc) {
             uint32_t nxt = p.prog[gb];     // first tap's offsets: in flight during the wait
-            mbar_wait(&full_bar[stage], phase);
+            if (!kXf || !resident) mbar_wait(&full_bar[stage], phase);      // TMA data (kXf: weight tiles only)
+            if (kXf) mbar_wait(&xf_bar[stage], phase);                       // both CTAs' A boxes transformed
             tc_fence_after_sync();
             // descriptor low words (start address >> 4 | LBO field); the high word is a constant. A tap's word of the
             // program holds its A offset inside the (halo) box - shifts are multiples of 8 rows = 1024 B, so the
@@ -946,7 +947,7 @@ static int conv_multi_tap_region(ConvTileParams& P, MapEncoder enc, const void* 
   // Wider tiles (the 88-channel stem) are epilogue-bound and lose to the second accumulator's loads
   // (DV_CONV_SPLIT_ISSUE=2 extends it to N <= 128 and any MMA count; tests/diag/layer_ab.py).
   const int mma_per_tile = ntaps * ((P.k_chunks - 1) * 4 + P.k_steps_last);
-  P.split = (g_split_issue && !xf && outv.esize == 2 && P.n_tiles == 1 &&
+  P.split = (g_split_issue && outv.esize == 2 && P.n_tiles == 1 &&
              P.block_n <= (g_split_issue == 2 ? kMaxBlockN / 2 : 64) && (g_split_issue == 2 || mma_per_tile >= 24) &&
              P.group_len[0] * (P.k_chunks > 1 ? 4 : P.k_steps_last) >= 2) ? 1 : 0;
   if (P.split) {
@@ -1014,6 +1015,10 @@ static int conv_multi_tap_region(ConvTileParams& P, MapEncoder enc, const void* 
                                     kSmemBudget));
     DV_CUDA_OK(cudaFuncSetAttribute(conv_tile_kernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     kSmemBudget));
+    DV_CUDA_OK(cudaFuncSetAttribute(conv_tile_kernel<false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kSmemBudget));
+    DV_CUDA_OK(cudaFuncSetAttribute(conv_tile_kernel<true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kSmemBudget));
     DV_CUDA_OK(cudaFuncSetAttribute(conv_tile_kernel<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     kSmemBudget));
     attr_set = true;
@@ -1023,7 +1028,8 @@ static int conv_multi_tap_region(ConvTileParams& P, MapEncoder enc, const void* 
   if (units > P.total_tiles) units = P.total_tiles;  // total_tiles is a multiple of n_tiles
   const bool f32 = P.out_f32 != nullptr;
   if (!pair) {
-    if (xf) conv_tile_kernel<false, false, true><<<units, kNumThreads + kXfThreads, smem_bytes, stream>>>(P);
+    if (xf && P.split) conv_tile_kernel<false, false, true, true><<<units, kNumThreads + kXfThreads + kIssue2Threads, smem_bytes, stream>>>(P);
+    else if (xf) conv_tile_kernel<false, false, true><<<units, kNumThreads + kXfThreads, smem_bytes, stream>>>(P);
     else if (f32) conv_tile_kernel<false, true><<<units, kNumThreads, smem_bytes, stream>>>(P);
     else if (P.split) conv_tile_kernel<false, false, false, true><<<units, kNumThreads + kIssue2Threads, smem_bytes, stream>>>(P);
     else conv_tile_kernel<false><<<units, kNumThreads, smem_bytes, stream>>>(P);
@@ -1038,7 +1044,8 @@ static int conv_multi_tap_region(ConvTileParams& P, MapEncoder enc, const void* 
     attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    if (xf) DV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tile_kernel<true, false, true>, P));
+    if (xf && P.split) DV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tile_kernel<true, false, true, true>, P));
+    else if (xf) DV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tile_kernel<true, false, true>, P));
     else if (f32) DV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tile_kernel<true, true>, P));
     else if (P.split) DV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tile_kernel<true, false, false, true>, P));
     else DV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tile_kernel<true>, P));

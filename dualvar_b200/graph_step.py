@@ -28,6 +28,8 @@ replay in lockstep (they do: same loop). Under torch's own DistributedDataParall
 needs its own warm-up protocol for capture). All eager warm-up steps and the capture run on ONE dedicated stream, so
 that per-stream resources (the weight-gradient side stream, the BatchNorm exchange channel) exist before the capture.
 """
+import gc
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -115,11 +117,18 @@ class GraphedTrainStep:
         PM._perm_source = self._perm_source
         from . import _lib
         n0 = _lib.load().dv_launch_count()
+        # no cyclic garbage collection while the stream captures: a collection that happens to release CUDA objects of an
+        # earlier (e.g. failed and abandoned) graph frees device memory, which invalidates the running capture
+        gc_was_on = gc.isenabled()
         try:
             torch.cuda.synchronize()
+            gc.collect()
+            gc.disable()
             with torch.cuda.graph(g, stream=self.stream):
                 out = self._step(set_to_none=False)
         finally:
+            if gc_was_on:
+                gc.enable()
             PM._perm_source = prev
         self.launches_per_step = int(_lib.load().dv_launch_count() - n0)
         self.graph, self.out, self.sig = g, out, self._lr_signature()

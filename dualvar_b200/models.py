@@ -284,36 +284,78 @@ class _MoCoBase(nn.Module):
 
     @torch.no_grad()
     def _shuffle_plan(self, n_local):
-        """idx_shuffle from rank 0 + its inverse (model/moco.py:371-381)."""
+        """idx_shuffle from rank 0 (model/moco.py:371-374) turned into an all-to-all plan (shuffle_bn_plan): every rank
+        draws a permutation (the reference's RNG consumption), rank 0's wins; one 8-byte-per-clip read-back gives the
+        host the split sizes."""
         import torch.distributed as dist
         world = dist.get_world_size()
         idx = torch.randperm(n_local * world).cuda()
         dist.broadcast(idx, src=0)
-        return idx, torch.argsort(idx), idx.view(world, -1)[dist.get_rank()]
+        return shuffle_bn_plan(idx.cpu(), world, dist.get_rank(), n_local, idx.device)
 
     @torch.no_grad()
-    def _unshuffle(self, x, idx_unshuffle):
-        import torch.distributed as dist
-        xg = concat_all_gather(x)
-        return xg[idx_unshuffle.view(dist.get_world_size(), -1)[dist.get_rank()]]
+    def _unshuffle(self, x, rows):
+        """Keys back in the original order (model/moco.py:385-402): gather every rank's keys (128 floats per clip) and
+        take this rank's rows."""
+        return concat_all_gather(x)[rows]
 
     def _key_input(self, backbone, block, view):
-        """Ingest the key clips; with shuffle-BN the bf16 ingested clips (not the fp32 frames) are
-        all-gathered and this rank keeps its shuffled share (model/moco.py:357-383)."""
+        """Ingest the key clips; with shuffle-BN every rank SENDS each of its bf16 ingested clips to the one rank whose
+        BatchNorm group the permutation puts it in (one all-to-all: B clips leave and B clips arrive per rank, instead of
+        gathering world * B clips and dropping all but B; model/moco.py:357-383)."""
         s2d = backbone.wants_s2d(block)
         if not self._distributed_on():
             return (lambda: E.ingest(block, first_view=view, n_views=1, s2d=s2d)), None
         B = (block.block_shape if isinstance(block, E.RawClips) else block.shape)[0]
-        idx, unshuf, mine = self._shuffle_plan(B)
+        plan = self._shuffle_plan(B)
 
         def make():
             local = E.ingest(block, first_view=view, n_views=1, s2d=s2d)
             cd = E.clip_dim()      # fp32 mode: split planes [K][clips][...]
             t = E.input_tensor(local)
-            allx = concat_all_gather(t) if cd == 0 else concat_all_gather(t.transpose(0, 1).contiguous()).transpose(0, 1)
-            sel = allx.index_select(cd, mine).contiguous()
+            if cd == 0:
+                sel = exchange_clips(t, plan)
+            else:
+                sel = exchange_clips(t.transpose(0, 1).contiguous(), plan).transpose(0, 1).contiguous()
             return E.input_act(sel, local.C, local.s2d)
-        return make, unshuf
+        return make, plan["unshuffle_rows"]
+
+
+def shuffle_bn_plan(idx, world, rank, n_local, device=None):
+    """All-to-all plan of MoCo's shuffle-BN for one rank.
+
+    ``idx`` (host, int64, world * n_local) is the reference's ``idx_shuffle``: rank g's key encoder sees the clips
+    ``idx.view(world, -1)[g]`` of the gathered batch (model/moco.py:376-381). Clip j lives on rank j // n_local, so
+    rank r sends to rank g its clips {j % n_local : j in idx_g, j // n_local == r}. BatchNorm statistics do not depend
+    on the order of the clips inside a rank's batch, so a rank keeps its share in ARRIVAL order (by source rank, then
+    by position in idx_g) - no reordering copy - and the un-shuffle indices account for that order: the gathered keys
+    come back exactly in the original order, as with the reference's ``idx_unshuffle`` (model/moco.py:377,400).
+    Returns send_index (local clip indices in send order), send_counts / recv_counts per peer, and unshuffle_rows (rows of
+    the all-gathered keys that are this rank's original clips)."""
+    idx = idx.view(world, n_local)
+    src = idx // n_local
+    # arrival order on rank g: stable sort of idx_g by source rank
+    order = torch.argsort(src, dim=1, stable=True)
+    eff = torch.gather(idx, 1, order)                       # eff[g][q] = original global clip in slot q of rank g
+    send_index = torch.cat([(eff[g][eff[g] // n_local == rank]) % n_local for g in range(world)])
+    send_counts = [int((eff[g] // n_local == rank).sum()) for g in range(world)]
+    recv_counts = [int((eff[rank] // n_local == r).sum()) for r in range(world)]
+    unshuffle = torch.argsort(eff.reshape(-1))              # position of original clip j among the gathered keys
+    rows = unshuffle.view(world, n_local)[rank]
+    if device is not None:
+        send_index, rows = send_index.to(device), rows.to(device)
+    return {"send_index": send_index, "send_counts": send_counts, "recv_counts": recv_counts, "unshuffle_rows": rows,
+            "effective": eff}
+
+
+@torch.no_grad()
+def exchange_clips(t, plan):
+    """This rank's shuffled share of the clips ``t`` [n_local, ...] (see shuffle_bn_plan): one all_to_all_single."""
+    import torch.distributed as dist
+    send = t.index_select(0, plan["send_index"]).contiguous()
+    out = torch.empty_like(t)
+    dist.all_to_all_single(out, send, output_split_sizes=plan["recv_counts"], input_split_sizes=plan["send_counts"])
+    return out
 
 
 class MoCo_Naked(_MoCoBase):

@@ -91,3 +91,49 @@ def test_cuda_row_kernel_column_order_matches_oracle(n, N, rank, local):
             j = 0 if c == p else 1 + c - (1 if c > s else 0) - (1 if c > p else 0)
             got[j] = c
         assert got == want[i].tolist()
+
+
+def _shuffle_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dualvar_b200.models import shuffle_bn_plan, exchange_clips, concat_all_gather
+        ok = {}
+        for n_local, seed in ((4, 0), (5, 1), (1, 2), (8, 3)):
+            torch.manual_seed(seed)
+            idx = torch.randperm(n_local * world)
+            dist.broadcast(idx, src=0)                      # rank 0's permutation, as model/moco.py:371-374
+            plan = shuffle_bn_plan(idx, world, rank, n_local)
+            # clip j of the gathered batch carries the value j in every element
+            mine = torch.arange(rank * n_local, (rank + 1) * n_local, dtype=torch.float32).view(-1, 1, 1).expand(-1, 3, 2).contiguous()
+            got = exchange_clips(mine, plan)
+            want_set = sorted(idx.view(world, n_local)[rank].tolist())     # the reference's BatchNorm group of this rank
+            ok[f"group_{n_local}"] = sorted(got[:, 0, 0].long().tolist()) == want_set and bool((got == got[:, :1, :1]).all())
+            ok[f"order_{n_local}"] = got[:, 0, 0].long().tolist() == plan["effective"][rank].tolist()
+            # "keys" = the clip id the encoder saw in each slot; un-shuffled they must be this rank's own clips in order
+            keys = got[:, 0, :1].contiguous()
+            back = concat_all_gather(keys)[plan["unshuffle_rows"]]
+            ok[f"unshuffle_{n_local}"] = back[:, 0].long().tolist() == list(range(rank * n_local, (rank + 1) * n_local))
+            ok[f"counts_{n_local}"] = sum(plan["send_counts"]) == n_local and sum(plan["recv_counts"]) == n_local
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_moco_shuffle_bn_all_to_all_plan(world):
+    """MoCo's shuffle-BN as ONE all-to-all (models.shuffle_bn_plan / exchange_clips; model/moco.py:357-402): every rank ends
+    up with exactly the reference's BatchNorm group, and the un-shuffle returns every key to its own rank and slot."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shuffle_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, out in results:
+        for k, v in out.items():
+            assert v, (rank, k)
