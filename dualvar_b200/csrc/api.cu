@@ -98,6 +98,13 @@ int relu_bwd(const float* dy, const float* y, float* dx, long long n, cudaStream
 int l2norm_fwd(const float* x, float* y, float* inv_norm, long long rows, int d, float eps, cudaStream_t stream);
 int l2norm_bwd(const float* dy, const float* y, const float* inv_norm, float* dx, long long rows, int d,
                cudaStream_t stream);
+int sim_ce_blocks(int C);
+int sim_ce_fwd(const float* a, int lda, const float* b, int ldb, int b_dmajor, int R, int C, int d, float* S, int ld_s,
+               int col0, float* logits, int ld_logits, const int* self_col, const int* pos_col, float inv_T,
+               float* partials, cudaStream_t stream);
+int sim_ce_finish(float* S, int ld_s, int R, int C, int col0, const float* partials, float* logits, int ld_logits,
+                  const int* self_col, const int* pos_col, float inv_T, float grad_scale, float* loss_sum, int* hits,
+                  cudaStream_t stream);
 int contrast_rows(float* S, float* logits, const int* self_col, const int* pos_col, int R, int C,
                   int ld_s, int ld_logits, float inv_T, float grad_scale, float* loss_sum, int* hits,
                   cudaStream_t stream);
@@ -378,6 +385,23 @@ int dv_contrast_rows(float* S, float* logits, const int32_t* self_col, const int
   DV_REQUIRE(S && pos_col && loss_sum && R > 0 && C > 1, "bad contrast_rows arguments");
   return contrast_rows(S, logits, self_col, pos_col, R, C, ld_s, ld_logits, inv_T, grad_scale, loss_sum,
                        hits, ST);
+}
+int dv_sim_ce_blocks(int C) { return sim_ce_blocks(C); }
+int dv_sim_ce_fwd(const float* a, int lda, const float* b, int ldb, int b_dmajor, int R, int C, int d, float* S,
+                  int ld_s, int col0, float* logits, int ld_logits, const int32_t* self_col, const int32_t* pos_col,
+                  float inv_T, float* partials, void* stream) {
+  DV_REQUIRE(a && b && S && pos_col && partials && R > 0 && C > 0 && d > 0 && col0 >= 0 && ld_s >= col0 + C,
+             "bad sim_ce_fwd arguments");
+  return sim_ce_fwd(a, lda, b, ldb, b_dmajor, R, C, d, S, ld_s, col0, logits, ld_logits, self_col, pos_col, inv_T,
+                    partials, ST);
+}
+int dv_sim_ce_finish(float* S, int ld_s, int R, int C, int col0, const float* partials, float* logits, int ld_logits,
+                     const int32_t* self_col, const int32_t* pos_col, float inv_T, float grad_scale, float* loss_sum,
+                     int32_t* hits, void* stream) {
+  DV_REQUIRE(S && pos_col && partials && loss_sum && R > 0 && C > 0 && col0 >= 0 && col0 + C > 1,
+             "bad sim_ce_finish arguments");
+  return sim_ce_finish(S, ld_s, R, C, col0, partials, logits, ld_logits, self_col, pos_col, inv_T, grad_scale,
+                       loss_sum, hits, ST);
 }
 int dv_rank_loss(const float* a, const float* b, float* da, float* db, float* logits, float* loss_sum,
                  int32_t* hits, int B, int s, int e, float theta, float clip_max, float weight,

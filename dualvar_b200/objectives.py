@@ -143,6 +143,11 @@ class PermuteSegmentsFn(torch.autograd.Function):
 _index_cache = {}
 
 
+def _sim_blocks(C):
+    """Column blocks of the fused similarity / log-sum-exp launch (dv_sim_ce_blocks: 128 columns each)."""
+    return (int(C) + 127) // 128
+
+
 def _row_indices(n, N, rank, local_only, device):
     key = (n, N, rank, local_only, str(device))
     hit = _index_cache.get(key)
@@ -184,13 +189,17 @@ class ContrastFn(torch.autograd.Function):
         rows, self_col, pos_col = _row_indices(n, N, rank, local_rows, dev)
         f_rows = f_all.index_select(0, rows) if local_rows else f_all
         R = f_rows.shape[0]
+        # similarity GEMM fused with the row-wise log-sum-exp (csrc/sim_ce.cu): S, the logits in reference order and
+        # the online-softmax partials in one launch; the finish launch turns S into dLoss/dS
         S = torch.empty((R, 2 * N), dtype=torch.float32, device=dev)
-        _sgemm(0, 1, R, 2 * N, d, 1.0, f_rows, d, f_all, d, 0.0, S, 2 * N)
         logits = torch.empty((R, 2 * N - 1), dtype=torch.float32, device=dev)
         loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
         hits = torch.zeros(2, dtype=torch.int32, device=dev)
-        call("dv_contrast_rows", ptr(S), ptr(logits), ptr(self_col), ptr(pos_col), R, 2 * N, 2 * N, 2 * N - 1,
-             _f(1.0 / temperature), _f(1.0 / R), ptr(loss_sum), ptr(hits), stream_ptr())
+        partials = torch.empty((R, _sim_blocks(2 * N), 2), dtype=torch.float32, device=dev)
+        call("dv_sim_ce_fwd", ptr(f_rows), d, ptr(f_all), d, 0, R, 2 * N, d, ptr(S), 2 * N, 0, ptr(logits), 2 * N - 1,
+             ptr(self_col), ptr(pos_col), _f(1.0 / temperature), ptr(partials), stream_ptr())
+        call("dv_sim_ce_finish", ptr(S), 2 * N, R, 2 * N, 0, ptr(partials), ptr(logits), 2 * N - 1, ptr(self_col),
+             ptr(pos_col), _f(1.0 / temperature), _f(1.0 / R), ptr(loss_sum), ptr(hits), stream_ptr())
         # S now holds dLoss/dS. Column-role gradient for every clip, row-role gradient for the rows.
         d_all = torch.empty((2 * N, d), dtype=torch.float32, device=dev)
         _sgemm(1, 0, 2 * N, d, R, 1.0, S, 2 * N, f_rows, d, 0.0, d_all, d)
@@ -246,14 +255,18 @@ class QueueContrastFn(torch.autograd.Function):
         B, d = q.shape
         K = queue.shape[1]
         dev = q.device
+        # column 0 = q.k (the positive), columns 1..K = q.queue: the queue GEMM fused with the row-wise log-sum-exp
+        # (csrc/sim_ce.cu) reads the (d, K) queue buffer as it is; the finish launch folds column 0 in
         S = torch.empty((B, K + 1), dtype=torch.float32, device=dev)
         call("dv_rowdot", ptr(q), ptr(k), ptr(S), B, d, K + 1, stream_ptr())
-        _sgemm(0, 0, B, K, d, 1.0, q, d, queue, K, 0.0, S[:, 1:], K + 1)
         logits = torch.empty((B, K + 1), dtype=torch.float32, device=dev)
         loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
         hits = torch.zeros(2, dtype=torch.int32, device=dev)
         pos = torch.zeros(B, dtype=torch.int32, device=dev)
-        call("dv_contrast_rows", ptr(S), ptr(logits), None, ptr(pos), B, K + 1, K + 1, K + 1,
+        partials = torch.empty((B, _sim_blocks(K), 2), dtype=torch.float32, device=dev)
+        call("dv_sim_ce_fwd", ptr(q), d, ptr(queue), K, 1, B, K, d, ptr(S), K + 1, 1, ptr(logits), K + 1, None, ptr(pos),
+             _f(1.0 / temperature), ptr(partials), stream_ptr())
+        call("dv_sim_ce_finish", ptr(S), K + 1, B, K, 1, ptr(partials), ptr(logits), K + 1, None, ptr(pos),
              _f(1.0 / temperature), _f(1.0 / B), ptr(loss_sum), ptr(hits), stream_ptr())
         dq = torch.empty_like(q)
         _sgemm(0, 1, B, d, K, 1.0, S[:, 1:], K + 1, queue, K, 0.0, dq, d)

@@ -171,6 +171,22 @@ int dv_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, float*
 int dv_contrast_rows(float* S, float* logits, const int32_t* self_col, const int32_t* pos_col, int R,
                      int C, int ld_s, int ld_logits, float inv_T, float grad_scale, float* loss_sum,
                      int32_t* hits, void* stream);
+/* The similarity GEMM FUSED with the row-wise log-sum-exp / cross-entropy (replaces torch.matmul(features, features.T)
+ * + masks + CrossEntropyLoss of model/simclr.py:198-221,299-329 and einsum('nc,ck->nk') + cat + CE of
+ * model/moco.py:426-438). dv_sim_ce_fwd: S[r][col0 + c] = a[r] . b[c] (b row-major [C][ldb], or d-major [d][ldb] =
+ * MoCo's queue buffer when b_dmajor = 1), the logits S/T in the reference's column order (positive first, self column
+ * dropped, rest ascending; self_col / pos_col are S-column indices, self_col may be NULL) and per (row, 128-column
+ * block) the online-softmax partial (max, sum exp) into partials [R][dv_sim_ce_blocks(C)][2].
+ * dv_sim_ce_finish: combines the partials with the col0 leading columns the caller filled itself (MoCo: q.k), adds
+ * sum_r CE to *loss_sum, counts top-1 / top-5 (utils/utils.py:75-92), writes the leading columns' logits and
+ * overwrites S [R][col0 + C] with dLoss/dS * grad_scale (0 in the self column). */
+int dv_sim_ce_blocks(int C);
+int dv_sim_ce_fwd(const float* a, int lda, const float* b, int ldb, int b_dmajor, int R, int C, int d, float* S,
+                  int ld_s, int col0, float* logits, int ld_logits, const int32_t* self_col, const int32_t* pos_col,
+                  float inv_T, float* partials, void* stream);
+int dv_sim_ce_finish(float* S, int ld_s, int R, int C, int col0, const float* partials, float* logits, int ld_logits,
+                     const int32_t* self_col, const int32_t* pos_col, float inv_T, float grad_scale, float* loss_sum,
+                     int32_t* hits, void* stream);
 /* Shuffle-rank loss + gradient (model/simclr.py:231-278; clip_max<=0: model/moco.py:440-480) */
 int dv_rank_loss(const float* a, const float* b, float* da, float* db, float* logits, float* loss_sum,
                  int32_t* hits, int B, int s, int e, float theta, float clip_max, float weight,

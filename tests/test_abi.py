@@ -135,3 +135,13 @@ def test_new_entry_points_validate_arguments_without_a_gpu():
     # ingest into planes: plane stride must cover one plane
     assert lib.dv_ingest_clips_planes(P, 0, P, 8, 2, None, 1, 1, 1, 1, 1, 3, 4, 8, 8, 0, 1, 0, None, None, 0, None) != 0 \
         and "plane_stride" in err()
+
+
+def test_sim_ce_block_count_matches_the_host_mirror():
+    """objectives._sim_blocks sizes the partials buffer of the fused similarity / log-sum-exp launch: it must equal the
+    library's own column-block count (host-only entry point: no GPU needed)."""
+    from dualvar_b200 import _lib
+    from dualvar_b200.objectives import _sim_blocks
+    lib = _lib.load()
+    for C in (1, 2, 127, 128, 129, 1024, 16384, 16385):
+        assert lib.dv_sim_ce_blocks(C) == _sim_blocks(C)
