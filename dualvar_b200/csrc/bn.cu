@@ -14,6 +14,8 @@
 // per-channel coefficients sit in registers; a CTA covers (channel groups) x (rows) so that a warp
 // reads contiguous memory.
 #include <cuda_bf16.h>
+#include <stdlib.h>
+#include <algorithm>
 
 #include "bn_math.cuh"
 #include "host_common.h"
@@ -104,21 +106,30 @@ struct ApplyArgs {
 
 // kRows independent rows per thread and iteration: all their 16-byte loads are issued before the first use, which
 // is what keeps enough bytes in flight per SM to reach the HBM rate (tests/diag/bn_bw.py).
-template <bool kY2, bool kRes, int kRows>
+//
+// kFlat (dense tensors: every row is exactly Cp channels wide): the tensor is ONE array of 16-byte vectors, thread t of
+// block b owns the vectors b*256 + t + j*stride with stride = gridDim.x*256 a multiple of the vectors per row (flat_grid),
+// so its channel group - hence its coefficients - never changes, every warp is full and every warp access is a 512-byte
+// aligned run. The (channel group) x (rows) blocks of the general form have partial warps and runs that straddle
+// 128-byte lines whenever Cp/8 is not a power of two (144, 88, 232 ... channels: 5.4 instead of 6.1 TB/s,
+// tests/diag/bn_bw.py).
+template <bool kY2, bool kRes, int kRows, bool kFlat>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const ApplyArgs a) {
   const int G = a.Cp >> 3;
-  for (int cg = threadIdx.x; cg < G; cg += blockDim.x) {
+  const long long first = kFlat ? (long long)blockIdx.x * 256 + threadIdx.x : (long long)blockIdx.x * blockDim.y + threadIdx.y;
+  const long long limit = kFlat ? a.rows * G : a.rows;
+  const long long stride = kFlat ? (long long)gridDim.x * 256 : (long long)gridDim.x * blockDim.y;
+  for (int cg = kFlat ? (int)(first % G) : (int)threadIdx.x; cg < G; cg += kFlat ? G : (int)blockDim.x) {
     const Vec8 s1 = loadf8(a.ss1 + cg * 8), b1 = loadf8(a.ss1 + a.Cp + cg * 8);
     Vec8 s2, b2;
     if (kY2) { s2 = loadf8(a.ss2 + cg * 8); b2 = loadf8(a.ss2 + a.Cp + cg * 8); }
-    const long long stride = (long long)gridDim.x * blockDim.y;
-    for (long long r0 = (long long)blockIdx.x * blockDim.y + threadIdx.y; r0 < a.rows; r0 += kRows * stride) {
+    for (long long r0 = first; r0 < limit; r0 += kRows * stride) {
       uint4 u1[kRows], u2[kRows], u3[kRows];
 #pragma unroll
       for (int k = 0; k < kRows; ++k) {
         const long long r = r0 + k * stride;
-        if (r < a.rows) {
-          const long long off = r * a.Cp + cg * 8;
+        if (r < limit) {
+          const long long off = kFlat ? r * 8 : r * a.Cp + cg * 8;
           u1[k] = ldcs16(a.y1 + off);
           if (kY2) u2[k] = ldcs16(a.y2 + off);
           if (kRes) u3[k] = ldcs16(a.res + off);
@@ -127,7 +138,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const ApplyArgs a) {
 #pragma unroll
       for (int k = 0; k < kRows; ++k) {
         const long long r = r0 + k * stride;
-        if (r < a.rows) {
+        if (r < limit) {
           Vec8 x = unpack8(u1[k]);
 #pragma unroll
           for (int i = 0; i < 8; ++i) x.v[i] = fmaf(x.v[i], s1.v[i], b1.v[i]);
@@ -145,7 +156,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const ApplyArgs a) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) x.v[i] = fmaxf(x.v[i], 0.f);
           }
-          stcs8(a.out + r * a.out_ld + a.out_coff + cg * 8, x);
+          stcs8(a.out + (kFlat ? r * 8 : r * a.out_ld + a.out_coff + cg * 8), x);
         }
       }
     }
@@ -170,6 +181,76 @@ struct BwdArgs {
 };
 
 // kMask: 0 = no ReLU, 1 = mask recomputed from (scale, shift, y), 2 = mask read from `out`
+template <bool kD2, int kMask, int kRows>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_flat_kernel(const BwdArgs a) {
+  // dense tensors, flat vector indexing (see bn_apply_kernel): a thread's channel group is fixed; its 16 partial sums go
+  // to shared memory and are added per channel in a FIXED order (the threads of a channel group are t0, t0 + G, ...),
+  // so a block's contribution is reproducible - only the order of the double atomics across blocks varies, as before
+  __shared__ float red[256][17];
+  const int G = a.Cp >> 3;
+  const long long first = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long limit = a.rows * G;
+  const long long stride = (long long)gridDim.x * 256;
+  const int cg = (int)(first % G);
+  float sg[8], sgy[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sg[i] = 0.f; sgy[i] = 0.f; }
+  Vec8 fs, fb;
+  if (kMask == 1) { fs = loadf8(a.ss + cg * 8); fb = loadf8(a.ss + a.Cp + cg * 8); }
+  for (long long v0 = first; v0 < limit; v0 += kRows * stride) {
+    uint4 ud[kRows], uy[kRows], ue[kRows], uo[kRows];
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+      const long long v = v0 + k * stride;
+      if (v < limit) {
+        ud[k] = ldcs16(a.dout + v * 8);
+        uy[k] = ldcs16(a.y + v * 8);
+        if (kD2) ue[k] = ldcs16(a.dout2 + v * 8);
+        if (kMask == 2) uo[k] = ldcs16(a.out + v * 8);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+      const long long v = v0 + k * stride;
+      if (v < limit) {
+        Vec8 d = unpack8(ud[k]);
+        const Vec8 yv = unpack8(uy[k]);
+        if (kD2) {
+          const Vec8 e = unpack8(ue[k]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d.v[i] += e.v[i];
+        }
+        if (kMask == 1) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d.v[i] = fmaf(yv.v[i], fs.v[i], fb.v[i]) > 0.f ? d.v[i] : 0.f;
+        } else if (kMask == 2) {
+          const Vec8 o = unpack8(uo[k]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d.v[i] = o.v[i] > 0.f ? d.v[i] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { sg[i] += d.v[i]; sgy[i] = fmaf(d.v[i], yv.v[i], sgy[i]); }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    red[threadIdx.x][i] = sg[i];
+    red[threadIdx.x][8 + i] = sgy[i];
+  }
+  __syncthreads();
+  const int shift = (int)(((long long)blockIdx.x * 256) % G);     // channel group of thread 0
+  for (int o = threadIdx.x; o < 2 * a.Cp; o += 256) {
+    const int which = o >= a.Cp ? 1 : 0;
+    const int c = o - which * a.Cp;
+    int t = (c >> 3) - shift;
+    if (t < 0) t += G;
+    float sum = 0.f;
+    for (; t < 256; t += G) sum += red[t][which * 8 + (c & 7)];
+    atomicAdd(&a.sums[o], (double)sum);
+  }
+}
+
 template <bool kD2, int kMask, int kRows>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BwdArgs a) {
   extern __shared__ float red[];  // [blockDim.y][2][8*blockDim.x]
@@ -257,22 +338,24 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums_local,
                           grad_beta);
 }
 
-template <bool kD2, int kMask, bool kGout, int kRows>
+template <bool kD2, int kMask, bool kGout, int kRows, bool kFlat>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdArgs a) {
   const int G = a.Cp >> 3;
-  for (int cg = threadIdx.x; cg < G; cg += blockDim.x) {
+  const long long first = kFlat ? (long long)blockIdx.x * 256 + threadIdx.x : (long long)blockIdx.x * blockDim.y + threadIdx.y;
+  const long long limit = kFlat ? a.rows * G : a.rows;
+  const long long stride = kFlat ? (long long)gridDim.x * 256 : (long long)gridDim.x * blockDim.y;
+  for (int cg = kFlat ? (int)(first % G) : (int)threadIdx.x; cg < G; cg += kFlat ? G : (int)blockDim.x) {
     const Vec8 A = loadf8(a.coef + cg * 8), B = loadf8(a.coef + a.Cp + cg * 8),
                C = loadf8(a.coef + 2 * a.Cp + cg * 8);
     Vec8 fs, fb;
     if (kMask == 1) { fs = loadf8(a.ss + cg * 8); fb = loadf8(a.ss + a.Cp + cg * 8); }
-    const long long stride = (long long)gridDim.x * blockDim.y;
-    for (long long r0 = (long long)blockIdx.x * blockDim.y + threadIdx.y; r0 < a.rows; r0 += kRows * stride) {
+    for (long long r0 = first; r0 < limit; r0 += kRows * stride) {
       uint4 ud[kRows], uy[kRows], ue[kRows], uo[kRows];
 #pragma unroll
       for (int k = 0; k < kRows; ++k) {
         const long long r = r0 + k * stride;
-        if (r < a.rows) {
-          const long long oo = r * a.o_ld + a.o_coff + cg * 8, yo = r * a.Cp + cg * 8;
+        if (r < limit) {
+          const long long oo = kFlat ? r * 8 : r * a.o_ld + a.o_coff + cg * 8, yo = kFlat ? r * 8 : r * a.Cp + cg * 8;
           ud[k] = ldcs16(a.dout + oo);
           uy[k] = ldcs16(a.y + yo);
           if (kD2) ue[k] = ldcs16(a.dout2 + yo);
@@ -282,8 +365,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdArgs a) {
 #pragma unroll
       for (int k = 0; k < kRows; ++k) {
         const long long r = r0 + k * stride;
-        if (r < a.rows) {
-          const long long off = r * a.Cp + cg * 8;
+        if (r < limit) {
+          const long long off = kFlat ? r * 8 : r * a.Cp + cg * 8;
           Vec8 d = unpack8(ud[k]);
           const Vec8 yv = unpack8(uy[k]);
           if (kD2) {
@@ -338,6 +421,30 @@ static void row_block(int Cp, long long rows, dim3* block, int* grid) {
   *grid = (int)want;
 }
 
+// Grid of the flat (dense) kernels: 256-thread blocks whose count is a multiple of G / gcd(G, 32), so that the stride
+// gridDim * 256 of a thread's vectors is a multiple of the G vectors of a row (fixed channel group per thread) and of
+// 32 (aligned warp runs). DV_BN_FLAT=0 keeps the (channel group) x (rows) blocks everywhere.
+static int g_bn_flat = -1;
+static bool flat_grid(int Cp, long long rows, int* grid) {
+  if (g_bn_flat < 0) {
+    const char* e = getenv("DV_BN_FLAT");
+    g_bn_flat = e ? atoi(e) : 1;
+  }
+  if (!g_bn_flat) return false;
+  const int G = Cp / 8;
+  int gq = G;
+  while (gq % 2 == 0 && G / gq < 32) gq /= 2;      // gq = G / gcd(G, 32)
+  const long long nvec = rows * G;
+  long long want = ceil_div_ll(nvec, 256 * 4);      // ~4 vectors per thread minimum
+  const long long cap = (long long)sm_count() * 8;
+  if (want > cap) want = cap;
+  want = want / gq * gq;
+  if (want < gq) want = gq;
+  if (want > 65535LL * 16) return false;
+  *grid = (int)want;
+  return true;
+}
+
 int bn_finalize(const double* stats, const float* gamma, const float* beta, float* running_mean,
                 float* running_var, float* ss, float* saved, int C, int Cp, double count, float eps,
                 float momentum, int training, cudaStream_t stream) {
@@ -358,11 +465,19 @@ int bn_apply(const void* y1, const float* ss1, const void* y2, const float* ss2,
   a.out = (__nv_bfloat16*)out;
   a.rows = rows; a.Cp = Cp; a.out_ld = out_ld; a.out_coff = out_coff; a.relu = relu;
   dim3 block; int grid;
+  if (out_ld == Cp && out_coff == 0 && flat_grid(Cp, rows, &grid)) {
+    if (a.y2 && a.res) bn_apply_kernel<true, true, 2, true><<<grid, 256, 0, stream>>>(a);
+    else if (a.y2) bn_apply_kernel<true, false, 2, true><<<grid, 256, 0, stream>>>(a);
+    else if (a.res) bn_apply_kernel<false, true, 4, true><<<grid, 256, 0, stream>>>(a);
+    else bn_apply_kernel<false, false, 8, true><<<grid, 256, 0, stream>>>(a);
+    DV_LAUNCH_OK();
+    return kOk;
+  }
   row_block(Cp, rows, &block, &grid);
-  if (a.y2 && a.res) bn_apply_kernel<true, true, 2><<<grid, block, 0, stream>>>(a);
-  else if (a.y2) bn_apply_kernel<true, false, 2><<<grid, block, 0, stream>>>(a);
-  else if (a.res) bn_apply_kernel<false, true, 4><<<grid, block, 0, stream>>>(a);
-  else bn_apply_kernel<false, false, 8><<<grid, block, 0, stream>>>(a);
+  if (a.y2 && a.res) bn_apply_kernel<true, true, 2, false><<<grid, block, 0, stream>>>(a);
+  else if (a.y2) bn_apply_kernel<true, false, 2, false><<<grid, block, 0, stream>>>(a);
+  else if (a.res) bn_apply_kernel<false, true, 4, false><<<grid, block, 0, stream>>>(a);
+  else bn_apply_kernel<false, false, 8, false><<<grid, block, 0, stream>>>(a);
   DV_LAUNCH_OK();
   return kOk;
 }
@@ -376,9 +491,20 @@ int bn_bwd_reduce(const void* dout, const void* dout2, const void* out, const vo
   a.y = (const __nv_bfloat16*)y; a.rows = rows; a.Cp = Cp; a.o_ld = o_ld; a.o_coff = o_coff;
   a.relu = relu; a.sums = sums;
   dim3 block; int grid;
+  const int mask = !relu ? 0 : (ss ? 1 : 2);
+  if (o_ld == Cp && o_coff == 0 && flat_grid(Cp, rows, &grid)) {
+#define DV_REDF(D2, M, R) bn_bwd_reduce_flat_kernel<D2, M, R><<<grid, 256, 0, stream>>>(a)
+    if (a.dout2) {
+      if (mask == 0) DV_REDF(true, 0, 2); else if (mask == 1) DV_REDF(true, 1, 2); else DV_REDF(true, 2, 2);
+    } else {
+      if (mask == 0) DV_REDF(false, 0, 4); else if (mask == 1) DV_REDF(false, 1, 4); else DV_REDF(false, 2, 2);
+    }
+#undef DV_REDF
+    DV_LAUNCH_OK();
+    return kOk;
+  }
   row_block(Cp, rows, &block, &grid);
   const size_t smem = (size_t)block.y * 16 * block.x * sizeof(float);
-  const int mask = !relu ? 0 : (ss ? 1 : 2);
 #define DV_RED(D2, M, R) bn_bwd_reduce_kernel<D2, M, R><<<grid, block, smem, stream>>>(a)
   if (a.dout2) {
     if (mask == 0) DV_RED(true, 0, 2); else if (mask == 1) DV_RED(true, 1, 2); else DV_RED(true, 2, 2);
@@ -409,9 +535,15 @@ int bn_bwd_apply(const void* dout, const void* dout2, const void* out, const voi
   a.y = (const __nv_bfloat16*)y; a.rows = rows; a.Cp = Cp; a.o_ld = o_ld; a.o_coff = o_coff;
   a.relu = relu; a.coef = coef; a.dy = (__nv_bfloat16*)dy; a.g_out = (__nv_bfloat16*)g_out;
   dim3 block; int grid;
-  row_block(Cp, rows, &block, &grid);
   const int mask = !relu ? 0 : (ss ? 1 : 2);
-#define DV_APP(D2, M, GO, R) bn_bwd_apply_kernel<D2, M, GO, R><<<grid, block, 0, stream>>>(a)
+  const bool flat = o_ld == Cp && o_coff == 0 && flat_grid(Cp, rows, &grid);
+  if (flat) block = dim3(256, 1);
+  else row_block(Cp, rows, &block, &grid);
+#define DV_APP(D2, M, GO, R)                                                            \
+  do {                                                                                  \
+    if (flat) bn_bwd_apply_kernel<D2, M, GO, R, true><<<grid, block, 0, stream>>>(a);   \
+    else bn_bwd_apply_kernel<D2, M, GO, R, false><<<grid, block, 0, stream>>>(a);       \
+  } while (0)
 #define DV_APP_M(D2, GO, R)                                                               \
   do {                                                                                    \
     if (mask == 0) DV_APP(D2, 0, GO, R); else if (mask == 1) DV_APP(D2, 1, GO, R); else DV_APP(D2, 2, GO, R); \

@@ -15,7 +15,7 @@ def timeit(fn, n=5):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
 
-for rows, Cp in [(9633792, 144), (9633792, 64), (3211264, 144), (1204224, 288)]:
+for rows, Cp in [(9633792, 144), (9633792, 128), (9633792, 160), (9633792, 64), (9633792, 88), (3211264, 144), (1204224, 288)]:
     y = torch.randn(rows, Cp, device=dev).bfloat16()
     dz = torch.randn(rows, Cp, device=dev).bfloat16()
     z = torch.empty_like(y); dy = torch.empty_like(y); gb = torch.empty_like(y)
