@@ -345,7 +345,10 @@ def other_configs_leg(dev):
             opt.zero_grad(set_to_none=False)
             loss.backward()
             opt.step()
-            return loss
+            # detached: a kept loss WITH autograd history keeps the parameters' AccumulateGrad nodes (bound to this
+            # stream) alive, and autograd then synchronises the graph-capture stream below with this one - which
+            # invalidates the capture
+            return loss.detach()
 
         def timed(fn, k):
             torch.cuda.synchronize()
@@ -384,7 +387,7 @@ def other_configs_leg(dev):
         out["configs[2] MoCo+DualVar r21d K=16384 m=0.999 16x112^2"] = time_step(m, frames, B)
         del m, frames
     except Exception as e:  # noqa: BLE001
-        out["configs[2]"] = {"error": f"{type(e).__name__}: {e}"}
+        out["configs[2]"] = {"error": f"{type(e).__name__}: {e}", "reserved_gb": torch.cuda.memory_reserved() / 1e9}
     torch.cuda.empty_cache()
     try:
         seed_all(0)
@@ -654,8 +657,8 @@ def run_ours(args):
             roof = {"bound": "tensor", "kernel": top, "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": ach / peaks["bf16_tflops"], "traffic": traffic, "traffic_detail": traffic_detail,
                     "peak_source": peaks["source"],
-                    "share_of_step": kern[top]["ms_per_step"] / ms_step_serial, "kernels": kern, "calls": calls,
-                    "conv_share_of_step": conv_ms / args.steps / ms_step_serial, "ms_step_serial": ms_step_serial,
+                    "share_of_step": kern[top]["ms_per_step"] / ms_step, "kernels": kern, "calls": calls,
+                    "conv_share_of_step": conv_ms / args.steps / ms_step, "ms_step_serial": ms_step_serial,
                     "layers": layers,
                     "per_layer_roofline": {
                         "what": "each layer against ITS OWN roofline = max(algorithmic FLOPs / bf16 peak, algorithmic "
@@ -667,7 +670,8 @@ def run_ours(args):
                     "note": "achieved = algorithmic conv FLOPs (2*positions*Cout*Cin*taps, logical channels) of all "
                             "launches of the kernel / their summed CUDA-event time, taken in a second pass of the same "
                             "steps with the weight-gradient side stream folded back (single stream: ms_step_serial), "
-                            "because concurrent kernels make per-launch event times overlap; traffic = avg DRAM bytes "
+                            "because concurrent kernels make per-launch event times overlap; share_of_step = that device "
+                            "time / ms_per_step of the headline (graph-replayed) step; traffic = avg DRAM bytes "
                             "per launch from ncu (profiles/), null if no capture"}
         line = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,

@@ -121,6 +121,7 @@ class Context:
         self.overrides = {}        # (id(concat Act), channel offset) -> dense gradient replacing the slice's
         self.side_used = False     # weight gradients are in flight on the side stream
         self.defer_running = None  # list: running-statistic updates of a concurrent pass, applied in order at the join
+        self.nbt_pending = []      # num_batches_tracked buffers of the BatchNorm layers this pass has updated
         self._arena = None         # zeroed fp64 scratch the per-layer statistic buffers are carved from
         self._arena_used = 0
         self.rpass = None          # parallel._Pass during backward: parameter gradients go into its flat buckets
@@ -533,9 +534,26 @@ def conv_stats(ctx, x, conv, bn):
 
 def _after_finalize(ctx, r, bn, momentum, upd, deferred):
     if upd:
-        bn.num_batches_tracked += 1
+        # one multi-tensor increment per pass (flush_batch_counters) instead of a torch kernel per BatchNorm layer
+        ctx.nbt_pending.append(bn.num_batches_tracked)
     elif deferred:
         ctx.defer_running.append((bn, r.saved, r.count, momentum))
+
+
+def flush_batch_counters(ctx):
+    """num_batches_tracked += 1 for every BatchNorm layer the pass updated (nn.BatchNorm3d.forward), as one
+    multi-tensor launch. A layer met twice in one pass is incremented twice."""
+    if ctx.nbt_pending:
+        uniq, counts = [], {}
+        for t in ctx.nbt_pending:
+            if id(t) not in counts:
+                uniq.append(t)
+            counts[id(t)] = counts.get(id(t), 0) + 1
+        torch._foreach_add_(uniq, 1)
+        for t in uniq:
+            if counts[id(t)] > 1:
+                t += counts[id(t)] - 1
+        ctx.nbt_pending = []
 
 
 def apply_deferred_running(items):
@@ -988,6 +1006,7 @@ class BackboneFunction(torch.autograd.Function):
         ectx = Context(training, record=record)
         x = make_input()
         feat = program(ectx, x)
+        flush_batch_counters(ectx)
         fctx.ectx, fctx.feat, fctx.pooled, fctx.params, fctx.reducer = ectx, feat, pooled, params, reducer
         fctx.set_materialize_grads(False)
         out = global_pool(ectx, feat) if pooled else to_ncdhw(feat)
@@ -1057,6 +1076,7 @@ class BackbonePairFunction(torch.autograd.Function):
         ectx_a = Context(training, record=record)
         xa = make_inputs[0]()
         feat_a = program(ectx_a, xa)
+        flush_batch_counters(ectx_a)
         out_a = global_pool(ectx_a, feat_a)
         ectx_b = Context(training, record=record)
         ectx_b.defer_running = []

@@ -124,8 +124,16 @@ class GraphedTrainStep:
             torch.cuda.synchronize()
             gc.collect()
             gc.disable()
-            with torch.cuda.graph(g, stream=self.stream):
+            # "relaxed": a cudaFree / cudaMalloc that torch's allocator or a destructor issues while this stream captures
+            # (memory of an earlier, released graph going back to the driver) is legal instead of invalidating the capture
+            with torch.cuda.graph(g, stream=self.stream, capture_error_mode="relaxed"):
                 out = self._step(set_to_none=False)
+        except Exception as e:
+            raise RuntimeError(
+                "CUDA-graph capture of the training step failed. A frequent cause: a tensor WITH autograd history from an "
+                "eager step issued on another stream is still referenced (a kept `loss`, a kept output dict) - the "
+                "parameters' AccumulateGrad nodes then belong to that stream and autograd synchronises the capturing stream "
+                "with it. Detach or drop such tensors before the first call of GraphedTrainStep.") from e
         finally:
             if gc_was_on:
                 gc.enable()
