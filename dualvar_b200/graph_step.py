@@ -29,6 +29,7 @@ needs its own warm-up protocol for capture). All eager warm-up steps and the cap
 that per-stream resources (the weight-gradient side stream, the BatchNorm exchange channel) exist before the capture.
 """
 import gc
+import os
 
 import numpy as np
 import torch
@@ -37,6 +38,9 @@ import torch.distributed as dist
 from . import models as PM
 from .engine import RawClips
 from .pretrain_loop import total_loss
+
+
+STEP_STREAM_PRIORITY = int(os.environ.get("DV_STEP_STREAM_PRIORITY", "-1"))
 
 
 class GraphedTrainStep:
@@ -92,7 +96,9 @@ class GraphedTrainStep:
             return self._eager_body(frames)
         cur = torch.cuda.current_stream()
         if self.stream is None:
-            self.stream = torch.cuda.Stream()
+            # high priority: the weight-gradient side stream (engine._side_stream, default priority) must never hold back
+            # a kernel of the critical path - conv / BatchNorm chain - when both have CTAs waiting for an SM
+            self.stream = torch.cuda.Stream(priority=STEP_STREAM_PRIORITY)
         self.stream.wait_stream(cur)
         with torch.cuda.stream(self.stream):
             out = self._eager_body(frames)
