@@ -9,6 +9,7 @@ One "step" = what pretrain.py:400-451 does for one batch: Normalize/transpose in
 Prints ONE JSON line (rank 0). See DESIGN.md "Measurement" for the definition of every field.
 """
 import argparse
+import glob
 import json
 import os
 import random
@@ -215,7 +216,9 @@ def _spawn_leg(impl, extra, marker, timeout):
         return {"error": f"leg {impl}: {type(e).__name__}: {e}"}
 
 
-NCU_TRAFFIC = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+# the newest per-layer ncu capture of the round (profiles/r02*_ncu_traffic.json, written by tests/diag/ncu_traffic.py)
+NCU_TRAFFIC = (sorted(glob.glob(os.path.join(ROOT, "profiles", "r0*_ncu_traffic.json"))) or
+               [os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")])[-1]
 
 
 def ncu_traffic():
