@@ -346,7 +346,11 @@ static int wgrad_launch(WgradParams& P, int ntaps, int cin_p, int cout_p, int ta
   if (P.stages < 2) return fail(kUnsupported, "wgrad: stage too large for shared memory");
   P.pos_tiles = g.tiles_w * g.tiles_h * g.tiles_t * g.tiles_n;
   const int items = groups * P.n_tiles;
-  int ksplit = (2 * sm_count()) / items;
+  // CTAs per SM over the kernel's life ("waves"): more, shorter CTAs let kernels of the high-priority main stream get an SM
+  // sooner when this kernel runs on the weight-gradient side stream, at the price of more fp32 reductions (DV_WGRAD_WAVES)
+  static int waves = -1;
+  if (waves < 0) { const char* e = getenv("DV_WGRAD_WAVES"); waves = e ? atoi(e) : 2; if (waves < 1) waves = 1; }
+  int ksplit = (waves * sm_count()) / items;
   if (ksplit < 1) ksplit = 1;
   if (ksplit > P.pos_tiles) ksplit = P.pos_tiles;
   P.tiles_per_split = ceil_div(P.pos_tiles, ksplit);

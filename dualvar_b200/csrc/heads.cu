@@ -76,6 +76,85 @@ sgemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, int 
   }
 }
 
+// The same product for the SMALL head / loss GEMMs (a few hundred rows and columns, K <= 512): 32 x 32 tiles so that the
+// output still spreads over ~100 CTAs, K tiles of 32 held in two shared-memory buffers with the next tile's global loads
+// issued BEFORE the current tile's arithmetic (register prefetch). The one-buffer kernel above waited a full global-load
+// latency per K tile - 36 us per launch, 0.8 ms per step for the 22 head launches - this one overlaps it.
+__global__ void __launch_bounds__(256)
+sgemm_small_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, int lda, int ta,
+                   const float* __restrict__ B, int ldb, int tb, float beta, float* __restrict__ C, int ldc,
+                   const float* __restrict__ bias, int relu) {
+  constexpr int BM = 32, BN = 32, BK = 32;
+  __shared__ float As[2][BK][BM + 1];
+  __shared__ float Bs[2][BK][BN + 1];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;          // 16 x 16 threads, each a 2 x 2 block of outputs
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  // element e = tid + 256 * i of a 32 x 32 tile: the index that is contiguous in memory varies fastest across threads
+  float ra[4], rb[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + 256 * i;
+      int m, k;
+      if (ta) { m = e & 31; k = e >> 5; } else { k = e & 31; m = e >> 5; }
+      const int gm = m0 + m, gka = k0 + k;
+      ra[i] = (gm < M && gka < K) ? (ta ? A[(long long)gka * lda + gm] : A[(long long)gm * lda + gka]) : 0.f;
+      int n;
+      if (tb) { k = e & 31; n = e >> 5; } else { n = e & 31; k = e >> 5; }
+      const int gn = n0 + n, gkb = k0 + k;
+      rb[i] = (gn < N && gkb < K) ? (tb ? B[(long long)gn * ldb + gkb] : B[(long long)gkb * ldb + gn]) : 0.f;
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + 256 * i;
+      int m, k;
+      if (ta) { m = e & 31; k = e >> 5; } else { k = e & 31; m = e >> 5; }
+      As[buf][k][m] = ra[i];
+      int n;
+      if (tb) { k = e & 31; n = e >> 5; } else { n = e & 31; k = e >> 5; }
+      Bs[buf][k][n] = rb[i];
+    }
+  };
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  const int nk = (K + BK - 1) / BK;
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) fetch((kt + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float a0 = As[buf][k][ty * 2], a1 = As[buf][k][ty * 2 + 1];
+      const float b0 = Bs[buf][k][tx * 2], b1 = Bs[buf][k][tx * 2 + 1];
+      acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
+      acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
+    }
+    if (kt + 1 < nk) {
+      stash(buf ^ 1);      // the other buffer: its last readers passed the barrier at the end of the previous iteration
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int gm = m0 + ty * 2 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int gn = n0 + tx * 2 + j;
+      if (gn >= N) continue;
+      float v = alpha * acc[i][j];
+      if (bias) v += bias[gn];
+      if (beta != 0.f) v = fmaf(beta, C[(long long)gm * ldc + gn], v);
+      if (relu) v = fmaxf(v, 0.f);
+      C[(long long)gm * ldc + gn] = v;
+    }
+  }
+}
+
 // out[n] = beta*out[n] + sum_m X[m][n]   (bias gradient)
 __global__ void colsum_kernel(const float* __restrict__ X, float* __restrict__ out, int M, int N, int ld,
                               float beta) {
@@ -131,8 +210,7 @@ int sgemm(int ta, int tb, int M, int N, int K, float alpha, const float* A, int 
   // small head / loss GEMMs: 32x32 tiles so that a 192x512 output still spreads over ~100 CTAs
   if ((long long)ceil_div(N, 64) * ceil_div(M, 64) < 2 * sm_count()) {
     dim3 grid(ceil_div(N, 32), ceil_div(M, 32));
-    sgemm_kernel<32, 32, 16, 2, 2><<<grid, 256, 0, stream>>>(M, N, K, alpha, A, lda, ta, B, ldb, tb, beta, C, ldc,
-                                                            bias, relu);
+    sgemm_small_kernel<<<grid, 256, 0, stream>>>(M, N, K, alpha, A, lda, ta, B, ldb, tb, beta, C, ldc, bias, relu);
   } else {
     dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
     sgemm_kernel<64, 64, 16, 4, 4><<<grid, 256, 0, stream>>>(M, N, K, alpha, A, lda, ta, B, ldb, tb, beta, C, ldc,

@@ -586,8 +586,14 @@ def _side_stream(device):
     return s
 
 
+_DIAG_SKIP_WGRAD = os.environ.get("DV_DIAG_SKIP_WGRAD", "0") != "0"   # timing experiments only: gradients are WRONG
+
+
 def _wgrad(r, dy, gw):
     g = r.geom
+    if _DIAG_SKIP_WGRAD:
+        gw.zero_()
+        return
     if r.stem:
         dwp = torch.empty((g.Cout_p, g.kt * 4, 64), dtype=torch.float32, device=dy.device)
         call("dv_conv3d_stem_wgrad_bf16", ptr(r.x.data), ptr(dy), ptr(dwp), ctypes.byref(g), stream_ptr())
