@@ -330,3 +330,88 @@ def test_self_gating_kernels_match_torch(N, S, C, ld, coff):
     _lib.call("dv_gate_bwd_apply", ptr(dout), ptr(w), ptr(dmean), ptr(dz), N, S, C, C, ld, coff, stream_ptr())
     want = (w[:, None, :] * dsl + dmean[:, None, :] / S)
     assert ((dz.float() - want).abs().max() / want.abs().max()).item() < 1e-2      # bf16 output
+
+
+@pytest.mark.parametrize("M,N,K", [(192, 512, 512), (37, 129, 70), (1, 1, 1), (256, 128, 33), (300, 600, 96), (64, 16385, 128)])
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_sgemm_ragged_sizes_and_transposes_match_torch(M, N, K, ta, tb):
+    """dv_sgemm through the C ABI (small double-buffered kernel below 2 x 148 tiles of 64 x 64, the 64 x 64 kernel above):
+    every transpose combination, ragged M / N / K, bias + ReLU epilogue and beta accumulation, against torch fp32."""
+    import ctypes
+    from dualvar_b200 import _lib
+    torch.backends.cuda.matmul.allow_tf32 = False
+    gen = torch.Generator(device=dev).manual_seed(M * 7 + N * 3 + K + ta * 2 + tb)
+    A = torch.randn((K, M) if ta else (M, K), device=dev, generator=gen)
+    B = torch.randn((N, K) if tb else (K, N), device=dev, generator=gen)
+    bias = torch.randn(N, device=dev, generator=gen)
+    C0 = torch.randn(M, N, device=dev, generator=gen)
+    C = C0.clone()
+    _lib.call("dv_sgemm", ta, tb, M, N, K, ctypes.c_float(0.5), _lib.ptr(A), A.shape[1], _lib.ptr(B), B.shape[1],
+              ctypes.c_float(0.25), _lib.ptr(C), N, _lib.ptr(bias), 1, _lib.stream_ptr())
+    want = F.relu(0.5 * ((A.t() if ta else A).double() @ (B.t() if tb else B).double()) + bias.double() + 0.25 * C0.double())
+    assert (C.double() - want).abs().max().item() <= 1e-5 * max(1.0, want.abs().max().item()) * max(1, K) ** 0.5
+
+
+@pytest.mark.parametrize("R,C,d,col0,dmajor", [(128, 128, 128, 0, 0), (8, 24, 64, 0, 0), (64, 16384, 128, 1, 1),
+                                               (37, 301, 40, 1, 1), (5, 130, 16, 2, 0)])
+def test_fused_similarity_logsumexp_matches_a_torch_evaluation(R, C, d, col0, dmajor):
+    """dv_sim_ce_fwd + dv_sim_ce_finish (similarity GEMM fused with the row-wise log-sum-exp / cross-entropy,
+    model/simclr.py:198-221, model/moco.py:426-438): S, logits in the reference's column order, loss, top-1 / top-5
+    counts and dLoss/dS against a float64 torch evaluation - NT-Xent layout (self column dropped, row-major columns),
+    MoCo layout (leading positive column, d-major queue) and ragged sizes."""
+    import ctypes
+    from dualvar_b200 import _lib
+    from dualvar_b200.objectives import _sim_blocks
+    gen = torch.Generator(device=dev).manual_seed(R + C + d)
+    a = F.normalize(torch.randn(R, d, device=dev, generator=gen), dim=1)
+    bmat = F.normalize(torch.randn(C, d, device=dev, generator=gen), dim=1)           # column features [C][d]
+    b_arg = bmat.t().contiguous() if dmajor else bmat
+    ldb = C if dmajor else d
+    Ct = col0 + C
+    inv_T = 1.0 / 0.07
+    S = torch.zeros(R, Ct, device=dev)
+    lead = torch.randn(R, col0, device=dev, generator=gen) if col0 else None
+    if col0:
+        S[:, :col0] = lead
+    use_self = col0 == 0
+    self_col = (torch.arange(R, device=dev) % Ct).to(torch.int32) if use_self else None
+    pos_col = ((torch.arange(R, device=dev) * 7 + 3) % Ct).to(torch.int32)
+    if use_self:
+        pos_col = torch.where(pos_col == self_col, (pos_col + 1) % Ct, pos_col).to(torch.int32)
+    n_out = Ct - (1 if use_self else 0)
+    logits = torch.full((R, n_out), float("nan"), device=dev)
+    partials = torch.empty(R, _sim_blocks(C), 2, device=dev)
+    loss_sum = torch.zeros(1, device=dev)
+    hits = torch.zeros(2, dtype=torch.int32, device=dev)
+    _lib.call("dv_sim_ce_fwd", _lib.ptr(a), d, _lib.ptr(b_arg), ldb, dmajor, R, C, d, _lib.ptr(S), Ct, col0, _lib.ptr(logits),
+              n_out, _lib.ptr(self_col), _lib.ptr(pos_col), ctypes.c_float(inv_T), _lib.ptr(partials), _lib.stream_ptr())
+    S_raw = S.clone()
+    _lib.call("dv_sim_ce_finish", _lib.ptr(S), Ct, R, C, col0, _lib.ptr(partials), _lib.ptr(logits), n_out,
+              _lib.ptr(self_col), _lib.ptr(pos_col), ctypes.c_float(inv_T), ctypes.c_float(1.0 / R), _lib.ptr(loss_sum),
+              _lib.ptr(hits), _lib.stream_ptr())
+    # reference evaluation in float64
+    full = torch.cat([lead.double(), a.double() @ bmat.double().t()], dim=1) if col0 else a.double() @ bmat.double().t()
+    torch.testing.assert_close(S_raw.double(), full, rtol=0, atol=2e-6)
+    z = S_raw.double() * inv_T                     # the kernel's own products: isolates the softmax part
+    loss, top1, top5 = 0.0, 0, 0
+    dS = torch.zeros_like(z)
+    for r in range(R):
+        keep = torch.ones(Ct, dtype=torch.bool, device=dev)
+        if use_self:
+            keep[int(self_col[r])] = False
+        p = int(pos_col[r])
+        zr = z[r][keep]
+        lse = torch.logsumexp(zr, 0)
+        loss += float(lse - z[r, p])
+        above = int(((z[r] > z[r, p]) & keep).sum())
+        top1 += above < 1
+        top5 += above < 5
+        sm = torch.zeros(Ct, dtype=torch.float64, device=dev)
+        sm[keep] = torch.softmax(zr, 0)
+        sm[p] -= 1.0
+        dS[r] = sm * inv_T / R
+        order = [p] + [c for c in range(Ct) if c != p and keep[c]]
+        torch.testing.assert_close(logits[r].double(), z[r][order], rtol=1e-6, atol=1e-5)
+    assert abs(float(loss_sum) - loss) <= 2e-5 * max(1.0, abs(loss))
+    assert hits.tolist() == [top1, top5]
+    torch.testing.assert_close(S.double(), dS, rtol=1e-4, atol=1e-7)
