@@ -22,7 +22,11 @@ LAYERS = [("spatial 64->144", (N, 16, 56, 56, 64, 144, (1, 3, 3), (1, 1, 1), (0,
           ("spatial s2 128->460", (N, 8, 28, 28, 128, 460, (1, 3, 3), (1, 2, 2), (0, 1, 1))),
           ("spatial 256->576", (N, 4, 14, 14, 256, 576, (1, 3, 3), (1, 1, 1), (0, 1, 1))),
           ("spatial 512->1152", (N, 2, 7, 7, 512, 1152, (1, 3, 3), (1, 1, 1), (0, 1, 1))),
-          ("stem", (N, 16, 112, 112, 3, 83, (1, 7, 7), (1, 2, 2), (0, 3, 3)))]
+          ("stem", (N, 16, 112, 112, 3, 83, (1, 7, 7), (1, 2, 2), (0, 3, 3))),
+          # probes (not layers of the network): the same spatial conv without a partial last K chunk / with fewer channels
+          ("probe spatial 64->128", (N, 16, 56, 56, 64, 128, (1, 3, 3), (1, 1, 1), (0, 1, 1))),
+          ("probe spatial 64->192", (N, 16, 56, 56, 64, 192, (1, 3, 3), (1, 1, 1), (0, 1, 1))),
+          ("probe temporal 128->64", (N, 16, 56, 56, 128, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0)))]
 if os.environ.get("ONLY"):
     LAYERS = [l for l in LAYERS if any(k in l[0] for k in os.environ["ONLY"].split(","))]
 
