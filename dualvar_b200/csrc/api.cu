@@ -12,6 +12,9 @@ int conv_fprop_bf16(const void* x, const void* w_packed, void* y, double* stats,
                     const ConvGeom& c, cudaStream_t stream, int y_f32 = 0, const float* xf_ss = nullptr, int xf_relu = 0);
 int conv_dgrad_bf16(const void* dy, const void* w_packed_t, void* dx, const ConvGeom& c,
                     cudaStream_t stream, const BnReduce* red, int dx_f32 = 0);
+int conv_dgrad_stack_ok(const ConvGeom& c);
+int conv_dgrad_stack_bf16(const void* dy, const void* w_stack, void* dx, const ConvGeom& c, cudaStream_t stream,
+                          const BnReduce* red);
 int conv_wgrad_bf16(const void* x, const void* dy, float* dw, const ConvGeom& c, cudaStream_t stream,
                     bool accumulate = false, const float* xf_ss = nullptr, int xf_relu = 0);
 int pack_weights(const float* w, void* wf, void* wt, int Cout, int Cin, int taps, int Cout_p,
@@ -258,6 +261,19 @@ int dv_conv3d_dgrad_bnred_bf16(const void* dy, const void* wt, void* dx, const d
   DV_REQUIRE(dy && wt && dx && y_prev && sums, "NULL tensor pointer");
   const BnReduce red = {y_prev, ss_prev, sums};
   return conv_dgrad_bf16(dy, wt, dx, to_geom<ConvGeom>(g), (cudaStream_t)stream, &red);
+}
+
+int dv_conv3d_dgrad_stack_ok(const dv_conv_geom* g) {
+  if (check_geom(g)) return 0;
+  return conv_dgrad_stack_ok(to_geom<ConvGeom>(g));
+}
+int dv_conv3d_dgrad_stack_bf16(const void* dy, const void* w_stack, void* dx, const dv_conv_geom* g, const void* y_prev,
+                               const float* ss_prev, double* sums, void* stream) {
+  if (int rc = check_geom(g)) return rc;
+  DV_REQUIRE(dy && w_stack && dx, "NULL tensor pointer");
+  DV_REQUIRE((y_prev == nullptr) == (sums == nullptr), "y_prev and sums go together");
+  const BnReduce red = {y_prev, ss_prev, sums};
+  return conv_dgrad_stack_bf16(dy, w_stack, dx, to_geom<ConvGeom>(g), (cudaStream_t)stream, sums ? &red : nullptr);
 }
 
 int dv_conv3d_wgrad_bf16(const void* x, const void* dy, float* dw_packed, const dv_conv_geom* g,

@@ -58,10 +58,15 @@ constexpr int kSmemBudget = 232448 - 20480;  // 227 KB minus static smem (stat p
 //      issuing threads reach 43. The last warp of the CTA therefore issues every second MMA of a tile into a SECOND
 //      accumulator (TMEM columns +128; a thread's own MMAs stay ordered, the two threads' MMAs never touch the same
 //      columns), both warps commit to the stage / accumulator barriers (count 2), the epilogue adds the two halves.
+// kStack ("kh taps stacked along N", 64-column 3x3 dgrads): the tile's M rows are an UNSHIFTED 16h x 8w input box and one
+//      MMA per (kw, K step) multiplies it with B = [W(kh=2); W(kh=1); W(kh=0)] (N = 192), so the box is read from shared
+//      memory once instead of once per kh tap and the MMA is tensor-bound instead of operand-fetch-bound. Accumulator
+//      chunk s belongs to the output row one h row (8 lanes) further up per s: the epilogue adds D0[r] + D1[r + 8] +
+//      D2[r + 16] (warp shuffles, a small shared-memory exchange at the warp boundaries) and stores 14h x 8w outputs.
 // kXf: consumer-side BatchNorm instance (bn_xform.cuh): A boxes land on a CTA-local barrier, warps 10-13 apply
 //      relu?(scale*y + shift) in place and signal the (leader's) transform barrier the MMA warp waits for; the fused
 //      BatchNorm-backward reduce of the epilogue is compiled out of this instance (forward only).
-template <bool kPair, bool kF32 = false, bool kXf = false, bool kSplit = false>
+template <bool kPair, bool kF32 = false, bool kXf = false, bool kSplit = false, bool kStack = false>
 __global__ void __launch_bounds__((kXf ? kNumThreads + kXfThreads : kNumThreads) + (kSplit ? kIssue2Threads : 0), 1)
 conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -169,7 +174,7 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
         const int hb = m_id % g.tiles_h; m_id /= g.tiles_h;
         const int tb = m_id % g.tiles_t; m_id /= g.tiles_t;
         const int nb = m_id;
-        const int w0 = wb << g.lw, h0 = hb << g.lh, t0 = tb << g.lt, n0 = nb << g.ln;
+        const int w0 = wb << g.lw, h0 = hb * g.step_h, t0 = tb << g.lt, n0 = nb << g.ln;
         int gb = 0;
         for (int grp = 0; grp < p.num_groups; ++grp) {
           const int len = p.group_len[grp];
@@ -383,7 +388,7 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
       const int hb = m_id % g.tiles_h; m_id /= g.tiles_h;
       const int tb = m_id % g.tiles_t; m_id /= g.tiles_t;
       const int nb = m_id;
-      const int w0 = wb << g.lw, h0 = hb << g.lh, t0 = tb << g.lt, n0 = nb << g.ln;
+      const int w0 = wb << g.lw, h0 = hb * g.step_h, t0 = tb << g.lt, n0 = nb << g.ln;
       int gb = 0;
       for (int grp = 0; grp < p.num_groups; ++grp) {
         const Tap lead = p.taps[gb];
@@ -427,9 +432,132 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
       const int hb = m_id % g.tiles_h; m_id /= g.tiles_h;
       const int tb = m_id % g.tiles_t; m_id /= g.tiles_t;
       const int nb = m_id;
-      const int w0 = wb << g.lw, h0 = hb << g.lh, t0 = tb << g.lt, n0 = nb << g.ln;
+      const int w0 = wb << g.lw, h0 = hb * g.step_h, t0 = tb << g.lt, n0 = nb << g.ln;
       const bool valid = (w0 + rw < g.ext_w) && (h0 + rh < g.ext_h) && (t0 + rt < g.ext_t) &&
                          (n0 + rn < g.ext_n);
+      if (kStack) {
+        // ---- kStack epilogue: out[r] = D0[r] + D1[r + 8] + D2[r + 16] for the 112 rows with rh < 14. Both epilogue groups
+        // work on every tile: group g takes the columns [32g, 32g + 32) (two pieces of 16), one shared staging buffer.
+        const int sacc = it & 1;
+        mbar_wait(&tmem_full_bar[sacc], (it >> 1) & 1);
+        tc_fence_after_sync();
+        const uint32_t ta = tmem_base + sacc * kMaxBlockN + (static_cast<uint32_t>(q * 32) << 16);
+        uint8_t* ob = o_smem;                                                                 // staging buffer (both groups)
+        float* xb = reinterpret_cast<float*>(o_smem + kOutBufBytes) + grp * (4 * 24 * 16);    // [4 warps][24 rows][16]
+        if (threadIdx.x == 64) tma_store_wait_read<0>();                                      // the previous tile's store has read `ob`
+        named_bar_sync(3, kEpiThreads);
+        const bool keep = rh < 14;
+        const bool up1 = lane >= 24 && q < 3, up2 = lane >= 16 && q < 3;
+#pragma unroll 1
+        for (int pi = 0; pi < 2; ++pi) {
+          const int pc = grp * 2 + pi;
+          uint32_t d0[16], d1[16], d2[16];
+          tmem_ld16(ta + pc * 16, d0);
+          tmem_ld16(ta + 64 + pc * 16, d1);
+          tmem_ld16(ta + 128 + pc * 16, d2);
+          tmem_ld_wait();
+          if (pi == 1) {
+            tc_fence_before_sync();
+            if (kPair) mbar_arrive_cluster(acc_free0 + (uint32_t)sacc * 8u); else mbar_arrive(&tmem_empty_bar[sacc]);
+          }
+          // rows the warp above needs from this one: D1 of lanes 0-7, D2 of lanes 0-15
+          if (lane < 8) {
+            float4* dst = reinterpret_cast<float4*>(xb + (q * 24 + lane) * 16);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              dst[j] = make_float4(__uint_as_float(d1[4 * j]), __uint_as_float(d1[4 * j + 1]), __uint_as_float(d1[4 * j + 2]),
+                                   __uint_as_float(d1[4 * j + 3]));
+          }
+          if (lane < 16) {
+            float4* dst = reinterpret_cast<float4*>(xb + (q * 24 + 8 + lane) * 16);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              dst[j] = make_float4(__uint_as_float(d2[4 * j]), __uint_as_float(d2[4 * j + 1]), __uint_as_float(d2[4 * j + 2]),
+                                   __uint_as_float(d2[4 * j + 3]));
+          }
+          named_bar_sync(1 + grp, 128);
+          float x1v[16], x2v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            x1v[j] = __shfl_down_sync(0xffffffffu, __uint_as_float(d1[j]), 8);
+            x2v[j] = __shfl_down_sync(0xffffffffu, __uint_as_float(d2[j]), 16);
+          }
+          if (up1) {
+            const float4* src = reinterpret_cast<const float4*>(xb + ((q + 1) * 24 + (lane - 24)) * 16);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 v4 = src[j];
+              x1v[4 * j] = v4.x; x1v[4 * j + 1] = v4.y; x1v[4 * j + 2] = v4.z; x1v[4 * j + 3] = v4.w;
+            }
+          }
+          if (up2) {
+            const float4* src = reinterpret_cast<const float4*>(xb + ((q + 1) * 24 + 8 + (lane - 16)) * 16);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 v4 = src[j];
+              x2v[4 * j] = v4.x; x2v[4 * j + 1] = v4.y; x2v[4 * j + 2] = v4.z; x2v[4 * j + 3] = v4.w;
+            }
+          }
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            const float s0 = __uint_as_float(d0[j]) + x1v[j] + x2v[j];
+            const float s1 = __uint_as_float(d0[j + 1]) + x1v[j + 1] + x2v[j + 1];
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(keep ? s0 : 0.f, keep ? s1 : 0.f);
+            pk[j >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          uint8_t* orow = ob + row * 128;
+          *reinterpret_cast<uint4*>(orow + (((2 * pc) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(orow + (((2 * pc + 1) ^ (row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          if (pi == 0) named_bar_sync(1 + grp, 128);      // the exchange buffer is re-used by the second piece
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(3, kEpiThreads);
+        if (threadIdx.x == 64) {
+          tma_store_5d(&p.out_map, ob, 0, w0, h0, t0, n0);
+          tma_store_commit();
+        }
+        if (red) {
+          // column sums of g = dx * relu_mask(y) and g * y over the staged tile (rows with rh >= 14 hold zeros): thread ->
+          // (channel pair, eighth of the rows)
+          const int word = et & 31;
+          const int r8 = grp * 4 + (et >> 5);
+          const int c = word * 2;
+          if (c < p.stats_ld) {
+            const __nv_bfloat16* ybase = reinterpret_cast<const __nv_bfloat16*>(p.red_y) + c + w0 * p.red_stride[0] +
+                                         h0 * p.red_stride[1] + t0 * p.red_stride[2] + n0 * p.red_stride[3];
+            uint32_t yv[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int r = r8 * 16 + i;
+              yv[i] = ldg_u32_pred(ybase + (r & 7) * p.red_stride[0] + (r >> 3) * p.red_stride[1], (r >> 3) < 14);
+            }
+            float sc0 = 0.f, sc1 = 0.f, sh0 = 1.f, sh1 = 1.f;   // no ReLU: mask always true
+            if (p.red_ss != nullptr) {
+              sc0 = p.red_ss[c]; sc1 = p.red_ss[c + 1];
+              sh0 = p.red_ss[p.stats_ld + c]; sh1 = p.red_ss[p.stats_ld + c + 1];
+            }
+            float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int r = r8 * 16 + i;
+              const uint32_t off = r * 128 + ((((word >> 2) ^ (r & 7))) << 4) + ((word & 3) << 2);
+              const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ob + off));
+              const float2 yy = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yv[i]));
+              const float g0 = fmaf(yy.x, sc0, sh0) > 0.f ? d.x : 0.f;
+              const float g1 = fmaf(yy.y, sc1, sh1) > 0.f ? d.y : 0.f;
+              a0 += g0; a1 += g1;
+              b0 = fmaf(g0, yy.x, b0); b1 = fmaf(g1, yy.y, b1);
+            }
+            float2* ps = reinterpret_cast<float2*>(&s_part[r8][0][c]);
+            float2* pq = reinterpret_cast<float2*>(&s_part[r8][1][c]);
+            float2 s2 = *ps, q2 = *pq;
+            s2.x += a0; s2.y += a1; q2.x += b0; q2.y += b1;
+            *ps = s2; *pq = q2;
+          }
+        }
+        continue;
+      }
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const long long ce = prof_on ? clock64() : 0;
@@ -873,6 +1001,7 @@ static int conv_multi_tap_region(ConvTileParams& P, MapEncoder enc, const void* 
   g.org_h = org_h;
   g.tiles_w = ceil_div(eW, 1 << g.lw);
   g.tiles_h = ceil_div(eH, 1 << g.lh);
+  g.step_h = 1 << g.lh;
   g.tiles_t = ceil_div(eT, 1 << g.lt);
   g.tiles_n = ceil_div(eN, 1 << g.ln);
 
@@ -1215,6 +1344,97 @@ static int encode_stem_map(CUtensorMap* m, const void* ctx, int /*view*/, const 
   uint64_t strides[5] = {2, 32, (uint64_t)W2p * 32, (uint64_t)s->H2 * W2p * 32,
                          (uint64_t)s->T * s->H2 * W2p * 32};
   return encode_tmap(m, s->x, 2, 5, dims, strides, box, true);
+}
+
+// Eligibility of the kh-stacked data gradient (see kStack): 3x3 spatial filter, stride 1, padding 1, 64 input channels,
+// H a multiple of 14 and W of 8, and enough tiles to fill the chip with CTA pairs.
+int conv_dgrad_stack_ok(const ConvGeom& c) {
+  const long long tiles = (long long)c.N * c.T * (c.H / 14) * (c.W / 8);
+  return c.kt == 1 && c.kh == 3 && c.kw == 3 && c.st == 1 && c.sh == 1 && c.sw == 1 && c.pt == 0 && c.ph == 1 && c.pw == 1 &&
+         c.Cin_p == 64 && c.H % 14 == 0 && c.W % 8 == 0 && c.To == c.T && c.Ho == c.H && c.Wo == c.W &&
+         tiles >= 2LL * sm_count() && ceil_div(c.Cout_p, 64) * 3 * 96 * 128 <= 112 * 1024;
+}
+
+// dX = dgrad(dY, W) with the kh taps stacked along N. w_stack: bf16 [192][3][Cout_p]: row s*64 + ci, tap kw holds
+// W[co][ci][kh = 2 - s][kw] (the engine permutes the transposed pack).
+int conv_dgrad_stack_bf16(const void* dy, const void* w_stack, void* dx, const ConvGeom& c, cudaStream_t stream,
+                          const BnReduce* red) {
+  if (!conv_dgrad_stack_ok(c)) return fail(kUnsupported, "stacked dgrad: geometry not eligible");
+  static thread_local ConvTileParams P;
+  P = ConvTileParams{};
+  TileGeom& g = P.g;
+  g.lw = 3; g.lh = 4; g.lt = 0; g.ln = 0;
+  g.step_h = 14;
+  g.tiles_w = c.W / 8; g.tiles_h = c.H / 14; g.tiles_t = c.T; g.tiles_n = c.N;
+  g.ext_w = c.W; g.ext_h = c.H; g.ext_t = c.T; g.ext_n = c.N;
+  g.org_h = 0;
+  for (int kw = 0; kw < 3; ++kw) {
+    Tap& tp = P.taps[kw];
+    tp.map = 0; tp.dt = 0; tp.dh = -1; tp.dw = (int8_t)(1 - kw); tp.widx = (int16_t)kw; tp.shift_rows = 0;
+    P.group_len[kw] = 1;
+  }
+  P.num_taps = 3; P.num_groups = 3; P.max_group = 1;
+  P.a_tx_bytes = 128 * 128;
+  P.a_stage_bytes = 128 * 128;
+  P.k_chunks = ceil_div(c.Cout_p, kChunkK);
+  P.k_steps_last = ceil_div(c.Cout_p - (P.k_chunks - 1) * kChunkK, 16);
+  P.n_tiles = 1; P.block_n = 192; P.last_n = 192;
+  const long long m_tiles = (long long)g.tiles_w * g.tiles_h * g.tiles_t * g.tiles_n;
+  P.total_tiles = (int)((m_tiles + 1) / 2);
+  const int b_tap_bytes = 96 * 128;
+  const int res_bytes = 3 * P.k_chunks * b_tap_bytes;
+  const int out_bytes = kOutBufBytes + 12 * 1024;         // one staging buffer + the two groups' exchange buffers
+  const int avail = kSmemBudget - 1024 - out_bytes;
+  P.b_resident = 1;
+  P.stages = (avail - res_bytes) / P.a_stage_bytes;
+  if (P.stages > kMaxStages) P.stages = kMaxStages;
+  if (P.stages < 3) return fail(kUnsupported, "stacked dgrad: not enough shared memory");
+  P.stats = nullptr; P.stats_ld = c.Cin_p; P.bias = nullptr; P.prof = g_prof;   // (g_prof: diagnostics build only)
+  P.out_f32 = nullptr; P.xf_ss = nullptr; P.split = 0;
+  const View5 dyv = make_ndhwc(dy, c.N, c.T, c.H, c.W, c.Cout_p);
+  const View5 dxv = make_ndhwc(dx, c.N, c.T, c.H, c.W, c.Cin_p);
+  for (int i = 0; i < 4; ++i) P.red_stride[i] = dxv.stride[i + 1];
+  if (red != nullptr) {
+    P.stats = red->sums;
+    P.red_y = red->y;
+    P.red_ss = red->ss;
+  }
+  {
+    const uint32_t abox[5] = {kChunkK, 8, 16, 1, 1};
+    int rc = encode_view(&P.a_map[0], dyv, abox);
+    if (rc) return rc;
+    for (int i = 1; i < kMaxAMaps; ++i) P.a_map[i] = P.a_map[0];
+    uint64_t dims[3] = {(uint64_t)c.Cout_p, 3, 192};
+    uint64_t strides[3] = {2, (uint64_t)c.Cout_p * 2, (uint64_t)c.Cout_p * 3 * 2};
+    uint32_t bbox[3] = {kChunkK, 1, 96};
+    rc = encode_tmap(&P.b_map, w_stack, 2, 3, dims, strides, bbox, true);
+    if (rc) return rc;
+    const uint32_t obox[5] = {kChunkK, 8, 14, 1, 1};
+    rc = encode_view(&P.out_map, dxv, obox);
+    if (rc) return rc;
+  }
+  const int smem_bytes = 1024 + res_bytes + P.stages * P.a_stage_bytes + out_bytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DV_CUDA_OK(cudaFuncSetAttribute(conv_tile_kernel<true, false, false, false, true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    attr_set = true;
+  }
+  int units = sm_count() / 2;
+  if (units > P.total_tiles) units = P.total_tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * units);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  DV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tile_kernel<true, false, false, false, true>, P));
+  DV_LAUNCH_OK();
+  return kOk;
 }
 
 int conv_stem_fprop_bf16(const void* x_s2d, const void* w_stem, void* y, double* stats, const float* bias,

@@ -33,6 +33,7 @@ struct TileGeom {
   int tiles_w, tiles_h, tiles_t, tiles_n;
   int ext_w, ext_h, ext_t, ext_n;
   int org_h;   // h offset of the output region in the full tensor (input box coordinates), 0 unless the map is split
+  int step_h;  // distance of consecutive tiles along h: 1 << lh, or the 14 output rows of a kStack tile (16-row box)
 };
 
 struct alignas(64) ConvTileParams {

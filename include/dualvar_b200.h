@@ -80,6 +80,15 @@ int dv_conv3d_dgrad_bf16(const void* dy, const void* wt, void* dx, const dv_conv
  * from dx in a separate pass (autograd of nn.BatchNorm3d + nn.ReLU, backbone/r21d.py:56-57,68). */
 int dv_conv3d_dgrad_bnred_bf16(const void* dy, const void* wt, void* dx, const dv_conv_geom* g,
                                const void* y_prev, const float* ss_prev, double* sums, void* stream);
+/* The data gradient of a 3x3 spatial convolution with 64 input channels (the gradient's output columns) with the kh
+ * taps STACKED along N: one tcgen05.mma per (kw, K step) over the unshifted 16h x 8w box of dy with N = 192, the epilogue
+ * adds the three row-shifted 64-column results (autograd of nn.Conv3d in backbone/r21d.py:54-57, same result as
+ * dv_conv3d_dgrad_bf16 up to the fp32 summation order). w_stack: bf16 [192][3][Cout_p], row s*64 + ci and tap kw hold
+ * W[co][ci][kh = 2 - s][kw] (a permutation of the transposed pack). y_prev / ss_prev / sums as for
+ * dv_conv3d_dgrad_bnred_bf16, or all NULL. dv_conv3d_dgrad_stack_ok: 1 if the geometry is eligible. */
+int dv_conv3d_dgrad_stack_ok(const dv_conv_geom* g);
+int dv_conv3d_dgrad_stack_bf16(const void* dy, const void* w_stack, void* dx, const dv_conv_geom* g, const void* y_prev,
+                               const float* ss_prev, double* sums, void* stream);
 /* dw_packed (fp32 [Cout_p][taps][Cin_p]) = correlation(x, dy); buffer is overwritten */
 int dv_conv3d_wgrad_bf16(const void* x, const void* dy, float* dw_packed, const dv_conv_geom* g,
                          void* stream);

@@ -222,3 +222,58 @@ def test_consumer_side_batchnorm_is_bit_identical_to_the_two_pass_path(case, rel
     _lib.call("dv_conv3d_wgrad_bnrelu_bf16", ptr(y_prev), ptr(ss), 1 if relu else 0, ptr(dy), ptr(dw_b), ctypes.byref(g),
               stream_ptr())
     assert ((dw_a - dw_b).abs().max() / dw_a.abs().max()).item() < 2e-5
+
+
+@pytest.mark.parametrize("geom", [(4, 8, 28, 56, 64, 144), (3, 4, 56, 56, 64, 40), (3, 16, 42, 24, 57, 128)])
+def test_kh_stacked_dgrad_matches_the_tap_by_tap_dgrad(geom):
+    """dv_conv3d_dgrad_stack_bf16 (kh taps stacked along N, one MMA per kw and K step on the unshifted box, row-shifted sum in
+    the epilogue) against dv_conv3d_dgrad_bf16: same products in another fp32 summation order - equal up to one bf16
+    last place on a few elements; its fused BatchNorm-backward sums against the fused tap-by-tap launch."""
+    import ctypes
+    import kernel_handles as K
+    from dualvar_b200 import _lib
+    n, t, h, w, ci, co = geom
+    dev = "cuda:0"
+    g = K.make_geom(n, t, h, w, ci, co, (1, 3, 3), (1, 1, 1), (0, 1, 1))
+    assert _lib.load().dv_conv3d_dgrad_stack_ok(ctypes.byref(g)) == 1
+    gen = torch.Generator(device=dev).manual_seed(n + h + co)
+    wt_f = torch.randn(co, ci, 1, 3, 3, device=dev, generator=gen) / (ci * 9) ** 0.5
+    _, wt = K.pack_conv_weight(wt_f, g)
+    ws = wt.view(g.Cin_p, 3, 3, g.Cout_p).flip(1).permute(1, 0, 2, 3).reshape(3 * g.Cin_p, 3, g.Cout_p).contiguous()
+    dy = torch.randn(n, t, h, w, g.Cout_p, device=dev, generator=gen).bfloat16()
+    dy[..., co:] = 0
+    ref = K.conv3d_dgrad(dy, wt, g)
+    dx = torch.full_like(ref, float("nan"))
+    _lib.call("dv_conv3d_dgrad_stack_bf16", _lib.ptr(dy), _lib.ptr(ws), _lib.ptr(dx), ctypes.byref(g), None, None, None,
+              _lib.stream_ptr())
+    diff = (dx.float() - ref.float()).abs()
+    assert not torch.isnan(dx.float()).any()
+    assert diff.max().item() <= 2.0 ** -7 * ref.float().abs().max().item()
+    assert (diff > 0).float().mean().item() < 5e-3
+    if g.Cin_p > ci:
+        assert bool((dx[..., ci:] == 0).all())
+    y_prev = torch.randn(n, t, h, w, g.Cin_p, device=dev, generator=gen).bfloat16()
+    y_prev[..., ci:] = 0
+    ss = torch.randn(2 * g.Cin_p, device=dev, generator=gen)
+    s_ref = torch.zeros(2 * g.Cin_p, dtype=torch.float64, device=dev)
+    s_new = torch.zeros_like(s_ref)
+    dx1, dx2 = torch.empty_like(ref), torch.empty_like(ref)
+    _lib.call("dv_conv3d_dgrad_bnred_bf16", _lib.ptr(dy), _lib.ptr(wt), _lib.ptr(dx1), ctypes.byref(g), _lib.ptr(y_prev),
+              _lib.ptr(ss), _lib.ptr(s_ref), _lib.stream_ptr())
+    _lib.call("dv_conv3d_dgrad_stack_bf16", _lib.ptr(dy), _lib.ptr(ws), _lib.ptr(dx2), ctypes.byref(g), _lib.ptr(y_prev),
+              _lib.ptr(ss), _lib.ptr(s_new), _lib.stream_ptr())
+    assert torch.equal(dx2, dx)
+    assert (s_new - s_ref).abs().max().item() <= 2e-3 * (s_ref.abs().max().item() + 1.0)
+
+
+def test_kh_stacked_dgrad_refuses_other_geometries():
+    import ctypes
+    import kernel_handles as K
+    from dualvar_b200 import _lib
+    for geom, k, s, p in [((4, 8, 28, 56, 128, 144), (1, 3, 3), (1, 1, 1), (0, 1, 1)),      # 128 gradient columns
+                          ((4, 8, 28, 56, 64, 144), (3, 1, 1), (1, 1, 1), (1, 0, 0)),       # temporal filter
+                          ((4, 8, 56, 56, 64, 144), (1, 3, 3), (1, 2, 2), (0, 1, 1)),       # strided
+                          ((4, 8, 30, 56, 64, 144), (1, 3, 3), (1, 1, 1), (0, 1, 1)),       # H not a multiple of 14
+                          ((1, 1, 28, 56, 64, 144), (1, 3, 3), (1, 1, 1), (0, 1, 1))]:      # too few tiles
+        g = K.make_geom(*geom, k, s, p)
+        assert _lib.load().dv_conv3d_dgrad_stack_ok(ctypes.byref(g)) == 0
