@@ -107,7 +107,14 @@ def load():
             "root). dualvar_b200 has no CPU/eager fallback.")
     lib = ctypes.CDLL(_LIB_PATH)
     for name, (res, args) in _SIGNATURES.items():
-        fn = getattr(lib, name)
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            # an OLDER build loaded through DV_LIB_PATH for an A/B run may lack entry points this header declares;
+            # the product library itself must export every one of them (tests/test_abi.py)
+            if os.environ.get("DV_LIB_PATH"):
+                continue
+            raise
         fn.restype = res
         fn.argtypes = args
     _lib = lib
