@@ -110,6 +110,30 @@ class RawBN:
     __slots__ = ("y", "ss", "saved", "geom", "x", "conv", "bn", "packed", "count", "sync", "stem")
 
 
+# Direct parameter gradients (graph_step.GraphedTrainStep, single process): inside ``direct_param_grads(params)`` the
+# weight-gradient unpack and the BatchNorm-backward finalisation ADD their results straight into the parameters' existing
+# (zeroed) ``.grad`` tensors and the backbone pass returns None for them - autograd then neither sums the two passes of a
+# step (one add kernel per parameter) nor adds that sum into ``.grad`` (another one): ~160 tiny kernels per R(2+1)D step,
+# ~600 per S3D-G step. Outside the context gradients go back through autograd as usual (DDP hooks, fit()'s eager loop).
+_direct_ids = None
+
+
+class direct_param_grads:
+    def __init__(self, params):
+        self.ids = {id(p) for p in params if p.requires_grad and p.grad is not None and p.grad.is_contiguous()}
+
+    def __enter__(self):
+        global _direct_ids
+        self.prev = _direct_ids
+        _direct_ids = self.ids
+        return self
+
+    def __exit__(self, *exc):
+        global _direct_ids
+        _direct_ids = self.prev
+        return False
+
+
 class Context:
     """Per-forward state: tape of backward closures, parameter-gradient sink, mode flags."""
 
@@ -125,6 +149,13 @@ class Context:
         self._arena = None         # zeroed fp64 scratch the per-layer statistic buffers are carved from
         self._arena_used = 0
         self.rpass = None          # parallel._Pass during backward: parameter gradients go into its flat buckets
+        self.direct = set()        # ids of parameters whose gradient was added straight into .grad (direct_param_grads)
+
+    def direct_target(self, p):
+        """p.grad if this backward may add p's gradient into it in place (direct_param_grads), else None."""
+        if _direct_ids is None or self.rpass is not None or id(p) not in _direct_ids or id(p) in self.param_grads:
+            return None
+        return p.grad
 
     def zeros64(self, n, device):
         """A zero-initialised float64 vector of n elements: one memset per ~64 K elements instead of one tiny
@@ -589,7 +620,7 @@ def _side_stream(device):
 _DIAG_SKIP_WGRAD = os.environ.get("DV_DIAG_SKIP_WGRAD", "0") != "0"   # timing experiments only: gradients are WRONG
 
 
-def _wgrad(r, dy, gw):
+def _wgrad(r, dy, gw, beta=0.0):
     g = r.geom
     if _DIAG_SKIP_WGRAD:
         gw.zero_()
@@ -597,7 +628,7 @@ def _wgrad(r, dy, gw):
     if r.stem:
         dwp = torch.empty((g.Cout_p, g.kt * 4, 64), dtype=torch.float32, device=dy.device)
         call("dv_conv3d_stem_wgrad_bf16", ptr(r.x.data), ptr(dy), ptr(dwp), ctypes.byref(g), stream_ptr())
-        call("dv_unpack_stem_wgrad", ptr(dwp), ptr(gw), ctypes.byref(g), ctypes.c_float(0.0), stream_ptr())
+        call("dv_unpack_stem_wgrad", ptr(dwp), ptr(gw), ctypes.byref(g), ctypes.c_float(beta), stream_ptr())
     else:
         dwp = torch.empty((g.Cout_p, g.taps, g.Cin_p), dtype=torch.float32, device=dy.device)
         if r.x.lazy is not None:      # the operand z is recomputed from the raw y of the conv below (never stored)
@@ -606,7 +637,7 @@ def _wgrad(r, dy, gw):
                  ctypes.byref(g), stream_ptr())
         else:
             call("dv_conv3d_wgrad_bf16", ptr(r.x.data), ptr(dy), ptr(dwp), ctypes.byref(g), stream_ptr())
-        call("dv_unpack_conv_wgrad", ptr(dwp), ptr(gw), ctypes.byref(g), ctypes.c_float(0.0), stream_ptr())
+        call("dv_unpack_conv_wgrad", ptr(dwp), ptr(gw), ctypes.byref(g), ctypes.c_float(beta), stream_ptr())
 
 
 def _conv_backward_f32(ctx, r, dyp):
@@ -641,13 +672,19 @@ def _conv_backward(ctx, r, dy):
     """wgrad into the parameter-gradient sink, dgrad into r.x.grad."""
     g = r.geom
     first = id(r.conv.weight) not in ctx.param_grads
-    gw = ctx.grad_out(r.conv.weight) if first else torch.empty_like(r.conv.weight)
+    direct = ctx.direct_target(r.conv.weight)
+    beta = 0.0
+    if direct is not None:      # added straight into .grad (zeroed by zero_grad; the other pass of the step adds too)
+        gw, beta, first = direct, 1.0, False
+        ctx.direct.add(id(r.conv.weight))
+    else:
+        gw = ctx.grad_out(r.conv.weight) if first else torch.empty_like(r.conv.weight)
     if WGRAD_SIDE_STREAM:
         main = torch.cuda.current_stream()
         side = _side_stream(dy.device)
         side.wait_stream(main)                 # dy (and, on the first use, x) are ready
         with torch.cuda.stream(side):
-            _wgrad(r, dy, gw)
+            _wgrad(r, dy, gw, beta)
         # the caching allocator must not hand these blocks to later main-stream work while the side stream reads them
         dy.record_stream(side)
         r.x.stored.record_stream(side)
@@ -655,8 +692,9 @@ def _conv_backward(ctx, r, dy):
         ctx.side_used = True
     else:
         side = None
-        _wgrad(r, dy, gw)
-    ctx.add_param_grad(r.conv.weight, gw)
+        _wgrad(r, dy, gw, beta)
+    if direct is None:
+        ctx.add_param_grad(r.conv.weight, gw)
     if first:
         ctx.grad_ready(r.conv.weight, side)
     if r.conv.bias is not None:
@@ -682,13 +720,21 @@ def _bn_bwd_finalize(ctx, r, sums, Cp, dev):
     dy = A*g + B*y + C; cross-replica BatchNorm exchanges the sums first (fused over NVLink peer memory)."""
     bn = r.bn
     first = id(bn.weight) not in ctx.param_grads
-    dgamma = ctx.grad_out(bn.weight) if first else torch.empty_like(bn.weight)
-    dbeta = ctx.grad_out(bn.bias) if first else torch.empty_like(bn.bias)
+    dw_direct, db_direct = ctx.direct_target(bn.weight), ctx.direct_target(bn.bias)
+    direct = dw_direct is not None and db_direct is not None
+    grad_beta = 0.0
+    if direct:                  # dgamma / dbeta are added straight into .grad (see direct_param_grads)
+        dgamma, dbeta, grad_beta, first = dw_direct, db_direct, 1.0, False
+        ctx.direct.add(id(bn.weight))
+        ctx.direct.add(id(bn.bias))
+    else:
+        dgamma = ctx.grad_out(bn.weight) if first else torch.empty_like(bn.weight)
+        dbeta = ctx.grad_out(bn.bias) if first else torch.empty_like(bn.bias)
     coef = torch.empty(3 * Cp, dtype=torch.float32, device=dev)
     peer = comm.peer_state(dev, 2 * Cp) if r.sync else None
     if peer is not None:  # exchange of the sums + finalisation in one launch over NVLink peer memory
         call("dv_bn_bwd_finalize_sync", ptr(sums), ptr(bn.weight.detach()), ptr(r.saved), ptr(dgamma),
-             ptr(dbeta), ptr(coef), r.geom.Cout, Cp, ctypes.c_double(r.count), ctypes.c_float(0.0),
+             ptr(dbeta), ptr(coef), r.geom.Cout, Cp, ctypes.c_double(r.count), ctypes.c_float(grad_beta),
              *peer.next_call(), stream_ptr())
     else:
         sums_g = sums
@@ -697,9 +743,10 @@ def _bn_bwd_finalize(ctx, r, sums, Cp, dev):
             comm.small_allreduce_(sums_g)
         call("dv_bn_bwd_finalize", ptr(sums), ptr(sums_g), ptr(bn.weight.detach()), ptr(r.saved),
              ptr(dgamma), ptr(dbeta), ptr(coef), r.geom.Cout, Cp, ctypes.c_double(r.count),
-             ctypes.c_float(0.0), stream_ptr())
-    ctx.add_param_grad(bn.weight, dgamma)
-    ctx.add_param_grad(bn.bias, dbeta)
+             ctypes.c_float(grad_beta), stream_ptr())
+    if not direct:
+        ctx.add_param_grad(bn.weight, dgamma)
+        ctx.add_param_grad(bn.bias, dbeta)
     if first:
         ctx.grad_ready(bn.weight)
         ctx.grad_ready(bn.bias)
@@ -1045,6 +1092,7 @@ class BackboneFunction(torch.autograd.Function):
             ectx.rpass = None
         grads = tuple(ectx.param_grads.get(id(p)) if p.requires_grad else None for p in fctx.params)
         ectx.param_grads = {}
+        ectx.direct = set()
         fctx.feat = None
         return (None, None, None, None, None, None) + grads
 

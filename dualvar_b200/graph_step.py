@@ -36,7 +36,7 @@ import torch
 import torch.distributed as dist
 
 from . import models as PM
-from .engine import RawClips
+from .engine import RawClips, direct_param_grads
 from .pretrain_loop import total_loss
 
 
@@ -59,6 +59,7 @@ class GraphedTrainStep:
         distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self.enabled = bool(getattr(target, "graph_safe", False)) and \
             not (distributed and isinstance(model, torch.nn.parallel.DistributedDataParallel))
+        self.direct = not distributed and os.environ.get("DV_DIRECT_GRADS", "1") != "0"
         self.n_series = getattr(target, "n_series", 0) or 0
         self.replays = self.eager_steps = self.captures = 0
         self.launches_per_step = 0          # kernel launches recorded into the graph (C-ABI launch counter during capture)
@@ -78,11 +79,20 @@ class GraphedTrainStep:
     def _lr_signature(self):
         return tuple((g["lr"], g.get("momentum", 0.0), g.get("weight_decay", 0.0)) for g in self.opt.param_groups)
 
+    def _backward(self, loss):
+        """loss.backward() with the backbone's parameter gradients added straight into the (zeroed) .grad tensors
+        (engine.direct_param_grads: no per-parameter accumulation kernels of autograd); single process only."""
+        if self.direct:
+            with direct_param_grads(self.model.parameters()):
+                loss.backward()
+        else:
+            loss.backward()
+
     def _step(self, set_to_none):
         ret = self.model(self.wrap(self.frames))
         loss = self.loss_fn(ret)
         self.opt.zero_grad(set_to_none=set_to_none)
-        loss.backward()
+        self._backward(loss)
         self.opt.step()
         out = dict(ret)
         out["loss"] = loss.detach()
@@ -109,7 +119,7 @@ class GraphedTrainStep:
         ret = self.model(self.wrap(frames))
         loss = self.loss_fn(ret)
         self.opt.zero_grad(set_to_none=False)
-        loss.backward()
+        self._backward(loss)
         self.opt.step()
         out = dict(ret)
         out["loss"] = loss.detach()

@@ -47,6 +47,20 @@ class SGD(torch.optim.Optimizer):
             self._tables[key] = hit
         return hit[1]
 
+    def zero_grad(self, set_to_none=True):
+        """As torch.optim.Optimizer.zero_grad; the in-place form zeroes all gradients with multi-tensor launches instead
+        of one fill kernel per parameter (one param group per tensor, pretrain.py:262-264, defeats torch's grouping)."""
+        if set_to_none:
+            return super().zero_grad(set_to_none=True)
+        grads = [p.grad for group in self.param_groups for p in group["params"] if p.grad is not None]
+        for g in grads:
+            if g.grad_fn is not None:
+                g.detach_()
+            else:
+                g.requires_grad_(False)
+        if grads:
+            torch._foreach_zero_(grads)
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
