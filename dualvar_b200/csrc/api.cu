@@ -12,6 +12,12 @@ int conv_fprop_bf16(const void* x, const void* w_packed, void* y, double* stats,
                     const ConvGeom& c, cudaStream_t stream, int y_f32 = 0, const float* xf_ss = nullptr, int xf_relu = 0);
 int conv_dgrad_bf16(const void* dy, const void* w_packed_t, void* dx, const ConvGeom& c,
                     cudaStream_t stream, const BnReduce* red, int dx_f32 = 0);
+int conv_fprop_f32planes(const void* x_planes, long long plane_stride, int K, const void* wf_all, float* y,
+                         double* stats, const float* bias, const ConvGeom& c, cudaStream_t stream);
+int conv_dgrad_f32planes(const void* dy_planes, long long plane_stride, int K, const void* wt_all, float* dx,
+                         const ConvGeom& c, cudaStream_t stream);
+int conv_wgrad_f32planes(const void* x_planes, const void* dy_planes, int K, float* dw, const ConvGeom& c,
+                         cudaStream_t stream);
 int conv_dgrad_stack_ok(const ConvGeom& c);
 int conv_dgrad_stack_bf16(const void* dy, const void* w_stack, void* dx, const ConvGeom& c, cudaStream_t stream,
                           const BnReduce* red);
@@ -501,6 +507,24 @@ int dv_conv3d_dgrad_f32acc(const void* dy_plane, const void* wt_plane, float* dx
   if (int rc = check_geom(g)) return rc;
   DV_REQUIRE(dy_plane && wt_plane && dx, "NULL tensor pointer");
   return conv_dgrad_bf16(dy_plane, wt_plane, dx, to_geom<ConvGeom>(g), ST, nullptr, accumulate ? 1 : 2);
+}
+int dv_conv3d_fprop_f32planes(const void* x_planes, int64_t plane_stride, int n_planes, const void* wf_all, float* y,
+                              double* stats, const float* bias_padded, const dv_conv_geom* g, void* stream) {
+  if (int rc = check_geom(g)) return rc;
+  DV_REQUIRE(x_planes && wf_all && y && plane_stride > 0, "bad fprop_f32planes arguments");
+  return conv_fprop_f32planes(x_planes, plane_stride, n_planes, wf_all, y, stats, bias_padded, to_geom<ConvGeom>(g), ST);
+}
+int dv_conv3d_wgrad_f32planes(const void* x_planes, const void* dy_planes, int n_planes, float* dw_packed,
+                              const dv_conv_geom* g, void* stream) {
+  if (int rc = check_geom(g)) return rc;
+  DV_REQUIRE(x_planes && dy_planes && dw_packed, "NULL tensor pointer");
+  return conv_wgrad_f32planes(x_planes, dy_planes, n_planes, dw_packed, to_geom<ConvGeom>(g), ST);
+}
+int dv_conv3d_dgrad_f32planes(const void* dy_planes, int64_t plane_stride, int n_planes, const void* wt_all, float* dx,
+                              const dv_conv_geom* g, void* stream) {
+  if (int rc = check_geom(g)) return rc;
+  DV_REQUIRE(dy_planes && wt_all && dx && plane_stride > 0, "bad dgrad_f32planes arguments");
+  return conv_dgrad_f32planes(dy_planes, plane_stride, n_planes, wt_all, dx, to_geom<ConvGeom>(g), ST);
 }
 int dv_conv3d_wgrad_bf16_acc(const void* x_plane, const void* dy_plane, float* dw_packed, const dv_conv_geom* g,
                              void* stream) {

@@ -675,6 +675,44 @@ conv_tile_kernel(const __grid_constant__ ConvTileParams p) {
                                  __uint_as_float(v[j + 3]));
             }
           }
+          if (do_stats) {
+            // merged plane products: the accumulator is the finished sum, so the batch statistics are taken here.
+            // Transposing butterfly over the warp's 32 rows: every round halves the values a lane carries and
+            // doubles the rows they cover; after 5 rounds lane l holds the sums of columns 2l and 2l + 1.
+            const int lane = et & 31;
+            float cs[32], cq[32];
+            {
+              const bool up = (lane & 16) != 0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float lo = (i < ncols) ? __uint_as_float(v[i]) : 0.f;
+                const float hi = (i + 32 < ncols) ? __uint_as_float(v[i + 32]) : 0.f;
+                const float keep = up ? hi : lo;
+                const float got = __shfl_xor_sync(0xffffffffu, up ? lo : hi, 16);
+                cs[i] = keep + got;
+                cq[i] = fmaf(keep, keep, got * got);
+              }
+            }
+#pragma unroll
+            for (int m = 8; m >= 1; m >>= 1) {
+              const bool up = (lane & m) != 0;
+#pragma unroll
+              for (int i = 0; i < 2 * m; ++i) {
+                const float ks = up ? cs[i + 2 * m] : cs[i], ss = up ? cs[i] : cs[i + 2 * m];
+                const float kq = up ? cq[i + 2 * m] : cq[i], sq = up ? cq[i] : cq[i + 2 * m];
+                cs[i] = ks + __shfl_xor_sync(0xffffffffu, ss, m);
+                cq[i] = kq + __shfl_xor_sync(0xffffffffu, sq, m);
+              }
+            }
+            if (lane * 2 < ncols) {      // each (epilogue warp, channel) partial has one owner: no atomics
+              const int c = cc * 64 + lane * 2;
+              float2* ps = reinterpret_cast<float2*>(&s_part[grp * 4 + (et >> 5)][0][c]);
+              float2* pq = reinterpret_cast<float2*>(&s_part[grp * 4 + (et >> 5)][1][c]);
+              float2 s2 = *ps, q2 = *pq;
+              s2.x += cs[0]; s2.y += cs[1]; q2.x += cq[0]; q2.y += cq[1];
+              *ps = s2; *pq = q2;
+            }
+          }
           continue;
         }
         uint8_t* orow = ob + row * 128;
@@ -893,6 +931,11 @@ struct TapSpec {
 
 using MapEncoder = int (*)(CUtensorMap*, const void* ctx, int view, const uint32_t box[5]);
 
+// fp32 mode, all plane products of a convolution in ONE launch (conv_fprop_f32planes / conv_dgrad_f32planes): the input
+// "views" are the bf16 split planes of one tensor (same geometry), not stride-parity classes - tap grouping stays legal.
+static thread_local bool t_plane_views = false;
+static thread_local int t_plane_taps = 0;      // filter taps per weight plane (tap index / t_plane_taps = weight plane)
+
 static long long* g_prof = nullptr;
 #ifdef DV_DIAG
 void set_conv_profile(long long* p) { g_prof = p; }
@@ -940,7 +983,7 @@ static int conv_multi_tap_region(ConvTileParams& P, MapEncoder enc, const void* 
   }
   const int span_t = max_t - min_t + 1, span_h = max_h - min_h + 1, span_w = max_w - min_w + 1;
   enum { kPlain, kTemporal, kRows } mode = kPlain;
-  if (g_halo_enabled && allow_group && n_views == 1 && taps_in.size() > 1) {
+  if (g_halo_enabled && allow_group && (n_views == 1 || t_plane_views) && taps_in.size() > 1) {
     if (span_h == 1 && span_w == 1 && span_t > 1) {
       mode = kTemporal;
     } else if (span_h > 1 && rows_forced) {
@@ -1018,12 +1061,21 @@ static int conv_multi_tap_region(ConvTileParams& P, MapEncoder enc, const void* 
   } else {
     // groups: all taps with the same ow (temporal mode has a single ow); leader origin = (min_t, min_h, ow)
     const int bh = (int)abox[2], bw = (int)abox[1];
+    // plane products: one group per (operand plane, weight plane, ow) - the kh / kt taps of ONE product share a box, so a
+    // stage holds one box and one product's weight tiles (all weight planes of an operand plane in one group would not
+    // leave room for three stages)
+    const int n_wplanes = (t_plane_views && t_plane_taps > 0) ? ceil_div(w_taps, t_plane_taps) : 1;
+    // (operand plane, weight plane) pairs with the smallest contributions (largest plane indices) first
+    for (int rank = n_views + n_wplanes - 2; rank >= 0; --rank)
+    for (int view = 0; view < n_views; ++view)
+    for (int wp = 0; wp < n_wplanes; ++wp)
     for (int ow = min_w; ow <= max_w; ++ow) {
+      if (view + wp != rank) continue;
       int len = 0;
       for (const TapSpec& t : taps_in) {
-        if (t.ow != ow) continue;
+        if (t.ow != ow || t.view != view || (n_wplanes > 1 && t.widx / t_plane_taps != wp)) continue;
         Tap& tp = P.taps[ntaps++];
-        tp.map = 0; tp.dt = (int8_t)min_t; tp.dh = (int8_t)min_h; tp.dw = (int8_t)ow;
+        tp.map = (int8_t)view; tp.dt = (int8_t)min_t; tp.dh = (int8_t)min_h; tp.dw = (int8_t)ow;
         tp.widx = (int16_t)t.widx;
         tp.shift_rows = (int16_t)(((t.ot - min_t) * bh + (t.oh - min_h)) * bw);
         ++len;
@@ -1100,8 +1152,8 @@ static int conv_multi_tap_region(ConvTileParams& P, MapEncoder enc, const void* 
   for (int i = 0; i < 4; ++i) P.red_stride[i] = outv.stride[i + 1];
   P.out_f32 = outv.esize == 4 ? static_cast<float*>(const_cast<void*>(outv.base)) : nullptr;
   P.f32_store = outv.store;
-  if (P.out_f32 != nullptr && (stats != nullptr || red != nullptr))
-    return fail(kBadArg, "fp32 accumulate output has no fused statistics");
+  if (P.out_f32 != nullptr && (red != nullptr || (stats != nullptr && !outv.store)))
+    return fail(kBadArg, "fp32 output: fused statistics only for a launch that stores the finished sum");
   if (xf && (P.out_f32 != nullptr || red != nullptr))
     return fail(kBadArg, "consumer-side BatchNorm is a forward, bf16-output launch");
   if (red != nullptr) {
@@ -1196,7 +1248,7 @@ static int conv_multi_tap(ConvTileParams& P, MapEncoder enc, const void* enc_ctx
   const int eH = (int)outv.dim[2], eW = (int)outv.dim[1];
   bool spatial = false;
   for (const TapSpec& t : taps_in) spatial = spatial || t.oh != taps_in[0].oh;
-  if (g_halo_enabled && g_split_enabled && allow_group && n_views == 1 && spatial && eH % 16 == 8 && eH >= 24 &&
+  if (g_halo_enabled && g_split_enabled && allow_group && (n_views == 1 || t_plane_views) && spatial && eH % 16 == 8 && eH >= 24 &&
       (double)round_up(eW, 8) / eW <= 1.16 && (double)round_up(eW, 16) / eW <= 1.16) {
     const int h_main = eH - 8;
     View5 va = outv, vb = outv;
@@ -1344,6 +1396,107 @@ static int encode_stem_map(CUtensorMap* m, const void* ctx, int /*view*/, const 
   uint64_t strides[5] = {2, 32, (uint64_t)W2p * 32, (uint64_t)s->H2 * W2p * 32,
                          (uint64_t)s->T * s->H2 * W2p * 32};
   return encode_tmap(m, s->x, 2, 5, dims, strides, box, true);
+}
+
+// fp32 mode: y (fp32) = sum over the plane products (i, j), i + j < K, of conv(x_i, w_j) in ONE launch - the products are
+// extra taps of one accumulator (smallest contributions first), the epilogue stores the fp32 rows once instead of one
+// store + five read-modify-write passes (dv_conv3d_fprop_f32acc per product). x_planes: bf16 [K][N][T][H][W][Cin_p];
+// wf_all: bf16 [Cout_p][K * taps][Cin_p] (plane j in tap slots [j * taps, (j + 1) * taps)). Stride 1 only.
+int conv_fprop_f32planes(const void* x_planes, long long plane_stride, int K, const void* wf_all, float* y,
+                         double* stats, const float* bias, const ConvGeom& c, cudaStream_t stream) {
+  if (c.st != 1 || c.sh != 1 || c.sw != 1) return fail(kUnsupported, "merged plane products: stride-1 convolutions only");
+  if (K < 1 || K > 3) return fail(kBadArg, "1..3 split planes");
+  static thread_local ConvTileParams P;
+  P.xf_ss = nullptr;
+  const int taps_total = c.kt * c.kh * c.kw;
+  ViewSet vs;
+  for (int i = 0; i < K; ++i) {
+    vs.v[i] = make_ndhwc(static_cast<const uint8_t*>(x_planes) + (long long)i * plane_stride * 2, c.N, c.T, c.H, c.W, c.Cin_p);
+    for (int d = 0; d < 4; ++d) P.a_dims[i][d] = (int)vs.v[i].dim[1 + d];
+  }
+  View5 outv = make_ndhwc(y, c.N, c.To, c.Ho, c.Wo, c.Cout_p);
+  outv.esize = 4; outv.store = 1;
+  std::vector<TapSpec> taps;
+  for (int s = 2 * (K - 1); s >= 0; --s)            // i + j = s: smallest contributions first
+    for (int i = 0; i < K; ++i) {
+      const int j = s - i;
+      if (j < 0 || j >= K - i) continue;            // products with i + j < K only
+      for (int a = 0; a < c.kt; ++a)
+        for (int b = 0; b < c.kh; ++b)
+          for (int d = 0; d < c.kw; ++d) {
+            const int ot = a - c.pt, oh = b - c.ph, ow = d - c.pw;
+            taps.push_back({i, ot, oh, ow, j * taps_total + (a * c.kh + b) * c.kw + d});
+          }
+    }
+  t_plane_views = true;
+  t_plane_taps = taps_total;
+  const int rc = conv_multi_tap(P, encode_from_viewset, &vs, K, taps, outv, c.Cout_p, wf_all, c.Cout_p, K * taps_total,
+                                c.Cin_p, stats, bias, stream);
+  t_plane_views = false;
+  return rc;
+}
+
+// fp32 mode: dx (fp32) = sum over the plane products of dgrad(dy_i, w_j) in one launch per stride-parity class.
+// dy_planes: bf16 [K][N][To][Ho][Wo][Cout_p]; wt_all: bf16 [Cin_p][K * taps][Cout_p].
+int conv_dgrad_f32planes(const void* dy_planes, long long plane_stride, int K, const void* wt_all, float* dx,
+                         const ConvGeom& c, cudaStream_t stream) {
+  if (K < 1 || K > 3) return fail(kBadArg, "1..3 split planes");
+  static thread_local ConvTileParams P;
+  P.xf_ss = nullptr;
+  const int taps_total = c.kt * c.kh * c.kw;
+  ViewSet vs;
+  for (int i = 0; i < K; ++i)
+    vs.v[i] = make_ndhwc(static_cast<const uint8_t*>(dy_planes) + (long long)i * plane_stride * 2, c.N, c.To, c.Ho, c.Wo,
+                         c.Cout_p);
+  View5 dxv = make_ndhwc(dx, c.N, c.T, c.H, c.W, c.Cin_p);
+  dxv.esize = 4; dxv.store = 1;
+  bool need_zero = false;
+  for (int rt = 0; rt < c.st; ++rt)
+    for (int rh = 0; rh < c.sh; ++rh)
+      for (int rw = 0; rw < c.sw; ++rw) {
+        int cnt = 0;
+        for (int a = 0; a < c.kt; ++a) if (posmod(rt + c.pt - a, c.st) == 0)
+          for (int b = 0; b < c.kh; ++b) if (posmod(rh + c.ph - b, c.sh) == 0)
+            for (int d = 0; d < c.kw; ++d) if (posmod(rw + c.pw - d, c.sw) == 0) ++cnt;
+        if (cnt == 0) need_zero = true;
+      }
+  if (need_zero) DV_CUDA_OK(cudaMemsetAsync(dx, 0, (size_t)c.N * c.T * c.H * c.W * c.Cin_p * 4, stream));
+  for (int rt = 0; rt < c.st; ++rt)
+    for (int rh = 0; rh < c.sh; ++rh)
+      for (int rw = 0; rw < c.sw; ++rw) {
+        if (rt >= c.T || rh >= c.H || rw >= c.W) continue;
+        View5 ov = dxv;
+        subsample(ov, 3, rt, c.st);
+        subsample(ov, 2, rh, c.sh);
+        subsample(ov, 1, rw, c.sw);
+        std::vector<TapSpec> taps;
+        for (int s = 2 * (K - 1); s >= 0; --s)
+          for (int i = 0; i < K; ++i) {
+            const int j = s - i;
+            if (j < 0 || j >= K - i) continue;
+            for (int a = 0; a < c.kt; ++a) {
+              if (posmod(rt + c.pt - a, c.st) != 0) continue;
+              for (int b = 0; b < c.kh; ++b) {
+                if (posmod(rh + c.ph - b, c.sh) != 0) continue;
+                for (int d = 0; d < c.kw; ++d) {
+                  if (posmod(rw + c.pw - d, c.sw) != 0) continue;
+                  taps.push_back({i, (rt + c.pt - a) / c.st, (rh + c.ph - b) / c.sh, (rw + c.pw - d) / c.sw,
+                                  j * taps_total + (a * c.kh + b) * c.kw + d});
+                }
+              }
+            }
+          }
+        if (taps.empty()) continue;
+        for (int i = 0; i < K; ++i)
+          for (int d = 0; d < 4; ++d) P.a_dims[i][d] = (int)vs.v[i].dim[1 + d];
+        t_plane_views = true;
+        t_plane_taps = taps_total;
+        const int rc = conv_multi_tap(P, encode_from_viewset, &vs, K, taps, ov, c.Cin_p, wt_all, c.Cin_p, K * taps_total,
+                                      c.Cout_p, nullptr, nullptr, stream);
+        t_plane_views = false;
+        if (rc) return rc;
+      }
+  return kOk;
 }
 
 // Eligibility of the kh-stacked data gradient (see kStack): 3x3 spatial filter, stride 1, padding 1, 64 input channels,

@@ -59,6 +59,11 @@ struct alignas(64) WgradParams {
   int xf_relu;
   int xb_h, xb_t;          // halo mode: box extents along h and t
   int a_dims[kMaxAMaps][4];   // W, H, T, N extents of every X tensor map (row validity = the convolution's zero padding)
+  // fp32 mode, all plane products in one launch: X and dY are stacks of bf16 split planes along N ([K*N][T][H][W][C]);
+  // every position tile is contracted once per product (x plane i, dy plane j) into the SAME accumulators, so the
+  // fp32 reduction into dw happens once instead of once per product. n_prod = 1: the plain weight gradient.
+  int n_prod;
+  int prod_nx[6], prod_ny[6];   // batch offset (plane * N) of the product's X / dY plane
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -121,37 +126,42 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
     uint32_t phase = 0;
     const uint32_t tx = p.halo ? (uint32_t)(nbox * p.x_box_bytes + nbx * kBoxBytes)
                                : (uint32_t)((nu + nbx) * kBoxBytes);
-    for (int tile = tile_begin; tile < tile_end; ++tile) {
-      int m_id = tile;
-      const int wb = m_id % g.tiles_w; m_id /= g.tiles_w;
-      const int hb = m_id % g.tiles_h; m_id /= g.tiles_h;
-      const int tb = m_id % g.tiles_t; m_id /= g.tiles_t;
-      const int nb = m_id;
-      const int w0 = wb << g.lw, h0 = hb << g.lh, t0 = tb << g.lt, n0 = nb << g.ln;
-      mbar_wait(&empty_bar[stage], phase ^ 1);
-      if (issuer) {
-        mbar_expect_tx(&full_bar[stage], tx);
-        uint8_t* a_s = smem + stage * stage_bytes;
-        uint8_t* b_s = a_s + a_bytes;
-        for (int j = 0; j < nbx; ++j)
-          tma_load_5d(b_s + j * kBoxBytes, &p.dy_map, &full_bar[stage], n_tile * p.block_n + j * 64, w0, h0, t0, n0);
-        if (p.halo) {
-          for (int b = 0; b < nbox; ++b)
-            tma_load_5d(a_s + b * p.x_box_bytes, &p.a_map[0], &full_bar[stage], p.box_kc[box0 + b] * 64,
-                        w0 + p.box_dw[box0 + b], h0 + p.box_dh[box0 + b], t0 + p.box_dt[box0 + b], n0);
-        } else {
-          for (int i = 0; i < nu; ++i) {
-            const int u = unit0 + i;
-            const int tap = u / p.k_chunks;
-            const int kc = u - tap * p.k_chunks;
-            const Tap tp = p.taps[tap];
-            tma_load_5d(a_s + i * kBoxBytes, &p.a_map[tp.map], &full_bar[stage], kc * 64, w0 + tp.dw, h0 + tp.dh,
-                        t0 + tp.dt, n0);
+    // plane products outermost, smallest contributions first: the tensor core aligns every addend to the running
+    // sum and truncates, so the 2^-16-scale products must meet a small accumulator (measured: interleaved 1e-4, this 1e-7)
+    for (int pi = 0; pi < p.n_prod; ++pi) {
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        int m_id = tile;
+        const int wb = m_id % g.tiles_w; m_id /= g.tiles_w;
+        const int hb = m_id % g.tiles_h; m_id /= g.tiles_h;
+        const int tb = m_id % g.tiles_t; m_id /= g.tiles_t;
+        const int nb = m_id;
+        const int w0 = wb << g.lw, h0 = hb << g.lh, t0 = tb << g.lt, n0 = nb << g.ln;
+        const int nx = n0 + p.prod_nx[pi], ny = n0 + p.prod_ny[pi];
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (issuer) {
+          mbar_expect_tx(&full_bar[stage], tx);
+          uint8_t* a_s = smem + stage * stage_bytes;
+          uint8_t* b_s = a_s + a_bytes;
+          for (int j = 0; j < nbx; ++j)
+            tma_load_5d(b_s + j * kBoxBytes, &p.dy_map, &full_bar[stage], n_tile * p.block_n + j * 64, w0, h0, t0, ny);
+          if (p.halo) {
+            for (int b = 0; b < nbox; ++b)
+              tma_load_5d(a_s + b * p.x_box_bytes, &p.a_map[0], &full_bar[stage], p.box_kc[box0 + b] * 64,
+                          w0 + p.box_dw[box0 + b], h0 + p.box_dh[box0 + b], t0 + p.box_dt[box0 + b], nx);
+          } else {
+            for (int i = 0; i < nu; ++i) {
+              const int u = unit0 + i;
+              const int tap = u / p.k_chunks;
+              const int kc = u - tap * p.k_chunks;
+              const Tap tp = p.taps[tap];
+              tma_load_5d(a_s + i * kBoxBytes, &p.a_map[tp.map], &full_bar[stage], kc * 64, w0 + tp.dw, h0 + tp.dh,
+                          t0 + tp.dt, nx);
+            }
           }
         }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      __syncwarp();
-      if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
     // MMA issuer: uniform loop state (descriptor words in uniform registers), one elected lane issues
@@ -165,7 +175,8 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
     int stage = 0;
     uint32_t phase = 0;
     uint32_t accumulate = 0;
-    for (int tile = tile_begin; tile < tile_end; ++tile) {
+    const int n_steps = (tile_end - tile_begin) * p.n_prod;     // one pipeline stage per (position tile, plane product)
+    for (int step = 0; step < n_steps; ++step) {
       mbar_wait(xf ? &xf_bar[stage] : &full_bar[stage], phase);
       tc_fence_after_sync();
       const uint32_t a_lo = lo_flags | (base_enc + (uint32_t)stage * stage_enc);
@@ -371,10 +382,29 @@ static int wgrad_launch(WgradParams& P, int ntaps, int cin_p, int cout_p, int ta
   return kOk;
 }
 
+// fp32 mode (conv_wgrad_f32planes): number of split planes stacked along N in both operands, 1 = plain tensors
+static thread_local int t_wg_planes = 1;
+
+static void set_products(WgradParams& P, int K, int N) {
+  P.n_prod = 0;
+  for (int s = 2 * (K - 1); s >= 0; --s)        // products with i + j < K, smallest contributions first
+    for (int i = 0; i < K; ++i) {
+      const int j = s - i;
+      if (j < 0 || j >= K - i) continue;
+      P.prod_nx[P.n_prod] = i * N;
+      P.prod_ny[P.n_prod] = j * N;
+      ++P.n_prod;
+    }
+}
+
 int conv_wgrad_bf16(const void* x, const void* dy, float* dw, const ConvGeom& c,
                     cudaStream_t stream, bool accumulate, const float* xf_ss, int xf_relu) {
   static thread_local WgradParams P;
   const int taps_total = c.kt * c.kh * c.kw;
+  const int K = t_wg_planes;
+  const long long NK = (long long)K * c.N;       // batch extent of the tensor maps (stacked planes)
+  if (K > 1 && xf_ss != nullptr) return fail(kBadArg, "merged plane products have no operand transform");
+  set_products(P, K, c.N);
   P.xf_ss = xf_ss;
   P.xf_relu = xf_relu;
   for (int i = 0; i < kMaxAMaps; ++i) { P.a_dims[i][0] = c.W; P.a_dims[i][1] = c.H; P.a_dims[i][2] = c.T; P.a_dims[i][3] = c.N; }
@@ -452,12 +482,12 @@ int conv_wgrad_bf16(const void* x, const void* dy, float* dw, const ConvGeom& c,
         const uint32_t ybox[5] = {64, 1u << g.lw, 1u << g.lh, 1u << g.lt, 1};
         const uint32_t xbox[5] = {64, 1u << g.lw, (uint32_t)((1 << g.lh) + (spatial ? c.kh - 1 : 0)),
                                   (uint32_t)((1 << g.lt) + (temporal ? c.kt - 1 : 0)), 1};
-        uint64_t ydims[5] = {(uint64_t)c.Cout_p, (uint64_t)c.Wo, (uint64_t)c.Ho, (uint64_t)c.To, (uint64_t)c.N};
+        uint64_t ydims[5] = {(uint64_t)c.Cout_p, (uint64_t)c.Wo, (uint64_t)c.Ho, (uint64_t)c.To, (uint64_t)NK};
         uint64_t ystr[5] = {2, (uint64_t)c.Cout_p * 2, (uint64_t)c.Wo * c.Cout_p * 2,
                             (uint64_t)c.Ho * c.Wo * c.Cout_p * 2, (uint64_t)c.To * c.Ho * c.Wo * c.Cout_p * 2};
         int rc = encode_tmap(&P.dy_map, dy, 2, 5, ydims, ystr, ybox, true);
         if (rc) return rc;
-        uint64_t xdims[5] = {(uint64_t)c.Cin_p, (uint64_t)c.W, (uint64_t)c.H, (uint64_t)c.T, (uint64_t)c.N};
+        uint64_t xdims[5] = {(uint64_t)c.Cin_p, (uint64_t)c.W, (uint64_t)c.H, (uint64_t)c.T, (uint64_t)NK};
         uint64_t xstrd[5] = {2, (uint64_t)c.Cin_p * 2, (uint64_t)c.W * c.Cin_p * 2,
                              (uint64_t)c.H * c.W * c.Cin_p * 2, (uint64_t)c.T * c.H * c.W * c.Cin_p * 2};
         rc = encode_tmap(&P.a_map[0], x, 2, 5, xdims, xstrd, xbox, true);
@@ -506,10 +536,12 @@ int conv_wgrad_bf16(const void* x, const void* dy, float* dw, const ConvGeom& c,
     for (int i = 0; i < 5; ++i) { dims[i] = (uint64_t)dim[i]; strides[i] = (uint64_t)str[i] * 2; }
     return encode_tmap(m, base, 2, 5, dims, strides, box, true);
   };
-  const long long xdim[5] = {c.Cin_p, c.W, c.H, c.T, c.N};
+  if (K > 1 && g.ln > 0 && c.N % (1 << g.ln) != 0)
+    return fail(kUnsupported, "merged plane products: position tiles would straddle two planes");
+  const long long xdim[5] = {c.Cin_p, c.W, c.H, c.T, NK};
   const long long xstr[5] = {1, c.Cin_p, (long long)c.W * c.Cin_p, (long long)c.H * c.W * c.Cin_p,
                              (long long)c.T * c.H * c.W * c.Cin_p};
-  const long long ydim[5] = {c.Cout_p, c.Wo, c.Ho, c.To, c.N};
+  const long long ydim[5] = {c.Cout_p, c.Wo, c.Ho, c.To, NK};
   const long long ystr[5] = {1, c.Cout_p, (long long)c.Wo * c.Cout_p, (long long)c.Ho * c.Wo * c.Cout_p,
                              (long long)c.To * c.Ho * c.Wo * c.Cout_p};
   int rc = encode5(&P.dy_map, dy, ydim, ystr);
@@ -555,10 +587,35 @@ int conv_wgrad_bf16(const void* x, const void* dy, float* dw, const ConvGeom& c,
   return wgrad_launch(P, ntaps, c.Cin_p, c.Cout_p, taps_total, dw, stream);
 }
 
+// fp32 mode: dw (fp32, packed) = sum over the plane products of wgrad(x_i, dy_j) in ONE launch. x_planes / dy_planes:
+// bf16 [K][N][...] contiguous stacks of the split planes.
+int conv_wgrad_f32planes(const void* x_planes, const void* dy_planes, int K, float* dw, const ConvGeom& c,
+                         cudaStream_t stream) {
+  if (K < 1 || K > 3) return fail(kBadArg, "1..3 split planes");
+  t_wg_planes = K;
+  int rc = conv_wgrad_bf16(x_planes, dy_planes, dw, c, stream, false, nullptr, 0);
+  t_wg_planes = 1;
+  if (rc != kUnsupported) return rc;
+  // position tiles spanning several clips with a ragged last one: one launch per product, accumulating
+  const long long xs = (long long)c.N * c.T * c.H * c.W * c.Cin_p * 2, ys = (long long)c.N * c.To * c.Ho * c.Wo * c.Cout_p * 2;
+  bool first = true;
+  for (int s = 2 * (K - 1); s >= 0; --s)
+    for (int i = 0; i < K; ++i) {
+      const int j = s - i;
+      if (j < 0 || j >= K - i) continue;
+      rc = conv_wgrad_bf16(static_cast<const uint8_t*>(x_planes) + i * xs, static_cast<const uint8_t*>(dy_planes) + j * ys,
+                           dw, c, stream, !first, nullptr, 0);
+      if (rc) return rc;
+      first = false;
+    }
+  return kOk;
+}
+
 int conv_stem_wgrad_bf16(const void* x_s2d, const void* dy, float* dw, int N, int T, int H2, int W2,
                          int Cout_p, int kt, int pt, cudaStream_t stream, bool accumulate) {
   static thread_local WgradParams P;
   P.xf_ss = nullptr;
+  set_products(P, 1, N);
   const int To = T + 2 * pt - kt + 1;
   const int taps_total = kt * 4;
   if (!accumulate) DV_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout_p * taps_total * 64, stream));

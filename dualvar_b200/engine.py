@@ -265,7 +265,7 @@ def invalidate_weights(params):
     """Drop cached packed copies of parameters that were modified through raw pointers (kernels do not
     bump Tensor._version)."""
     for p in params:
-        for key in (id(p), ("stem", id(p)), ("f32", id(p)), ("f32stem", id(p))):
+        for key in (id(p), ("stem", id(p)), ("f32", id(p)), ("f32stem", id(p)), ("f32all", id(p))):
             hit = _weight_cache.get(key)
             if hit is not None:      # keep the weak reference (and its finalizer), drop version and payload
                 _weight_cache[key] = (hit[0], None, None)
@@ -312,6 +312,28 @@ def packed_weight_planes(conv):
         wt = torch.empty((g.Cin_p, g.taps, g.Cout_p), dtype=torch.bfloat16, device=w.device)
         call("dv_pack_conv_weight", ptr(planes[k]), ptr(wf), ptr(wt), ctypes.byref(g), stream_ptr())
         out.append((wf, wt))
+    _cache_put(key, w, ver, (out, _pack_mark()))
+    return out
+
+
+# fp32 mode: all plane products of a convolution in ONE launch (dv_conv3d_fprop_f32planes / dv_conv3d_dgrad_f32planes):
+# the products are extra taps of one TMEM accumulator and the fp32 output is stored once, instead of one launch per
+# product with a read-modify-write of the output for all but the first. DV_F32_MERGE=0 restores the per-product launches.
+F32_MERGE = os.environ.get("DV_F32_MERGE", "1") != "0"
+
+
+def packed_weight_planes_all(conv):
+    """fp32 mode: (wf_all [Cout_p][K*taps][Cin_p], wt_all [Cin_p][K*taps][Cout_p]) - the K packed planes side by side
+    along the tap dimension (plane j in tap slots [j*taps, (j+1)*taps)), for the merged plane-product launches."""
+    w = conv.weight
+    key = ("f32all", id(w))
+    ver = (w._version, w.data_ptr(), F32_PLANES)
+    hit = _cache_get(key, w, ver)
+    if hit is not None:
+        _after_pack(hit[1])
+        return hit[0]
+    planes = packed_weight_planes(conv)
+    out = (torch.cat([p_[0] for p_ in planes], 1).contiguous(), torch.cat([p_[1] for p_ in planes], 1).contiguous())
     _cache_put(key, w, ver, (out, _pack_mark()))
     return out
 
@@ -505,11 +527,17 @@ def conv_stats(ctx, x, conv, bn):
         y = torch.empty((N, g.To, g.Ho, g.Wo, g.Cout_p), dtype=torch.float32, device=dev)
         packed = packed_stem_weight_planes(conv, g) if stem else packed_weight_planes(conv)
         bias = _bias_padded(conv, g.Cout_p)
-        for n, (i, j) in enumerate(_terms()):      # the first product overwrites y, the others add to it
-            call("dv_conv3d_stem_fprop_f32acc" if stem else "dv_conv3d_fprop_f32acc", ptr(x.planes[i]),
-                 ptr(packed[j][0]), ptr(y), ptr(bias) if n == 0 else None, ctypes.byref(g), 1 if n else 0, stream_ptr())
-        if training_stats:
-            call("dv_f32_colstats", ptr(y), ptr(stats), y.numel() // g.Cout_p, g.Cout_p, stream_ptr())
+        if F32_MERGE and not stem and tuple(conv.stride) == (1, 1, 1):
+            wf_all, _ = packed_weight_planes_all(conv)      # every plane product in one launch, y stored once
+            call("dv_conv3d_fprop_f32planes", ptr(x.planes), x.planes.stride(0), F32_PLANES, ptr(wf_all), ptr(y),
+                 ptr(stats), ptr(bias), ctypes.byref(g), stream_ptr())      # batch statistics from the epilogue
+        else:
+            for n, (i, j) in enumerate(_terms()):      # the first product overwrites y, the others add to it
+                call("dv_conv3d_stem_fprop_f32acc" if stem else "dv_conv3d_fprop_f32acc", ptr(x.planes[i]),
+                     ptr(packed[j][0]), ptr(y), ptr(bias) if n == 0 else None, ctypes.byref(g), 1 if n else 0,
+                     stream_ptr())
+            if training_stats:
+                call("dv_f32_colstats", ptr(y), ptr(stats), y.numel() // g.Cout_p, g.Cout_p, stream_ptr())
     elif stem:
         y = torch.empty((N, g.To, g.Ho, g.Wo, g.Cout_p), dtype=torch.bfloat16, device=dev)
         packed = (packed_stem_weights(conv, g), None)
@@ -653,18 +681,26 @@ def _conv_backward_f32(ctx, r, dyp):
         call("dv_unpack_stem_wgrad", ptr(dwp), ptr(gw), ctypes.byref(g), ctypes.c_float(0.0), stream_ptr())
     else:
         dwp = torch.empty((g.Cout_p, g.taps, g.Cin_p), dtype=torch.float32, device=dyp.device)
-        for n, (i, j) in enumerate(terms):
-            call("dv_conv3d_wgrad_bf16" if n == 0 else "dv_conv3d_wgrad_bf16_acc", ptr(r.x.planes[i]), ptr(dyp[j]),
-                 ptr(dwp), ctypes.byref(g), stream_ptr())
+        if F32_MERGE and r.x.planes.is_contiguous() and dyp.is_contiguous():
+            call("dv_conv3d_wgrad_f32planes", ptr(r.x.planes), ptr(dyp), F32_PLANES, ptr(dwp), ctypes.byref(g), stream_ptr())
+        else:
+            for n, (i, j) in enumerate(terms):
+                call("dv_conv3d_wgrad_bf16" if n == 0 else "dv_conv3d_wgrad_bf16_acc", ptr(r.x.planes[i]), ptr(dyp[j]),
+                     ptr(dwp), ctypes.byref(g), stream_ptr())
         call("dv_unpack_conv_wgrad", ptr(dwp), ptr(gw), ctypes.byref(g), ctypes.c_float(0.0), stream_ptr())
     ctx.add_param_grad(r.conv.weight, gw)
     if r.conv.bias is not None:
         ctx.add_param_grad(r.conv.bias, torch.zeros_like(r.conv.bias))
     if r.x.needs_grad:
         dx = torch.empty(r.x.shape5, dtype=torch.float32, device=dyp.device)
-        for n, (i, j) in enumerate(terms):
-            call("dv_conv3d_dgrad_f32acc", ptr(dyp[i]), ptr(r.packed[j][1]), ptr(dx), ctypes.byref(g), 1 if n else 0,
+        if F32_MERGE:
+            _, wt_all = packed_weight_planes_all(r.conv)
+            call("dv_conv3d_dgrad_f32planes", ptr(dyp), dyp.stride(0), F32_PLANES, ptr(wt_all), ptr(dx), ctypes.byref(g),
                  stream_ptr())
+        else:
+            for n, (i, j) in enumerate(terms):
+                call("dv_conv3d_dgrad_f32acc", ptr(dyp[i]), ptr(r.packed[j][1]), ptr(dx), ctypes.byref(g), 1 if n else 0,
+                     stream_ptr())
         _acc_grad(r.x, dx)
 
 

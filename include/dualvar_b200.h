@@ -307,6 +307,23 @@ int dv_comm_status(int* peer, int64_t* seq, int clear);
 /* fp32 values -> n_planes fp32 tensors [n_planes][n] holding the bf16-representable parts (feed each plane to
  * dv_pack_conv_weight / dv_pack_stem_weight, which then rounds exactly) */
 int dv_f32_split_planes(const float* src, float* dst_planes, int64_t n, int n_planes, void* stream);
+/* fp32 mode, ALL plane products of a convolution in one launch: y = sum_{i + j < K} conv(x_i, w_j) accumulated in one
+ * TMEM accumulator (the products are extra taps, smallest contributions first) and stored to the fp32 output once -
+ * instead of one dv_conv3d_fprop_f32acc launch per product (one store + K(K+1)/2 - 1 read-modify-write passes).
+ * x_planes / dy_planes: the K bf16 split planes, plane_stride elements apart; wf_all: bf16 [Cout_p][K*taps][Cin_p] and
+ * wt_all: bf16 [Cin_p][K*taps][Cout_p] with plane j in tap slots [j*taps, (j+1)*taps). fprop: stride-1 convolutions;
+ * stats (may be NULL): double [2*Cout_p], per-channel sum / sum of squares of y ADDED to it by the epilogue (zero it
+ * first) - the fused BatchNorm batch statistics, possible here because the launch holds the finished sum. */
+int dv_conv3d_fprop_f32planes(const void* x_planes, int64_t plane_stride, int n_planes, const void* wf_all, float* y,
+                              double* stats, const float* bias_padded, const dv_conv_geom* g, void* stream);
+int dv_conv3d_dgrad_f32planes(const void* dy_planes, int64_t plane_stride, int n_planes, const void* wt_all, float* dx,
+                              const dv_conv_geom* g, void* stream);
+/* the weight gradient of the same sum in one launch: dw_packed fp32 [Cout_p][taps][Cin_p] (overwritten) =
+ * sum_{i + j < K} wgrad(x_i, dy_j); both operands are CONTIGUOUS stacks [K][N][...] of their bf16 split planes (the
+ * kernel walks them as one tensor of K*N clips), every position tile is contracted once per product into the same
+ * TMEM accumulators and reduced into dw_packed once. Unpack with dv_unpack_conv_wgrad. */
+int dv_conv3d_wgrad_f32planes(const void* x_planes, const void* dy_planes, int n_planes, float* dw_packed,
+                              const dv_conv_geom* g, void* stream);
 /* y (+)= conv(x_plane, w_plane) (+ bias); y fp32 [N][To][Ho][Wo][Cout_p]. accumulate = 0: the first product of a sum,
  * y is overwritten (no zero fill needed); accumulate = 1: added to y */
 int dv_conv3d_fprop_f32acc(const void* x_plane, const void* wf_plane, float* y, const float* bias_padded,

@@ -110,6 +110,26 @@ def test_conv_trio_fp32_mode_matches_fp64(case, K, tol):
     assert _relmax(y[..., :Cout].permute(0, 4, 1, 2, 3), yr.detach()) < tol
     if g.Cout_p > Cout:
         assert bool((y[..., Cout:] == 0).all())
+    # the same products as extra taps of ONE launch (the engine's path for stride-1 layers): same bound
+    wf_all, wt_all = E.packed_weight_planes_all(conv)
+    ym = torch.full_like(y, float("nan"))
+    if s == (1, 1, 1):
+        mstats = torch.zeros(2 * g.Cout_p, dtype=torch.float64, device=dev)
+        call("dv_conv3d_fprop_f32planes", ptr(xp), xp.stride(0), K, ptr(wf_all), ptr(ym), ptr(mstats), ptr(bias_p),
+             ctypes.byref(g), st())
+        assert _relmax(ym[..., :Cout].permute(0, 4, 1, 2, 3), yr.detach()) < tol
+        # the epilogue's batch statistics (fp32 partials per CTA, double across CTAs) of the stored output
+        ysm = ym.reshape(-1, g.Cout_p).double()
+        scale = ysm.abs().sum(0).clamp_min(1e-30)
+        assert float(((mstats[:g.Cout_p] - ysm.sum(0)).abs() / scale).max()) < 2e-6
+        assert float(((mstats[g.Cout_p:] - (ysm * ysm).sum(0)).abs() / (ysm * ysm).sum(0).clamp_min(1e-30)).max()) < 2e-6
+        assert _relmax(ym, y) < tol
+        if g.Cout_p > Cout:
+            assert bool((ym[..., Cout:] == 0).all())
+    else:
+        with pytest.raises(_lib.DualVarNativeError, match="stride-1"):
+            call("dv_conv3d_fprop_f32planes", ptr(xp), xp.stride(0), K, ptr(wf_all), ptr(ym), None, ptr(bias_p),
+                 ctypes.byref(g), st())
     # batch statistics of the fp32 output
     stats = torch.zeros(2 * g.Cout_p, dtype=torch.float64, device=dev)
     call("dv_f32_colstats", ptr(y), ptr(stats), y.numel() // g.Cout_p, g.Cout_p, st())
@@ -122,12 +142,20 @@ def test_conv_trio_fp32_mode_matches_fp64(case, K, tol):
     for n, (i, j) in enumerate(E._terms()):
         call("dv_conv3d_dgrad_f32acc", ptr(dyp[i]), ptr(wp[j][1]), ptr(dx), ctypes.byref(g), 1 if n else 0, st())
     assert _relmax(dx[..., :Cin].permute(0, 4, 1, 2, 3), xr.grad) < tol
+    dxm = torch.full_like(dx, float("nan"))      # merged launch (one per stride-parity class), any stride
+    call("dv_conv3d_dgrad_f32planes", ptr(dyp), dyp.stride(0), K, ptr(wt_all), ptr(dxm), ctypes.byref(g), st())
+    assert _relmax(dxm[..., :Cin].permute(0, 4, 1, 2, 3), xr.grad) < tol
+    assert _relmax(dxm, dx) < tol
     dwp = torch.empty((g.Cout_p, g.taps, g.Cin_p), dtype=torch.float32, device=dev)
     for n, (i, j) in enumerate(E._terms()):
         call("dv_conv3d_wgrad_bf16" if n == 0 else "dv_conv3d_wgrad_bf16_acc", ptr(xp[i]), ptr(dyp[j]), ptr(dwp),
              ctypes.byref(g), st())
     dw = KK.unpack_conv_wgrad(dwp, g)
     assert _relmax(dw, wr.grad) < tol
+    dwm = torch.full_like(dwp, float("nan"))     # all products in one launch, one reduction into the packed buffer
+    call("dv_conv3d_wgrad_f32planes", ptr(xp), ptr(dyp), K, ptr(dwm), ctypes.byref(g), st())
+    assert _relmax(KK.unpack_conv_wgrad(dwm, g), wr.grad) < tol
+    assert _relmax(dwm, dwp) < tol
 
 
 def test_split_planes_are_exact():
@@ -340,7 +368,7 @@ def test_dualvar_step_fp32_mode_within_1e4_of_oracle(kind, net):
     sum(v for k, v in rp.items() if "loss" in k).backward()
     if r64 is not None:
         sum(v for k, v in r64.items() if "loss" in k).backward()
-    assert _lib.load().dv_launch_count() - n0 > 600          # the native path really ran (6 launches per conv)
+    assert _lib.load().dv_launch_count() - n0 > 300          # the native path really ran (merged plane products: 1 fprop + 1 dgrad + 6 wgrad launches per stride-1 conv)
     _grad_report(f"{kind}/{net}", ref, prod, ref64 if r64 is not None else None)
     for (n, br), (_, bp) in zip(ref.named_buffers(), prod.named_buffers()):
         if br.dtype.is_floating_point and "queue" not in n:
