@@ -303,24 +303,40 @@ def fp32_mode_leg(dev, host_frames, steps=3, batch=16):
         def st():
             ret = m(RawClips(frames, 3))
             loss = sum(v for k, v in ret.items() if "loss" in k)
-            opt.zero_grad(set_to_none=True)
+            opt.zero_grad(set_to_none=False)
             loss.backward()
             opt.step()
-            return loss
+            return loss.detach()      # (detached: see time_step.eager in other_configs_leg)
+
+        def timed(fn):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                out = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / steps, out
         for _ in range(2):
             st()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            loss = st()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / steps
-        return {"value": batch / (ms / 1e3), "unit": "samples/s", "ms_per_step": ms, "samples_per_gpu": batch,
-                "steps": steps, "split_planes": 3, "final_loss": float(loss.detach()),
-                "dtype": "f32 activations; conv = 6 bf16 plane products, fp32 accumulate",
-                "parity": "losses within 1e-4 of the fp32 oracle (tests/test_fp32_mode_gpu.py)"}
+        ms, loss = timed(st)
+        res = {"value": batch / (ms / 1e3), "unit": "samples/s", "ms_per_step": ms, "mode": "eager", "samples_per_gpu": batch,
+               "steps": steps, "split_planes": 3, "final_loss": float(loss),
+               "dtype": "f32 activations; conv = 6 bf16 plane products in one launch, fp32 accumulate",
+               "parity": "losses within 1e-4 of the fp32 oracle (tests/test_fp32_mode_gpu.py)"}
+        try:      # the same step replayed as one CUDA graph; the eager figure stands if the capture is refused
+            from dualvar_b200.graph_step import GraphedTrainStep
+            gs = GraphedTrainStep(m, opt, n_views=3, warmup=1)
+            if gs.enabled:
+                for _ in range(2):
+                    gs(frames)
+                ms_g, out = timed(lambda: gs(frames))
+                res["eager"] = {"value": res["value"], "ms_per_step": ms}
+                res.update(value=batch / (ms_g / 1e3), ms_per_step=ms_g, mode="cuda_graph", final_loss=float(out["loss"]))
+                gs.release()
+        except Exception as e:  # noqa: BLE001
+            res["graph_error"] = f"{type(e).__name__}: {e}"[:300]
+        return res
     except Exception as e:  # noqa: BLE001 - a side figure must not take the headline line down
         return {"error": f"{type(e).__name__}: {e}"}
     finally:

@@ -1404,16 +1404,42 @@ static int encode_stem_map(CUtensorMap* m, const void* ctx, int /*view*/, const 
 // wf_all: bf16 [Cout_p][K * taps][Cin_p] (plane j in tap slots [j * taps, (j + 1) * taps)). Stride 1 only.
 int conv_fprop_f32planes(const void* x_planes, long long plane_stride, int K, const void* wf_all, float* y,
                          double* stats, const float* bias, const ConvGeom& c, cudaStream_t stream) {
-  if (c.st != 1 || c.sh != 1 || c.sw != 1) return fail(kUnsupported, "merged plane products: stride-1 convolutions only");
   if (K < 1 || K > 3) return fail(kBadArg, "1..3 split planes");
   static thread_local ConvTileParams P;
   P.xf_ss = nullptr;
   const int taps_total = c.kt * c.kh * c.kw;
+  const bool unit_stride = c.st == 1 && c.sh == 1 && c.sw == 1;
+  // views: (stride-parity class, plane) - a strided layer reads each plane through one subsampled map per class
   ViewSet vs;
-  for (int i = 0; i < K; ++i) {
-    vs.v[i] = make_ndhwc(static_cast<const uint8_t*>(x_planes) + (long long)i * plane_stride * 2, c.N, c.T, c.H, c.W, c.Cin_p);
-    for (int d = 0; d < 4; ++d) P.a_dims[i][d] = (int)vs.v[i].dim[1 + d];
-  }
+  int view_of[8][3];
+  for (int i = 0; i < 8; ++i) for (int k = 0; k < 3; ++k) view_of[i][k] = -1;
+  int nviews = 0;
+  struct Hit { int key, ot, oh, ow, widx; };
+  std::vector<Hit> hits;
+  for (int a = 0; a < c.kt; ++a)
+    for (int b = 0; b < c.kh; ++b)
+      for (int d = 0; d < c.kw; ++d) {
+        const int ot = a - c.pt, oh = b - c.ph, ow = d - c.pw;
+        const int rt = posmod(ot, c.st), rh = posmod(oh, c.sh), rw = posmod(ow, c.sw);
+        if (rt > 1 || rh > 1 || rw > 1) return fail(kUnsupported, "conv stride > 2 not supported");
+        if (rt >= c.T || rh >= c.H || rw >= c.W) continue;  // tap never touches real data
+        const int key = (rt * 2 + rh) * 2 + rw;
+        if (view_of[key][0] < 0) {
+          if (nviews + K > kMaxAMaps)
+            return fail(kUnsupported, "merged plane products: more than %d (parity class, plane) views", kMaxAMaps);
+          for (int i = 0; i < K; ++i) {
+            View5 v = make_ndhwc(static_cast<const uint8_t*>(x_planes) + (long long)i * plane_stride * 2, c.N, c.T, c.H,
+                                 c.W, c.Cin_p);
+            subsample(v, 3, rt, c.st);
+            subsample(v, 2, rh, c.sh);
+            subsample(v, 1, rw, c.sw);
+            vs.v[nviews] = v;
+            for (int q = 0; q < 4; ++q) P.a_dims[nviews][q] = (int)v.dim[1 + q];
+            view_of[key][i] = nviews++;
+          }
+        }
+        hits.push_back({key, floordiv(ot, c.st), floordiv(oh, c.sh), floordiv(ow, c.sw), (a * c.kh + b) * c.kw + d});
+      }
   View5 outv = make_ndhwc(y, c.N, c.To, c.Ho, c.Wo, c.Cout_p);
   outv.esize = 4; outv.store = 1;
   std::vector<TapSpec> taps;
@@ -1421,17 +1447,13 @@ int conv_fprop_f32planes(const void* x_planes, long long plane_stride, int K, co
     for (int i = 0; i < K; ++i) {
       const int j = s - i;
       if (j < 0 || j >= K - i) continue;            // products with i + j < K only
-      for (int a = 0; a < c.kt; ++a)
-        for (int b = 0; b < c.kh; ++b)
-          for (int d = 0; d < c.kw; ++d) {
-            const int ot = a - c.pt, oh = b - c.ph, ow = d - c.pw;
-            taps.push_back({i, ot, oh, ow, j * taps_total + (a * c.kh + b) * c.kw + d});
-          }
+      for (const Hit& h : hits) taps.push_back({view_of[h.key][i], h.ot, h.oh, h.ow, j * taps_total + h.widx});
     }
-  t_plane_views = true;
+  // stride 1: view = plane, the taps of one plane product may share halo boxes; strided layers keep one box per tap
+  t_plane_views = unit_stride;
   t_plane_taps = taps_total;
-  const int rc = conv_multi_tap(P, encode_from_viewset, &vs, K, taps, outv, c.Cout_p, wf_all, c.Cout_p, K * taps_total,
-                                c.Cin_p, stats, bias, stream);
+  const int rc = conv_multi_tap(P, encode_from_viewset, &vs, nviews, taps, outv, c.Cout_p, wf_all, c.Cout_p,
+                                K * taps_total, c.Cin_p, stats, bias, stream);
   t_plane_views = false;
   return rc;
 }

@@ -16,7 +16,7 @@ namespace dv {
 constexpr int kTileM = 128;        // output positions per tile (= TMEM lanes)
 constexpr int kChunkK = 64;        // bf16 channels per TMA box row (= 128 B, one swizzle span)
 constexpr int kMaxTaps = 168;      // (3,7,7) stem = 147 taps; fp32 mode: 6 plane products x 27 taps = 162 virtual taps
-constexpr int kMaxAMaps = 8;       // 2 x 2 x 2 stride parities
+constexpr int kMaxAMaps = 12;      // 2 x 2 x 2 stride parities; fp32 mode: (parity class, split plane) pairs, e.g. 4 x 3
 constexpr int kMaxBlockN = 256;
 
 struct Tap {

@@ -527,7 +527,11 @@ def conv_stats(ctx, x, conv, bn):
         y = torch.empty((N, g.To, g.Ho, g.Wo, g.Cout_p), dtype=torch.float32, device=dev)
         packed = packed_stem_weight_planes(conv, g) if stem else packed_weight_planes(conv)
         bias = _bias_padded(conv, g.Cout_p)
-        if F32_MERGE and not stem and tuple(conv.stride) == (1, 1, 1):
+        # (a strided layer reads every plane through one tensor map per stride-parity class its taps reach: 12 maps at most)
+        n_parity = 1
+        for k_, s_ in zip(w.shape[2:], conv.stride):
+            n_parity *= min(int(k_), int(s_))
+        if F32_MERGE and not stem and n_parity * F32_PLANES <= 12:
             wf_all, _ = packed_weight_planes_all(conv)      # every plane product in one launch, y stored once
             call("dv_conv3d_fprop_f32planes", ptr(x.planes), x.planes.stride(0), F32_PLANES, ptr(wf_all), ptr(y),
                  ptr(stats), ptr(bias), ctypes.byref(g), stream_ptr())      # batch statistics from the epilogue

@@ -311,7 +311,8 @@ int dv_f32_split_planes(const float* src, float* dst_planes, int64_t n, int n_pl
  * TMEM accumulator (the products are extra taps, smallest contributions first) and stored to the fp32 output once -
  * instead of one dv_conv3d_fprop_f32acc launch per product (one store + K(K+1)/2 - 1 read-modify-write passes).
  * x_planes / dy_planes: the K bf16 split planes, plane_stride elements apart; wf_all: bf16 [Cout_p][K*taps][Cin_p] and
- * wt_all: bf16 [Cin_p][K*taps][Cout_p] with plane j in tap slots [j*taps, (j+1)*taps). fprop: stride-1 convolutions;
+ * wt_all: bf16 [Cin_p][K*taps][Cout_p] with plane j in tap slots [j*taps, (j+1)*taps). fprop of a strided layer reads
+ * every plane through one tensor map per stride-parity class its taps reach (at most 12 maps, a non-zero status beyond);
  * stats (may be NULL): double [2*Cout_p], per-channel sum / sum of squares of y ADDED to it by the epilogue (zero it
  * first) - the fused BatchNorm batch statistics, possible here because the launch holds the finished sum. */
 int dv_conv3d_fprop_f32planes(const void* x_planes, int64_t plane_stride, int n_planes, const void* wf_all, float* y,

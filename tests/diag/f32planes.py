@@ -39,7 +39,7 @@ for (n, t, h, w, ci, co, k, s, p) in [(NCL, 16, 56, 56, 64, 144, (1, 3, 3), (1, 
     def per_product():
         for m, (i, j) in enumerate(terms):
             call("dv_conv3d_fprop_f32acc", ptr(xp[i]), ptr(wfl[j]), ptr(y0), None, ctypes.byref(g), 1 if m else 0, stream_ptr())
-    stride1 = s == (1, 1, 1)
+    stride1 = True      # strided layers: one tensor map per (stride-parity class, plane)
     merged = lambda: call("dv_conv3d_fprop_f32planes", ptr(xp), xp[0].numel(), KP, ptr(wf_all), ptr(y1), None, None, ctypes.byref(g), stream_ptr())
     per_product()
     line = f"{(ci, co, k, s)}: fprop per-product {timed(per_product):.3f} ms"
