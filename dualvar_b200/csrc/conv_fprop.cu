@@ -935,6 +935,12 @@ using MapEncoder = int (*)(CUtensorMap*, const void* ctx, int view, const uint32
 // "views" are the bf16 split planes of one tensor (same geometry), not stride-parity classes - tap grouping stays legal.
 static thread_local bool t_plane_views = false;
 static thread_local int t_plane_taps = 0;      // filter taps per weight plane (tap index / t_plane_taps = weight plane)
+static thread_local bool t_f32_split = false;  // set by the merged plane-product entry points: two-issuer instances allowed
+static bool f32_split_enabled() {               // DV_F32_SPLIT_ISSUE=0: one issuing thread in the fp32 instances (A/B)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DV_F32_SPLIT_ISSUE"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
 
 static long long* g_prof = nullptr;
 #ifdef DV_DIAG
@@ -1128,7 +1134,9 @@ static int conv_multi_tap_region(ConvTileParams& P, MapEncoder enc, const void* 
   // Wider tiles (the 88-channel stem) are epilogue-bound and lose to the second accumulator's loads
   // (DV_CONV_SPLIT_ISSUE=2 extends it to N <= 128 and any MMA count; tests/diag/layer_ab.py).
   const int mma_per_tile = ntaps * ((P.k_chunks - 1) * 4 + P.k_steps_last);
-  P.split = (g_split_issue && outv.esize == 2 && P.n_tiles == 1 &&
+  // (fp32 mode: the merged plane-product launches that store the finished sum; both issuers walk the taps in order,
+  // so each half accumulator still meets its smallest contributions first)
+  P.split = (g_split_issue && (outv.esize == 2 || (outv.esize == 4 && outv.store && t_f32_split)) && P.n_tiles == 1 &&
              P.block_n <= (g_split_issue == 2 ? kMaxBlockN / 2 : 64) && (g_split_issue == 2 || mma_per_tile >= 24) &&
              P.group_len[0] * (P.k_chunks > 1 ? 4 : P.k_steps_last) >= 2) ? 1 : 0;
   if (P.split) {
@@ -1202,6 +1210,10 @@ static int conv_multi_tap_region(ConvTileParams& P, MapEncoder enc, const void* 
                                     kSmemBudget));
     DV_CUDA_OK(cudaFuncSetAttribute(conv_tile_kernel<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     kSmemBudget));
+    DV_CUDA_OK(cudaFuncSetAttribute(conv_tile_kernel<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kSmemBudget));
+    DV_CUDA_OK(cudaFuncSetAttribute(conv_tile_kernel<true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kSmemBudget));
     attr_set = true;
   }
   // CTAs (or CTA pairs): one per SM (pair of SMs), a multiple of the channel-tile count
@@ -1211,6 +1223,7 @@ static int conv_multi_tap_region(ConvTileParams& P, MapEncoder enc, const void* 
   if (!pair) {
     if (xf && P.split) conv_tile_kernel<false, false, true, true><<<units, kNumThreads + kXfThreads + kIssue2Threads, smem_bytes, stream>>>(P);
     else if (xf) conv_tile_kernel<false, false, true><<<units, kNumThreads + kXfThreads, smem_bytes, stream>>>(P);
+    else if (f32 && P.split) conv_tile_kernel<false, true, false, true><<<units, kNumThreads + kIssue2Threads, smem_bytes, stream>>>(P);
     else if (f32) conv_tile_kernel<false, true><<<units, kNumThreads, smem_bytes, stream>>>(P);
     else if (P.split) conv_tile_kernel<false, false, false, true><<<units, kNumThreads + kIssue2Threads, smem_bytes, stream>>>(P);
     else conv_tile_kernel<false><<<units, kNumThreads, smem_bytes, stream>>>(P);
@@ -1227,6 +1240,7 @@ static int conv_multi_tap_region(ConvTileParams& P, MapEncoder enc, const void* 
     cfg.numAttrs = 1;
     if (xf && P.split) DV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tile_kernel<true, false, true, true>, P));
     else if (xf) DV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tile_kernel<true, false, true>, P));
+    else if (f32 && P.split) DV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tile_kernel<true, true, false, true>, P));
     else if (f32) DV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tile_kernel<true, true>, P));
     else if (P.split) DV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tile_kernel<true, false, false, true>, P));
     else DV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tile_kernel<true>, P));
@@ -1452,9 +1466,12 @@ int conv_fprop_f32planes(const void* x_planes, long long plane_stride, int K, co
   // stride 1: view = plane, the taps of one plane product may share halo boxes; strided layers keep one box per tap
   t_plane_views = unit_stride;
   t_plane_taps = taps_total;
+  // (no two-issuer instance here: measured on the 144->64 temporal layer it is 9 % slower than one issuer - 1.43 against
+  // 1.31 ms at 48 clips - while the 64<-144 data gradient gains 22 %; profiles/r02d_fp32_merged_plane_products.txt)
   const int rc = conv_multi_tap(P, encode_from_viewset, &vs, nviews, taps, outv, c.Cout_p, wf_all, c.Cout_p,
                                 K * taps_total, c.Cin_p, stats, bias, stream);
   t_plane_views = false;
+  t_f32_split = false;
   return rc;
 }
 
@@ -1513,9 +1530,11 @@ int conv_dgrad_f32planes(const void* dy_planes, long long plane_stride, int K, c
           for (int d = 0; d < 4; ++d) P.a_dims[i][d] = (int)vs.v[i].dim[1 + d];
         t_plane_views = true;
         t_plane_taps = taps_total;
+        t_f32_split = f32_split_enabled();
         const int rc = conv_multi_tap(P, encode_from_viewset, &vs, K, taps, ov, c.Cin_p, wt_all, c.Cin_p, K * taps_total,
                                       c.Cout_p, nullptr, nullptr, stream);
         t_plane_views = false;
+        t_f32_split = false;
         if (rc) return rc;
       }
   return kOk;
