@@ -313,6 +313,38 @@ def test_backbone_fp32_mode_matches_oracle(net, shape):
             assert _rel(bp, br) < 1e-4, n
 
 
+@pytest.mark.parametrize("net,shape", [("r21d", (4, 3, 8, 64, 64)), ("r3d", (4, 3, 8, 64, 64))])
+def test_merged_and_per_product_engine_paths_agree(net, shape):
+    """engine.F32_MERGE (all plane products of a convolution in one launch, statistics from the epilogue) against one
+    launch per product + dv_f32_colstats on the same backbone: output, parameter gradients and running statistics."""
+    from dualvar_b200 import backbones as PB, engine as E, _lib
+    _seed(3)
+    a, _ = PB.select_backbone(net)
+    a = a.to(dev).train()
+    b = copy.deepcopy(a)
+    x = torch.randn(*shape, device=dev)
+    res = []
+    for m, merge in ((a, True), (b, False)):
+        old = E.F32_MERGE
+        E.F32_MERGE = merge
+        try:
+            n0 = _lib.load().dv_launch_count()
+            y = m(x)
+            (y * torch.linspace(-1, 1, y.numel(), device=dev).view_as(y)).sum().backward()
+            res.append((y.detach(), _lib.load().dv_launch_count() - n0))
+        finally:
+            E.F32_MERGE = old
+    (ya, la), (yb, lb) = res
+    assert la < 0.7 * lb, (la, lb)            # the merged path really ran (well under half of the launches)
+    assert _relmax(ya, yb) < 5e-6
+    worst = max(_rel(pa.grad, pb.grad) for pa, pb in zip(a.parameters(), b.parameters()) if pa.grad is not None)
+    print(f"{net}: merged vs per-product: output {_relmax(ya, yb):.2e}, worst gradient rel L2 {worst:.2e}, launches {la} vs {lb}")
+    assert worst < 2e-4, worst
+    for (n, ba), (_, bb) in zip(a.named_buffers(), b.named_buffers()):
+        if ba.dtype.is_floating_point:
+            assert _relmax(ba, bb) < 1e-5, n
+
+
 def _model_pair(kind, net):
     from dualvar_b200 import models as PM
     from oracle import models as OM
