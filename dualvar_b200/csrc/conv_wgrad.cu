@@ -64,6 +64,9 @@ struct alignas(64) WgradParams {
   // fp32 reduction into dw happens once instead of once per product. n_prod = 1: the plain weight gradient.
   int n_prod;
   int prod_nx[6], prod_ny[6];   // batch offset (plane * N) of the product's X / dY plane
+  // dY sharing: the two unit groups of a layer are the two CTAs of a cluster, walk the position tiles in lockstep and
+  // each fetches half of the dY boxes of a stage, multicast into both (see wgrad_launch)
+  int cluster;
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -99,10 +102,12 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
   const int b_bytes = ((p.block_n + 63) >> 6) * kBoxBytes;
   const int stage_bytes = a_bytes + b_bytes;
 
+  const bool clus = p.cluster != 0;
+  const uint32_t crank = clus ? cluster_ctarank() : 0u;
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], clus ? 2 : 1);   // cluster: a stage is free when BOTH CTAs' MMAs have read it
       mbar_init(&xf_bar[i], 128);
     }
     mbar_init(&acc_bar, 1);
@@ -115,6 +120,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
   if (xf) stage_ss_table(xf_table, p.xf_ss, p.cin_p, p.k_chunks, threadIdx.x, kWgThreads);
   tc_fence_before_sync();
   __syncthreads();
+  if (clus) cluster_sync_all();     // the peer's barriers are initialised before anything is multicast to them
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_slot;
   const TileGeom& g = p.g;
@@ -142,8 +148,13 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
           mbar_expect_tx(&full_bar[stage], tx);
           uint8_t* a_s = smem + stage * stage_bytes;
           uint8_t* b_s = a_s + a_bytes;
-          for (int j = 0; j < nbx; ++j)
-            tma_load_5d(b_s + j * kBoxBytes, &p.dy_map, &full_bar[stage], n_tile * p.block_n + j * 64, w0, h0, t0, ny);
+          for (int j = 0; j < nbx; ++j) {
+            if (!clus)
+              tma_load_5d(b_s + j * kBoxBytes, &p.dy_map, &full_bar[stage], n_tile * p.block_n + j * 64, w0, h0, t0, ny);
+            else if ((uint32_t)(j & 1) == crank)     // this CTA's share of the dY boxes, delivered to both
+              tma_load_5d_mc(b_s + j * kBoxBytes, &p.dy_map, &full_bar[stage], n_tile * p.block_n + j * 64, w0, h0, t0, ny,
+                             (uint16_t)3);
+          }
           if (p.halo) {
             for (int b = 0; b < nbox; ++b)
               tma_load_5d(a_s + b * p.x_box_bytes, &p.a_map[0], &full_bar[stage], p.box_kc[box0 + b] * 64,
@@ -163,6 +174,14 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
+    if (clus) {
+      // tail: every stage's last release has arrived (own commit and the peer's multicast one) before this CTA goes on
+      // to exit - nothing of the peer may still be in flight towards this CTA's barriers
+      for (int i = 0; i < p.stages; ++i) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
   } else if (warp == 1) {
     // MMA issuer: uniform loop state (descriptor words in uniform registers), one elected lane issues
     const bool issuer = elect_one();
@@ -170,7 +189,9 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
     // MN-major SWIZZLE_128B: 8-position (K) groups 1024 B apart (SBO), 64-channel (M/N) groups one box apart (LBO)
     const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
     const uint32_t lo_flags = (uint32_t)(kBoxBytes >> 4) << 16;
-    const uint32_t base_enc = smem_u32(smem) >> 4, stage_enc = (uint32_t)stage_bytes >> 4;
+    // (start-address field: 14 bits of address >> 4 inside the CTA's own 256 KB window - in a cluster launch the shared
+    // window address of a CTA carries its rank in higher bits, which must not spill into the descriptor's LBO field)
+    const uint32_t base_enc = (smem_u32(smem) & 0x3ffffu) >> 4, stage_enc = (uint32_t)stage_bytes >> 4;
     const uint32_t a_enc = (uint32_t)a_bytes >> 4;
     int stage = 0;
     uint32_t phase = 0;
@@ -200,7 +221,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
           umma_bf16_lohi(dt, al + 256, b_lo + 256, desc_hi, idesc, 1);
           umma_bf16_lohi(dt, al + 384, b_lo + 384, desc_hi, idesc, 1);
         }
-        umma_commit(&empty_bar[stage]);
+        if (clus) umma_commit_mc(&empty_bar[stage], (uint16_t)3); else umma_commit(&empty_bar[stage]);
       }
       accumulate = 1;
       __syncwarp();
@@ -292,6 +313,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
   }
   tc_fence_before_sync();
   __syncthreads();
+  if (clus) cluster_sync_all();     // neither CTA leaves while the other may still address its shared memory
   if (warp == 1) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 512);
@@ -377,7 +399,30 @@ static int wgrad_launch(WgradParams& P, int ntaps, int cin_p, int cout_p, int ta
   }
   const int smem_bytes = 1024 + xf_bytes + P.stages * stage_bytes;
   dim3 grid(items, ksplit);
-  conv_wgrad_kernel<<<grid, kWgThreads, smem_bytes, stream>>>(P);
+  // Two unit groups of one channel tile (the 64->144 3x3 layers: 2 + 1 halo boxes): launched side by side they drift apart
+  // (44 against 34 KB per position tile), the second read of dY misses L2 and the launch moves 1.8x its algorithmic bytes
+  // through HBM (profiles/r02d_bench_n1.json) next to the HBM-bound BatchNorm passes. As a cluster of 2 they stay in
+  // lockstep and fetch every dY box once for both. Measured (profiles/r02d_wgrad_cluster_multicast.txt): the launch alone
+  // is 2-4 % slower (the smaller group waits for the larger one), the step is a tie (913.6 vs 914.4 samples/s) - the HBM
+  // relief pays for the lockstep and no more - so it is opt-in: DV_WGRAD_CLUSTER=1 (read per call).
+  const char* ce = getenv("DV_WGRAD_CLUSTER");
+  const int cluster_env = ce ? atoi(ce) : 0;
+  P.cluster = (cluster_env && P.halo && groups == 2 && P.n_tiles == 1 && P.xf_ss == nullptr && P.n_prod == 1) ? 1 : 0;
+  if (P.cluster) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kWgThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    DV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_wgrad_kernel, P));
+  } else {
+    conv_wgrad_kernel<<<grid, kWgThreads, smem_bytes, stream>>>(P);
+  }
   DV_LAUNCH_OK();
   return kOk;
 }

@@ -41,6 +41,28 @@ def _rel(a, b):
     return ((a - b).abs().max() / (b.abs().max() + 1e-12)).item()
 
 
+def test_wgrad_cluster_of_two_unit_groups_matches_torch(monkeypatch):
+    """DV_WGRAD_CLUSTER=1: the two unit groups of the 64->144 3x3 weight gradient as a cluster of 2 CTAs in lockstep, each
+    fetching half of the dY boxes of a stage with TMA multicast (opt-in, csrc/conv_wgrad.cu wgrad_launch): same result."""
+    import kernel_handles as K
+    torch.backends.cudnn.allow_tf32 = False
+    dev = "cuda:0"
+    name, N, T, H, W, Cin, Cout, k, s, p = [c for c in CASES if "2 unit groups" in c[0]][0]
+    g = K.make_geom(N, T, H, W, Cin, Cout, k, s, p)
+    gen = torch.Generator(device=dev).manual_seed(11)
+    x = torch.randn(N, Cin, T, H, W, device=dev, generator=gen).bfloat16().float()
+    dy = torch.randn(N, Cout, T, H, W, device=dev, generator=gen).bfloat16().float()
+    w = torch.zeros(Cout, Cin, *k, device=dev, requires_grad=True)
+    F.conv3d(x, w, None, s, p).backward(dy)
+    x_nd, dy_nd = K.to_ndhwc(x), K.to_ndhwc(dy)
+    plain = K.unpack_conv_wgrad(K.conv3d_wgrad_packed(x_nd, dy_nd, g), g)
+    monkeypatch.setenv("DV_WGRAD_CLUSTER", "1")
+    clustered = K.unpack_conv_wgrad(K.conv3d_wgrad_packed(x_nd, dy_nd, g), g)
+    assert _rel(plain, w.grad) < 1e-4
+    assert _rel(clustered, w.grad) < 1e-4
+    assert _rel(clustered, plain) < 1e-5
+
+
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_conv_trio_matches_torch(case):
     import kernel_handles as K
